@@ -1,0 +1,545 @@
+#!/usr/bin/env python
+"""bench.py -- MDQE hot-path throughput on B200: MSDeformAttn fwd+bwd clips/s (+ roofline, CPU baseline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dist local|uniform]
+                    [--dtype fp32|bf16]
+
+One *step* = the hot path of ONE training clip per GPU at the R50_ovis_360 shape (BASELINE.json
+configs[1]; T=4 frames 384x640 padded, 4-level pyramid 48x80..6x10 => S=5100, 8 heads x D=32, 4 points):
+
+  36 MSDeformAttn forward + 36 backward calls through the C ABI of libmsda_b200.so
+     6 encoder layers        N=4 frames, Lq=S=5100, L=4          (transformer_enc.py:100-110)
+     6 decoder spatial       N=4 frames, Lq=196,    L=4          (transformer_dec.py:340-346)
+     6x4 decoder temporal    N=1 clip,   Lq=196,    L=T=4 frames of one pyramid level each (:361-395)
+  + the mask-logit contraction Q=196 x K=32 x (T*96*160) forward and backward  (matcher.py:182)
+
+run forward in layer order and backward in reverse (as autograd would), every call on its own input and
+output buffers (~1.5 GB per step, so no call finds its inputs in the 126 MB L2).  Inputs are synthetic
+(seed = rank), SURVEY 8(d): value ~ randn, aw = softmax(randn), loc "local" = reference point +
+0.05*randn clamped to [-0.1, 1.1] (default) or "uniform" in [0,1).
+
+Output: ONE JSON line (rank 0).  `value` is clips/s with inputs resident in HBM (CUDA-graph replay of the
+step, CUDA events, max over ranks); `e2e` is the same step through the *_host C-ABI entries with pinned
+host buffers (H2D of every input and D2H of every output inside the timed region); `roofline` is the
+dominant kernel (encoder-shape backward) timed per launch with CUDA events on its stream;
+`cpu_baseline` / `--impl reference` time oracle/torch_port.py (the reference's CPU path restated:
+F.grid_sample + autograd) on the host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PYRAMID = [(48, 80), (24, 40), (12, 20), (6, 10)]   # R50_ovis_360: 384x640 padded frame, strides 8..64
+T_FRAMES, HEADS, HEAD_DIM, POINTS, QUERIES, MASK_K = 4, 8, 32, 4, 196, 32
+MASK_PLANE = (96, 160)
+N_LAYERS = 6
+METRIC = "msda_fwd_bwd_clips_per_s"
+UNIT = "clips/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dist", default="local", choices=["local", "uniform"])
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--layers", type=int, default=N_LAYERS, help="debug: fewer layers (the result is then not a valid bench value)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- workload
+def ref_points(torch, shapes):
+    pts = []
+    for H, W in shapes:
+        ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32) + 0.5, torch.arange(W, dtype=torch.float32) + 0.5,
+                                indexing="ij")
+        pts.append(torch.stack([xs.reshape(-1) / W, ys.reshape(-1) / H], -1))
+    return torch.cat(pts)
+
+
+def make_loc(torch, g, ref, N, Lq, L, dist):
+    if dist == "uniform":
+        return torch.rand(N, Lq, HEADS, L, POINTS, 2, generator=g)
+    loc = ref.view(1, Lq, 1, 1, 1, 2) + 0.05 * torch.randn(N, Lq, HEADS, L, POINTS, 2, generator=g)
+    return loc.clamp_(-0.1, 1.1)
+
+
+def build_calls(torch, dist, seed, layers):
+    """CPU tensors of every MSDA call of one clip, in forward order, plus the mask operands."""
+    g = torch.Generator().manual_seed(seed)
+    shapes = torch.tensor(PYRAMID, dtype=torch.long)
+    sizes = shapes[:, 0] * shapes[:, 1]
+    S = int(sizes.sum())
+    lsi = torch.cat([sizes.new_zeros(1), sizes.cumsum(0)[:-1]])
+    pix = ref_points(torch, PYRAMID)
+
+    def aw_(N, Lq, L):
+        return torch.softmax(torch.randn(N, Lq, HEADS, L * POINTS, generator=g), -1).view(N, Lq, HEADS, L, POINTS)
+
+    calls = []
+    for _ in range(layers):                                   # encoder self-attention, queries = pixels
+        calls.append(dict(kind="enc", value=torch.randn(T_FRAMES, S, HEADS, HEAD_DIM, generator=g), shapes=shapes,
+                          lsi=lsi, loc=make_loc(torch, g, pix, T_FRAMES, S, 4, dist), aw=aw_(T_FRAMES, S, 4),
+                          go=torch.randn(T_FRAMES, S, HEADS * HEAD_DIM, generator=g)))
+    for _ in range(layers):                                   # decoder: frame-level then clip-level cross-attention
+        qref = torch.rand(QUERIES, 2, generator=g)
+        calls.append(dict(kind="dec_spatial", value=torch.randn(T_FRAMES, S, HEADS, HEAD_DIM, generator=g), shapes=shapes,
+                          lsi=lsi, loc=make_loc(torch, g, qref, T_FRAMES, QUERIES, 4, dist), aw=aw_(T_FRAMES, QUERIES, 4),
+                          go=torch.randn(T_FRAMES, QUERIES, HEADS * HEAD_DIM, generator=g)))
+        value_t = torch.randn(1, T_FRAMES * S, HEADS, HEAD_DIM, generator=g)
+        loc_t = make_loc(torch, g, qref, 1, QUERIES, T_FRAMES, dist)
+        aw_t = aw_(1, QUERIES, T_FRAMES)
+        for lvl in range(4):                                  # one call per pyramid level; "levels" = the T frames
+            calls.append(dict(kind="dec_temporal", value=value_t, shapes=shapes[lvl].view(1, 2).expand(T_FRAMES, 2).contiguous(),
+                              lsi=torch.arange(T_FRAMES) * S + lsi[lvl], loc=loc_t, aw=aw_t,
+                              go=torch.randn(1, QUERIES, HEADS * HEAD_DIM, generator=g)))
+    mask = dict(coeff=torch.tanh(torch.randn(1, QUERIES, MASK_K, generator=g)),
+                proto=torch.randn(1, MASK_K, T_FRAMES, *MASK_PLANE, generator=g),
+                go=torch.randn(1, QUERIES, T_FRAMES, *MASK_PLANE, generator=g))
+    return calls, mask
+
+
+def call_dims(c):
+    N, S, M, D = c["value"].shape
+    _, Lq, _, L, P, _ = c["loc"].shape
+    return N, S, M, D, L, Lq, P
+
+
+def algorithmic_bytes(c, esize, lsize):
+    """fwd = value + loc + aw + out ; bwd = value, loc, aw, grad_out read + gv, gloc, gaw written.
+    For temporal calls only the rows of the sampled windows count as `value`."""
+    N, S, M, D, L, Lq, P = call_dims(c)
+    rows = int((c["shapes"][:, 0] * c["shapes"][:, 1]).sum()) if c["kind"] == "dec_temporal" else S
+    v = N * rows * M * D * esize
+    smp = N * Lq * M * L * P
+    o = N * Lq * M * D * esize
+    return v + 3 * smp * lsize + o, 2 * v + 6 * smp * lsize + o
+
+
+# -------------------------------------------------------------------------------------------- our arm
+class DeviceStep:
+    """All buffers of one clip resident on the GPU + pre-bound C-ABI argument lists."""
+
+    def __init__(self, torch, lib, libmod, calls, mask, device, dtype):
+        self.torch, self.lib, self.device = torch, lib, device
+        vt = torch.bfloat16 if dtype == "bf16" else torch.float32
+        self.code = libmod.MSDA_BF16 if dtype == "bf16" else libmod.MSDA_F32
+        self.mcode = self.code
+        self.keep = []
+        self.fwd, self.bwd = [], []
+        cache = {}
+
+        def dev(t, cast=True):
+            key = t.data_ptr()
+            if key not in cache:
+                cache[key] = (t.to(vt) if (cast and t.is_floating_point()) else t).to(device).contiguous()
+            return cache[key]
+
+        for c in calls:
+            N, S, M, D, L, Lq, P = call_dims(c)
+            v, loc, aw, go = dev(c["value"]), dev(c["loc"]), dev(c["aw"]), dev(c["go"])
+            sh, ls = dev(c["shapes"], False), dev(c["lsi"], False)
+            out = torch.empty(N, Lq, M * D, dtype=vt, device=device)
+            gv, gl, ga = torch.empty_like(v), torch.empty_like(loc), torch.empty_like(aw)
+            ws_bytes = lib.msda_backward_workspace_bytes(self.code, N, S, M, D)
+            ws = torch.empty(max(ws_bytes // 4, 1), dtype=torch.float32, device=device)
+            self.keep += [v, loc, aw, go, sh, ls, out, gv, gl, ga, ws]
+            dims = (N, S, M, D, L, Lq, P)
+            self.fwd.append((self.code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr()) + dims
+                            + (out.data_ptr(),))
+            self.bwd.append((self.code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr(), go.data_ptr())
+                            + dims + (gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), ws.data_ptr() if ws_bytes else None, ws_bytes))
+        # mask contraction: forward in the I/O dtype, backward is fp32-only (training precision of the reference)
+        mc, mp = dev(mask["coeff"]), dev(mask["proto"])
+        B, Q, K = mc.shape
+        ncols = mp.numel() // (B * K)
+        mo = torch.empty(B, Q, ncols, dtype=vt, device=device)
+        self.mask_fwd = (self.mcode, self.mcode, mc.data_ptr(), mp.data_ptr(), B, Q, K, ncols, mo.data_ptr())
+        c32, p32, g32 = mask["coeff"].to(device), mask["proto"].to(device), mask["go"].to(device)
+        gc, gp = torch.empty_like(c32), torch.empty_like(p32)
+        self.mask_bwd = (libmod.MSDA_F32, c32.data_ptr(), p32.data_ptr(), g32.data_ptr(), B, Q, K, ncols, gc.data_ptr(), gp.data_ptr())
+        self.keep += [mc, mp, mo, c32, p32, g32, gc, gp]
+        self.outputs = dict(mask=mo)
+
+    def run(self):
+        """enqueue one step on the current stream (no host sync)."""
+        lib = self.lib
+        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        rc = 0
+        for a in self.fwd:
+            rc |= lib.msda_forward(st, *a)
+        rc |= lib.mask_logits_forward(st, *self.mask_fwd)
+        rc |= lib.mask_logits_backward(st, *self.mask_bwd)
+        for a in reversed(self.bwd):
+            rc |= lib.msda_backward(st, *a)
+        if rc:
+            from mdqe_cvpr2023_b200 import _lib
+            raise RuntimeError("C-ABI call failed: " + _lib.last_error())
+
+
+class HostStep:
+    """Same step through the *_host C-ABI entries: pinned host buffers in, pinned host buffers out."""
+
+    def __init__(self, torch, lib, libmod, calls, mask, device_index, dtype):
+        self.lib, self.dev = lib, device_index
+        vt = torch.bfloat16 if dtype == "bf16" else torch.float32
+        code = libmod.MSDA_BF16 if dtype == "bf16" else libmod.MSDA_F32
+        self.keep, self.fwd, self.bwd = [], [], []
+        self.h2d = self.d2h = 0
+        cache = {}
+
+        def pin(t, cast=True):
+            key = t.data_ptr()
+            if key not in cache:
+                cache[key] = (t.to(vt) if (cast and t.is_floating_point()) else t).contiguous().pin_memory()
+            return cache[key]
+
+        nb = lambda t: t.numel() * t.element_size()
+        # output staging shared by all calls (max size), pinned
+        big = max(calls, key=lambda c: c["loc"].numel())
+        bigv = max(calls, key=lambda c: c["value"].numel())
+        out_h = torch.empty(big["go"].numel(), dtype=vt).pin_memory()
+        gv_h = torch.empty(bigv["value"].numel(), dtype=vt).pin_memory()
+        gl_h = torch.empty(big["loc"].numel(), dtype=vt).pin_memory()
+        ga_h = torch.empty(big["aw"].numel(), dtype=vt).pin_memory()
+        self.keep += [out_h, gv_h, gl_h, ga_h]
+        for c in calls:
+            dims = call_dims(c)
+            v, loc, aw, go = pin(c["value"]), pin(c["loc"]), pin(c["aw"]), pin(c["go"])
+            sh, ls = pin(c["shapes"], False), pin(c["lsi"], False)
+            self.keep += [v, loc, aw, go, sh, ls]
+            self.fwd.append((device_index, code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr())
+                            + dims + (out_h.data_ptr(),))
+            self.bwd.append((device_index, code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr(),
+                             go.data_ptr()) + dims + (gv_h.data_ptr(), gl_h.data_ptr(), ga_h.data_ptr()))
+            small = nb(sh) + nb(ls)
+            self.h2d += 2 * (nb(v) + nb(loc) + nb(aw) + small) + nb(go)
+            self.d2h += nb(go) + nb(v) + nb(loc) + nb(aw)
+        mc, mp = pin(mask["coeff"]), pin(mask["proto"])
+        B, Q, K = mc.shape
+        ncols = mp.numel() // (B * K)
+        mo = torch.empty(B * Q * ncols, dtype=vt).pin_memory()
+        self.keep += [mc, mp, mo]
+        self.mask_fwd = (device_index, code, code, mc.data_ptr(), mp.data_ptr(), B, Q, K, ncols, mo.data_ptr())
+        self.h2d += nb(mc) + nb(mp)
+        self.d2h += nb(mo)
+
+    def run(self):
+        lib, rc = self.lib, 0
+        for a in self.fwd:
+            rc |= lib.msda_forward_host(*a)
+        rc |= lib.mask_logits_forward_host(*self.mask_fwd)
+        for a in reversed(self.bwd):
+            rc |= lib.msda_backward_host(*a)
+        if rc:
+            from mdqe_cvpr2023_b200 import _lib
+            raise RuntimeError("C-ABI host call failed: " + _lib.last_error())
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = the upper half of the samples by power draw
+        order = sorted(range(len(sm)), key=lambda i: power[i])
+        load = [sm[i] for i in order[len(order) // 2:]]
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sample(torch, calls, mask, reps, warm):
+    """Reference CPU path (torch port) on one layer's calls + the mask contraction; returns seconds
+    (layer part, mask part), averaged over `reps`."""
+    from oracle import torch_port as TP
+    layer = [next(c for c in calls if c["kind"] == "enc"), next(c for c in calls if c["kind"] == "dec_spatial")] + \
+            [c for c in calls if c["kind"] == "dec_temporal"][:4]
+    t_layer, t_mask = [], []
+    for it in range(warm + reps):
+        t0 = time.perf_counter()
+        for c in layer:
+            TP.msda_fwd_bwd_torch(c["value"], c["shapes"], c["loc"], c["aw"], c["go"], c["lsi"])
+        t1 = time.perf_counter()
+        coeff = mask["coeff"].clone().requires_grad_(True)
+        proto = mask["proto"].clone().requires_grad_(True)
+        TP.mask_logits_torch(coeff, proto).backward(mask["go"])
+        t2 = time.perf_counter()
+        if it >= warm:
+            t_layer.append(t1 - t0)
+            t_mask.append(t2 - t1)
+    return sum(t_layer) / len(t_layer), sum(t_mask) / len(t_mask)
+
+
+def config_dict(args, extra=None):
+    cfg = {"workload": "R50_ovis_360 clip hot path: 36 MSDeformAttn fwd+bwd (6 enc N=4 S=Lq=5100, 6 dec-spatial Lq=196, "
+                       "24 dec-temporal L=T=4) + mask contraction Q=196 K=32 N=61440 fwd+bwd",
+           "clips_per_gpu_per_step": 1, "frames": T_FRAMES, "pyramid": PYRAMID, "heads": HEADS, "head_dim": HEAD_DIM,
+           "points": POINTS, "queries": QUERIES, "layers": args.layers, "loc_dist": args.dist,
+           "l2_policy": "inputs larger than L2 (every call has its own buffers, ~1.5 GB touched per step)",
+           "parallelism": f"clip-sharded x{args.gpus}"}
+    cfg.update(extra or {})
+    return cfg
+
+
+# --------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    calls, mask = build_calls(torch, args.dist, 0, 1)
+    t_layer, t_mask = [], []
+    for it in range(args.warmup + args.steps):
+        a, b = cpu_sample(torch, calls, mask, 1, 0)
+        if it >= args.warmup:
+            t_layer.append(a)
+            t_mask.append(b)
+    tl, tm = sum(t_layer) / len(t_layer), sum(t_mask) / len(t_mask)
+    clip_s = N_LAYERS * tl + tm
+    value = 1.0 / clip_s
+    sample = "each step = 1 of the 6 layers (1 enc + 1 dec-spatial + 4 dec-temporal MSDA fwd+bwd) + mask fwd+bwd; clip time = 6*layer + mask"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": clip_s * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, {"device": "cpu", "threads": torch.get_num_threads()}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- main
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from mdqe_cvpr2023_b200 import _lib as libmod
+    lib = libmod.load()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    calls, mask = build_calls(torch, args.dist, rank, args.layers)
+    step = DeviceStep(torch, lib, libmod, calls, mask, device, args.dtype)
+    # gradient all-reduce of the enc+dec parameters (4.54 M + 14.94 M fp32) -- the only
+    # cross-GPU step of clip-sharded DDP training; issued after the backward, not overlapped.
+    grad_buf = torch.zeros(19_480_000, device=device) if world > 1 else None
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up (eager), then capture one step into a CUDA graph
+    for _ in range(max(args.warmup, 3)):
+        step.run()
+        if grad_buf is not None:
+            dist.all_reduce(grad_buf)
+    torch.cuda.synchronize()
+    graph = None
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step.run()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step.run()
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+
+    def one_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            step.run()
+        if grad_buf is not None:
+            dist.all_reduce(grad_buf)
+
+    # ---- timed region: exactly K steps, CUDA events, max over ranks
+    libmod.launch_count_reset()
+    sync_all()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    sync_all()
+    clocks = sampler.stop() if sampler else None
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    launches_per_step = len(step.fwd) + len(step.bwd) + 2 + (len(step.bwd) if args.dtype == "bf16" else 0)
+    gpu_launches = launches_per_step * args.steps      # graph replays re-launch the captured kernels
+    value = world * 1.0 / (ms_step / 1e3)
+
+    # ---- per-launch kernel timing (eager pass over the same buffers, events right around the kernels)
+    esize = 2 if args.dtype == "bf16" else 4
+    enc = next(c for c in calls if c["kind"] == "enc")
+    enc_pairs = T_FRAMES * sum(h * w for h, w in PYRAMID) * HEADS
+    libmod.set_option("profile", 1)
+    for _ in range(min(args.steps, 10)):
+        step.run()
+    torch.cuda.synchronize()
+    bwd_ms, bwd_n = libmod.profile_read(libmod.PROF_MSDA_BWD, enc_pairs)
+    fwd_ms, fwd_n = libmod.profile_read(libmod.PROF_MSDA_FWD, enc_pairs)
+    mfw_ms, mfw_n = libmod.profile_read(libmod.PROF_MASK_FWD, 0)
+    mbw_ms, mbw_n = libmod.profile_read(libmod.PROF_MASK_BWD, 0)
+    libmod.set_option("profile", 0)
+    fwd_bytes, bwd_bytes = algorithmic_bytes(enc, esize, esize)
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peaks = json.load(open(peaks_path))
+        hbm_peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json"
+    else:
+        hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    def roof(nbytes, ms, n, name):
+        if not n:
+            return None
+        us = ms / n * 1e3
+        ach = nbytes / (us * 1e-6) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": None, "avg_launch_us": us, "launches_timed": n, "algorithmic_bytes": nbytes, "peak_source": peak_src}
+
+    roofline = roof(bwd_bytes, bwd_ms, bwd_n, "msda_bwd_fast_kernel<float,float,32> (encoder shape N=4,S=Lq=5100)")
+    roofline_fwd = roof(fwd_bytes, fwd_ms, fwd_n, "msda_fwd_fast_kernel<float,float,32> (encoder shape)")
+    mB = QUERIES * MASK_K + MASK_K * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
+    mO = QUERIES * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
+    roofline_mask = roof(mB * esize + mO * esize, mfw_ms, mfw_n, "mask_logits forward")
+    if roofline_mask:
+        flops = 2.0 * QUERIES * MASK_K * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
+        roofline_mask["tflops"] = flops / (roofline_mask["avg_launch_us"] * 1e-6) / 1e12
+    roofline_mask_bwd = roof((mB + mO + mB) * 4, mbw_ms, mbw_n, "mask_logits backward (fp32)")
+
+    # ---- eager (no graph) step time, for reference
+    sync_all()
+    libmod.launch_count_reset()
+    e0.record()
+    for _ in range(min(args.steps, 10)):
+        step.run()
+    e1.record()
+    torch.cuda.synchronize()
+    eager_ms = e0.elapsed_time(e1) / min(args.steps, 10)
+    counted_per_step = libmod.launch_count() / min(args.steps, 10)
+
+    # ---- end to end through the host-buffer C ABI (H2D + kernels + D2H every call), wall clock
+    e2e = None
+    if not args.no_e2e:
+        host = HostStep(torch, lib, libmod, calls, mask, local_rank, args.dtype)
+        host.run()                                   # warm-up: arena allocation, page faults
+        n_e2e = max(1, min(args.steps, 5))
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            host.run()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": host.h2d, "d2h_bytes_per_step": host.d2h,
+               "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3, "timing": "wall clock around synchronous *_host C-ABI calls",
+               "note": "mask backward is not part of the host-buffer step"}
+        lib.msda_host_arena_release()
+
+    # ---- CPU baseline (rank 0, single-GPU runs only): the reference's CPU path restated in torch
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        tl, tm = cpu_sample(torch, calls, mask, reps=3, warm=1)
+        cpu = {"value": 1.0 / (N_LAYERS * tl + tm), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "1 of 6 layers (1 enc + 1 dec-spatial + 4 dec-temporal MSDA fwd+bwd) + mask fwd+bwd via oracle/torch_port.py, "
+                         "mean of 3 after 1 warm-up; clip time = 6*layer + mask",
+               "layer_ms": tl * 1e3, "mask_ms": tm * 1e3}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
+                "config": config_dict(args, {"launch": "cuda_graph" if graph is not None else "eager",
+                                             "allreduce": "19.48M fp32 grads per step, NCCL, after backward" if world > 1 else None}),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "launches_per_step": launches_per_step,
+                "lib_launch_count_per_eager_step": counted_per_step,
+                "roofline": roofline, "roofline_fwd": roofline_fwd, "roofline_mask": roofline_mask,
+                "roofline_mask_bwd": roofline_mask_bwd, "eager_ms_per_step": eager_ms, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,145 @@
+/*
+ * msda_b200.h -- C ABI of the B200-native (sm_100a) MDQE hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / ATen types.  It is what a
+ * binding for the reference's extension seam binds.  Reference interfaces replaced
+ * (paths relative to /root/reference/mdqe/models/ops unless noted):
+ *
+ *   msda_forward        <- ms_deform_attn_forward  (src/vision.cpp:14, src/ms_deform_attn.h:20-39,
+ *                          src/cuda/ms_deform_attn_cuda.cu:20-80) and the launcher
+ *                          ms_deformable_im2col_cuda (src/cuda/ms_deform_im2col_cuda.cuh:923-954)
+ *   msda_backward       <- ms_deform_attn_backward (src/vision.cpp:15, src/ms_deform_attn.h:41-61,
+ *                          src/cuda/ms_deform_attn_cuda.cu:83-153) and ms_deformable_col2im_cuda
+ *                          (src/cuda/ms_deform_im2col_cuda.cuh:956-1326)
+ *   mask_logits_*       <- torch.einsum('bqm,bmthw->bqthw') at mdqe/models/transformer_dec.py:255,
+ *                          mdqe/mdqe.py:384, mdqe/models/matcher.py:182, mdqe/models/criterion.py:440
+ *   *_host variants     <- the same calls with HOST buffers (the library stages them through
+ *                          device memory); this is the end-to-end entry bench.py times as `e2e`.
+ *
+ * Conventions
+ *   - Every function returns 0 on success or a negative msda_status; msda_last_error() returns a
+ *     thread-local, human readable description of the last failure (the reference only printf'd
+ *     launch errors: ms_deform_im2col_cuda.cuh:948-952).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls only
+ *     enqueue work: no host synchronisation, no allocation, safe under CUDA-graph capture.
+ *     The *_host variants synchronise the stream before returning.
+ *   - All device tensors are contiguous, row-major, in the reference's layouts:
+ *       value [N,S,M,D]   shapes [L,2] (H,W) int64 ON DEVICE   level_start [L] int64 ON DEVICE
+ *       loc [N,Lq,M,L,P,2] (x,y) normalised to [0,1]   aw [N,Lq,M,L,P]   out / grad_out [N,Lq,M*D]
+ *   - The caller owns every buffer.  There is no CPU fallback: without a CUDA device every compute
+ *     entry fails with MSDA_ERR_CUDA.
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_B200_ABI_VERSION 1
+
+typedef enum {
+  MSDA_OK = 0,
+  MSDA_ERR_INVALID_ARG = -1,   /* NULL pointer, non-positive size, unsupported dtype ...        */
+  MSDA_ERR_UNSUPPORTED = -2,   /* shape outside what the kernels implement (e.g. L > 32)        */
+  MSDA_ERR_CUDA = -3,          /* a CUDA runtime call or kernel launch failed                    */
+  MSDA_ERR_WORKSPACE = -4      /* workspace missing or too small                                */
+} msda_status;
+
+/* Storage type of the tensors.  Arithmetic is fp32 (fp64 for MSDA_F64) in every mode.
+ *   MSDA_F32        : everything fp32 (the reference's only mode besides fp64:
+ *                     AT_DISPATCH_FLOATING_TYPES, ms_deform_attn_cuda.cu:64)
+ *   MSDA_BF16       : value/out/grad_out/grad_value AND loc/aw/grad_loc/grad_aw are bf16
+ *   MSDA_F64        : everything fp64 (gradcheck path of ops/test.py:63-78)
+ *   MSDA_BF16_LOC32 : value/out/grad_out/grad_value bf16; loc/aw/grad_loc/grad_aw fp32
+ */
+typedef enum { MSDA_F32 = 0, MSDA_BF16 = 1, MSDA_F64 = 2, MSDA_BF16_LOC32 = 3 } msda_dtype;
+
+int msda_abi_version(void);
+const char* msda_last_error(void);
+
+/* Tuning knobs (kernel variant selection used by bench.py / tests); unknown keys fail.
+ * Keys: "fwd_variant", "bwd_variant", "chunk_pairs", "mask_variant", "profile". */
+int msda_set_option(const char* key, int value);
+int msda_get_option(const char* key, int* value);
+
+/* out[n,q,m*D+c] = sum_{l,p} aw[n,q,m,l,p] * bilinear(value_l[n,:,m,c], loc[n,q,m,l,p]*(W_l,H_l)-0.5)
+ * with zero padding; `out` is fully overwritten (no pre-zeroing needed). */
+int msda_forward(void* stream, int dtype,
+                 const void* value, const int64_t* shapes, const int64_t* level_start,
+                 const void* loc, const void* aw,
+                 int N, int S, int M, int D, int L, int Lq, int P,
+                 void* out);
+
+/* Bytes of scratch msda_backward needs for this problem (0 for MSDA_F32 / MSDA_F64; the bf16
+ * modes accumulate grad_value in an fp32 image of it). */
+size_t msda_backward_workspace_bytes(int dtype, int N, int S, int M, int D);
+
+/* grad_value, grad_loc, grad_aw are fully written (grad_value is zero-filled inside the call).
+ * `workspace` may be NULL when msda_backward_workspace_bytes() is 0. */
+int msda_backward(void* stream, int dtype,
+                  const void* value, const int64_t* shapes, const int64_t* level_start,
+                  const void* loc, const void* aw, const void* grad_out,
+                  int N, int S, int M, int D, int L, int Lq, int P,
+                  void* grad_value, void* grad_loc, void* grad_aw,
+                  void* workspace, size_t workspace_bytes);
+
+/* Mask contraction: out[b,q,n] = sum_k coeff[b,q,k] * proto[b,k,n], n over the flattened (t,h,w)
+ * plane (Ncols = T*H*W).  coeff [B,Q,K], proto [B,K,Ncols], out [B,Q,Ncols].
+ *   in_dtype  MSDA_F32 (inputs rounded to bf16 hi+lo pairs on chip: 3 tensor-core passes, fp32
+ *             accumulate, parity with the fp32 einsum to ~1e-5) or MSDA_BF16 (one pass)
+ *   out_dtype MSDA_F32 or MSDA_BF16
+ * Runs on the 5th-gen tensor cores (tcgen05, accumulators in TMEM). */
+int mask_logits_forward(void* stream, int in_dtype, int out_dtype,
+                        const void* coeff, const void* proto,
+                        int B, int Q, int K, int64_t Ncols, void* out);
+
+/* grad_coeff[b,q,k] = sum_n grad_out[b,q,n] proto[b,k,n];  grad_proto[b,k,n] = sum_q coeff[b,q,k] grad_out[b,q,n].
+ * Either output may be NULL to skip it.  All tensors use `dtype` (MSDA_F32 or MSDA_BF16). */
+int mask_logits_backward(void* stream, int dtype,
+                         const void* coeff, const void* proto, const void* grad_out,
+                         int B, int Q, int K, int64_t Ncols,
+                         void* grad_coeff, void* grad_proto);
+
+/* Host-buffer entries: same semantics, every pointer is HOST memory (pinned memory makes the
+ * copies asynchronous).  The library owns a grow-only device arena per process; `device` selects
+ * the GPU.  These return after the results have landed in the host output buffers. */
+int msda_forward_host(int device, int dtype,
+                      const void* value, const int64_t* shapes, const int64_t* level_start,
+                      const void* loc, const void* aw,
+                      int N, int S, int M, int D, int L, int Lq, int P,
+                      void* out);
+int msda_backward_host(int device, int dtype,
+                       const void* value, const int64_t* shapes, const int64_t* level_start,
+                       const void* loc, const void* aw, const void* grad_out,
+                       int N, int S, int M, int D, int L, int Lq, int P,
+                       void* grad_value, void* grad_loc, void* grad_aw);
+int mask_logits_forward_host(int device, int in_dtype, int out_dtype,
+                             const void* coeff, const void* proto,
+                             int B, int Q, int K, int64_t Ncols, void* out);
+/* Release the device arena used by the *_host entries. */
+int msda_host_arena_release(void);
+
+/* Per-launch kernel timing (CUDA events on the launching stream, recorded right around the kernel).
+ * Enable with msda_set_option("profile", 1); every launch of the given kind since the last read whose
+ * work size (pairs N*Lq*M for MSDA, B*Q*Ncols for the mask kernels) is >= min_units is summed into
+ * *total_ms and counted in *count; the records of that kind are then dropped.  Synchronises on the
+ * recorded events.  Launches made under CUDA-graph capture are not recorded. */
+#define MSDA_PROF_MSDA_FWD 0
+#define MSDA_PROF_MSDA_BWD 1
+#define MSDA_PROF_MASK_FWD 2
+#define MSDA_PROF_MASK_BWD 3
+int msda_profile_read(int kind, int64_t min_units, double* total_ms, int64_t* count);
+
+/* Number of kernels this library has launched since load / since the last reset (bench.py's
+ * gpu_launches claim is read from here). */
+int64_t msda_launch_count(void);
+void msda_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

@@ -1,0 +1,453 @@
+// C ABI of libmsda_b200.so: argument validation, kernel selection and launch for the multi-scale
+// deformable attention operator, plus the host-buffer entry points.  See include/msda_b200.h for the
+// contract and the reference interfaces each entry replaces.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <type_traits>
+#include <vector>
+
+#include "msda_fast.cuh"
+#include "msda_generic.cuh"
+#include "msda_internal.h"
+
+namespace msda {
+
+// ------------------------------------------------------------------------------------ bookkeeping
+static thread_local char t_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_cuda(cudaError_t err, const char* what) {
+  if (err == cudaSuccess) return 0;
+  return fail(MSDA_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(err), cudaGetErrorName(err));
+}
+
+int after_launch(const char* kernel_name) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_cuda(cudaGetLastError(), kernel_name);
+}
+
+struct Options {
+  std::atomic<int> fwd_variant{0};    // 0 = auto (fast when eligible), 1 = force generic
+  std::atomic<int> bwd_variant{0};    // 0 = auto, 1 = force generic
+  std::atomic<int> chunk_pairs{0};    // 0 = auto
+  std::atomic<int> mask_variant{0};   // 0 = auto (tcgen05 when eligible), 1 = SIMT fp32, 2 = force tcgen05
+  std::atomic<int> profile{0};        // 1 = bracket the main kernels with CUDA events (msda_profile_read)
+};
+static Options g_opt;
+
+static std::atomic<int>* find_option(const char* key) {
+  if (!key) return nullptr;
+  if (!strcmp(key, "fwd_variant")) return &g_opt.fwd_variant;
+  if (!strcmp(key, "bwd_variant")) return &g_opt.bwd_variant;
+  if (!strcmp(key, "chunk_pairs")) return &g_opt.chunk_pairs;
+  if (!strcmp(key, "mask_variant")) return &g_opt.mask_variant;
+  if (!strcmp(key, "profile")) return &g_opt.profile;
+  return nullptr;
+}
+
+int option(const char* key) {
+  std::atomic<int>* o = find_option(key);
+  return o ? o->load() : 0;
+}
+
+// ---------------------------------------------------------------------------------------- profiling
+// Optional per-launch timing with CUDA events recorded on the launching stream, right around the
+// kernel (not around memsets or conversions).  Used by bench.py for the roofline figure.
+struct ProfRec { cudaEvent_t a, b; int kind; int64_t units; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+
+ProfScope::ProfScope(cudaStream_t st, int kind, int64_t units) : st_(st), kind_(kind), units_(units) {
+  if (!g_opt.profile.load()) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+  if (cudaEventCreate(&a_) != cudaSuccess || cudaEventCreate(&b_) != cudaSuccess) { a_ = b_ = nullptr; return; }
+  cudaEventRecord(a_, st_);
+  on_ = true;
+}
+ProfScope::~ProfScope() {
+  if (!on_) return;
+  cudaEventRecord(b_, st_);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (g_prof.size() < (1u << 16)) g_prof.push_back(ProfRec{a_, b_, kind_, units_});
+  else { cudaEventDestroy(a_); cudaEventDestroy(b_); }
+}
+
+// -------------------------------------------------------------------------------------- validation
+struct Problem {
+  int N, S, M, D, L, Lq, P;
+  int64_t n_pairs;
+};
+
+static int validate(const char* who, int dtype, const void* value, const int64_t* shapes, const int64_t* lsi,
+                    const void* loc, const void* aw, int N, int S, int M, int D, int L, int Lq, int P) {
+  if (dtype_size(dtype) == 0) return fail(MSDA_ERR_INVALID_ARG, "%s: unknown dtype %d", who, dtype);
+  if (N < 0 || S < 0 || M <= 0 || D <= 0 || L <= 0 || Lq < 0 || P <= 0)
+    return fail(MSDA_ERR_INVALID_ARG, "%s: bad sizes N=%d S=%d M=%d D=%d L=%d Lq=%d P=%d", who, N, S, M, D, L, Lq, P);
+  if (!shapes || !lsi) return fail(MSDA_ERR_INVALID_ARG, "%s: spatial_shapes / level_start_index is NULL", who);
+  if ((int64_t)N * S * M * D > 0 && !value) return fail(MSDA_ERR_INVALID_ARG, "%s: value is NULL", who);
+  if ((int64_t)N * Lq > 0 && (!loc || !aw)) return fail(MSDA_ERR_INVALID_ARG, "%s: sampling_loc / attn_weight is NULL", who);
+  return 0;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static bool fast_eligible(int dtype, const Problem& pb, const void* a, const void* b, const void* c) {
+  if (dtype == MSDA_F64) return false;
+  if (pb.D != 32 && pb.D != 24) return false;
+  if (pb.L > kMaxLevels || pb.L * pb.P > 32) return false;
+  if ((int64_t)pb.N * pb.S * pb.M * pb.D >= (int64_t(1) << 31)) return false;   // 32-bit row offsets
+  return aligned16(a) && aligned16(b) && aligned16(c);
+}
+
+static int pick_chunk(const Problem& pb) {
+  const int qpw = 32 / (pb.L * pb.P);
+  const int unit = kWarpsPerCta * qpw;                   // pairs one CTA round covers
+  int chunk = g_opt.chunk_pairs.load();
+  if (chunk <= 0) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = pb.n_pairs / (int64_t(sms) * 8);  // aim at >= 8 CTAs per SM
+    chunk = static_cast<int>(want < 64 ? want : 64);
+  }
+  chunk = ((chunk + unit - 1) / unit) * unit;
+  return chunk < unit ? unit : chunk;
+}
+
+template <typename VT, typename LT>
+static int launch_fwd(cudaStream_t st, const Problem& pb, bool fast, const void* value, const int64_t* shapes,
+                      const int64_t* lsi, const void* loc, const void* aw, void* out) {
+  const VT* v = static_cast<const VT*>(value);
+  const LT* lc = static_cast<const LT*>(loc);
+  const LT* a = static_cast<const LT*>(aw);
+  VT* o = static_cast<VT*>(out);
+  ProfScope prof(st, MSDA_PROF_MSDA_FWD, pb.n_pairs);
+  if constexpr (!std::is_same<VT, double>::value) {
+    if (fast) {
+      const int chunk = pick_chunk(pb);
+      const unsigned grid = static_cast<unsigned>((pb.n_pairs + chunk - 1) / chunk);
+      if (pb.D == 32)
+        msda_fwd_fast_kernel<VT, LT, 32><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.Lq, pb.P, pb.n_pairs, chunk);
+      else
+        msda_fwd_fast_kernel<VT, LT, 24><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.Lq, pb.P, pb.n_pairs, chunk);
+      return after_launch("msda_fwd_fast_kernel");
+    }
+  }
+  const int64_t blocks = (pb.n_pairs + kWarpsPerCta - 1) / kWarpsPerCta;
+  const unsigned grid = static_cast<unsigned>(blocks < 148 * 64 ? blocks : 148 * 64);
+  msda_fwd_generic_kernel<VT, LT><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.D, pb.L, pb.Lq, pb.P, pb.n_pairs);
+  return after_launch("msda_fwd_generic_kernel");
+}
+
+template <typename VT, typename LT, typename GT>
+static int launch_bwd(cudaStream_t st, const Problem& pb, bool fast, const void* value, const int64_t* shapes,
+                      const int64_t* lsi, const void* loc, const void* aw, const void* grad_out, GT* gv_acc,
+                      void* grad_loc, void* grad_aw) {
+  const VT* v = static_cast<const VT*>(value);
+  const LT* lc = static_cast<const LT*>(loc);
+  const LT* a = static_cast<const LT*>(aw);
+  const VT* go = static_cast<const VT*>(grad_out);
+  LT* gl = static_cast<LT*>(grad_loc);
+  LT* ga = static_cast<LT*>(grad_aw);
+  ProfScope prof(st, MSDA_PROF_MSDA_BWD, pb.n_pairs);
+  if constexpr (std::is_same<GT, float>::value) {
+    if (fast) {
+      const int chunk = pick_chunk(pb);
+      const unsigned grid = static_cast<unsigned>((pb.n_pairs + chunk - 1) / chunk);
+      if (pb.D == 32)
+        msda_bwd_fast_kernel<VT, LT, 32><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, go, gv_acc, gl, ga, pb.S, pb.M, pb.L, pb.Lq, pb.P, pb.n_pairs, chunk);
+      else
+        msda_bwd_fast_kernel<VT, LT, 24><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, go, gv_acc, gl, ga, pb.S, pb.M, pb.L, pb.Lq, pb.P, pb.n_pairs, chunk);
+      return after_launch("msda_bwd_fast_kernel");
+    }
+  }
+  const int64_t blocks = (pb.n_pairs + kWarpsPerCta - 1) / kWarpsPerCta;
+  const unsigned grid = static_cast<unsigned>(blocks < 148 * 64 ? blocks : 148 * 64);
+  msda_bwd_generic_kernel<VT, LT, GT><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, go, gv_acc, gl, ga, pb.S, pb.M, pb.D, pb.L, pb.Lq, pb.P, pb.n_pairs);
+  return after_launch("msda_bwd_generic_kernel");
+}
+
+}  // namespace msda
+
+using namespace msda;
+
+// ===================================================================================== public ABI
+extern "C" {
+
+int msda_abi_version(void) { return MSDA_B200_ABI_VERSION; }
+const char* msda_last_error(void) { return t_err; }
+
+int msda_set_option(const char* key, int value) {
+  std::atomic<int>* o = find_option(key);
+  if (!o) return fail(MSDA_ERR_INVALID_ARG, "msda_set_option: unknown key '%s'", key ? key : "(null)");
+  o->store(value);
+  return 0;
+}
+
+int msda_get_option(const char* key, int* value) {
+  std::atomic<int>* o = find_option(key);
+  if (!o || !value) return fail(MSDA_ERR_INVALID_ARG, "msda_get_option: unknown key '%s'", key ? key : "(null)");
+  *value = o->load();
+  return 0;
+}
+
+int msda_profile_read(int kind, int64_t min_units, double* total_ms, int64_t* count) {
+  if (!total_ms || !count) return fail(MSDA_ERR_INVALID_ARG, "msda_profile_read: NULL output");
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  double tot = 0.0;
+  int64_t n = 0;
+  std::vector<ProfRec> keep;
+  for (const ProfRec& r : g_prof) {
+    if (r.kind != kind) { keep.push_back(r); continue; }
+    if (int rc = check_cuda(cudaEventSynchronize(r.b), "cudaEventSynchronize(profile)")) return rc;
+    float ms = 0.f;
+    if (r.units >= min_units && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { tot += ms; ++n; }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.swap(keep);
+  *total_ms = tot;
+  *count = n;
+  return 0;
+}
+
+int64_t msda_launch_count(void) { return g_launches.load(); }
+void msda_launch_count_reset(void) { g_launches.store(0); }
+
+int msda_forward(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                 const void* loc, const void* aw, int N, int S, int M, int D, int L, int Lq, int P, void* out) {
+  if (int rc = validate("msda_forward", dtype, value, shapes, level_start, loc, aw, N, S, M, D, L, Lq, P)) return rc;
+  Problem pb{N, S, M, D, L, Lq, P, (int64_t)N * Lq * M};
+  if (pb.n_pairs == 0) return 0;
+  if (!out) return fail(MSDA_ERR_INVALID_ARG, "msda_forward: out is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool fast = g_opt.fwd_variant.load() != 1 && fast_eligible(dtype, pb, value, out, loc);
+  switch (dtype) {
+    case MSDA_F32: return launch_fwd<float, float>(st, pb, fast, value, shapes, level_start, loc, aw, out);
+    case MSDA_BF16: return launch_fwd<__nv_bfloat16, __nv_bfloat16>(st, pb, fast, value, shapes, level_start, loc, aw, out);
+    case MSDA_BF16_LOC32: return launch_fwd<__nv_bfloat16, float>(st, pb, fast, value, shapes, level_start, loc, aw, out);
+    case MSDA_F64: return launch_fwd<double, double>(st, pb, false, value, shapes, level_start, loc, aw, out);
+  }
+  return fail(MSDA_ERR_INVALID_ARG, "msda_forward: unknown dtype %d", dtype);
+}
+
+size_t msda_backward_workspace_bytes(int dtype, int N, int S, int M, int D) {
+  if (dtype == MSDA_BF16 || dtype == MSDA_BF16_LOC32) return (size_t)N * S * M * D * sizeof(float);
+  return 0;
+}
+
+int msda_backward(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                  const void* loc, const void* aw, const void* grad_out, int N, int S, int M, int D, int L, int Lq,
+                  int P, void* grad_value, void* grad_loc, void* grad_aw, void* workspace, size_t workspace_bytes) {
+  if (int rc = validate("msda_backward", dtype, value, shapes, level_start, loc, aw, N, S, M, D, L, Lq, P)) return rc;
+  Problem pb{N, S, M, D, L, Lq, P, (int64_t)N * Lq * M};
+  const size_t n_value = (size_t)N * S * M * D;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_value > 0 && !grad_value) return fail(MSDA_ERR_INVALID_ARG, "msda_backward: grad_value is NULL");
+  const bool is_bf16 = dtype == MSDA_BF16 || dtype == MSDA_BF16_LOC32;
+  const size_t need = msda_backward_workspace_bytes(dtype, N, S, M, D);
+  if (need > 0 && (!workspace || workspace_bytes < need))
+    return fail(MSDA_ERR_WORKSPACE, "msda_backward: bf16 needs a %zu-byte fp32 workspace (got %zu)", need, workspace_bytes);
+  void* acc = is_bf16 ? workspace : grad_value;
+  const size_t acc_bytes = is_bf16 ? need : n_value * dtype_size(dtype);
+  if (acc_bytes > 0)
+    if (int rc = check_cuda(cudaMemsetAsync(acc, 0, acc_bytes, st), "cudaMemsetAsync(grad_value)")) return rc;
+  if (pb.n_pairs == 0) {
+    if (is_bf16 && n_value > 0)
+      return check_cuda(cudaMemsetAsync(grad_value, 0, n_value * 2, st), "cudaMemsetAsync(grad_value)");
+    return 0;
+  }
+  if (!grad_out || !grad_loc || !grad_aw) return fail(MSDA_ERR_INVALID_ARG, "msda_backward: grad_out / grad_loc / grad_aw is NULL");
+  const bool fast = g_opt.bwd_variant.load() != 1 && fast_eligible(dtype, pb, value, grad_out, acc) &&
+                    aligned16(loc) && aligned16(grad_loc);
+  int rc = 0;
+  switch (dtype) {
+    case MSDA_F32:
+      rc = launch_bwd<float, float, float>(st, pb, fast, value, shapes, level_start, loc, aw, grad_out,
+                                           static_cast<float*>(acc), grad_loc, grad_aw);
+      break;
+    case MSDA_BF16:
+      rc = launch_bwd<__nv_bfloat16, __nv_bfloat16, float>(st, pb, fast, value, shapes, level_start, loc, aw, grad_out,
+                                                           static_cast<float*>(acc), grad_loc, grad_aw);
+      break;
+    case MSDA_BF16_LOC32:
+      rc = launch_bwd<__nv_bfloat16, float, float>(st, pb, fast, value, shapes, level_start, loc, aw, grad_out,
+                                                   static_cast<float*>(acc), grad_loc, grad_aw);
+      break;
+    case MSDA_F64:
+      rc = launch_bwd<double, double, double>(st, pb, false, value, shapes, level_start, loc, aw, grad_out,
+                                              static_cast<double*>(acc), grad_loc, grad_aw);
+      break;
+    default:
+      return fail(MSDA_ERR_INVALID_ARG, "msda_backward: unknown dtype %d", dtype);
+  }
+  if (rc) return rc;
+  if (is_bf16) {
+    if (n_value % 4 != 0 || !aligned16(workspace) || (reinterpret_cast<uintptr_t>(grad_value) & 7u))
+      return fail(MSDA_ERR_UNSUPPORTED, "msda_backward: bf16 grad_value conversion needs N*S*M*D %% 4 == 0 and aligned buffers");
+    const int64_t n4 = (int64_t)(n_value / 4);
+    const unsigned grid = static_cast<unsigned>((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    cvt_f32_to_bf16_kernel<<<grid, 256, 0, st>>>(static_cast<const float4*>(workspace), static_cast<uint2*>(grad_value), n4);
+    return after_launch("cvt_f32_to_bf16_kernel");
+  }
+  return 0;
+}
+
+int mask_logits_forward(void* stream, int in_dtype, int out_dtype, const void* coeff, const void* proto, int B, int Q,
+                        int K, int64_t Ncols, void* out) {
+  if (B < 0 || Q < 0 || K <= 0 || Ncols < 0) return fail(MSDA_ERR_INVALID_ARG, "mask_logits_forward: bad sizes B=%d Q=%d K=%d Ncols=%lld", B, Q, K, (long long)Ncols);
+  if ((in_dtype != MSDA_F32 && in_dtype != MSDA_BF16) || (out_dtype != MSDA_F32 && out_dtype != MSDA_BF16))
+    return fail(MSDA_ERR_INVALID_ARG, "mask_logits_forward: dtypes must be MSDA_F32 or MSDA_BF16");
+  if ((int64_t)B * Q * Ncols == 0) return 0;
+  if (!coeff || !proto || !out) return fail(MSDA_ERR_INVALID_ARG, "mask_logits_forward: NULL tensor");
+  return mask_forward_dispatch(static_cast<cudaStream_t>(stream), in_dtype, out_dtype, coeff, proto, B, Q, K, Ncols, out);
+}
+
+int mask_logits_backward(void* stream, int dtype, const void* coeff, const void* proto, const void* grad_out, int B,
+                         int Q, int K, int64_t Ncols, void* grad_coeff, void* grad_proto) {
+  if (B < 0 || Q < 0 || K <= 0 || Ncols < 0) return fail(MSDA_ERR_INVALID_ARG, "mask_logits_backward: bad sizes");
+  if (dtype != MSDA_F32 && dtype != MSDA_BF16) return fail(MSDA_ERR_INVALID_ARG, "mask_logits_backward: dtype must be MSDA_F32 or MSDA_BF16");
+  if (!coeff || !proto || !grad_out) return fail(MSDA_ERR_INVALID_ARG, "mask_logits_backward: NULL tensor");
+  return mask_backward_dispatch(static_cast<cudaStream_t>(stream), dtype, coeff, proto, grad_out, B, Q, K, Ncols, grad_coeff, grad_proto);
+}
+
+// ------------------------------------------------------------------------------- host-buffer entries
+namespace {
+struct Arena {
+  std::mutex mu;
+  int device = -1;
+  char* base = nullptr;
+  size_t cap = 0;
+  cudaStream_t stream = nullptr;
+};
+Arena g_arena;
+
+// Carves 256-byte aligned sub-buffers out of the (grow-only) arena.
+struct Carver {
+  size_t off = 0;
+  size_t take(size_t bytes) { const size_t at = off; off += (bytes + 255) & ~size_t(255); return at; }
+};
+
+int arena_prepare(int device, size_t bytes) {
+  if (int rc = check_cuda(cudaSetDevice(device), "cudaSetDevice")) return rc;
+  if (g_arena.device != device && g_arena.base) {
+    cudaFree(g_arena.base); g_arena.base = nullptr; g_arena.cap = 0;
+    if (g_arena.stream) { cudaStreamDestroy(g_arena.stream); g_arena.stream = nullptr; }
+  }
+  g_arena.device = device;
+  if (!g_arena.stream)
+    if (int rc = check_cuda(cudaStreamCreateWithFlags(&g_arena.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return rc;
+  if (bytes > g_arena.cap) {
+    if (g_arena.base) { cudaStreamSynchronize(g_arena.stream); cudaFree(g_arena.base); g_arena.base = nullptr; g_arena.cap = 0; }
+    const size_t want = bytes + bytes / 4;
+    if (int rc = check_cuda(cudaMalloc(&g_arena.base, want), "cudaMalloc(host arena)")) return rc;
+    g_arena.cap = want;
+  }
+  return 0;
+}
+}  // namespace
+
+int msda_forward_host(int device, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                      const void* loc, const void* aw, int N, int S, int M, int D, int L, int Lq, int P, void* out) {
+  if (int rc = validate("msda_forward_host", dtype, value, shapes, level_start, loc, aw, N, S, M, D, L, Lq, P)) return rc;
+  const size_t es = dtype_size(dtype), ls = loc_dtype_size(dtype);
+  const size_t b_val = (size_t)N * S * M * D * es, b_loc = (size_t)N * Lq * M * L * P * 2 * ls, b_aw = b_loc / 2;
+  const size_t b_out = (size_t)N * Lq * M * D * es, b_shp = (size_t)L * 2 * 8, b_lsi = (size_t)L * 8;
+  if (b_out == 0) return 0;
+  if (!out) return fail(MSDA_ERR_INVALID_ARG, "msda_forward_host: out is NULL");
+  std::lock_guard<std::mutex> lock(g_arena.mu);
+  Carver cv;
+  const size_t o_val = cv.take(b_val), o_loc = cv.take(b_loc), o_aw = cv.take(b_aw), o_out = cv.take(b_out);
+  const size_t o_shp = cv.take(b_shp), o_lsi = cv.take(b_lsi);
+  if (int rc = arena_prepare(device, cv.off)) return rc;
+  char* d = g_arena.base;
+  cudaStream_t st = g_arena.stream;
+  if (int rc = check_cuda(cudaMemcpyAsync(d + o_val, value, b_val, cudaMemcpyHostToDevice, st), "H2D value")) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(d + o_loc, loc, b_loc, cudaMemcpyHostToDevice, st), "H2D loc")) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(d + o_aw, aw, b_aw, cudaMemcpyHostToDevice, st), "H2D aw")) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(d + o_shp, shapes, b_shp, cudaMemcpyHostToDevice, st), "H2D shapes")) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(d + o_lsi, level_start, b_lsi, cudaMemcpyHostToDevice, st), "H2D level_start")) return rc;
+  if (int rc = msda_forward(st, dtype, d + o_val, reinterpret_cast<int64_t*>(d + o_shp), reinterpret_cast<int64_t*>(d + o_lsi),
+                            d + o_loc, d + o_aw, N, S, M, D, L, Lq, P, d + o_out)) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(out, d + o_out, b_out, cudaMemcpyDeviceToHost, st), "D2H out")) return rc;
+  return check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+}
+
+int msda_backward_host(int device, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                       const void* loc, const void* aw, const void* grad_out, int N, int S, int M, int D, int L, int Lq,
+                       int P, void* grad_value, void* grad_loc, void* grad_aw) {
+  if (int rc = validate("msda_backward_host", dtype, value, shapes, level_start, loc, aw, N, S, M, D, L, Lq, P)) return rc;
+  const size_t es = dtype_size(dtype), ls = loc_dtype_size(dtype);
+  const size_t b_val = (size_t)N * S * M * D * es, b_loc = (size_t)N * Lq * M * L * P * 2 * ls, b_aw = b_loc / 2;
+  const size_t b_go = (size_t)N * Lq * M * D * es, b_shp = (size_t)L * 2 * 8, b_lsi = (size_t)L * 8;
+  const size_t b_ws = msda_backward_workspace_bytes(dtype, N, S, M, D);
+  std::lock_guard<std::mutex> lock(g_arena.mu);
+  Carver cv;
+  const size_t o_val = cv.take(b_val), o_loc = cv.take(b_loc), o_aw = cv.take(b_aw), o_go = cv.take(b_go);
+  const size_t o_shp = cv.take(b_shp), o_lsi = cv.take(b_lsi);
+  const size_t o_gv = cv.take(b_val), o_gl = cv.take(b_loc), o_ga = cv.take(b_aw), o_ws = cv.take(b_ws);
+  if (int rc = arena_prepare(device, cv.off)) return rc;
+  char* d = g_arena.base;
+  cudaStream_t st = g_arena.stream;
+  if (int rc = check_cuda(cudaMemcpyAsync(d + o_val, value, b_val, cudaMemcpyHostToDevice, st), "H2D value")) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(d + o_loc, loc, b_loc, cudaMemcpyHostToDevice, st), "H2D loc")) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(d + o_aw, aw, b_aw, cudaMemcpyHostToDevice, st), "H2D aw")) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(d + o_go, grad_out, b_go, cudaMemcpyHostToDevice, st), "H2D grad_out")) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(d + o_shp, shapes, b_shp, cudaMemcpyHostToDevice, st), "H2D shapes")) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(d + o_lsi, level_start, b_lsi, cudaMemcpyHostToDevice, st), "H2D level_start")) return rc;
+  if (int rc = msda_backward(st, dtype, d + o_val, reinterpret_cast<int64_t*>(d + o_shp), reinterpret_cast<int64_t*>(d + o_lsi),
+                             d + o_loc, d + o_aw, d + o_go, N, S, M, D, L, Lq, P, d + o_gv, d + o_gl, d + o_ga,
+                             b_ws ? d + o_ws : nullptr, b_ws)) return rc;
+  if (b_val) if (int rc = check_cuda(cudaMemcpyAsync(grad_value, d + o_gv, b_val, cudaMemcpyDeviceToHost, st), "D2H grad_value")) return rc;
+  if (b_loc) {
+    if (int rc = check_cuda(cudaMemcpyAsync(grad_loc, d + o_gl, b_loc, cudaMemcpyDeviceToHost, st), "D2H grad_loc")) return rc;
+    if (int rc = check_cuda(cudaMemcpyAsync(grad_aw, d + o_ga, b_aw, cudaMemcpyDeviceToHost, st), "D2H grad_aw")) return rc;
+  }
+  return check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+}
+
+int mask_logits_forward_host(int device, int in_dtype, int out_dtype, const void* coeff, const void* proto, int B, int Q,
+                             int K, int64_t Ncols, void* out) {
+  if (B < 0 || Q < 0 || K <= 0 || Ncols < 0) return fail(MSDA_ERR_INVALID_ARG, "mask_logits_forward_host: bad sizes");
+  const size_t ei = dtype_size(in_dtype), eo = dtype_size(out_dtype);
+  const size_t b_c = (size_t)B * Q * K * ei, b_p = (size_t)B * K * Ncols * ei, b_o = (size_t)B * Q * Ncols * eo;
+  if (b_o == 0) return 0;
+  if (!coeff || !proto || !out) return fail(MSDA_ERR_INVALID_ARG, "mask_logits_forward_host: NULL tensor");
+  std::lock_guard<std::mutex> lock(g_arena.mu);
+  Carver cv;
+  const size_t o_c = cv.take(b_c), o_p = cv.take(b_p), o_o = cv.take(b_o);
+  if (int rc = arena_prepare(device, cv.off)) return rc;
+  char* d = g_arena.base;
+  cudaStream_t st = g_arena.stream;
+  if (int rc = check_cuda(cudaMemcpyAsync(d + o_c, coeff, b_c, cudaMemcpyHostToDevice, st), "H2D coeff")) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(d + o_p, proto, b_p, cudaMemcpyHostToDevice, st), "H2D proto")) return rc;
+  if (int rc = mask_logits_forward(st, in_dtype, out_dtype, d + o_c, d + o_p, B, Q, K, Ncols, d + o_o)) return rc;
+  if (int rc = check_cuda(cudaMemcpyAsync(out, d + o_o, b_o, cudaMemcpyDeviceToHost, st), "D2H out")) return rc;
+  return check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+}
+
+int msda_host_arena_release(void) {
+  std::lock_guard<std::mutex> lock(g_arena.mu);
+  if (g_arena.base) {
+    cudaSetDevice(g_arena.device);
+    if (g_arena.stream) cudaStreamSynchronize(g_arena.stream);
+    cudaFree(g_arena.base);
+    g_arena.base = nullptr; g_arena.cap = 0;
+  }
+  if (g_arena.stream) { cudaStreamDestroy(g_arena.stream); g_arena.stream = nullptr; }
+  g_arena.device = -1;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+// Shared device helpers for the multi-scale deformable attention kernels (sm_100a).
+//
+// Semantics follow the reference operator (paths relative to /root/reference/mdqe/models/ops):
+//   pixel mapping  x = loc_x * W - 0.5, y = loc_y * H - 0.5      src/cuda/ms_deform_im2col_cuda.cuh:285-286
+//   a corner contributes only when it lies inside the level        src/cuda/ms_deform_im2col_cuda.cuh:60-82
+//   which equals grid_sample(bilinear, zeros, align_corners=False) functions/ms_deform_attn_func.py:58-59
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace msda {
+
+constexpr int kMaxLevels = 32;       // "levels" seen by the op (pyramid levels, or T frames in temporal mode)
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+
+struct LevelInfo {                    // staged once per CTA in shared memory
+  int H, W, start, pad;
+};
+
+// One bilinear corner of one sample: where to read, and with which (attention-scaled) weight.
+// Out-of-range corners carry w == 0 and are never dereferenced.
+struct __align__(8) Slot {
+  uint32_t off;                       // element offset of the corner's channel row in `value`
+  float w;
+};
+
+__device__ __forceinline__ float ld_as_float(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ double ld_as_float(const double* p) { return __ldg(p); }
+
+__device__ __forceinline__ void st_from_float(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_from_float(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void st_from_float(double* p, double v) { *p = v; }
+
+// 16-byte channel vector of the value tensor -> fp32 registers.
+template <typename VT> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int kN = 4;
+  __device__ __forceinline__ static void load(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ static void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int kN = 8;
+  __device__ __forceinline__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {       // bf16 -> fp32 is a 16-bit shift
+      v[2 * i] = __uint_as_float(u[i] << 16);
+      v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+    }
+  }
+  __device__ __forceinline__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      u[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(u[0], u[1], u[2], u[3]);
+  }
+};
+
+// fp32 vector reduction into global memory (one 16-byte L2 atomic): SASS REDG.E.ADD.F32x4.
+__device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Stage the per-level geometry (int64 on device in the reference API) into shared memory.
+__device__ __forceinline__ void stage_levels(LevelInfo* s_lvl, const int64_t* __restrict__ shapes,
+                                             const int64_t* __restrict__ level_start, int L) {
+  if (threadIdx.x < L) {
+    LevelInfo li;
+    li.H = static_cast<int>(shapes[2 * threadIdx.x]);
+    li.W = static_cast<int>(shapes[2 * threadIdx.x + 1]);
+    li.start = static_cast<int>(level_start[threadIdx.x]);
+    li.pad = 0;
+    s_lvl[threadIdx.x] = li;
+  }
+}
+
+// Geometry of one sample: integer corner, fractional parts and per-corner validity.
+struct SampleGeom {
+  int x0, y0;
+  float lx, ly;                        // fractional position inside the cell
+  bool okx0, okx1, oky0, oky1;
+};
+
+__device__ __forceinline__ SampleGeom sample_geom(float locx, float locy, int H, int W) {
+  SampleGeom g;
+  const float x = locx * static_cast<float>(W) - 0.5f;
+  const float y = locy * static_cast<float>(H) - 0.5f;
+  const float fx = floorf(x), fy = floorf(y);
+  g.lx = x - fx;
+  g.ly = y - fy;
+  // NaN / huge coordinates fail every comparison below -> all corners invalid (sample skipped).
+  const bool sane = (fx >= -1.f) && (fx <= static_cast<float>(W)) && (fy >= -1.f) && (fy <= static_cast<float>(H));
+  g.x0 = sane ? static_cast<int>(fx) : -8;
+  g.y0 = sane ? static_cast<int>(fy) : -8;
+  g.okx0 = g.x0 >= 0 && g.x0 < W;
+  g.okx1 = g.x0 + 1 >= 0 && g.x0 + 1 < W;
+  g.oky0 = g.y0 >= 0 && g.y0 < H;
+  g.oky1 = g.y0 + 1 >= 0 && g.y0 + 1 < H;
+  return g;
+}
+
+}  // namespace msda

@@ -1,0 +1,62 @@
+// Internal glue shared by the translation units of libmsda_b200.so (not part of the public ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/msda_b200.h"
+
+namespace msda {
+
+// Records `msg` as the calling thread's last error and returns `code`.
+int fail(int code, const char* fmt, ...);
+// Converts a CUDA error into MSDA_ERR_CUDA (+ message); returns 0 when err == cudaSuccess.
+int check_cuda(cudaError_t err, const char* what);
+// Call after every kernel launch: counts it and turns launch errors into status codes.
+int after_launch(const char* kernel_name);
+
+int option(const char* key);          // current value of a tuning knob
+
+// RAII event bracket around one kernel launch; active only when the "profile" option is 1 and the
+// stream is not being captured into a CUDA graph.
+class ProfScope {
+ public:
+  ProfScope(cudaStream_t st, int kind, int64_t units);
+  ~ProfScope();
+  ProfScope(const ProfScope&) = delete;
+  ProfScope& operator=(const ProfScope&) = delete;
+ private:
+  cudaStream_t st_;
+  int kind_;
+  int64_t units_;
+  cudaEvent_t a_ = nullptr, b_ = nullptr;
+  bool on_ = false;
+};
+
+// mask_gemm.cu
+int mask_forward_dispatch(cudaStream_t stream, int in_dtype, int out_dtype, const void* coeff, const void* proto,
+                          int B, int Q, int K, int64_t Ncols, void* out);
+int mask_backward_dispatch(cudaStream_t stream, int dtype, const void* coeff, const void* proto, const void* grad_out,
+                           int B, int Q, int K, int64_t Ncols, void* grad_coeff, void* grad_proto);
+
+inline size_t dtype_size(int dtype) {
+  switch (dtype) {
+    case MSDA_F32: return 4;
+    case MSDA_BF16: return 2;
+    case MSDA_F64: return 8;
+    case MSDA_BF16_LOC32: return 2;
+    default: return 0;
+  }
+}
+inline size_t loc_dtype_size(int dtype) {
+  switch (dtype) {
+    case MSDA_F32: return 4;
+    case MSDA_BF16: return 2;
+    case MSDA_F64: return 8;
+    case MSDA_BF16_LOC32: return 4;
+    default: return 0;
+  }
+}
+
+}  // namespace msda

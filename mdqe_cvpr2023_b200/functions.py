@@ -1,0 +1,62 @@
+"""Autograd surface of the hot path.
+
+`MSDeformAttnFunction` keeps the reference signature
+``apply(value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights, im2col_step)``
+(/root/reference/mdqe/models/ops/functions/ms_deform_attn_func.py:22-42): gradients for arguments
+0, 3 and 4 only, once-differentiable, inputs cast to fp32 under autocast (custom_fwd(cast_inputs=float32)),
+so the default behaviour equals the reference.  bf16 is opt-in: tensors that arrive as bf16 OUTSIDE
+autocast run the bf16 kernels (fp32 arithmetic).
+
+`mask_logits` is the operator form of the four ``torch.einsum('bqm,bmthw->bqthw')`` sites
+(transformer_dec.py:255, mdqe/mdqe.py:384, matcher.py:182, criterion.py:440).
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ops
+
+
+class MSDeformAttnFunction(Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+                im2col_step):
+        ctx.im2col_step = im2col_step
+        output = ops.ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                                            attention_weights, im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                              attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        value, shapes, level_start, loc, aw = ctx.saved_tensors
+        grad_value, grad_loc, grad_aw = ops.ms_deform_attn_backward(
+            value, shapes, level_start, loc, aw, grad_output.contiguous(), ctx.im2col_step)
+        return grad_value, None, None, grad_loc, grad_aw, None
+
+
+class _MaskLogitsFunction(Function):
+    @staticmethod
+    def forward(ctx, coeff, proto):
+        ctx.save_for_backward(coeff, proto)
+        return ops.mask_logits_forward(coeff, proto)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        coeff, proto = ctx.saved_tensors
+        gc, gp = ops.mask_logits_backward(coeff, proto, grad_out.contiguous(),
+                                          need_coeff=ctx.needs_input_grad[0], need_proto=ctx.needs_input_grad[1])
+        return gc, gp
+
+
+def mask_logits(coeff, proto):
+    """Drop-in for ``torch.einsum('bqm,bmthw->bqthw', coeff, proto)`` (also accepts the unbatched
+    'qm,mthw->qthw' form of mdqe/mdqe.py:384)."""
+    if coeff.dim() == 2:
+        return _MaskLogitsFunction.apply(coeff.unsqueeze(0).contiguous(), proto.unsqueeze(0).contiguous()).squeeze(0)
+    return _MaskLogitsFunction.apply(coeff.contiguous(), proto.contiguous())

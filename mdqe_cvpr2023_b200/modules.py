@@ -1,0 +1,170 @@
+"""`MSDeformAttn` with the reference module's constructor, forward signature and state-dict keys
+(/root/reference/mdqe/models/ops/modules/ms_deform_attn.py:34-238), running on the B200 kernels.
+
+Kept identical so that mdqe/models/transformer_{enc,dec}.py and released checkpoints work as-is:
+  * parameters  value_proj, output_proj, attention_weights, and sampling_offsets (pred_offsets=True,
+    encoder) or sampling_grid_offsets (pred_offsets=False, decoder)            (ms_deform_attn.py:68-74)
+  * buffers     lvl_spatial_scales, and sampling_offsets when pred_offsets=False  (:63-66, :96)
+  * `_reset_parameters()` is public in practice: the decoder calls it again    (transformer_dec.py:72-74)
+  * mode 'spatial' samples the L pyramid levels of one frame; mode 'temporal' samples the T frames of
+    the clip level by level and averages the levels                           (:118-173, :175-238)
+
+What differs from the reference implementation (not from its results):
+  * temporal mode hands the operator a *view* of the whole [B, T*S, M, D] value tensor and encodes
+    "frame t of level l" in level_start_index (= t*S + start_l) instead of materialising four
+    `.contiguous()` copies per call (ms_deform_attn.py:222-224);
+  * all tensor work below the Linear layers goes through MSDeformAttnFunction -> libmsda_b200.so.
+"""
+import math
+import warnings
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .functions import MSDeformAttnFunction
+
+
+def _is_power_of_2(n):
+    if not isinstance(n, int) or n < 0:
+        raise ValueError(f"invalid input for _is_power_of_2: {n} (type: {type(n)})")
+    return n != 0 and (n & (n - 1)) == 0
+
+
+class MSDeformAttn(nn.Module):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, n_frames=1, pred_offsets=True,
+                 mode='spatial'):
+        super().__init__()
+        if d_model % n_heads != 0:
+            raise ValueError(f'd_model must be divisible by n_heads, but got {d_model} and {n_heads}')
+        if not _is_power_of_2(d_model // n_heads):
+            warnings.warn("MSDeformAttn: a power-of-2 head dimension is the fast path of the reference CUDA "
+                          "kernels; here 32 and 24 are specialised and every other size takes the generic kernel.")
+        if mode not in ('spatial', 'temporal'):
+            raise ValueError(f"mode must be 'spatial' or 'temporal', got {mode!r}")
+
+        self.im2col_step = 64
+        self.mode = mode
+        self.d_model = d_model
+        self.n_levels = n_levels
+        self.n_heads = n_heads
+        self.n_points = n_points
+        self.pred_offsets = pred_offsets
+        self.scale = 8.
+        self.n_frames = n_frames
+
+        # what the operator sees as "levels": pyramid levels of a frame, or the frames of a clip
+        if mode == 'spatial':
+            self.lvl = n_levels
+            lvl_spatial_scales = torch.arange(1, self.lvl + 1)
+        else:
+            self.lvl = n_frames
+            lvl_spatial_scales = torch.full((self.lvl,), 2, dtype=torch.long)
+        self.register_buffer("lvl_spatial_scales", lvl_spatial_scales)
+
+        n_samples = n_heads * self.lvl * n_points
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        self.attention_weights = nn.Linear(d_model, n_samples)
+        if pred_offsets:
+            self.sampling_offsets = nn.Linear(d_model, n_samples * 2)
+        else:
+            self.sampling_grid_offsets = nn.Linear(d_model, n_samples * 2)
+        self._reset_parameters()
+
+    # ------------------------------------------------------------------------------------- init
+    def _reset_parameters(self):
+        H, L, K = self.n_heads, self.lvl, self.n_points
+        angle = torch.arange(H, dtype=torch.float32) * (2.0 * math.pi / H)
+        ray = torch.stack([angle.cos(), angle.sin()], -1)
+        ray = ray / ray.abs().max(-1, keepdim=True)[0]                       # unit square directions, one per head
+        steps = torch.arange(1, K + 1, dtype=torch.float32).view(1, 1, K, 1)
+        grid = ray.view(H, 1, 1, 2).repeat(1, L, K, 1) * steps               # H L K 2: k-th point k+1 steps out
+        grid = grid / K * self.scale
+        if self.pred_offsets:
+            nn.init.constant_(self.sampling_offsets.weight.data, 0.)
+            grid = grid * 0.05 * self.lvl_spatial_scales.reshape(1, -1, 1, 1).to(grid)
+            with torch.no_grad():
+                self.sampling_offsets.bias = nn.Parameter(grid.reshape(-1))
+        else:
+            self.register_buffer("sampling_offsets", grid.view(1, 1, H, L, K, 2).clone())
+            nn.init.constant_(self.sampling_grid_offsets.weight.data, 0.)
+            nn.init.constant_(self.sampling_grid_offsets.bias.data, 0.)
+        nn.init.constant_(self.attention_weights.weight.data, 0.)
+        nn.init.constant_(self.attention_weights.bias.data, 0.)
+        nn.init.xavier_uniform_(self.value_proj.weight.data)
+        nn.init.constant_(self.value_proj.bias.data, 0.)
+        nn.init.xavier_uniform_(self.output_proj.weight.data)
+        nn.init.constant_(self.output_proj.bias.data, 0.)
+
+    # ---------------------------------------------------------------------------------- pieces
+    def _sampling(self, query, reference_points):
+        """-> (sampling_locations [B,Q,H,L,K,2], attention_weights [B,Q,H,L,K]) for L = self.lvl."""
+        B, Q, _ = query.shape
+        H, L, K = self.n_heads, self.lvl, self.n_points
+        ref = reference_points.view(B, Q, 1, 1, 1, -1)
+        if self.pred_offsets:
+            offsets = self.sampling_offsets(query).view(B, Q, H, L, K, 2)
+        else:
+            # fixed ray grid scaled to half the reference box, plus a learned residual clamped to +-8 boxes
+            box = ref[..., 2:]
+            residual = self.sampling_grid_offsets(query).view(B, Q, H, L, K, 2).to(ref)
+            bound = box * self.scale
+            residual = torch.where(residual > -bound, residual, -bound)
+            residual = torch.where(residual < bound, residual, bound)
+            offsets = self.sampling_offsets * 0.5 * box + residual
+        locations = ref[..., :2] + offsets / self.scale
+        logits = self.attention_weights(query).view(B, Q, H, L * K)
+        weights = F.softmax(logits, -1).view(B, Q, H, L, K)
+        return locations, weights
+
+    def _project_value(self, input_flatten, input_padding_mask):
+        value = self.value_proj(input_flatten)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None], float(0))
+        return value.view(*value.shape[:-1], self.n_heads, self.d_model // self.n_heads)
+
+    @staticmethod
+    def _level_starts(spatial_shapes):
+        sizes = spatial_shapes.prod(-1)
+        return torch.cat([sizes.new_zeros(1), sizes.cumsum(0)[:-1]]).long(), sizes
+
+    # --------------------------------------------------------------------------------- forward
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_padding_mask=None):
+        if self.mode == 'spatial':
+            return self.spatial_forward(query, reference_points, input_flatten, input_spatial_shapes,
+                                        input_padding_mask)
+        return self.temporal_clip_forward(query, reference_points, input_flatten, input_spatial_shapes,
+                                          input_padding_mask)
+
+    @torch.amp.autocast("cuda", enabled=False)
+    def spatial_forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_padding_mask=None):
+        """query BxQxC, reference_points BxQx4 (cx, cy, w, h), input_flatten BxSxC with S = sum_l H_l*W_l."""
+        level_start, sizes = self._level_starts(input_spatial_shapes)
+        assert int(sizes.sum()) == input_flatten.shape[1]
+        value = self._project_value(input_flatten, input_padding_mask)               # B S H D
+        locations, weights = self._sampling(query, reference_points)
+        sampled = MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes.contiguous(), level_start,
+                                             locations.contiguous(), weights.contiguous(), self.im2col_step)
+        return self.output_proj(sampled)
+
+    @torch.amp.autocast("cuda", enabled=False)
+    def temporal_clip_forward(self, query, reference_points, input_flatten, input_spatial_shapes,
+                              input_padding_mask=None):
+        """query BxQxC, reference_points BxQx4, input_flatten BxTxSxC; the T frames play the role of levels."""
+        B, T, S, _ = input_flatten.shape
+        assert T == self.n_frames, f"temporal MSDeformAttn built for {self.n_frames} frames, got {T}"
+        level_start, _ = self._level_starts(input_spatial_shapes)
+        value = self._project_value(input_flatten, input_padding_mask)               # B T S H D
+        value = value.contiguous().view(B, T * S, self.n_heads, -1)                  # frames back to back, no copies
+        locations, weights = self._sampling(query, reference_points)
+        locations, weights = locations.contiguous(), weights.contiguous()
+        frame_base = torch.arange(T, device=level_start.device, dtype=level_start.dtype) * S
+        sampled = None
+        for lvl in range(input_spatial_shapes.shape[0]):
+            shapes_l = input_spatial_shapes[lvl].view(1, 2).expand(T, 2).contiguous()
+            starts_l = frame_base + level_start[lvl]
+            out_l = MSDeformAttnFunction.apply(value, shapes_l, starts_l, locations, weights, self.im2col_step)
+            sampled = out_l if sampled is None else sampled + out_l
+        sampled = sampled / input_spatial_shapes.shape[0]
+        return self.output_proj(sampled)

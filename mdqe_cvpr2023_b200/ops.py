@@ -1,0 +1,153 @@
+"""Tensor-level entry points with the reference extension's names and argument order.
+
+`ms_deform_attn_forward` / `ms_deform_attn_backward` mirror the two functions the reference's
+compiled module `MultiScaleDeformableAttention` exports (/root/reference/mdqe/models/ops/src/vision.cpp:13-16,
+src/ms_deform_attn.h:20-61, src/cuda/ms_deform_attn_cuda.cu:20-153): same positional arguments, same
+returned shapes, same failure modes (non-contiguous or CPU tensors and a batch that `im2col_step`
+does not divide raise RuntimeError).  Underneath they pass raw device pointers and the current CUDA
+stream to the C ABI of libmsda_b200.so.
+"""
+import torch
+
+from . import _lib
+
+_VALUE_DTYPES = (torch.float32, torch.bfloat16, torch.float64)
+
+
+def _dtype_code(value, loc, aw, who):
+    if value.dtype not in _VALUE_DTYPES:
+        raise RuntimeError(f"{who}: unsupported value dtype {value.dtype} (float32, bfloat16, float64)")
+    if loc.dtype != aw.dtype:
+        raise RuntimeError(f"{who}: sampling_loc ({loc.dtype}) and attn_weight ({aw.dtype}) dtypes differ")
+    if value.dtype == torch.float32 and loc.dtype == torch.float32:
+        return _lib.MSDA_F32
+    if value.dtype == torch.float64 and loc.dtype == torch.float64:
+        return _lib.MSDA_F64
+    if value.dtype == torch.bfloat16 and loc.dtype == torch.bfloat16:
+        return _lib.MSDA_BF16
+    if value.dtype == torch.bfloat16 and loc.dtype == torch.float32:
+        return _lib.MSDA_BF16_LOC32
+    raise RuntimeError(f"{who}: unsupported dtype combination value={value.dtype}, sampling_loc={loc.dtype}")
+
+
+def _check_inputs(who, tensors):
+    for name, t in tensors:
+        if not t.is_cuda:
+            # the reference dispatches on value.type().is_cuda() and AT_ERRORs otherwise (ms_deform_attn.h:38,60)
+            raise RuntimeError(f"{who}: Not implemented on the CPU ({name} must be a CUDA tensor)")
+        if not t.is_contiguous():
+            raise RuntimeError(f"{who}: {name} tensor has to be contiguous")
+    dev = tensors[0][1].device
+    for name, t in tensors:
+        if t.device != dev:
+            raise RuntimeError(f"{who}: {name} is on {t.device}, expected {dev}")
+
+
+def _dims(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step, who):
+    if value.dim() != 4 or sampling_loc.dim() != 6 or attn_weight.dim() != 5:
+        raise RuntimeError(f"{who}: expected value[N,S,M,D], sampling_loc[N,Lq,M,L,P,2], attn_weight[N,Lq,M,L,P]")
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq, P = sampling_loc.shape[1], sampling_loc.shape[4]
+    if tuple(sampling_loc.shape) != (N, Lq, M, L, P, 2) or tuple(attn_weight.shape) != (N, Lq, M, L, P):
+        raise RuntimeError(f"{who}: inconsistent shapes value={tuple(value.shape)} spatial_shapes={tuple(spatial_shapes.shape)} "
+                           f"sampling_loc={tuple(sampling_loc.shape)} attn_weight={tuple(attn_weight.shape)}")
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError(f"{who}: spatial_shapes and level_start_index must be int64")
+    if tuple(spatial_shapes.shape) != (L, 2) or level_start_index.numel() != L:
+        raise RuntimeError(f"{who}: spatial_shapes must be [L,2] and level_start_index [L]")
+    step = min(N, int(im2col_step))
+    if N > 0 and (step <= 0 or N % step != 0):
+        # same contract as ms_deform_attn_cuda.cu:50-52
+        raise RuntimeError(f"{who}: batch({N}) must divide im2col_step({step})")
+    return N, S, M, D, L, Lq, P
+
+
+def _stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    """-> Tensor[N, Lq, M*D]; drop-in for MultiScaleDeformableAttention.ms_deform_attn_forward."""
+    who = "ms_deform_attn_forward"
+    _check_inputs(who, [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                        ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)])
+    N, S, M, D, L, Lq, P = _dims(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step, who)
+    code = _dtype_code(value, sampling_loc, attn_weight, who)
+    lib = _lib.load()
+    with torch.cuda.device(value.device):
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        rc = lib.msda_forward(_stream_ptr(value.device), code, value.data_ptr(), spatial_shapes.data_ptr(),
+                              level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                              N, S, M, D, L, Lq, P, out.data_ptr())
+    _lib.check(rc, who)
+    return out
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            im2col_step):
+    """-> [grad_value, grad_sampling_loc, grad_attn_weight]; drop-in for the extension's backward."""
+    who = "ms_deform_attn_backward"
+    _check_inputs(who, [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                        ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("grad_output", grad_output)])
+    N, S, M, D, L, Lq, P = _dims(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step, who)
+    if grad_output.dtype != value.dtype or grad_output.numel() != N * Lq * M * D:
+        raise RuntimeError(f"{who}: grad_output must be {value.dtype} with {N * Lq * M * D} elements")
+    code = _dtype_code(value, sampling_loc, attn_weight, who)
+    lib = _lib.load()
+    with torch.cuda.device(value.device):
+        grad_value = torch.empty_like(value)
+        grad_loc = torch.empty_like(sampling_loc)
+        grad_aw = torch.empty_like(attn_weight)
+        ws_bytes = lib.msda_backward_workspace_bytes(code, N, S, M, D)
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
+        rc = lib.msda_backward(_stream_ptr(value.device), code, value.data_ptr(), spatial_shapes.data_ptr(),
+                               level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                               grad_output.data_ptr(), N, S, M, D, L, Lq, P,
+                               grad_value.data_ptr(), grad_loc.data_ptr(), grad_aw.data_ptr(),
+                               ws.data_ptr() if ws is not None else None, ws_bytes)
+    _lib.check(rc, who)
+    return [grad_value, grad_loc, grad_aw]
+
+
+_MASK_CODES = {torch.float32: _lib.MSDA_F32, torch.bfloat16: _lib.MSDA_BF16}
+
+
+def mask_logits_forward(coeff, proto, out_dtype=None):
+    """coeff[B,Q,K] x proto[B,K,*plane] -> [B,Q,*plane]  ==  einsum('bqm,bmthw->bqthw')."""
+    who = "mask_logits_forward"
+    _check_inputs(who, [("coeff", coeff), ("proto", proto)])
+    if coeff.dim() != 3 or proto.dim() < 3 or proto.shape[0] != coeff.shape[0] or proto.shape[1] != coeff.shape[2]:
+        raise RuntimeError(f"{who}: expected coeff[B,Q,K] and proto[B,K,...], got {tuple(coeff.shape)} {tuple(proto.shape)}")
+    if coeff.dtype != proto.dtype or coeff.dtype not in _MASK_CODES:
+        raise RuntimeError(f"{who}: coeff/proto must both be float32 or bfloat16")
+    out_dtype = out_dtype or coeff.dtype
+    B, Q, K = coeff.shape
+    plane = tuple(proto.shape[2:])
+    ncols = 1
+    for s in plane:
+        ncols *= s
+    lib = _lib.load()
+    with torch.cuda.device(coeff.device):
+        out = torch.empty((B, Q) + plane, dtype=out_dtype, device=coeff.device)
+        rc = lib.mask_logits_forward(_stream_ptr(coeff.device), _MASK_CODES[coeff.dtype], _MASK_CODES[out_dtype],
+                                     coeff.data_ptr(), proto.data_ptr(), B, Q, K, ncols, out.data_ptr())
+    _lib.check(rc, who)
+    return out
+
+
+def mask_logits_backward(coeff, proto, grad_out, need_coeff=True, need_proto=True):
+    who = "mask_logits_backward"
+    _check_inputs(who, [("coeff", coeff), ("proto", proto), ("grad_out", grad_out)])
+    B, Q, K = coeff.shape
+    ncols = proto.numel() // max(1, B * K)
+    lib = _lib.load()
+    with torch.cuda.device(coeff.device):
+        gc = torch.empty_like(coeff) if need_coeff else None
+        gp = torch.empty_like(proto) if need_proto else None
+        rc = lib.mask_logits_backward(_stream_ptr(coeff.device), _MASK_CODES[coeff.dtype], coeff.data_ptr(),
+                                      proto.data_ptr(), grad_out.data_ptr(), B, Q, K, ncols,
+                                      gc.data_ptr() if gc is not None else None,
+                                      gp.data_ptr() if gp is not None else None)
+    _lib.check(rc, who)
+    return gc, gp

@@ -46,7 +46,7 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def _prep(value, shapes, loc, aw):
+def _prep(value, shapes, loc, aw, level_start=None):
     dt = value.dtype
     assert dt in (np.float32, np.float64), dt
     value = np.ascontiguousarray(value, dtype=dt)
@@ -56,16 +56,19 @@ def _prep(value, shapes, loc, aw):
     N, S, M, D = value.shape
     _, Lq, _, L, P, _ = loc.shape
     assert shapes.shape == (L, 2)
-    assert int((shapes[:, 0] * shapes[:, 1]).sum()) == S
-    lsi = np.concatenate([[0], np.cumsum(shapes[:, 0] * shapes[:, 1])[:-1]]).astype(np.int64)
+    if level_start is None:
+        assert int((shapes[:, 0] * shapes[:, 1]).sum()) == S
+        lsi = np.concatenate([[0], np.cumsum(shapes[:, 0] * shapes[:, 1])[:-1]]).astype(np.int64)
+    else:
+        # explicit starts: levels may be any sub-windows of the S value rows (temporal mode)
+        lsi = np.ascontiguousarray(level_start, dtype=np.int64).reshape(L)
+        assert L == 0 or int((lsi + shapes[:, 0] * shapes[:, 1]).max()) <= S
     return value, shapes, lsi, loc, aw, (N, S, M, D, L, Lq, P)
 
 
 def msda_forward(value, shapes, loc, aw, level_start=None):
     """out[N,Lq,M*D] for value[N,S,M,D], shapes[L,2], loc[N,Lq,M,L,P,2], aw[N,Lq,M,L,P]."""
-    value, shapes, lsi, loc, aw, dims = _prep(value, shapes, loc, aw)
-    if level_start is not None:
-        lsi = np.ascontiguousarray(level_start, dtype=np.int64)
+    value, shapes, lsi, loc, aw, dims = _prep(value, shapes, loc, aw, level_start)
     N, S, M, D, L, Lq, P = dims
     out = np.empty((N, Lq, M * D), dtype=value.dtype)
     fn = getattr(_load(), "msda_oracle_forward_f32" if value.dtype == np.float32 else "msda_oracle_forward_f64")
@@ -76,9 +79,7 @@ def msda_forward(value, shapes, loc, aw, level_start=None):
 
 def msda_backward(value, shapes, loc, aw, grad_out, level_start=None):
     """(grad_value, grad_loc, grad_aw) of sum(out * grad_out)."""
-    value, shapes, lsi, loc, aw, dims = _prep(value, shapes, loc, aw)
-    if level_start is not None:
-        lsi = np.ascontiguousarray(level_start, dtype=np.int64)
+    value, shapes, lsi, loc, aw, dims = _prep(value, shapes, loc, aw, level_start)
     N, S, M, D, L, Lq, P = dims
     go = np.ascontiguousarray(grad_out, dtype=value.dtype).reshape(N, Lq, M * D)
     gv = np.zeros_like(value)

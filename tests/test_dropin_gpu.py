@@ -1,0 +1,52 @@
+"""The three drop-in levels of SURVEY 8(b) on the GPU: (L0) a module named MultiScaleDeformableAttention,
+(L1) MSDeformAttnFunction, (L2) the MSDeformAttn module -- the latter against fixtures recorded from
+the unmodified reference module."""
+import pytest
+import torch
+
+from tests.helpers import load_golden, module_from_golden, module_inputs, nerr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_l0_extension_module_name_and_signatures():
+    import mdqe_cvpr2023_b200 as pkg
+    msda = pkg.install_dropin()
+    import MultiScaleDeformableAttention as again
+    assert again is msda and msda.__name__ == "MultiScaleDeformableAttention"
+    z = load_golden("pyramid_D32_f32")
+    t = {k: torch.from_numpy(z[k]).cuda() for k in ("value", "shapes", "level_start", "loc", "aw", "grad_out")}
+    out = msda.ms_deform_attn_forward(t["value"], t["shapes"], t["level_start"], t["loc"], t["aw"], 64)
+    assert tuple(out.shape) == tuple(z["out"].shape) and nerr(out, z["out"]) < 2e-5
+    grads = msda.ms_deform_attn_backward(t["value"], t["shapes"], t["level_start"], t["loc"], t["aw"], t["grad_out"], 64)
+    assert isinstance(grads, list) and len(grads) == 3
+    for g, k in zip(grads, ("grad_value", "grad_loc", "grad_aw")):
+        assert nerr(g, z[k]) < 2e-5
+
+
+@pytest.mark.parametrize("name", ["module_spatial_pred", "module_spatial_grid", "module_temporal_grid"])
+def test_l2_module_matches_reference_module(name):
+    from mdqe_cvpr2023_b200 import MSDeformAttn
+    z = load_golden(name)
+    mod = module_from_golden(z, MSDeformAttn).cuda()
+    query, ref, inp, shapes, mask = module_inputs(z, "cuda")
+    out = mod(query, ref, inp, shapes, mask)
+    assert nerr(out, z["out"]) <= 1e-4
+    out.backward(torch.from_numpy(z["grad_out"]).cuda())
+    assert nerr(query.grad, z["grad_query"]) <= 1e-4
+    assert nerr(inp.grad, z["grad_input"]) <= 1e-4
+    for k, p in mod.named_parameters():
+        assert nerr(p.grad, z["gp." + k]) <= 2e-4, k
+
+
+def test_module_r50_shape_runs_under_autocast():
+    from mdqe_cvpr2023_b200 import MSDeformAttn
+    torch.manual_seed(0)
+    mod = MSDeformAttn().cuda()
+    shapes = torch.tensor([(48, 80), (24, 40), (12, 20), (6, 10)], device="cuda")
+    S = 5100
+    x = torch.randn(2, S, 256, device="cuda")
+    ref = torch.rand(2, S, 4, device="cuda")
+    with torch.autocast("cuda", dtype=torch.float16):
+        y = mod(x, ref, x, shapes, None)
+    assert y.dtype == torch.float32 and tuple(y.shape) == (2, S, 256) and bool(torch.isfinite(y).all())

@@ -1,0 +1,61 @@
+"""Mask contraction (coeff x proto) on the GPU against the einsum fixtures and torch.einsum (config 5
+sweep, reduced).  fp32 tolerance 1e-4 normalised (asserted 2e-5), bf16 2e-2."""
+import itertools
+
+import pytest
+import torch
+
+from tests.helpers import load_golden, nerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _reset_options():
+    from mdqe_cvpr2023_b200 import _lib
+    yield
+    _lib.set_option("mask_variant", 0)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("name", ["mask_einsum_K32", "mask_einsum_K24"])
+def test_mask_golden(name, variant):
+    from mdqe_cvpr2023_b200 import _lib, mask_logits
+    _lib.set_option("mask_variant", variant)
+    z = load_golden(name)
+    coeff = torch.from_numpy(z["coeff"]).cuda().requires_grad_(True)
+    proto = torch.from_numpy(z["proto"]).cuda().requires_grad_(True)
+    out = mask_logits(coeff, proto)
+    assert tuple(out.shape) == tuple(z["out"].shape)
+    assert nerr(out, z["out"]) < 2e-5
+    out.backward(torch.from_numpy(z["grad_out"]).cuda())
+    assert nerr(coeff.grad, z["grad_coeff"]) < 2e-5
+    assert nerr(proto.grad, z["grad_proto"]) < 2e-5
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("Q,T,plane,K", [(196, 4, (96, 160), 32), (100, 2, (96, 160), 24), (300, 2, (160, 288), 32),
+                                         (196, 3, (96, 160), 24), (7, 1, (5, 9), 32), (130, 2, (33, 17), 40)])
+def test_mask_sweep_vs_einsum(Q, T, plane, K, variant):
+    from mdqe_cvpr2023_b200 import _lib, ops
+    _lib.set_option("mask_variant", variant)
+    g = torch.Generator(device="cuda").manual_seed(Q + T)
+    coeff = torch.tanh(torch.randn(1, Q, K, device="cuda", generator=g))
+    proto = torch.randn(1, K, T, *plane, device="cuda", generator=g)
+    want = torch.einsum("bqm,bmthw->bqthw", coeff.double(), proto.double())
+    out = ops.mask_logits_forward(coeff, proto)
+    assert nerr(out, want) < 2e-5
+    out16 = ops.mask_logits_forward(coeff.bfloat16(), proto.bfloat16())
+    want16 = torch.einsum("bqm,bmthw->bqthw", coeff.bfloat16().double(), proto.bfloat16().double())
+    assert out16.dtype == torch.bfloat16 and nerr(out16.float(), want16) < 2e-2
+    out_mixed = ops.mask_logits_forward(coeff, proto, out_dtype=torch.bfloat16)
+    assert nerr(out_mixed.float(), want) < 2e-2
+
+
+def test_mask_unbatched_form_and_empty():
+    from mdqe_cvpr2023_b200 import mask_logits, ops
+    coeff = torch.randn(5, 32, device="cuda")
+    proto = torch.randn(32, 2, 6, 8, device="cuda")
+    assert nerr(mask_logits(coeff, proto), torch.einsum("qm,mthw->qthw", coeff, proto)) < 2e-5   # mdqe/mdqe.py:384
+    out = ops.mask_logits_forward(torch.zeros(1, 0, 32, device="cuda"), torch.zeros(1, 32, 1, 4, 4, device="cuda"))
+    assert tuple(out.shape) == (1, 0, 1, 4, 4)

@@ -1,0 +1,255 @@
+"""Parity of the CUDA multi-scale deformable attention (through the C ABI) against the oracle and
+the golden fixtures recorded from the reference's Python.  Tolerances (north_star / SURVEY 8d):
+normalised max error <= 1e-4 in fp32 (we assert 2e-5), <= 2e-2 in bf16, 1e-10 in fp64."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.gpu_util import R50_360, R50_720, make_inputs, oracle_all, to_cuda
+from tests.helpers import GOLDEN, load_golden, nerr
+
+pytestmark = pytest.mark.gpu
+
+CORE = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+              if not os.path.basename(p).startswith(("module_", "mask_")))
+
+
+@pytest.fixture(autouse=True)
+def _reset_options():
+    from mdqe_cvpr2023_b200 import _lib
+    yield
+    for k in ("fwd_variant", "bwd_variant", "chunk_pairs", "mask_variant"):
+        _lib.set_option(k, 0)
+
+
+def run_op(inp):
+    from mdqe_cvpr2023_b200 import ops
+    out = ops.ms_deform_attn_forward(inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["aw"], 64)
+    gv, gl, ga = ops.ms_deform_attn_backward(inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["aw"],
+                                             inp["grad_out"], 64)
+    torch.cuda.synchronize()
+    return out, gv, gl, ga
+
+
+def check(got, want, tol, what=""):
+    names = ("out", "grad_value", "grad_loc", "grad_aw")
+    for g, w, n in zip(got, want, names):
+        e = nerr(g.float() if g.dtype == torch.bfloat16 else g, np.asarray(w).reshape(tuple(g.shape)))
+        assert e <= tol, f"{what} {n}: normalised max error {e:.3e} > {tol:.1e}"
+
+
+@pytest.mark.parametrize("name", CORE)
+def test_golden_fixtures(name):
+    z = load_golden(name)
+    inp = {k: torch.from_numpy(z[k]).cuda() for k in ("value", "shapes", "level_start", "loc", "aw", "grad_out")}
+    tol = 1e-10 if z["value"].dtype == np.float64 else 2e-5
+    got = run_op(inp)
+    check(got, (z["out"], z["grad_value"], z["grad_loc"], z["grad_aw"]), tol, name)
+    if name.startswith("ref_fixture") and z["value"].dtype == np.float32:
+        assert torch.allclose(got[0].cpu(), torch.from_numpy(z["out"]), rtol=1e-2, atol=1e-3)   # ops/test.py:56
+
+
+@pytest.mark.parametrize("dist", ["uniform", "local", "wide"])
+@pytest.mark.parametrize("D", [32, 24])
+def test_encoder_shape_fp32_vs_oracle(dist, D):
+    inp = make_inputs(1, R50_360, 8, D, 4, dist=dist, seed=1)
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"enc {dist} D{D}")
+
+
+@pytest.mark.parametrize("N,Lq", [(3, 196), (4, 50), (1, 1), (2, 7)])
+def test_decoder_shapes_fp32_vs_oracle(N, Lq):
+    inp = make_inputs(N, R50_360, 8, 32, 4, Lq=Lq, dist="wide", seed=2)
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"dec N{N} Lq{Lq}")
+
+
+@pytest.mark.parametrize("L,P", [(1, 4), (2, 4), (3, 4), (4, 2), (4, 8), (8, 4), (5, 3), (4, 9)])
+def test_level_point_combinations(L, P):
+    shapes = [(10 + 3 * i, 7 + 2 * i) for i in range(L)]
+    inp = make_inputs(2, shapes, 8, 32, P, Lq=33, dist="wide", seed=3)
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"L{L} P{P}")
+
+
+@pytest.mark.parametrize("M,D", [(1, 32), (3, 24), (4, 16), (2, 8), (8, 30), (2, 64), (1, 71), (1, 200)])
+def test_head_configs(M, D):
+    inp = make_inputs(2, [(9, 11), (5, 6)], M, D, 4, Lq=21, dist="wide", seed=4)
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"M{M} D{D}")
+
+
+@pytest.mark.parametrize("variant", ["fwd_variant", "bwd_variant"])
+def test_generic_kernels_on_fast_shape(variant):
+    from mdqe_cvpr2023_b200 import _lib
+    _lib.set_option(variant, 1)
+    inp = make_inputs(1, R50_360, 8, 32, 4, Lq=300, dist="local", seed=5)
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, variant)
+
+
+@pytest.mark.parametrize("chunk", [16, 48, 256])
+def test_chunk_sizes(chunk):
+    from mdqe_cvpr2023_b200 import _lib
+    _lib.set_option("chunk_pairs", chunk)
+    inp = make_inputs(2, [(12, 20), (6, 10), (3, 5), (2, 3)], 8, 32, 4, dist="local", seed=6)
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"chunk {chunk}")
+
+
+@pytest.mark.parametrize("loc_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("D", [32, 24, 16])
+def test_bf16_vs_oracle_on_rounded_inputs(loc_dtype, D):
+    inp = make_inputs(2, [(24, 40), (12, 20), (6, 10), (3, 5)], 8, D, 4, dist="local", seed=7)
+    for k in ("value", "grad_out"):
+        inp[k] = inp[k].to(torch.bfloat16)
+    for k in ("loc", "aw"):
+        inp[k] = inp[k].to(loc_dtype)
+    got = run_op(to_cuda(inp))
+    assert got[0].dtype == torch.bfloat16 and got[1].dtype == torch.bfloat16 and got[2].dtype == loc_dtype
+    check(got, oracle_all(inp), 2e-2, f"bf16 loc={loc_dtype} D{D}")
+
+
+def test_temporal_level_start_windows():
+    """levels = T frames of one pyramid level inside a [B, T*S] value tensor (modules.py temporal mode)."""
+    T, S = 4, 5100
+    g = torch.Generator().manual_seed(8)
+    H, W, start = 24, 40, 3840
+    value = torch.randn(2, T * S, 8, 32, generator=g)
+    loc = torch.rand(2, 196, 8, T, 4, 2, generator=g) * 1.2 - 0.1
+    aw = torch.softmax(torch.randn(2, 196, 8, T * 4, generator=g), -1).view(2, 196, 8, T, 4)
+    inp = dict(value=value, shapes=torch.tensor([[H, W]] * T), level_start=torch.arange(T) * S + start, loc=loc, aw=aw,
+               grad_out=torch.randn(2, 196, 256, generator=g))
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, "temporal")
+
+
+def test_empty_and_degenerate():
+    from mdqe_cvpr2023_b200 import ops
+    inp = to_cuda(make_inputs(2, [(4, 4)], 8, 32, 4, Lq=0, seed=9))
+    out = ops.ms_deform_attn_forward(inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["aw"], 64)
+    assert tuple(out.shape) == (2, 0, 256)
+    gv, gl, ga = ops.ms_deform_attn_backward(inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["aw"],
+                                             inp["grad_out"], 64)
+    assert float(gv.abs().max()) == 0.0 and gl.numel() == 0 and ga.numel() == 0
+    # NaN / inf locations are skipped like in the reference CUDA kernel (comparisons are false)
+    inp = to_cuda(make_inputs(1, [(4, 4)], 8, 32, 4, Lq=5, seed=10))
+    inp["loc"][0, 0] = float("nan")
+    inp["loc"][0, 1] = float("inf")
+    out = ops.ms_deform_attn_forward(inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["aw"], 64)
+    assert float(out[0, :2].abs().max()) == 0.0 and bool(torch.isfinite(out).all())
+
+
+def test_error_behaviour_matches_reference():
+    from mdqe_cvpr2023_b200 import ops
+    cpu = make_inputs(2, [(4, 4)], 8, 32, 4, Lq=3, seed=11)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        ops.ms_deform_attn_forward(cpu["value"], cpu["shapes"], cpu["level_start"], cpu["loc"], cpu["aw"], 64)
+    inp = to_cuda(cpu)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        ops.ms_deform_attn_forward(inp["value"].transpose(0, 1), inp["shapes"], inp["level_start"], inp["loc"], inp["aw"], 64)
+    inp3 = to_cuda(make_inputs(3, [(4, 4)], 8, 32, 4, Lq=3, seed=11))
+    with pytest.raises(RuntimeError, match="must divide im2col_step"):      # ms_deform_attn_cuda.cu:50-52
+        ops.ms_deform_attn_forward(inp3["value"], inp3["shapes"], inp3["level_start"], inp3["loc"], inp3["aw"], 2)
+    with pytest.raises(RuntimeError):
+        ops.ms_deform_attn_forward(inp["value"].half(), inp["shapes"], inp["level_start"], inp["loc"], inp["aw"], 64)
+
+
+@pytest.mark.parametrize("D", [30, 32, 64, 71, 1025])
+def test_gradcheck_double_reference_sweep(D):
+    """ops/test.py:63-86 check_gradient_numerical on the reference fixture (D list minus the two largest)."""
+    from mdqe_cvpr2023_b200 import MSDeformAttnFunction
+    N, M, Lq, L, P = 1, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long).cuda()
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = 30
+    torch.manual_seed(3)
+    value = (torch.rand(N, S, M, D) * 0.01).double().cuda().requires_grad_(True)
+    loc = torch.rand(N, Lq, M, L, P, 2).double().cuda().requires_grad_(True)
+    aw = torch.rand(N, Lq, M, L, P) + 1e-5
+    aw = (aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)).double().cuda().requires_grad_(True)
+    assert torch.autograd.gradcheck(MSDeformAttnFunction.apply, (value, shapes, lsi, loc, aw, 2))
+
+
+def test_autograd_function_and_autocast():
+    from mdqe_cvpr2023_b200 import MSDeformAttnFunction
+    inp = make_inputs(2, [(12, 20), (6, 10)], 8, 32, 4, Lq=40, dist="wide", seed=12)
+    want = oracle_all(inp)
+    d = to_cuda(inp)
+    v, l, a = d["value"].requires_grad_(True), d["loc"].requires_grad_(True), d["aw"].requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = MSDeformAttnFunction.apply(v.bfloat16(), d["shapes"], d["level_start"], l, a, 64)   # cast back to fp32
+    assert out.dtype == torch.float32
+    out2 = MSDeformAttnFunction.apply(v, d["shapes"], d["level_start"], l, a, 64)
+    out2.backward(d["grad_out"])
+    check((out2, v.grad, l.grad, a.grad), want, 2e-5, "autograd")
+
+
+def test_full_size_properties_r50_720():
+    """BASELINE configs[2] size (N=4, S=Lq=15300): size-independent identities instead of the oracle.
+    out is linear in value and in aw  =>  <grad_value, value> = <grad_aw, aw> = <out, grad_out>."""
+    inp = to_cuda(make_inputs(4, R50_720, 8, 32, 4, dist="local", seed=13))
+    out, gv, gl, ga = run_op(inp)
+    ref = (out.double() * inp["grad_out"].double()).sum()
+    assert abs(float((gv.double() * inp["value"].double()).sum() / ref) - 1) < 1e-4
+    assert abs(float((ga.double() * inp["aw"].double()).sum() / ref) - 1) < 1e-4
+    inp2 = dict(inp)
+    inp2["value"] = inp["value"] * 2.5
+    out2 = run_op(inp2)[0]
+    assert nerr(out2, out * 2.5) < 1e-6
+    ones = dict(inp)
+    ones["value"] = torch.ones_like(inp["value"])
+    ones["loc"] = inp["loc"].clamp(0.2, 0.8)                 # every corner in range -> out = sum(aw) = 1
+    assert nerr(run_op(ones)[0], torch.ones_like(out)) < 1e-5
+    # determinism of everything but the atomically accumulated grad_value
+    again = run_op(inp)
+    assert torch.equal(again[0], out) and torch.equal(again[2], gl) and torch.equal(again[3], ga)
+    assert nerr(again[1], gv) < 1e-5
+
+
+def test_cuda_graph_capture_replay():
+    from mdqe_cvpr2023_b200 import ops
+    inp = to_cuda(make_inputs(2, R50_360, 8, 32, 4, Lq=196, dist="local", seed=14))
+    eager = run_op(inp)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            run_op(inp)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = ops.ms_deform_attn_forward(inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["aw"], 64)
+        grads = ops.ms_deform_attn_backward(inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["aw"],
+                                            inp["grad_out"], 64)
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager[0]) and torch.equal(grads[1], eager[2])
+    assert nerr(grads[0], eager[1]) < 1e-5
+
+
+def test_host_buffer_entry():
+    import ctypes
+    from mdqe_cvpr2023_b200 import _lib
+    inp = make_inputs(2, [(12, 20), (6, 10)], 8, 32, 4, Lq=40, dist="wide", seed=15)
+    want = oracle_all(inp)
+    lib = _lib.load()
+    pin = {k: v.contiguous().pin_memory() for k, v in inp.items()}
+    N, S, M, D = inp["value"].shape
+    Lq, L, P = 40, 2, 4
+    out = torch.empty(N, Lq, M * D).pin_memory()
+    _lib.check(lib.msda_forward_host(0, _lib.MSDA_F32, pin["value"].data_ptr(), pin["shapes"].data_ptr(),
+                                     pin["level_start"].data_ptr(), pin["loc"].data_ptr(), pin["aw"].data_ptr(),
+                                     N, S, M, D, L, Lq, P, out.data_ptr()), "msda_forward_host")
+    gv, gl, ga = torch.empty_like(pin["value"]), torch.empty_like(pin["loc"]), torch.empty_like(pin["aw"])
+    _lib.check(lib.msda_backward_host(0, _lib.MSDA_F32, pin["value"].data_ptr(), pin["shapes"].data_ptr(),
+                                      pin["level_start"].data_ptr(), pin["loc"].data_ptr(), pin["aw"].data_ptr(),
+                                      pin["grad_out"].data_ptr(), N, S, M, D, L, Lq, P, gv.data_ptr(), gl.data_ptr(),
+                                      ga.data_ptr()), "msda_backward_host")
+    check((out, gv, gl, ga), want, 2e-5, "host entry")
+    lib.msda_host_arena_release()
+
+
+def test_launch_counter_counts_kernels():
+    from mdqe_cvpr2023_b200 import _lib
+    inp = to_cuda(make_inputs(1, [(8, 8)], 8, 32, 4, Lq=8, seed=16))
+    _lib.launch_count_reset()
+    run_op(inp)
+    assert _lib.launch_count() == 2

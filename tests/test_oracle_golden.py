@@ -80,3 +80,16 @@ def test_empty_query_set():
     shapes = np.array([[2, 2]], dtype=np.int64)
     out = O.msda_forward(np.ones((1, 4, 1, 4)), shapes, np.zeros((1, 0, 1, 1, 1, 2)), np.zeros((1, 0, 1, 1, 1)))
     assert out.shape == (1, 0, 4)
+
+
+@pytest.mark.parametrize("name", [n for n in CORE if n.endswith("f32")] + ["edge_coords_f64"])
+def test_torch_port_against_reference_python(name):
+    """oracle/torch_port.py (the CPU baseline bench.py times) reproduces the reference's function."""
+    import torch
+    from oracle import torch_port as TP
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    t = {k: torch.from_numpy(z[k]) for k in ("value", "shapes", "level_start", "loc", "aw", "grad_out")}
+    out, gv, gl, ga = TP.msda_fwd_bwd_torch(t["value"], t["shapes"], t["loc"], t["aw"], t["grad_out"], t["level_start"])
+    tol = 1e-12 if z["value"].dtype == np.float64 else 1e-6
+    for got, key in ((out, "out"), (gv, "grad_value"), (gl, "grad_loc"), (ga, "grad_aw")):
+        assert nerr(got.numpy(), z[key]) <= tol, key

@@ -1,0 +1,20 @@
+#!/bin/bash
+# One GPU session: parity tests, smoke, bench, kernel sweep, ncu launch list + full capture.
+# Usage (from the repo root on the GPU box):  bash tools/gpu_round.sh [tag]
+TAG=${1:-r01}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi_${TAG}.txt 2>&1
+echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q --maxfail=30 -x > gpurun_out/pytest_gpu_${TAG}.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu_${TAG}.log
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_${TAG}.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke_${TAG}.log
+echo "== bench local"; timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/bench_${TAG}.json; tail -5 gpurun_out/bench_${TAG}.err
+echo "== bench uniform"; timeout 600 python bench.py --steps 20 --warmup 3 --dist uniform --no-e2e --no-cpu-baseline > gpurun_out/bench_uniform_${TAG}.json 2>> gpurun_out/bench_${TAG}.err; tail -c 1500 gpurun_out/bench_uniform_${TAG}.json
+echo "== kernel sweep"; timeout 900 python tools/kernel_bench.py --iters 15 > gpurun_out/kernel_bench_${TAG}.log 2>&1; echo "sweep rc=$?"; tail -3 gpurun_out/kernel_bench_${TAG}.log
+echo "== ncu launch list"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_${TAG}.csv \
+    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph > gpurun_out/ncu_launch_${TAG}.log 2>&1; echo "ncu list rc=$?"
+echo "== ncu full (bwd, fwd)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:msda_bwd_fast -c 2 -f -o gpurun_out/prof_bwd_${TAG} \
+    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph --layers 1 > gpurun_out/ncu_bwd_${TAG}.log 2>&1; echo "ncu bwd rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:msda_fwd_fast -c 2 -f -o gpurun_out/prof_fwd_${TAG} \
+    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph --layers 1 > gpurun_out/ncu_fwd_${TAG}.log 2>&1; echo "ncu fwd rc=$?"
+ls -la gpurun_out | tail -20
