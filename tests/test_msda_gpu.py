@@ -47,7 +47,22 @@ def test_golden_fixtures(name):
     inp = {k: torch.from_numpy(z[k]).cuda() for k in ("value", "shapes", "level_start", "loc", "aw", "grad_out")}
     tol = 1e-10 if z["value"].dtype == np.float64 else 2e-5
     got = run_op(inp)
-    check(got, (z["out"], z["grad_value"], z["grad_loc"], z["grad_aw"]), tol, name)
+    want = [z["out"], z["grad_value"], z["grad_loc"].copy(), z["grad_aw"]]
+    if name.startswith("edge_coords"):
+        # grad_sampling_loc is discontinuous where a sample sits exactly on a pixel centre; there the
+        # reference's two code paths themselves disagree (grid_sample unnormalises ((g+1)*W-1)/2, the CUDA
+        # kernel loc*W-0.5, ms_deform_im2col_cuda.cuh:285-286: last-bit differences pick different cells).
+        # Compare grad_loc only away from those kinks (SURVEY 8c "measure-zero set").
+        H, W = (int(v) for v in z["shapes"][0])
+        px, py = z["loc"][..., 0] * W - 0.5, z["loc"][..., 1] * H - 0.5
+        kink = (np.abs(px - np.round(px)) < 1e-9) | (np.abs(py - np.round(py)) < 1e-9)
+        got = list(got)
+        gl = got[2].clone()
+        gl[torch.from_numpy(kink).to(gl.device)] = 0
+        got[2] = gl
+        want[2][kink] = 0
+        assert kink.any() and (~kink).any()
+    check(got, want, tol, name)
     if name.startswith("ref_fixture") and z["value"].dtype == np.float32:
         assert torch.allclose(got[0].cpu(), torch.from_numpy(z["out"]), rtol=1e-2, atol=1e-3)   # ops/test.py:56
 
