@@ -1,9 +1,74 @@
 // Mask contraction dispatch: out[b,q,n] = sum_k coeff[b,q,k] * proto[b,k,n] and its gradients.
 // See include/msda_b200.h (mask_logits_*) for the contract.
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
 #include "mask_simt.cuh"
+#include "mask_tc.cuh"
 #include "msda_internal.h"
 
 namespace msda {
+
+// ------------------------------------------------------------------------------ tcgen05 / TMA path
+// cuTensorMapEncodeTiled is a driver-API entry; it is resolved through the runtime so that the library
+// does not link against libcuda (and still loads on a box without a driver, e.g. for the CPU-side tests).
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// bf16 tensor [d2, d1, d0] (d0 contiguous) -> 3-D tiled map with a {64, box1, 1} box and 128B swizzle.
+static int make_map_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
+  if (!enc) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  const cuuint32_t box[3] = {64, box1, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+  return 0;
+}
+
+static bool mask_tc_eligible(int in_dtype, const void* coeff, const void* proto, int Q, int K, int64_t Ncols) {
+  if (in_dtype != MSDA_BF16) return false;
+  if (K < 8 || K > 64 || K % 8 != 0) return false;                     // 16-byte global strides, <= 4 K steps
+  if (Q < 1 || Q > 256) return false;                                  // one MMA N extent / TMEM allocation
+  if (Ncols % 8 != 0 || Ncols >= (int64_t(1) << 31)) return false;
+  return ((reinterpret_cast<uintptr_t>(coeff) | reinterpret_cast<uintptr_t>(proto)) & 15u) == 0;
+}
+
+template <typename OT>
+static int launch_mask_tc(cudaStream_t st, const void* coeff, const void* proto, void* out, int B, int Q, int K,
+                          int64_t Ncols) {
+  const int KP = (K + 15) / 16 * 16, QP = (Q + 15) / 16 * 16;
+  int tmem_cols = 32;
+  while (tmem_cols < QP) tmem_cols *= 2;
+  CUtensorMap map_proto, map_coeff;
+  if (int rc = make_map_bf16(&map_proto, proto, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, (uint32_t)KP)) return rc;
+  if (int rc = make_map_bf16(&map_coeff, coeff, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QP)) return rc;
+  const size_t smem = mask_tc_smem_bytes(KP, QP);
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(mask_fwd_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(mask_fwd_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  });
+  const dim3 grid(static_cast<unsigned>((Ncols + kTcTileN - 1) / kTcTileN), B);
+  ProfScope prof(st, MSDA_PROF_MASK_FWD, (int64_t)B * Q * Ncols);
+  mask_fwd_tc_kernel<OT><<<grid, kTcThreads, smem, st>>>(map_proto, map_coeff, static_cast<OT*>(out), Q, Ncols, KP, QP, tmem_cols);
+  return after_launch("mask_fwd_tc_kernel");
+}
 
 template <typename IT, typename OT>
 static int launch_mask_simt(cudaStream_t st, const void* coeff, const void* proto, void* out, int B, int Q, int K,
@@ -19,6 +84,14 @@ static int launch_mask_simt(cudaStream_t st, const void* coeff, const void* prot
 int mask_forward_dispatch(cudaStream_t st, int in_dtype, int out_dtype, const void* coeff, const void* proto, int B,
                           int Q, int K, int64_t Ncols, void* out) {
   if (B > 65535) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: B=%d > 65535", B);
+  const int variant = option("mask_variant");
+  const bool tc_ok = mask_tc_eligible(in_dtype, coeff, proto, Q, K, Ncols);
+  if (variant == 2 && !tc_ok)
+    return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: tcgen05 path needs bf16 inputs, K %% 8 == 0, K <= 64, Q <= 256, Ncols %% 8 == 0");
+  if (variant != 1 && tc_ok) {
+    if (out_dtype == MSDA_F32) return launch_mask_tc<float>(st, coeff, proto, out, B, Q, K, Ncols);
+    return launch_mask_tc<__nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
+  }
   if (in_dtype == MSDA_F32 && out_dtype == MSDA_F32) return launch_mask_simt<float, float>(st, coeff, proto, out, B, Q, K, Ncols);
   if (in_dtype == MSDA_F32 && out_dtype == MSDA_BF16) return launch_mask_simt<float, __nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
   if (in_dtype == MSDA_BF16 && out_dtype == MSDA_F32) return launch_mask_simt<__nv_bfloat16, float>(st, coeff, proto, out, B, Q, K, Ncols);

@@ -1,0 +1,189 @@
+// Tensor-core mask contraction for sm_100a: tcgen05.mma with the accumulator in TMEM, operands staged
+// by TMA (cp.async.bulk.tensor) into 128B-swizzled shared memory.
+//
+//   out[b, q, n] = sum_k coeff[b, q, k] * proto[b, k, n]          (einsum 'bqm,bmthw->bqthw',
+//   /root/reference/mdqe/models/matcher.py:182, criterion.py:440, transformer_dec.py:255, mdqe/mdqe.py:384)
+//
+// Shape of the problem: K = hidden_dim/8 = 32 (24 for Swin-L), Q ~ 200, N = T*H/4*W/4 ~ 6e4..2e5.  The
+// contraction is bound by WRITING the Q x N result (arithmetic intensity ~14-28 flop/B), so the design
+// goal is an epilogue that streams TMEM -> registers -> fully coalesced global stores, with the
+// tensor-core work (2 MMA instructions per tile) and the TMA loads hidden under it.
+//
+// Mapping (one 128-column tile of the plane per CTA, 2-3 CTAs resident per SM overlap each other):
+//   MMA M (128 TMEM lanes) = 128 consecutive plane columns n      A = proto tile, MN-major (n contiguous)
+//   MMA N (TMEM columns)   = the queries, padded to 16            B = coeff, K-major (k contiguous)
+//   MMA K                  = K padded to 16 (TMA zero-fills the padding)
+// so that in the epilogue lane i of a warp owns plane column n0+i and a warp-wide store of one query row
+// is one contiguous 128-byte (fp32) segment of `out`.
+//
+// Shared-memory operand layouts are the canonical UMMA 128B-swizzle layouts, produced directly by TMA
+// with CU_TENSOR_MAP_SWIZZLE_128B:
+//   A (MN-major): per 64-column half a box of KP rows x 128 B; 8-row groups 1024 B apart (SBO), the two
+//                 halves KP*128 B apart (LBO); a K step of 16 advances the start address by 2048 B.
+//   B (K-major) : rows (queries) of 128 B = 64 k-slots of which KP are used; 8-row groups 1024 B apart
+//                 (SBO); a K step of 16 advances the start address by 32 B inside the swizzle atom.
+#pragma once
+
+#include <cuda.h>
+
+#include "msda_common.cuh"
+
+namespace msda {
+
+constexpr int kTcTileN = 128;        // plane columns per CTA (= MMA M)
+constexpr int kTcThreads = 128;      // 4 warps: warp w drains TMEM lanes 32w..32w+31
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// UMMA shared-memory descriptor, 128B swizzle (layout type 2), descriptor version 1 (Blackwell).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);                 // start address, bits [0,14)
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;            // leading byte offset, bits [16,30)
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;            // stride byte offset, bits [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                                     // version = 1
+  d |= static_cast<uint64_t>(2) << 61;                                     // SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: D = fp32, A = B = bf16, A MN-major, B K-major, M = 128, N = n.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_m128(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (0u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <typename OT>
+__device__ __forceinline__ void mask_store(OT* p, float v);
+template <> __device__ __forceinline__ void mask_store<float>(float* p, float v) { __stcs(p, v); }
+template <> __device__ __forceinline__ void mask_store<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// grid (ceil(Ncols/128), B); block 128 threads; dynamic smem: see mask_tc_smem_bytes().
+//   KP     K rounded up to 16 (<= 64)          QP  Q rounded up to 16 (<= 256)
+//   tmem_cols  power of two >= max(32, QP)
+template <typename OT>
+__global__ void __launch_bounds__(kTcThreads)
+mask_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_constant__ CUtensorMap map_coeff,
+                   OT* __restrict__ out, int Q, int64_t Ncols, int KP, int QP, int tmem_cols) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte aligned operand tiles (required by the 128B swizzle pattern)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes_half = static_cast<uint32_t>(KP) * 128u;          // one 64-column half of the proto tile
+  uint8_t* sA = smem;                                                      // 2 halves
+  uint8_t* sB = smem + 2 * a_bytes_half;                                   // QP rows x 128 B (2*KP*128 is a multiple of 1024)
+  __shared__ __align__(8) uint64_t bars[2];                                // [0] operands landed, [1] accumulator ready
+  __shared__ uint32_t s_tmem_base;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * kTcTileN;
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_acc = smem_u32(&bars[1]);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_full, 1);
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_proto) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_coeff) : "memory");
+  }
+  if (warp == 0) {                                                         // one warp owns TMEM allocation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (threadIdx.x == 0) {
+    // ---- TMA: both halves of the proto tile + the coefficient block, one transaction barrier
+    const uint32_t tx = 2 * a_bytes_half + static_cast<uint32_t>(QP) * 128u;
+    mbar_expect_tx(bar_full, tx);
+    tma_load_3d(smem_u32(sA), &map_proto, bar_full, static_cast<int>(n0), 0, b);
+    tma_load_3d(smem_u32(sA + a_bytes_half), &map_proto, bar_full, static_cast<int>(n0) + 64, 0, b);
+    tma_load_3d(smem_u32(sB), &map_coeff, bar_full, 0, 0, b);
+    // ---- MMA: KP/16 instructions of 128 x QP x 16, issued by this one thread
+    mbar_wait(bar_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(QP));
+    const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+    for (int ks = 0; ks < KP / 16; ++ks) {
+      const uint64_t a_desc = umma_desc_sw128(a_addr + ks * 2048u, /*lbo=*/a_bytes_half, /*sbo=*/1024u);
+      const uint64_t b_desc = umma_desc_sw128(b_addr + ks * 32u, /*lbo=*/16u, /*sbo=*/1024u);
+      umma_bf16(tmem_base, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
+    }
+    // arrives on bar_acc when the MMAs above have completed (implies fence::before_thread_sync)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_acc) : "memory");
+  }
+  __syncwarp();
+
+  // ---- epilogue: every warp drains its 32 lanes; lane i <-> plane column n0 + 32*warp + i
+  mbar_wait(bar_acc, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int64_t col = n0 + warp * 32 + lane;
+  const bool col_ok = col < Ncols;
+  OT* orow = out + static_cast<int64_t>(b) * Q * Ncols + col;
+  const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  for (int q0 = 0; q0 < Q; q0 += 32) {
+    float v[32];
+    tmem_ld32(lane_base + static_cast<uint32_t>(q0), v);
+    if (col_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (q0 + j < Q) mask_store<OT>(orow + static_cast<int64_t>(q0 + j) * Ncols, v[j]);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+}
+
+inline size_t mask_tc_smem_bytes(int KP, int QP) { return 1024 + 2 * static_cast<size_t>(KP) * 128 + static_cast<size_t>(QP) * 128; }
+
+}  // namespace msda

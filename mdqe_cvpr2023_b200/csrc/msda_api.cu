@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "msda_fast.cuh"
+#include "msda_fast2.cuh"
 #include "msda_generic.cuh"
 #include "msda_internal.h"
 
@@ -38,8 +39,8 @@ int after_launch(const char* kernel_name) {
 }
 
 struct Options {
-  std::atomic<int> fwd_variant{0};    // 0 = auto (fast when eligible), 1 = force generic
-  std::atomic<int> bwd_variant{0};    // 0 = auto, 1 = force generic
+  std::atomic<int> fwd_variant{0};    // 0 = auto (fast2 / fast when eligible), 1 = force generic, 2 = first-generation fast
+  std::atomic<int> bwd_variant{0};    // same
   std::atomic<int> chunk_pairs{0};    // 0 = auto
   std::atomic<int> mask_variant{0};   // 0 = auto (tcgen05 when eligible), 1 = SIMT fp32, 2 = force tcgen05
   std::atomic<int> profile{0};        // 1 = bracket the main kernels with CUDA events (msda_profile_read)
@@ -108,6 +109,7 @@ static bool fast_eligible(int dtype, const Problem& pb, const void* a, const voi
   if (pb.D != 32 && pb.D != 24) return false;
   if (pb.L > kMaxLevels || pb.L * pb.P > 32) return false;
   if ((int64_t)pb.N * pb.S * pb.M * pb.D >= (int64_t(1) << 31)) return false;   // 32-bit row offsets
+  if (pb.n_pairs >= (int64_t(1) << 31) / 64) return false;                        // 32-bit pair / sample indices
   return aligned16(a) && aligned16(b) && aligned16(c);
 }
 
@@ -125,6 +127,43 @@ static int pick_chunk(const Problem& pb) {
   return chunk < unit ? unit : chunk;
 }
 
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{d, 0u, 0u};
+  if (d <= 1) return f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;                                   // ceil(log2 d)
+  const unsigned p = 31 + l;
+  f.mul = static_cast<uint32_t>(((1ull << p) + d - 1) / d);
+  f.shr = p - 32;
+  return f;
+}
+
+static bool fast2_lp(int lp) { return lp == 16 || lp == 12 || lp == 8; }
+
+template <typename VT, typename LT, int D>
+static void launch_fwd2_lp(cudaStream_t st, const Problem& pb, unsigned grid, int chunk, const VT* v, const int64_t* shapes,
+                           const int64_t* lsi, const LT* lc, const LT* a, VT* o) {
+  const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
+  const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
+  switch (pb.L * pb.P) {
+    case 16: msda_fwd_fast2_kernel<VT, LT, D, 16><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
+    case 12: msda_fwd_fast2_kernel<VT, LT, D, 12><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
+    default: msda_fwd_fast2_kernel<VT, LT, D, 8><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
+  }
+}
+
+template <typename VT, typename LT, int D>
+static void launch_bwd2_lp(cudaStream_t st, const Problem& pb, unsigned grid, int chunk, const VT* v, const int64_t* shapes,
+                           const int64_t* lsi, const LT* lc, const LT* a, const VT* go, float* gv, LT* gl, LT* ga) {
+  const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
+  const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
+  switch (pb.L * pb.P) {
+    case 16: msda_bwd_fast2_kernel<VT, LT, D, 16><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
+    case 12: msda_bwd_fast2_kernel<VT, LT, D, 12><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
+    default: msda_bwd_fast2_kernel<VT, LT, D, 8><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
+  }
+}
+
 template <typename VT, typename LT>
 static int launch_fwd(cudaStream_t st, const Problem& pb, bool fast, const void* value, const int64_t* shapes,
                       const int64_t* lsi, const void* loc, const void* aw, void* out) {
@@ -137,6 +176,11 @@ static int launch_fwd(cudaStream_t st, const Problem& pb, bool fast, const void*
     if (fast) {
       const int chunk = pick_chunk(pb);
       const unsigned grid = static_cast<unsigned>((pb.n_pairs + chunk - 1) / chunk);
+      if (g_opt.fwd_variant.load() != 2 && fast2_lp(pb.L * pb.P)) {
+        if (pb.D == 32) launch_fwd2_lp<VT, LT, 32>(st, pb, grid, chunk, v, shapes, lsi, lc, a, o);
+        else launch_fwd2_lp<VT, LT, 24>(st, pb, grid, chunk, v, shapes, lsi, lc, a, o);
+        return after_launch("msda_fwd_fast2_kernel");
+      }
       if (pb.D == 32)
         msda_fwd_fast_kernel<VT, LT, 32><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.Lq, pb.P, pb.n_pairs, chunk);
       else
@@ -165,6 +209,11 @@ static int launch_bwd(cudaStream_t st, const Problem& pb, bool fast, const void*
     if (fast) {
       const int chunk = pick_chunk(pb);
       const unsigned grid = static_cast<unsigned>((pb.n_pairs + chunk - 1) / chunk);
+      if (g_opt.bwd_variant.load() != 2 && fast2_lp(pb.L * pb.P)) {
+        if (pb.D == 32) launch_bwd2_lp<VT, LT, 32>(st, pb, grid, chunk, v, shapes, lsi, lc, a, go, gv_acc, gl, ga);
+        else launch_bwd2_lp<VT, LT, 24>(st, pb, grid, chunk, v, shapes, lsi, lc, a, go, gv_acc, gl, ga);
+        return after_launch("msda_bwd_fast2_kernel");
+      }
       if (pb.D == 32)
         msda_bwd_fast_kernel<VT, LT, 32><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, go, gv_acc, gl, ga, pb.S, pb.M, pb.L, pb.Lq, pb.P, pb.n_pairs, chunk);
       else

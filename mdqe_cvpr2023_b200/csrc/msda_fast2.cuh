@@ -1,0 +1,244 @@
+// Second-generation fast kernels: same decomposition as msda_fast.cuh (one warp per (n,q,m) pair, one
+// lane group per bilinear corner, 16-byte channel vectors) with the instruction overhead removed.
+// ncu on the first generation showed the forward to be ISSUE bound (75 % issue-active, 468 warp
+// instructions per pair, only ~130 of them loads/FMAs; profiles/r01a_summary.md).  Changes:
+//   * L*P is a template parameter (8, 12, 16: every MDQE call), the corner loop is fully unrolled and
+//     its shared-memory addresses are immediates;
+//   * slot records hold the row offset in 16-byte units, so an address is ONE 32x32->64 multiply-add;
+//     they are stored corner-major so one LDS.128 fetches the records of two consecutive iterations;
+//   * (n, m) of a pair come from multiply-shift division by host-computed magic numbers instead of
+//     two 64-bit divisions;
+//   * backward dot partials go to a transposed, padded tile [lane][sample] (conflict-free, immediate
+//     offsets) and phase 3 folds them per corner.
+#pragma once
+
+#include "msda_fast.cuh"
+
+namespace msda {
+
+struct FastDiv {              // q = x / d for 0 <= x < 2^31 (host: make_fastdiv)
+  uint32_t d, mul, shr;
+};
+__device__ __forceinline__ uint32_t fd_div(uint32_t x, const FastDiv f) {
+  return f.d == 1 ? x : (__umulhi(x, f.mul) >> f.shr);
+}
+
+template <typename VT, int D, int LP>
+struct Cfg2 : FastCfg<VT, D> {
+  using B = FastCfg<VT, D>;
+  static constexpr int NSG = B::NG / 4;              // sample groups (1 for fp32, 2 for bf16)
+  static constexpr int SPG = LP / NSG;               // samples each lane group walks per pair
+  static constexpr int QPW = 32 / LP;                // pairs prepared per warp round
+  static constexpr int LPP = LP + 2;                 // corner stride in records: +16 B so that the four corner
+                                                     // streams sit in different banks (one LDS.128 wavefront)
+  static constexpr int NSLOT = 4 * LPP;              // slot records per pair (incl. padding)
+  static constexpr int D16 = D / B::CPL;             // 16-byte units per channel row
+  static constexpr bool kAllLanes = (B::G * B::NG == 32);
+  static_assert(LP % NSG == 0 && SPG % 2 == 0, "sample groups must split L*P evenly");
+};
+
+// value pointer + slot offset -> address of this lane's 16-byte channel vector
+template <typename VT>
+__device__ __forceinline__ const VT* row_ptr(const VT* base, uint32_t off16) {
+  return reinterpret_cast<const VT*>(reinterpret_cast<const char*>(base) + static_cast<uint64_t>(off16) * 16u);
+}
+
+// Phase 1 for one sample (lane): slot records in corner-major order.
+//   dst[corner * LPP + s] = {off16, weight};  invalid corners: off16 = kInvalidOff, weight = 0.
+template <int D16, int LPP>
+__device__ __forceinline__ SampleGeom make_slots2(Slot* dst, int s, float locx, float locy, float a, const LevelInfo li,
+                                                  uint32_t n, uint32_t m, int S, int M) {
+  const SampleGeom g = sample_geom(locx, locy, li.H, li.W);
+  const uint32_t row = static_cast<uint32_t>(M) * D16;
+  const uint32_t base = (n * static_cast<uint32_t>(S) + li.start) * row + m * D16;
+  const uint32_t o00 = base + static_cast<uint32_t>(g.y0 * li.W + g.x0) * row;
+  const uint32_t o10 = o00 + static_cast<uint32_t>(li.W) * row;
+  const float hx = 1.f - g.lx, hy = 1.f - g.ly;
+  const bool v00 = g.oky0 && g.okx0, v01 = g.oky0 && g.okx1, v10 = g.oky1 && g.okx0, v11 = g.oky1 && g.okx1;
+  Slot e;
+  e.off = v00 ? o00 : kInvalidOff;        e.w = v00 ? hx * hy * a : 0.f;      dst[0 * LPP + s] = e;
+  e.off = v01 ? o00 + row : kInvalidOff;  e.w = v01 ? g.lx * hy * a : 0.f;    dst[1 * LPP + s] = e;
+  e.off = v10 ? o10 : kInvalidOff;        e.w = v10 ? hx * g.ly * a : 0.f;    dst[2 * LPP + s] = e;
+  e.off = v11 ? o10 + row : kInvalidOff;  e.w = v11 ? g.lx * g.ly * a : 0.f;  dst[3 * LPP + s] = e;
+  return g;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+template <typename VT, typename LT, int D, int LP>
+__global__ void __launch_bounds__(kThreads)
+msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                      const int64_t* __restrict__ level_start, const LT* __restrict__ loc,
+                      const LT* __restrict__ aw, VT* __restrict__ out,
+                      int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq) {
+  using C = Cfg2<VT, D, LP>;
+  __shared__ LevelInfo s_lvl[kMaxLevels];
+  __shared__ __align__(16) Slot s_slot[kWarpsPerCta][C::QPW * C::NSLOT];
+
+  stage_levels(s_lvl, shapes, level_start, L);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane / C::G, c = lane - grp * C::G;
+  const bool active = C::kAllLanes || grp < C::NG;
+  const int corner = grp & 3, sgrp = (grp >> 2) & (C::NSG - 1);
+  Slot* my_slots = s_slot[warp];
+  // this lane's slot stream: records of its corner for samples sgrp*SPG .. +SPG-1 (contiguous)
+  const Slot* my_stream = my_slots + corner * C::LPP + sgrp * C::SPG;
+  const VT* vlane = value + c * C::CPL;
+
+  const uint32_t chunk_begin = blockIdx.x * static_cast<uint32_t>(chunk_pairs);
+  const uint32_t chunk_end = min(n_pairs, chunk_begin + static_cast<uint32_t>(chunk_pairs));
+  const int ps = (lane < C::QPW * LP) ? lane / LP : 0;        // phase-1 role: pair slot and sample of this lane
+  const int ss = lane - ps * LP;
+  const int lvl = ss / P;
+
+  for (uint32_t p0 = chunk_begin + warp * C::QPW; p0 < chunk_end; p0 += kWarpsPerCta * C::QPW) {
+    const int npair = static_cast<int>(min(static_cast<uint32_t>(C::QPW), chunk_end - p0));
+    if (lane < npair * LP) {
+      const uint32_t pair = p0 + ps;
+      const uint32_t nq = fd_div(pair, div_m);
+      const uint32_t m = pair - nq * div_m.d;
+      const uint32_t n = fd_div(pair, div_mq);
+      float x, y, a;
+      load_loc_aw<LT>(loc, aw, static_cast<int64_t>(p0) * LP + lane, x, y, a);
+      make_slots2<C::D16, C::LPP>(my_slots + ps * C::NSLOT, ss, x, y, a, s_lvl[lvl], n, m, S, M);
+    }
+    __syncwarp();
+
+#pragma unroll
+    for (int pl = 0; pl < C::QPW; ++pl) {
+      if (pl < npair) {
+        float acc[C::CPL];
+#pragma unroll
+        for (int j = 0; j < C::CPL; ++j) acc[j] = 0.f;
+        const uint4* stream = reinterpret_cast<const uint4*>(my_stream + pl * C::NSLOT);
+#pragma unroll
+        for (int it = 0; it < C::SPG / 2; ++it) {
+          const uint4 two = stream[it];                       // records of two consecutive samples
+          const uint32_t off[2] = {two.x, two.z};
+          const float w[2] = {__uint_as_float(two.y), __uint_as_float(two.w)};
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (active && w[u] != 0.f) {
+              float v[C::CPL];
+              Vec16<VT>::load(row_ptr(vlane, off[u]), v);
+#pragma unroll
+              for (int j = 0; j < C::CPL; ++j) acc[j] = fmaf(w[u], v[j], acc[j]);
+            }
+          }
+        }
+#pragma unroll
+        for (int k = C::NG / 2; k >= 1; k >>= 1) {
+#pragma unroll
+          for (int j = 0; j < C::CPL; ++j) acc[j] += __shfl_down_sync(0xffffffffu, acc[j], k * C::G);
+        }
+        if (lane < C::G) Vec16<VT>::store(out + static_cast<int64_t>(p0 + pl) * D + lane * C::CPL, acc);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ----------------------------------------------------------------------------------------- backward
+template <typename VT, typename LT, int D, int LP>
+__global__ void __launch_bounds__(kThreads)
+msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                      const int64_t* __restrict__ level_start, const LT* __restrict__ loc,
+                      const LT* __restrict__ aw, const VT* __restrict__ grad_out,
+                      float* __restrict__ grad_value, LT* __restrict__ grad_loc, LT* __restrict__ grad_aw,
+                      int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq) {
+  using C = Cfg2<VT, D, LP>;
+  constexpr int kDotStride = 33;                         // [element][sample] tile, padded: conflict-free both ways
+  __shared__ LevelInfo s_lvl[kMaxLevels];
+  __shared__ __align__(16) Slot s_slot[kWarpsPerCta][C::QPW * C::NSLOT];
+  __shared__ float s_dot[kWarpsPerCta][C::ROW * kDotStride];
+
+  stage_levels(s_lvl, shapes, level_start, L);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane / C::G, c = lane - grp * C::G;
+  const bool active = C::kAllLanes || grp < C::NG;
+  const int corner = grp & 3, sgrp = (grp >> 2) & (C::NSG - 1);
+  Slot* my_slots = s_slot[warp];
+  const Slot* my_stream = my_slots + corner * C::LPP + sgrp * C::SPG;
+  const VT* vlane = value + c * C::CPL;
+  float* gvlane = grad_value + c * C::CPL;
+  // dot partial of (element = corner*G + c, sample): written by the corner lanes, read by the sample lanes
+  float* dot_w = s_dot[warp] + (corner * C::G + c) * kDotStride + sgrp * C::SPG;
+  const float* dot_r = s_dot[warp] + lane;
+
+  const uint32_t chunk_begin = blockIdx.x * static_cast<uint32_t>(chunk_pairs);
+  const uint32_t chunk_end = min(n_pairs, chunk_begin + static_cast<uint32_t>(chunk_pairs));
+  const int ps = (lane < C::QPW * LP) ? lane / LP : 0;
+  const int ss = lane - ps * LP;
+  const int lvl = ss / P;
+
+  for (uint32_t p0 = chunk_begin + warp * C::QPW; p0 < chunk_end; p0 += kWarpsPerCta * C::QPW) {
+    const int npair = static_cast<int>(min(static_cast<uint32_t>(C::QPW), chunk_end - p0));
+    const bool has_sample = lane < npair * LP;
+    SampleGeom geo;
+    float a = 0.f;
+    int lvl_h = 0, lvl_w = 0;
+    if (has_sample) {
+      const uint32_t pair = p0 + ps;
+      const uint32_t nq = fd_div(pair, div_m);
+      const uint32_t m = pair - nq * div_m.d;
+      const uint32_t n = fd_div(pair, div_mq);
+      float x, y;
+      load_loc_aw<LT>(loc, aw, static_cast<int64_t>(p0) * LP + lane, x, y, a);
+      const LevelInfo li = s_lvl[lvl];
+      lvl_h = li.H; lvl_w = li.W;
+      geo = make_slots2<C::D16, C::LPP>(my_slots + ps * C::NSLOT, ss, x, y, a, li, n, m, S, M);
+    }
+    __syncwarp();
+
+#pragma unroll
+    for (int pl = 0; pl < C::QPW; ++pl) {
+      if (pl < npair) {
+        float go[C::CPL];
+        Vec16<VT>::load(grad_out + static_cast<int64_t>(p0 + pl) * D + c * C::CPL, go);
+        const uint4* stream = reinterpret_cast<const uint4*>(my_stream + pl * C::NSLOT);
+#pragma unroll
+        for (int it = 0; it < C::SPG / 2; ++it) {
+          const uint4 two = stream[it];
+          const uint32_t off[2] = {two.x, two.z};
+          const float w[2] = {__uint_as_float(two.y), __uint_as_float(two.w)};
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            float dot = 0.f;
+            if (active && off[u] != kInvalidOff) {
+              float v[C::CPL];
+              Vec16<VT>::load(row_ptr(vlane, off[u]), v);
+#pragma unroll
+              for (int j = 0; j < C::CPL; ++j) dot = fmaf(go[j], v[j], dot);
+              float* gv = const_cast<float*>(reinterpret_cast<const float*>(
+                  reinterpret_cast<const char*>(gvlane) + static_cast<uint64_t>(off[u]) * (16u * sizeof(float) / sizeof(VT))));
+#pragma unroll
+              for (int j = 0; j < C::CPL; j += 4)
+                red_add_f32x4(gv + j, w[u] * go[j], w[u] * go[j + 1], w[u] * go[j + 2], w[u] * go[j + 3]);
+            }
+            if (active) dot_w[pl * LP + 2 * it + u] = dot;
+          }
+        }
+      }
+    }
+    __syncwarp();
+
+    if (has_sample) {
+      float dc[4] = {0.f, 0.f, 0.f, 0.f};     // per-corner <grad_out, value row>
+#pragma unroll
+      for (int e = 0; e < C::ROW; ++e) dc[e / C::G] += dot_r[e * kDotStride];
+      const float hx = 1.f - geo.lx, hy = 1.f - geo.ly;
+      const float g_aw = hy * (hx * dc[0] + geo.lx * dc[1]) + geo.ly * (hx * dc[2] + geo.lx * dc[3]);
+      const float g_x = a * static_cast<float>(lvl_w) * (hy * (dc[1] - dc[0]) + geo.ly * (dc[3] - dc[2]));
+      const float g_y = a * static_cast<float>(lvl_h) * (hx * (dc[2] - dc[0]) + geo.lx * (dc[3] - dc[1]));
+      const int64_t si = static_cast<int64_t>(p0) * LP + lane;
+      store_pair(grad_loc + 2 * si, g_x, g_y);
+      st_from_float(grad_aw + si, g_aw);
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace msda

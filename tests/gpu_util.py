@@ -64,3 +64,18 @@ def oracle_all(inp):
 
 def to_cuda(inp):
     return {k: v.cuda() for k, v in inp.items()}
+
+
+def kink_mask(inp, eps=1e-6):
+    """[N,Lq,M,L,P] bool: samples whose pixel coordinate sits (numerically) on a pixel centre line.
+    grad_sampling_loc is discontinuous there and the reference's own two code paths disagree: grid_sample
+    unnormalises ((g+1)*W-1)/2 while the CUDA kernel computes loc*W-0.5 (ms_deform_im2col_cuda.cuh:285-286), so the
+    last bit decides which cell's slope is returned.  Such samples are excluded from grad_loc comparisons."""
+    loc = inp["loc"].detach().float().cpu()
+    shapes = inp["shapes"].cpu()
+    W = shapes[:, 1].view(1, 1, 1, -1, 1).float()
+    H = shapes[:, 0].view(1, 1, 1, -1, 1).float()
+    px, py = loc[..., 0] * W - 0.5, loc[..., 1] * H - 0.5
+    near = lambda t, size: (t - t.round()).abs() < eps * size
+    inside = (px > -1) & (px < W) & (py > -1) & (py < H)
+    return ((near(px, W) | near(py, H)) & inside).numpy()

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.gpu_util import R50_360, R50_720, make_inputs, oracle_all, to_cuda
+from tests.gpu_util import R50_360, R50_720, kink_mask, make_inputs, oracle_all, to_cuda
 from tests.helpers import GOLDEN, load_golden, nerr
 
 pytestmark = pytest.mark.gpu
@@ -34,10 +34,20 @@ def run_op(inp):
     return out, gv, gl, ga
 
 
-def check(got, want, tol, what=""):
+def check(got, want, tol, what="", inp=None):
+    """all four results against the oracle; grad_loc is compared away from pixel-centre kinks (kink_mask)."""
     names = ("out", "grad_value", "grad_loc", "grad_aw")
     for g, w, n in zip(got, want, names):
-        e = nerr(g.float() if g.dtype == torch.bfloat16 else g, np.asarray(w).reshape(tuple(g.shape)))
+        g = g.float() if g.dtype == torch.bfloat16 else g
+        w = np.asarray(w).reshape(tuple(g.shape))
+        if n == "grad_loc" and inp is not None:
+            kink = kink_mask(inp)
+            assert kink.mean() < 2e-3, "kink mask must stay a (numerically) measure-zero exclusion"
+            g = g.detach().cpu().clone()
+            g[torch.from_numpy(kink)] = 0
+            w = w.copy()
+            w[kink] = 0
+        e = nerr(g, w)
         assert e <= tol, f"{what} {n}: normalised max error {e:.3e} > {tol:.1e}"
 
 
@@ -71,26 +81,26 @@ def test_golden_fixtures(name):
 @pytest.mark.parametrize("D", [32, 24])
 def test_encoder_shape_fp32_vs_oracle(dist, D):
     inp = make_inputs(1, R50_360, 8, D, 4, dist=dist, seed=1)
-    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"enc {dist} D{D}")
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"enc {dist} D{D}", inp)
 
 
 @pytest.mark.parametrize("N,Lq", [(3, 196), (4, 50), (1, 1), (2, 7)])
 def test_decoder_shapes_fp32_vs_oracle(N, Lq):
     inp = make_inputs(N, R50_360, 8, 32, 4, Lq=Lq, dist="wide", seed=2)
-    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"dec N{N} Lq{Lq}")
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"dec N{N} Lq{Lq}", inp)
 
 
 @pytest.mark.parametrize("L,P", [(1, 4), (2, 4), (3, 4), (4, 2), (4, 8), (8, 4), (5, 3), (4, 9)])
 def test_level_point_combinations(L, P):
     shapes = [(10 + 3 * i, 7 + 2 * i) for i in range(L)]
     inp = make_inputs(2, shapes, 8, 32, P, Lq=33, dist="wide", seed=3)
-    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"L{L} P{P}")
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"L{L} P{P}", inp)
 
 
 @pytest.mark.parametrize("M,D", [(1, 32), (3, 24), (4, 16), (2, 8), (8, 30), (2, 64), (1, 71), (1, 200)])
 def test_head_configs(M, D):
     inp = make_inputs(2, [(9, 11), (5, 6)], M, D, 4, Lq=21, dist="wide", seed=4)
-    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"M{M} D{D}")
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"M{M} D{D}", inp)
 
 
 @pytest.mark.parametrize("variant", ["fwd_variant", "bwd_variant"])
@@ -98,7 +108,7 @@ def test_generic_kernels_on_fast_shape(variant):
     from mdqe_cvpr2023_b200 import _lib
     _lib.set_option(variant, 1)
     inp = make_inputs(1, R50_360, 8, 32, 4, Lq=300, dist="local", seed=5)
-    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, variant)
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, variant, inp)
 
 
 @pytest.mark.parametrize("chunk", [16, 48, 256])
@@ -106,7 +116,7 @@ def test_chunk_sizes(chunk):
     from mdqe_cvpr2023_b200 import _lib
     _lib.set_option("chunk_pairs", chunk)
     inp = make_inputs(2, [(12, 20), (6, 10), (3, 5), (2, 3)], 8, 32, 4, dist="local", seed=6)
-    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"chunk {chunk}")
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"chunk {chunk}", inp)
 
 
 @pytest.mark.parametrize("loc_dtype", [torch.bfloat16, torch.float32])
@@ -119,7 +129,7 @@ def test_bf16_vs_oracle_on_rounded_inputs(loc_dtype, D):
         inp[k] = inp[k].to(loc_dtype)
     got = run_op(to_cuda(inp))
     assert got[0].dtype == torch.bfloat16 and got[1].dtype == torch.bfloat16 and got[2].dtype == loc_dtype
-    check(got, oracle_all(inp), 2e-2, f"bf16 loc={loc_dtype} D{D}")
+    check(got, oracle_all(inp), 2e-2, f"bf16 loc={loc_dtype} D{D}", inp)
 
 
 def test_temporal_level_start_windows():
@@ -132,7 +142,7 @@ def test_temporal_level_start_windows():
     aw = torch.softmax(torch.randn(2, 196, 8, T * 4, generator=g), -1).view(2, 196, 8, T, 4)
     inp = dict(value=value, shapes=torch.tensor([[H, W]] * T), level_start=torch.arange(T) * S + start, loc=loc, aw=aw,
                grad_out=torch.randn(2, 196, 256, generator=g))
-    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, "temporal")
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, "temporal", inp)
 
 
 def test_empty_and_degenerate():
@@ -193,7 +203,7 @@ def test_autograd_function_and_autocast():
     assert out.dtype == torch.float32
     out2 = MSDeformAttnFunction.apply(v, d["shapes"], d["level_start"], l, a, 64)
     out2.backward(d["grad_out"])
-    check((out2, v.grad, l.grad, a.grad), want, 2e-5, "autograd")
+    check((out2, v.grad, l.grad, a.grad), want, 2e-5, "autograd", inp)
 
 
 def test_full_size_properties_r50_720():
@@ -258,7 +268,7 @@ def test_host_buffer_entry():
                                       pin["level_start"].data_ptr(), pin["loc"].data_ptr(), pin["aw"].data_ptr(),
                                       pin["grad_out"].data_ptr(), N, S, M, D, L, Lq, P, gv.data_ptr(), gl.data_ptr(),
                                       ga.data_ptr()), "msda_backward_host")
-    check((out, gv, gl, ga), want, 2e-5, "host entry")
+    check((out, gv, gl, ga), want, 2e-5, "host entry", inp)
     lib.msda_host_arena_release()
 
 

@@ -1,0 +1,41 @@
+"""Quick correctness + timing probe of the tcgen05 mask kernel (run under `timeout`)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from mdqe_cvpr2023_b200 import _lib, ops
+
+def nerr(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+torch.manual_seed(0)
+for (B, Q, K, T, H, W) in [(1, 16, 32, 1, 8, 16), (1, 196, 32, 4, 96, 160), (2, 100, 24, 2, 96, 160), (1, 256, 64, 1, 16, 24), (1, 7, 8, 1, 5, 8), (1, 300 - 44, 32, 2, 33, 24), (1, 196, 32, 4, 160, 288)]:
+    coeff = torch.tanh(torch.randn(B, Q, K, device="cuda")).bfloat16()
+    proto = torch.randn(B, K, T, H, W, device="cuda").bfloat16()
+    want = torch.einsum("bqm,bmthw->bqthw", coeff.double(), proto.double())
+    for variant in (1, 2):
+        _lib.set_option("mask_variant", variant)
+        for od in (torch.float32, torch.bfloat16):
+            out = ops.mask_logits_forward(coeff, proto, out_dtype=od)
+            torch.cuda.synchronize()
+            print(f"B{B} Q{Q} K{K} N{T*H*W} variant {variant} out {od}: nerr {nerr(out, want):.3e}", flush=True)
+_lib.set_option("mask_variant", 0)
+# timing
+flush = torch.empty(128 * 1024 * 1024, device="cuda")
+coeff = torch.tanh(torch.randn(1, 196, 32, device="cuda")).bfloat16()
+for plane in ((96, 160), (160, 288)):
+    proto = torch.randn(1, 32, 4, *plane, device="cuda").bfloat16()
+    for name, fn in (("tc f32out", lambda: ops.mask_logits_forward(coeff, proto, out_dtype=torch.float32)),
+                     ("tc bf16out", lambda: ops.mask_logits_forward(coeff, proto)),
+                     ("einsum bf16", lambda: torch.einsum("bqm,bmthw->bqthw", coeff, proto))):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(20):
+            flush.fill_(1.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        ts.sort()
+        n = 4 * plane[0] * plane[1]
+        ob = 4 if "f32" in name else 2
+        byts = 2 * (196 * 32 + 32 * n) + ob * 196 * n
+        print(f"plane {plane} {name}: median {ts[10]:.1f} us  -> {byts / ts[10] / 1e3:.0f} GB/s", flush=True)
