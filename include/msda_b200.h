@@ -62,7 +62,7 @@ int msda_abi_version(void);
 const char* msda_last_error(void);
 
 /* Tuning knobs (kernel variant selection used by bench.py / tests); unknown keys fail.
- * Keys: "fwd_variant", "bwd_variant", "chunk_pairs", "mask_variant", "profile". */
+ * Keys: "fwd_variant", "bwd_variant", "chunk_pairs", "mask_variant", "profile", "mask_debug". */
 int msda_set_option(const char* key, int value);
 int msda_get_option(const char* key, int* value);
 
@@ -133,6 +133,11 @@ int msda_host_arena_release(void);
 #define MSDA_PROF_MASK_FWD 2
 #define MSDA_PROF_MASK_BWD 3
 int msda_profile_read(int kind, int64_t min_units, double* total_ms, int64_t* count);
+
+/* Debugging aid for the pipelined tensor-core mask kernel: with option "mask_debug" = 1 CTA 0 records clock64()
+ * stamps for its first 16 work items; this copies the 5 x 16 table (rows: TMA issued, MMA thread starts waiting,
+ * operands landed, epilogue starts, epilogue done) to `host80` (80 values). */
+int msda_debug_read(long long* host80);
 
 /* Number of kernels this library has launched since load / since the last reset (bench.py's
  * gpu_launches claim is read from here). */

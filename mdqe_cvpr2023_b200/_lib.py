@@ -34,6 +34,7 @@ PROTOTYPES = {
     "mask_logits_forward_host": (_c_int, [_c_int, _c_int, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_vp]),
     "msda_host_arena_release": (_c_int, []),
     "msda_profile_read": (_c_int, [_c_int, _c_i64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_c_i64)]),
+    "msda_debug_read": (_c_int, [ctypes.POINTER(ctypes.c_longlong)]),
     "msda_launch_count": (_c_i64, []),
     "msda_launch_count_reset": (None, []),
 }

@@ -49,6 +49,74 @@ static bool mask_tc_eligible(int in_dtype, const void* coeff, const void* proto,
   return ((reinterpret_cast<uintptr_t>(coeff) | reinterpret_cast<uintptr_t>(proto)) & 15u) == 0;
 }
 
+static long long* g_mask_dbg = nullptr;
+// debugging aid: per-item clock64 stamps of CTA 0 (rows: TMA issued, MMA waits, operands landed, epilogue starts, epilogue ends)
+int mask_debug_copy(long long* host80) {
+  if (!g_mask_dbg) return fail(MSDA_ERR_INVALID_ARG, "mask_debug: no debug buffer (set option mask_debug=1 and run the tcgen05 kernel)");
+  return check_cuda(cudaMemcpy(host80, g_mask_dbg, 80 * sizeof(long long), cudaMemcpyDeviceToHost), "cudaMemcpy(mask_debug)");
+}
+
+// Persistent pipelined kernel.  The query range is cut into chunks (multiples of 16 rows, <= 256) so that there
+// are at least ~6 work items per SM: with whole-Q items a 360p clip has only 480 tiles for 148 SMs (3.24 per SM,
+// i.e. a 4-vs-3 imbalance).
+// [d2, d1, d0] tensor of 2- or 4-byte elements, no swizzle, box {128, 32, 1}: the output side of the epilogue.
+static int make_map_out(CUtensorMap* map, void* base, bool bf16, uint64_t d0, uint64_t d1, uint64_t d2) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
+  if (!enc) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const uint64_t es = bf16 ? 2 : 4;
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {d0 * es, d0 * d1 * es};
+  const cuuint32_t box[3] = {kTcTileN, 32, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed (CUresult %d)", static_cast<int>(r));
+  return 0;
+}
+
+template <typename OT>
+static int launch_mask_tc2(cudaStream_t st, const void* coeff, const void* proto, void* out, int B, int Q, int K,
+                           int64_t Ncols) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int KP = (K + 15) / 16 * 16;
+  const int n_tiles_n = static_cast<int>((Ncols + kTcTileN - 1) / kTcTileN);
+  const int64_t tiles = (int64_t)B * n_tiles_n;
+  // query chunks: starts at multiples of 32 (QS), the last chunk takes the remainder
+  int n_qchunks = 1;
+  while (n_qchunks < 4 && tiles * n_qchunks < 6LL * sms && (Q / (n_qchunks + 1)) / 32 * 32 >= 32) ++n_qchunks;
+  int QS = (n_qchunks == 1) ? ((Q + 31) / 32 * 32) : (Q / n_qchunks) / 32 * 32;
+  const int last_rows = Q - (n_qchunks - 1) * QS;
+  const int QN = ((QS > last_rows ? QS : last_rows) + 15) / 16 * 16;
+  if (QN > 256) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: query chunk of %d rows exceeds one MMA", QN);
+  const int64_t n_items = tiles * n_qchunks;
+  if (n_items >= (int64_t(1) << 31)) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: too many tiles");
+  CUtensorMap map_proto, map_coeff, map_out;
+  if (int rc = make_map_bf16(&map_proto, proto, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, (uint32_t)KP)) return rc;
+  if (int rc = make_map_bf16(&map_coeff, coeff, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QN)) return rc;
+  if (int rc = make_map_out(&map_out, out, sizeof(OT) == 2, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B)) return rc;
+  const size_t smem = mask_tc2_smem_bytes(KP, QN, sizeof(OT));
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(mask_fwd_tc2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(mask_fwd_tc2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  });
+  const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);
+  long long* dbg = nullptr;
+  if (option("mask_debug")) {
+    static long long* d_dbg = nullptr;
+    if (!d_dbg) cudaMalloc(&d_dbg, 5 * 16 * sizeof(long long));
+    cudaMemsetAsync(d_dbg, 0, 5 * 16 * sizeof(long long), st);
+    dbg = d_dbg;
+    g_mask_dbg = d_dbg;
+  }
+  ProfScope prof(st, MSDA_PROF_MASK_FWD, (int64_t)B * Q * Ncols);
+  mask_fwd_tc2_kernel<OT><<<grid, kTc2Threads, smem, st>>>(map_proto, map_coeff, map_out, Q, KP, QS, QN, n_qchunks, n_tiles_n,
+                                                          static_cast<int>(n_items), dbg);
+  return after_launch("mask_fwd_tc2_kernel");
+}
+
 template <typename OT>
 static int launch_mask_tc(cudaStream_t st, const void* coeff, const void* proto, void* out, int B, int Q, int K,
                           int64_t Ncols) {
@@ -88,9 +156,13 @@ int mask_forward_dispatch(cudaStream_t st, int in_dtype, int out_dtype, const vo
   const bool tc_ok = mask_tc_eligible(in_dtype, coeff, proto, Q, K, Ncols);
   if (variant == 2 && !tc_ok)
     return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: tcgen05 path needs bf16 inputs, K %% 8 == 0, K <= 64, Q <= 256, Ncols %% 8 == 0");
-  if (variant != 1 && tc_ok) {
+  if (variant == 3 && tc_ok) {                       // 3 = first (one tile per CTA) tensor-core kernel, kept for A/B timing
     if (out_dtype == MSDA_F32) return launch_mask_tc<float>(st, coeff, proto, out, B, Q, K, Ncols);
     return launch_mask_tc<__nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
+  }
+  if (variant != 1 && tc_ok) {
+    if (out_dtype == MSDA_F32) return launch_mask_tc2<float>(st, coeff, proto, out, B, Q, K, Ncols);
+    return launch_mask_tc2<__nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
   }
   if (in_dtype == MSDA_F32 && out_dtype == MSDA_F32) return launch_mask_simt<float, float>(st, coeff, proto, out, B, Q, K, Ncols);
   if (in_dtype == MSDA_F32 && out_dtype == MSDA_BF16) return launch_mask_simt<float, __nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);

@@ -184,6 +184,200 @@ mask_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_c
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
 }
 
+// -------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised version: one CTA per SM walks work items (b, 128-column tile, query chunk);
+// a 4-stage TMA ring feeds the single-thread MMA issuer, two TMEM accumulators (columns 0 and 256) let the
+// tensor core fill one while eight epilogue warps drain the other, so the output stream to HBM never stops.
+//   warp 0      TMA producer (one lane)
+//   warp 1      TMEM allocation + MMA issue (one lane)
+//   warps 2..9  epilogue: warp w drains TMEM lanes 32*(w%4)..+31 (the hardware restricts a warp to the lane
+//               quarter given by its index mod 4); the two warps of a quarter take alternate 32-query blocks
+constexpr int kTc2Stages = 4;
+constexpr int kTc2Threads = 320;
+constexpr int kTc2EpiWarps = 8;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 queries x 32 plane columns of one warp -> global.  Lane i owns plane column `col`.
+__device__ __forceinline__ void mask_store_block(float* out_col, int64_t Ncols, int qn, bool col_ok, int lane, const float (&v)[32]) {
+  if (!col_ok) return;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < qn) __stcs(out_col + static_cast<int64_t>(j) * Ncols, v[j]);
+}
+// bf16: neighbouring lanes trade one value per row pair so that every store is a packed bf16x2 (4 bytes per
+// lane): even lanes write the even rows (columns i, i+1), odd lanes the odd rows (columns i-1, i).
+__device__ __forceinline__ void mask_store_block(__nv_bfloat16* out_col, int64_t Ncols, int qn, bool col_ok, int lane, const float (&v)[32]) {
+  const bool odd = lane & 1;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const float give = odd ? v[j] : v[j + 1];
+    const float got = __shfl_xor_sync(0xffffffffu, give, 1);
+    const int row = j + (odd ? 1 : 0);
+    const __nv_bfloat162 packed = odd ? __floats2bfloat162_rn(got, v[j + 1]) : __floats2bfloat162_rn(v[j], got);
+    // Ncols is even and tiles start at multiples of 128, so the partner column is valid whenever this one is
+    if (col_ok && row < qn)
+      *reinterpret_cast<__nv_bfloat162*>(out_col + static_cast<int64_t>(row) * Ncols - (odd ? 1 : 0)) = packed;
+  }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void st_stage(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_stage(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// Work item = (b, 128-column tile, query chunk qc): rows [qc*QS, qc*QS + rows) with QS a multiple of 32 so that the
+// 32-row output boxes of one item never reach into the next item's rows; the last chunk takes the remainder and
+// TMA clips its final box at Q.  QN = MMA N = rows of the largest chunk rounded up to 16.
+//
+// Epilogue: the first kernel stored straight from registers (one 128-byte row segment per warp instruction) and
+// was limited by the number of stores eight warps can keep in flight (~9 B/clk/SM, clock stamps in
+// profiles/r01e_mask_tc2_timeline.txt).  Here a chunk of 32 query rows x 128 columns is transposed through shared
+// memory and leaves as ONE bulk tensor store, so a few instructions keep tens of KB in flight.
+template <typename OT>
+__global__ void __launch_bounds__(kTc2Threads, 1)
+mask_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_constant__ CUtensorMap map_coeff,
+                    const __grid_constant__ CUtensorMap map_out, int Q, int KP, int QS, int QN, int n_qchunks,
+                    int n_tiles_n, int n_items, long long* __restrict__ dbg) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_half = static_cast<uint32_t>(KP) * 128u;
+  const uint32_t b_bytes = static_cast<uint32_t>(QN) * 128u;
+  const uint32_t stage_bytes = (2 * a_half + b_bytes + 1023u) & ~1023u;
+  constexpr uint32_t kOutBuf = 32u * kTcTileN * sizeof(OT);             // one 32-row x 128-column output box
+  uint8_t* out_stage = smem + kTc2Stages * stage_bytes;                  // [half][2 buffers]
+  __shared__ __align__(8) uint64_t bars[2 * kTc2Stages + 4];
+  __shared__ uint32_t s_tmem_base;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (kTc2Stages + s); };
+  auto bar_tfull = [&](int a) { return bar0 + 8u * (2 * kTc2Stages + a); };
+  auto bar_tempty = [&](int a) { return bar0 + 8u * (2 * kTc2Stages + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTc2Stages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), kTc2EpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_proto) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_coeff) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem_base;
+
+  // items are ordered chunk-major (all tiles of chunk 0, then chunk 1, ...): neighbouring CTAs share `coeff` rows
+  auto decode = [&](int item, int& b, int& tile, int& qc) {
+    const int per_chunk = n_items / n_qchunks;
+    qc = item / per_chunk;
+    const int t = item - qc * per_chunk;
+    tile = t % n_tiles_n;
+    b = t / n_tiles_n;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int i = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+        const int s = i % kTc2Stages;
+        const uint32_t ph = (i / kTc2Stages) & 1;
+        int b, tile, qc;
+        decode(item, b, tile, qc);
+        mbar_wait(bar_empty(s), ph ^ 1);
+        const uint32_t dst = smem_u32(smem) + s * stage_bytes;
+        mbar_expect_tx(bar_full(s), 2 * a_half + b_bytes);
+        tma_load_3d(dst, &map_proto, bar_full(s), tile * kTcTileN, 0, b);
+        tma_load_3d(dst + a_half, &map_proto, bar_full(s), tile * kTcTileN + 64, 0, b);
+        tma_load_3d(dst + 2 * a_half, &map_coeff, bar_full(s), 0, qc * QS, b);
+        if (dbg && blockIdx.x == 0 && i < 16) dbg[0 * 16 + i] = clock64();
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(QN));
+      int i = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+        const int s = i % kTc2Stages, a = i & 1;
+        const uint32_t ph = (i / kTc2Stages) & 1, aph = (i >> 1) & 1;
+        mbar_wait(bar_tempty(a), aph ^ 1);                     // the epilogue has drained this accumulator
+        if (dbg && blockIdx.x == 0 && i < 16) dbg[1 * 16 + i] = clock64();
+        mbar_wait(bar_full(s), ph);                            // operands have landed
+        if (dbg && blockIdx.x == 0 && i < 16) dbg[2 * 16 + i] = clock64();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = smem_u32(smem) + s * stage_bytes, b_addr = a_addr + 2 * a_half;
+        for (int ks = 0; ks < KP / 16; ++ks) {
+          const uint64_t a_desc = umma_desc_sw128(a_addr + ks * 2048u, a_half, 1024u);
+          const uint64_t b_desc = umma_desc_sw128(b_addr + ks * 32u, 16u, 1024u);
+          umma_bf16(tmem_base + a * 256u, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_empty(s)) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_tfull(a)) : "memory");
+      }
+    }
+  } else {
+    // epilogue: two independent groups ("halves") of four warps; a group owns alternate 32-row chunks of an item
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const bool is_issuer = ((warp - 2) & 3) == 0 && lane == 0;    // first warp of each group
+    OT* my_stage = reinterpret_cast<OT*>(out_stage + (half * 2) * kOutBuf);
+    uint32_t use = 0;                                               // chunks this group has staged so far
+    int i = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+      const int a = i & 1;
+      const uint32_t aph = (i >> 1) & 1;
+      int b, tile, qc;
+      decode(item, b, tile, qc);
+      const int q_begin = qc * QS;
+      const int rows = (qc == n_qchunks - 1) ? (Q - q_begin) : QS;
+      mbar_wait(bar_tfull(a), aph);
+      if (dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 16) dbg[3 * 16 + i] = clock64();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t lane_base = tmem_base + a * 256u + (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int q0 = half * 32; q0 < rows; q0 += 64, ++use) {
+        OT* buf = my_stage + (use & 1) * (32 * kTcTileN);
+        // the bulk store that last read this buffer (two chunks ago) must have drained it
+        if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        named_bar_sync(1 + half, 128);
+        float v[32];
+        tmem_ld32(lane_base + static_cast<uint32_t>(q0), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st_stage(buf + j * kTcTileN + quarter * 32 + lane, v[j]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        named_bar_sync(1 + half, 128);
+        if (is_issuer) tma_store_3d(&map_out, smem_u32(buf), tile * kTcTileN, q_begin + q0, b);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 16) dbg[4 * 16 + i] = clock64();
+      if (lane == 0) mbar_arrive(bar_tempty(a));
+    }
+    if (is_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+inline size_t mask_tc2_smem_bytes(int KP, int QN, size_t out_elem) {
+  const size_t stage = (2 * static_cast<size_t>(KP) * 128 + static_cast<size_t>(QN) * 128 + 1023) & ~size_t(1023);
+  return 1024 + kTc2Stages * stage + 4 * 32 * kTcTileN * out_elem;
+}
+
 inline size_t mask_tc_smem_bytes(int KP, int QP) { return 1024 + 2 * static_cast<size_t>(KP) * 128 + static_cast<size_t>(QP) * 128; }
 
 }  // namespace msda

@@ -39,10 +39,11 @@ int after_launch(const char* kernel_name) {
 }
 
 struct Options {
-  std::atomic<int> fwd_variant{0};    // 0 = auto (fast2 / fast when eligible), 1 = force generic, 2 = first-generation fast
+  std::atomic<int> fwd_variant{0};    // 0 = auto (fast2 / fast when eligible), 1 = force generic, 2 = first-generation fast, 3 = fast2 with batched gathers (80 registers)
   std::atomic<int> bwd_variant{0};    // same
   std::atomic<int> chunk_pairs{0};    // 0 = auto
   std::atomic<int> mask_variant{0};   // 0 = auto (tcgen05 when eligible), 1 = SIMT fp32, 2 = force tcgen05
+  std::atomic<int> mask_debug{0};     // 1 = the tcgen05 mask kernel records per-item clock stamps of CTA 0
   std::atomic<int> profile{0};        // 1 = bracket the main kernels with CUDA events (msda_profile_read)
 };
 static Options g_opt;
@@ -54,6 +55,7 @@ static std::atomic<int>* find_option(const char* key) {
   if (!strcmp(key, "chunk_pairs")) return &g_opt.chunk_pairs;
   if (!strcmp(key, "mask_variant")) return &g_opt.mask_variant;
   if (!strcmp(key, "profile")) return &g_opt.profile;
+  if (!strcmp(key, "mask_debug")) return &g_opt.mask_debug;
   return nullptr;
 }
 
@@ -140,15 +142,15 @@ static FastDiv make_fastdiv(uint32_t d) {
 
 static bool fast2_lp(int lp) { return lp == 16 || lp == 12 || lp == 8; }
 
-template <typename VT, typename LT, int D>
+template <typename VT, typename LT, int D, int MINB>
 static void launch_fwd2_lp(cudaStream_t st, const Problem& pb, unsigned grid, int chunk, const VT* v, const int64_t* shapes,
                            const int64_t* lsi, const LT* lc, const LT* a, VT* o) {
   const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
   const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
   switch (pb.L * pb.P) {
-    case 16: msda_fwd_fast2_kernel<VT, LT, D, 16><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
-    case 12: msda_fwd_fast2_kernel<VT, LT, D, 12><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
-    default: msda_fwd_fast2_kernel<VT, LT, D, 8><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
+    case 16: msda_fwd_fast2_kernel<VT, LT, D, 16, MINB><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
+    case 12: msda_fwd_fast2_kernel<VT, LT, D, 12, MINB><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
+    default: msda_fwd_fast2_kernel<VT, LT, D, 8, MINB><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
   }
 }
 
@@ -177,8 +179,14 @@ static int launch_fwd(cudaStream_t st, const Problem& pb, bool fast, const void*
       const int chunk = pick_chunk(pb);
       const unsigned grid = static_cast<unsigned>((pb.n_pairs + chunk - 1) / chunk);
       if (g_opt.fwd_variant.load() != 2 && fast2_lp(pb.L * pb.P)) {
-        if (pb.D == 32) launch_fwd2_lp<VT, LT, 32>(st, pb, grid, chunk, v, shapes, lsi, lc, a, o);
-        else launch_fwd2_lp<VT, LT, 24>(st, pb, grid, chunk, v, shapes, lsi, lc, a, o);
+        const bool lean = g_opt.fwd_variant.load() != 3;      // default: register-lean schedule (82 vs 90 us on the encoder shape, profiles/r01d); 3 = batched gathers
+        if (pb.D == 32) {
+          if (lean) launch_fwd2_lp<VT, LT, 32, 6>(st, pb, grid, chunk, v, shapes, lsi, lc, a, o);
+          else launch_fwd2_lp<VT, LT, 32, 3>(st, pb, grid, chunk, v, shapes, lsi, lc, a, o);
+        } else {
+          if (lean) launch_fwd2_lp<VT, LT, 24, 6>(st, pb, grid, chunk, v, shapes, lsi, lc, a, o);
+          else launch_fwd2_lp<VT, LT, 24, 3>(st, pb, grid, chunk, v, shapes, lsi, lc, a, o);
+        }
         return after_launch("msda_fwd_fast2_kernel");
       }
       if (pb.D == 32)
@@ -270,6 +278,8 @@ int msda_profile_read(int kind, int64_t min_units, double* total_ms, int64_t* co
   *count = n;
   return 0;
 }
+
+int msda_debug_read(long long* host80) { return mask_debug_copy(host80); }
 
 int64_t msda_launch_count(void) { return g_launches.load(); }
 void msda_launch_count_reset(void) { g_launches.store(0); }

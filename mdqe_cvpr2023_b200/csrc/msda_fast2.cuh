@@ -64,8 +64,10 @@ __device__ __forceinline__ SampleGeom make_slots2(Slot* dst, int s, float locx, 
 }
 
 // ------------------------------------------------------------------------------------------ forward
-template <typename VT, typename LT, int D, int LP>
-__global__ void __launch_bounds__(kThreads)
+// MINB = minimum resident CTAs per SM promised to ptxas: 3 leaves it 80+ registers, enough to keep a whole
+// batch of gathers in flight; 6 reproduces the register-lean, load-by-load schedule.
+template <typename VT, typename LT, int D, int LP, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                       const int64_t* __restrict__ level_start, const LT* __restrict__ loc,
                       const LT* __restrict__ aw, VT* __restrict__ out,
@@ -112,20 +114,34 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 #pragma unroll
         for (int j = 0; j < C::CPL; ++j) acc[j] = 0.f;
         const uint4* stream = reinterpret_cast<const uint4*>(my_stream + pl * C::NSLOT);
+        // Batches of kBatch corner rows: all slot records, then all gathers (kBatch 16-byte loads in flight
+        // per lane), then the FMAs.  The kernel is latency bound once the instruction count is down
+        // (profiles/r01b: 19 long-scoreboard stall cycles per issue), so memory-level parallelism matters.
+        constexpr int kBatch = (C::SPG < 8) ? C::SPG : 8;
 #pragma unroll
-        for (int it = 0; it < C::SPG / 2; ++it) {
-          const uint4 two = stream[it];                       // records of two consecutive samples
-          const uint32_t off[2] = {two.x, two.z};
-          const float w[2] = {__uint_as_float(two.y), __uint_as_float(two.w)};
+        for (int b0 = 0; b0 < C::SPG; b0 += kBatch) {
+          uint32_t off[kBatch];
+          float w[kBatch];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
+          for (int i = 0; i < kBatch / 2; ++i) {
+            const uint4 two = stream[(b0 >> 1) + i];          // records of two consecutive samples
+            off[2 * i] = two.x; w[2 * i] = __uint_as_float(two.y);
+            off[2 * i + 1] = two.z; w[2 * i + 1] = __uint_as_float(two.w);
+          }
+          float v[kBatch][C::CPL];
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
             if (active && w[u] != 0.f) {
-              float v[C::CPL];
-              Vec16<VT>::load(row_ptr(vlane, off[u]), v);
+              Vec16<VT>::load(row_ptr(vlane, off[u]), v[u]);
+            } else {
 #pragma unroll
-              for (int j = 0; j < C::CPL; ++j) acc[j] = fmaf(w[u], v[j], acc[j]);
+              for (int j = 0; j < C::CPL; ++j) v[u][j] = 0.f;
             }
           }
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u)
+#pragma unroll
+            for (int j = 0; j < C::CPL; ++j) acc[j] = fmaf(w[u], v[u][j], acc[j]);
         }
 #pragma unroll
         for (int k = C::NG / 2; k >= 1; k >>= 1) {
@@ -148,10 +164,13 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
                       float* __restrict__ grad_value, LT* __restrict__ grad_loc, LT* __restrict__ grad_aw,
                       int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq) {
   using C = Cfg2<VT, D, LP>;
-  constexpr int kDotStride = 33;                         // [element][sample] tile, padded: conflict-free both ways
+  // <grad_out, corner row> per (corner, sample): [4][33] floats per warp.  The partials are folded inside the
+  // corner group with shuffles first, so the tile stays tiny and shared memory stays small: the first version
+  // kept per-lane partials (34 KB per CTA), which left only ~16 KB of L1 per SM and cost the gathers their hit rate.
+  constexpr int kDotStride = 33;
   __shared__ LevelInfo s_lvl[kMaxLevels];
   __shared__ __align__(16) Slot s_slot[kWarpsPerCta][C::QPW * C::NSLOT];
-  __shared__ float s_dot[kWarpsPerCta][C::ROW * kDotStride];
+  __shared__ float s_dot[kWarpsPerCta][4 * kDotStride];
 
   stage_levels(s_lvl, shapes, level_start, L);
   __syncthreads();
@@ -164,8 +183,8 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
   const Slot* my_stream = my_slots + corner * C::LPP + sgrp * C::SPG;
   const VT* vlane = value + c * C::CPL;
   float* gvlane = grad_value + c * C::CPL;
-  // dot partial of (element = corner*G + c, sample): written by the corner lanes, read by the sample lanes
-  float* dot_w = s_dot[warp] + (corner * C::G + c) * kDotStride + sgrp * C::SPG;
+  // dot of (corner, sample): written by lane 0 of each corner group, read by the sample lanes
+  float* dot_w = s_dot[warp] + corner * kDotStride + sgrp * C::SPG;
   const float* dot_r = s_dot[warp] + lane;
 
   const uint32_t chunk_begin = blockIdx.x * static_cast<uint32_t>(chunk_pairs);
@@ -218,7 +237,20 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
               for (int j = 0; j < C::CPL; j += 4)
                 red_add_f32x4(gv + j, w[u] * go[j], w[u] * go[j + 1], w[u] * go[j + 2], w[u] * go[j + 3]);
             }
-            if (active) dot_w[pl * LP + 2 * it + u] = dot;
+            // fold the G per-lane partials of this corner row (groups are G consecutive lanes)
+            if constexpr ((C::G & (C::G - 1)) == 0) {
+#pragma unroll
+              for (int o = C::G / 2; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            } else {                                          // G = 6 or 3: walk down inside the group
+              float t = dot;
+#pragma unroll
+              for (int o = 1; o < C::G; ++o) {
+                const float nb = __shfl_down_sync(0xffffffffu, dot, o);
+                if (c + o < C::G) t += nb;
+              }
+              dot = t;
+            }
+            if (active && c == 0) dot_w[pl * LP + 2 * it + u] = dot;
           }
         }
       }
@@ -226,9 +258,9 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
     __syncwarp();
 
     if (has_sample) {
-      float dc[4] = {0.f, 0.f, 0.f, 0.f};     // per-corner <grad_out, value row>
+      float dc[4];                              // per-corner <grad_out, value row>
 #pragma unroll
-      for (int e = 0; e < C::ROW; ++e) dc[e / C::G] += dot_r[e * kDotStride];
+      for (int e = 0; e < 4; ++e) dc[e] = dot_r[e * kDotStride];
       const float hx = 1.f - geo.lx, hy = 1.f - geo.ly;
       const float g_aw = hy * (hx * dc[0] + geo.lx * dc[1]) + geo.ly * (hx * dc[2] + geo.lx * dc[3]);
       const float g_x = a * static_cast<float>(lvl_w) * (hy * (dc[1] - dc[0]) + geo.ly * (dc[3] - dc[2]));

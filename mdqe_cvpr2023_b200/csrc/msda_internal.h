@@ -35,6 +35,7 @@ class ProfScope {
 };
 
 // mask_gemm.cu
+int mask_debug_copy(long long* host80);
 int mask_forward_dispatch(cudaStream_t stream, int in_dtype, int out_dtype, const void* coeff, const void* proto,
                           int B, int Q, int K, int64_t Ncols, void* out);
 int mask_backward_dispatch(cudaStream_t stream, int dtype, const void* coeff, const void* proto, const void* grad_out,

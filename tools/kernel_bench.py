@@ -76,6 +76,12 @@ def main():
                 rec(f"ours_fwd_chunk{chunk}", timed(lambda: ops.ms_deform_attn_forward(*a, 64), args.iters, flush), fwd_b)
                 rec(f"ours_bwd_chunk{chunk}", timed(lambda: ops.ms_deform_attn_backward(*a, inp["grad_out"], 64), args.iters, flush), bwd_b)
             _lib.set_option("chunk_pairs", 0)
+            _lib.set_option("fwd_variant", 3)
+            rec("ours_fwd_lean", timed(lambda: ops.ms_deform_attn_forward(*a, 64), args.iters, flush), fwd_b)
+            _lib.set_option("fwd_variant", 2)
+            _lib.set_option("bwd_variant", 2)
+            rec("ours_fwd_gen1", timed(lambda: ops.ms_deform_attn_forward(*a, 64), args.iters, flush), fwd_b)
+            rec("ours_bwd_gen1", timed(lambda: ops.ms_deform_attn_backward(*a, inp["grad_out"], 64), args.iters, flush), bwd_b)
             _lib.set_option("fwd_variant", 1)
             _lib.set_option("bwd_variant", 1)
             rec("ours_generic_fwd", timed(lambda: ops.ms_deform_attn_forward(*a, 64), args.iters, flush), fwd_b)
