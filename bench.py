@@ -104,10 +104,13 @@ def build_calls(torch, dist, seed, layers):
         value_t = torch.randn(1, T_FRAMES * S, HEADS, HEAD_DIM, generator=g)
         loc_t = make_loc(torch, g, qref, 1, QUERIES, T_FRAMES, dist)
         aw_t = aw_(1, QUERIES, T_FRAMES)
-        for lvl in range(4):                                  # one call per pyramid level; "levels" = the T frames
+        go_t = torch.randn(1, QUERIES, HEADS * HEAD_DIM, generator=g)
+        for lvl in range(4):                                  # reference form: one call per pyramid level; "levels" = the T frames
             calls.append(dict(kind="dec_temporal", value=value_t, shapes=shapes[lvl].view(1, 2).expand(T_FRAMES, 2).contiguous(),
-                              lsi=torch.arange(T_FRAMES) * S + lsi[lvl], loc=loc_t, aw=aw_t,
-                              go=torch.randn(1, QUERIES, HEADS * HEAD_DIM, generator=g)))
+                              lsi=torch.arange(T_FRAMES) * S + lsi[lvl], loc=loc_t, aw=aw_t, go=go_t))
+        # the same four calls as ONE grouped launch (msda_forward_grouped: G = 4 level tables, mean folded in)
+        calls.append(dict(kind="dec_temporal_grouped", value=value_t, shapes=shapes.view(4, 1, 2).expand(4, T_FRAMES, 2).contiguous(),
+                          lsi=(lsi.view(4, 1) + (torch.arange(T_FRAMES) * S).view(1, T_FRAMES)).contiguous(), loc=loc_t, aw=aw_t, go=go_t))
     mask = dict(coeff=torch.tanh(torch.randn(1, QUERIES, MASK_K, generator=g)),
                 proto=torch.randn(1, MASK_K, T_FRAMES, *MASK_PLANE, generator=g),
                 go=torch.randn(1, QUERIES, T_FRAMES, *MASK_PLANE, generator=g))
@@ -116,7 +119,7 @@ def build_calls(torch, dist, seed, layers):
 
 def call_dims(c):
     N, S, M, D = c["value"].shape
-    _, Lq, _, L, P, _ = c["loc"].shape
+    _, Lq, _, L, P, _ = c["loc"].shape        # for the grouped temporal call L = T frames per level table
     return N, S, M, D, L, Lq, P
 
 
@@ -151,6 +154,8 @@ class DeviceStep:
             return cache[key]
 
         for c in calls:
+            if c["kind"] == "dec_temporal":
+                continue                                      # the device step runs the grouped form instead
             N, S, M, D, L, Lq, P = call_dims(c)
             v, loc, aw, go = dev(c["value"]), dev(c["loc"]), dev(c["aw"]), dev(c["go"])
             sh, ls = dev(c["shapes"], False), dev(c["lsi"], False)
@@ -159,11 +164,12 @@ class DeviceStep:
             ws_bytes = lib.msda_backward_workspace_bytes(self.code, N, S, M, D)
             ws = torch.empty(max(ws_bytes // 4, 1), dtype=torch.float32, device=device)
             self.keep += [v, loc, aw, go, sh, ls, out, gv, gl, ga, ws]
-            dims = (N, S, M, D, L, Lq, P)
-            self.fwd.append((self.code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr()) + dims
-                            + (out.data_ptr(),))
-            self.bwd.append((self.code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr(), go.data_ptr())
-                            + dims + (gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), ws.data_ptr() if ws_bytes else None, ws_bytes))
+            grouped = c["kind"] == "dec_temporal_grouped"
+            dims = (N, S, M, D, 4, L, Lq, P, 0.25) if grouped else (N, S, M, D, L, Lq, P)
+            self.fwd.append((grouped, (self.code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr()) + dims
+                             + (out.data_ptr(),)))
+            self.bwd.append((grouped, (self.code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr(), go.data_ptr())
+                             + dims + (gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), ws.data_ptr() if ws_bytes else None, ws_bytes)))
         # mask contraction: forward in the I/O dtype, backward is fp32-only (training precision of the reference)
         mc, mp = dev(mask["coeff"]), dev(mask["proto"])
         B, Q, K = mc.shape
@@ -181,12 +187,12 @@ class DeviceStep:
         lib = self.lib
         st = self.torch.cuda.current_stream(self.device).cuda_stream
         rc = 0
-        for a in self.fwd:
-            rc |= lib.msda_forward(st, *a)
+        for grouped, a in self.fwd:
+            rc |= (lib.msda_forward_grouped if grouped else lib.msda_forward)(st, *a)
         rc |= lib.mask_logits_forward(st, *self.mask_fwd)
         rc |= lib.mask_logits_backward(st, *self.mask_bwd)
-        for a in reversed(self.bwd):
-            rc |= lib.msda_backward(st, *a)
+        for grouped, a in reversed(self.bwd):
+            rc |= (lib.msda_backward_grouped if grouped else lib.msda_backward)(st, *a)
         if rc:
             from mdqe_cvpr2023_b200 import _lib
             raise RuntimeError("C-ABI call failed: " + _lib.last_error())
@@ -211,7 +217,7 @@ class HostStep:
 
         nb = lambda t: t.numel() * t.element_size()
         # output staging shared by all calls (max size), pinned
-        big = max(calls, key=lambda c: c["loc"].numel())
+        big = max(calls, key=lambda c: c["go"].numel())
         bigv = max(calls, key=lambda c: c["value"].numel())
         out_h = torch.empty(big["go"].numel(), dtype=vt).pin_memory()
         gv_h = torch.empty(bigv["value"].numel(), dtype=vt).pin_memory()
@@ -219,6 +225,8 @@ class HostStep:
         ga_h = torch.empty(big["aw"].numel(), dtype=vt).pin_memory()
         self.keep += [out_h, gv_h, gl_h, ga_h]
         for c in calls:
+            if c["kind"] == "dec_temporal_grouped":
+                continue                                      # the host-buffer ABI has the per-level entries only
             dims = call_dims(c)
             v, loc, aw, go = pin(c["value"]), pin(c["loc"]), pin(c["aw"]), pin(c["go"])
             sh, ls = pin(c["shapes"], False), pin(c["lsi"], False)
@@ -322,7 +330,7 @@ def cpu_sample(torch, calls, mask, reps, warm):
 
 def config_dict(args, extra=None):
     cfg = {"workload": "R50_ovis_360 clip hot path: 36 MSDeformAttn fwd+bwd (6 enc N=4 S=Lq=5100, 6 dec-spatial Lq=196, "
-                       "24 dec-temporal L=T=4) + mask contraction Q=196 K=32 N=61440 fwd+bwd",
+                       "24 dec-temporal L=T=4 run as 6 grouped launches) + mask contraction Q=196 K=32 N=61440 fwd+bwd",
            "clips_per_gpu_per_step": 1, "frames": T_FRAMES, "pyramid": PYRAMID, "heads": HEADS, "head_dim": HEAD_DIM,
            "points": POINTS, "queries": QUERIES, "layers": args.layers, "loc_dist": args.dist,
            "l2_policy": "inputs larger than L2 (every call has its own buffers, ~1.5 GB touched per step)",
@@ -440,6 +448,7 @@ def main():
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     launches_per_step = len(step.fwd) + len(step.bwd) + 2 + (len(step.bwd) if args.dtype == "bf16" else 0)
+    n_msda_calls = sum(4 if g else 1 for g, _ in step.fwd)     # reference-equivalent Function applications (36 per direction)
     gpu_launches = launches_per_step * args.steps      # graph replays re-launch the captured kernels
     value = world * 1.0 / (ms_step / 1e3)
 
@@ -473,8 +482,8 @@ def main():
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                 "traffic": None, "avg_launch_us": us, "launches_timed": n, "algorithmic_bytes": nbytes, "peak_source": peak_src}
 
-    roofline = roof(bwd_bytes, bwd_ms, bwd_n, "msda_bwd_fast_kernel<float,float,32> (encoder shape N=4,S=Lq=5100)")
-    roofline_fwd = roof(fwd_bytes, fwd_ms, fwd_n, "msda_fwd_fast_kernel<float,float,32> (encoder shape)")
+    roofline = roof(bwd_bytes, bwd_ms, bwd_n, "msda_bwd_fast2_kernel<%s,32,16> (encoder shape N=4,S=Lq=5100)" % ("bf16" if args.dtype == "bf16" else "float"))
+    roofline_fwd = roof(fwd_bytes, fwd_ms, fwd_n, "msda_fwd_fast2_kernel<%s,32,16> (encoder shape N=4,S=Lq=5100)" % ("bf16" if args.dtype == "bf16" else "float"))
     mB = QUERIES * MASK_K + MASK_K * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
     mO = QUERIES * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
     roofline_mask = roof(mB * esize + mO * esize, mfw_ms, mfw_n, "mask_logits forward")

@@ -87,6 +87,25 @@ int msda_backward(void* stream, int dtype,
                   void* grad_value, void* grad_loc, void* grad_aw,
                   void* workspace, size_t workspace_bytes);
 
+/* Grouped ("temporal") form used by the clip-level decoder attention (ms_deform_attn.py:219-235): G level tables of L
+ * levels each share ONE set of sampling locations / attention weights,
+ *     out = scale * sum_{g<G} msda(value, shapes[g], level_start[g], loc, aw)
+ * with shapes [G,L,2] and level_start [G,L] (int64, device).  In MDQE g runs over the pyramid levels, the L "levels" are
+ * the T frames of the clip inside a [B, T*S, M, D] value tensor (level_start[g][t] = t*S + start_g) and scale = 1/G.
+ * One launch instead of G, no per-level copies, one zero-fill of grad_value.  Supported where the fast kernels are
+ * (D in {32,24}, L*P in {8,12,16}, fp32/bf16, G*L <= 32); otherwise MSDA_ERR_UNSUPPORTED (call msda_forward per group). */
+int msda_forward_grouped(void* stream, int dtype,
+                         const void* value, const int64_t* shapes, const int64_t* level_start,
+                         const void* loc, const void* aw,
+                         int N, int S, int M, int D, int G, int L, int Lq, int P, float scale,
+                         void* out);
+int msda_backward_grouped(void* stream, int dtype,
+                          const void* value, const int64_t* shapes, const int64_t* level_start,
+                          const void* loc, const void* aw, const void* grad_out,
+                          int N, int S, int M, int D, int G, int L, int Lq, int P, float scale,
+                          void* grad_value, void* grad_loc, void* grad_aw,
+                          void* workspace, size_t workspace_bytes);
+
 /* Mask contraction: out[b,q,n] = sum_k coeff[b,q,k] * proto[b,k,n], n over the flattened (t,h,w)
  * plane (Ncols = T*H*W).  coeff [B,Q,K], proto [B,K,Ncols], out [B,Q,Ncols].
  *   in_dtype  MSDA_F32 (inputs rounded to bf16 hi+lo pairs on chip: 3 tensor-core passes, fp32

@@ -91,6 +91,8 @@ ProfScope::~ProfScope() {
 struct Problem {
   int N, S, M, D, L, Lq, P;
   int64_t n_pairs;
+  int G = 1;            // level-table groups sharing loc/aw (temporal form); 1 = the plain operator
+  float scale = 1.f;    // out = scale * sum over groups
 };
 
 static int validate(const char* who, int dtype, const void* value, const int64_t* shapes, const int64_t* lsi,
@@ -147,11 +149,15 @@ static void launch_fwd2_lp(cudaStream_t st, const Problem& pb, unsigned grid, in
                            const int64_t* lsi, const LT* lc, const LT* a, VT* o) {
   const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
   const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
+#define MSDA_FWD2(LPV, GRP) msda_fwd_fast2_kernel<VT, LT, D, LPV, MINB, GRP><<<grid, kThreads, 0, st>>>( \
+      v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale)
+  const bool grouped = pb.G > 1 || pb.scale != 1.f;
   switch (pb.L * pb.P) {
-    case 16: msda_fwd_fast2_kernel<VT, LT, D, 16, MINB><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
-    case 12: msda_fwd_fast2_kernel<VT, LT, D, 12, MINB><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
-    default: msda_fwd_fast2_kernel<VT, LT, D, 8, MINB><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
+    case 16: if (grouped) MSDA_FWD2(16, true); else MSDA_FWD2(16, false); break;
+    case 12: if (grouped) MSDA_FWD2(12, true); else MSDA_FWD2(12, false); break;
+    default: if (grouped) MSDA_FWD2(8, true); else MSDA_FWD2(8, false); break;
   }
+#undef MSDA_FWD2
 }
 
 template <typename VT, typename LT, int D>
@@ -159,11 +165,15 @@ static void launch_bwd2_lp(cudaStream_t st, const Problem& pb, unsigned grid, in
                            const int64_t* lsi, const LT* lc, const LT* a, const VT* go, float* gv, LT* gl, LT* ga) {
   const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
   const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
+#define MSDA_BWD2(LPV, GRP) msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP><<<grid, kThreads, 0, st>>>( \
+      v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale)
+  const bool grouped = pb.G > 1 || pb.scale != 1.f;
   switch (pb.L * pb.P) {
-    case 16: msda_bwd_fast2_kernel<VT, LT, D, 16><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
-    case 12: msda_bwd_fast2_kernel<VT, LT, D, 12><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
-    default: msda_bwd_fast2_kernel<VT, LT, D, 8><<<grid, kThreads, 0, st>>>(v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq); break;
+    case 16: if (grouped) MSDA_BWD2(16, true); else MSDA_BWD2(16, false); break;
+    case 12: if (grouped) MSDA_BWD2(12, true); else MSDA_BWD2(12, false); break;
+    default: if (grouped) MSDA_BWD2(8, true); else MSDA_BWD2(8, false); break;
   }
+#undef MSDA_BWD2
 }
 
 template <typename VT, typename LT>
@@ -284,21 +294,42 @@ int msda_debug_read(long long* host80) { return mask_debug_copy(host80); }
 int64_t msda_launch_count(void) { return g_launches.load(); }
 void msda_launch_count_reset(void) { g_launches.store(0); }
 
-int msda_forward(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
-                 const void* loc, const void* aw, int N, int S, int M, int D, int L, int Lq, int P, void* out) {
-  if (int rc = validate("msda_forward", dtype, value, shapes, level_start, loc, aw, N, S, M, D, L, Lq, P)) return rc;
-  Problem pb{N, S, M, D, L, Lq, P, (int64_t)N * Lq * M};
+static int grouped_supported(const char* who, int dtype, const Problem& pb, bool fast) {
+  if (pb.G == 1) return 0;
+  if (pb.G < 1 || pb.G * pb.L > kMaxLevels) return fail(MSDA_ERR_UNSUPPORTED, "%s: G*L = %d exceeds %d level tables", who, pb.G * pb.L, kMaxLevels);
+  if (!fast || !fast2_lp(pb.L * pb.P) || dtype == MSDA_F64)
+    return fail(MSDA_ERR_UNSUPPORTED, "%s: the grouped form needs D in {32,24}, L*P in {8,12,16}, fp32/bf16 and 16-byte aligned tensors", who);
+  return 0;
+}
+
+static int forward_impl(const char* who, void* stream, int dtype, const void* value, const int64_t* shapes,
+                        const int64_t* level_start, const void* loc, const void* aw, int N, int S, int M, int D, int G, int L,
+                        int Lq, int P, float scale, void* out) {
+  if (int rc = validate(who, dtype, value, shapes, level_start, loc, aw, N, S, M, D, L, Lq, P)) return rc;
+  Problem pb{N, S, M, D, L, Lq, P, (int64_t)N * Lq * M, G, scale};
   if (pb.n_pairs == 0) return 0;
-  if (!out) return fail(MSDA_ERR_INVALID_ARG, "msda_forward: out is NULL");
+  if (!out) return fail(MSDA_ERR_INVALID_ARG, "%s: out is NULL", who);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool fast = g_opt.fwd_variant.load() != 1 && fast_eligible(dtype, pb, value, out, loc);
+  const bool fast = (G > 1 || g_opt.fwd_variant.load() != 1) && fast_eligible(dtype, pb, value, out, loc);
+  if (int rc = grouped_supported(who, dtype, pb, fast)) return rc;
   switch (dtype) {
     case MSDA_F32: return launch_fwd<float, float>(st, pb, fast, value, shapes, level_start, loc, aw, out);
     case MSDA_BF16: return launch_fwd<__nv_bfloat16, __nv_bfloat16>(st, pb, fast, value, shapes, level_start, loc, aw, out);
     case MSDA_BF16_LOC32: return launch_fwd<__nv_bfloat16, float>(st, pb, fast, value, shapes, level_start, loc, aw, out);
     case MSDA_F64: return launch_fwd<double, double>(st, pb, false, value, shapes, level_start, loc, aw, out);
   }
-  return fail(MSDA_ERR_INVALID_ARG, "msda_forward: unknown dtype %d", dtype);
+  return fail(MSDA_ERR_INVALID_ARG, "%s: unknown dtype %d", who, dtype);
+}
+
+int msda_forward(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                 const void* loc, const void* aw, int N, int S, int M, int D, int L, int Lq, int P, void* out) {
+  return forward_impl("msda_forward", stream, dtype, value, shapes, level_start, loc, aw, N, S, M, D, 1, L, Lq, P, 1.f, out);
+}
+
+int msda_forward_grouped(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                         const void* loc, const void* aw, int N, int S, int M, int D, int G, int L, int Lq, int P, float scale,
+                         void* out) {
+  return forward_impl("msda_forward_grouped", stream, dtype, value, shapes, level_start, loc, aw, N, S, M, D, G, L, Lq, P, scale, out);
 }
 
 size_t msda_backward_workspace_bytes(int dtype, int N, int S, int M, int D) {
@@ -306,18 +337,19 @@ size_t msda_backward_workspace_bytes(int dtype, int N, int S, int M, int D) {
   return 0;
 }
 
-int msda_backward(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
-                  const void* loc, const void* aw, const void* grad_out, int N, int S, int M, int D, int L, int Lq,
-                  int P, void* grad_value, void* grad_loc, void* grad_aw, void* workspace, size_t workspace_bytes) {
-  if (int rc = validate("msda_backward", dtype, value, shapes, level_start, loc, aw, N, S, M, D, L, Lq, P)) return rc;
-  Problem pb{N, S, M, D, L, Lq, P, (int64_t)N * Lq * M};
+static int backward_impl(const char* who, void* stream, int dtype, const void* value, const int64_t* shapes,
+                         const int64_t* level_start, const void* loc, const void* aw, const void* grad_out, int N, int S, int M,
+                         int D, int G, int L, int Lq, int P, float scale, void* grad_value, void* grad_loc, void* grad_aw,
+                         void* workspace, size_t workspace_bytes) {
+  if (int rc = validate(who, dtype, value, shapes, level_start, loc, aw, N, S, M, D, L, Lq, P)) return rc;
+  Problem pb{N, S, M, D, L, Lq, P, (int64_t)N * Lq * M, G, scale};
   const size_t n_value = (size_t)N * S * M * D;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (n_value > 0 && !grad_value) return fail(MSDA_ERR_INVALID_ARG, "msda_backward: grad_value is NULL");
+  if (n_value > 0 && !grad_value) return fail(MSDA_ERR_INVALID_ARG, "%s: grad_value is NULL", who);
   const bool is_bf16 = dtype == MSDA_BF16 || dtype == MSDA_BF16_LOC32;
   const size_t need = msda_backward_workspace_bytes(dtype, N, S, M, D);
   if (need > 0 && (!workspace || workspace_bytes < need))
-    return fail(MSDA_ERR_WORKSPACE, "msda_backward: bf16 needs a %zu-byte fp32 workspace (got %zu)", need, workspace_bytes);
+    return fail(MSDA_ERR_WORKSPACE, "%s: bf16 needs a %zu-byte fp32 workspace (got %zu)", who, need, workspace_bytes);
   void* acc = is_bf16 ? workspace : grad_value;
   const size_t acc_bytes = is_bf16 ? need : n_value * dtype_size(dtype);
   if (acc_bytes > 0)
@@ -327,9 +359,10 @@ int msda_backward(void* stream, int dtype, const void* value, const int64_t* sha
       return check_cuda(cudaMemsetAsync(grad_value, 0, n_value * 2, st), "cudaMemsetAsync(grad_value)");
     return 0;
   }
-  if (!grad_out || !grad_loc || !grad_aw) return fail(MSDA_ERR_INVALID_ARG, "msda_backward: grad_out / grad_loc / grad_aw is NULL");
-  const bool fast = g_opt.bwd_variant.load() != 1 && fast_eligible(dtype, pb, value, grad_out, acc) &&
+  if (!grad_out || !grad_loc || !grad_aw) return fail(MSDA_ERR_INVALID_ARG, "%s: grad_out / grad_loc / grad_aw is NULL", who);
+  const bool fast = (G > 1 || g_opt.bwd_variant.load() != 1) && fast_eligible(dtype, pb, value, grad_out, acc) &&
                     aligned16(loc) && aligned16(grad_loc);
+  if (int rcg = grouped_supported(who, dtype, pb, fast)) return rcg;
   int rc = 0;
   switch (dtype) {
     case MSDA_F32:
@@ -349,18 +382,33 @@ int msda_backward(void* stream, int dtype, const void* value, const int64_t* sha
                                               static_cast<double*>(acc), grad_loc, grad_aw);
       break;
     default:
-      return fail(MSDA_ERR_INVALID_ARG, "msda_backward: unknown dtype %d", dtype);
+      return fail(MSDA_ERR_INVALID_ARG, "%s: unknown dtype %d", who, dtype);
   }
   if (rc) return rc;
   if (is_bf16) {
     if (n_value % 4 != 0 || !aligned16(workspace) || (reinterpret_cast<uintptr_t>(grad_value) & 7u))
-      return fail(MSDA_ERR_UNSUPPORTED, "msda_backward: bf16 grad_value conversion needs N*S*M*D %% 4 == 0 and aligned buffers");
+      return fail(MSDA_ERR_UNSUPPORTED, "%s: bf16 grad_value conversion needs N*S*M*D %% 4 == 0 and aligned buffers", who);
     const int64_t n4 = (int64_t)(n_value / 4);
     const unsigned grid = static_cast<unsigned>((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
     cvt_f32_to_bf16_kernel<<<grid, 256, 0, st>>>(static_cast<const float4*>(workspace), static_cast<uint2*>(grad_value), n4);
     return after_launch("cvt_f32_to_bf16_kernel");
   }
   return 0;
+}
+
+int msda_backward(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                  const void* loc, const void* aw, const void* grad_out, int N, int S, int M, int D, int L, int Lq,
+                  int P, void* grad_value, void* grad_loc, void* grad_aw, void* workspace, size_t workspace_bytes) {
+  return backward_impl("msda_backward", stream, dtype, value, shapes, level_start, loc, aw, grad_out, N, S, M, D, 1, L, Lq, P,
+                       1.f, grad_value, grad_loc, grad_aw, workspace, workspace_bytes);
+}
+
+int msda_backward_grouped(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                          const void* loc, const void* aw, const void* grad_out, int N, int S, int M, int D, int G, int L,
+                          int Lq, int P, float scale, void* grad_value, void* grad_loc, void* grad_aw, void* workspace,
+                          size_t workspace_bytes) {
+  return backward_impl("msda_backward_grouped", stream, dtype, value, shapes, level_start, loc, aw, grad_out, N, S, M, D, G, L,
+                       Lq, P, scale, grad_value, grad_loc, grad_aw, workspace, workspace_bytes);
 }
 
 int mask_logits_forward(void* stream, int in_dtype, int out_dtype, const void* coeff, const void* proto, int B, int Q,

@@ -101,8 +101,9 @@ __device__ __forceinline__ SampleGeom sample_geom(float locx, float locy, int H,
   const float fx = floorf(x), fy = floorf(y);
   g.lx = x - fx;
   g.ly = y - fy;
-  // NaN / huge coordinates fail every comparison below -> all corners invalid (sample skipped).
-  const bool sane = (fx >= -1.f) && (fx <= static_cast<float>(W)) && (fy >= -1.f) && (fy <= static_cast<float>(H));
+  // The reference takes a sample only if -1 < x < W and -1 < y < H, strictly (ms_deform_im2col_cuda.cuh:288); NaN /
+  // huge coordinates fail the comparisons -> all corners invalid (sample skipped, zero gradient).
+  const bool sane = (x > -1.f) && (x < static_cast<float>(W)) && (y > -1.f) && (y < static_cast<float>(H));
   g.x0 = sane ? static_cast<int>(fx) : -8;
   g.y0 = sane ? static_cast<int>(fy) : -8;
   g.okx0 = g.x0 >= 0 && g.x0 < W;

@@ -66,17 +66,19 @@ __device__ __forceinline__ SampleGeom make_slots2(Slot* dst, int s, float locx, 
 // ------------------------------------------------------------------------------------------ forward
 // MINB = minimum resident CTAs per SM promised to ptxas: 3 leaves it 80+ registers, enough to keep a whole
 // batch of gathers in flight; 6 reproduces the register-lean, load-by-load schedule.
-template <typename VT, typename LT, int D, int LP, int MINB>
+template <typename VT, typename LT, int D, int LP, int MINB, bool GROUPED>
 __global__ void __launch_bounds__(kThreads, MINB)
 msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                       const int64_t* __restrict__ level_start, const LT* __restrict__ loc,
                       const LT* __restrict__ aw, VT* __restrict__ out,
-                      int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq) {
+                      int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq,
+                      int G, float scale) {
+  // G > 1: "grouped" (temporal) form -- G level tables share loc/aw, out = scale * sum_g (see msda_forward_grouped)
   using C = Cfg2<VT, D, LP>;
   __shared__ LevelInfo s_lvl[kMaxLevels];
   __shared__ __align__(16) Slot s_slot[kWarpsPerCta][C::QPW * C::NSLOT];
 
-  stage_levels(s_lvl, shapes, level_start, L);
+  stage_levels(s_lvl, shapes, level_start, G * L);
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,73 +98,107 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 
   for (uint32_t p0 = chunk_begin + warp * C::QPW; p0 < chunk_end; p0 += kWarpsPerCta * C::QPW) {
     const int npair = static_cast<int>(min(static_cast<uint32_t>(C::QPW), chunk_end - p0));
-    if (lane < npair * LP) {
+    const bool has_sample = lane < npair * LP;
+    float x = 0.f, y = 0.f, a = 0.f;
+    uint32_t n = 0, m = 0;
+    if (has_sample) {
       const uint32_t pair = p0 + ps;
       const uint32_t nq = fd_div(pair, div_m);
-      const uint32_t m = pair - nq * div_m.d;
-      const uint32_t n = fd_div(pair, div_mq);
-      float x, y, a;
+      m = pair - nq * div_m.d;
+      n = fd_div(pair, div_mq);
       load_loc_aw<LT>(loc, aw, static_cast<int64_t>(p0) * LP + lane, x, y, a);
-      make_slots2<C::D16, C::LPP>(my_slots + ps * C::NSLOT, ss, x, y, a, s_lvl[lvl], n, m, S, M);
+      a *= scale;
     }
-    __syncwarp();
+    // GROUPED keeps one accumulator set per pair alive across the G level tables; the plain operator (G == 1)
+    // reduces and stores each pair as soon as its corner loop ends (fewer live registers: 81 vs 94 us measured)
+    float acc_g[GROUPED ? C::QPW : 1][C::CPL];
+    if constexpr (GROUPED) {
+#pragma unroll
+      for (int pl = 0; pl < C::QPW; ++pl)
+#pragma unroll
+        for (int j = 0; j < C::CPL; ++j) acc_g[pl][j] = 0.f;
+    }
 
+    for (int g = 0; g < (GROUPED ? G : 1); ++g) {
+      if (has_sample) make_slots2<C::D16, C::LPP>(my_slots + ps * C::NSLOT, ss, x, y, a, s_lvl[g * L + lvl], n, m, S, M);
+      __syncwarp();
 #pragma unroll
-    for (int pl = 0; pl < C::QPW; ++pl) {
-      if (pl < npair) {
-        float acc[C::CPL];
+      for (int pl = 0; pl < C::QPW; ++pl) {
+        if (pl < npair) {
+          float acc[C::CPL];
 #pragma unroll
-        for (int j = 0; j < C::CPL; ++j) acc[j] = 0.f;
-        const uint4* stream = reinterpret_cast<const uint4*>(my_stream + pl * C::NSLOT);
-        // Batches of kBatch corner rows: all slot records, then all gathers (kBatch 16-byte loads in flight
-        // per lane), then the FMAs.  The kernel is latency bound once the instruction count is down
-        // (profiles/r01b: 19 long-scoreboard stall cycles per issue), so memory-level parallelism matters.
-        constexpr int kBatch = (C::SPG < 8) ? C::SPG : 8;
+          for (int j = 0; j < C::CPL; ++j) acc[j] = GROUPED ? acc_g[GROUPED ? pl : 0][j] : 0.f;
+          const uint4* stream = reinterpret_cast<const uint4*>(my_stream + pl * C::NSLOT);
+          // Batches of kBatch corner rows: slot records, then the gathers, then the FMAs (with MINB = 3 ptxas keeps
+          // the whole batch in flight; the default register-lean build interleaves them, which measured faster).
+          constexpr int kBatch = (C::SPG % 8 == 0) ? 8 : ((C::SPG % 6 == 0) ? 6 : ((C::SPG % 4 == 0) ? 4 : 2));   // must divide SPG
+          static_assert(C::SPG % kBatch == 0 && kBatch % 2 == 0, "batch must tile the slot stream");
 #pragma unroll
-        for (int b0 = 0; b0 < C::SPG; b0 += kBatch) {
-          uint32_t off[kBatch];
-          float w[kBatch];
+          for (int b0 = 0; b0 < C::SPG; b0 += kBatch) {
+            uint32_t off[kBatch];
+            float w[kBatch];
 #pragma unroll
-          for (int i = 0; i < kBatch / 2; ++i) {
-            const uint4 two = stream[(b0 >> 1) + i];          // records of two consecutive samples
-            off[2 * i] = two.x; w[2 * i] = __uint_as_float(two.y);
-            off[2 * i + 1] = two.z; w[2 * i + 1] = __uint_as_float(two.w);
-          }
-          float v[kBatch][C::CPL];
-#pragma unroll
-          for (int u = 0; u < kBatch; ++u) {
-            if (active && w[u] != 0.f) {
-              Vec16<VT>::load(row_ptr(vlane, off[u]), v[u]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < C::CPL; ++j) v[u][j] = 0.f;
+            for (int i = 0; i < kBatch / 2; ++i) {
+              const uint4 two = stream[(b0 >> 1) + i];          // records of two consecutive samples
+              off[2 * i] = two.x; w[2 * i] = __uint_as_float(two.y);
+              off[2 * i + 1] = two.z; w[2 * i + 1] = __uint_as_float(two.w);
             }
+            float v[kBatch][C::CPL];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+              if (active && w[u] != 0.f) {
+                Vec16<VT>::load(row_ptr(vlane, off[u]), v[u]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < C::CPL; ++j) v[u][j] = 0.f;
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u)
+#pragma unroll
+              for (int j = 0; j < C::CPL; ++j) acc[j] = fmaf(w[u], v[u][j], acc[j]);
           }
+          if constexpr (GROUPED) {
 #pragma unroll
-          for (int u = 0; u < kBatch; ++u)
+            for (int j = 0; j < C::CPL; ++j) acc_g[GROUPED ? pl : 0][j] = acc[j];
+          } else {
 #pragma unroll
-            for (int j = 0; j < C::CPL; ++j) acc[j] = fmaf(w[u], v[u][j], acc[j]);
+            for (int k = C::NG / 2; k >= 1; k >>= 1) {
+#pragma unroll
+              for (int j = 0; j < C::CPL; ++j) acc[j] += __shfl_down_sync(0xffffffffu, acc[j], k * C::G);
+            }
+            if (lane < C::G) Vec16<VT>::store(out + static_cast<int64_t>(p0 + pl) * D + lane * C::CPL, acc);
+          }
         }
+      }
+      __syncwarp();
+    }
+
+    if constexpr (GROUPED) {
 #pragma unroll
-        for (int k = C::NG / 2; k >= 1; k >>= 1) {
+      for (int pl = 0; pl < C::QPW; ++pl) {
+        if (pl < npair) {
 #pragma unroll
-          for (int j = 0; j < C::CPL; ++j) acc[j] += __shfl_down_sync(0xffffffffu, acc[j], k * C::G);
+          for (int k = C::NG / 2; k >= 1; k >>= 1) {
+#pragma unroll
+            for (int j = 0; j < C::CPL; ++j) acc_g[pl][j] += __shfl_down_sync(0xffffffffu, acc_g[pl][j], k * C::G);
+          }
+          if (lane < C::G) Vec16<VT>::store(out + static_cast<int64_t>(p0 + pl) * D + lane * C::CPL, acc_g[pl]);
         }
-        if (lane < C::G) Vec16<VT>::store(out + static_cast<int64_t>(p0 + pl) * D + lane * C::CPL, acc);
       }
     }
-    __syncwarp();
   }
 }
 
 // ----------------------------------------------------------------------------------------- backward
-template <typename VT, typename LT, int D, int LP>
+template <typename VT, typename LT, int D, int LP, bool GROUPED>
 __global__ void __launch_bounds__(kThreads)
 msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                       const int64_t* __restrict__ level_start, const LT* __restrict__ loc,
                       const LT* __restrict__ aw, const VT* __restrict__ grad_out,
                       float* __restrict__ grad_value, LT* __restrict__ grad_loc, LT* __restrict__ grad_aw,
-                      int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq) {
+                      int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq,
+                      int G, float scale) {
   using C = Cfg2<VT, D, LP>;
   // <grad_out, corner row> per (corner, sample): [4][33] floats per warp.  The partials are folded inside the
   // corner group with shuffles first, so the tile stays tiny and shared memory stays small: the first version
@@ -172,7 +208,7 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
   __shared__ __align__(16) Slot s_slot[kWarpsPerCta][C::QPW * C::NSLOT];
   __shared__ float s_dot[kWarpsPerCta][4 * kDotStride];
 
-  stage_levels(s_lvl, shapes, level_start, L);
+  stage_levels(s_lvl, shapes, level_start, G * L);
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -196,80 +232,101 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
   for (uint32_t p0 = chunk_begin + warp * C::QPW; p0 < chunk_end; p0 += kWarpsPerCta * C::QPW) {
     const int npair = static_cast<int>(min(static_cast<uint32_t>(C::QPW), chunk_end - p0));
     const bool has_sample = lane < npair * LP;
-    SampleGeom geo;
-    float a = 0.f;
-    int lvl_h = 0, lvl_w = 0;
+    float x = 0.f, y = 0.f, a = 0.f;
+    uint32_t n = 0, m = 0;
     if (has_sample) {
       const uint32_t pair = p0 + ps;
       const uint32_t nq = fd_div(pair, div_m);
-      const uint32_t m = pair - nq * div_m.d;
-      const uint32_t n = fd_div(pair, div_mq);
-      float x, y;
+      m = pair - nq * div_m.d;
+      n = fd_div(pair, div_mq);
       load_loc_aw<LT>(loc, aw, static_cast<int64_t>(p0) * LP + lane, x, y, a);
-      const LevelInfo li = s_lvl[lvl];
-      lvl_h = li.H; lvl_w = li.W;
-      geo = make_slots2<C::D16, C::LPP>(my_slots + ps * C::NSLOT, ss, x, y, a, li, n, m, S, M);
+      a *= scale;                                   // d out / d value carries the group scale; aw/loc grads are rescaled below
     }
-    __syncwarp();
+    float go_g[GROUPED ? C::QPW : 1][C::CPL];      // GROUPED: grad_out rows stay in registers across the level tables
+    if constexpr (GROUPED) {
+#pragma unroll
+      for (int pl = 0; pl < C::QPW; ++pl)
+        if (pl < npair) Vec16<VT>::load(grad_out + static_cast<int64_t>(p0 + pl) * D + c * C::CPL, go_g[pl]);
+    }
+    float g_aw = 0.f, g_x = 0.f, g_y = 0.f;
+
+    for (int g = 0; g < (GROUPED ? G : 1); ++g) {
+      SampleGeom geo;
+      int lvl_h = 0, lvl_w = 0;
+      if (has_sample) {
+        const LevelInfo li = s_lvl[g * L + lvl];
+        lvl_h = li.H; lvl_w = li.W;
+        geo = make_slots2<C::D16, C::LPP>(my_slots + ps * C::NSLOT, ss, x, y, a, li, n, m, S, M);
+      }
+      __syncwarp();
 
 #pragma unroll
-    for (int pl = 0; pl < C::QPW; ++pl) {
-      if (pl < npair) {
-        float go[C::CPL];
-        Vec16<VT>::load(grad_out + static_cast<int64_t>(p0 + pl) * D + c * C::CPL, go);
-        const uint4* stream = reinterpret_cast<const uint4*>(my_stream + pl * C::NSLOT);
+      for (int pl = 0; pl < C::QPW; ++pl) {
+        if (pl < npair) {
+          float go[C::CPL];
+          if constexpr (GROUPED) {
 #pragma unroll
-        for (int it = 0; it < C::SPG / 2; ++it) {
-          const uint4 two = stream[it];
-          const uint32_t off[2] = {two.x, two.z};
-          const float w[2] = {__uint_as_float(two.y), __uint_as_float(two.w)};
+            for (int j = 0; j < C::CPL; ++j) go[j] = go_g[GROUPED ? pl : 0][j];
+          } else {
+            Vec16<VT>::load(grad_out + static_cast<int64_t>(p0 + pl) * D + c * C::CPL, go);
+          }
+          const uint4* stream = reinterpret_cast<const uint4*>(my_stream + pl * C::NSLOT);
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            float dot = 0.f;
-            if (active && off[u] != kInvalidOff) {
-              float v[C::CPL];
-              Vec16<VT>::load(row_ptr(vlane, off[u]), v);
+          for (int it = 0; it < C::SPG / 2; ++it) {
+            const uint4 two = stream[it];
+            const uint32_t off[2] = {two.x, two.z};
+            const float w[2] = {__uint_as_float(two.y), __uint_as_float(two.w)};
 #pragma unroll
-              for (int j = 0; j < C::CPL; ++j) dot = fmaf(go[j], v[j], dot);
-              float* gv = const_cast<float*>(reinterpret_cast<const float*>(
-                  reinterpret_cast<const char*>(gvlane) + static_cast<uint64_t>(off[u]) * (16u * sizeof(float) / sizeof(VT))));
+            for (int u = 0; u < 2; ++u) {
+              float dot = 0.f;
+              if (active && off[u] != kInvalidOff) {
+                float v[C::CPL];
+                Vec16<VT>::load(row_ptr(vlane, off[u]), v);
 #pragma unroll
-              for (int j = 0; j < C::CPL; j += 4)
-                red_add_f32x4(gv + j, w[u] * go[j], w[u] * go[j + 1], w[u] * go[j + 2], w[u] * go[j + 3]);
-            }
-            // fold the G per-lane partials of this corner row (groups are G consecutive lanes)
-            if constexpr ((C::G & (C::G - 1)) == 0) {
+                for (int j = 0; j < C::CPL; ++j) dot = fmaf(go[j], v[j], dot);
+                float* gv = const_cast<float*>(reinterpret_cast<const float*>(
+                    reinterpret_cast<const char*>(gvlane) + static_cast<uint64_t>(off[u]) * (16u * sizeof(float) / sizeof(VT))));
 #pragma unroll
-              for (int o = C::G / 2; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-            } else {                                          // G = 6 or 3: walk down inside the group
-              float t = dot;
-#pragma unroll
-              for (int o = 1; o < C::G; ++o) {
-                const float nb = __shfl_down_sync(0xffffffffu, dot, o);
-                if (c + o < C::G) t += nb;
+                for (int j = 0; j < C::CPL; j += 4)
+                  red_add_f32x4(gv + j, w[u] * go[j], w[u] * go[j + 1], w[u] * go[j + 2], w[u] * go[j + 3]);
               }
-              dot = t;
+              // fold the G per-lane partials of this corner row (groups are G consecutive lanes)
+              if constexpr ((C::G & (C::G - 1)) == 0) {
+#pragma unroll
+                for (int o = C::G / 2; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+              } else {                                          // G = 6 or 3: walk down inside the group
+                float t = dot;
+#pragma unroll
+                for (int o = 1; o < C::G; ++o) {
+                  const float nb = __shfl_down_sync(0xffffffffu, dot, o);
+                  if (c + o < C::G) t += nb;
+                }
+                dot = t;
+              }
+              if (active && c == 0) dot_w[pl * LP + 2 * it + u] = dot;
             }
-            if (active && c == 0) dot_w[pl * LP + 2 * it + u] = dot;
           }
         }
       }
+      __syncwarp();
+
+      if (has_sample) {
+        float dc[4];                              // per-corner <grad_out, value row>
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dc[e] = dot_r[e * kDotStride];
+        const float hx = 1.f - geo.lx, hy = 1.f - geo.ly;
+        g_aw += hy * (hx * dc[0] + geo.lx * dc[1]) + geo.ly * (hx * dc[2] + geo.lx * dc[3]);
+        g_x += static_cast<float>(lvl_w) * (hy * (dc[1] - dc[0]) + geo.ly * (dc[3] - dc[2]));
+        g_y += static_cast<float>(lvl_h) * (hx * (dc[2] - dc[0]) + geo.lx * (dc[3] - dc[1]));
+      }
+      __syncwarp();
     }
-    __syncwarp();
 
     if (has_sample) {
-      float dc[4];                              // per-corner <grad_out, value row>
-#pragma unroll
-      for (int e = 0; e < 4; ++e) dc[e] = dot_r[e * kDotStride];
-      const float hx = 1.f - geo.lx, hy = 1.f - geo.ly;
-      const float g_aw = hy * (hx * dc[0] + geo.lx * dc[1]) + geo.ly * (hx * dc[2] + geo.lx * dc[3]);
-      const float g_x = a * static_cast<float>(lvl_w) * (hy * (dc[1] - dc[0]) + geo.ly * (dc[3] - dc[2]));
-      const float g_y = a * static_cast<float>(lvl_h) * (hx * (dc[2] - dc[0]) + geo.lx * (dc[3] - dc[1]));
       const int64_t si = static_cast<int64_t>(p0) * LP + lane;
-      store_pair(grad_loc + 2 * si, g_x, g_y);
-      st_from_float(grad_aw + si, g_aw);
+      store_pair(grad_loc + 2 * si, a * g_x, a * g_y);     // a already carries `scale`
+      st_from_float(grad_aw + si, scale * g_aw);
     }
-    __syncwarp();
   }
 }
 

@@ -25,7 +25,8 @@ __device__ __forceinline__ GeomG<AT> geom_generic(AT locx, AT locy, int H, int W
   const AT fx = floor(x), fy = floor(y);
   g.lx = x - fx;
   g.ly = y - fy;
-  const bool sane = (fx >= -1) && (fx <= static_cast<AT>(W)) && (fy >= -1) && (fy <= static_cast<AT>(H));
+  // strict predicate of the reference kernel (ms_deform_im2col_cuda.cuh:288)
+  const bool sane = (x > -1) && (x < static_cast<AT>(W)) && (y > -1) && (y < static_cast<AT>(H));
   g.x0 = sane ? static_cast<int>(fx) : -8;
   g.y0 = sane ? static_cast<int>(fy) : -8;
   g.okx0 = g.x0 >= 0 && g.x0 < W;

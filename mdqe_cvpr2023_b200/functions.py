@@ -39,6 +39,30 @@ class MSDeformAttnFunction(Function):
         return grad_value, None, None, grad_loc, grad_aw, None
 
 
+class MSDeformAttnGroupedFunction(Function):
+    """apply(value, spatial_shapes[G,L,2], level_start_index[G,L], sampling_locations, attention_weights, scale):
+    scale * sum over the G level tables, one kernel launch forward and one backward.  This is the clip-level ("temporal")
+    attention of the reference module (ms_deform_attn.py:219-235: one Function call per pyramid level, then a mean)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, value, spatial_shapes, level_start_index, sampling_locations, attention_weights, scale):
+        ctx.scale = float(scale)
+        output = ops.ms_deform_attn_grouped_forward(value, spatial_shapes, level_start_index, sampling_locations,
+                                                    attention_weights, ctx.scale)
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        value, shapes, level_start, loc, aw = ctx.saved_tensors
+        grad_value, grad_loc, grad_aw = ops.ms_deform_attn_grouped_backward(
+            value, shapes, level_start, loc, aw, grad_output.contiguous(), ctx.scale)
+        return grad_value, None, None, grad_loc, grad_aw, None
+
+
 class _MaskLogitsFunction(Function):
     @staticmethod
     def forward(ctx, coeff, proto):

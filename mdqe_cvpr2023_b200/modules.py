@@ -12,7 +12,8 @@ Kept identical so that mdqe/models/transformer_{enc,dec}.py and released checkpo
 What differs from the reference implementation (not from its results):
   * temporal mode hands the operator a *view* of the whole [B, T*S, M, D] value tensor and encodes
     "frame t of level l" in level_start_index (= t*S + start_l) instead of materialising four
-    `.contiguous()` copies per call (ms_deform_attn.py:222-224);
+    `.contiguous()` copies per call (ms_deform_attn.py:222-224); on the fast-kernel configurations all
+    pyramid levels run in ONE launch (MSDeformAttnGroupedFunction) with the mean folded in;
   * all tensor work below the Linear layers goes through MSDeformAttnFunction -> libmsda_b200.so.
 """
 import math
@@ -22,7 +23,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .functions import MSDeformAttnFunction
+from . import ops
+from .functions import MSDeformAttnFunction, MSDeformAttnGroupedFunction
 
 
 def _is_power_of_2(n):
@@ -160,6 +162,13 @@ class MSDeformAttn(nn.Module):
         locations, weights = self._sampling(query, reference_points)
         locations, weights = locations.contiguous(), weights.contiguous()
         frame_base = torch.arange(T, device=level_start.device, dtype=level_start.dtype) * S
+        n_lvl = input_spatial_shapes.shape[0]
+        if ops.grouped_supported(value, n_lvl, T, self.n_points):
+            # all pyramid levels in ONE launch: level table g = the T frames of pyramid level g, mean folded in
+            shapes_g = input_spatial_shapes.view(n_lvl, 1, 2).expand(n_lvl, T, 2).contiguous()
+            starts_g = (level_start.view(n_lvl, 1) + frame_base.view(1, T)).contiguous()
+            sampled = MSDeformAttnGroupedFunction.apply(value, shapes_g, starts_g, locations, weights, 1.0 / n_lvl)
+            return self.output_proj(sampled)
         sampled = None
         for lvl in range(input_spatial_shapes.shape[0]):
             shapes_l = input_spatial_shapes[lvl].view(1, 2).expand(T, 2).contiguous()

@@ -110,6 +110,66 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     return [grad_value, grad_loc, grad_aw]
 
 
+def grouped_supported(value, n_groups, n_levels, n_points):
+    """True when msda_forward_grouped / msda_backward_grouped implement this configuration (fast kernels only)."""
+    return (value.is_cuda and value.dim() == 4 and value.shape[3] in (32, 24) and value.dtype in (torch.float32, torch.bfloat16)
+            and n_levels * n_points in (8, 12, 16) and n_groups * n_levels <= 32 and value.numel() < 2 ** 31)
+
+
+def _grouped_dims(value, shapes, level_start, loc, aw, who):
+    if shapes.dim() != 3 or shapes.shape[2] != 2 or tuple(level_start.shape) != tuple(shapes.shape[:2]):
+        raise RuntimeError(f"{who}: expected spatial_shapes[G,L,2] and level_start_index[G,L]")
+    if shapes.dtype != torch.int64 or level_start.dtype != torch.int64:
+        raise RuntimeError(f"{who}: spatial_shapes and level_start_index must be int64")
+    G, L = shapes.shape[0], shapes.shape[1]
+    N, S, M, D = value.shape
+    Lq, P = loc.shape[1], loc.shape[4]
+    if tuple(loc.shape) != (N, Lq, M, L, P, 2) or tuple(aw.shape) != (N, Lq, M, L, P):
+        raise RuntimeError(f"{who}: inconsistent shapes value={tuple(value.shape)} sampling_loc={tuple(loc.shape)} "
+                           f"attn_weight={tuple(aw.shape)} for L={L}")
+    return N, S, M, D, G, L, Lq, P
+
+
+def ms_deform_attn_grouped_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, scale):
+    """scale * sum_g msda(value, spatial_shapes[g], level_start_index[g], sampling_loc, attn_weight) in ONE launch
+    (the clip-level decoder attention of ms_deform_attn.py:219-235).  -> Tensor[N, Lq, M*D]."""
+    who = "ms_deform_attn_grouped_forward"
+    _check_inputs(who, [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                        ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)])
+    N, S, M, D, G, L, Lq, P = _grouped_dims(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, who)
+    code = _dtype_code(value, sampling_loc, attn_weight, who)
+    lib = _lib.load()
+    with torch.cuda.device(value.device):
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        rc = lib.msda_forward_grouped(_stream_ptr(value.device), code, value.data_ptr(), spatial_shapes.data_ptr(),
+                                      level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                                      N, S, M, D, G, L, Lq, P, float(scale), out.data_ptr())
+    _lib.check(rc, who)
+    return out
+
+
+def ms_deform_attn_grouped_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, scale):
+    who = "ms_deform_attn_grouped_backward"
+    _check_inputs(who, [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                        ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("grad_output", grad_output)])
+    N, S, M, D, G, L, Lq, P = _grouped_dims(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, who)
+    if grad_output.dtype != value.dtype or grad_output.numel() != N * Lq * M * D:
+        raise RuntimeError(f"{who}: grad_output must be {value.dtype} with {N * Lq * M * D} elements")
+    code = _dtype_code(value, sampling_loc, attn_weight, who)
+    lib = _lib.load()
+    with torch.cuda.device(value.device):
+        grad_value, grad_loc, grad_aw = torch.empty_like(value), torch.empty_like(sampling_loc), torch.empty_like(attn_weight)
+        ws_bytes = lib.msda_backward_workspace_bytes(code, N, S, M, D)
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
+        rc = lib.msda_backward_grouped(_stream_ptr(value.device), code, value.data_ptr(), spatial_shapes.data_ptr(),
+                                       level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                                       grad_output.data_ptr(), N, S, M, D, G, L, Lq, P, float(scale),
+                                       grad_value.data_ptr(), grad_loc.data_ptr(), grad_aw.data_ptr(),
+                                       ws.data_ptr() if ws is not None else None, ws_bytes)
+    _lib.check(rc, who)
+    return [grad_value, grad_loc, grad_aw]
+
+
 _MASK_CODES = {torch.float32: _lib.MSDA_F32, torch.bfloat16: _lib.MSDA_BF16}
 
 

@@ -77,5 +77,5 @@ def kink_mask(inp, eps=1e-6):
     H = shapes[:, 0].view(1, 1, 1, -1, 1).float()
     px, py = loc[..., 0] * W - 0.5, loc[..., 1] * H - 0.5
     near = lambda t, size: (t - t.round()).abs() < eps * size
-    inside = (px > -1) & (px < W) & (py > -1) & (py < H)
+    inside = (px >= -1 - 1e-4) & (px <= W + 1e-4) & (py >= -1 - 1e-4) & (py <= H + 1e-4)   # the borders -1 and W/H are kinks too
     return ((near(px, W) | near(py, H)) & inside).numpy()

@@ -34,7 +34,7 @@ def run_op(inp):
     return out, gv, gl, ga
 
 
-def check(got, want, tol, what="", inp=None):
+def check(got, want, tol, what="", inp=None, max_kink=2e-3):
     """all four results against the oracle; grad_loc is compared away from pixel-centre kinks (kink_mask)."""
     names = ("out", "grad_value", "grad_loc", "grad_aw")
     for g, w, n in zip(got, want, names):
@@ -42,7 +42,7 @@ def check(got, want, tol, what="", inp=None):
         w = np.asarray(w).reshape(tuple(g.shape))
         if n == "grad_loc" and inp is not None:
             kink = kink_mask(inp)
-            assert kink.mean() < 2e-3, "kink mask must stay a (numerically) measure-zero exclusion"
+            assert kink.mean() < max_kink, "kink mask must stay a (numerically) measure-zero exclusion"
             g = g.detach().cpu().clone()
             g[torch.from_numpy(kink)] = 0
             w = w.copy()
@@ -129,7 +129,8 @@ def test_bf16_vs_oracle_on_rounded_inputs(loc_dtype, D):
         inp[k] = inp[k].to(loc_dtype)
     got = run_op(to_cuda(inp))
     assert got[0].dtype == torch.bfloat16 and got[1].dtype == torch.bfloat16 and got[2].dtype == loc_dtype
-    check(got, oracle_all(inp), 2e-2, f"bf16 loc={loc_dtype} D{D}", inp)
+    # bf16 locations are quantised to 8 bits: a few percent of them land exactly on pixel-centre lines
+    check(got, oracle_all(inp), 2e-2, f"bf16 loc={loc_dtype} D{D}", inp, max_kink=0.05 if loc_dtype == torch.bfloat16 else 2e-3)
 
 
 def test_temporal_level_start_windows():
@@ -278,3 +279,65 @@ def test_launch_counter_counts_kernels():
     _lib.launch_count_reset()
     run_op(inp)
     assert _lib.launch_count() == 2
+
+
+@pytest.mark.parametrize("T,D,dtype", [(4, 32, torch.float32), (3, 32, torch.float32), (2, 24, torch.float32), (4, 32, torch.bfloat16)])
+def test_grouped_temporal_form_vs_oracle(T, D, dtype):
+    """msda_forward/backward_grouped: G = 4 pyramid levels x L = T frames sharing loc/aw, scale 1/G, in one launch,
+    against the oracle evaluated per pyramid level and averaged (what ms_deform_attn.py:219-235 computes)."""
+    from mdqe_cvpr2023_b200 import ops
+    g = torch.Generator().manual_seed(20 + T)
+    pyr = [(12, 20), (6, 10), (3, 5), (2, 3)]
+    S = sum(h * w for h, w in pyr)
+    starts = [0, 240, 300, 315]
+    B, Q, M, P, G = 2, 37, 8, 4, 4
+    value = torch.randn(B, T * S, M, D, generator=g)
+    loc = torch.rand(B, Q, M, T, P, 2, generator=g) * 1.2 - 0.1
+    aw = torch.softmax(torch.randn(B, Q, M, T * P, generator=g), -1).view(B, Q, M, T, P)
+    go = torch.randn(B, Q, M * D, generator=g)
+    if dtype == torch.bfloat16:
+        value, loc, aw, go = (t.bfloat16().float() for t in (value, loc, aw, go))
+    shapes_g = torch.tensor([[pyr[l]] * T for l in range(G)])                       # [G, T, 2]
+    starts_g = torch.tensor([[t * S + starts[l] for t in range(T)] for l in range(G)])
+    want = [0, 0, 0, 0]
+    for l in range(G):
+        inp = dict(value=value, shapes=shapes_g[l], level_start=starts_g[l], loc=loc, aw=aw, grad_out=go)
+        res = oracle_all(inp)
+        want = [w + r / G for w, r in zip(want, res)]
+    dev = lambda t: t.to(dtype).cuda() if t.is_floating_point() else t.cuda()
+    out = ops.ms_deform_attn_grouped_forward(dev(value), dev(shapes_g), dev(starts_g), dev(loc), dev(aw), 1.0 / G)
+    gv, gl, ga = ops.ms_deform_attn_grouped_backward(dev(value), dev(shapes_g), dev(starts_g), dev(loc), dev(aw), dev(go), 1.0 / G)
+    check((out, gv, gl, ga), want, 2e-5 if dtype == torch.float32 else 2e-2, f"grouped T{T} D{D}")
+
+
+def test_temporal_module_grouped_equals_per_level_loop():
+    """The module's one-launch temporal path (R50 sizes: D=32, T=4) against its own per-level loop path."""
+    import mdqe_cvpr2023_b200.modules as M
+    from mdqe_cvpr2023_b200 import ops
+    torch.manual_seed(0)
+    mod = M.MSDeformAttn(d_model=256, n_levels=4, n_heads=8, n_points=4, n_frames=4, pred_offsets=False, mode="temporal").cuda()
+    with torch.no_grad():
+        for p in mod.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    shapes = torch.tensor([(12, 20), (6, 10), (3, 5), (2, 3)], device="cuda")
+    S = 321
+    B, Q, T = 2, 19, 4
+    x = torch.randn(B, T, S, 256, device="cuda")
+    q = torch.randn(B, Q, 256, device="cuda")
+    ref = torch.cat([torch.rand(B, Q, 2, device="cuda"), torch.rand(B, Q, 2, device="cuda") * 0.3 + 0.05], -1)
+
+    def run(grouped):
+        orig = ops.grouped_supported
+        M.ops.grouped_supported = orig if grouped else (lambda *a: False)
+        try:
+            xi, qi = x.clone().requires_grad_(True), q.clone().requires_grad_(True)
+            mod.zero_grad()
+            out = mod(qi, ref, xi, shapes, None)
+            out.square().sum().backward()
+            return out.detach(), xi.grad, qi.grad, {k: p.grad.clone() for k, p in mod.named_parameters()}
+        finally:
+            M.ops.grouped_supported = orig
+    a, b = run(True), run(False)
+    assert nerr(a[0], b[0]) < 1e-5 and nerr(a[1], b[1]) < 1e-4 and nerr(a[2], b[2]) < 1e-4
+    for k in a[3]:
+        assert nerr(a[3][k], b[3][k]) < 1e-4, k
