@@ -181,12 +181,35 @@ int mask_backward_dispatch(cudaStream_t st, int dtype, const void* coeff, const 
     return 0;
   }
   if (!grad_coeff && !grad_proto) return 0;
-  const dim3 grid(static_cast<unsigned>((Ncols + kMaskTN - 1) / kMaskTN), (K + kMaskKC - 1) / kMaskKC, B);
   ProfScope prof(st, MSDA_PROF_MASK_BWD, (int64_t)B * Q * Ncols);
-  mask_bwd_simt_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(coeff), static_cast<const float*>(proto),
-                                             static_cast<const float*>(grad_out), static_cast<float*>(grad_coeff),
-                                             static_cast<float*>(grad_proto), Q, K, Ncols);
-  return after_launch("mask_bwd_simt_kernel");
+  if (option("mask_variant") == 4) {                    // 4 = first-generation fused backward (A/B timing)
+    const dim3 grid(static_cast<unsigned>((Ncols + kMaskTN - 1) / kMaskTN), (K + kMaskKC - 1) / kMaskKC, B);
+    mask_bwd_simt_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(coeff), static_cast<const float*>(proto),
+                                               static_cast<const float*>(grad_out), static_cast<float*>(grad_coeff),
+                                               static_cast<float*>(grad_proto), Q, K, Ncols);
+    return after_launch("mask_bwd_simt_kernel");
+  }
+  const unsigned kblocks = (K + 31) / 32;
+  if (grad_coeff) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int q_blocks = (Q + kGcQ - 1) / kGcQ;
+    int64_t slices = (2LL * sms) / ((int64_t)B * q_blocks * kblocks);
+    if (slices < 1) slices = 1;
+    int64_t cols = ((Ncols + slices - 1) / slices + kGcNC - 1) / kGcNC * kGcNC;
+    slices = (Ncols + cols - 1) / cols;
+    const dim3 grid(static_cast<unsigned>(slices), kblocks, static_cast<unsigned>(B * q_blocks));
+    mask_grad_coeff_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(proto), static_cast<const float*>(grad_out),
+                                                 static_cast<float*>(grad_coeff), Q, K, Ncols, cols, q_blocks);
+    if (int rc = after_launch("mask_grad_coeff_kernel")) return rc;
+  }
+  if (grad_proto) {
+    const dim3 grid(static_cast<unsigned>((Ncols + kGpTN - 1) / kGpTN), kblocks, B);
+    mask_grad_proto_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(coeff), static_cast<const float*>(grad_out),
+                                                 static_cast<float*>(grad_proto), Q, K, Ncols);
+    if (int rc = after_launch("mask_grad_proto_kernel")) return rc;
+  }
+  return 0;
 }
 
 }  // namespace msda

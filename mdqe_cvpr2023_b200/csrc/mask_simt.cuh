@@ -190,4 +190,153 @@ mask_bwd_simt_kernel(const float* __restrict__ coeff, const float* __restrict__ 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Second-generation fp32 backward: two register-tiled kernels instead of the fused one above (542 us at R50_360;
+// its grad_coeff half issued 5 shared loads per 16 FMAs).  grad_out (48 MB) is read by both, back to back, so the
+// second read comes out of the 126 MB L2.
+//
+// grad_proto[b,k,n] = sum_q coeff[b,q,k] * go[b,q,n]:  CTA = 32 k x 256 columns, thread = 4 k x 8 columns,
+// q walked in chunks of 28 rows through shared memory (coeff reads are warp broadcasts).
+constexpr int kGpTN = 256, kGpQC = 28;
+__global__ void __launch_bounds__(256)
+mask_grad_proto_kernel(const float* __restrict__ coeff, const float* __restrict__ go, float* __restrict__ gproto,
+                       int Q, int K, int64_t Ncols) {
+  __shared__ __align__(16) float sC[kGpQC][32];
+  __shared__ __align__(16) float sG[kGpQC][kGpTN];
+  const int b = blockIdx.z, k0 = blockIdx.y * 32;
+  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * kGpTN;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // ty: 4 k each, tx: columns tx*4 and 128 + tx*4
+  const float* A = coeff + static_cast<int64_t>(b) * Q * K;
+  const float* G = go + static_cast<int64_t>(b) * Q * Ncols;
+  const bool vec = (Ncols % 4 == 0);
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int q0 = 0; q0 < Q; q0 += kGpQC) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kGpQC * 32; idx += 256) {
+      const int qi = idx >> 5, kk = idx & 31;
+      sC[qi][kk] = (q0 + qi < Q && k0 + kk < K) ? __ldg(A + static_cast<int64_t>(q0 + qi) * K + k0 + kk) : 0.f;
+    }
+    for (int idx = threadIdx.x; idx < kGpQC * (kGpTN / 4); idx += 256) {
+      const int qi = idx / (kGpTN / 4), c4 = (idx % (kGpTN / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q0 + qi < Q) {
+        const float* src = G + static_cast<int64_t>(q0 + qi) * Ncols + n0 + c4;
+        if (vec && n0 + c4 + 3 < Ncols) v = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          if (n0 + c4 + 0 < Ncols) v.x = __ldg(src + 0);
+          if (n0 + c4 + 1 < Ncols) v.y = __ldg(src + 1);
+          if (n0 + c4 + 2 < Ncols) v.z = __ldg(src + 2);
+          if (n0 + c4 + 3 < Ncols) v.w = __ldg(src + 3);
+        }
+      }
+      *reinterpret_cast<float4*>(&sG[qi][c4]) = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int qi = 0; qi < kGpQC; ++qi) {
+      const float4 a = *reinterpret_cast<const float4*>(&sC[qi][ty * 4]);
+      const float4 g0 = *reinterpret_cast<const float4*>(&sG[qi][tx * 4]);
+      const float4 g1 = *reinterpret_cast<const float4*>(&sG[qi][128 + tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], gv[j], acc[i][j]);
+    }
+  }
+  float* GP = gproto + static_cast<int64_t>(b) * K * Ncols;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty * 4 + i;
+    if (k >= K) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t n = n0 + h * 128 + tx * 4;
+      float* dst = GP + static_cast<int64_t>(k) * Ncols + n;
+      if (vec && n + 3 < Ncols) *reinterpret_cast<float4*>(dst) = make_float4(acc[i][4 * h], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]);
+      else
+        for (int j = 0; j < 4; ++j)
+          if (n + j < Ncols) dst[j] = acc[i][4 * h + j];
+    }
+  }
+}
+
+// grad_coeff[b,q,k] = sum_n go[b,q,n] * proto[b,k,n]:  CTA = all (<= 256) q x 32 k over a slice of the columns,
+// thread = 8 q x 4 k (rows qg + 32 i, columns kg + 8 j: neighbouring lanes touch neighbouring shared-memory rows,
+// whose 36-float pitch puts them in different banks), columns walked 32 at a time through shared memory; per-CTA partial sums are added to
+// grad_coeff with atomics (the caller zero-fills it).  grid (column slices, ceil(K/32), B * ceil(Q/256)).
+constexpr int kGcQ = 256, kGcNC = 32, kGcPitch = kGcNC + 4;
+__global__ void __launch_bounds__(256)
+mask_grad_coeff_kernel(const float* __restrict__ proto, const float* __restrict__ go, float* __restrict__ gcoeff,
+                       int Q, int K, int64_t Ncols, int64_t cols_per_cta, int q_blocks) {
+  __shared__ __align__(16) float sG[kGcQ][kGcPitch];      // pitch 36 floats: the 8 q-groups of a warp hit different banks
+  __shared__ __align__(16) float sP[32][kGcPitch];
+  const int b = blockIdx.z / q_blocks, qb = blockIdx.z % q_blocks;
+  const int q_base = qb * kGcQ, k0 = blockIdx.y * 32;
+  const int64_t n_begin = static_cast<int64_t>(blockIdx.x) * cols_per_cta;
+  const int64_t n_end = min(Ncols, n_begin + cols_per_cta);
+  const int kg = threadIdx.x & 7, qg = threadIdx.x >> 3;           // 8 k-groups x 32 q-groups (8 q each)
+  const float* Pm = proto + static_cast<int64_t>(b) * K * Ncols;
+  const float* G = go + static_cast<int64_t>(b) * Q * Ncols;
+  const bool vec = (Ncols % 4 == 0);
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int64_t n0 = n_begin; n0 < n_end; n0 += kGcNC) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < (kGcQ + 32) * (kGcNC / 4); idx += 256) {
+      const int r = idx / (kGcNC / 4), c4 = (idx % (kGcNC / 4)) * 4;
+      const bool is_p = r >= kGcQ;
+      const int row = is_p ? (r - kGcQ) : r;
+      const bool row_ok = is_p ? (k0 + row < K) : (q_base + row < Q);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_ok) {
+        const float* src = (is_p ? Pm + static_cast<int64_t>(k0 + row) * Ncols : G + static_cast<int64_t>(q_base + row) * Ncols) + n0 + c4;
+        if (vec && n0 + c4 + 3 < n_end) v = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          if (n0 + c4 + 0 < n_end) v.x = __ldg(src + 0);
+          if (n0 + c4 + 1 < n_end) v.y = __ldg(src + 1);
+          if (n0 + c4 + 2 < n_end) v.z = __ldg(src + 2);
+          if (n0 + c4 + 3 < n_end) v.w = __ldg(src + 3);
+        }
+      }
+      *reinterpret_cast<float4*>(is_p ? &sP[row][c4] : &sG[row][c4]) = v;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int nn = 0; nn < kGcNC; nn += 4) {
+      float4 p[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) p[j] = *reinterpret_cast<const float4*>(&sP[kg + 8 * j][nn]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 g = *reinterpret_cast<const float4*>(&sG[qg + 32 * i][nn]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          acc[i][j] = fmaf(g.x, p[j].x, fmaf(g.y, p[j].y, fmaf(g.z, p[j].z, fmaf(g.w, p[j].w, acc[i][j]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int q = q_base + qg + 32 * i;
+    if (q >= Q) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + kg + 8 * j;
+      if (k < K) atomicAdd(gcoeff + (static_cast<int64_t>(b) * Q + q) * K + k, acc[i][j]);
+    }
+  }
+}
+
 }  // namespace msda

@@ -51,4 +51,19 @@ for plane in ((96, 160), (160, 288)):
             ts.append(a.elapsed_time(b) * 1e3)
         ts.sort()
         print(f"plane {plane} {name}: median {ts[10]:.1f} us (events around the torch call)", flush=True)
+# backward (fp32): second-generation SIMT pair vs the first fused kernel
+    go = torch.randn(1, 196, 4, *plane, device="cuda")
+    for name, variant in (("bwd gen2", 0), ("bwd gen1 fused", 4)):
+        _lib.set_option("mask_variant", variant)
+        ops.mask_logits_backward(c32, p32, go); torch.cuda.synchronize()
+        _lib.profile_read(_lib.PROF_MASK_BWD)
+        for _ in range(10):
+            flush.fill_(1.0)
+            gc, gp = ops.mask_logits_backward(c32, p32, go)
+        torch.cuda.synchronize()
+        ms, cnt = _lib.profile_read(_lib.PROF_MASK_BWD)
+        want_c = torch.einsum("bqthw,bmthw->bqm", go.double(), p32.double())
+        want_p = torch.einsum("bqm,bqthw->bmthw", c32.double(), go.double())
+        print(f"plane {plane} {name}: {ms / cnt * 1e3:.1f} us  nerr gc {nerr(gc, want_c):.2e} gp {nerr(gp, want_p):.2e}", flush=True)
+    _lib.set_option("mask_variant", 0)
 _lib.set_option("profile", 0)
