@@ -144,8 +144,17 @@ static FastDiv make_fastdiv(uint32_t d) {
 
 static bool fast2_lp(int lp) { return lp == 16 || lp == 12 || lp == 8; }
 
+// Split the level tables of a grouped call across CTAs?  Only worth it (and only implemented) for all-fp32 calls
+// that cannot fill the GPU on their own: fewer than ~4 CTAs per SM.
+template <typename VT, typename LT>
+static bool split_groups(const Problem& pb) {
+  if (pb.G <= 1 || !std::is_same<VT, float>::value || !std::is_same<LT, float>::value) return false;
+  if (g_opt.chunk_pairs.load() < 0) return false;           // chunk_pairs = -1 disables the split (A/B timing)
+  return pb.n_pairs < 148LL * 4 * 16;
+}
+
 template <typename VT, typename LT, int D, int MINB>
-static void launch_fwd2_lp(cudaStream_t st, const Problem& pb, unsigned grid, int chunk, const VT* v, const int64_t* shapes,
+static void launch_fwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int chunk, const VT* v, const int64_t* shapes,
                            const int64_t* lsi, const LT* lc, const LT* a, VT* o) {
   const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
   const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
@@ -161,7 +170,7 @@ static void launch_fwd2_lp(cudaStream_t st, const Problem& pb, unsigned grid, in
 }
 
 template <typename VT, typename LT, int D>
-static void launch_bwd2_lp(cudaStream_t st, const Problem& pb, unsigned grid, int chunk, const VT* v, const int64_t* shapes,
+static void launch_bwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int chunk, const VT* v, const int64_t* shapes,
                            const int64_t* lsi, const LT* lc, const LT* a, const VT* go, float* gv, LT* gl, LT* ga) {
   const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
   const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
@@ -189,13 +198,18 @@ static int launch_fwd(cudaStream_t st, const Problem& pb, bool fast, const void*
       const int chunk = pick_chunk(pb);
       const unsigned grid = static_cast<unsigned>((pb.n_pairs + chunk - 1) / chunk);
       if (g_opt.fwd_variant.load() != 2 && fast2_lp(pb.L * pb.P)) {
+        dim3 grid2(grid, 1, 1);
+        if (split_groups<VT, LT>(pb)) {      // small grouped call: one CTA row per level table, reductions into zeroed `out`
+          grid2.y = pb.G;
+          if (check_cuda(cudaMemsetAsync(o, 0, (size_t)pb.n_pairs * pb.D * sizeof(VT), st), "cudaMemsetAsync(out)")) return MSDA_ERR_CUDA;
+        }
         const bool lean = g_opt.fwd_variant.load() != 3;      // default: register-lean schedule (82 vs 90 us on the encoder shape, profiles/r01d); 3 = batched gathers
         if (pb.D == 32) {
-          if (lean) launch_fwd2_lp<VT, LT, 32, 6>(st, pb, grid, chunk, v, shapes, lsi, lc, a, o);
-          else launch_fwd2_lp<VT, LT, 32, 3>(st, pb, grid, chunk, v, shapes, lsi, lc, a, o);
+          if (lean) launch_fwd2_lp<VT, LT, 32, 6>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);
+          else launch_fwd2_lp<VT, LT, 32, 3>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);
         } else {
-          if (lean) launch_fwd2_lp<VT, LT, 24, 6>(st, pb, grid, chunk, v, shapes, lsi, lc, a, o);
-          else launch_fwd2_lp<VT, LT, 24, 3>(st, pb, grid, chunk, v, shapes, lsi, lc, a, o);
+          if (lean) launch_fwd2_lp<VT, LT, 24, 6>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);
+          else launch_fwd2_lp<VT, LT, 24, 3>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);
         }
         return after_launch("msda_fwd_fast2_kernel");
       }
@@ -228,8 +242,15 @@ static int launch_bwd(cudaStream_t st, const Problem& pb, bool fast, const void*
       const int chunk = pick_chunk(pb);
       const unsigned grid = static_cast<unsigned>((pb.n_pairs + chunk - 1) / chunk);
       if (g_opt.bwd_variant.load() != 2 && fast2_lp(pb.L * pb.P)) {
-        if (pb.D == 32) launch_bwd2_lp<VT, LT, 32>(st, pb, grid, chunk, v, shapes, lsi, lc, a, go, gv_acc, gl, ga);
-        else launch_bwd2_lp<VT, LT, 24>(st, pb, grid, chunk, v, shapes, lsi, lc, a, go, gv_acc, gl, ga);
+        dim3 grid2(grid, 1, 1);
+        if (split_groups<VT, LT>(pb)) {
+          grid2.y = pb.G;
+          const size_t n_smp = (size_t)pb.n_pairs * pb.L * pb.P;
+          if (check_cuda(cudaMemsetAsync(gl, 0, n_smp * 2 * sizeof(LT), st), "cudaMemsetAsync(grad_loc)")) return MSDA_ERR_CUDA;
+          if (check_cuda(cudaMemsetAsync(ga, 0, n_smp * sizeof(LT), st), "cudaMemsetAsync(grad_aw)")) return MSDA_ERR_CUDA;
+        }
+        if (pb.D == 32) launch_bwd2_lp<VT, LT, 32>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, go, gv_acc, gl, ga);
+        else launch_bwd2_lp<VT, LT, 24>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, go, gv_acc, gl, ga);
         return after_launch("msda_bwd_fast2_kernel");
       }
       if (pb.D == 32)

@@ -12,6 +12,8 @@
 //     offsets) and phase 3 folds them per corner.
 #pragma once
 
+#include <type_traits>
+
 #include "msda_fast.cuh"
 
 namespace msda {
@@ -119,7 +121,12 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
         for (int j = 0; j < C::CPL; ++j) acc_g[pl][j] = 0.f;
     }
 
-    for (int g = 0; g < (GROUPED ? G : 1); ++g) {
+    // gridDim.y > 1: the level tables are split across CTAs (small clip-level calls are parallelism bound: 1568 pairs
+    // are 98 CTAs); each CTA then adds its table's contribution into a zero-filled fp32 `out` with vector reductions
+    const bool g_split = GROUPED && gridDim.y > 1;
+    const int g_begin = g_split ? static_cast<int>(blockIdx.y) : 0;
+    const int g_end = GROUPED ? (g_split ? g_begin + 1 : G) : 1;
+    for (int g = g_begin; g < g_end; ++g) {
       if (has_sample) make_slots2<C::D16, C::LPP>(my_slots + ps * C::NSLOT, ss, x, y, a, s_lvl[g * L + lvl], n, m, S, M);
       __syncwarp();
 #pragma unroll
@@ -183,7 +190,15 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 #pragma unroll
             for (int j = 0; j < C::CPL; ++j) acc_g[pl][j] += __shfl_down_sync(0xffffffffu, acc_g[pl][j], k * C::G);
           }
-          if (lane < C::G) Vec16<VT>::store(out + static_cast<int64_t>(p0 + pl) * D + lane * C::CPL, acc_g[pl]);
+          if (lane < C::G) {
+            VT* dst = out + static_cast<int64_t>(p0 + pl) * D + lane * C::CPL;
+            if constexpr (std::is_same<VT, float>::value) {
+              if (g_split) red_add_f32x4(dst, acc_g[pl][0], acc_g[pl][1], acc_g[pl][2], acc_g[pl][3]);
+              else Vec16<VT>::store(dst, acc_g[pl]);
+            } else {
+              Vec16<VT>::store(dst, acc_g[pl]);
+            }
+          }
         }
       }
     }
@@ -250,7 +265,10 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
     }
     float g_aw = 0.f, g_x = 0.f, g_y = 0.f;
 
-    for (int g = 0; g < (GROUPED ? G : 1); ++g) {
+    const bool g_split = GROUPED && gridDim.y > 1;       // see the forward kernel; grad_loc / grad_aw are then accumulated
+    const int g_begin = g_split ? static_cast<int>(blockIdx.y) : 0;
+    const int g_end = GROUPED ? (g_split ? g_begin + 1 : G) : 1;
+    for (int g = g_begin; g < g_end; ++g) {
       SampleGeom geo;
       int lvl_h = 0, lvl_w = 0;
       if (has_sample) {
@@ -324,8 +342,19 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 
     if (has_sample) {
       const int64_t si = static_cast<int64_t>(p0) * LP + lane;
-      store_pair(grad_loc + 2 * si, a * g_x, a * g_y);     // a already carries `scale`
-      st_from_float(grad_aw + si, scale * g_aw);
+      if constexpr (std::is_same<LT, float>::value) {
+        if (g_split) {                                       // zero-filled by the host
+          atomicAdd(grad_loc + 2 * si, a * g_x);
+          atomicAdd(grad_loc + 2 * si + 1, a * g_y);
+          atomicAdd(grad_aw + si, scale * g_aw);
+        } else {
+          store_pair(grad_loc + 2 * si, a * g_x, a * g_y);     // a already carries `scale`
+          st_from_float(grad_aw + si, scale * g_aw);
+        }
+      } else {
+        store_pair(grad_loc + 2 * si, a * g_x, a * g_y);
+        st_from_float(grad_aw + si, scale * g_aw);
+      }
     }
   }
 }
