@@ -144,7 +144,7 @@ class DeviceStep:
         self.code = libmod.MSDA_BF16 if dtype == "bf16" else libmod.MSDA_F32
         self.mcode = self.code
         self.keep = []
-        self.fwd, self.bwd = [], []
+        self.fwd, self.bwd, self.kinds = [], [], []
         cache = {}
 
         def dev(t, cast=True):
@@ -165,6 +165,7 @@ class DeviceStep:
             ws = torch.empty(max(ws_bytes // 4, 1), dtype=torch.float32, device=device)
             self.keep += [v, loc, aw, go, sh, ls, out, gv, gl, ga, ws]
             grouped = c["kind"] == "dec_temporal_grouped"
+            self.kinds.append(c["kind"])
             dims = (N, S, M, D, 4, L, Lq, P, 0.25) if grouped else (N, S, M, D, L, Lq, P)
             self.fwd.append((grouped, (self.code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr()) + dims
                              + (out.data_ptr(),)))
@@ -182,16 +183,25 @@ class DeviceStep:
         self.keep += [mc, mp, mo, c32, p32, g32, gc, gp]
         self.outputs = dict(mask=mo)
 
-    def run(self):
-        """enqueue one step on the current stream (no host sync)."""
+    def run(self, part="all"):
+        """enqueue one step on the current stream (no host sync).  part "head" = forward + mask + decoder backward,
+        part "tail" = encoder backward (the split lets the multi-GPU run overlap the decoder-gradient all-reduce with
+        the encoder backward, as DDP's buckets do)."""
         lib = self.lib
         st = self.torch.cuda.current_stream(self.device).cuda_stream
         rc = 0
-        for grouped, a in self.fwd:
-            rc |= (lib.msda_forward_grouped if grouped else lib.msda_forward)(st, *a)
-        rc |= lib.mask_logits_forward(st, *self.mask_fwd)
-        rc |= lib.mask_logits_backward(st, *self.mask_bwd)
-        for grouped, a in reversed(self.bwd):
+        n_enc = sum(1 for k in self.kinds if k == "enc")
+        if part in ("all", "head"):
+            for grouped, a in self.fwd:
+                rc |= (lib.msda_forward_grouped if grouped else lib.msda_forward)(st, *a)
+            rc |= lib.mask_logits_forward(st, *self.mask_fwd)
+            rc |= lib.mask_logits_backward(st, *self.mask_bwd)
+        order = list(reversed(self.bwd))                       # decoder calls first, the n_enc encoder calls last
+        if part == "head":
+            order = order[:len(order) - n_enc]
+        elif part == "tail":
+            order = order[len(order) - n_enc:]
+        for grouped, a in order:
             rc |= (lib.msda_backward_grouped if grouped else lib.msda_backward)(st, *a)
         if rc:
             from mdqe_cvpr2023_b200 import _lib
@@ -374,6 +384,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout (one JSON line only)
     import torch
     import torch.distributed as dist
     from mdqe_cvpr2023_b200 import _lib as libmod
@@ -392,9 +403,11 @@ def main():
 
     calls, mask = build_calls(torch, args.dist, rank, args.layers)
     step = DeviceStep(torch, lib, libmod, calls, mask, device, args.dtype)
-    # gradient all-reduce of the enc+dec parameters (4.54 M + 14.94 M fp32) -- the only
-    # cross-GPU step of clip-sharded DDP training; issued after the backward, not overlapped.
-    grad_buf = torch.zeros(19_480_000, device=device) if world > 1 else None
+    # gradient all-reduce of the enc+dec parameters (decoder 14.94 M, encoder 4.54 M fp32) -- the only
+    # cross-GPU step of clip-sharded DDP training.  Two buckets like DDP's: the decoder bucket is reduced on NCCL's
+    # stream while the encoder backward still runs, the encoder bucket after the backward ends.
+    dec_buf = torch.zeros(14_940_000, device=device) if world > 1 else None
+    enc_buf = torch.zeros(4_540_000, device=device) if world > 1 else None
 
     def sync_all():
         torch.cuda.synchronize()
@@ -405,30 +418,47 @@ def main():
     # ---- warm-up (eager), then capture one step into a CUDA graph
     for _ in range(max(args.warmup, 3)):
         step.run()
-        if grad_buf is not None:
-            dist.all_reduce(grad_buf)
+        if world > 1:
+            dist.all_reduce(dec_buf)
+            dist.all_reduce(enc_buf)
     torch.cuda.synchronize()
-    graph = None
+    graphs = None
     if not args.no_graph:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             step.run()
         torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            step.run()
+        graphs = []
+        for part in (("all",) if world == 1 else ("head", "tail")):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step.run(part)
+            graphs.append(g)
         for _ in range(2):
-            graph.replay()
+            for g in graphs:
+                g.replay()
         torch.cuda.synchronize()
+    graph = graphs
 
     def one_step():
-        if graph is not None:
-            graph.replay()
+        if world == 1:
+            if graphs is not None:
+                graphs[0].replay()
+            else:
+                step.run()
+            return
+        if graphs is not None:
+            graphs[0].replay()
         else:
-            step.run()
-        if grad_buf is not None:
-            dist.all_reduce(grad_buf)
+            step.run("head")
+        work = dist.all_reduce(dec_buf, async_op=True)          # overlaps with the encoder backward below
+        if graphs is not None:
+            graphs[1].replay()
+        else:
+            step.run("tail")
+        dist.all_reduce(enc_buf)
+        work.wait()
 
     # ---- timed region: exactly K steps, CUDA events, max over ranks
     libmod.launch_count_reset()
@@ -474,23 +504,28 @@ def main():
     else:
         hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
 
+    traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    traffic_db = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+
     def roof(nbytes, ms, n, name):
         if not n:
             return None
         us = ms / n * 1e3
         ach = nbytes / (us * 1e-6) / 1e9
+        # DRAM bytes of one launch from the committed `ncu --set full` capture of the same kernel and shape (fp32)
+        traffic = traffic_db.get(name.split("<")[0]) if args.dtype == "fp32" else None
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "avg_launch_us": us, "launches_timed": n, "algorithmic_bytes": nbytes, "peak_source": peak_src}
+                "traffic": traffic, "traffic_source": traffic_db.get("source") if traffic else None, "avg_launch_us": us, "launches_timed": n, "algorithmic_bytes": nbytes, "peak_source": peak_src}
 
     roofline = roof(bwd_bytes, bwd_ms, bwd_n, "msda_bwd_fast2_kernel<%s,32,16> (encoder shape N=4,S=Lq=5100)" % ("bf16" if args.dtype == "bf16" else "float"))
     roofline_fwd = roof(fwd_bytes, fwd_ms, fwd_n, "msda_fwd_fast2_kernel<%s,32,16> (encoder shape N=4,S=Lq=5100)" % ("bf16" if args.dtype == "bf16" else "float"))
     mB = QUERIES * MASK_K + MASK_K * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
     mO = QUERIES * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
-    roofline_mask = roof(mB * esize + mO * esize, mfw_ms, mfw_n, "mask_logits forward")
+    roofline_mask = roof(mB * esize + mO * esize, mfw_ms, mfw_n, "mask_fwd_tc2_kernel<bf16> (tcgen05)" if args.dtype == "bf16" else "mask_fwd_simt_kernel<float,float>")
     if roofline_mask:
         flops = 2.0 * QUERIES * MASK_K * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
         roofline_mask["tflops"] = flops / (roofline_mask["avg_launch_us"] * 1e-6) / 1e12
-    roofline_mask_bwd = roof((mB + mO + mB) * 4, mbw_ms, mbw_n, "mask_logits backward (fp32)")
+    roofline_mask_bwd = roof((mB + mO + mB) * 4, mbw_ms, mbw_n, "mask_grad_coeff_kernel + mask_grad_proto_kernel (fp32)")
 
     # ---- eager (no graph) step time, for reference
     sync_all()
@@ -540,7 +575,7 @@ def main():
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
                 "config": config_dict(args, {"launch": "cuda_graph" if graph is not None else "eager",
-                                             "allreduce": "19.48M fp32 grads per step, NCCL, after backward" if world > 1 else None}),
+                                             "allreduce": "NCCL, 2 buckets per step: decoder 14.94M fp32 overlapped with the encoder backward, encoder 4.54M after it" if world > 1 else None}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "launches_per_step": launches_per_step,
                 "lib_launch_count_per_eager_step": counted_per_step,
                 "roofline": roofline, "roofline_fwd": roofline_fwd, "roofline_mask": roofline_mask,
