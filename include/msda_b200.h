@@ -62,7 +62,7 @@ int msda_abi_version(void);
 const char* msda_last_error(void);
 
 /* Tuning knobs (kernel variant selection used by bench.py / tests); unknown keys fail.
- * Keys: "fwd_variant", "bwd_variant", "chunk_pairs", "mask_variant", "profile", "mask_debug". */
+ * Keys: "fwd_variant", "bwd_variant", "chunk_pairs", "mask_variant", "profile", "mask_debug", "host_async". */
 int msda_set_option(const char* key, int value);
 int msda_get_option(const char* key, int* value);
 
@@ -139,6 +139,10 @@ int msda_backward_host(int device, int dtype,
 int mask_logits_forward_host(int device, int in_dtype, int out_dtype,
                              const void* coeff, const void* proto,
                              int B, int Q, int K, int64_t Ncols, void* out);
+/* With msda_set_option("host_async", 1) the *_host entries return as soon as their copies and kernels are enqueued
+ * (upload, kernels and download of consecutive calls overlap on three streams; PCIe runs full duplex); host output
+ * buffers are valid, and host input buffers may be reused, only after msda_host_sync().  Returns the first error. */
+int msda_host_sync(void);
 /* Release the device arena used by the *_host entries. */
 int msda_host_arena_release(void);
 

@@ -35,6 +35,7 @@ PROTOTYPES = {
     "msda_backward_host": (_c_int, [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + _SEVEN
                            + [_c_vp, _c_vp, _c_vp]),
     "mask_logits_forward_host": (_c_int, [_c_int, _c_int, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_vp]),
+    "msda_host_sync": (_c_int, []),
     "msda_host_arena_release": (_c_int, []),
     "msda_profile_read": (_c_int, [_c_int, _c_i64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_c_i64)]),
     "msda_debug_read": (_c_int, [ctypes.POINTER(ctypes.c_longlong)]),

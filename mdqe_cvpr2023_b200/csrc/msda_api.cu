@@ -44,6 +44,7 @@ struct Options {
   std::atomic<int> chunk_pairs{0};    // 0 = auto
   std::atomic<int> mask_variant{0};   // 0 = auto (tcgen05 when eligible), 1 = SIMT fp32, 2 = force tcgen05
   std::atomic<int> mask_debug{0};     // 1 = the tcgen05 mask kernel records per-item clock stamps of CTA 0
+  std::atomic<int> host_async{0};     // 1 = the *_host entries only enqueue; msda_host_sync() completes them
   std::atomic<int> profile{0};        // 1 = bracket the main kernels with CUDA events (msda_profile_read)
 };
 static Options g_opt;
@@ -56,6 +57,7 @@ static std::atomic<int>* find_option(const char* key) {
   if (!strcmp(key, "mask_variant")) return &g_opt.mask_variant;
   if (!strcmp(key, "profile")) return &g_opt.profile;
   if (!strcmp(key, "mask_debug")) return &g_opt.mask_debug;
+  if (!strcmp(key, "host_async")) return &g_opt.host_async;
   return nullptr;
 }
 
@@ -451,39 +453,100 @@ int mask_logits_backward(void* stream, int dtype, const void* coeff, const void*
 }
 
 // ------------------------------------------------------------------------------- host-buffer entries
+// Three streams form a pipeline per call: H2D copies -> kernels -> D2H copies, chained with events.  In the default
+// synchronous mode a call returns when its results are in host memory.  With option "host_async" = 1 calls only
+// enqueue (device buffers are bump-allocated from the arena and stay live until msda_host_sync()), so the upload of
+// call i+1, the kernels of call i and the download of call i-1 overlap and PCIe runs full duplex.
 namespace {
-struct Arena {
+struct HostPipe {
   std::mutex mu;
   int device = -1;
   char* base = nullptr;
-  size_t cap = 0;
-  cudaStream_t stream = nullptr;
+  size_t cap = 0, used = 0;
+  cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+  static constexpr int kEvents = 64;
+  cudaEvent_t ev_in[kEvents] = {}, ev_run[kEvents] = {};
+  int ev_next = 0;
+  int first_error = 0;
 };
-Arena g_arena;
+HostPipe g_pipe;
 
-// Carves 256-byte aligned sub-buffers out of the (grow-only) arena.
+// Carves 256-byte aligned sub-buffers out of the arena, starting at the current bump offset.
 struct Carver {
   size_t off = 0;
   size_t take(size_t bytes) { const size_t at = off; off += (bytes + 255) & ~size_t(255); return at; }
 };
 
-int arena_prepare(int device, size_t bytes) {
+int pipe_drain() {
+  int rc = 0;
+  if (g_pipe.s_in) rc |= check_cuda(cudaStreamSynchronize(g_pipe.s_in), "cudaStreamSynchronize(h2d)");
+  if (g_pipe.s_run) rc |= check_cuda(cudaStreamSynchronize(g_pipe.s_run), "cudaStreamSynchronize(compute)");
+  if (g_pipe.s_out) rc |= check_cuda(cudaStreamSynchronize(g_pipe.s_out), "cudaStreamSynchronize(d2h)");
+  g_pipe.used = 0;
+  return rc ? MSDA_ERR_CUDA : 0;
+}
+
+void pipe_free() {
+  if (g_pipe.base) { cudaFree(g_pipe.base); g_pipe.base = nullptr; }
+  g_pipe.cap = g_pipe.used = 0;
+  for (cudaStream_t* s : {&g_pipe.s_in, &g_pipe.s_run, &g_pipe.s_out})
+    if (*s) { cudaStreamDestroy(*s); *s = nullptr; }
+  for (int i = 0; i < HostPipe::kEvents; ++i) {
+    if (g_pipe.ev_in[i]) { cudaEventDestroy(g_pipe.ev_in[i]); g_pipe.ev_in[i] = nullptr; }
+    if (g_pipe.ev_run[i]) { cudaEventDestroy(g_pipe.ev_run[i]); g_pipe.ev_run[i] = nullptr; }
+  }
+}
+
+// Reserve `bytes` of device memory for one call; returns the arena offset of its first byte in *at.
+int pipe_reserve(int device, size_t bytes, size_t* at) {
   if (int rc = check_cuda(cudaSetDevice(device), "cudaSetDevice")) return rc;
-  if (g_arena.device != device && g_arena.base) {
-    cudaFree(g_arena.base); g_arena.base = nullptr; g_arena.cap = 0;
-    if (g_arena.stream) { cudaStreamDestroy(g_arena.stream); g_arena.stream = nullptr; }
+  if (g_pipe.device != device) { pipe_drain(); pipe_free(); g_pipe.device = device; }
+  if (!g_pipe.s_in) {
+    for (cudaStream_t* s : {&g_pipe.s_in, &g_pipe.s_run, &g_pipe.s_out})
+      if (int rc = check_cuda(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking), "cudaStreamCreate")) return rc;
+    for (int i = 0; i < HostPipe::kEvents; ++i) {
+      if (int rc = check_cuda(cudaEventCreateWithFlags(&g_pipe.ev_in[i], cudaEventDisableTiming), "cudaEventCreate")) return rc;
+      if (int rc = check_cuda(cudaEventCreateWithFlags(&g_pipe.ev_run[i], cudaEventDisableTiming), "cudaEventCreate")) return rc;
+    }
   }
-  g_arena.device = device;
-  if (!g_arena.stream)
-    if (int rc = check_cuda(cudaStreamCreateWithFlags(&g_arena.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return rc;
-  if (bytes > g_arena.cap) {
-    if (g_arena.base) { cudaStreamSynchronize(g_arena.stream); cudaFree(g_arena.base); g_arena.base = nullptr; g_arena.cap = 0; }
-    const size_t want = bytes + bytes / 4;
-    if (int rc = check_cuda(cudaMalloc(&g_arena.base, want), "cudaMalloc(host arena)")) return rc;
-    g_arena.cap = want;
+  const bool async = g_opt.host_async.load() != 0;
+  if (!async) g_pipe.used = 0;                            // synchronous mode: the previous call has completed
+  if (g_pipe.used + bytes > g_pipe.cap) {
+    if (int rc = pipe_drain()) return rc;                 // nothing in flight any more, bump pointer back to 0
+    if (bytes > g_pipe.cap) {
+      if (g_pipe.base) { cudaFree(g_pipe.base); g_pipe.base = nullptr; g_pipe.cap = 0; }
+      // async: room for many calls in flight (a training clip's 73 calls stage ~7 GB; the part has 180 GB)
+      const size_t want = async ? (bytes * 8 > (size_t(8) << 30) ? bytes * 8 : (size_t(8) << 30)) : bytes + bytes / 4;
+      if (cudaMalloc(&g_pipe.base, want) == cudaSuccess) g_pipe.cap = want;
+      else {
+        cudaGetLastError();
+        if (int rc = check_cuda(cudaMalloc(&g_pipe.base, bytes), "cudaMalloc(host arena)")) return rc;
+        g_pipe.cap = bytes;
+      }
+    }
   }
+  *at = g_pipe.used;
+  g_pipe.used += (bytes + 255) & ~size_t(255);
   return 0;
 }
+
+// Event pair of the next call slot (the ring is long enough: a slot is reused 64 calls later, and every call waits
+// for its own events on the consuming stream before they can be re-recorded meaningfully).
+void pipe_events(cudaEvent_t* in, cudaEvent_t* run) {
+  const int i = g_pipe.ev_next++ % HostPipe::kEvents;
+  *in = g_pipe.ev_in[i];
+  *run = g_pipe.ev_run[i];
+}
+
+int pipe_finish_call() {
+  if (g_opt.host_async.load() != 0) return 0;
+  return check_cuda(cudaStreamSynchronize(g_pipe.s_out), "cudaStreamSynchronize(d2h)");
+}
+
+#define H2D(dst, src, bytes, what) \
+  if ((bytes) > 0) if (int rc_ = check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_pipe.s_in), "H2D " what)) return rc_
+#define D2H(dst, src, bytes, what) \
+  if ((bytes) > 0) if (int rc_ = check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_pipe.s_out), "D2H " what)) return rc_
 }  // namespace
 
 int msda_forward_host(int device, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
@@ -494,22 +557,28 @@ int msda_forward_host(int device, int dtype, const void* value, const int64_t* s
   const size_t b_out = (size_t)N * Lq * M * D * es, b_shp = (size_t)L * 2 * 8, b_lsi = (size_t)L * 8;
   if (b_out == 0) return 0;
   if (!out) return fail(MSDA_ERR_INVALID_ARG, "msda_forward_host: out is NULL");
-  std::lock_guard<std::mutex> lock(g_arena.mu);
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
   Carver cv;
   const size_t o_val = cv.take(b_val), o_loc = cv.take(b_loc), o_aw = cv.take(b_aw), o_out = cv.take(b_out);
   const size_t o_shp = cv.take(b_shp), o_lsi = cv.take(b_lsi);
-  if (int rc = arena_prepare(device, cv.off)) return rc;
-  char* d = g_arena.base;
-  cudaStream_t st = g_arena.stream;
-  if (int rc = check_cuda(cudaMemcpyAsync(d + o_val, value, b_val, cudaMemcpyHostToDevice, st), "H2D value")) return rc;
-  if (int rc = check_cuda(cudaMemcpyAsync(d + o_loc, loc, b_loc, cudaMemcpyHostToDevice, st), "H2D loc")) return rc;
-  if (int rc = check_cuda(cudaMemcpyAsync(d + o_aw, aw, b_aw, cudaMemcpyHostToDevice, st), "H2D aw")) return rc;
-  if (int rc = check_cuda(cudaMemcpyAsync(d + o_shp, shapes, b_shp, cudaMemcpyHostToDevice, st), "H2D shapes")) return rc;
-  if (int rc = check_cuda(cudaMemcpyAsync(d + o_lsi, level_start, b_lsi, cudaMemcpyHostToDevice, st), "H2D level_start")) return rc;
-  if (int rc = msda_forward(st, dtype, d + o_val, reinterpret_cast<int64_t*>(d + o_shp), reinterpret_cast<int64_t*>(d + o_lsi),
+  size_t at = 0;
+  if (int rc = pipe_reserve(device, cv.off, &at)) return rc;
+  char* d = g_pipe.base + at;
+  cudaEvent_t e_in, e_run;
+  pipe_events(&e_in, &e_run);
+  H2D(d + o_val, value, b_val, "value");
+  H2D(d + o_loc, loc, b_loc, "loc");
+  H2D(d + o_aw, aw, b_aw, "aw");
+  H2D(d + o_shp, shapes, b_shp, "shapes");
+  H2D(d + o_lsi, level_start, b_lsi, "level_start");
+  cudaEventRecord(e_in, g_pipe.s_in);
+  cudaStreamWaitEvent(g_pipe.s_run, e_in, 0);
+  if (int rc = msda_forward(g_pipe.s_run, dtype, d + o_val, reinterpret_cast<int64_t*>(d + o_shp), reinterpret_cast<int64_t*>(d + o_lsi),
                             d + o_loc, d + o_aw, N, S, M, D, L, Lq, P, d + o_out)) return rc;
-  if (int rc = check_cuda(cudaMemcpyAsync(out, d + o_out, b_out, cudaMemcpyDeviceToHost, st), "D2H out")) return rc;
-  return check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+  cudaEventRecord(e_run, g_pipe.s_run);
+  cudaStreamWaitEvent(g_pipe.s_out, e_run, 0);
+  D2H(out, d + o_out, b_out, "out");
+  return pipe_finish_call();
 }
 
 int msda_backward_host(int device, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
@@ -520,29 +589,33 @@ int msda_backward_host(int device, int dtype, const void* value, const int64_t* 
   const size_t b_val = (size_t)N * S * M * D * es, b_loc = (size_t)N * Lq * M * L * P * 2 * ls, b_aw = b_loc / 2;
   const size_t b_go = (size_t)N * Lq * M * D * es, b_shp = (size_t)L * 2 * 8, b_lsi = (size_t)L * 8;
   const size_t b_ws = msda_backward_workspace_bytes(dtype, N, S, M, D);
-  std::lock_guard<std::mutex> lock(g_arena.mu);
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
   Carver cv;
   const size_t o_val = cv.take(b_val), o_loc = cv.take(b_loc), o_aw = cv.take(b_aw), o_go = cv.take(b_go);
   const size_t o_shp = cv.take(b_shp), o_lsi = cv.take(b_lsi);
   const size_t o_gv = cv.take(b_val), o_gl = cv.take(b_loc), o_ga = cv.take(b_aw), o_ws = cv.take(b_ws);
-  if (int rc = arena_prepare(device, cv.off)) return rc;
-  char* d = g_arena.base;
-  cudaStream_t st = g_arena.stream;
-  if (int rc = check_cuda(cudaMemcpyAsync(d + o_val, value, b_val, cudaMemcpyHostToDevice, st), "H2D value")) return rc;
-  if (int rc = check_cuda(cudaMemcpyAsync(d + o_loc, loc, b_loc, cudaMemcpyHostToDevice, st), "H2D loc")) return rc;
-  if (int rc = check_cuda(cudaMemcpyAsync(d + o_aw, aw, b_aw, cudaMemcpyHostToDevice, st), "H2D aw")) return rc;
-  if (int rc = check_cuda(cudaMemcpyAsync(d + o_go, grad_out, b_go, cudaMemcpyHostToDevice, st), "H2D grad_out")) return rc;
-  if (int rc = check_cuda(cudaMemcpyAsync(d + o_shp, shapes, b_shp, cudaMemcpyHostToDevice, st), "H2D shapes")) return rc;
-  if (int rc = check_cuda(cudaMemcpyAsync(d + o_lsi, level_start, b_lsi, cudaMemcpyHostToDevice, st), "H2D level_start")) return rc;
-  if (int rc = msda_backward(st, dtype, d + o_val, reinterpret_cast<int64_t*>(d + o_shp), reinterpret_cast<int64_t*>(d + o_lsi),
+  size_t at = 0;
+  if (int rc = pipe_reserve(device, cv.off, &at)) return rc;
+  char* d = g_pipe.base + at;
+  cudaEvent_t e_in, e_run;
+  pipe_events(&e_in, &e_run);
+  H2D(d + o_val, value, b_val, "value");
+  H2D(d + o_loc, loc, b_loc, "loc");
+  H2D(d + o_aw, aw, b_aw, "aw");
+  H2D(d + o_go, grad_out, b_go, "grad_out");
+  H2D(d + o_shp, shapes, b_shp, "shapes");
+  H2D(d + o_lsi, level_start, b_lsi, "level_start");
+  cudaEventRecord(e_in, g_pipe.s_in);
+  cudaStreamWaitEvent(g_pipe.s_run, e_in, 0);
+  if (int rc = msda_backward(g_pipe.s_run, dtype, d + o_val, reinterpret_cast<int64_t*>(d + o_shp), reinterpret_cast<int64_t*>(d + o_lsi),
                              d + o_loc, d + o_aw, d + o_go, N, S, M, D, L, Lq, P, d + o_gv, d + o_gl, d + o_ga,
                              b_ws ? d + o_ws : nullptr, b_ws)) return rc;
-  if (b_val) if (int rc = check_cuda(cudaMemcpyAsync(grad_value, d + o_gv, b_val, cudaMemcpyDeviceToHost, st), "D2H grad_value")) return rc;
-  if (b_loc) {
-    if (int rc = check_cuda(cudaMemcpyAsync(grad_loc, d + o_gl, b_loc, cudaMemcpyDeviceToHost, st), "D2H grad_loc")) return rc;
-    if (int rc = check_cuda(cudaMemcpyAsync(grad_aw, d + o_ga, b_aw, cudaMemcpyDeviceToHost, st), "D2H grad_aw")) return rc;
-  }
-  return check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+  cudaEventRecord(e_run, g_pipe.s_run);
+  cudaStreamWaitEvent(g_pipe.s_out, e_run, 0);
+  D2H(grad_value, d + o_gv, b_val, "grad_value");
+  D2H(grad_loc, d + o_gl, b_loc, "grad_loc");
+  D2H(grad_aw, d + o_ga, b_aw, "grad_aw");
+  return pipe_finish_call();
 }
 
 int mask_logits_forward_host(int device, int in_dtype, int out_dtype, const void* coeff, const void* proto, int B, int Q,
@@ -552,29 +625,40 @@ int mask_logits_forward_host(int device, int in_dtype, int out_dtype, const void
   const size_t b_c = (size_t)B * Q * K * ei, b_p = (size_t)B * K * Ncols * ei, b_o = (size_t)B * Q * Ncols * eo;
   if (b_o == 0) return 0;
   if (!coeff || !proto || !out) return fail(MSDA_ERR_INVALID_ARG, "mask_logits_forward_host: NULL tensor");
-  std::lock_guard<std::mutex> lock(g_arena.mu);
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
   Carver cv;
   const size_t o_c = cv.take(b_c), o_p = cv.take(b_p), o_o = cv.take(b_o);
-  if (int rc = arena_prepare(device, cv.off)) return rc;
-  char* d = g_arena.base;
-  cudaStream_t st = g_arena.stream;
-  if (int rc = check_cuda(cudaMemcpyAsync(d + o_c, coeff, b_c, cudaMemcpyHostToDevice, st), "H2D coeff")) return rc;
-  if (int rc = check_cuda(cudaMemcpyAsync(d + o_p, proto, b_p, cudaMemcpyHostToDevice, st), "H2D proto")) return rc;
-  if (int rc = mask_logits_forward(st, in_dtype, out_dtype, d + o_c, d + o_p, B, Q, K, Ncols, d + o_o)) return rc;
-  if (int rc = check_cuda(cudaMemcpyAsync(out, d + o_o, b_o, cudaMemcpyDeviceToHost, st), "D2H out")) return rc;
-  return check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+  size_t at = 0;
+  if (int rc = pipe_reserve(device, cv.off, &at)) return rc;
+  char* d = g_pipe.base + at;
+  cudaEvent_t e_in, e_run;
+  pipe_events(&e_in, &e_run);
+  H2D(d + o_c, coeff, b_c, "coeff");
+  H2D(d + o_p, proto, b_p, "proto");
+  cudaEventRecord(e_in, g_pipe.s_in);
+  cudaStreamWaitEvent(g_pipe.s_run, e_in, 0);
+  if (int rc = mask_logits_forward(g_pipe.s_run, in_dtype, out_dtype, d + o_c, d + o_p, B, Q, K, Ncols, d + o_o)) return rc;
+  cudaEventRecord(e_run, g_pipe.s_run);
+  cudaStreamWaitEvent(g_pipe.s_out, e_run, 0);
+  D2H(out, d + o_o, b_o, "out");
+  return pipe_finish_call();
+}
+
+int msda_host_sync(void) {
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
+  if (g_pipe.device < 0) return 0;
+  cudaSetDevice(g_pipe.device);
+  return pipe_drain();
 }
 
 int msda_host_arena_release(void) {
-  std::lock_guard<std::mutex> lock(g_arena.mu);
-  if (g_arena.base) {
-    cudaSetDevice(g_arena.device);
-    if (g_arena.stream) cudaStreamSynchronize(g_arena.stream);
-    cudaFree(g_arena.base);
-    g_arena.base = nullptr; g_arena.cap = 0;
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
+  if (g_pipe.device >= 0) {
+    cudaSetDevice(g_pipe.device);
+    pipe_drain();
+    pipe_free();
   }
-  if (g_arena.stream) { cudaStreamDestroy(g_arena.stream); g_arena.stream = nullptr; }
-  g_arena.device = -1;
+  g_pipe.device = -1;
   return 0;
 }
 

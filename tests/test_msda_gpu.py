@@ -273,6 +273,34 @@ def test_host_buffer_entry():
     lib.msda_host_arena_release()
 
 
+def test_host_buffer_entry_async_pipeline():
+    """host_async = 1: calls only enqueue (H2D / kernels / D2H on three streams); results are valid after msda_host_sync()."""
+    from mdqe_cvpr2023_b200 import _lib
+    lib = _lib.load()
+    cases = []
+    for seed in range(4):
+        inp = make_inputs(2, [(12, 20), (6, 10)], 8, 32, 4, Lq=30 + seed, dist="wide", seed=30 + seed)
+        pin = {k: v.contiguous().pin_memory() for k, v in inp.items()}
+        N, S, M, D = inp["value"].shape
+        Lq = inp["loc"].shape[1]
+        outs = (torch.empty(N, Lq, M * D).pin_memory(), torch.empty_like(pin["value"]).pin_memory(),
+                torch.empty_like(pin["loc"]).pin_memory(), torch.empty_like(pin["aw"]).pin_memory())
+        cases.append((inp, pin, (N, S, M, D, 2, Lq, 4), outs))
+    _lib.set_option("host_async", 1)
+    try:
+        for inp, pin, dims, (out, gv, gl, ga) in cases:
+            a = (pin["value"].data_ptr(), pin["shapes"].data_ptr(), pin["level_start"].data_ptr(), pin["loc"].data_ptr(), pin["aw"].data_ptr())
+            _lib.check(lib.msda_forward_host(0, _lib.MSDA_F32, *a, *dims, out.data_ptr()), "msda_forward_host")
+            _lib.check(lib.msda_backward_host(0, _lib.MSDA_F32, *a, pin["grad_out"].data_ptr(), *dims, gv.data_ptr(), gl.data_ptr(),
+                                              ga.data_ptr()), "msda_backward_host")
+        _lib.check(lib.msda_host_sync(), "msda_host_sync")
+    finally:
+        _lib.set_option("host_async", 0)
+    for inp, pin, dims, outs in cases:
+        check(outs, oracle_all(inp), 2e-5, "async host entry", inp)
+    lib.msda_host_arena_release()
+
+
 def test_launch_counter_counts_kernels():
     from mdqe_cvpr2023_b200 import _lib
     inp = to_cuda(make_inputs(1, [(8, 8)], 8, 32, 4, Lq=8, seed=16))
