@@ -106,6 +106,28 @@ int msda_backward_grouped(void* stream, int dtype,
                           void* grad_value, void* grad_loc, void* grad_aw,
                           void* workspace, size_t workspace_bytes);
 
+/* Fused sampler prologue (replaces the elementwise tail of MSDeformAttn.forward, ms_deform_attn.py:142-161):
+ * the kernel takes what the module's Linear layers produce and computes softmax and sampling locations itself.
+ *   offsets [N,Lq,M,L,P,2] raw output of sampling_offsets / sampling_grid_offsets,  logits [N,Lq,M,L*P] raw attention logits,
+ *   ref_points [N,Lq,R] (R = 2: cx,cy; R = 4: cx,cy,w,h),  grid [M,L,P,2] = the module's `sampling_offsets` buffer (mode 1)
+ *   mode 0 (pred_offsets=True, encoder):  loc = ref_xy + offsets / offset_scale
+ *   mode 1 (pred_offsets=False, decoder): loc = ref_xy + (grid * 0.5 * ref_wh + clamp(offsets, +-ref_wh*offset_scale)) / offset_scale
+ *   aw = softmax(logits) over L*P;  out = scale * sum_{g<G} msda(value, shapes[g], level_start[g], loc, aw)   (G = 1: spatial)
+ * The backward returns d/d value, d/d offsets and d/d logits (reference points are treated as constants).
+ * fp32 only, D in {32,24}, L*P in {8,16}; otherwise MSDA_ERR_UNSUPPORTED. */
+int msda_fused_forward(void* stream, int dtype,
+                       const void* value, const int64_t* shapes, const int64_t* level_start,
+                       const void* ref_points, int R, const void* offsets, const void* logits, const void* grid,
+                       int mode, float offset_scale,
+                       int N, int S, int M, int D, int G, int L, int Lq, int P, float scale,
+                       void* out);
+int msda_fused_backward(void* stream, int dtype,
+                        const void* value, const int64_t* shapes, const int64_t* level_start,
+                        const void* ref_points, int R, const void* offsets, const void* logits, const void* grid,
+                        int mode, float offset_scale, const void* grad_out,
+                        int N, int S, int M, int D, int G, int L, int Lq, int P, float scale,
+                        void* grad_value, void* grad_offsets, void* grad_logits);
+
 /* Mask contraction: out[b,q,n] = sum_k coeff[b,q,k] * proto[b,k,n], n over the flattened (t,h,w)
  * plane (Ncols = T*H*W).  coeff [B,Q,K], proto [B,K,Ncols], out [B,Q,Ncols].
  *   in_dtype  MSDA_F32 (inputs rounded to bf16 hi+lo pairs on chip: 3 tensor-core passes, fp32

@@ -29,6 +29,10 @@ PROTOTYPES = {
     "msda_forward_grouped": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + [_c_int] * 8 + [ctypes.c_float, _c_vp]),
     "msda_backward_grouped": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + [_c_int] * 8
                               + [ctypes.c_float, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz]),
+    "msda_fused_forward": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, ctypes.c_float]
+                           + [_c_int] * 8 + [ctypes.c_float, _c_vp]),
+    "msda_fused_backward": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, ctypes.c_float,
+                                     _c_vp] + [_c_int] * 8 + [ctypes.c_float, _c_vp, _c_vp, _c_vp]),
     "mask_logits_forward": (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_vp]),
     "mask_logits_backward": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_vp, _c_vp]),
     "msda_forward_host": (_c_int, [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + _SEVEN + [_c_vp]),

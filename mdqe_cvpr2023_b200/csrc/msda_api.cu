@@ -95,6 +95,7 @@ struct Problem {
   int64_t n_pairs;
   int G = 1;            // level-table groups sharing loc/aw (temporal form); 1 = the plain operator
   float scale = 1.f;    // out = scale * sum over groups
+  FusedArgs fz{nullptr, nullptr, 0, 0, 1.f};   // fused softmax / location prologue (ref != nullptr)
 };
 
 static int validate(const char* who, int dtype, const void* value, const int64_t* shapes, const int64_t* lsi,
@@ -151,6 +152,7 @@ static bool fast2_lp(int lp) { return lp == 16 || lp == 12 || lp == 8; }
 template <typename VT, typename LT>
 static bool split_groups(const Problem& pb) {
   if (pb.G <= 1 || !std::is_same<VT, float>::value || !std::is_same<LT, float>::value) return false;
+  if (pb.fz.ref != nullptr) return false;                   // the fused softmax backward needs the sum over all tables
   if (g_opt.chunk_pairs.load() < 0) return false;           // chunk_pairs = -1 disables the split (A/B timing)
   return pb.n_pairs < 148LL * 4 * 16;
 }
@@ -161,7 +163,7 @@ static void launch_fwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int ch
   const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
   const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
 #define MSDA_FWD2(LPV, GRP) msda_fwd_fast2_kernel<VT, LT, D, LPV, MINB, GRP><<<grid, kThreads, 0, st>>>( \
-      v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale)
+      v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz)
   const bool grouped = pb.G > 1 || pb.scale != 1.f;
   switch (pb.L * pb.P) {
     case 16: if (grouped) MSDA_FWD2(16, true); else MSDA_FWD2(16, false); break;
@@ -177,7 +179,7 @@ static void launch_bwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int ch
   const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
   const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
 #define MSDA_BWD2(LPV, GRP) msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP><<<grid, kThreads, 0, st>>>( \
-      v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale)
+      v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz)
   const bool grouped = pb.G > 1 || pb.scale != 1.f;
   switch (pb.L * pb.P) {
     case 16: if (grouped) MSDA_BWD2(16, true); else MSDA_BWD2(16, false); break;
@@ -325,16 +327,27 @@ static int grouped_supported(const char* who, int dtype, const Problem& pb, bool
   return 0;
 }
 
+static int fused_supported(const char* who, int dtype, const Problem& pb, bool fast) {
+  if (pb.fz.ref == nullptr) return 0;
+  const int lp = pb.L * pb.P;
+  if (!fast || dtype != MSDA_F32 || (lp != 8 && lp != 16))
+    return fail(MSDA_ERR_UNSUPPORTED, "%s: the fused prologue needs fp32, D in {32,24}, L*P in {8,16} and 16-byte aligned tensors", who);
+  if ((pb.fz.R != 2 && pb.fz.R != 4) || (pb.fz.mode != 0 && pb.fz.mode != 1) || (pb.fz.mode == 1 && (pb.fz.R != 4 || !pb.fz.grid)) || !(pb.fz.scale > 0.f))
+    return fail(MSDA_ERR_INVALID_ARG, "%s: bad fused arguments (R=%d mode=%d scale=%g)", who, pb.fz.R, pb.fz.mode, (double)pb.fz.scale);
+  return 0;
+}
+
 static int forward_impl(const char* who, void* stream, int dtype, const void* value, const int64_t* shapes,
                         const int64_t* level_start, const void* loc, const void* aw, int N, int S, int M, int D, int G, int L,
-                        int Lq, int P, float scale, void* out) {
+                        int Lq, int P, float scale, void* out, FusedArgs fz = FusedArgs{nullptr, nullptr, 0, 0, 1.f}) {
   if (int rc = validate(who, dtype, value, shapes, level_start, loc, aw, N, S, M, D, L, Lq, P)) return rc;
-  Problem pb{N, S, M, D, L, Lq, P, (int64_t)N * Lq * M, G, scale};
+  Problem pb{N, S, M, D, L, Lq, P, (int64_t)N * Lq * M, G, scale, fz};
   if (pb.n_pairs == 0) return 0;
   if (!out) return fail(MSDA_ERR_INVALID_ARG, "%s: out is NULL", who);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool fast = (G > 1 || g_opt.fwd_variant.load() != 1) && fast_eligible(dtype, pb, value, out, loc);
+  const bool fast = (G > 1 || fz.ref || g_opt.fwd_variant.load() != 1) && fast_eligible(dtype, pb, value, out, loc);
   if (int rc = grouped_supported(who, dtype, pb, fast)) return rc;
+  if (int rc = fused_supported(who, dtype, pb, fast)) return rc;
   switch (dtype) {
     case MSDA_F32: return launch_fwd<float, float>(st, pb, fast, value, shapes, level_start, loc, aw, out);
     case MSDA_BF16: return launch_fwd<__nv_bfloat16, __nv_bfloat16>(st, pb, fast, value, shapes, level_start, loc, aw, out);
@@ -363,9 +376,9 @@ size_t msda_backward_workspace_bytes(int dtype, int N, int S, int M, int D) {
 static int backward_impl(const char* who, void* stream, int dtype, const void* value, const int64_t* shapes,
                          const int64_t* level_start, const void* loc, const void* aw, const void* grad_out, int N, int S, int M,
                          int D, int G, int L, int Lq, int P, float scale, void* grad_value, void* grad_loc, void* grad_aw,
-                         void* workspace, size_t workspace_bytes) {
+                         void* workspace, size_t workspace_bytes, FusedArgs fz = FusedArgs{nullptr, nullptr, 0, 0, 1.f}) {
   if (int rc = validate(who, dtype, value, shapes, level_start, loc, aw, N, S, M, D, L, Lq, P)) return rc;
-  Problem pb{N, S, M, D, L, Lq, P, (int64_t)N * Lq * M, G, scale};
+  Problem pb{N, S, M, D, L, Lq, P, (int64_t)N * Lq * M, G, scale, fz};
   const size_t n_value = (size_t)N * S * M * D;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n_value > 0 && !grad_value) return fail(MSDA_ERR_INVALID_ARG, "%s: grad_value is NULL", who);
@@ -383,9 +396,10 @@ static int backward_impl(const char* who, void* stream, int dtype, const void* v
     return 0;
   }
   if (!grad_out || !grad_loc || !grad_aw) return fail(MSDA_ERR_INVALID_ARG, "%s: grad_out / grad_loc / grad_aw is NULL", who);
-  const bool fast = (G > 1 || g_opt.bwd_variant.load() != 1) && fast_eligible(dtype, pb, value, grad_out, acc) &&
+  const bool fast = (G > 1 || fz.ref || g_opt.bwd_variant.load() != 1) && fast_eligible(dtype, pb, value, grad_out, acc) &&
                     aligned16(loc) && aligned16(grad_loc);
   if (int rcg = grouped_supported(who, dtype, pb, fast)) return rcg;
+  if (int rcf = fused_supported(who, dtype, pb, fast)) return rcf;
   int rc = 0;
   switch (dtype) {
     case MSDA_F32:
@@ -432,6 +446,25 @@ int msda_backward_grouped(void* stream, int dtype, const void* value, const int6
                           size_t workspace_bytes) {
   return backward_impl("msda_backward_grouped", stream, dtype, value, shapes, level_start, loc, aw, grad_out, N, S, M, D, G, L,
                        Lq, P, scale, grad_value, grad_loc, grad_aw, workspace, workspace_bytes);
+}
+
+int msda_fused_forward(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                       const void* ref_points, int R, const void* offsets, const void* logits, const void* grid, int mode,
+                       float offset_scale, int N, int S, int M, int D, int G, int L, int Lq, int P, float scale, void* out) {
+  if (!ref_points) return fail(MSDA_ERR_INVALID_ARG, "msda_fused_forward: reference points are NULL");
+  const FusedArgs fz{static_cast<const float*>(ref_points), static_cast<const float*>(grid), R, mode, offset_scale};
+  return forward_impl("msda_fused_forward", stream, dtype, value, shapes, level_start, offsets, logits, N, S, M, D, G, L, Lq, P,
+                      scale, out, fz);
+}
+
+int msda_fused_backward(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                        const void* ref_points, int R, const void* offsets, const void* logits, const void* grid, int mode,
+                        float offset_scale, const void* grad_out, int N, int S, int M, int D, int G, int L, int Lq, int P,
+                        float scale, void* grad_value, void* grad_offsets, void* grad_logits) {
+  if (!ref_points) return fail(MSDA_ERR_INVALID_ARG, "msda_fused_backward: reference points are NULL");
+  const FusedArgs fz{static_cast<const float*>(ref_points), static_cast<const float*>(grid), R, mode, offset_scale};
+  return backward_impl("msda_fused_backward", stream, dtype, value, shapes, level_start, offsets, logits, grad_out, N, S, M, D, G,
+                       L, Lq, P, scale, grad_value, grad_offsets, grad_logits, nullptr, 0, fz);
 }
 
 int mask_logits_forward(void* stream, int in_dtype, int out_dtype, const void* coeff, const void* proto, int B, int Q,

@@ -25,6 +25,62 @@ __device__ __forceinline__ uint32_t fd_div(uint32_t x, const FastDiv f) {
   return f.d == 1 ? x : (__umulhi(x, f.mul) >> f.shr);
 }
 
+// Fused sampler prologue (ms_deform_attn.py:142-161 folded into the kernel): instead of ready-made
+// sampling locations and softmax-normalised weights the kernel gets what the module's Linear layers produce --
+// raw offsets (in the `loc` slot) and raw attention logits (in the `aw` slot) -- plus the reference points, and does
+//   aw  = softmax(logits) over the L*P samples of a (query, head)
+//   loc = ref_xy + offsets / scale                                                         (mode 0: pred_offsets)
+//   loc = ref_xy + (grid[m,l,p] * 0.5 * ref_wh + clamp(offsets, +-ref_wh * scale)) / scale   (mode 1: box-scaled grid)
+// itself; the backward returns d/d offsets and d/d logits.  ref == nullptr: plain operator.
+struct FusedArgs {
+  const float* ref;     // [N*Lq, R]
+  const float* grid;    // [M, L, P, 2] (mode 1) or nullptr
+  int R;                // 2 (cx, cy) or 4 (cx, cy, w, h)
+  int mode;
+  float scale;          // the module's self.scale (8)
+};
+
+// softmax over the LP-lane segment that holds one (query, head) pair; every lane of the warp must call this
+template <int LP>
+__device__ __forceinline__ float segment_softmax(float logit, bool valid) {
+  float mx = valid ? logit : -INFINITY;
+#pragma unroll
+  for (int o = LP / 2; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float e = valid ? expf(logit - mx) : 0.f;
+  float sum = e;
+#pragma unroll
+  for (int o = LP / 2; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  return valid ? e / sum : 0.f;
+}
+template <int LP>
+__device__ __forceinline__ float segment_sum(float v) {
+#pragma unroll
+  for (int o = LP / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// raw offsets (x, y) -> sampling location; mask = d loc / d offset * scale (0 where the clamp is active)
+__device__ __forceinline__ void fused_location(const FusedArgs& fz, uint32_t nq, uint32_t m, int ss, int LPv, float& x, float& y,
+                                               float& mask_x, float& mask_y) {
+  const float* rp = fz.ref + static_cast<size_t>(nq) * fz.R;
+  const float inv = 1.f / fz.scale;
+  mask_x = mask_y = 1.f;
+  if (fz.mode == 0) {
+    x = __ldg(rp) + x * inv;
+    y = __ldg(rp + 1) + y * inv;
+  } else {
+    const float bw = __ldg(rp + 2), bh = __ldg(rp + 3);
+    const float2 g = __ldg(reinterpret_cast<const float2*>(fz.grid) + (m * LPv + ss));
+    const float bx = bw * fz.scale, by = bh * fz.scale;
+    mask_x = (x > -bx && x < bx) ? 1.f : 0.f;
+    mask_y = (y > -by && y < by) ? 1.f : 0.f;
+    float cx = x > -bx ? x : -bx;  cx = cx < bx ? cx : bx;       // the two torch.where of ms_deform_attn.py:149-152
+    float cy = y > -by ? y : -by;  cy = cy < by ? cy : by;
+    x = __ldg(rp) + (g.x * 0.5f * bw + cx) * inv;
+    y = __ldg(rp + 1) + (g.y * 0.5f * bh + cy) * inv;
+  }
+}
+
 template <typename VT, int D, int LP>
 struct Cfg2 : FastCfg<VT, D> {
   using B = FastCfg<VT, D>;
@@ -74,7 +130,7 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
                       const int64_t* __restrict__ level_start, const LT* __restrict__ loc,
                       const LT* __restrict__ aw, VT* __restrict__ out,
                       int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq,
-                      int G, float scale) {
+                      int G, float scale, FusedArgs fz) {
   // G > 1: "grouped" (temporal) form -- G level tables share loc/aw, out = scale * sum_g (see msda_forward_grouped)
   using C = Cfg2<VT, D, LP>;
   __shared__ LevelInfo s_lvl[kMaxLevels];
@@ -102,15 +158,22 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
     const int npair = static_cast<int>(min(static_cast<uint32_t>(C::QPW), chunk_end - p0));
     const bool has_sample = lane < npair * LP;
     float x = 0.f, y = 0.f, a = 0.f;
-    uint32_t n = 0, m = 0;
+    uint32_t n = 0, m = 0, nq = 0;
     if (has_sample) {
       const uint32_t pair = p0 + ps;
-      const uint32_t nq = fd_div(pair, div_m);
+      nq = fd_div(pair, div_m);
       m = pair - nq * div_m.d;
       n = fd_div(pair, div_mq);
       load_loc_aw<LT>(loc, aw, static_cast<int64_t>(p0) * LP + lane, x, y, a);
-      a *= scale;
     }
+    if constexpr (std::is_same<LT, float>::value && (LP & (LP - 1)) == 0) {
+      if (fz.ref != nullptr) {                      // fused prologue: (x, y) are raw offsets, a is a raw logit
+        a = segment_softmax<LP>(a, has_sample);
+        float mk_x, mk_y;
+        if (has_sample) fused_location(fz, nq, m, ss, LP, x, y, mk_x, mk_y);
+      }
+    }
+    a *= scale;
     // GROUPED keeps one accumulator set per pair alive across the G level tables; the plain operator (G == 1)
     // reduces and stores each pair as soon as its corner loop ends (fewer live registers: 81 vs 94 us measured)
     float acc_g[GROUPED ? C::QPW : 1][C::CPL];
@@ -213,7 +276,7 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
                       const LT* __restrict__ aw, const VT* __restrict__ grad_out,
                       float* __restrict__ grad_value, LT* __restrict__ grad_loc, LT* __restrict__ grad_aw,
                       int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq,
-                      int G, float scale) {
+                      int G, float scale, FusedArgs fz) {
   using C = Cfg2<VT, D, LP>;
   // <grad_out, corner row> per (corner, sample): [4][33] floats per warp.  The partials are folded inside the
   // corner group with shuffles first, so the tile stays tiny and shared memory stays small: the first version
@@ -247,16 +310,25 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
   for (uint32_t p0 = chunk_begin + warp * C::QPW; p0 < chunk_end; p0 += kWarpsPerCta * C::QPW) {
     const int npair = static_cast<int>(min(static_cast<uint32_t>(C::QPW), chunk_end - p0));
     const bool has_sample = lane < npair * LP;
-    float x = 0.f, y = 0.f, a = 0.f;
-    uint32_t n = 0, m = 0;
+    float x = 0.f, y = 0.f, a = 0.f, a_raw = 0.f, mk_x = 1.f, mk_y = 1.f;
+    uint32_t n = 0, m = 0, nq = 0;
     if (has_sample) {
       const uint32_t pair = p0 + ps;
-      const uint32_t nq = fd_div(pair, div_m);
+      nq = fd_div(pair, div_m);
       m = pair - nq * div_m.d;
       n = fd_div(pair, div_mq);
       load_loc_aw<LT>(loc, aw, static_cast<int64_t>(p0) * LP + lane, x, y, a);
-      a *= scale;                                   // d out / d value carries the group scale; aw/loc grads are rescaled below
     }
+    bool fused = false;
+    if constexpr (std::is_same<LT, float>::value && (LP & (LP - 1)) == 0) {
+      fused = fz.ref != nullptr;
+      if (fused) {                                  // fused prologue: (x, y) are raw offsets, a is a raw logit
+        a = segment_softmax<LP>(a, has_sample);
+        if (has_sample) fused_location(fz, nq, m, ss, LP, x, y, mk_x, mk_y);
+      }
+    }
+    a_raw = a;
+    a *= scale;                                     // d out / d value carries the group scale; aw/loc grads are rescaled below
     float go_g[GROUPED ? C::QPW : 1][C::CPL];      // GROUPED: grad_out rows stay in registers across the level tables
     if constexpr (GROUPED) {
 #pragma unroll
@@ -340,6 +412,20 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
       __syncwarp();
     }
 
+    if constexpr (std::is_same<LT, float>::value && (LP & (LP - 1)) == 0) {
+      if (fused) {
+        // softmax backward inside the pair's lane segment, chain rule through loc = ref + offsets / scale (+ clamp)
+        const float t = a_raw * (scale * g_aw);
+        const float tsum = segment_sum<LP>(t);
+        if (has_sample) {
+          const int64_t si = static_cast<int64_t>(p0) * LP + lane;
+          const float inv = 1.f / fz.scale;
+          store_pair(grad_loc + 2 * si, a * g_x * inv * mk_x, a * g_y * inv * mk_y);       // d / d raw offsets
+          st_from_float(grad_aw + si, t - a_raw * tsum);                                   // d / d logits
+        }
+        continue;
+      }
+    }
     if (has_sample) {
       const int64_t si = static_cast<int64_t>(p0) * LP + lane;
       if constexpr (std::is_same<LT, float>::value) {

@@ -63,6 +63,36 @@ class MSDeformAttnGroupedFunction(Function):
         return grad_value, None, None, grad_loc, grad_aw, None
 
 
+class MSDeformAttnFusedFunction(Function):
+    """apply(value, spatial_shapes, level_start_index, reference_points, offsets, logits, grid, mode, offset_scale, scale):
+    the sampler with softmax and sampling-location arithmetic inside the kernel (ms_deform_attn.py:142-161 fused, SURVEY 8f
+    N1).  `offsets` / `logits` are the raw outputs of the module's Linear layers; gradients flow to value, offsets, logits
+    (reference points are constants on this path)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, value, spatial_shapes, level_start_index, reference_points, offsets, logits, grid, mode, offset_scale, scale):
+        ctx.cfg = (int(mode), float(offset_scale), float(scale))
+        out = ops.ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, reference_points, offsets, logits,
+                                               grid, *ctx.cfg)
+        ctx.has_grid = grid is not None
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, reference_points, offsets, logits,
+                              *([grid] if grid is not None else []))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        saved = ctx.saved_tensors
+        value, shapes, starts, ref, offsets, logits = saved[:6]
+        grid = saved[6] if ctx.has_grid else None
+        mode, offset_scale, scale = ctx.cfg
+        gv, goff, glog = ops.ms_deform_attn_fused_backward(value, shapes, starts, ref, offsets, logits, grid, mode, offset_scale,
+                                                           grad_output.contiguous(), scale)
+        return gv, None, None, None, goff, glog, None, None, None, None
+
+
 class _MaskLogitsFunction(Function):
     @staticmethod
     def forward(ctx, coeff, proto):

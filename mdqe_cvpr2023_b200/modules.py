@@ -24,7 +24,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from .functions import MSDeformAttnFunction, MSDeformAttnGroupedFunction
+from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnGroupedFunction
 
 
 def _is_power_of_2(n):
@@ -54,6 +54,9 @@ class MSDeformAttn(nn.Module):
         self.pred_offsets = pred_offsets
         self.scale = 8.
         self.n_frames = n_frames
+        # fold softmax + sampling-location arithmetic into the sampler kernel where it is implemented (fp32, D in
+        # {32,24}, L*P in {8,16}, reference points without gradient); set False to run the reference's op sequence
+        self.fused_prologue = True
 
         # what the operator sees as "levels": pyramid levels of a frame, or the frames of a clip
         if mode == 'spatial':
@@ -120,6 +123,16 @@ class MSDeformAttn(nn.Module):
         weights = F.softmax(logits, -1).view(B, Q, H, L, K)
         return locations, weights
 
+    def _fused_inputs(self, query):
+        """raw Linear outputs in the layouts msda_fused_forward expects (views, no copies)."""
+        B, Q, _ = query.shape
+        H, L, K = self.n_heads, self.lvl, self.n_points
+        lin = self.sampling_offsets if self.pred_offsets else self.sampling_grid_offsets
+        offsets = lin(query).view(B, Q, H, L, K, 2)
+        logits = self.attention_weights(query).view(B, Q, H, L * K)
+        grid = None if self.pred_offsets else self.sampling_offsets.reshape(H, L, K, 2).contiguous()
+        return offsets, logits, grid, (0 if self.pred_offsets else 1)
+
     def _project_value(self, input_flatten, input_padding_mask):
         value = self.value_proj(input_flatten)
         if input_padding_mask is not None:
@@ -144,7 +157,12 @@ class MSDeformAttn(nn.Module):
         """query BxQxC, reference_points BxQx4 (cx, cy, w, h), input_flatten BxSxC with S = sum_l H_l*W_l."""
         level_start, sizes = self._level_starts(input_spatial_shapes)
         assert int(sizes.sum()) == input_flatten.shape[1]
-        value = self._project_value(input_flatten, input_padding_mask)               # B S H D
+        value = self._project_value(input_flatten, input_padding_mask).contiguous()  # B S H D
+        if self.fused_prologue and ops.fused_supported(value, reference_points, 1, self.lvl, self.n_points):
+            offsets, logits, grid, mode = self._fused_inputs(query)
+            sampled = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes.contiguous(), level_start,
+                                                      reference_points.contiguous(), offsets, logits, grid, mode, self.scale, 1.0)
+            return self.output_proj(sampled)
         locations, weights = self._sampling(query, reference_points)
         sampled = MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes.contiguous(), level_start,
                                              locations.contiguous(), weights.contiguous(), self.im2col_step)
@@ -159,10 +177,18 @@ class MSDeformAttn(nn.Module):
         level_start, _ = self._level_starts(input_spatial_shapes)
         value = self._project_value(input_flatten, input_padding_mask)               # B T S H D
         value = value.contiguous().view(B, T * S, self.n_heads, -1)                  # frames back to back, no copies
-        locations, weights = self._sampling(query, reference_points)
-        locations, weights = locations.contiguous(), weights.contiguous()
         frame_base = torch.arange(T, device=level_start.device, dtype=level_start.dtype) * S
         n_lvl = input_spatial_shapes.shape[0]
+        if self.fused_prologue and ops.fused_supported(value, reference_points, n_lvl, T, self.n_points):
+            # one launch: all pyramid levels (grouped form) + softmax / location arithmetic inside the kernel
+            shapes_g = input_spatial_shapes.view(n_lvl, 1, 2).expand(n_lvl, T, 2).contiguous()
+            starts_g = (level_start.view(n_lvl, 1) + frame_base.view(1, T)).contiguous()
+            offsets, logits, grid, mode = self._fused_inputs(query)
+            sampled = MSDeformAttnFusedFunction.apply(value, shapes_g, starts_g, reference_points.contiguous(), offsets, logits,
+                                                      grid, mode, self.scale, 1.0 / n_lvl)
+            return self.output_proj(sampled)
+        locations, weights = self._sampling(query, reference_points)
+        locations, weights = locations.contiguous(), weights.contiguous()
         if ops.grouped_supported(value, n_lvl, T, self.n_points):
             # all pyramid levels in ONE launch: level table g = the T frames of pyramid level g, mean folded in
             shapes_g = input_spatial_shapes.view(n_lvl, 1, 2).expand(n_lvl, T, 2).contiguous()

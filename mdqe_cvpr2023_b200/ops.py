@@ -170,6 +170,76 @@ def ms_deform_attn_grouped_backward(value, spatial_shapes, level_start_index, sa
     return [grad_value, grad_loc, grad_aw]
 
 
+def fused_supported(value, reference_points, n_groups, n_levels, n_points):
+    """True when msda_fused_forward / msda_fused_backward implement this configuration."""
+    return (value.is_cuda and value.dim() == 4 and value.dtype == torch.float32 and value.shape[3] in (32, 24)
+            and n_levels * n_points in (8, 16) and n_groups * n_levels <= 32 and value.numel() < 2 ** 31
+            and reference_points.dtype == torch.float32 and reference_points.shape[-1] in (2, 4)
+            and not reference_points.requires_grad)
+
+
+def _fused_dims(value, shapes, level_start, ref, offsets, logits, grid, mode, who):
+    if shapes.dim() == 2:
+        shapes, level_start = shapes.unsqueeze(0), level_start.unsqueeze(0)
+    if shapes.dim() != 3 or shapes.shape[2] != 2 or tuple(level_start.shape) != tuple(shapes.shape[:2]):
+        raise RuntimeError(f"{who}: expected spatial_shapes[G,L,2] (or [L,2]) and matching level_start_index")
+    G, L = shapes.shape[0], shapes.shape[1]
+    N, S, M, D = value.shape
+    if offsets.dim() != 6 or offsets.shape[0] != N or offsets.shape[2] != M or offsets.shape[3] != L or offsets.shape[5] != 2:
+        raise RuntimeError(f"{who}: offsets must be [N,Lq,M,L,P,2], got {tuple(offsets.shape)}")
+    Lq, P = offsets.shape[1], offsets.shape[4]
+    if logits.numel() != N * Lq * M * L * P or ref.dim() != 3 or tuple(ref.shape[:2]) != (N, Lq):
+        raise RuntimeError(f"{who}: logits must have N*Lq*M*L*P elements and reference_points be [N,Lq,R]")
+    if mode == 1 and (grid is None or grid.numel() != M * L * P * 2 or ref.shape[2] != 4):
+        raise RuntimeError(f"{who}: mode 1 needs grid[M,L,P,2] and 4-component reference points")
+    return shapes, level_start, (N, S, M, D, G, L, Lq, P), int(ref.shape[2])
+
+
+def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, reference_points, offsets, logits, grid, mode,
+                                 offset_scale, scale=1.0):
+    """Sampler with the module's elementwise tail folded in (softmax over L*P, loc = ref + offsets/offset_scale, or the
+    box-scaled grid form of the decoder); see msda_fused_forward in include/msda_b200.h.  -> Tensor[N, Lq, M*D]."""
+    who = "ms_deform_attn_fused_forward"
+    tensors = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+               ("reference_points", reference_points), ("offsets", offsets), ("logits", logits)]
+    if grid is not None:
+        tensors.append(("grid", grid))
+    _check_inputs(who, tensors)
+    shapes, starts, (N, S, M, D, G, L, Lq, P), R = _fused_dims(value, spatial_shapes, level_start_index, reference_points,
+                                                               offsets, logits, grid, mode, who)
+    lib = _lib.load()
+    with torch.cuda.device(value.device):
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        rc = lib.msda_fused_forward(_stream_ptr(value.device), _lib.MSDA_F32, value.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
+                                    reference_points.data_ptr(), R, offsets.data_ptr(), logits.data_ptr(),
+                                    grid.data_ptr() if grid is not None else None, int(mode), float(offset_scale),
+                                    N, S, M, D, G, L, Lq, P, float(scale), out.data_ptr())
+    _lib.check(rc, who)
+    return out
+
+
+def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, reference_points, offsets, logits, grid, mode,
+                                  offset_scale, grad_output, scale=1.0):
+    who = "ms_deform_attn_fused_backward"
+    tensors = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+               ("reference_points", reference_points), ("offsets", offsets), ("logits", logits), ("grad_output", grad_output)]
+    if grid is not None:
+        tensors.append(("grid", grid))
+    _check_inputs(who, tensors)
+    shapes, starts, (N, S, M, D, G, L, Lq, P), R = _fused_dims(value, spatial_shapes, level_start_index, reference_points,
+                                                               offsets, logits, grid, mode, who)
+    lib = _lib.load()
+    with torch.cuda.device(value.device):
+        grad_value, grad_offsets, grad_logits = torch.empty_like(value), torch.empty_like(offsets), torch.empty_like(logits)
+        rc = lib.msda_fused_backward(_stream_ptr(value.device), _lib.MSDA_F32, value.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
+                                     reference_points.data_ptr(), R, offsets.data_ptr(), logits.data_ptr(),
+                                     grid.data_ptr() if grid is not None else None, int(mode), float(offset_scale),
+                                     grad_output.data_ptr(), N, S, M, D, G, L, Lq, P, float(scale),
+                                     grad_value.data_ptr(), grad_offsets.data_ptr(), grad_logits.data_ptr())
+    _lib.check(rc, who)
+    return grad_value, grad_offsets, grad_logits
+
+
 _MASK_CODES = {torch.float32: _lib.MSDA_F32, torch.bfloat16: _lib.MSDA_BF16}
 
 

@@ -338,34 +338,70 @@ def test_grouped_temporal_form_vs_oracle(T, D, dtype):
     check((out, gv, gl, ga), want, 2e-5 if dtype == torch.float32 else 2e-2, f"grouped T{T} D{D}")
 
 
-def test_temporal_module_grouped_equals_per_level_loop():
-    """The module's one-launch temporal path (R50 sizes: D=32, T=4) against its own per-level loop path."""
+def _module_run(mod, q, ref, x, shapes, fused, grouped=True):
     import mdqe_cvpr2023_b200.modules as M
     from mdqe_cvpr2023_b200 import ops
+    orig = ops.grouped_supported
+    M.ops.grouped_supported = orig if grouped else (lambda *a: False)
+    mod.fused_prologue = fused
+    try:
+        xi, qi = x.clone().requires_grad_(True), q.clone().requires_grad_(True)
+        mod.zero_grad()
+        out = mod(qi, ref, xi, shapes, None)
+        (out * torch.linspace(-1, 1, out.numel(), device=out.device).view_as(out)).sum().backward()
+        return out.detach(), xi.grad, qi.grad, {k: p.grad.clone() for k, p in mod.named_parameters()}
+    finally:
+        M.ops.grouped_supported = orig
+        mod.fused_prologue = True
+
+
+def _assert_same(a, b, what):
+    assert nerr(a[0], b[0]) < 2e-5, what + " out"
+    assert nerr(a[1], b[1]) < 1e-4, what + " grad input"
+    assert nerr(a[2], b[2]) < 1e-4, what + " grad query"
+    for k in a[3]:
+        assert nerr(a[3][k], b[3][k]) < 1e-4, f"{what} grad {k}"
+
+
+def test_temporal_module_fused_grouped_and_loop_paths_agree():
+    """R50 sizes (D=32, T=4): the module's three temporal code paths -- fused prologue + grouped launch (default), grouped
+    launch with torch softmax / location arithmetic, and the per-level loop of plain operator calls -- give the same
+    output and gradients (the loop path is the one pinned to the reference module by the golden fixtures)."""
+    import mdqe_cvpr2023_b200.modules as M
     torch.manual_seed(0)
     mod = M.MSDeformAttn(d_model=256, n_levels=4, n_heads=8, n_points=4, n_frames=4, pred_offsets=False, mode="temporal").cuda()
     with torch.no_grad():
         for p in mod.parameters():
             p.add_(0.05 * torch.randn_like(p))
     shapes = torch.tensor([(12, 20), (6, 10), (3, 5), (2, 3)], device="cuda")
-    S = 321
-    B, Q, T = 2, 19, 4
+    S, B, Q, T = 321, 2, 19, 4
     x = torch.randn(B, T, S, 256, device="cuda")
     q = torch.randn(B, Q, 256, device="cuda")
     ref = torch.cat([torch.rand(B, Q, 2, device="cuda"), torch.rand(B, Q, 2, device="cuda") * 0.3 + 0.05], -1)
+    loop = _module_run(mod, q, ref, x, shapes, fused=False, grouped=False)
+    _assert_same(_module_run(mod, q, ref, x, shapes, fused=False, grouped=True), loop, "grouped")
+    _assert_same(_module_run(mod, q, ref, x, shapes, fused=True), loop, "fused")
 
-    def run(grouped):
-        orig = ops.grouped_supported
-        M.ops.grouped_supported = orig if grouped else (lambda *a: False)
-        try:
-            xi, qi = x.clone().requires_grad_(True), q.clone().requires_grad_(True)
-            mod.zero_grad()
-            out = mod(qi, ref, xi, shapes, None)
-            out.square().sum().backward()
-            return out.detach(), xi.grad, qi.grad, {k: p.grad.clone() for k, p in mod.named_parameters()}
-        finally:
-            M.ops.grouped_supported = orig
-    a, b = run(True), run(False)
-    assert nerr(a[0], b[0]) < 1e-5 and nerr(a[1], b[1]) < 1e-4 and nerr(a[2], b[2]) < 1e-4
-    for k in a[3]:
-        assert nerr(a[3][k], b[3][k]) < 1e-4, k
+
+@pytest.mark.parametrize("pred_offsets", [True, False])
+def test_spatial_module_fused_prologue_equals_unfused(pred_offsets):
+    """Encoder (learned offsets) and decoder (box-scaled grid + clamped residual) forms of the fused prologue against the
+    module's own torch arithmetic + plain operator, forward and every gradient; the clamp is active for some samples."""
+    import mdqe_cvpr2023_b200.modules as M
+    torch.manual_seed(1)
+    mod = M.MSDeformAttn(d_model=256, n_levels=4, n_heads=8, n_points=4, pred_offsets=pred_offsets, mode="spatial").cuda()
+    with torch.no_grad():
+        for p in mod.parameters():
+            p.add_(0.1 * torch.randn_like(p))
+    shapes = torch.tensor([(12, 20), (6, 10), (3, 5), (2, 3)], device="cuda")
+    S, B = 321, 3
+    Q = S if pred_offsets else 23
+    x = torch.randn(B, S, 256, device="cuda")
+    q = torch.randn(B, Q, 256, device="cuda") * (1.0 if pred_offsets else 3.0)
+    ref = torch.cat([torch.rand(B, Q, 2, device="cuda"), torch.rand(B, Q, 2, device="cuda") * 0.2 + 0.02], -1)
+    _assert_same(_module_run(mod, q, ref, x, shapes, fused=True), _module_run(mod, q, ref, x, shapes, fused=False), "spatial fused")
+    if not pred_offsets:      # the test is only meaningful if some residuals hit the clamp and some do not
+        res = mod.sampling_grid_offsets(q).view(B, Q, 8, 4, 4, 2)
+        bound = ref[..., 2:].view(B, Q, 1, 1, 1, 2) * 8
+        frac = ((res <= -bound) | (res >= bound)).float().mean().item()
+        assert 0.01 < frac < 0.99, frac
