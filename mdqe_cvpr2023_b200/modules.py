@@ -140,9 +140,21 @@ class MSDeformAttn(nn.Module):
         return value.view(*value.shape[:-1], self.n_heads, self.d_model // self.n_heads)
 
     @staticmethod
-    def _level_starts(spatial_shapes):
+    def _geometry(spatial_shapes, n_frames=0, rows_per_frame=0):
+        """level_start_index and (temporal mode) the [G,T,2] / [G,T] level tables, computed on the device without a host
+        sync (the reference's shape assert, ms_deform_attn.py:134, costs one sync per call; a mismatch here surfaces as
+        out-of-range level starts instead).  Not cached: callers rebuild `spatial_shapes` every forward
+        (transformer_enc.py:46) and multi-scale training changes its contents."""
         sizes = spatial_shapes.prod(-1)
-        return torch.cat([sizes.new_zeros(1), sizes.cumsum(0)[:-1]]).long(), sizes
+        starts = torch.cat([sizes.new_zeros(1), sizes.cumsum(0)[:-1]]).long()
+        shapes_c = spatial_shapes.contiguous()
+        shapes_g = starts_g = None
+        if n_frames:
+            n_lvl = spatial_shapes.shape[0]
+            frame_base = torch.arange(n_frames, device=starts.device, dtype=starts.dtype) * rows_per_frame
+            shapes_g = shapes_c.view(n_lvl, 1, 2).expand(n_lvl, n_frames, 2).contiguous()
+            starts_g = (starts.view(n_lvl, 1) + frame_base.view(1, n_frames)).contiguous()
+        return starts, shapes_c, shapes_g, starts_g
 
     # --------------------------------------------------------------------------------- forward
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_padding_mask=None):
@@ -155,16 +167,15 @@ class MSDeformAttn(nn.Module):
     @torch.amp.autocast("cuda", enabled=False)
     def spatial_forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_padding_mask=None):
         """query BxQxC, reference_points BxQx4 (cx, cy, w, h), input_flatten BxSxC with S = sum_l H_l*W_l."""
-        level_start, sizes = self._level_starts(input_spatial_shapes)
-        assert int(sizes.sum()) == input_flatten.shape[1]
+        level_start, shapes_c, _, _ = self._geometry(input_spatial_shapes)
         value = self._project_value(input_flatten, input_padding_mask).contiguous()  # B S H D
         if self.fused_prologue and ops.fused_supported(value, reference_points, 1, self.lvl, self.n_points):
             offsets, logits, grid, mode = self._fused_inputs(query)
-            sampled = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes.contiguous(), level_start,
+            sampled = MSDeformAttnFusedFunction.apply(value, shapes_c, level_start,
                                                       reference_points.contiguous(), offsets, logits, grid, mode, self.scale, 1.0)
             return self.output_proj(sampled)
         locations, weights = self._sampling(query, reference_points)
-        sampled = MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes.contiguous(), level_start,
+        sampled = MSDeformAttnFunction.apply(value.contiguous(), shapes_c, level_start,
                                              locations.contiguous(), weights.contiguous(), self.im2col_step)
         return self.output_proj(sampled)
 
@@ -174,15 +185,12 @@ class MSDeformAttn(nn.Module):
         """query BxQxC, reference_points BxQx4, input_flatten BxTxSxC; the T frames play the role of levels."""
         B, T, S, _ = input_flatten.shape
         assert T == self.n_frames, f"temporal MSDeformAttn built for {self.n_frames} frames, got {T}"
-        level_start, _ = self._level_starts(input_spatial_shapes)
+        level_start, _, shapes_g, starts_g = self._geometry(input_spatial_shapes, T, S)
         value = self._project_value(input_flatten, input_padding_mask)               # B T S H D
         value = value.contiguous().view(B, T * S, self.n_heads, -1)                  # frames back to back, no copies
-        frame_base = torch.arange(T, device=level_start.device, dtype=level_start.dtype) * S
         n_lvl = input_spatial_shapes.shape[0]
         if self.fused_prologue and ops.fused_supported(value, reference_points, n_lvl, T, self.n_points):
             # one launch: all pyramid levels (grouped form) + softmax / location arithmetic inside the kernel
-            shapes_g = input_spatial_shapes.view(n_lvl, 1, 2).expand(n_lvl, T, 2).contiguous()
-            starts_g = (level_start.view(n_lvl, 1) + frame_base.view(1, T)).contiguous()
             offsets, logits, grid, mode = self._fused_inputs(query)
             sampled = MSDeformAttnFusedFunction.apply(value, shapes_g, starts_g, reference_points.contiguous(), offsets, logits,
                                                       grid, mode, self.scale, 1.0 / n_lvl)
@@ -191,14 +199,11 @@ class MSDeformAttn(nn.Module):
         locations, weights = locations.contiguous(), weights.contiguous()
         if ops.grouped_supported(value, n_lvl, T, self.n_points):
             # all pyramid levels in ONE launch: level table g = the T frames of pyramid level g, mean folded in
-            shapes_g = input_spatial_shapes.view(n_lvl, 1, 2).expand(n_lvl, T, 2).contiguous()
-            starts_g = (level_start.view(n_lvl, 1) + frame_base.view(1, T)).contiguous()
             sampled = MSDeformAttnGroupedFunction.apply(value, shapes_g, starts_g, locations, weights, 1.0 / n_lvl)
             return self.output_proj(sampled)
         sampled = None
-        for lvl in range(input_spatial_shapes.shape[0]):
-            shapes_l = input_spatial_shapes[lvl].view(1, 2).expand(T, 2).contiguous()
-            starts_l = frame_base + level_start[lvl]
+        for lvl in range(n_lvl):
+            shapes_l, starts_l = shapes_g[lvl], starts_g[lvl]
             out_l = MSDeformAttnFunction.apply(value, shapes_l, starts_l, locations, weights, self.im2col_step)
             sampled = out_l if sampled is None else sampled + out_l
         sampled = sampled / input_spatial_shapes.shape[0]
