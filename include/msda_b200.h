@@ -62,7 +62,8 @@ int msda_abi_version(void);
 const char* msda_last_error(void);
 
 /* Tuning knobs (kernel variant selection used by bench.py / tests); unknown keys fail.
- * Keys: "fwd_variant", "bwd_variant", "chunk_pairs", "mask_variant", "profile", "mask_debug", "host_async". */
+ * Keys: "fwd_variant", "bwd_variant", "chunk_pairs", "mask_variant", "profile", "mask_debug", "host_async",
+ * "tile_rows", "tile_q". */
 int msda_set_option(const char* key, int value);
 int msda_get_option(const char* key, int* value);
 

@@ -11,6 +11,7 @@
 
 #include "msda_fast.cuh"
 #include "msda_fast2.cuh"
+#include "msda_bwd_tile.cuh"
 #include "msda_generic.cuh"
 #include "msda_internal.h"
 
@@ -40,10 +41,12 @@ int after_launch(const char* kernel_name) {
 
 struct Options {
   std::atomic<int> fwd_variant{0};    // 0 = auto (fast2 / fast when eligible), 1 = force generic, 2 = first-generation fast, 3 = fast2 with batched gathers (80 registers)
-  std::atomic<int> bwd_variant{0};    // same
+  std::atomic<int> bwd_variant{0};    // 0 = auto (fast2 / fast), 1 = generic, 2 = first-generation fast, 5 = tiled fixed-point kernel (experiment, slower)
   std::atomic<int> chunk_pairs{0};    // 0 = auto
   std::atomic<int> mask_variant{0};   // 0 = auto (tcgen05 when eligible), 1 = SIMT fp32, 2 = force tcgen05
   std::atomic<int> mask_debug{0};     // 1 = the tcgen05 mask kernel records per-item clock stamps of CTA 0
+  std::atomic<int> tile_rows{320};    // shared-memory budget (value rows) of the tiled backward (bwd_variant 5 only)
+  std::atomic<int> tile_q{64};        // queries per CTA of the tiled backward
   std::atomic<int> host_async{0};     // 1 = the *_host entries only enqueue; msda_host_sync() completes them
   std::atomic<int> profile{0};        // 1 = bracket the main kernels with CUDA events (msda_profile_read)
 };
@@ -58,6 +61,8 @@ static std::atomic<int>* find_option(const char* key) {
   if (!strcmp(key, "profile")) return &g_opt.profile;
   if (!strcmp(key, "mask_debug")) return &g_opt.mask_debug;
   if (!strcmp(key, "host_async")) return &g_opt.host_async;
+  if (!strcmp(key, "tile_rows")) return &g_opt.tile_rows;
+  if (!strcmp(key, "tile_q")) return &g_opt.tile_q;
   return nullptr;
 }
 
@@ -245,6 +250,28 @@ static int launch_bwd(cudaStream_t st, const Problem& pb, bool fast, const void*
     if (fast) {
       const int chunk = pick_chunk(pb);
       const unsigned grid = static_cast<unsigned>((pb.n_pairs + chunk - 1) / chunk);
+      if constexpr (std::is_same<VT, float>::value && std::is_same<LT, float>::value) {
+        // large plain fp32 calls with MDQE's 4 levels x 4 points: coarse levels pre-reduced in shared memory
+        const int rows = g_opt.tile_rows.load(), qpc = g_opt.tile_q.load();
+        const int bv = g_opt.bwd_variant.load();
+        if (bv == 5 && rows > 0 && qpc >= 16 && pb.G == 1 && pb.scale == 1.f && pb.fz.ref == nullptr && pb.L == 4 &&
+            pb.P == 4 && pb.Lq >= 4 * qpc && pb.M <= 65535 && pb.N <= 65535) {
+          const size_t dyn = (size_t)rows * kTilePitch * sizeof(int);
+          static std::once_flag once;
+          std::call_once(once, [] {
+            cudaFuncSetAttribute(msda_bwd_tile_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            cudaFuncSetAttribute(msda_bwd_tile_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+          });
+          if (dyn <= 160 * 1024) {
+            const dim3 gridt((pb.Lq + qpc - 1) / qpc, pb.M, pb.N);
+            if (pb.D == 32)
+              msda_bwd_tile_kernel<32><<<gridt, kThreads, dyn, st>>>(v, shapes, lsi, lc, a, go, gv_acc, gl, ga, pb.S, pb.M, pb.Lq, qpc, rows);
+            else
+              msda_bwd_tile_kernel<24><<<gridt, kThreads, dyn, st>>>(v, shapes, lsi, lc, a, go, gv_acc, gl, ga, pb.S, pb.M, pb.Lq, qpc, rows);
+            return after_launch("msda_bwd_tile_kernel");
+          }
+        }
+      }
       if (g_opt.bwd_variant.load() != 2 && fast2_lp(pb.L * pb.P)) {
         dim3 grid2(grid, 1, 1);
         if (split_groups<VT, LT>(pb)) {
