@@ -26,15 +26,16 @@ static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
   return fn;
 }
 
-// bf16 tensor [d2, d1, d0] (d0 contiguous) -> 3-D tiled map with a {64, box1, 1} box and 128B swizzle.
-static int make_map_bf16(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1) {
+// bf16 / fp32 tensor [d2, d1, d0] (d0 contiguous) -> 3-D tiled map with a {128 bytes, box1, 1} box and 128B swizzle.
+static int make_map_in(CUtensorMap* map, const void* base, bool fp32, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
   if (!enc) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const uint64_t es = fp32 ? 4 : 2;
   const cuuint64_t dims[3] = {d0, d1, d2};
-  const cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
-  const cuuint32_t box[3] = {64, box1, 1};
+  const cuuint64_t strides[2] = {d0 * es, d0 * d1 * es};
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / es), box1, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  const CUresult r = enc(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
@@ -93,8 +94,8 @@ static int launch_mask_tc2(cudaStream_t st, const void* coeff, const void* proto
   const int64_t n_items = tiles * n_qchunks;
   if (n_items >= (int64_t(1) << 31)) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: too many tiles");
   CUtensorMap map_proto, map_coeff, map_out;
-  if (int rc = make_map_bf16(&map_proto, proto, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, (uint32_t)KP)) return rc;
-  if (int rc = make_map_bf16(&map_coeff, coeff, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QN)) return rc;
+  if (int rc = make_map_in(&map_proto, proto, false, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, (uint32_t)KP)) return rc;
+  if (int rc = make_map_in(&map_coeff, coeff, false, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QN)) return rc;
   if (int rc = make_map_out(&map_out, out, sizeof(OT) == 2, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B)) return rc;
   const size_t smem = mask_tc2_smem_bytes(KP, QN, sizeof(OT));
   static std::once_flag attr_once;
@@ -117,6 +118,69 @@ static int launch_mask_tc2(cudaStream_t st, const void* coeff, const void* proto
   return after_launch("mask_fwd_tc2_kernel");
 }
 
+// fp32 tensor [d2, d1, d0], no swizzle, box {128, box1, 1}: the proto tile of the 3xTF32 kernel (transposed on chip)
+static int make_map_plain_f32(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
+  if (!enc) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
+  const cuuint32_t box[3] = {kTcTileN, box1, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled(proto fp32) failed (CUresult %d)", static_cast<int>(r));
+  return 0;
+}
+
+// fp32 inputs: 3xTF32 on the tensor cores (mask_fwd_tc3_kernel)
+static bool mask_tc3_eligible(int in_dtype, const void* coeff, const void* proto, int Q, int K, int64_t Ncols) {
+  if (in_dtype != MSDA_F32) return false;
+  if (K < 8 || K > 32 || K % 8 != 0) return false;                     // one 128-byte fp32 row per query, K steps of 8
+  if (Q < 1) return false;
+  if (Ncols % 4 != 0 || Ncols >= (int64_t(1) << 31)) return false;     // 16-byte global strides
+  return ((reinterpret_cast<uintptr_t>(coeff) | reinterpret_cast<uintptr_t>(proto)) & 15u) == 0;
+}
+
+template <typename OT>
+static int launch_mask_tc3(cudaStream_t st, const void* coeff, const void* proto, void* out, int B, int Q, int K,
+                           int64_t Ncols) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int KP = (K + 7) / 8 * 8;
+  const int n_tiles_n = static_cast<int>((Ncols + kTcTileN - 1) / kTcTileN);
+  const int64_t tiles = (int64_t)B * n_tiles_n;
+  int n_qchunks = (Q + 127) / 128;                                      // at most 128 query rows per item (shared-memory budget)
+  while (n_qchunks < 4 && tiles * n_qchunks < 6LL * sms && (Q / (n_qchunks + 1)) / 32 * 32 >= 32) ++n_qchunks;
+  int QS = 0, QN = 0;
+  for (;; ++n_qchunks) {                                                 // chunk starts are multiples of 32, the last takes the rest
+    QS = (n_qchunks == 1) ? ((Q + 31) / 32 * 32) : (Q / n_qchunks) / 32 * 32;
+    if (QS < 32) break;
+    const int last_rows = Q - (n_qchunks - 1) * QS;
+    QN = ((QS > last_rows ? QS : last_rows) + 15) / 16 * 16;
+    if (QN <= 128) break;
+  }
+  if (QN > 128 || QS < 32) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: cannot chunk Q=%d for the tensor-core kernel", Q);
+  const int64_t n_items = tiles * n_qchunks;
+  if (n_items >= (int64_t(1) << 31)) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: too many tiles");
+  CUtensorMap map_proto, map_coeff, map_out;
+  if (int rc = make_map_plain_f32(&map_proto, proto, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, (uint32_t)KP)) return rc;
+  if (int rc = make_map_in(&map_coeff, coeff, true, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QN)) return rc;
+  if (int rc = make_map_out(&map_out, out, sizeof(OT) == 2, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B)) return rc;
+  const size_t smem = mask_tc3_smem_bytes(KP, QN, sizeof(OT));
+  if (smem > 225 * 1024) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: tile does not fit shared memory");
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(mask_fwd_tc3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    cudaFuncSetAttribute(mask_fwd_tc3_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+  });
+  const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);
+  ProfScope prof(st, MSDA_PROF_MASK_FWD, (int64_t)B * Q * Ncols);
+  mask_fwd_tc3_kernel<OT><<<grid, kTc3Threads, smem, st>>>(map_proto, map_coeff, map_out, Q, KP, QS, QN, n_qchunks, n_tiles_n,
+                                                          static_cast<int>(n_items));
+  return after_launch("mask_fwd_tc3_kernel");
+}
+
 template <typename OT>
 static int launch_mask_tc(cudaStream_t st, const void* coeff, const void* proto, void* out, int B, int Q, int K,
                           int64_t Ncols) {
@@ -124,8 +188,8 @@ static int launch_mask_tc(cudaStream_t st, const void* coeff, const void* proto,
   int tmem_cols = 32;
   while (tmem_cols < QP) tmem_cols *= 2;
   CUtensorMap map_proto, map_coeff;
-  if (int rc = make_map_bf16(&map_proto, proto, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, (uint32_t)KP)) return rc;
-  if (int rc = make_map_bf16(&map_coeff, coeff, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QP)) return rc;
+  if (int rc = make_map_in(&map_proto, proto, false, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, (uint32_t)KP)) return rc;
+  if (int rc = make_map_in(&map_coeff, coeff, false, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QP)) return rc;
   const size_t smem = mask_tc_smem_bytes(KP, QP);
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
@@ -154,8 +218,8 @@ int mask_forward_dispatch(cudaStream_t st, int in_dtype, int out_dtype, const vo
   if (B > 65535) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: B=%d > 65535", B);
   const int variant = option("mask_variant");
   const bool tc_ok = mask_tc_eligible(in_dtype, coeff, proto, Q, K, Ncols);
-  if (variant == 2 && !tc_ok)
-    return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: tcgen05 path needs bf16 inputs, K %% 8 == 0, K <= 64, Q <= 256, Ncols %% 8 == 0");
+  if (variant == 2 && !tc_ok && !mask_tc3_eligible(in_dtype, coeff, proto, Q, K, Ncols))
+    return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: tcgen05 path needs K %% 8 == 0 with K <= 64 (bf16) / 32 (fp32) and 16-byte aligned rows");
   if (variant == 3 && tc_ok) {                       // 3 = first (one tile per CTA) tensor-core kernel, kept for A/B timing
     if (out_dtype == MSDA_F32) return launch_mask_tc<float>(st, coeff, proto, out, B, Q, K, Ncols);
     return launch_mask_tc<__nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
@@ -163,6 +227,10 @@ int mask_forward_dispatch(cudaStream_t st, int in_dtype, int out_dtype, const vo
   if (variant != 1 && tc_ok) {
     if (out_dtype == MSDA_F32) return launch_mask_tc2<float>(st, coeff, proto, out, B, Q, K, Ncols);
     return launch_mask_tc2<__nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
+  }
+  if (variant != 1 && mask_tc3_eligible(in_dtype, coeff, proto, Q, K, Ncols)) {
+    if (out_dtype == MSDA_F32) return launch_mask_tc3<float>(st, coeff, proto, out, B, Q, K, Ncols);
+    return launch_mask_tc3<__nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
   }
   if (in_dtype == MSDA_F32 && out_dtype == MSDA_F32) return launch_mask_simt<float, float>(st, coeff, proto, out, B, Q, K, Ncols);
   if (in_dtype == MSDA_F32 && out_dtype == MSDA_BF16) return launch_mask_simt<float, __nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);

@@ -373,6 +373,220 @@ mask_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
+// -------------------------------------------------------------------------------------------------
+// fp32 inputs on the tensor cores with fp32 accuracy ("3xTF32"): the reference trains in fp32 (AMP disabled,
+// configs/R50_coco.yaml:41-42) and a single TF32 or bf16 pass would miss the 1e-4 parity bar, so every operand is split
+// on chip into  a = hi + lo,  hi = a with the low 13 mantissa bits cleared (exactly a TF32 number), lo = a - hi (exact in
+// fp32, 13 significant bits), and the product is accumulated as  hi*hi + hi*lo + lo*hi  in the fp32 TMEM accumulator
+// (the dropped lo*lo term is 2^-22 relative).  Same persistent pipeline as mask_fwd_tc2_kernel plus one stage:
+//   warp 0 TMA producer -> warps 10..13 "split" warps (hi in place, lo to a twin tile; generic-proxy writes are made
+//   visible to the tensor core with fence.proxy.async) -> warp 1 MMA issuer (kind::tf32, K = 8 per instruction, 3 terms)
+//   -> warps 2..9 epilogue (TMEM -> shared -> bulk tensor store).
+// Both operands are staged K-major for kind::tf32: coeff rows (32 k x 4 B = one 128-byte swizzle row) arrive that way
+// from TMA and are split in place; the proto tile arrives as plain [k][128 columns] rows (no swizzle) and the split warps
+// transpose it into the canonical K-major 128B-swizzle layout while splitting (element (n, k) -> n*128 + ((k/4) ^ (n%8))*16
+// + (k%4)*4: 4 conflict-free LDS.32 and one conflict-free STS.128 per 4 elements).  K <= 32, <= 128 query rows per item.
+constexpr int kTc3Stages = 2;
+constexpr int kTc3Threads = 448;
+constexpr int kTc3SplitWarps = 4;
+
+// kind::tf32, D = fp32, A and B both K-major (32-bit operands are staged K-major: the split warps transpose proto)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_m128(uint32_t n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <typename OT>
+__global__ void __launch_bounds__(kTc3Threads, 1)
+mask_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_constant__ CUtensorMap map_coeff,
+                    const __grid_constant__ CUtensorMap map_out, int Q, int KP, int QS, int QN, int n_qchunks,
+                    int n_tiles_n, int n_items) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t raw_bytes = (static_cast<uint32_t>(KP) * kTcTileN * 4u + 1023u) & ~1023u;   // proto tile as loaded: [k][128 n]
+  const uint32_t a_bytes = kTcTileN * 128u;                              // K-major operand tile: 128 rows (n) x 128 B
+  const uint32_t b_bytes = (static_cast<uint32_t>(QN) * 128u + 1023u) & ~1023u;
+  const uint32_t stage_bytes = raw_bytes + 2 * a_bytes + 2 * b_bytes;    // [raw][A hi][A lo][B hi][B lo]
+  constexpr uint32_t kOutBuf = 32u * kTcTileN * sizeof(OT);
+  uint8_t* out_stage = smem + kTc3Stages * stage_bytes;
+  __shared__ __align__(8) uint64_t bars[3 * kTc3Stages + 4];
+  __shared__ uint32_t s_tmem_base;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };                                  // TMA landed
+  auto bar_ready = [&](int s) { return bar0 + 8u * (kTc3Stages + s); };                  // split done
+  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * kTc3Stages + s); };              // MMAs consumed the stage
+  auto bar_tfull = [&](int a) { return bar0 + 8u * (3 * kTc3Stages + a); };
+  auto bar_tempty = [&](int a) { return bar0 + 8u * (3 * kTc3Stages + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTc3Stages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_ready(s), kTc3SplitWarps); mbar_init(bar_empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), kTc2EpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_proto) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_coeff) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem_base;
+
+  auto decode = [&](int item, int& b, int& tile, int& qc) {
+    const int per_chunk = n_items / n_qchunks;
+    qc = item / per_chunk;
+    const int t = item - qc * per_chunk;
+    tile = t % n_tiles_n;
+    b = t / n_tiles_n;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int i = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+        const int s = i % kTc3Stages;
+        const uint32_t ph = (i / kTc3Stages) & 1;
+        int b, tile, qc;
+        decode(item, b, tile, qc);
+        mbar_wait(bar_empty(s), ph ^ 1);
+        const uint32_t dst = smem_u32(smem) + s * stage_bytes;
+        mbar_expect_tx(bar_full(s), static_cast<uint32_t>(KP) * kTcTileN * 4u + static_cast<uint32_t>(QN) * 128u);
+        tma_load_3d(dst, &map_proto, bar_full(s), tile * kTcTileN, 0, b);
+        tma_load_3d(dst + raw_bytes + 2 * a_bytes, &map_coeff, bar_full(s), 0, qc * QS, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32_m128(static_cast<uint32_t>(QN));
+      int i = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+        const int s = i % kTc3Stages, a = i & 1;
+        const uint32_t ph = (i / kTc3Stages) & 1, aph = (i >> 1) & 1;
+        mbar_wait(bar_tempty(a), aph ^ 1);
+        mbar_wait(bar_ready(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_u32(smem) + s * stage_bytes + raw_bytes, a_lo = a_hi + a_bytes;
+        const uint32_t b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
+        const uint32_t a_sel[3] = {a_hi, a_hi, a_lo}, b_sel[3] = {b_hi, b_lo, b_hi};     // hi*hi + hi*lo + lo*hi
+        uint32_t acc = 0;
+        for (int term = 0; term < 3; ++term)
+          for (int ks = 0; ks < KP / 8; ++ks) {
+            const uint64_t a_desc = umma_desc_sw128(a_sel[term] + ks * 32u, 16u, 1024u);
+            const uint64_t b_desc = umma_desc_sw128(b_sel[term] + ks * 32u, 16u, 1024u);
+            umma_tf32(tmem_base + a * 256u, a_desc, b_desc, idesc, acc);
+            acc = 1;
+          }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_empty(s)) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_tfull(a)) : "memory");
+      }
+    }
+  } else if (warp >= 2 + kTc2EpiWarps) {
+    // ---- split warps: hi in place, lo into the twin tile (same swizzled position: the op is element-wise)
+    const int t = threadIdx.x - (2 + kTc2EpiWarps) * 32;                 // 0 .. 127
+    int i = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+      const int s = i % kTc3Stages;
+      const uint32_t ph = (i / kTc3Stages) & 1;
+      mbar_wait(bar_full(s), ph);
+      uint8_t* st = smem + s * stage_bytes;
+      const float* raw = reinterpret_cast<const float*>(st);
+      uint8_t* a_hi = st + raw_bytes;
+      uint8_t* a_lo = a_hi + a_bytes;
+      uint4* b_hi = reinterpret_cast<uint4*>(st + raw_bytes + 2 * a_bytes);
+      uint4* b_lo = reinterpret_cast<uint4*>(st + raw_bytes + 2 * a_bytes + b_bytes);
+      auto split = [](uint4& v, uint4& lo) {
+        uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
+        uint32_t* pl = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t hi = pv[e] & 0xffffe000u;
+          pl[e] = __float_as_uint(__uint_as_float(pv[e]) - __uint_as_float(hi));
+          pv[e] = hi;
+        }
+      };
+      // proto: transpose [k][n] -> K-major rows of n, split; thread <-> column n (conflict-free both ways).  k rows
+      // beyond KP (up to 32) are zero so that the unused half of a K step contributes nothing.
+      {
+        const int n = t;                                                // 128 split threads <-> 128 columns
+        const uint32_t rowoff = static_cast<uint32_t>(n) * 128u;
+#pragma unroll
+        for (int kq = 0; kq < 8; ++kq) {
+          uint4 v = make_uint4(0u, 0u, 0u, 0u), lo;
+          if (kq * 4 < KP) {
+            v.x = __float_as_uint(raw[(kq * 4 + 0) * kTcTileN + n]);
+            v.y = __float_as_uint(raw[(kq * 4 + 1) * kTcTileN + n]);
+            v.z = __float_as_uint(raw[(kq * 4 + 2) * kTcTileN + n]);
+            v.w = __float_as_uint(raw[(kq * 4 + 3) * kTcTileN + n]);
+          }
+          split(v, lo);
+          const uint32_t off = rowoff + static_cast<uint32_t>((kq ^ (n & 7)) * 16);
+          *reinterpret_cast<uint4*>(a_hi + off) = v;
+          *reinterpret_cast<uint4*>(a_lo + off) = lo;
+        }
+      }
+      for (uint32_t k = t; k < static_cast<uint32_t>(QN) * 8u; k += kTc3SplitWarps * 32) { uint4 v = b_hi[k], lo; split(v, lo); b_hi[k] = v; b_lo[k] = lo; }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ready(s));
+    }
+  } else {
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const bool is_issuer = ((warp - 2) & 3) == 0 && lane == 0;
+    OT* my_stage = reinterpret_cast<OT*>(out_stage + (half * 2) * kOutBuf);
+    uint32_t use = 0;
+    int i = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+      const int a = i & 1;
+      const uint32_t aph = (i >> 1) & 1;
+      int b, tile, qc;
+      decode(item, b, tile, qc);
+      const int q_begin = qc * QS;
+      const int rows = (qc == n_qchunks - 1) ? (Q - q_begin) : QS;
+      mbar_wait(bar_tfull(a), aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t lane_base = tmem_base + a * 256u + (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int q0 = half * 32; q0 < rows; q0 += 64, ++use) {
+        OT* buf = my_stage + (use & 1) * (32 * kTcTileN);
+        if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        named_bar_sync(1 + half, 128);
+        float v[32];
+        tmem_ld32(lane_base + static_cast<uint32_t>(q0), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st_stage(buf + j * kTcTileN + quarter * 32 + lane, v[j]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        named_bar_sync(1 + half, 128);
+        if (is_issuer) tma_store_3d(&map_out, smem_u32(buf), tile * kTcTileN, q_begin + q0, b);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty(a));
+    }
+    if (is_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+inline size_t mask_tc3_smem_bytes(int KP, int QN, size_t out_elem) {
+  const size_t raw_bytes = (static_cast<size_t>(KP) * kTcTileN * 4 + 1023) & ~size_t(1023);
+  const size_t a_bytes = static_cast<size_t>(kTcTileN) * 128;
+  const size_t b_bytes = (static_cast<size_t>(QN) * 128 + 1023) & ~size_t(1023);
+  return 1024 + kTc3Stages * (raw_bytes + 2 * a_bytes + 2 * b_bytes) + 4 * 32 * kTcTileN * out_elem;
+}
+
 inline size_t mask_tc2_smem_bytes(int KP, int QN, size_t out_elem) {
   const size_t stage = (2 * static_cast<size_t>(KP) * 128 + static_cast<size_t>(QN) * 128 + 1023) & ~size_t(1023);
   return 1024 + kTc2Stages * stage + 4 * 32 * kTcTileN * out_elem;

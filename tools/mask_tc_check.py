@@ -27,7 +27,7 @@ for plane in ((96, 160), (160, 288)):
     proto = torch.randn(1, 32, 4, *plane, device="cuda").bfloat16()
     c32, p32 = coeff.float(), proto.float()
     n = 4 * plane[0] * plane[1]
-    for name, variant, cc, pp, od in (("simt f32->f32", 1, c32, p32, torch.float32), ("tc1 bf16->f32", 3, coeff, proto, torch.float32),
+    for name, variant, cc, pp, od in (("simt f32->f32", 1, c32, p32, torch.float32), ("tc3 f32->f32 (3xTF32)", 0, c32, p32, torch.float32), ("tc1 bf16->f32", 3, coeff, proto, torch.float32),
                                       ("tc1 bf16->bf16", 3, coeff, proto, torch.bfloat16), ("tc2 bf16->f32", 2, coeff, proto, torch.float32),
                                       ("tc2 bf16->bf16", 2, coeff, proto, torch.bfloat16)):
         _lib.set_option("mask_variant", variant)
