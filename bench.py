@@ -534,7 +534,7 @@ def main():
     roofline_fwd = roof(fwd_bytes, fwd_ms, fwd_n, "msda_fwd_fast2_kernel<%s,32,16> (encoder shape N=4,S=Lq=5100)" % ("bf16" if args.dtype == "bf16" else "float"))
     mB = QUERIES * MASK_K + MASK_K * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
     mO = QUERIES * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
-    roofline_mask = roof(mB * esize + mO * esize, mfw_ms, mfw_n, "mask_fwd_tc2_kernel<bf16> (tcgen05)" if args.dtype == "bf16" else "mask_fwd_simt_kernel<float,float>")
+    roofline_mask = roof(mB * esize + mO * esize, mfw_ms, mfw_n, "mask_fwd_tc2_kernel<bf16> (tcgen05)" if args.dtype == "bf16" else "mask_fwd_tc3_kernel<float> (tcgen05, 3xTF32)")
     if roofline_mask:
         flops = 2.0 * QUERIES * MASK_K * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
         roofline_mask["tflops"] = flops / (roofline_mask["avg_launch_us"] * 1e-6) / 1e12
