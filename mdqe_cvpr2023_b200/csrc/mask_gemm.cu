@@ -6,6 +6,7 @@
 
 #include "mask_simt.cuh"
 #include "mask_tc.cuh"
+#include "mask_tc_bwd.cuh"
 #include "msda_internal.h"
 
 namespace msda {
@@ -119,12 +120,13 @@ static int launch_mask_tc2(cudaStream_t st, const void* coeff, const void* proto
 }
 
 // fp32 tensor [d2, d1, d0], no swizzle, box {128, box1, 1}: the proto tile of the 3xTF32 kernel (transposed on chip)
-static int make_map_plain_f32(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1) {
+static int make_map_plain_f32(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1,
+                              uint32_t box0 = kTcTileN) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
   if (!enc) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[3] = {d0, d1, d2};
   const cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
-  const cuuint32_t box[3] = {kTcTileN, box1, 1};
+  const cuuint32_t box[3] = {box0, box1, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -136,18 +138,19 @@ static int make_map_plain_f32(CUtensorMap* map, const void* base, uint64_t d0, u
 // fp32 inputs: 3xTF32 on the tensor cores (mask_fwd_tc3_kernel)
 static bool mask_tc3_eligible(int in_dtype, const void* coeff, const void* proto, int Q, int K, int64_t Ncols) {
   if (in_dtype != MSDA_F32) return false;
-  if (K < 8 || K > 32 || K % 8 != 0) return false;                     // one 128-byte fp32 row per query, K steps of 8
+  if (K < 4 || K % 4 != 0) return false;                               // 16-byte global row strides (reduction walked 32 at a time)
   if (Q < 1) return false;
   if (Ncols % 4 != 0 || Ncols >= (int64_t(1) << 31)) return false;     // 16-byte global strides
   return ((reinterpret_cast<uintptr_t>(coeff) | reinterpret_cast<uintptr_t>(proto)) & 15u) == 0;
 }
 
-template <typename OT>
+// out[b, r, n] = sum_k A[b, r, k] * P[b, k, n]  (kTransA: A is given as [b, k, r]).  Q = rows r, K = reduction length.
+template <typename OT, bool kTransA>
 static int launch_mask_tc3(cudaStream_t st, const void* coeff, const void* proto, void* out, int B, int Q, int K,
-                           int64_t Ncols) {
+                           int64_t Ncols, int prof_kind = MSDA_PROF_MASK_FWD) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int KP = (K + 7) / 8 * 8;
+  const int n_kchunks = (K + 31) / 32;
   const int n_tiles_n = static_cast<int>((Ncols + kTcTileN - 1) / kTcTileN);
   const int64_t tiles = (int64_t)B * n_tiles_n;
   int n_qchunks = (Q + 127) / 128;                                      // at most 128 query rows per item (shared-memory budget)
@@ -164,19 +167,25 @@ static int launch_mask_tc3(cudaStream_t st, const void* coeff, const void* proto
   const int64_t n_items = tiles * n_qchunks;
   if (n_items >= (int64_t(1) << 31)) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: too many tiles");
   CUtensorMap map_proto, map_coeff, map_out;
-  if (int rc = make_map_plain_f32(&map_proto, proto, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, (uint32_t)KP)) return rc;
-  if (int rc = make_map_in(&map_coeff, coeff, true, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QN)) return rc;
+  if (int rc = make_map_plain_f32(&map_proto, proto, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, 32u)) return rc;
+  if (kTransA) {
+    if (int rc = make_map_plain_f32(&map_coeff, coeff, (uint64_t)Q, (uint64_t)K, (uint64_t)B, 32u, (uint32_t)QN)) return rc;
+  } else {
+    if (int rc = make_map_in(&map_coeff, coeff, true, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QN)) return rc;
+  }
   if (int rc = make_map_out(&map_out, out, sizeof(OT) == 2, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B)) return rc;
-  const size_t smem = mask_tc3_smem_bytes(KP, QN, sizeof(OT));
+  const size_t smem = mask_tc3_smem_bytes(QN, sizeof(OT), kTransA);
   if (smem > 225 * 1024) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: tile does not fit shared memory");
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(mask_fwd_tc3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-    cudaFuncSetAttribute(mask_fwd_tc3_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    cudaFuncSetAttribute(mask_fwd_tc3_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    cudaFuncSetAttribute(mask_fwd_tc3_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    cudaFuncSetAttribute(mask_fwd_tc3_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    cudaFuncSetAttribute(mask_fwd_tc3_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
   });
   const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);
-  ProfScope prof(st, MSDA_PROF_MASK_FWD, (int64_t)B * Q * Ncols);
-  mask_fwd_tc3_kernel<OT><<<grid, kTc3Threads, smem, st>>>(map_proto, map_coeff, map_out, Q, KP, QS, QN, n_qchunks, n_tiles_n,
+  ProfScope prof(st, prof_kind, (int64_t)B * Q * Ncols);
+  mask_fwd_tc3_kernel<OT, kTransA><<<grid, kTc3Threads, smem, st>>>(map_proto, map_coeff, map_out, Q, n_kchunks, QS, QN, n_qchunks, n_tiles_n,
                                                           static_cast<int>(n_items));
   return after_launch("mask_fwd_tc3_kernel");
 }
@@ -229,13 +238,45 @@ int mask_forward_dispatch(cudaStream_t st, int in_dtype, int out_dtype, const vo
     return launch_mask_tc2<__nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
   }
   if (variant != 1 && mask_tc3_eligible(in_dtype, coeff, proto, Q, K, Ncols)) {
-    if (out_dtype == MSDA_F32) return launch_mask_tc3<float>(st, coeff, proto, out, B, Q, K, Ncols);
-    return launch_mask_tc3<__nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
+    if (out_dtype == MSDA_F32) return launch_mask_tc3<float, false>(st, coeff, proto, out, B, Q, K, Ncols);
+    return launch_mask_tc3<__nv_bfloat16, false>(st, coeff, proto, out, B, Q, K, Ncols);
   }
   if (in_dtype == MSDA_F32 && out_dtype == MSDA_F32) return launch_mask_simt<float, float>(st, coeff, proto, out, B, Q, K, Ncols);
   if (in_dtype == MSDA_F32 && out_dtype == MSDA_BF16) return launch_mask_simt<float, __nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
   if (in_dtype == MSDA_BF16 && out_dtype == MSDA_F32) return launch_mask_simt<__nv_bfloat16, float>(st, coeff, proto, out, B, Q, K, Ncols);
   return launch_mask_simt<__nv_bfloat16, __nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
+}
+
+// grad_coeff on the tensor cores (mask_grad_coeff_tc_kernel); grad_coeff must already be zeroed
+static int launch_mask_grad_coeff_tc(cudaStream_t st, const void* proto, const void* grad_out, void* grad_coeff, int B,
+                                     int Q, int K, int64_t Ncols) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int KP = (K + 15) / 16 * 16;
+  const int MH = Q > 128 ? 2 : 1;
+  const int n_qblocks = (Q + 128 * MH - 1) / (128 * MH);
+  const int n_chunks = static_cast<int>((Ncols + 31) / 32);
+  const size_t b_bytes = (static_cast<size_t>(KP) * 128 + 1023) & ~size_t(1023);
+  const size_t stage = 2 * static_cast<size_t>(MH) * kGcTcHalfBytes + 2 * b_bytes;
+  int n_stages = static_cast<int>((224 * 1024) / stage);
+  if (n_stages > kGcTcMaxStages) n_stages = kGcTcMaxStages;
+  if (n_stages < 2) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_backward: K=%d too large for the tensor-core kernel", K);
+  int64_t slices = sms / ((int64_t)B * n_qblocks);
+  if (slices < 1) slices = 1;
+  if (slices > n_chunks) slices = n_chunks;
+  const int cps = static_cast<int>((n_chunks + slices - 1) / slices);
+  slices = (n_chunks + cps - 1) / cps;
+  CUtensorMap map_go, map_proto;
+  if (int rc = make_map_in(&map_go, grad_out, true, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B, 128u)) return rc;
+  if (int rc = make_map_in(&map_proto, proto, true, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, (uint32_t)KP)) return rc;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(mask_grad_coeff_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  });
+  const dim3 grid(static_cast<unsigned>(slices), static_cast<unsigned>(n_qblocks), static_cast<unsigned>(B));
+  mask_grad_coeff_tc_kernel<<<grid, kGcTcThreads, 1024 + n_stages * stage, st>>>(map_go, map_proto, static_cast<float*>(grad_coeff), Q, K, KP, MH,
+                                                                                n_stages, n_chunks, cps);
+  return after_launch("mask_grad_coeff_tc_kernel");
 }
 
 int mask_backward_dispatch(cudaStream_t st, int dtype, const void* coeff, const void* proto, const void* grad_out,
@@ -258,7 +299,12 @@ int mask_backward_dispatch(cudaStream_t st, int dtype, const void* coeff, const 
     return after_launch("mask_bwd_simt_kernel");
   }
   const unsigned kblocks = (K + 31) / 32;
-  if (grad_coeff) {
+  const bool tc_ok = option("mask_variant") != 1 && K % 4 == 0 && K <= 128 && Ncols % 4 == 0 && Ncols < (int64_t(1) << 31) && Q < 65536 * 128 &&
+                     ((reinterpret_cast<uintptr_t>(coeff) | reinterpret_cast<uintptr_t>(proto) | reinterpret_cast<uintptr_t>(grad_out) |
+                       reinterpret_cast<uintptr_t>(grad_coeff) | reinterpret_cast<uintptr_t>(grad_proto)) & 15u) == 0;
+  if (grad_coeff && tc_ok) {
+    if (int rc = launch_mask_grad_coeff_tc(st, proto, grad_out, grad_coeff, B, Q, K, Ncols)) return rc;
+  } else if (grad_coeff) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int q_blocks = (Q + kGcQ - 1) / kGcQ;
@@ -270,6 +316,11 @@ int mask_backward_dispatch(cudaStream_t st, int dtype, const void* coeff, const 
     mask_grad_coeff_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(proto), static_cast<const float*>(grad_out),
                                                  static_cast<float*>(grad_coeff), Q, K, Ncols, cols, q_blocks);
     if (int rc = after_launch("mask_grad_coeff_kernel")) return rc;
+  }
+  // grad_proto[b, k, n] = sum_q coeff[b, q, k] * grad_out[b, q, n] on the tensor cores (3xTF32): the forward kernel with
+  // rows = k, reduction = q (7 chunks of 32 for Q = 196) and the row operand transposed on chip
+  if (grad_proto && tc_ok) {
+    return launch_mask_tc3<float, true>(st, coeff, grad_out, grad_proto, B, K, Q, Ncols, -1);
   }
   if (grad_proto) {
     const dim3 grid(static_cast<unsigned>((Ncols + kGpTN - 1) / kGpTN), kblocks, B);

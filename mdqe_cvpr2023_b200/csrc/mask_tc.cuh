@@ -402,17 +402,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint
       ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-template <typename OT>
+// kTransA: the row operand is given as [reduction][rows] (rows contiguous) instead of [rows][reduction] -- the layout of
+// `coeff` when the kernel computes grad_proto[k, n] = sum_q coeff[q, k] * grad_out[q, n].  Its chunk then arrives as a
+// plain [32 q][QN k] box and the split warps transpose it like the column operand.
+template <typename OT, bool kTransA>
 __global__ void __launch_bounds__(kTc3Threads, 1)
 mask_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_constant__ CUtensorMap map_coeff,
-                    const __grid_constant__ CUtensorMap map_out, int Q, int KP, int QS, int QN, int n_qchunks,
+                    const __grid_constant__ CUtensorMap map_out, int Q, int n_kchunks, int QS, int QN, int n_qchunks,
                     int n_tiles_n, int n_items) {
+  // The reduction dimension is walked in chunks of 32 (one 128-byte fp32 swizzle row): n_kchunks stages per work item.
+  // TMA zero-fills rows / columns beyond the tensor, so partial chunks need no special casing.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t raw_bytes = (static_cast<uint32_t>(KP) * kTcTileN * 4u + 1023u) & ~1023u;   // proto tile as loaded: [k][128 n]
+  constexpr uint32_t raw_bytes = 32u * kTcTileN * 4u;                   // proto chunk as loaded: [32 k][128 n], plain rows
   const uint32_t a_bytes = kTcTileN * 128u;                              // K-major operand tile: 128 rows (n) x 128 B
   const uint32_t b_bytes = (static_cast<uint32_t>(QN) * 128u + 1023u) & ~1023u;
-  const uint32_t stage_bytes = raw_bytes + 2 * a_bytes + 2 * b_bytes;    // [raw][A hi][A lo][B hi][B lo]
+  const uint32_t rawb_bytes = kTransA ? ((32u * static_cast<uint32_t>(QN) * 4u + 1023u) & ~1023u) : 0u;   // [32 q][QN k] plain
+  const uint32_t stage_bytes = raw_bytes + 2 * a_bytes + 2 * b_bytes + rawb_bytes;   // [raw][A hi][A lo][B hi][B lo][raw B]
   constexpr uint32_t kOutBuf = 32u * kTcTileN * sizeof(OT);
   uint8_t* out_stage = smem + kTc3Stages * stage_bytes;
   __shared__ __align__(8) uint64_t bars[3 * kTc3Stages + 4];
@@ -453,40 +459,46 @@ mask_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_
   if (warp == 0) {
     if (lane == 0) {
       int i = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
-        const int s = i % kTc3Stages;
-        const uint32_t ph = (i / kTc3Stages) & 1;
-        int b, tile, qc;
-        decode(item, b, tile, qc);
-        mbar_wait(bar_empty(s), ph ^ 1);
-        const uint32_t dst = smem_u32(smem) + s * stage_bytes;
-        mbar_expect_tx(bar_full(s), static_cast<uint32_t>(KP) * kTcTileN * 4u + static_cast<uint32_t>(QN) * 128u);
-        tma_load_3d(dst, &map_proto, bar_full(s), tile * kTcTileN, 0, b);
-        tma_load_3d(dst + raw_bytes + 2 * a_bytes, &map_coeff, bar_full(s), 0, qc * QS, b);
-      }
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+        for (int kc = 0; kc < n_kchunks; ++kc, ++i) {
+          const int s = i % kTc3Stages;
+          const uint32_t ph = (i / kTc3Stages) & 1;
+          int b, tile, qc;
+          decode(item, b, tile, qc);
+          mbar_wait(bar_empty(s), ph ^ 1);
+          const uint32_t dst = smem_u32(smem) + s * stage_bytes;
+          mbar_expect_tx(bar_full(s), raw_bytes + static_cast<uint32_t>(QN) * 128u);
+          tma_load_3d(dst, &map_proto, bar_full(s), tile * kTcTileN, kc * 32, b);
+          if constexpr (kTransA) tma_load_3d(dst + raw_bytes + 2 * a_bytes + 2 * b_bytes, &map_coeff, bar_full(s), qc * QS, kc * 32, b);
+          else tma_load_3d(dst + raw_bytes + 2 * a_bytes, &map_coeff, bar_full(s), kc * 32, qc * QS, b);
+        }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32_m128(static_cast<uint32_t>(QN));
-      int i = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
-        const int s = i % kTc3Stages, a = i & 1;
-        const uint32_t ph = (i / kTc3Stages) & 1, aph = (i >> 1) & 1;
+      int i = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int a = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
         mbar_wait(bar_tempty(a), aph ^ 1);
-        mbar_wait(bar_ready(s), ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = smem_u32(smem) + s * stage_bytes + raw_bytes, a_lo = a_hi + a_bytes;
-        const uint32_t b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
-        const uint32_t a_sel[3] = {a_hi, a_hi, a_lo}, b_sel[3] = {b_hi, b_lo, b_hi};     // hi*hi + hi*lo + lo*hi
         uint32_t acc = 0;
-        for (int term = 0; term < 3; ++term)
-          for (int ks = 0; ks < KP / 8; ++ks) {
-            const uint64_t a_desc = umma_desc_sw128(a_sel[term] + ks * 32u, 16u, 1024u);
-            const uint64_t b_desc = umma_desc_sw128(b_sel[term] + ks * 32u, 16u, 1024u);
-            umma_tf32(tmem_base + a * 256u, a_desc, b_desc, idesc, acc);
-            acc = 1;
-          }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_empty(s)) : "memory");
+        for (int kc = 0; kc < n_kchunks; ++kc, ++i) {
+          const int s = i % kTc3Stages;
+          const uint32_t ph = (i / kTc3Stages) & 1;
+          mbar_wait(bar_ready(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = smem_u32(smem) + s * stage_bytes + raw_bytes, a_lo = a_hi + a_bytes;
+          const uint32_t b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
+          const uint32_t a_sel[3] = {a_hi, a_hi, a_lo}, b_sel[3] = {b_hi, b_lo, b_hi};     // hi*hi + hi*lo + lo*hi
+          for (int term = 0; term < 3; ++term)
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t a_desc = umma_desc_sw128(a_sel[term] + ks * 32u, 16u, 1024u);
+              const uint64_t b_desc = umma_desc_sw128(b_sel[term] + ks * 32u, 16u, 1024u);
+              umma_tf32(tmem_base + a * 256u, a_desc, b_desc, idesc, acc);
+              acc = 1;
+            }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_empty(s)) : "memory");
+        }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_tfull(a)) : "memory");
       }
     }
@@ -494,7 +506,8 @@ mask_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_
     // ---- split warps: hi in place, lo into the twin tile (same swizzled position: the op is element-wise)
     const int t = threadIdx.x - (2 + kTc2EpiWarps) * 32;                 // 0 .. 127
     int i = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+     for (int kc = 0; kc < n_kchunks; ++kc, ++i) {
       const int s = i % kTc3Stages;
       const uint32_t ph = (i / kTc3Stages) & 1;
       mbar_wait(bar_full(s), ph);
@@ -514,27 +527,43 @@ mask_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_
           pv[e] = hi;
         }
       };
-      // proto: transpose [k][n] -> K-major rows of n, split; thread <-> column n (conflict-free both ways).  k rows
-      // beyond KP (up to 32) are zero so that the unused half of a K step contributes nothing.
+      // proto: transpose [k][n] -> K-major rows of n, split; thread <-> column n (conflict-free both ways)
       {
         const int n = t;                                                // 128 split threads <-> 128 columns
         const uint32_t rowoff = static_cast<uint32_t>(n) * 128u;
 #pragma unroll
         for (int kq = 0; kq < 8; ++kq) {
-          uint4 v = make_uint4(0u, 0u, 0u, 0u), lo;
-          if (kq * 4 < KP) {
-            v.x = __float_as_uint(raw[(kq * 4 + 0) * kTcTileN + n]);
-            v.y = __float_as_uint(raw[(kq * 4 + 1) * kTcTileN + n]);
-            v.z = __float_as_uint(raw[(kq * 4 + 2) * kTcTileN + n]);
-            v.w = __float_as_uint(raw[(kq * 4 + 3) * kTcTileN + n]);
-          }
+          uint4 v, lo;                                        // rows beyond the tensor were zero-filled by TMA
+          v.x = __float_as_uint(raw[(kq * 4 + 0) * kTcTileN + n]);
+          v.y = __float_as_uint(raw[(kq * 4 + 1) * kTcTileN + n]);
+          v.z = __float_as_uint(raw[(kq * 4 + 2) * kTcTileN + n]);
+          v.w = __float_as_uint(raw[(kq * 4 + 3) * kTcTileN + n]);
           split(v, lo);
           const uint32_t off = rowoff + static_cast<uint32_t>((kq ^ (n & 7)) * 16);
           *reinterpret_cast<uint4*>(a_hi + off) = v;
           *reinterpret_cast<uint4*>(a_lo + off) = lo;
         }
       }
-      for (uint32_t k = t; k < static_cast<uint32_t>(QN) * 8u; k += kTc3SplitWarps * 32) { uint4 v = b_hi[k], lo; split(v, lo); b_hi[k] = v; b_lo[k] = lo; }
+      if constexpr (kTransA) {
+        // row operand: [32 q][QN k] plain -> K-major rows k of 32 q, swizzled, split
+        const float* rawb = reinterpret_cast<const float*>(st + raw_bytes + 2 * a_bytes + 2 * b_bytes);
+        uint8_t* bh = reinterpret_cast<uint8_t*>(b_hi);
+        uint8_t* bl = reinterpret_cast<uint8_t*>(b_lo);
+        for (int task = t; task < QN * 8; task += kTc3SplitWarps * 32) {
+          const int row = task % QN, qq = task / QN;                     // lanes walk the rows (k): conflict-free reads
+          uint4 v, lo;
+          v.x = __float_as_uint(rawb[(qq * 4 + 0) * QN + row]);
+          v.y = __float_as_uint(rawb[(qq * 4 + 1) * QN + row]);
+          v.z = __float_as_uint(rawb[(qq * 4 + 2) * QN + row]);
+          v.w = __float_as_uint(rawb[(qq * 4 + 3) * QN + row]);
+          split(v, lo);
+          const uint32_t off = static_cast<uint32_t>(row) * 128u + static_cast<uint32_t>((qq ^ (row & 7)) * 16);
+          *reinterpret_cast<uint4*>(bh + off) = v;
+          *reinterpret_cast<uint4*>(bl + off) = lo;
+        }
+      } else {
+        for (uint32_t k = t; k < static_cast<uint32_t>(QN) * 8u; k += kTc3SplitWarps * 32) { uint4 v = b_hi[k], lo; split(v, lo); b_hi[k] = v; b_lo[k] = lo; }
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ready(s));
@@ -580,11 +609,12 @@ mask_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
-inline size_t mask_tc3_smem_bytes(int KP, int QN, size_t out_elem) {
-  const size_t raw_bytes = (static_cast<size_t>(KP) * kTcTileN * 4 + 1023) & ~size_t(1023);
+inline size_t mask_tc3_smem_bytes(int QN, size_t out_elem, bool trans_a) {
+  const size_t raw_bytes = static_cast<size_t>(32) * kTcTileN * 4;
   const size_t a_bytes = static_cast<size_t>(kTcTileN) * 128;
   const size_t b_bytes = (static_cast<size_t>(QN) * 128 + 1023) & ~size_t(1023);
-  return 1024 + kTc3Stages * (raw_bytes + 2 * a_bytes + 2 * b_bytes) + 4 * 32 * kTcTileN * out_elem;
+  const size_t rawb = trans_a ? ((static_cast<size_t>(32) * QN * 4 + 1023) & ~size_t(1023)) : 0;
+  return 1024 + kTc3Stages * (raw_bytes + 2 * a_bytes + 2 * b_bytes + rawb) + 4 * 32 * kTcTileN * out_elem;
 }
 
 inline size_t mask_tc2_smem_bytes(int KP, int QN, size_t out_elem) {

@@ -79,7 +79,7 @@ static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
 
 ProfScope::ProfScope(cudaStream_t st, int kind, int64_t units) : st_(st), kind_(kind), units_(units) {
-  if (!g_opt.profile.load()) return;
+  if (kind < 0 || !g_opt.profile.load()) return;      // kind < 0: the caller already times this launch
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
   if (cudaEventCreate(&a_) != cudaSuccess || cudaEventCreate(&b_) != cudaSuccess) { a_ = b_ = nullptr; return; }
