@@ -63,7 +63,8 @@ const char* msda_last_error(void);
 
 /* Tuning knobs (kernel variant selection used by bench.py / tests); unknown keys fail.
  * Keys: "fwd_variant", "bwd_variant", "chunk_pairs", "mask_variant", "profile", "mask_debug", "host_async",
- * "tile_rows", "tile_q". */
+ * "tile_rows", "tile_q".  mask_variant: 0 auto (tensor cores when eligible), 1 SIMT, 2 require tensor cores,
+ * 3 / 5 earlier tensor-core kernels and 4 the first SIMT backward (kept for A/B timing). */
 int msda_set_option(const char* key, int value);
 int msda_get_option(const char* key, int* value);
 
@@ -131,8 +132,8 @@ int msda_fused_backward(void* stream, int dtype,
 
 /* Mask contraction: out[b,q,n] = sum_k coeff[b,q,k] * proto[b,k,n], n over the flattened (t,h,w)
  * plane (Ncols = T*H*W).  coeff [B,Q,K], proto [B,K,Ncols], out [B,Q,Ncols].
- *   in_dtype  MSDA_F32 (inputs rounded to bf16 hi+lo pairs on chip: 3 tensor-core passes, fp32
- *             accumulate, parity with the fp32 einsum to ~1e-5) or MSDA_BF16 (one pass)
+ *   in_dtype  MSDA_F32 (3xTF32: operands split on chip into hi + lo TF32 parts, hi*hi + hi*lo + lo*hi
+ *             accumulated in fp32, parity with the fp32 einsum to ~1e-6) or MSDA_BF16 (one pass)
  *   out_dtype MSDA_F32 or MSDA_BF16
  * Runs on the 5th-gen tensor cores (tcgen05, accumulators in TMEM). */
 int mask_logits_forward(void* stream, int in_dtype, int out_dtype,
@@ -140,7 +141,10 @@ int mask_logits_forward(void* stream, int in_dtype, int out_dtype,
                         int B, int Q, int K, int64_t Ncols, void* out);
 
 /* grad_coeff[b,q,k] = sum_n grad_out[b,q,n] proto[b,k,n];  grad_proto[b,k,n] = sum_q coeff[b,q,k] grad_out[b,q,n].
- * Either output may be NULL to skip it.  All tensors use `dtype` (MSDA_F32 or MSDA_BF16). */
+ * Either output may be NULL to skip it.  `dtype` must be MSDA_F32 (the reference trains the mask head in fp32).
+ * Both gradients run as 3xTF32 on the tensor cores when K % 4 == 0, K <= 128, Ncols % 4 == 0 and the pointers are
+ * 16-byte aligned (otherwise register-tiled SIMT kernels); grad_coeff is accumulated with atomics, so its last bits
+ * depend on the schedule, like the reference's atomicAdd-based op gradients. */
 int mask_logits_backward(void* stream, int dtype,
                          const void* coeff, const void* proto, const void* grad_out,
                          int B, int Q, int K, int64_t Ncols,

@@ -6,6 +6,7 @@
 
 #include "mask_simt.cuh"
 #include "mask_tc.cuh"
+#include "mask_tc4.cuh"
 #include "mask_tc_bwd.cuh"
 #include "msda_internal.h"
 
@@ -37,7 +38,8 @@ static int make_map_in(CUtensorMap* map, const void* base, bool fp32, uint64_t d
   const cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / es), box1, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = enc(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         option("mask_debug") == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
   return 0;
@@ -190,6 +192,73 @@ static int launch_mask_tc3(cudaStream_t st, const void* coeff, const void* proto
   return after_launch("mask_fwd_tc3_kernel");
 }
 
+// fp32 tensor [d2, d1, d0], box {32, 32, 1}, "128B swizzle with 32B atoms": the MN-major tf32 operand layout (UMMA layout type 1)
+static int make_map_mn_f32(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
+  if (!enc) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
+  const cuuint32_t box[3] = {32, 32, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                         option("mask_debug") == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled(MN-major fp32) failed (CUresult %d)", static_cast<int>(r));
+  return 0;
+}
+
+// out[b, r, n] = sum_k A[b, r, k] * P[b, k, n]  (kTransB: A is given as [b, k, r]).  Q = rows r, K = reduction length.
+template <typename OT, bool kTransB>
+static int launch_mask_tc4(cudaStream_t st, const void* coeff, const void* proto, void* out, int B, int Q, int K,
+                           int64_t Ncols, int prof_kind = MSDA_PROF_MASK_FWD) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n_kchunks = (K + 31) / 32;
+  const int n_tiles_n = static_cast<int>((Ncols + kTcTileN - 1) / kTcTileN);
+  const int64_t tiles = (int64_t)B * n_tiles_n;
+  int n_qchunks = (Q + 127) / 128;
+  while (n_qchunks < 4 && tiles * n_qchunks < 6LL * sms && (Q / (n_qchunks + 1)) / 32 * 32 >= 32) ++n_qchunks;
+  int QS = 0, QN = 0;
+  for (;; ++n_qchunks) {
+    QS = (n_qchunks == 1) ? ((Q + 31) / 32 * 32) : (Q / n_qchunks) / 32 * 32;
+    if (QS < 32) break;
+    const int last_rows = Q - (n_qchunks - 1) * QS;
+    QN = ((QS > last_rows ? QS : last_rows) + 15) / 16 * 16;
+    if (QN <= 128) break;
+  }
+  if (QN > 128 || QS < 32) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits: cannot chunk %d rows for the tensor-core kernel", Q);
+  const int64_t n_items = tiles * n_qchunks;
+  if (n_items >= (int64_t(1) << 31)) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits: too many tiles");
+  CUtensorMap map_plane, map_rows, map_out;
+  if (int rc = make_map_mn_f32(&map_plane, proto, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B)) return rc;
+  if (kTransB) {
+    if (int rc = make_map_mn_f32(&map_rows, coeff, (uint64_t)Q, (uint64_t)K, (uint64_t)B)) return rc;
+  } else {
+    if (int rc = make_map_in(&map_rows, coeff, true, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QN)) return rc;
+  }
+  if (int rc = make_map_out(&map_out, out, sizeof(OT) == 2, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B)) return rc;
+  const size_t stage = mask_tc4_stage_bytes(QN, kTransB);
+  const size_t out_bytes = 4 * 32 * kTcTileN * sizeof(OT);
+  int n_stages = static_cast<int>((224 * 1024 - out_bytes) / stage);
+  if (n_stages > kTc4MaxStages) n_stages = kTc4MaxStages;
+  if (n_stages > n_kchunks + 2) n_stages = n_kchunks + 2;
+  if (n_stages < 2) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits: tile does not fit shared memory");
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(mask_fwd_tc4_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaFuncSetAttribute(mask_fwd_tc4_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaFuncSetAttribute(mask_fwd_tc4_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaFuncSetAttribute(mask_fwd_tc4_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  });
+  const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);
+  ProfScope prof(st, prof_kind, (int64_t)B * Q * Ncols);
+  mask_fwd_tc4_kernel<OT, kTransB><<<grid, kTc4Threads, 1024 + n_stages * stage + out_bytes, st>>>(
+      map_plane, map_rows, map_out, Q, n_kchunks, QS, QN, n_qchunks, n_tiles_n, static_cast<int>(n_items), n_stages,
+      option("mask_debug") != 2);
+  return after_launch("mask_fwd_tc4_kernel");
+}
+
 template <typename OT>
 static int launch_mask_tc(cudaStream_t st, const void* coeff, const void* proto, void* out, int B, int Q, int K,
                           int64_t Ncols) {
@@ -238,8 +307,12 @@ int mask_forward_dispatch(cudaStream_t st, int in_dtype, int out_dtype, const vo
     return launch_mask_tc2<__nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
   }
   if (variant != 1 && mask_tc3_eligible(in_dtype, coeff, proto, Q, K, Ncols)) {
-    if (out_dtype == MSDA_F32) return launch_mask_tc3<float, false>(st, coeff, proto, out, B, Q, K, Ncols);
-    return launch_mask_tc3<__nv_bfloat16, false>(st, coeff, proto, out, B, Q, K, Ncols);
+    if (variant == 5) {                                // 5 = third-generation kernel (on-chip transposition), kept for A/B timing
+      if (out_dtype == MSDA_F32) return launch_mask_tc3<float, false>(st, coeff, proto, out, B, Q, K, Ncols);
+      return launch_mask_tc3<__nv_bfloat16, false>(st, coeff, proto, out, B, Q, K, Ncols);
+    }
+    if (out_dtype == MSDA_F32) return launch_mask_tc4<float, false>(st, coeff, proto, out, B, Q, K, Ncols);
+    return launch_mask_tc4<__nv_bfloat16, false>(st, coeff, proto, out, B, Q, K, Ncols);
   }
   if (in_dtype == MSDA_F32 && out_dtype == MSDA_F32) return launch_mask_simt<float, float>(st, coeff, proto, out, B, Q, K, Ncols);
   if (in_dtype == MSDA_F32 && out_dtype == MSDA_BF16) return launch_mask_simt<float, __nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
@@ -274,8 +347,16 @@ static int launch_mask_grad_coeff_tc(cudaStream_t st, const void* proto, const v
     cudaFuncSetAttribute(mask_grad_coeff_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
   });
   const dim3 grid(static_cast<unsigned>(slices), static_cast<unsigned>(n_qblocks), static_cast<unsigned>(B));
+  long long* dbg = nullptr;
+  if (option("mask_debug") == 1) {
+    static long long* d_dbg = nullptr;
+    if (!d_dbg) cudaMalloc(&d_dbg, 5 * 16 * sizeof(long long));
+    cudaMemsetAsync(d_dbg, 0, 5 * 16 * sizeof(long long), st);
+    dbg = d_dbg;
+    g_mask_dbg = d_dbg;
+  }
   mask_grad_coeff_tc_kernel<<<grid, kGcTcThreads, 1024 + n_stages * stage, st>>>(map_go, map_proto, static_cast<float*>(grad_coeff), Q, K, KP, MH,
-                                                                                n_stages, n_chunks, cps);
+                                                                                n_stages, n_chunks, cps, option("mask_debug") != 2, dbg);
   return after_launch("mask_grad_coeff_tc_kernel");
 }
 
@@ -319,6 +400,9 @@ int mask_backward_dispatch(cudaStream_t st, int dtype, const void* coeff, const 
   }
   // grad_proto[b, k, n] = sum_q coeff[b, q, k] * grad_out[b, q, n] on the tensor cores (3xTF32): the forward kernel with
   // rows = k, reduction = q (7 chunks of 32 for Q = 196) and the row operand transposed on chip
+  if (grad_proto && tc_ok && option("mask_variant") != 5) {
+    return launch_mask_tc4<float, true>(st, coeff, grad_out, grad_proto, B, K, Q, Ncols, -1);
+  }
   if (grad_proto && tc_ok) {
     return launch_mask_tc3<float, true>(st, coeff, grad_out, grad_proto, B, K, Q, Ncols, -1);
   }

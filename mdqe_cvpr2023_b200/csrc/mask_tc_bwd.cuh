@@ -28,7 +28,7 @@ constexpr uint32_t kGcTcHalfBytes = 128u * 128u;                 // 128 rows x 3
 __global__ void __launch_bounds__(kGcTcThreads, 1)
 mask_grad_coeff_tc_kernel(const __grid_constant__ CUtensorMap map_go, const __grid_constant__ CUtensorMap map_proto,
                           float* __restrict__ grad_coeff, int Q, int K, int KP, int MH, int n_stages, int n_chunks,
-                          int chunks_per_slice) {
+                          int chunks_per_slice, int keep_raw, long long* __restrict__ dbg) {
   const int c_begin = blockIdx.x * chunks_per_slice;
   const int c_end = min(n_chunks, c_begin + chunks_per_slice);
   if (c_begin >= c_end) return;                                  // uniform per CTA, before any barrier / TMEM allocation
@@ -72,6 +72,7 @@ mask_grad_coeff_tc_kernel(const __grid_constant__ CUtensorMap map_go, const __gr
         const int s = i % n_stages;
         const uint32_t ph = (i / n_stages) & 1;
         mbar_wait(bar_empty(s), ph ^ 1);
+        if (dbg && blockIdx.x == 0 && i < 16) dbg[0 * 16 + i] = clock64();            // TMA issued
         const uint32_t dst = smem_u32(smem) + s * stage_bytes;
         mbar_expect_tx(bar_full(s), a_bytes + static_cast<uint32_t>(KP) * 128u);
         for (int h = 0; h < MH; ++h) tma_load_3d(dst + h * kGcTcHalfBytes, &map_go, bar_full(s), c * 32, q_base + h * 128, b);
@@ -87,6 +88,7 @@ mask_grad_coeff_tc_kernel(const __grid_constant__ CUtensorMap map_go, const __gr
         const int s = i % n_stages;
         const uint32_t ph = (i / n_stages) & 1;
         mbar_wait(bar_ready(s), ph);
+        if (dbg && blockIdx.x == 0 && i < 16) dbg[3 * 16 + i] = clock64();            // split done, MMAs issue
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_hi = smem_u32(smem) + s * stage_bytes, a_lo = a_hi + a_bytes;
         const uint32_t b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
@@ -114,6 +116,7 @@ mask_grad_coeff_tc_kernel(const __grid_constant__ CUtensorMap map_go, const __gr
       const int s = i % n_stages;
       const uint32_t ph = (i / n_stages) & 1;
       mbar_wait(bar_full(s), ph);
+      if (dbg && blockIdx.x == 0 && t == 0 && i < 16) dbg[1 * 16 + i] = clock64();    // operands landed
       uint8_t* st = smem + s * stage_bytes;
       uint4* a_hi = reinterpret_cast<uint4*>(st);
       uint4* a_lo = reinterpret_cast<uint4*>(st + a_bytes);
@@ -129,12 +132,15 @@ mask_grad_coeff_tc_kernel(const __grid_constant__ CUtensorMap map_go, const __gr
           pv[e] = hi;
         }
       };
+      // The MMA reads only the TF32 bits of an fp32 operand (truncation: checked on the device, tools/mask_keepraw_check.py), so the
+      // tile as loaded already is the "hi" operand; only lo = a - trunc(a) has to be produced.
 #pragma unroll 4
-      for (uint32_t k = t; k < a_vecs; k += kGcTcSplitWarps * 32) { uint4 v = a_hi[k], lo; split(v, lo); a_hi[k] = v; a_lo[k] = lo; }
-      for (uint32_t k = t; k < b_vecs; k += kGcTcSplitWarps * 32) { uint4 v = b_hi[k], lo; split(v, lo); b_hi[k] = v; b_lo[k] = lo; }
+      for (uint32_t k = t; k < a_vecs; k += kGcTcSplitWarps * 32) { uint4 v = a_hi[k], lo; split(v, lo); if (!keep_raw) a_hi[k] = v; a_lo[k] = lo; }
+      for (uint32_t k = t; k < b_vecs; k += kGcTcSplitWarps * 32) { uint4 v = b_hi[k], lo; split(v, lo); if (!keep_raw) b_hi[k] = v; b_lo[k] = lo; }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ready(s));
+      if (dbg && blockIdx.x == 0 && t == 0 && i < 16) dbg[2 * 16 + i] = clock64();    // this warp's split done
     }
     if (warp < 6) {
       // ---- drain: warps 2..5 cover the four TMEM lane quarters (quarter = warp % 4)

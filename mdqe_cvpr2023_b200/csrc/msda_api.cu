@@ -43,7 +43,7 @@ struct Options {
   std::atomic<int> fwd_variant{0};    // 0 = auto (fast2 / fast when eligible), 1 = force generic, 2 = first-generation fast, 3 = fast2 with batched gathers (80 registers)
   std::atomic<int> bwd_variant{0};    // 0 = auto (fast2 / fast), 1 = generic, 2 = first-generation fast, 5 = tiled fixed-point kernel (experiment, slower)
   std::atomic<int> chunk_pairs{0};    // 0 = auto
-  std::atomic<int> mask_variant{0};   // 0 = auto (tcgen05 when eligible), 1 = SIMT fp32, 2 = force tcgen05
+  std::atomic<int> mask_variant{0};   // 0 = auto (tcgen05 when eligible), 1 = SIMT fp32, 2 = force tcgen05, 3/5 = earlier tensor-core kernels (A/B), 4 = first fused SIMT backward
   std::atomic<int> mask_debug{0};     // 1 = the tcgen05 mask kernel records per-item clock stamps of CTA 0
   std::atomic<int> tile_rows{320};    // shared-memory budget (value rows) of the tiled backward (bwd_variant 5 only)
   std::atomic<int> tile_q{64};        // queries per CTA of the tiled backward

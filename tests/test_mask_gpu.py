@@ -59,3 +59,27 @@ def test_mask_unbatched_form_and_empty():
     assert nerr(mask_logits(coeff, proto), torch.einsum("qm,mthw->qthw", coeff, proto)) < 2e-5   # mdqe/mdqe.py:384
     out = ops.mask_logits_forward(torch.zeros(1, 0, 32, device="cuda"), torch.zeros(1, 32, 1, 4, 4, device="cuda"))
     assert tuple(out.shape) == (1, 0, 1, 4, 4)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 5])
+@pytest.mark.parametrize("B,Q,K,N", [(1, 196, 32, 4 * 24 * 40), (2, 100, 24, 1000), (1, 300, 32, 2048 + 36), (2, 37, 8, 516),
+                                     (1, 64, 40, 512), (1, 196, 128, 4096), (1, 520, 64, 1024), (1, 9, 32, 30)])
+def test_mask_backward_sweep(B, Q, K, N, variant):
+    """grad_coeff / grad_proto of the contraction against fp64 einsum: tensor-core kernels (variant 0: MN-major operands straight
+    from TMA + TMEM-resident grad_coeff; 5: third generation with on-chip transposition) and the SIMT kernels (1).  Covers several
+    batch items, K above one 32-wide reduction chunk, more than 256 query rows (two row blocks), column counts that are not a
+    multiple of the 32-column chunk / 128-column tile, and N % 4 != 0 (tensor-core path ineligible -> SIMT)."""
+    from mdqe_cvpr2023_b200 import _lib, ops
+    _lib.set_option("mask_variant", variant)
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + Q + K)
+    coeff = torch.tanh(torch.randn(B, Q, K, device="cuda", generator=g))
+    proto = torch.randn(B, K, 1, 1, N, device="cuda", generator=g)
+    go = torch.randn(B, Q, 1, 1, N, device="cuda", generator=g)
+    gc, gp = ops.mask_logits_backward(coeff, proto, go)
+    want_gp = torch.einsum("bqm,bqthw->bmthw", coeff.double(), go.double())
+    want_gc = torch.einsum("bmthw,bqthw->bqm", proto.double(), go.double())
+    assert nerr(gc, want_gc) < 2e-5 and nerr(gp, want_gp) < 2e-5
+    gc_only, none = ops.mask_logits_backward(coeff, proto, go, need_proto=False)
+    assert none is None and nerr(gc_only, want_gc) < 2e-5
+    none, gp_only = ops.mask_logits_backward(coeff, proto, go, need_coeff=False)
+    assert none is None and nerr(gp_only, want_gp) < 2e-5

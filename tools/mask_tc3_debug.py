@@ -38,14 +38,19 @@ for (B, Q, K, N) in [(1, 64, 40, 512), (2, 100, 64, 4096), (1, 196, 128, 8192), 
     _lib.set_option("mask_variant", 1)
     gc1, gp1 = ops.mask_logits_backward(coeff, proto, go)
     torch.cuda.synchronize()
+    _lib.set_option("mask_variant", 5)
+    out5 = ops.mask_logits_forward(coeff, proto)
+    gc5, gp5 = ops.mask_logits_backward(coeff, proto, go)
+    torch.cuda.synchronize()
     _lib.set_option("mask_variant", 0)
-    print(f"B{B} Q{Q} K{K} N{N}: fwd {nerr(out, want):.3e}  grad_proto tc {nerr(gp, want_gp):.3e} simt {nerr(gp1, want_gp):.3e}  grad_coeff {nerr(gc, want_gc):.3e}")
+    print(f"B{B} Q{Q} K{K} N{N}: fwd tc4 {nerr(out, want):.3e} tc3 {nerr(out5, want):.3e} | grad_proto tc4 {nerr(gp, want_gp):.3e} tc3 {nerr(gp5, want_gp):.3e} "
+          f"simt {nerr(gp1, want_gp):.3e} | grad_coeff {nerr(gc, want_gc):.3e}")
 
 # timing of the backward on the bench shape
 import time
 B, Q, K, N = 1, 196, 32, 7 * 96 * 160
 coeff = torch.tanh(torch.randn(B, Q, K, device="cuda")); proto = torch.randn(B, K, 7, 96, 160, device="cuda"); go = torch.randn(B, Q, 7, 96, 160, device="cuda")
-for variant in (1, 0):
+for variant in (1, 5, 0):
     _lib.set_option("mask_variant", variant)
     for _ in range(3): ops.mask_logits_backward(coeff, proto, go)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
