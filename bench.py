@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--layers", type=int, default=N_LAYERS, help="debug: fewer layers (the result is then not a valid bench value)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-legacy", action="store_true", help="time the first-generation host path (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     return ap.parse_args()
@@ -209,10 +210,15 @@ class DeviceStep:
 
 
 class HostStep:
-    """Same step through the *_host C-ABI entries: pinned host buffers in, pinned host buffers out."""
+    """The same step through the host-buffer C-ABI: pinned host buffers in, pinned host buffers out.  Forward calls use the
+    *_host_saved entries (device copies of the inputs stay alive like autograd's saved tensors; the backward uploads only
+    grad_out), the clip-level attention goes through the grouped form (one value upload instead of four), and the mask
+    head runs forward and backward -- exactly the launches of the device step.  `legacy=True` is the first-generation path
+    (every call re-uploads its inputs, temporal calls per level, no mask backward) kept for A/B timing."""
 
-    def __init__(self, torch, lib, libmod, calls, mask, device_index, dtype):
-        self.lib, self.dev = lib, device_index
+    def __init__(self, torch, lib, libmod, calls, mask, device_index, dtype, legacy=False):
+        import ctypes
+        self.lib, self.dev, self.legacy, self.ctypes = lib, device_index, legacy, ctypes
         vt = torch.bfloat16 if dtype == "bf16" else torch.float32
         code = libmod.MSDA_BF16 if dtype == "bf16" else libmod.MSDA_F32
         self.keep, self.fwd, self.bwd = [], [], []
@@ -234,19 +240,28 @@ class HostStep:
         gl_h = torch.empty(big["loc"].numel(), dtype=vt).pin_memory()
         ga_h = torch.empty(big["aw"].numel(), dtype=vt).pin_memory()
         self.keep += [out_h, gv_h, gl_h, ga_h]
+        skip = "dec_temporal_grouped" if legacy else "dec_temporal"
         for c in calls:
-            if c["kind"] == "dec_temporal_grouped":
-                continue                                      # the host-buffer ABI has the per-level entries only
-            dims = call_dims(c)
+            if c["kind"] == skip:
+                continue
+            N, S, M, D, L, Lq, P = call_dims(c)
             v, loc, aw, go = pin(c["value"]), pin(c["loc"]), pin(c["aw"]), pin(c["go"])
             sh, ls = pin(c["shapes"], False), pin(c["lsi"], False)
             self.keep += [v, loc, aw, go, sh, ls]
-            self.fwd.append((device_index, code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr())
-                            + dims + (out_h.data_ptr(),))
-            self.bwd.append((device_index, code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr(),
-                             go.data_ptr()) + dims + (gv_h.data_ptr(), gl_h.data_ptr(), ga_h.data_ptr()))
             small = nb(sh) + nb(ls)
-            self.h2d += 2 * (nb(v) + nb(loc) + nb(aw) + small) + nb(go)
+            if legacy:
+                dims = (N, S, M, D, L, Lq, P)
+                self.fwd.append((device_index, code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr())
+                                + dims + (out_h.data_ptr(),))
+                self.bwd.append((device_index, code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr(),
+                                 go.data_ptr()) + dims + (gv_h.data_ptr(), gl_h.data_ptr(), ga_h.data_ptr()))
+                self.h2d += 2 * (nb(v) + nb(loc) + nb(aw) + small) + nb(go)
+            else:
+                G, scale = (4, 0.25) if c["kind"] == "dec_temporal_grouped" else (1, 1.0)
+                self.fwd.append((device_index, code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr(),
+                                 N, S, M, D, G, L, Lq, P, scale, out_h.data_ptr()))
+                self.bwd.append((go.data_ptr(), gv_h.data_ptr(), gl_h.data_ptr(), ga_h.data_ptr()))
+                self.h2d += nb(v) + nb(loc) + nb(aw) + small + nb(go)
             self.d2h += nb(go) + nb(v) + nb(loc) + nb(aw)
         mc, mp = pin(mask["coeff"]), pin(mask["proto"])
         B, Q, K = mc.shape
@@ -256,14 +271,38 @@ class HostStep:
         self.mask_fwd = (device_index, code, code, mc.data_ptr(), mp.data_ptr(), B, Q, K, ncols, mo.data_ptr())
         self.h2d += nb(mc) + nb(mp)
         self.d2h += nb(mo)
+        self.mask_bwd = None
+        if not legacy and dtype != "bf16":                    # the mask backward is fp32-only (the reference's training precision)
+            mg = pin(mask["go"])
+            gc_h, gp_h = torch.empty_like(mc).pin_memory(), torch.empty_like(mp).pin_memory()
+            self.keep += [mg, gc_h, gp_h]
+            self.mask_bwd = (mg.data_ptr(), gc_h.data_ptr(), gp_h.data_ptr())
+            self.h2d += nb(mg)
+            self.d2h += nb(gc_h) + nb(gp_h)
 
     def run(self):
         lib, rc = self.lib, 0
-        for a in self.fwd:
-            rc |= lib.msda_forward_host(*a)
-        rc |= lib.mask_logits_forward_host(*self.mask_fwd)
-        for a in reversed(self.bwd):
-            rc |= lib.msda_backward_host(*a)
+        if self.legacy:
+            for a in self.fwd:
+                rc |= lib.msda_forward_host(*a)
+            rc |= lib.mask_logits_forward_host(*self.mask_fwd)
+            for a in reversed(self.bwd):
+                rc |= lib.msda_backward_host(*a)
+        else:
+            c_i64 = self.ctypes.c_int64
+            handles = []
+            for a in self.fwd:
+                h = c_i64(0)
+                rc |= lib.msda_forward_host_saved(*a, self.ctypes.byref(h))
+                handles.append(h.value)
+            if self.mask_bwd is not None:
+                h = c_i64(0)
+                rc |= lib.mask_logits_forward_host_saved(*self.mask_fwd, self.ctypes.byref(h))
+                rc |= lib.mask_logits_backward_host_saved(h.value, *self.mask_bwd)
+            else:
+                rc |= lib.mask_logits_forward_host(*self.mask_fwd)
+            for h, a in zip(reversed(handles), reversed(self.bwd)):
+                rc |= lib.msda_backward_host_saved(h, *a)
         if rc:
             from mdqe_cvpr2023_b200 import _lib
             raise RuntimeError("C-ABI host call failed: " + _lib.last_error())
@@ -554,7 +593,7 @@ def main():
     # ---- end to end through the host-buffer C ABI (H2D + kernels + D2H every call), wall clock
     e2e = None
     if not args.no_e2e:
-        host = HostStep(torch, lib, libmod, calls, mask, local_rank, args.dtype)
+        host = HostStep(torch, lib, libmod, calls, mask, local_rank, args.dtype, legacy=args.e2e_legacy)
         libmod.set_option("host_async", 1)           # calls enqueue on the library's H2D / compute / D2H streams ...
         host.run()                                   # warm-up: arena allocation, page faults
         libmod.check(lib.msda_host_sync(), "msda_host_sync")
@@ -573,7 +612,8 @@ def main():
             dt = float(t.item())
         e2e = {"value": world * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": host.h2d, "d2h_bytes_per_step": host.d2h,
                "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3, "timing": "wall clock; *_host C-ABI calls in host_async mode (3-stream pipeline), msda_host_sync() at the end of every step",
-               "note": "mask backward is not part of the host-buffer step"}
+               "note": ("first-generation host path: every call re-uploads its inputs, per-level temporal calls, no mask backward" if args.e2e_legacy else
+                        "same launches as the device step; forward inputs stay on the device for the backward (*_host_saved entries)")}
         lib.msda_host_arena_release()
 
     # ---- CPU baseline (rank 0, single-GPU runs only): the reference's CPU path restated in torch

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 1
+#define MSDA_B200_ABI_VERSION 2
 
 typedef enum {
   MSDA_OK = 0,
@@ -170,6 +170,25 @@ int mask_logits_forward_host(int device, int in_dtype, int out_dtype,
  * (upload, kernels and download of consecutive calls overlap on three streams; PCIe runs full duplex); host output
  * buffers are valid, and host input buffers may be reused, only after msda_host_sync().  Returns the first error. */
 int msda_host_sync(void);
+
+/* "Saved" host entries: the host-buffer counterpart of autograd's save_for_backward (ms_deform_attn_func.py:28-29 saves
+ * value, shapes, level_start_index, loc and aw on the device between forward and backward).  The forward keeps the device
+ * copies of its inputs in a pooled block and returns a handle in *saved; the backward takes the handle, uploads only
+ * grad_out and consumes the handle.  A forward whose backward never runs (inference) must call msda_host_saved_release().
+ * G / scale as in msda_forward_grouped (G = 1, scale = 1: the plain operator; shapes [G,L,2], level_start [G,L]).
+ * Halves the host->device traffic of a training step and lets the clip-level attention go up as ONE value tensor. */
+int msda_forward_host_saved(int device, int dtype,
+                            const void* value, const int64_t* shapes, const int64_t* level_start,
+                            const void* loc, const void* aw,
+                            int N, int S, int M, int D, int G, int L, int Lq, int P, float scale,
+                            void* out, int64_t* saved);
+int msda_backward_host_saved(int64_t saved, const void* grad_out,
+                             void* grad_value, void* grad_loc, void* grad_aw);
+int mask_logits_forward_host_saved(int device, int in_dtype, int out_dtype,
+                                   const void* coeff, const void* proto,
+                                   int B, int Q, int K, int64_t Ncols, void* out, int64_t* saved);
+int mask_logits_backward_host_saved(int64_t saved, const void* grad_out, void* grad_coeff, void* grad_proto);
+int msda_host_saved_release(int64_t saved);
 /* Release the device arena used by the *_host entries. */
 int msda_host_arena_release(void);
 

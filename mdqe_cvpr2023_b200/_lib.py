@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libmsda_b200.so")
 
 MSDA_F32, MSDA_BF16, MSDA_F64, MSDA_BF16_LOC32 = 0, 1, 2, 3
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _c_int, _c_vp, _c_i64, _c_sz = ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t
 _SEVEN = [_c_int] * 7
@@ -40,6 +40,13 @@ PROTOTYPES = {
                            + [_c_vp, _c_vp, _c_vp]),
     "mask_logits_forward_host": (_c_int, [_c_int, _c_int, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_vp]),
     "msda_host_sync": (_c_int, []),
+    "msda_forward_host_saved": (_c_int, [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + [_c_int] * 8
+                                + [ctypes.c_float, _c_vp, ctypes.POINTER(_c_i64)]),
+    "msda_backward_host_saved": (_c_int, [_c_i64, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "mask_logits_forward_host_saved": (_c_int, [_c_int, _c_int, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_vp,
+                                                ctypes.POINTER(_c_i64)]),
+    "mask_logits_backward_host_saved": (_c_int, [_c_i64, _c_vp, _c_vp, _c_vp]),
+    "msda_host_saved_release": (_c_int, [_c_i64]),
     "msda_host_arena_release": (_c_int, []),
     "msda_profile_read": (_c_int, [_c_int, _c_i64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_c_i64)]),
     "msda_debug_read": (_c_int, [ctypes.POINTER(ctypes.c_longlong)]),

@@ -704,6 +704,229 @@ int mask_logits_forward_host(int device, int in_dtype, int out_dtype, const void
   return pipe_finish_call();
 }
 
+// ---- "saved" host entries: autograd's save_for_backward for the host-buffer ABI.  The forward keeps the device copies of
+// its inputs in a pooled block and hands out a handle; the backward uploads only grad_out.  Blocks are recycled through a
+// grow-only pool (no cudaMalloc / cudaFree in steady state); reuse is ordered after the last kernel that read the block.
+namespace {
+struct SavedBlock {
+  char* base = nullptr;
+  size_t cap = 0;
+  cudaEvent_t last_use = nullptr;
+  bool in_use = false;
+  uint32_t gen = 1;
+  int kind = 0;                              // 1 = msda (plain / grouped), 2 = mask contraction
+  int dtype = 0, out_dtype = 0, N = 0, S = 0, M = 0, D = 0, G = 1, L = 0, Lq = 0, P = 0, B = 0, Q = 0, K = 0;
+  int64_t Ncols = 0;
+  float scale = 1.f;
+  size_t o_a = 0, o_b = 0, o_c = 0, o_shp = 0, o_lsi = 0;   // msda: value / loc / aw;  mask: coeff / proto
+};
+std::vector<SavedBlock*> g_saved;
+
+int saved_acquire(size_t bytes, int* index) {
+  int best = -1;
+  for (size_t i = 0; i < g_saved.size(); ++i)
+    if (!g_saved[i]->in_use && g_saved[i]->cap >= bytes && (best < 0 || g_saved[i]->cap < g_saved[best]->cap)) best = static_cast<int>(i);
+  if (best < 0) {
+    for (size_t i = 0; i < g_saved.size(); ++i)                 // recycle the slot of a free block that is too small
+      if (!g_saved[i]->in_use) { best = static_cast<int>(i); break; }
+    if (best < 0) { g_saved.push_back(new SavedBlock()); best = static_cast<int>(g_saved.size()) - 1; }
+    SavedBlock* b = g_saved[best];
+    if (b->base) {
+      if (b->last_use) cudaEventSynchronize(b->last_use);
+      cudaFree(b->base);
+      b->base = nullptr;
+      b->cap = 0;
+    }
+    const size_t want = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+    if (int rc = check_cuda(cudaMalloc(&b->base, want), "cudaMalloc(saved block)")) return rc;
+    b->cap = want;
+    if (!b->last_use)
+      if (int rc = check_cuda(cudaEventCreateWithFlags(&b->last_use, cudaEventDisableTiming), "cudaEventCreate")) return rc;
+    cudaEventRecord(b->last_use, g_pipe.s_run);
+  }
+  SavedBlock* b = g_saved[best];
+  b->in_use = true;
+  cudaStreamWaitEvent(g_pipe.s_in, b->last_use, 0);            // uploads into the block wait for its previous readers
+  *index = best;
+  return 0;
+}
+
+SavedBlock* saved_lookup(const char* who, int64_t handle, int kind) {
+  const uint32_t index = static_cast<uint32_t>(handle & 0xffffffff), gen = static_cast<uint32_t>(static_cast<uint64_t>(handle) >> 32);
+  if (handle <= 0 || index >= g_saved.size() || !g_saved[index]->in_use || g_saved[index]->gen != gen || g_saved[index]->kind != kind) {
+    fail(MSDA_ERR_INVALID_ARG, "%s: stale or foreign handle (each handle is consumed by one backward / release)", who);
+    return nullptr;
+  }
+  return g_saved[index];
+}
+
+void saved_free(SavedBlock* b) {
+  b->in_use = false;
+  ++b->gen;
+}
+
+// make sure the pipeline (streams, events) exists on `device` without reserving arena space
+int pipe_open(int device) {
+  size_t at = 0;
+  return pipe_reserve(device, 0, &at);
+}
+}  // namespace
+
+int msda_forward_host_saved(int device, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                            const void* loc, const void* aw, int N, int S, int M, int D, int G, int L, int Lq, int P, float scale,
+                            void* out, int64_t* saved) {
+  if (int rc = validate("msda_forward_host_saved", dtype, value, shapes, level_start, loc, aw, N, S, M, D, L, Lq, P)) return rc;
+  if (!saved) return fail(MSDA_ERR_INVALID_ARG, "msda_forward_host_saved: saved is NULL");
+  if (G < 1) return fail(MSDA_ERR_INVALID_ARG, "msda_forward_host_saved: G=%d", G);
+  *saved = 0;
+  const size_t es = dtype_size(dtype), ls = loc_dtype_size(dtype);
+  const size_t b_val = (size_t)N * S * M * D * es, b_loc = (size_t)N * Lq * M * L * P * 2 * ls, b_aw = b_loc / 2;
+  const size_t b_out = (size_t)N * Lq * M * D * es, b_shp = (size_t)G * L * 2 * 8, b_lsi = (size_t)G * L * 8;
+  if (b_out > 0 && !out) return fail(MSDA_ERR_INVALID_ARG, "msda_forward_host_saved: out is NULL");
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
+  size_t at = 0;
+  if (int rc = pipe_reserve(device, b_out, &at)) return rc;
+  char* d_out = g_pipe.base + at;
+  Carver cv;
+  const size_t o_val = cv.take(b_val), o_loc = cv.take(b_loc), o_aw = cv.take(b_aw), o_shp = cv.take(b_shp), o_lsi = cv.take(b_lsi);
+  int index = -1;
+  if (int rc = saved_acquire(cv.off + 256, &index)) return rc;
+  SavedBlock* b = g_saved[index];
+  b->kind = 1; b->dtype = dtype; b->N = N; b->S = S; b->M = M; b->D = D; b->G = G; b->L = L; b->Lq = Lq; b->P = P; b->scale = scale;
+  b->o_a = o_val; b->o_b = o_loc; b->o_c = o_aw; b->o_shp = o_shp; b->o_lsi = o_lsi;
+  char* d = b->base;
+  cudaEvent_t e_in, e_run;
+  pipe_events(&e_in, &e_run);
+  H2D(d + o_val, value, b_val, "value");
+  H2D(d + o_loc, loc, b_loc, "loc");
+  H2D(d + o_aw, aw, b_aw, "aw");
+  H2D(d + o_shp, shapes, b_shp, "shapes");
+  H2D(d + o_lsi, level_start, b_lsi, "level_start");
+  cudaEventRecord(e_in, g_pipe.s_in);
+  cudaStreamWaitEvent(g_pipe.s_run, e_in, 0);
+  int rc = 0;
+  if (b_out > 0)
+    rc = forward_impl("msda_forward_host_saved", g_pipe.s_run, dtype, d + o_val, reinterpret_cast<int64_t*>(d + o_shp),
+                      reinterpret_cast<int64_t*>(d + o_lsi), d + o_loc, d + o_aw, N, S, M, D, G, L, Lq, P, scale, d_out);
+  cudaEventRecord(b->last_use, g_pipe.s_run);
+  if (rc) { saved_free(b); return rc; }
+  cudaEventRecord(e_run, g_pipe.s_run);
+  cudaStreamWaitEvent(g_pipe.s_out, e_run, 0);
+  D2H(out, d_out, b_out, "out");
+  *saved = (static_cast<int64_t>(b->gen) << 32) | static_cast<int64_t>(index);
+  return pipe_finish_call();
+}
+
+int msda_backward_host_saved(int64_t saved, const void* grad_out, void* grad_value, void* grad_loc, void* grad_aw) {
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
+  SavedBlock* b = saved_lookup("msda_backward_host_saved", saved, 1);
+  if (!b) return MSDA_ERR_INVALID_ARG;
+  const size_t es = dtype_size(b->dtype), ls = loc_dtype_size(b->dtype);
+  const size_t b_val = (size_t)b->N * b->S * b->M * b->D * es, b_loc = (size_t)b->N * b->Lq * b->M * b->L * b->P * 2 * ls, b_aw = b_loc / 2;
+  const size_t b_go = (size_t)b->N * b->Lq * b->M * b->D * es;
+  const size_t b_ws = msda_backward_workspace_bytes(b->dtype, b->N, b->S, b->M, b->D);
+  if ((b_go > 0 && !grad_out) || (b_val > 0 && !grad_value) || (b_loc > 0 && (!grad_loc || !grad_aw)))
+    return fail(MSDA_ERR_INVALID_ARG, "msda_backward_host_saved: NULL tensor");
+  Carver cv;
+  const size_t o_go = cv.take(b_go), o_gv = cv.take(b_val), o_gl = cv.take(b_loc), o_ga = cv.take(b_aw), o_ws = cv.take(b_ws);
+  size_t at = 0;
+  if (int rc = pipe_reserve(g_pipe.device, cv.off, &at)) return rc;
+  char* t = g_pipe.base + at;
+  char* d = b->base;
+  cudaEvent_t e_in, e_run;
+  pipe_events(&e_in, &e_run);
+  H2D(t + o_go, grad_out, b_go, "grad_out");
+  cudaEventRecord(e_in, g_pipe.s_in);
+  cudaStreamWaitEvent(g_pipe.s_run, e_in, 0);
+  const int rc = backward_impl("msda_backward_host_saved", g_pipe.s_run, b->dtype, d + b->o_a, reinterpret_cast<int64_t*>(d + b->o_shp),
+                               reinterpret_cast<int64_t*>(d + b->o_lsi), d + b->o_b, d + b->o_c, t + o_go, b->N, b->S, b->M, b->D, b->G,
+                               b->L, b->Lq, b->P, b->scale, t + o_gv, t + o_gl, t + o_ga, b_ws ? t + o_ws : nullptr, b_ws);
+  cudaEventRecord(b->last_use, g_pipe.s_run);
+  saved_free(b);
+  if (rc) return rc;
+  cudaEventRecord(e_run, g_pipe.s_run);
+  cudaStreamWaitEvent(g_pipe.s_out, e_run, 0);
+  D2H(grad_value, t + o_gv, b_val, "grad_value");
+  D2H(grad_loc, t + o_gl, b_loc, "grad_loc");
+  D2H(grad_aw, t + o_ga, b_aw, "grad_aw");
+  return pipe_finish_call();
+}
+
+int mask_logits_forward_host_saved(int device, int in_dtype, int out_dtype, const void* coeff, const void* proto, int B, int Q,
+                                   int K, int64_t Ncols, void* out, int64_t* saved) {
+  if (B < 0 || Q < 0 || K <= 0 || Ncols < 0) return fail(MSDA_ERR_INVALID_ARG, "mask_logits_forward_host_saved: bad sizes");
+  if (!saved) return fail(MSDA_ERR_INVALID_ARG, "mask_logits_forward_host_saved: saved is NULL");
+  *saved = 0;
+  const size_t ei = dtype_size(in_dtype), eo = dtype_size(out_dtype);
+  const size_t b_c = (size_t)B * Q * K * ei, b_p = (size_t)B * K * Ncols * ei, b_o = (size_t)B * Q * Ncols * eo;
+  if ((b_c > 0 && !coeff) || (b_p > 0 && !proto) || (b_o > 0 && !out)) return fail(MSDA_ERR_INVALID_ARG, "mask_logits_forward_host_saved: NULL tensor");
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
+  size_t at = 0;
+  if (int rc = pipe_reserve(device, b_o, &at)) return rc;
+  char* d_out = g_pipe.base + at;
+  Carver cv;
+  const size_t o_c = cv.take(b_c), o_p = cv.take(b_p);
+  int index = -1;
+  if (int rc = saved_acquire(cv.off + 256, &index)) return rc;
+  SavedBlock* b = g_saved[index];
+  b->kind = 2; b->dtype = in_dtype; b->out_dtype = out_dtype; b->B = B; b->Q = Q; b->K = K; b->Ncols = Ncols; b->o_a = o_c; b->o_b = o_p;
+  char* d = b->base;
+  cudaEvent_t e_in, e_run;
+  pipe_events(&e_in, &e_run);
+  H2D(d + o_c, coeff, b_c, "coeff");
+  H2D(d + o_p, proto, b_p, "proto");
+  cudaEventRecord(e_in, g_pipe.s_in);
+  cudaStreamWaitEvent(g_pipe.s_run, e_in, 0);
+  int rc = 0;
+  if (b_o > 0) rc = mask_logits_forward(g_pipe.s_run, in_dtype, out_dtype, d + o_c, d + o_p, B, Q, K, Ncols, d_out);
+  cudaEventRecord(b->last_use, g_pipe.s_run);
+  if (rc) { saved_free(b); return rc; }
+  cudaEventRecord(e_run, g_pipe.s_run);
+  cudaStreamWaitEvent(g_pipe.s_out, e_run, 0);
+  D2H(out, d_out, b_o, "out");
+  *saved = (static_cast<int64_t>(b->gen) << 32) | static_cast<int64_t>(index);
+  return pipe_finish_call();
+}
+
+int mask_logits_backward_host_saved(int64_t saved, const void* grad_out, void* grad_coeff, void* grad_proto) {
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
+  SavedBlock* b = saved_lookup("mask_logits_backward_host_saved", saved, 2);
+  if (!b) return MSDA_ERR_INVALID_ARG;
+  const size_t e = dtype_size(b->dtype);
+  const size_t b_c = (size_t)b->B * b->Q * b->K * e, b_p = (size_t)b->B * b->K * b->Ncols * e, b_go = (size_t)b->B * b->Q * b->Ncols * e;
+  if (b_go > 0 && !grad_out) return fail(MSDA_ERR_INVALID_ARG, "mask_logits_backward_host_saved: grad_out is NULL");
+  Carver cv;
+  const size_t o_go = cv.take(b_go), o_gc = cv.take(b_c), o_gp = cv.take(b_p);
+  size_t at = 0;
+  if (int rc = pipe_reserve(g_pipe.device, cv.off, &at)) return rc;
+  char* t = g_pipe.base + at;
+  char* d = b->base;
+  cudaEvent_t e_in, e_run;
+  pipe_events(&e_in, &e_run);
+  H2D(t + o_go, grad_out, b_go, "grad_out");
+  cudaEventRecord(e_in, g_pipe.s_in);
+  cudaStreamWaitEvent(g_pipe.s_run, e_in, 0);
+  const int rc = mask_logits_backward(g_pipe.s_run, b->dtype, d + b->o_a, d + b->o_b, t + o_go, b->B, b->Q, b->K, b->Ncols,
+                                      grad_coeff ? t + o_gc : nullptr, grad_proto ? t + o_gp : nullptr);
+  cudaEventRecord(b->last_use, g_pipe.s_run);
+  saved_free(b);
+  if (rc) return rc;
+  cudaEventRecord(e_run, g_pipe.s_run);
+  cudaStreamWaitEvent(g_pipe.s_out, e_run, 0);
+  if (grad_coeff) D2H(grad_coeff, t + o_gc, b_c, "grad_coeff");
+  if (grad_proto) D2H(grad_proto, t + o_gp, b_p, "grad_proto");
+  return pipe_finish_call();
+}
+
+int msda_host_saved_release(int64_t saved) {
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
+  const uint32_t index = static_cast<uint32_t>(saved & 0xffffffff), gen = static_cast<uint32_t>(static_cast<uint64_t>(saved) >> 32);
+  if (saved <= 0 || index >= g_saved.size() || !g_saved[index]->in_use || g_saved[index]->gen != gen)
+    return fail(MSDA_ERR_INVALID_ARG, "msda_host_saved_release: stale handle");
+  saved_free(g_saved[index]);
+  return 0;
+}
+
 int msda_host_sync(void) {
   std::lock_guard<std::mutex> lock(g_pipe.mu);
   if (g_pipe.device < 0) return 0;
@@ -716,6 +939,12 @@ int msda_host_arena_release(void) {
   if (g_pipe.device >= 0) {
     cudaSetDevice(g_pipe.device);
     pipe_drain();
+    for (SavedBlock* b : g_saved) {                       // outstanding handles become stale
+      if (b->base) cudaFree(b->base);
+      if (b->last_use) cudaEventDestroy(b->last_use);
+      delete b;
+    }
+    g_saved.clear();
     pipe_free();
   }
   g_pipe.device = -1;

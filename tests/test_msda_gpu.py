@@ -301,6 +301,106 @@ def test_host_buffer_entry_async_pipeline():
     lib.msda_host_arena_release()
 
 
+@pytest.mark.parametrize("async_mode", [0, 1])
+def test_host_saved_entries(async_mode):
+    """*_host_saved: the forward keeps its inputs on the device (autograd's save_for_backward for the host-buffer ABI), the
+    backward uploads only grad_out.  Forwards of several calls first, backwards in reverse order (as a training step does),
+    pooled blocks get reused, a consumed / foreign handle is rejected, the mask head pair works the same way."""
+    import ctypes
+    from mdqe_cvpr2023_b200 import _lib
+    lib = _lib.load()
+    cases = []
+    for seed in range(3):
+        inp = make_inputs(2, [(12, 20), (6, 10)], 8, 32, 4, Lq=25 + 3 * seed, dist="wide", seed=50 + seed)
+        pin = {k: v.contiguous().pin_memory() for k, v in inp.items()}
+        N, S, M, D = inp["value"].shape
+        Lq = inp["loc"].shape[1]
+        outs = (torch.empty(N, Lq, M * D).pin_memory(), torch.empty_like(pin["value"]).pin_memory(),
+                torch.empty_like(pin["loc"]).pin_memory(), torch.empty_like(pin["aw"]).pin_memory())
+        cases.append((inp, pin, (N, S, M, D, 1, 2, Lq, 4, 1.0), outs))
+    coeff = torch.tanh(torch.randn(1, 50, 32)).pin_memory()
+    proto = torch.randn(1, 32, 2, 12, 20).pin_memory()
+    mgo = torch.randn(1, 50, 2, 12, 20).pin_memory()
+    mout, mgc, mgp = torch.empty(1, 50, 480).pin_memory(), torch.empty_like(coeff).pin_memory(), torch.empty_like(proto).pin_memory()
+    _lib.set_option("host_async", async_mode)
+    try:
+        for rounds in range(2):                                  # second round reuses the pooled blocks
+            handles = []
+            for inp, pin, dims, (out, gv, gl, ga) in cases:
+                h = ctypes.c_int64(0)
+                _lib.check(lib.msda_forward_host_saved(0, _lib.MSDA_F32, pin["value"].data_ptr(), pin["shapes"].data_ptr(),
+                                                       pin["level_start"].data_ptr(), pin["loc"].data_ptr(), pin["aw"].data_ptr(),
+                                                       *dims, out.data_ptr(), ctypes.byref(h)), "msda_forward_host_saved")
+                assert h.value > 0
+                handles.append(h.value)
+            mh = ctypes.c_int64(0)
+            _lib.check(lib.mask_logits_forward_host_saved(0, _lib.MSDA_F32, _lib.MSDA_F32, coeff.data_ptr(), proto.data_ptr(), 1, 50, 32,
+                                                          480, mout.data_ptr(), ctypes.byref(mh)), "mask_logits_forward_host_saved")
+            assert lib.msda_backward_host_saved(mh.value, None, None, None, None) == -1   # wrong kind of handle
+            _lib.check(lib.mask_logits_backward_host_saved(mh.value, mgo.data_ptr(), mgc.data_ptr(), mgp.data_ptr()), "mask bwd saved")
+            for h, (inp, pin, dims, (out, gv, gl, ga)) in zip(reversed(handles), reversed(cases)):
+                _lib.check(lib.msda_backward_host_saved(h, pin["grad_out"].data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr()),
+                           "msda_backward_host_saved")
+            assert lib.msda_backward_host_saved(handles[0], cases[0][1]["grad_out"].data_ptr(), cases[0][3][1].data_ptr(),
+                                                cases[0][3][2].data_ptr(), cases[0][3][3].data_ptr()) == -1
+            assert "handle" in _lib.last_error()
+            _lib.check(lib.msda_host_sync(), "msda_host_sync")
+            for inp, pin, dims, outs in cases:
+                check(outs, oracle_all(inp), 2e-5, "saved host entry", inp)
+            assert nerr(mout.view(1, 50, 2, 12, 20), torch.einsum("bqm,bmthw->bqthw", coeff.double(), proto.double())) < 2e-5
+            assert nerr(mgc, torch.einsum("bmthw,bqthw->bqm", proto.double(), mgo.double())) < 2e-5
+            assert nerr(mgp, torch.einsum("bqm,bqthw->bmthw", coeff.double(), mgo.double())) < 2e-5
+        # inference: forward only, then release
+        h = ctypes.c_int64(0)
+        inp, pin, dims, (out, gv, gl, ga) = cases[0]
+        _lib.check(lib.msda_forward_host_saved(0, _lib.MSDA_F32, pin["value"].data_ptr(), pin["shapes"].data_ptr(),
+                                               pin["level_start"].data_ptr(), pin["loc"].data_ptr(), pin["aw"].data_ptr(),
+                                               *dims, out.data_ptr(), ctypes.byref(h)), "msda_forward_host_saved")
+        _lib.check(lib.msda_host_saved_release(h.value), "msda_host_saved_release")
+        assert lib.msda_host_saved_release(h.value) == -1
+        _lib.check(lib.msda_host_sync(), "msda_host_sync")
+    finally:
+        _lib.set_option("host_async", 0)
+        lib.msda_host_arena_release()
+
+
+def test_host_saved_grouped_temporal_form():
+    """G > 1 through the saved host entries equals the mean of the per-level calls (ms_deform_attn.py:219-235)."""
+    import ctypes
+    from mdqe_cvpr2023_b200 import _lib
+    lib = _lib.load()
+    T, pyr, M, D, Lq, P = 3, [(12, 20), (6, 10), (3, 5)], 8, 32, 21, 4
+    S = sum(h * w for h, w in pyr)
+    g = torch.Generator().manual_seed(77)
+    value = torch.randn(1, T * S, M, D, generator=g)
+    loc = torch.rand(1, Lq, M, T, P, 2, generator=g) * 1.2 - 0.1
+    aw = torch.softmax(torch.randn(1, Lq, M, T * P, generator=g), -1).view(1, Lq, M, T, P)
+    go = torch.randn(1, Lq, M * D, generator=g)
+    starts = [0]
+    for h, w in pyr[:-1]:
+        starts.append(starts[-1] + h * w)
+    G = len(pyr)
+    shapes = torch.tensor([[list(hw)] * T for hw in pyr], dtype=torch.int64)                     # [G, T, 2]
+    lsi = torch.tensor([[t * S + starts[l] for t in range(T)] for l in range(G)], dtype=torch.int64)
+    from oracle import msda_oracle
+    outs, gvs, gls, gas = [], [], [], []
+    for l in range(G):
+        o = msda_oracle.msda_forward(value.numpy(), shapes[l].numpy(), loc.numpy(), aw.numpy(), level_start=lsi[l].numpy())
+        gv, gl, ga = msda_oracle.msda_backward(value.numpy(), shapes[l].numpy(), loc.numpy(), aw.numpy(), (go / G).numpy(), level_start=lsi[l].numpy())
+        outs.append(torch.from_numpy(o)); gvs.append(torch.from_numpy(gv)); gls.append(torch.from_numpy(gl)); gas.append(torch.from_numpy(ga))
+    want = (sum(outs) / G, sum(gvs), sum(gls), sum(gas))
+    pin = [t.contiguous().pin_memory() for t in (value, shapes, lsi, loc, aw, go)]
+    out, gv, gl, ga = (torch.empty(1, Lq, M * D).pin_memory(), torch.empty_like(value).pin_memory(), torch.empty_like(loc).pin_memory(),
+                       torch.empty_like(aw).pin_memory())
+    h = ctypes.c_int64(0)
+    _lib.check(lib.msda_forward_host_saved(0, _lib.MSDA_F32, pin[0].data_ptr(), pin[1].data_ptr(), pin[2].data_ptr(), pin[3].data_ptr(),
+                                           pin[4].data_ptr(), 1, T * S, M, D, G, T, Lq, P, 1.0 / G, out.data_ptr(), ctypes.byref(h)), "fwd")
+    _lib.check(lib.msda_backward_host_saved(h.value, pin[5].data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr()), "bwd")
+    lib.msda_host_arena_release()
+    for name, got, ref in zip(("out", "grad_value", "grad_loc", "grad_aw"), (out, gv, gl, ga), want):
+        assert nerr(got.view(ref.shape), ref) < 2e-5, name
+
+
 def test_launch_counter_counts_kernels():
     from mdqe_cvpr2023_b200 import _lib
     inp = to_cuda(make_inputs(1, [(8, 8)], 8, 32, 4, Lq=8, seed=16))
