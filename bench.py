@@ -565,7 +565,7 @@ def main():
         us = ms / n * 1e3
         ach = nbytes / (us * 1e-6) / 1e9
         # DRAM bytes of one launch from the committed `ncu --set full` capture of the same kernel and shape (fp32)
-        traffic = traffic_db.get(name.split("<")[0]) if args.dtype == "fp32" else None
+        traffic = traffic_db.get(name.split("<")[0].split(":")[0]) if args.dtype == "fp32" else None
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                 "traffic": traffic, "traffic_source": traffic_db.get("source") if traffic else None, "avg_launch_us": us, "launches_timed": n, "algorithmic_bytes": nbytes, "peak_source": peak_src}
 
@@ -573,11 +573,11 @@ def main():
     roofline_fwd = roof(fwd_bytes, fwd_ms, fwd_n, "msda_fwd_fast2_kernel<%s,32,16> (encoder shape N=4,S=Lq=5100)" % ("bf16" if args.dtype == "bf16" else "float"))
     mB = QUERIES * MASK_K + MASK_K * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
     mO = QUERIES * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
-    roofline_mask = roof(mB * esize + mO * esize, mfw_ms, mfw_n, "mask_fwd_tc2_kernel<bf16> (tcgen05)" if args.dtype == "bf16" else "mask_fwd_tc3_kernel<float> (tcgen05, 3xTF32)")
+    roofline_mask = roof(mB * esize + mO * esize, mfw_ms, mfw_n, "mask_fwd_tc2_kernel<bf16> (tcgen05)" if args.dtype == "bf16" else "mask_fwd_tc4_kernel<float,false> (tcgen05, 3xTF32)")
     if roofline_mask:
         flops = 2.0 * QUERIES * MASK_K * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
         roofline_mask["tflops"] = flops / (roofline_mask["avg_launch_us"] * 1e-6) / 1e12
-    roofline_mask_bwd = roof((mB + mO + mB) * 4, mbw_ms, mbw_n, "mask_grad_coeff_kernel + mask_grad_proto_kernel (fp32)")
+    roofline_mask_bwd = roof((mB + mO + mB) * 4, mbw_ms, mbw_n, "mask_backward_tc: mask_grad_coeff_tc_kernel + mask_fwd_tc4_kernel<float,true> (tcgen05, 3xTF32)")
 
     # ---- eager (no graph) step time, for reference
     sync_all()

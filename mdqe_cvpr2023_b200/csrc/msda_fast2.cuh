@@ -360,6 +360,21 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
           } else {
             Vec16<VT>::load(grad_out + static_cast<int64_t>(p0 + pl) * D + c * C::CPL, go);
           }
+          // 2-byte values: a lane owns 8 channels for the dot products, but two 16-byte reductions per lane at a 32-byte lane
+          // stride would half-fill every L2 sector.  The scatter only needs grad_out, so for it the lane takes channels
+          // [4c, 4c+4) and [4G+4c, 4G+4c+4): each warp-wide RED then covers contiguous 16-byte pieces (bf16 backward 439 -> fp32 speed).
+          float go_red[C::CPL == 8 ? 8 : 1];
+          if constexpr (C::CPL == 8) {
+            const VT* gp = grad_out + static_cast<int64_t>(p0 + pl) * D;
+            const uint2 lo4 = __ldg(reinterpret_cast<const uint2*>(gp + 4 * c));
+            const uint2 hi4 = __ldg(reinterpret_cast<const uint2*>(gp + 4 * C::G + 4 * c));
+            const uint32_t u4[4] = {lo4.x, lo4.y, hi4.x, hi4.y};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              go_red[2 * i] = __uint_as_float(u4[i] << 16);
+              go_red[2 * i + 1] = __uint_as_float(u4[i] & 0xffff0000u);
+            }
+          }
           const uint4* stream = reinterpret_cast<const uint4*>(my_stream + pl * C::NSLOT);
 #pragma unroll
           for (int it = 0; it < C::SPG / 2; ++it) {
@@ -374,11 +389,17 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
                 Vec16<VT>::load(row_ptr(vlane, off[u]), v);
 #pragma unroll
                 for (int j = 0; j < C::CPL; ++j) dot = fmaf(go[j], v[j], dot);
-                float* gv = const_cast<float*>(reinterpret_cast<const float*>(
-                    reinterpret_cast<const char*>(gvlane) + static_cast<uint64_t>(off[u]) * (16u * sizeof(float) / sizeof(VT))));
+                if constexpr (C::CPL == 8) {
+                  float* gv = grad_value + static_cast<uint64_t>(off[u]) * 8u + 4 * c;      // off counts 16-byte units of 2-byte elements
+                  red_add_f32x4(gv, w[u] * go_red[0], w[u] * go_red[1], w[u] * go_red[2], w[u] * go_red[3]);
+                  red_add_f32x4(gv + 4 * C::G, w[u] * go_red[4], w[u] * go_red[5], w[u] * go_red[6], w[u] * go_red[7]);
+                } else {
+                  float* gv = const_cast<float*>(reinterpret_cast<const float*>(
+                      reinterpret_cast<const char*>(gvlane) + static_cast<uint64_t>(off[u]) * (16u * sizeof(float) / sizeof(VT))));
 #pragma unroll
-                for (int j = 0; j < C::CPL; j += 4)
-                  red_add_f32x4(gv + j, w[u] * go[j], w[u] * go[j + 1], w[u] * go[j + 2], w[u] * go[j + 3]);
+                  for (int j = 0; j < C::CPL; j += 4)
+                    red_add_f32x4(gv + j, w[u] * go[j], w[u] * go[j + 1], w[u] * go[j + 2], w[u] * go[j + 3]);
+                }
               }
               // fold the G per-lane partials of this corner row (groups are G consecutive lanes)
               if constexpr ((C::G & (C::G - 1)) == 0) {

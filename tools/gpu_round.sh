@@ -13,8 +13,14 @@ echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph > gpurun_out/ncu_launch_${TAG}.log 2>&1; echo "ncu list rc=$?"
 echo "== ncu full (bwd, fwd)"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:msda_bwd_fast -c 2 -f -o gpurun_out/prof_bwd_${TAG} \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:msda_bwd_fast -s 9 -c 3 -f -o gpurun_out/prof_bwd_${TAG} \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph --layers 1 > gpurun_out/ncu_bwd_${TAG}.log 2>&1; echo "ncu bwd rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:msda_fwd_fast -c 2 -f -o gpurun_out/prof_fwd_${TAG} \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:msda_fwd_fast -s 9 -c 3 -f -o gpurun_out/prof_fwd_${TAG} \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph --layers 1 > gpurun_out/ncu_fwd_${TAG}.log 2>&1; echo "ncu fwd rc=$?"
+echo "== mask head (fp32 tensor-core kernels): breakdown, timeline, ncu"
+timeout 200 python tools/mask_bwd_breakdown.py > gpurun_out/mask_breakdown_${TAG}.txt 2>&1; cat gpurun_out/mask_breakdown_${TAG}.txt | tail -4
+timeout 100 python tools/mask_bwd_timeline.py > gpurun_out/mask_timeline_${TAG}.txt 2>&1
+timeout 100 python tools/mask_keepraw_check.py > gpurun_out/mask_keepraw_${TAG}.txt 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:mask_ -s 3 -c 3 -f -o gpurun_out/prof_mask_${TAG} \
+    python tools/mask_profile_target.py > gpurun_out/ncu_mask_${TAG}.log 2>&1; echo "ncu mask rc=$?"
 ls -la gpurun_out | tail -20

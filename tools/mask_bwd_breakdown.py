@@ -5,7 +5,7 @@ import torch
 from mdqe_cvpr2023_b200 import _lib, ops
 
 B, Q, K = 1, 196, 32
-T, H, W = 7, 96, 160
+T, H, W = 4, 96, 160
 coeff = torch.tanh(torch.randn(B, Q, K, device="cuda"))
 proto = torch.randn(B, K, T, H, W, device="cuda")
 go = torch.randn(B, Q, T, H, W, device="cuda")

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mdqe_cvpr2023_b200 import _lib, ops
 B, Q, K = 1, 196, 32
-coeff = torch.tanh(torch.randn(B, Q, K, device="cuda")); proto = torch.randn(B, K, 7, 96, 160, device="cuda"); go = torch.randn(B, Q, 7, 96, 160, device="cuda")
+coeff = torch.tanh(torch.randn(B, Q, K, device="cuda")); proto = torch.randn(B, K, 4, 96, 160, device="cuda"); go = torch.randn(B, Q, 4, 96, 160, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 ops.mask_logits_backward(coeff, proto, go, need_proto=False); torch.cuda.synchronize()
 flush.zero_()

@@ -4,8 +4,8 @@ import torch
 from mdqe_cvpr2023_b200 import _lib, ops
 def nerr(a, b): return float((a.double() - b.double()).abs().max() / b.double().abs().max())
 torch.manual_seed(0)
-B, Q, K, N = 1, 196, 32, 7 * 96 * 160
-coeff = torch.tanh(torch.randn(B, Q, K, device="cuda")); proto = torch.randn(B, K, 7, 96, 160, device="cuda"); go = torch.randn(B, Q, 7, 96, 160, device="cuda")
+B, Q, K, N = 1, 196, 32, 4 * 96 * 160
+coeff = torch.tanh(torch.randn(B, Q, K, device="cuda")); proto = torch.randn(B, K, 4, 96, 160, device="cuda"); go = torch.randn(B, Q, 4, 96, 160, device="cuda")
 want_gc = torch.einsum("bmthw,bqthw->bqm", proto.double(), go.double())
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for dbg in (2, 0, 2, 0):

@@ -48,8 +48,8 @@ for (B, Q, K, N) in [(1, 64, 40, 512), (2, 100, 64, 4096), (1, 196, 128, 8192), 
 
 # timing of the backward on the bench shape
 import time
-B, Q, K, N = 1, 196, 32, 7 * 96 * 160
-coeff = torch.tanh(torch.randn(B, Q, K, device="cuda")); proto = torch.randn(B, K, 7, 96, 160, device="cuda"); go = torch.randn(B, Q, 7, 96, 160, device="cuda")
+B, Q, K, N = 1, 196, 32, 4 * 96 * 160
+coeff = torch.tanh(torch.randn(B, Q, K, device="cuda")); proto = torch.randn(B, K, 4, 96, 160, device="cuda"); go = torch.randn(B, Q, 4, 96, 160, device="cuda")
 for variant in (1, 5, 0):
     _lib.set_option("mask_variant", variant)
     for _ in range(3): ops.mask_logits_backward(coeff, proto, go)
