@@ -48,7 +48,7 @@ static int make_map_in(CUtensorMap* map, const void* base, bool fp32, uint64_t d
 static bool mask_tc_eligible(int in_dtype, const void* coeff, const void* proto, int Q, int K, int64_t Ncols) {
   if (in_dtype != MSDA_BF16) return false;
   if (K < 8 || K > 64 || K % 8 != 0) return false;                     // 16-byte global strides, <= 4 K steps
-  if (Q < 1 || Q > 256) return false;                                  // one MMA N extent / TMEM allocation
+  if (Q < 1) return false;
   if (Ncols % 8 != 0 || Ncols >= (int64_t(1) << 31)) return false;
   return ((reinterpret_cast<uintptr_t>(coeff) | reinterpret_cast<uintptr_t>(proto)) & 15u) == 0;
 }
@@ -88,12 +88,17 @@ static int launch_mask_tc2(cudaStream_t st, const void* coeff, const void* proto
   const int n_tiles_n = static_cast<int>((Ncols + kTcTileN - 1) / kTcTileN);
   const int64_t tiles = (int64_t)B * n_tiles_n;
   // query chunks: starts at multiples of 32 (QS), the last chunk takes the remainder
-  int n_qchunks = 1;
+  int n_qchunks = (Q + 255) / 256;                                      // at most 256 query rows per item (one MMA N extent)
   while (n_qchunks < 4 && tiles * n_qchunks < 6LL * sms && (Q / (n_qchunks + 1)) / 32 * 32 >= 32) ++n_qchunks;
-  int QS = (n_qchunks == 1) ? ((Q + 31) / 32 * 32) : (Q / n_qchunks) / 32 * 32;
-  const int last_rows = Q - (n_qchunks - 1) * QS;
-  const int QN = ((QS > last_rows ? QS : last_rows) + 15) / 16 * 16;
-  if (QN > 256) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: query chunk of %d rows exceeds one MMA", QN);
+  int QS = 0, QN = 0;
+  for (;; ++n_qchunks) {
+    QS = (n_qchunks == 1) ? ((Q + 31) / 32 * 32) : (Q / n_qchunks) / 32 * 32;
+    if (QS < 32) break;
+    const int last_rows = Q - (n_qchunks - 1) * QS;
+    QN = ((QS > last_rows ? QS : last_rows) + 15) / 16 * 16;
+    if (QN <= 256 && mask_tc2_smem_bytes(KP, QN, sizeof(OT)) <= 220 * 1024) break;
+  }
+  if (QN > 256 || QS < 32) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: cannot chunk Q=%d for the tensor-core kernel", Q);
   const int64_t n_items = tiles * n_qchunks;
   if (n_items >= (int64_t(1) << 31)) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: too many tiles");
   CUtensorMap map_proto, map_coeff, map_out;
@@ -298,7 +303,7 @@ int mask_forward_dispatch(cudaStream_t st, int in_dtype, int out_dtype, const vo
   const bool tc_ok = mask_tc_eligible(in_dtype, coeff, proto, Q, K, Ncols);
   if (variant == 2 && !tc_ok && !mask_tc3_eligible(in_dtype, coeff, proto, Q, K, Ncols))
     return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: tcgen05 path needs K %% 8 == 0 with K <= 64 (bf16) / 32 (fp32) and 16-byte aligned rows");
-  if (variant == 3 && tc_ok) {                       // 3 = first (one tile per CTA) tensor-core kernel, kept for A/B timing
+  if (variant == 3 && tc_ok && Q <= 256) {           // 3 = first (one tile per CTA) tensor-core kernel, kept for A/B timing
     if (out_dtype == MSDA_F32) return launch_mask_tc<float>(st, coeff, proto, out, B, Q, K, Ncols);
     return launch_mask_tc<__nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
   }

@@ -35,7 +35,7 @@ def test_mask_golden(name, variant):
 
 @pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("Q,T,plane,K", [(196, 4, (96, 160), 32), (100, 2, (96, 160), 24), (300, 2, (160, 288), 32),
-                                         (196, 3, (96, 160), 24), (7, 1, (5, 9), 32), (130, 2, (33, 17), 40)])
+                                         (196, 3, (96, 160), 24), (7, 1, (5, 9), 32), (130, 2, (33, 17), 40), (256, 2, (160, 288), 64)])
 def test_mask_sweep_vs_einsum(Q, T, plane, K, variant):
     from mdqe_cvpr2023_b200 import _lib, ops
     _lib.set_option("mask_variant", variant)
