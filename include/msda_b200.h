@@ -150,6 +150,19 @@ int mask_logits_backward(void* stream, int dtype,
                          int B, int Q, int K, int64_t Ncols,
                          void* grad_coeff, void* grad_proto);
 
+/* Linear layers around the sampler on the tensor cores (ms_deform_attn.py:136-138 value_proj + masked_fill,
+ * :143-146 sampling offsets, :157 attention_weights, :171 output_proj; the reference runs them as fp32 cuBLAS SGEMMs):
+ *   y[r, o] = sum_i x[r, i] * weight[o, i] + bias[o];  rows r with row_mask[r] != 0 are written as 0 (masked_fill)
+ * x [rows, in_features], weight [out_features, in_features] (nn.Linear layout), bias [out_features] or NULL, row_mask
+ * [rows] bytes or NULL, y [rows, out_features]; all fp32, device memory.  3xTF32 (hi*hi + hi*lo + lo*hi, fp32
+ * accumulation): ~1e-6 of the exact fp32 product.  in_features and out_features must be multiples of 4.
+ * tc_linear_backward: grad_x[r, i] = sum_o grad_y[r, o] weight[o, i]; grad_weight[o, i] = sum_r grad_y[r, o] x[r, i]
+ * (zero-filled inside, accumulated across CTAs with TMA reduce-add stores); either output may be NULL. */
+int tc_linear_forward(void* stream, const void* x, const void* weight, const void* bias, const unsigned char* row_mask,
+                      int64_t rows, int in_features, int out_features, void* y);
+int tc_linear_backward(void* stream, const void* grad_y, const void* x, const void* weight,
+                       int64_t rows, int in_features, int out_features, void* grad_x, void* grad_weight);
+
 /* Host-buffer entries: same semantics, every pointer is HOST memory (pinned memory makes the
  * copies asynchronous).  The library owns a grow-only device arena per process; `device` selects
  * the GPU.  These return after the results have landed in the host output buffers. */

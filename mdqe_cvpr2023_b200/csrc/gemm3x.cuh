@@ -1,0 +1,236 @@
+// fp32 GEMM on the 5th-generation tensor cores as 3xTF32 (sm_100a): C[M x N] (+)= A[M x K] * B[K x N].
+//
+// Used for the Linear layers around the sampler (/root/reference/mdqe/models/ops/modules/ms_deform_attn.py:136-138
+// value_proj + masked_fill, :143-146 sampling_offsets / sampling_grid_offsets, :157 attention_weights, :171 output_proj), which the
+// reference runs as fp32 cuBLAS SGEMMs (TF32 disabled).  hi = the fp32 operand itself (the MMA truncates to TF32), lo = a - trunc(a)
+// produced on chip; hi*hi + hi*lo + lo*hi accumulated in fp32 in TMEM: ~1e-6 of the exact product.
+//
+// Both operands may be K-major (reduction index contiguous: TMA 128B swizzle, UMMA layout type 2) or MN-major (M / N index
+// contiguous: "128B swizzle, 32B atoms", layout type 1), so the three GEMMs of a Linear layer need no transposed copies:
+//   y  = x  W^T      A = x  [R][in]   K-major      B = W  [out][in]  K-major
+//   dx = dy W        A = dy [R][out]  K-major      B = W  [out][in]  = [K][N] -> MN-major
+//   dW = dy^T x      A = dy [R][out]  = [K][M] -> MN-major          B = x [R][in] = [K][N] -> MN-major, reduction over the rows
+//                    split across CTAs, partial tiles added with TMA reduce-add stores into a zeroed dW.
+// One persistent CTA per SM: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 2-9 epilogue (TMEM -> registers ->
+// bias / row mask -> swizzled staging tile -> TMA store), warps 10-17 produce the lo tiles.  Tile 128 x 128, reduction in
+// chunks of 32, 3-stage ring, two accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+
+#include "mask_tc4.cuh"
+
+namespace msda {
+
+constexpr int kG3Tile = 128;
+constexpr int kG3Stages = 3;
+constexpr int kG3SplitWarps = 8;
+constexpr int kG3Threads = (2 + 8 + kG3SplitWarps) * 32;               // 576
+constexpr uint32_t kG3OpBytes = kG3Tile * 128u;                        // one operand tile: 128 rows/columns x 32 fp32
+constexpr uint32_t kG3StageBytes = 4 * kG3OpBytes;                     // [A hi][A lo][B hi][B lo]
+constexpr uint32_t kG3OutBytes = kG3Tile * 128u;                       // staging: 128 rows x 32 columns
+
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template <bool kAMn, bool kBMn>
+__global__ void __launch_bounds__(kG3Threads, 1)
+gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+              const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias,
+              const unsigned char* __restrict__ row_mask, int M, int N, int n_kchunks, int chunks_per_split, int tiles_m,
+              int tiles_n, int n_items, int reduce) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* out_stage = smem + kG3Stages * kG3StageBytes;                // 2 x 16 KB (one per column half)
+  __shared__ __align__(8) uint64_t bars[3 * kG3Stages + 4];
+  __shared__ uint32_t s_tmem_base;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_ready = [&](int s) { return bar0 + 8u * (kG3Stages + s); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * kG3Stages + s); };
+  auto bar_tfull = [&](int a) { return bar0 + 8u * (3 * kG3Stages + a); };
+  auto bar_tempty = [&](int a) { return bar0 + 8u * (3 * kG3Stages + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kG3Stages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_ready(s), kG3SplitWarps); mbar_init(bar_empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem_base;
+
+  // item -> (split, row tile, column tile); column tiles of one row tile are neighbours so that A is re-read from L2
+  auto decode = [&](int item, int& split, int& tm, int& tn) {
+    tn = item % tiles_n;
+    const int r = item / tiles_n;
+    tm = r % tiles_m;
+    split = r / tiles_m;
+  };
+  auto chunk_range = [&](int split, int& c0, int& c1) {
+    c0 = split * chunks_per_split;
+    c1 = min(n_kchunks, c0 + chunks_per_split);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int i = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int split, tm, tn, c0, c1;
+        decode(item, split, tm, tn);
+        chunk_range(split, c0, c1);
+        for (int kc = c0; kc < c1; ++kc, ++i) {
+          const int s = i % kG3Stages;
+          const uint32_t ph = (i / kG3Stages) & 1;
+          mbar_wait(bar_empty(s), ph ^ 1);
+          const uint32_t dst = smem_u32(smem) + s * kG3StageBytes;
+          mbar_expect_tx(bar_full(s), 2 * kG3OpBytes);
+          if constexpr (kAMn) {
+            for (int j = 0; j < 4; ++j) tma_load_3d(dst + j * 4096u, &map_a, bar_full(s), tm * kG3Tile + j * 32, kc * 32, 0);
+          } else {
+            tma_load_3d(dst, &map_a, bar_full(s), kc * 32, tm * kG3Tile, 0);
+          }
+          if constexpr (kBMn) {
+            for (int j = 0; j < 4; ++j) tma_load_3d(dst + 2 * kG3OpBytes + j * 4096u, &map_b, bar_full(s), tn * kG3Tile + j * 32, kc * 32, 0);
+          } else {
+            tma_load_3d(dst + 2 * kG3OpBytes, &map_b, bar_full(s), kc * 32, tn * kG3Tile, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(kG3Tile, kAMn ? 1u : 0u, kBMn ? 1u : 0u);
+      int i = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        int split, tm, tn, c0, c1;
+        decode(item, split, tm, tn);
+        chunk_range(split, c0, c1);
+        const int a = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(bar_tempty(a), aph ^ 1);
+        uint32_t acc = 0;
+        for (int kc = c0; kc < c1; ++kc, ++i) {
+          const int s = i % kG3Stages;
+          const uint32_t ph = (i / kG3Stages) & 1;
+          mbar_wait(bar_ready(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = smem_u32(smem) + s * kG3StageBytes, a_lo = a_hi + kG3OpBytes;
+          const uint32_t b_hi = a_hi + 2 * kG3OpBytes, b_lo = b_hi + kG3OpBytes;
+          const uint32_t a_sel[3] = {a_hi, a_hi, a_lo}, b_sel[3] = {b_hi, b_lo, b_hi};     // hi*hi + hi*lo + lo*hi
+          for (int term = 0; term < 3; ++term)
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t a_desc = kAMn ? umma_desc(a_sel[term] + ks * 1024u, 4096u, 512u, 1u) : umma_desc(a_sel[term] + ks * 32u, 16u, 1024u, 2u);
+              const uint64_t b_desc = kBMn ? umma_desc(b_sel[term] + ks * 1024u, 4096u, 512u, 1u) : umma_desc(b_sel[term] + ks * 32u, 16u, 1024u, 2u);
+              umma_tf32(tmem_base + a * 128u, a_desc, b_desc, idesc, acc);
+              acc = 1;
+            }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_empty(s)) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_tfull(a)) : "memory");
+      }
+    }
+  } else if (warp >= 10) {
+    // ---- lo tiles: element-wise, layout-agnostic
+    const uint32_t t = threadIdx.x - 10 * 32;                              // 0 .. 255
+    int i = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int split, tm, tn, c0, c1;
+      decode(item, split, tm, tn);
+      chunk_range(split, c0, c1);
+      for (int kc = c0; kc < c1; ++kc, ++i) {
+        const int s = i % kG3Stages;
+        const uint32_t ph = (i / kG3Stages) & 1;
+        mbar_wait(bar_full(s), ph);
+        uint8_t* st = smem + s * kG3StageBytes;
+#pragma unroll
+        for (int op = 0; op < 2; ++op) {
+          const uint4* hi = reinterpret_cast<const uint4*>(st + op * 2 * kG3OpBytes);
+          uint4* lo = reinterpret_cast<uint4*>(st + op * 2 * kG3OpBytes + kG3OpBytes);
+#pragma unroll
+          for (uint32_t k = t; k < kG3OpBytes / 16; k += kG3SplitWarps * 32) {
+            const uint4 v = hi[k];
+            uint4 l;
+            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xffffe000u));
+            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xffffe000u));
+            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xffffe000u));
+            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xffffe000u));
+            lo[k] = l;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ready(s));
+      }
+    }
+  } else {
+    // ---- epilogue: warp (quarter, half) drains TMEM lanes [32*quarter, +32) x columns [64*half, +64) in two 32-column groups
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const bool is_issuer = quarter == ((2 + 4 * half) & 3) && lane == 0;     // first warp of each half
+    uint8_t* my_stage = out_stage + half * kG3OutBytes;
+    const int row_in_tile = quarter * 32 + lane;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      int split, tm, tn;
+      decode(item, split, tm, tn);
+      const int a = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int m = tm * kG3Tile + row_in_tile;
+      const bool masked = row_mask != nullptr && m < M && row_mask[m] != 0;
+      mbar_wait(bar_tfull(a), aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t lane_base = tmem_base + a * 128u + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int g = 0; g < 2; ++g) {
+        const int col0 = half * 64 + g * 32;                                // column of the tile
+        const int n0 = tn * kG3Tile + col0;
+        if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile free again
+        named_bar_sync(1 + half, 128);
+        float v[32];
+        tmem_ld32(lane_base + static_cast<uint32_t>(col0), v);
+        if (bias != nullptr && split == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += (n0 + j < N) ? __ldg(bias + n0 + j) : 0.f;
+        }
+        if (masked) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        // staging tile [128 rows][32 columns] in the 128B-swizzle layout of the output map: conflict-free 16-byte stores
+        uint8_t* row = my_stage + row_in_tile * 128;
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16)
+          *reinterpret_cast<float4*>(row + ((c16 ^ (row_in_tile & 7)) * 16)) = make_float4(v[4 * c16], v[4 * c16 + 1], v[4 * c16 + 2], v[4 * c16 + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        named_bar_sync(1 + half, 128);
+        if (is_issuer && n0 < N) {
+          if (reduce) tma_reduce_add_3d(&map_c, smem_u32(my_stage), n0, tm * kG3Tile, 0);
+          else tma_store_3d(&map_c, smem_u32(my_stage), n0, tm * kG3Tile, 0);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty(a));
+    }
+    if (is_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+}
+
+constexpr size_t kG3SmemBytes = 1024 + kG3Stages * kG3StageBytes + 2 * kG3OutBytes;
+
+}  // namespace msda

@@ -8,6 +8,7 @@
 #include "mask_tc.cuh"
 #include "mask_tc4.cuh"
 #include "mask_tc_bwd.cuh"
+#include "gemm3x.cuh"
 #include "msda_internal.h"
 
 namespace msda {
@@ -416,6 +417,85 @@ int mask_backward_dispatch(cudaStream_t st, int dtype, const void* coeff, const 
     mask_grad_proto_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(coeff), static_cast<const float*>(grad_out),
                                                  static_cast<float*>(grad_proto), Q, K, Ncols);
     if (int rc = after_launch("mask_grad_proto_kernel")) return rc;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ Linear layers (3xTF32 GEMM, gemm3x.cuh)
+// fp32 [d1][d0] matrix (d0 contiguous), box {32 columns, 128 rows}, 128B swizzle: output tiles of gemm3x_kernel
+static int make_map_c(CUtensorMap* map, void* base, uint64_t d0, uint64_t d1) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
+  if (!enc) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[3] = {d0, d1, 1};
+  const cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
+  const cuuint32_t box[3] = {32, kG3Tile, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled(gemm out) failed (CUresult %d)", static_cast<int>(r));
+  return 0;
+}
+
+// C[M x N] (+)= A * B.  a_mn: A is stored [K][M] (else [M][K]); b_mn: B is stored [K][N] (else [N][K]).  splits > 1: the reduction
+// is cut into `splits` ranges whose partial tiles are added into C (which must be zero) with TMA reduce-add stores.
+template <bool kAMn, bool kBMn>
+static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const void* Bm, void* C, int64_t M, int64_t N, int64_t K,
+                         const float* bias, const unsigned char* row_mask, int splits) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n_kchunks = static_cast<int>((K + 31) / 32);
+  const int tiles_m = static_cast<int>((M + kG3Tile - 1) / kG3Tile), tiles_n = static_cast<int>((N + kG3Tile - 1) / kG3Tile);
+  if (splits < 1) splits = 1;
+  if (splits > n_kchunks) splits = n_kchunks;
+  const int cps = (n_kchunks + splits - 1) / splits;
+  splits = (n_kchunks + cps - 1) / cps;
+  const int64_t n_items = (int64_t)tiles_m * tiles_n * splits;
+  if (n_items >= (int64_t(1) << 31)) return fail(MSDA_ERR_UNSUPPORTED, "%s: too many tiles", who);
+  CUtensorMap map_a, map_b, map_c;
+  if (kAMn) { if (int rc = make_map_mn_f32(&map_a, A, (uint64_t)M, (uint64_t)K, 1)) return rc; }
+  else { if (int rc = make_map_in(&map_a, A, true, (uint64_t)K, (uint64_t)M, 1, kG3Tile)) return rc; }
+  if (kBMn) { if (int rc = make_map_mn_f32(&map_b, Bm, (uint64_t)N, (uint64_t)K, 1)) return rc; }
+  else { if (int rc = make_map_in(&map_b, Bm, true, (uint64_t)K, (uint64_t)N, 1, kG3Tile)) return rc; }
+  if (int rc = make_map_c(&map_c, C, (uint64_t)N, (uint64_t)M)) return rc;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(gemm3x_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes);
+    cudaFuncSetAttribute(gemm3x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes);
+    cudaFuncSetAttribute(gemm3x_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes);
+  });
+  const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);
+  gemm3x_kernel<kAMn, kBMn><<<grid, kG3Threads, kG3SmemBytes, st>>>(map_a, map_b, map_c, bias, row_mask, (int)M, (int)N, n_kchunks, cps,
+                                                                   tiles_m, tiles_n, (int)n_items, splits > 1 ? 1 : 0);
+  return after_launch("gemm3x_kernel");
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int linear_forward_dispatch(cudaStream_t st, const void* x, const void* w, const void* bias, const unsigned char* row_mask,
+                            int64_t rows, int in_f, int out_f, void* y) {
+  if (rows >= (int64_t(1) << 31) - kG3Tile) return fail(MSDA_ERR_UNSUPPORTED, "tc_linear_forward: rows=%lld too large", (long long)rows);
+  if (in_f % 4 != 0 || out_f % 4 != 0 || !aligned16(x) || !aligned16(w) || !aligned16(y))
+    return fail(MSDA_ERR_UNSUPPORTED, "tc_linear_forward: in_features / out_features must be multiples of 4 and the tensors 16-byte aligned");
+  if (rows == 0) return 0;
+  return launch_gemm3x<false, false>(st, "tc_linear_forward", x, w, y, rows, out_f, in_f, static_cast<const float*>(bias), row_mask, 1);
+}
+
+int linear_backward_dispatch(cudaStream_t st, const void* gy, const void* x, const void* w, int64_t rows, int in_f, int out_f,
+                             void* gx, void* gw) {
+  if (rows >= (int64_t(1) << 31) - kG3Tile) return fail(MSDA_ERR_UNSUPPORTED, "tc_linear_backward: rows=%lld too large", (long long)rows);
+  if (in_f % 4 != 0 || out_f % 4 != 0 || !aligned16(gy) || (gx && (!aligned16(gx) || !aligned16(w))) || (gw && (!aligned16(gw) || !aligned16(x))))
+    return fail(MSDA_ERR_UNSUPPORTED, "tc_linear_backward: in_features / out_features must be multiples of 4 and the tensors 16-byte aligned");
+  if (gw)
+    if (int rc = check_cuda(cudaMemsetAsync(gw, 0, (size_t)out_f * in_f * sizeof(float), st), "cudaMemsetAsync(grad_weight)")) return rc;
+  if (rows == 0) return 0;
+  if (gx)                                                   // dx[r, i] = sum_o dy[r, o] W[o, i]
+    if (int rc = launch_gemm3x<false, true>(st, "tc_linear_backward", gy, w, gx, rows, in_f, out_f, nullptr, nullptr, 1)) return rc;
+  if (gw) {                                                 // dW[o, i] = sum_r dy[r, o] x[r, i]: reduction over the rows, split across the SMs
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int tiles = ((out_f + kG3Tile - 1) / kG3Tile) * ((in_f + kG3Tile - 1) / kG3Tile);
+    int splits = (sms + tiles - 1) / tiles;
+    if (int rc = launch_gemm3x<true, true>(st, "tc_linear_backward", gy, x, gw, out_f, in_f, rows, nullptr, nullptr, splits)) return rc;
   }
   return 0;
 }

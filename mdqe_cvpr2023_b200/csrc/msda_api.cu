@@ -512,6 +512,20 @@ int mask_logits_backward(void* stream, int dtype, const void* coeff, const void*
   return mask_backward_dispatch(static_cast<cudaStream_t>(stream), dtype, coeff, proto, grad_out, B, Q, K, Ncols, grad_coeff, grad_proto);
 }
 
+int tc_linear_forward(void* stream, const void* x, const void* weight, const void* bias, const unsigned char* row_mask,
+                      int64_t rows, int in_features, int out_features, void* y) {
+  if (rows < 0 || in_features <= 0 || out_features <= 0) return fail(MSDA_ERR_INVALID_ARG, "tc_linear_forward: bad sizes");
+  if (rows > 0 && (!x || !weight || !y)) return fail(MSDA_ERR_INVALID_ARG, "tc_linear_forward: NULL tensor");
+  return linear_forward_dispatch(static_cast<cudaStream_t>(stream), x, weight, bias, row_mask, rows, in_features, out_features, y);
+}
+
+int tc_linear_backward(void* stream, const void* grad_y, const void* x, const void* weight, int64_t rows, int in_features,
+                       int out_features, void* grad_x, void* grad_weight) {
+  if (rows < 0 || in_features <= 0 || out_features <= 0) return fail(MSDA_ERR_INVALID_ARG, "tc_linear_backward: bad sizes");
+  if (rows > 0 && (!grad_y || (grad_x && !weight) || (grad_weight && !x))) return fail(MSDA_ERR_INVALID_ARG, "tc_linear_backward: NULL tensor");
+  return linear_backward_dispatch(static_cast<cudaStream_t>(stream), grad_y, x, weight, rows, in_features, out_features, grad_x, grad_weight);
+}
+
 // ------------------------------------------------------------------------------- host-buffer entries
 // Three streams form a pipeline per call: H2D copies -> kernels -> D2H copies, chained with events.  In the default
 // synchronous mode a call returns when its results are in host memory.  With option "host_async" = 1 calls only

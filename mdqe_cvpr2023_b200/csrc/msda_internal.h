@@ -41,6 +41,11 @@ int mask_forward_dispatch(cudaStream_t stream, int in_dtype, int out_dtype, cons
 int mask_backward_dispatch(cudaStream_t stream, int dtype, const void* coeff, const void* proto, const void* grad_out,
                            int B, int Q, int K, int64_t Ncols, void* grad_coeff, void* grad_proto);
 
+int linear_forward_dispatch(cudaStream_t stream, const void* x, const void* w, const void* bias, const unsigned char* row_mask,
+                            int64_t rows, int in_f, int out_f, void* y);
+int linear_backward_dispatch(cudaStream_t stream, const void* gy, const void* x, const void* w, int64_t rows, int in_f, int out_f,
+                             void* gx, void* gw);
+
 inline size_t dtype_size(int dtype) {
   switch (dtype) {
     case MSDA_F32: return 4;

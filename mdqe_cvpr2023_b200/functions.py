@@ -114,3 +114,28 @@ def mask_logits(coeff, proto):
     if coeff.dim() == 2:
         return _MaskLogitsFunction.apply(coeff.unsqueeze(0).contiguous(), proto.unsqueeze(0).contiguous()).squeeze(0)
     return _MaskLogitsFunction.apply(coeff.contiguous(), proto.contiguous())
+
+
+class _TcLinearFunction(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, row_mask):
+        ctx.save_for_backward(x, weight, row_mask)
+        ctx.has_bias = bias is not None
+        return ops.tc_linear_forward(x, weight, bias, row_mask)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_y):
+        x, weight, row_mask = ctx.saved_tensors
+        grad_y = grad_y.contiguous()
+        if row_mask is not None:
+            grad_y = grad_y.masked_fill(row_mask.unsqueeze(-1), 0.0)
+        gx, gw = ops.tc_linear_backward(grad_y, x, weight, need_x=ctx.needs_input_grad[0], need_weight=ctx.needs_input_grad[1])
+        gb = grad_y.reshape(-1, grad_y.shape[-1]).sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb, None
+
+
+def tc_linear(x, weight, bias=None, row_mask=None):
+    """``F.linear(x, weight, bias)`` (optionally followed by ``masked_fill(row_mask[..., None], 0)``) on the tensor cores in
+    3xTF32 -- fp32-level accuracy without the fp32 SIMT GEMM (ms_deform_attn.py:136-138, :143-146, :157, :171)."""
+    return _TcLinearFunction.apply(x.contiguous(), weight.contiguous(), bias, row_mask.contiguous() if row_mask is not None else None)

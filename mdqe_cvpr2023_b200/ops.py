@@ -281,3 +281,58 @@ def mask_logits_backward(coeff, proto, grad_out, need_coeff=True, need_proto=Tru
                                       gp.data_ptr() if gp is not None else None)
     _lib.check(rc, who)
     return gc, gp
+
+
+def linear_supported(x, weight):
+    """The tensor-core Linear needs fp32 CUDA tensors with in/out features that are multiples of 4."""
+    return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and weight.dim() == 2
+            and weight.shape[0] % 4 == 0 and weight.shape[1] % 4 == 0 and x.shape[-1] == weight.shape[1])
+
+
+def tc_linear_forward(x, weight, bias=None, row_mask=None):
+    """y = x @ weight.T + bias with rows where ``row_mask`` is True zeroed -- ``F.linear`` (+ ``masked_fill(mask[..., None], 0)``,
+    ms_deform_attn.py:136-138) as one 3xTF32 tensor-core GEMM.  x [..., in], weight [out, in], row_mask [...] bool."""
+    who = "tc_linear_forward"
+    tensors = [("x", x), ("weight", weight)]
+    if bias is not None:
+        tensors.append(("bias", bias))
+    if row_mask is not None:
+        tensors.append(("row_mask", row_mask))
+    _check_inputs(who, tensors)
+    if x.dtype != torch.float32 or weight.dtype != torch.float32 or (bias is not None and bias.dtype != torch.float32):
+        raise RuntimeError(f"{who}: fp32 tensors expected")
+    out_f, in_f = weight.shape
+    if x.shape[-1] != in_f or (bias is not None and tuple(bias.shape) != (out_f,)):
+        raise RuntimeError(f"{who}: shape mismatch x{tuple(x.shape)} weight{tuple(weight.shape)}")
+    rows = x.numel() // max(in_f, 1)
+    mask8 = None
+    if row_mask is not None:
+        if row_mask.numel() != rows:
+            raise RuntimeError(f"{who}: row_mask must have one entry per row of x")
+        mask8 = row_mask.view(torch.uint8) if row_mask.dtype == torch.bool else row_mask.to(torch.uint8)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        y = torch.empty(x.shape[:-1] + (out_f,), dtype=torch.float32, device=x.device)
+        rc = lib.tc_linear_forward(_stream_ptr(x.device), x.data_ptr(), weight.data_ptr(),
+                                   bias.data_ptr() if bias is not None else None,
+                                   mask8.data_ptr() if mask8 is not None else None, rows, in_f, out_f, y.data_ptr())
+    _lib.check(rc, who)
+    return y
+
+
+def tc_linear_backward(grad_y, x, weight, need_x=True, need_weight=True):
+    """(grad_x, grad_weight) of y = x @ weight.T; grad_y must already carry the row mask (masked rows zero)."""
+    who = "tc_linear_backward"
+    _check_inputs(who, [("grad_y", grad_y), ("x", x), ("weight", weight)])
+    out_f, in_f = weight.shape
+    rows = x.numel() // max(in_f, 1)
+    if grad_y.numel() != rows * out_f:
+        raise RuntimeError(f"{who}: grad_y{tuple(grad_y.shape)} does not match x{tuple(x.shape)} / weight{tuple(weight.shape)}")
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        gx = torch.empty_like(x) if need_x else None
+        gw = torch.empty_like(weight) if need_weight else None
+        rc = lib.tc_linear_backward(_stream_ptr(x.device), grad_y.data_ptr(), x.data_ptr(), weight.data_ptr(), rows, in_f, out_f,
+                                    gx.data_ptr() if gx is not None else None, gw.data_ptr() if gw is not None else None)
+    _lib.check(rc, who)
+    return gx, gw

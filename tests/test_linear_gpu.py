@@ -1,0 +1,46 @@
+"""Tensor-core Linear (3xTF32 GEMM, csrc/gemm3x.cuh) against F.linear in fp64: forward with bias / row mask, dgrad, wgrad.
+Tolerance: 1e-4 normalised as for every fp32 kernel of the path (asserted 2e-5)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.helpers import nerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rows,in_f,out_f", [(4 * 5100, 256, 256), (4 * 5100, 256, 128), (784, 256, 256), (3 * 5100, 192, 192),
+                                             (3 * 5100, 192, 96), (1, 256, 256), (130, 36, 20), (257, 8, 300), (1000, 260, 4)])
+def test_tc_linear_vs_fp64(rows, in_f, out_f):
+    from mdqe_cvpr2023_b200 import tc_linear
+    g = torch.Generator(device="cuda").manual_seed(rows + in_f)
+    x = torch.randn(rows, in_f, device="cuda", generator=g, requires_grad=True)
+    w = (torch.randn(out_f, in_f, device="cuda", generator=g) / in_f ** 0.5).requires_grad_(True)
+    b = torch.randn(out_f, device="cuda", generator=g, requires_grad=True)
+    mask = torch.rand(rows, device="cuda", generator=g) < 0.1
+    gy = torch.randn(rows, out_f, device="cuda", generator=g)
+    y = tc_linear(x, w, b, mask)
+    y.backward(gy)
+    xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    yd = F.linear(xd, wd, bd).masked_fill(mask[:, None], 0.0)
+    yd.backward(gy.double())
+    assert nerr(y, yd) < 2e-5
+    assert nerr(x.grad, xd.grad) < 2e-5
+    assert nerr(w.grad, wd.grad) < 2e-5
+    assert nerr(b.grad, bd.grad) < 2e-5
+    # no bias, no mask, leading batch dims
+    x3 = x.detach().view(1, rows, in_f) if rows % 2 else x.detach().view(2, rows // 2, in_f)
+    y2 = tc_linear(x3, w.detach())
+    assert y2.shape == x3.shape[:-1] + (out_f,)
+    assert nerr(y2.reshape(rows, out_f), F.linear(x.detach().double(), w.detach().double())) < 2e-5
+
+
+def test_tc_linear_rejects_unsupported():
+    from mdqe_cvpr2023_b200 import ops
+    x = torch.randn(8, 6, device="cuda")
+    w = torch.randn(4, 6, device="cuda")
+    assert not ops.linear_supported(x, w)
+    with pytest.raises(RuntimeError, match="multiples of 4"):
+        ops.tc_linear_forward(x, w)
+    with pytest.raises(RuntimeError, match="CPU"):
+        ops.tc_linear_forward(torch.randn(8, 8), torch.randn(8, 8))
