@@ -14,7 +14,10 @@ What differs from the reference implementation (not from its results):
     "frame t of level l" in level_start_index (= t*S + start_l) instead of materialising four
     `.contiguous()` copies per call (ms_deform_attn.py:222-224); on the fast-kernel configurations all
     pyramid levels run in ONE launch (MSDeformAttnGroupedFunction) with the mean folded in;
-  * all tensor work below the Linear layers goes through MSDeformAttnFunction -> libmsda_b200.so.
+  * all tensor work below the Linear layers goes through MSDeformAttnFunction -> libmsda_b200.so;
+  * the four Linear layers themselves (value_proj + masked_fill, offsets, attention weights, output_proj) run as 3xTF32
+    tensor-core GEMMs (`tc_linear`, csrc/gemm3x.cuh) when `self.tc_linear` is set (default) and the tensors are fp32 on CUDA
+    -- same parameters, fp32-level accuracy, 2.7-4x less GPU time than the fp32 SGEMMs.
 """
 import math
 import warnings
@@ -24,7 +27,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnGroupedFunction
+from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnGroupedFunction, tc_linear
 
 
 def _is_power_of_2(n):
@@ -57,6 +60,7 @@ class MSDeformAttn(nn.Module):
         # fold softmax + sampling-location arithmetic into the sampler kernel where it is implemented (fp32, D in
         # {32,24}, L*P in {8,16}, reference points without gradient); set False to run the reference's op sequence
         self.fused_prologue = True
+        self.tc_linear = True
 
         # what the operator sees as "levels": pyramid levels of a frame, or the frames of a clip
         if mode == 'spatial':
@@ -103,23 +107,32 @@ class MSDeformAttn(nn.Module):
         nn.init.constant_(self.output_proj.bias.data, 0.)
 
     # ---------------------------------------------------------------------------------- pieces
+    def _linear(self, layer, x, row_mask=None):
+        """layer(x) (+ masked_fill of the rows selected by row_mask) -- on the tensor cores when possible."""
+        if self.tc_linear and ops.linear_supported(x, layer.weight) and not torch.is_autocast_enabled():
+            return tc_linear(x, layer.weight, layer.bias, row_mask)
+        y = layer(x)
+        if row_mask is not None:
+            y = y.masked_fill(row_mask[..., None], float(0))
+        return y
+
     def _sampling(self, query, reference_points):
         """-> (sampling_locations [B,Q,H,L,K,2], attention_weights [B,Q,H,L,K]) for L = self.lvl."""
         B, Q, _ = query.shape
         H, L, K = self.n_heads, self.lvl, self.n_points
         ref = reference_points.view(B, Q, 1, 1, 1, -1)
         if self.pred_offsets:
-            offsets = self.sampling_offsets(query).view(B, Q, H, L, K, 2)
+            offsets = self._linear(self.sampling_offsets, query).view(B, Q, H, L, K, 2)
         else:
             # fixed ray grid scaled to half the reference box, plus a learned residual clamped to +-8 boxes
             box = ref[..., 2:]
-            residual = self.sampling_grid_offsets(query).view(B, Q, H, L, K, 2).to(ref)
+            residual = self._linear(self.sampling_grid_offsets, query).view(B, Q, H, L, K, 2).to(ref)
             bound = box * self.scale
             residual = torch.where(residual > -bound, residual, -bound)
             residual = torch.where(residual < bound, residual, bound)
             offsets = self.sampling_offsets * 0.5 * box + residual
         locations = ref[..., :2] + offsets / self.scale
-        logits = self.attention_weights(query).view(B, Q, H, L * K)
+        logits = self._linear(self.attention_weights, query).view(B, Q, H, L * K)
         weights = F.softmax(logits, -1).view(B, Q, H, L, K)
         return locations, weights
 
@@ -128,15 +141,13 @@ class MSDeformAttn(nn.Module):
         B, Q, _ = query.shape
         H, L, K = self.n_heads, self.lvl, self.n_points
         lin = self.sampling_offsets if self.pred_offsets else self.sampling_grid_offsets
-        offsets = lin(query).view(B, Q, H, L, K, 2)
-        logits = self.attention_weights(query).view(B, Q, H, L * K)
+        offsets = self._linear(lin, query).view(B, Q, H, L, K, 2)
+        logits = self._linear(self.attention_weights, query).view(B, Q, H, L * K)
         grid = None if self.pred_offsets else self.sampling_offsets.reshape(H, L, K, 2).contiguous()
         return offsets, logits, grid, (0 if self.pred_offsets else 1)
 
     def _project_value(self, input_flatten, input_padding_mask):
-        value = self.value_proj(input_flatten)
-        if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask[..., None], float(0))
+        value = self._linear(self.value_proj, input_flatten, input_padding_mask)
         return value.view(*value.shape[:-1], self.n_heads, self.d_model // self.n_heads)
 
     @staticmethod
@@ -173,11 +184,11 @@ class MSDeformAttn(nn.Module):
             offsets, logits, grid, mode = self._fused_inputs(query)
             sampled = MSDeformAttnFusedFunction.apply(value, shapes_c, level_start,
                                                       reference_points.contiguous(), offsets, logits, grid, mode, self.scale, 1.0)
-            return self.output_proj(sampled)
+            return self._linear(self.output_proj, sampled)
         locations, weights = self._sampling(query, reference_points)
         sampled = MSDeformAttnFunction.apply(value.contiguous(), shapes_c, level_start,
                                              locations.contiguous(), weights.contiguous(), self.im2col_step)
-        return self.output_proj(sampled)
+        return self._linear(self.output_proj, sampled)
 
     @torch.amp.autocast("cuda", enabled=False)
     def temporal_clip_forward(self, query, reference_points, input_flatten, input_spatial_shapes,
@@ -194,17 +205,17 @@ class MSDeformAttn(nn.Module):
             offsets, logits, grid, mode = self._fused_inputs(query)
             sampled = MSDeformAttnFusedFunction.apply(value, shapes_g, starts_g, reference_points.contiguous(), offsets, logits,
                                                       grid, mode, self.scale, 1.0 / n_lvl)
-            return self.output_proj(sampled)
+            return self._linear(self.output_proj, sampled)
         locations, weights = self._sampling(query, reference_points)
         locations, weights = locations.contiguous(), weights.contiguous()
         if ops.grouped_supported(value, n_lvl, T, self.n_points):
             # all pyramid levels in ONE launch: level table g = the T frames of pyramid level g, mean folded in
             sampled = MSDeformAttnGroupedFunction.apply(value, shapes_g, starts_g, locations, weights, 1.0 / n_lvl)
-            return self.output_proj(sampled)
+            return self._linear(self.output_proj, sampled)
         sampled = None
         for lvl in range(n_lvl):
             shapes_l, starts_l = shapes_g[lvl], starts_g[lvl]
             out_l = MSDeformAttnFunction.apply(value, shapes_l, starts_l, locations, weights, self.im2col_step)
             sampled = out_l if sampled is None else sampled + out_l
         sampled = sampled / input_spatial_shapes.shape[0]
-        return self.output_proj(sampled)
+        return self._linear(self.output_proj, sampled)

@@ -24,19 +24,42 @@ def test_l0_extension_module_name_and_signatures():
         assert nerr(g, z[k]) < 2e-5
 
 
+@pytest.mark.parametrize("tc_linear", [False, True])
 @pytest.mark.parametrize("name", ["module_spatial_pred", "module_spatial_grid", "module_temporal_grid"])
-def test_l2_module_matches_reference_module(name):
+def test_l2_module_matches_reference_module(name, tc_linear):
+    """Output, input gradients and every parameter gradient against fixtures recorded from the unmodified reference module.
+    tc_linear=False keeps the Linear layers on torch (bit-comparable sampling locations); tc_linear=True (the default) runs them
+    as 3xTF32 GEMMs, whose ~1e-6 differences can move a sample across a pixel-centre line, where grad_sampling_loc is
+    discontinuous: when that happens the offset-branch gradients are held to 5e-3 instead of 1e-4."""
     from mdqe_cvpr2023_b200 import MSDeformAttn
     z = load_golden(name)
     mod = module_from_golden(z, MSDeformAttn).cuda()
+    mod.tc_linear = tc_linear
     query, ref, inp, shapes, mask = module_inputs(z, "cuda")
     out = mod(query, ref, inp, shapes, mask)
     assert nerr(out, z["out"]) <= 1e-4
     out.backward(torch.from_numpy(z["grad_out"]).cuda())
-    assert nerr(query.grad, z["grad_query"]) <= 1e-4
+    flipped = False
+    if tc_linear:                                  # did any sample change its bilinear cell relative to the torch Linear path?
+        with torch.no_grad():
+            q2 = query.detach()
+            loc_tc, _ = mod._sampling(q2, ref)
+            mod.tc_linear = False
+            loc_th, _ = mod._sampling(q2, ref)
+            mod.tc_linear = True
+            sizes = shapes.flip(-1).to(loc_tc.dtype)          # (W, H) per level
+            if loc_tc.shape[3] == sizes.shape[0]:
+                cell = lambda loc: torch.floor(loc * sizes.view(1, 1, 1, -1, 1, 2) - 0.5)
+                flipped = bool((cell(loc_tc) != cell(loc_th)).any())
+            else:                                               # temporal mode: every pyramid level is sampled with the same loc
+                flipped = any(bool((torch.floor(loc_tc * wh.view(1, 1, 1, 1, 1, 2) - 0.5) != torch.floor(loc_th * wh.view(1, 1, 1, 1, 1, 2) - 0.5)).any())
+                              for wh in sizes)
+    kink_tol = 5e-3 if flipped else 1e-4
+    assert nerr(query.grad, z["grad_query"]) <= kink_tol
     assert nerr(inp.grad, z["grad_input"]) <= 1e-4
     for k, p in mod.named_parameters():
-        assert nerr(p.grad, z["gp." + k]) <= 2e-4, k
+        tol = (5e-3 if flipped else 2e-4) if "offsets" in k else 2e-4
+        assert nerr(p.grad, z["gp." + k]) <= tol, k
 
 
 def test_module_r50_shape_runs_under_autocast():

@@ -1,8 +1,11 @@
 #!/usr/bin/env python
-"""Module-level timing: MSDeformAttn forward+backward at the R50_ovis_360 shapes, three ways:
-   fused    : this package's module, softmax/location arithmetic inside the kernel (+ grouped temporal launch)
+"""Module-level timing: MSDeformAttn forward+backward at the R50_ovis_360 shapes:
+   fused_tc : this package's module: softmax/location arithmetic inside the kernel, grouped temporal launch, Linear layers as
+              3xTF32 tensor-core GEMMs (the default configuration)
+   fused    : the same with the Linear layers on torch (cuBLAS fp32, TF32 off like the reference)
    unfused  : this package's module running the reference's op sequence on our kernels
    refcuda  : the same op sequence on the reference's own CUDA extension (oracle/_ref), per-level loop + .contiguous()
+each eager (host dispatch included) and, `*_graph_us`, as a replayed CUDA graph of the whole forward+backward (GPU time only).
 Writes gpurun_out/module_bench.json."""
 import json
 import os
@@ -32,7 +35,23 @@ def timed(fn, iters=20):
     return a.elapsed_time(b) / iters * 1e3
 
 
+def timed_graph(step, iters=20):
+    """capture forward+backward once, time replays"""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step()
+    return timed(g.replay, iters)
+
+
 def main():
+    torch.backends.cuda.matmul.allow_tf32 = False
     ref_ext = None
     try:
         from oracle import build_ref_cuda
@@ -60,11 +79,18 @@ def main():
             mod.zero_grad(set_to_none=True)
             q.grad = x.grad = None
             mod(q, ref, x, shapes, None).sum().backward()
+        def step_graph():                              # same work without python-side grad resets (static graph memory)
+            return torch.autograd.grad(mod(q, ref, x, shapes, None).sum(), (q, x) + tuple(mod.parameters()))
         row = {}
-        mod.fused_prologue = True
+        mod.fused_prologue, mod.tc_linear = True, True
+        row["fused_tc_us"] = timed(step)
+        row["fused_tc_graph_us"] = timed_graph(step_graph)
+        mod.tc_linear = False
         row["fused_us"] = timed(step)
+        row["fused_graph_us"] = timed_graph(step_graph)
         mod.fused_prologue = False
         row["unfused_us"] = timed(step)
+        row["unfused_graph_us"] = timed_graph(step_graph)
         if ref_ext is not None:
             # reference op sequence on the reference kernels: plain Function per level with .contiguous() copies
             class RefFn(torch.autograd.Function):
@@ -86,7 +112,7 @@ def main():
             finally:
                 M.MSDeformAttnFunction = orig_fn
                 M.ops.grouped_supported = orig_grouped
-        mod.fused_prologue = True
+        mod.fused_prologue, mod.tc_linear = True, True
         res[name] = row
         print(name, {k: round(v, 1) for k, v in row.items()}, flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
