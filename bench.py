@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--layers", type=int, default=N_LAYERS, help="debug: fewer layers (the result is then not a valid bench value)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-legacy", action="store_true", help="time the first-generation host path (A/B)")
+    ap.add_argument("--e2e-sync-every-step", action="store_true", help="drain the host pipeline after every step instead of keeping two steps in flight (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     return ap.parse_args()
@@ -595,14 +596,34 @@ def main():
     if not args.no_e2e:
         host = HostStep(torch, lib, libmod, calls, mask, local_rank, args.dtype, legacy=args.e2e_legacy)
         libmod.set_option("host_async", 1)           # calls enqueue on the library's H2D / compute / D2H streams ...
-        host.run()                                   # warm-up: arena allocation, page faults
+        import ctypes
+
+        def fence():
+            t = ctypes.c_int64(0)
+            libmod.check(lib.msda_host_fence(ctypes.byref(t)), "msda_host_fence")
+            return t.value
+
+        def e2e_steps(n):
+            # ... every step ends with a fence, and a step's ticket is waited for (all its results in host memory) while the NEXT
+            # step is already enqueued: at most two steps in flight, like a trainer that prefetches the next clip.  Step i+1's
+            # forward uploads then run under step i's backward downloads (PCIe full duplex across the step boundary).
+            prev = None
+            for _ in range(n):
+                host.run()
+                t = fence()
+                if args.e2e_sync_every_step:
+                    libmod.check(lib.msda_host_sync(), "msda_host_sync")
+                elif prev is not None:
+                    libmod.check(lib.msda_host_wait(prev), "msda_host_wait")
+                prev = t
+            libmod.check(lib.msda_host_wait(prev), "msda_host_wait")
+
+        e2e_steps(3)                                 # warm-up: arena allocation, saved-block pool for two steps in flight, page faults
         libmod.check(lib.msda_host_sync(), "msda_host_sync")
-        n_e2e = max(1, min(args.steps, 5))
+        n_e2e = max(1, min(args.steps, 10))
         sync_all()
         t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            host.run()
-            libmod.check(lib.msda_host_sync(), "msda_host_sync")     # ... and every step ends with all results in host memory
+        e2e_steps(n_e2e)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         libmod.set_option("host_async", 0)
@@ -611,7 +632,9 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": world * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": host.h2d, "d2h_bytes_per_step": host.d2h,
-               "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3, "timing": "wall clock; *_host C-ABI calls in host_async mode (3-stream pipeline), msda_host_sync() at the end of every step",
+               "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3, "timing": ("wall clock; *_host C-ABI calls in host_async mode (3-stream pipeline), msda_host_sync() at the end of every step" if args.e2e_sync_every_step else
+                          "wall clock over all steps; *_host C-ABI calls in host_async mode (3-stream pipeline); every step ends with msda_host_fence() and is "
+                          "waited for (msda_host_wait: all its results in host memory) while the next step is enqueued -- at most two steps in flight"),
                "note": ("first-generation host path: every call re-uploads its inputs, per-level temporal calls, no mask backward" if args.e2e_legacy else
                         "same launches as the device step; forward inputs stay on the device for the backward (*_host_saved entries)")}
         lib.msda_host_arena_release()

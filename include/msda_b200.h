@@ -183,6 +183,14 @@ int mask_logits_forward_host(int device, int in_dtype, int out_dtype,
  * (upload, kernels and download of consecutive calls overlap on three streams; PCIe runs full duplex); host output
  * buffers are valid, and host input buffers may be reused, only after msda_host_sync().  Returns the first error. */
 int msda_host_sync(void);
+/* Finer-grained completion for callers that keep several steps in flight (a data-parallel trainer prefetching the next
+ * clip: the uploads of step i+1's forward then run under the downloads of step i's backward and PCIe stays full duplex
+ * across step boundaries).  msda_host_fence() marks everything enqueued so far and returns a ticket;
+ * msda_host_wait(ticket) returns once all of that work's results are in host memory (its host input buffers may be
+ * reused, its staging space in the device arena is recycled).  Tickets complete in order; ticket 0 is always complete;
+ * msda_host_sync() completes every outstanding ticket. */
+int msda_host_fence(int64_t* ticket);
+int msda_host_wait(int64_t ticket);
 
 /* "Saved" host entries: the host-buffer counterpart of autograd's save_for_backward (ms_deform_attn_func.py:28-29 saves
  * value, shapes, level_start_index, loc and aw on the device between forward and backward).  The forward keeps the device

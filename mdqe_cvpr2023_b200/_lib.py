@@ -8,7 +8,8 @@ import ctypes
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libmsda_b200.so")
+# MSDA_B200_LIB: experiment builds only (tools/whatif_bench.py); the product library is always the in-tree one
+LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(PKG_DIR, "libmsda_b200.so")
 
 MSDA_F32, MSDA_BF16, MSDA_F64, MSDA_BF16_LOC32 = 0, 1, 2, 3
 ABI_VERSION = 2
@@ -42,6 +43,8 @@ PROTOTYPES = {
                            + [_c_vp, _c_vp, _c_vp]),
     "mask_logits_forward_host": (_c_int, [_c_int, _c_int, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_vp]),
     "msda_host_sync": (_c_int, []),
+    "msda_host_fence": (_c_int, [ctypes.POINTER(_c_i64)]),
+    "msda_host_wait": (_c_int, [_c_i64]),
     "msda_forward_host_saved": (_c_int, [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + [_c_int] * 8
                                 + [ctypes.c_float, _c_vp, ctypes.POINTER(_c_i64)]),
     "msda_backward_host_saved": (_c_int, [_c_i64, _c_vp, _c_vp, _c_vp, _c_vp]),

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <type_traits>
 #include <vector>
@@ -305,6 +306,9 @@ using namespace msda;
 extern "C" {
 
 int msda_abi_version(void) { return MSDA_B200_ABI_VERSION; }
+#ifdef MSDA_DBG_MASK
+int msda_debug_set_mask(int mask) { return check_cuda(cudaMemcpyToSymbol(g_dbg_mask, &mask, sizeof(int)), "msda_debug_set_mask"); }
+#endif
 const char* msda_last_error(void) { return t_err; }
 
 int msda_set_option(const char* key, int value) {
@@ -531,12 +535,19 @@ int tc_linear_backward(void* stream, const void* grad_y, const void* x, const vo
 // synchronous mode a call returns when its results are in host memory.  With option "host_async" = 1 calls only
 // enqueue (device buffers are bump-allocated from the arena and stay live until msda_host_sync()), so the upload of
 // call i+1, the kernels of call i and the download of call i-1 overlap and PCIe runs full duplex.
+// The arena is a ring: msda_host_fence() marks "everything enqueued so far", msda_host_wait(ticket) blocks until that
+// work's results are in host memory and frees its part of the ring -- so a caller can keep two steps in flight (the
+// uploads of step i+1's forward run under the downloads of step i's backward) without ever draining the pipeline.
 namespace {
+struct HostFence { cudaEvent_t ev; size_t head; int64_t id; };
 struct HostPipe {
   std::mutex mu;
   int device = -1;
   char* base = nullptr;
-  size_t cap = 0, used = 0;
+  size_t cap = 0, head = 0, tail = 0;          // live bytes: [tail, head), wrapped when head < tail
+  std::deque<HostFence> fences;                // oldest first
+  std::vector<cudaEvent_t> fence_pool;
+  int64_t fence_next = 1, fence_done = 0;
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
   static constexpr int kEvents = 64;
   cudaEvent_t ev_in[kEvents] = {}, ev_run[kEvents] = {};
@@ -556,13 +567,46 @@ int pipe_drain() {
   if (g_pipe.s_in) rc |= check_cuda(cudaStreamSynchronize(g_pipe.s_in), "cudaStreamSynchronize(h2d)");
   if (g_pipe.s_run) rc |= check_cuda(cudaStreamSynchronize(g_pipe.s_run), "cudaStreamSynchronize(compute)");
   if (g_pipe.s_out) rc |= check_cuda(cudaStreamSynchronize(g_pipe.s_out), "cudaStreamSynchronize(d2h)");
-  g_pipe.used = 0;
+  g_pipe.head = g_pipe.tail = 0;
+  for (const HostFence& f : g_pipe.fences) { g_pipe.fence_pool.push_back(f.ev); g_pipe.fence_done = f.id; }
+  g_pipe.fences.clear();
   return rc ? MSDA_ERR_CUDA : 0;
+}
+
+// the oldest fence has completed (or is waited for): its part of the ring is free again
+int pipe_retire_oldest(bool block) {
+  HostFence& f = g_pipe.fences.front();
+  if (block) {
+    if (int rc = check_cuda(cudaEventSynchronize(f.ev), "cudaEventSynchronize(fence)")) return rc;
+  } else if (cudaEventQuery(f.ev) != cudaSuccess) {
+    cudaGetLastError();
+    return 1;                                            // still running
+  }
+  g_pipe.tail = f.head;
+  g_pipe.fence_done = f.id;
+  g_pipe.fence_pool.push_back(f.ev);
+  g_pipe.fences.pop_front();
+  if (g_pipe.fences.empty() && g_pipe.tail == g_pipe.head) g_pipe.head = g_pipe.tail = 0;
+  return 0;
+}
+
+bool pipe_try_alloc(size_t bytes, size_t* at) {
+  if (g_pipe.head >= g_pipe.tail) {
+    if (g_pipe.head + bytes <= g_pipe.cap) { *at = g_pipe.head; g_pipe.head += bytes; return true; }
+    if (bytes < g_pipe.tail) { *at = 0; g_pipe.head = bytes; return true; }       // wrap; the end of the ring stays unused this lap
+    return false;
+  }
+  if (g_pipe.head + bytes < g_pipe.tail) { *at = g_pipe.head; g_pipe.head += bytes; return true; }
+  return false;
 }
 
 void pipe_free() {
   if (g_pipe.base) { cudaFree(g_pipe.base); g_pipe.base = nullptr; }
-  g_pipe.cap = g_pipe.used = 0;
+  g_pipe.cap = g_pipe.head = g_pipe.tail = 0;
+  for (const HostFence& f : g_pipe.fences) cudaEventDestroy(f.ev);
+  g_pipe.fences.clear();
+  for (cudaEvent_t e : g_pipe.fence_pool) cudaEventDestroy(e);
+  g_pipe.fence_pool.clear();
   for (cudaStream_t* s : {&g_pipe.s_in, &g_pipe.s_run, &g_pipe.s_out})
     if (*s) { cudaStreamDestroy(*s); *s = nullptr; }
   for (int i = 0; i < HostPipe::kEvents; ++i) {
@@ -584,23 +628,26 @@ int pipe_reserve(int device, size_t bytes, size_t* at) {
     }
   }
   const bool async = g_opt.host_async.load() != 0;
-  if (!async) g_pipe.used = 0;                            // synchronous mode: the previous call has completed
-  if (g_pipe.used + bytes > g_pipe.cap) {
-    if (int rc = pipe_drain()) return rc;                 // nothing in flight any more, bump pointer back to 0
-    if (bytes > g_pipe.cap) {
-      if (g_pipe.base) { cudaFree(g_pipe.base); g_pipe.base = nullptr; g_pipe.cap = 0; }
-      // async: room for many calls in flight (a training clip's 73 calls stage ~7 GB; the part has 180 GB)
-      const size_t want = async ? (bytes * 8 > (size_t(8) << 30) ? bytes * 8 : (size_t(8) << 30)) : bytes + bytes / 4;
-      if (cudaMalloc(&g_pipe.base, want) == cudaSuccess) g_pipe.cap = want;
-      else {
-        cudaGetLastError();
-        if (int rc = check_cuda(cudaMalloc(&g_pipe.base, bytes), "cudaMalloc(host arena)")) return rc;
-        g_pipe.cap = bytes;
-      }
+  if (!async && g_pipe.fences.empty()) g_pipe.head = g_pipe.tail = 0;      // synchronous mode: the previous call has completed
+  bytes = (bytes + 255) & ~size_t(255);
+  if (pipe_try_alloc(bytes, at)) return 0;
+  while (!g_pipe.fences.empty()) {                        // ring full: completed fences first, then wait for the oldest ones
+    if (int rc = pipe_retire_oldest(true)) return rc;
+    if (pipe_try_alloc(bytes, at)) return 0;
+  }
+  if (int rc = pipe_drain()) return rc;                   // nothing in flight any more, ring empty
+  if (bytes > g_pipe.cap) {
+    if (g_pipe.base) { cudaFree(g_pipe.base); g_pipe.base = nullptr; g_pipe.cap = 0; }
+    // async: room for many calls in flight (a training clip's 73 calls stage ~7 GB; the part has 180 GB)
+    const size_t want = async ? (bytes * 8 > (size_t(8) << 30) ? bytes * 8 : (size_t(8) << 30)) : bytes + bytes / 4;
+    if (cudaMalloc(&g_pipe.base, want) == cudaSuccess) g_pipe.cap = want;
+    else {
+      cudaGetLastError();
+      if (int rc = check_cuda(cudaMalloc(&g_pipe.base, bytes), "cudaMalloc(host arena)")) return rc;
+      g_pipe.cap = bytes;
     }
   }
-  *at = g_pipe.used;
-  g_pipe.used += (bytes + 255) & ~size_t(255);
+  if (!pipe_try_alloc(bytes, at)) return fail(MSDA_ERR_CUDA, "host arena: cannot place %zu bytes", bytes);
   return 0;
 }
 
@@ -735,33 +782,57 @@ struct SavedBlock {
   size_t o_a = 0, o_b = 0, o_c = 0, o_shp = 0, o_lsi = 0;   // msda: value / loc / aw;  mask: coeff / proto
 };
 std::vector<SavedBlock*> g_saved;
+std::deque<int> g_saved_free;                 // free blocks with memory, oldest release first
+size_t g_saved_bytes = 0;
+constexpr size_t kSavedPoolLimit = size_t(24) << 30;
 
+// Blocks are released in the order their last readers were enqueued on the compute stream, so the oldest free block that
+// fits is the one whose readers finish first.  If even that one is still being read (two steps in flight: the next step's
+// forward is enqueued while this step's backward runs) the pool grows instead of making the upload wait, up to a limit.
 int saved_acquire(size_t bytes, int* index) {
-  int best = -1;
-  for (size_t i = 0; i < g_saved.size(); ++i)
-    if (!g_saved[i]->in_use && g_saved[i]->cap >= bytes && (best < 0 || g_saved[i]->cap < g_saved[best]->cap)) best = static_cast<int>(i);
-  if (best < 0) {
-    for (size_t i = 0; i < g_saved.size(); ++i)                 // recycle the slot of a free block that is too small
-      if (!g_saved[i]->in_use) { best = static_cast<int>(i); break; }
-    if (best < 0) { g_saved.push_back(new SavedBlock()); best = static_cast<int>(g_saved.size()) - 1; }
-    SavedBlock* b = g_saved[best];
-    if (b->base) {
-      if (b->last_use) cudaEventSynchronize(b->last_use);
+  const size_t mb = size_t(1) << 20;
+  const size_t want = (bytes + mb - 1) & ~(mb - 1);
+  const size_t slack = want > 4 * mb ? want : 4 * mb;
+  int pick = -1;
+  bool pick_done = false;
+  std::deque<int>::iterator pick_it;
+  for (auto it = g_saved_free.begin(); it != g_saved_free.end(); ++it) {
+    SavedBlock* b = g_saved[*it];
+    if (b->cap < bytes || b->cap > want + slack) continue;
+    pick = *it;
+    pick_it = it;
+    pick_done = cudaEventQuery(b->last_use) == cudaSuccess;
+    if (!pick_done) cudaGetLastError();
+    break;
+  }
+  if (pick >= 0 && (pick_done || g_saved_bytes + want > kSavedPoolLimit)) {
+    g_saved_free.erase(pick_it);
+  } else {
+    while (g_saved_bytes + want > kSavedPoolLimit && !g_saved_free.empty()) {      // make room: drop the oldest free blocks
+      SavedBlock* b = g_saved[g_saved_free.front()];
+      g_saved_free.pop_front();
+      cudaEventSynchronize(b->last_use);
       cudaFree(b->base);
+      g_saved_bytes -= b->cap;
       b->base = nullptr;
       b->cap = 0;
     }
-    const size_t want = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
-    if (int rc = check_cuda(cudaMalloc(&b->base, want), "cudaMalloc(saved block)")) return rc;
+    pick = -1;
+    for (size_t i = 0; i < g_saved.size(); ++i)
+      if (!g_saved[i]->in_use && !g_saved[i]->base) { pick = static_cast<int>(i); break; }
+    if (pick < 0) { g_saved.push_back(new SavedBlock()); pick = static_cast<int>(g_saved.size()) - 1; }
+    SavedBlock* b = g_saved[pick];
+    if (int rc = check_cuda(cudaMalloc(&b->base, want), "cudaMalloc(saved block)")) { b->base = nullptr; return rc; }
     b->cap = want;
+    g_saved_bytes += want;
     if (!b->last_use)
       if (int rc = check_cuda(cudaEventCreateWithFlags(&b->last_use, cudaEventDisableTiming), "cudaEventCreate")) return rc;
     cudaEventRecord(b->last_use, g_pipe.s_run);
   }
-  SavedBlock* b = g_saved[best];
+  SavedBlock* b = g_saved[pick];
   b->in_use = true;
   cudaStreamWaitEvent(g_pipe.s_in, b->last_use, 0);            // uploads into the block wait for its previous readers
-  *index = best;
+  *index = pick;
   return 0;
 }
 
@@ -774,9 +845,11 @@ SavedBlock* saved_lookup(const char* who, int64_t handle, int kind) {
   return g_saved[index];
 }
 
-void saved_free(SavedBlock* b) {
+void saved_free(SavedBlock* b) {                // call after recording b->last_use behind the block's last reader
   b->in_use = false;
   ++b->gen;
+  for (size_t i = 0; i < g_saved.size(); ++i)
+    if (g_saved[i] == b) { g_saved_free.push_back(static_cast<int>(i)); break; }
 }
 
 // make sure the pipeline (streams, events) exists on `device` without reserving arena space
@@ -948,6 +1021,38 @@ int msda_host_sync(void) {
   return pipe_drain();
 }
 
+int msda_host_fence(int64_t* ticket) {
+  if (!ticket) return fail(MSDA_ERR_INVALID_ARG, "msda_host_fence: ticket is NULL");
+  *ticket = 0;
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
+  if (g_pipe.device < 0 || !g_pipe.s_out) return 0;      // nothing was ever enqueued: ticket 0 is always complete
+  cudaSetDevice(g_pipe.device);
+  cudaEvent_t ev = nullptr;
+  if (!g_pipe.fence_pool.empty()) { ev = g_pipe.fence_pool.back(); g_pipe.fence_pool.pop_back(); }
+  else if (int rc = check_cuda(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate(fence)")) return rc;
+  // every call's downloads wait for its kernels, which wait for its uploads, and the three streams are in order:
+  // an event behind the last download (plus the other two streams, for calls without outputs) covers all earlier work
+  cudaEvent_t e_in, e_run;
+  pipe_events(&e_in, &e_run);
+  cudaEventRecord(e_in, g_pipe.s_in);
+  cudaEventRecord(e_run, g_pipe.s_run);
+  cudaStreamWaitEvent(g_pipe.s_out, e_in, 0);
+  cudaStreamWaitEvent(g_pipe.s_out, e_run, 0);
+  if (int rc = check_cuda(cudaEventRecord(ev, g_pipe.s_out), "cudaEventRecord(fence)")) { g_pipe.fence_pool.push_back(ev); return rc; }
+  g_pipe.fences.push_back(HostFence{ev, g_pipe.head, g_pipe.fence_next});
+  *ticket = g_pipe.fence_next++;
+  return 0;
+}
+
+int msda_host_wait(int64_t ticket) {
+  std::lock_guard<std::mutex> lock(g_pipe.mu);
+  if (ticket < 0 || ticket >= g_pipe.fence_next) return fail(MSDA_ERR_INVALID_ARG, "msda_host_wait: unknown ticket %lld", (long long)ticket);
+  if (g_pipe.device >= 0) cudaSetDevice(g_pipe.device);
+  while (!g_pipe.fences.empty() && g_pipe.fences.front().id <= ticket)
+    if (int rc = pipe_retire_oldest(true)) return rc;
+  return 0;                                               // tickets at or below fence_done were completed by a wait or a sync
+}
+
 int msda_host_arena_release(void) {
   std::lock_guard<std::mutex> lock(g_pipe.mu);
   if (g_pipe.device >= 0) {
@@ -959,6 +1064,8 @@ int msda_host_arena_release(void) {
       delete b;
     }
     g_saved.clear();
+    g_saved_free.clear();
+    g_saved_bytes = 0;
     pipe_free();
   }
   g_pipe.device = -1;

@@ -18,6 +18,17 @@
 
 namespace msda {
 
+#ifdef MSDA_DBG_MASK
+// timing experiments only (tools/whatif_bench.py builds a separate library with -DMSDA_DBG_MASK): per-level bits that
+// drop work from the kernels -- bits 0-3 forward gathers, 4-7 backward reductions, 8-11 backward gathers + reductions
+__device__ int g_dbg_mask;
+#define MSDA_DBG_SKIP(shift, smp) (((dbg_mask >> ((shift) + ((smp) >> 2))) & 1) != 0)      // P = 4 only
+#define MSDA_DBG_LOAD const int dbg_mask = g_dbg_mask;
+#else
+#define MSDA_DBG_SKIP(shift, smp) false
+#define MSDA_DBG_LOAD
+#endif
+
 struct FastDiv {              // q = x / d for 0 <= x < 2^31 (host: make_fastdiv)
   uint32_t d, mul, shr;
 };
@@ -138,6 +149,7 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 
   stage_levels(s_lvl, shapes, level_start, G * L);
   __syncthreads();
+  MSDA_DBG_LOAD
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane / C::G, c = lane - grp * C::G;
@@ -216,7 +228,7 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
             float v[kBatch][C::CPL];
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
-              if (active && w[u] != 0.f) {
+              if (active && w[u] != 0.f && !MSDA_DBG_SKIP(0, sgrp * C::SPG + b0 + u)) {
                 Vec16<VT>::load(row_ptr(vlane, off[u]), v[u]);
               } else {
 #pragma unroll
@@ -288,6 +300,7 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 
   stage_levels(s_lvl, shapes, level_start, G * L);
   __syncthreads();
+  MSDA_DBG_LOAD
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane / C::G, c = lane - grp * C::G;
@@ -384,12 +397,13 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               float dot = 0.f;
-              if (active && off[u] != kInvalidOff) {
+              if (active && off[u] != kInvalidOff && !MSDA_DBG_SKIP(8, sgrp * C::SPG + 2 * it + u)) {
                 float v[C::CPL];
                 Vec16<VT>::load(row_ptr(vlane, off[u]), v);
 #pragma unroll
                 for (int j = 0; j < C::CPL; ++j) dot = fmaf(go[j], v[j], dot);
-                if constexpr (C::CPL == 8) {
+                if (MSDA_DBG_SKIP(4, sgrp * C::SPG + 2 * it + u)) {
+                } else if constexpr (C::CPL == 8) {
                   float* gv = grad_value + static_cast<uint64_t>(off[u]) * 8u + 4 * c;      // off counts 16-byte units of 2-byte elements
                   red_add_f32x4(gv, w[u] * go_red[0], w[u] * go_red[1], w[u] * go_red[2], w[u] * go_red[3]);
                   red_add_f32x4(gv + 4 * C::G, w[u] * go_red[4], w[u] * go_red[5], w[u] * go_red[6], w[u] * go_red[7]);

@@ -364,6 +364,53 @@ def test_host_saved_entries(async_mode):
         lib.msda_host_arena_release()
 
 
+def test_host_fence_wait_two_steps_in_flight():
+    """msda_host_fence / msda_host_wait: step i+1 is enqueued before step i is waited for (its uploads run under step i's
+    downloads); each step's results are complete after its own ticket, the ring arena and the saved-block pool recycle."""
+    import ctypes
+    from mdqe_cvpr2023_b200 import _lib
+    lib = _lib.load()
+    steps = []
+    for seed in range(4):
+        inp = make_inputs(2, [(12, 20), (6, 10)], 8, 32, 4, Lq=40 + seed, dist="wide", seed=90 + seed)
+        pin = {k: v.contiguous().pin_memory() for k, v in inp.items()}
+        N, S, M, D = inp["value"].shape
+        Lq = inp["loc"].shape[1]
+        outs = (torch.zeros(N, Lq, M * D).pin_memory(), torch.zeros_like(pin["value"]).pin_memory(),
+                torch.zeros_like(pin["loc"]).pin_memory(), torch.zeros_like(pin["aw"]).pin_memory())
+        steps.append((inp, pin, (N, S, M, D, 1, 2, Lq, 4, 1.0), outs))
+    t0 = ctypes.c_int64(-1)
+    _lib.check(lib.msda_host_fence(ctypes.byref(t0)), "fence before any work")
+    _lib.check(lib.msda_host_wait(t0.value), "wait on an empty pipeline")
+    assert lib.msda_host_wait(10 ** 9) == -1 and "ticket" in _lib.last_error()
+    _lib.set_option("host_async", 1)
+    try:
+        prev = None
+        tickets = []
+        for inp, pin, dims, (out, gv, gl, ga) in steps:
+            h = ctypes.c_int64(0)
+            _lib.check(lib.msda_forward_host_saved(0, _lib.MSDA_F32, pin["value"].data_ptr(), pin["shapes"].data_ptr(),
+                                                   pin["level_start"].data_ptr(), pin["loc"].data_ptr(), pin["aw"].data_ptr(),
+                                                   *dims, out.data_ptr(), ctypes.byref(h)), "msda_forward_host_saved")
+            _lib.check(lib.msda_backward_host_saved(h.value, pin["grad_out"].data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr()),
+                       "msda_backward_host_saved")
+            t = ctypes.c_int64(0)
+            _lib.check(lib.msda_host_fence(ctypes.byref(t)), "msda_host_fence")
+            tickets.append(t.value)
+            if prev is not None:                       # the previous step completes while this one is in flight
+                _lib.check(lib.msda_host_wait(prev[0]), "msda_host_wait")
+                check(prev[1][3], oracle_all(prev[1][0]), 2e-5, "fenced step", prev[1][0])
+            prev = (t.value, (inp, pin, dims, (out, gv, gl, ga)))
+        assert tickets == sorted(tickets) and len(set(tickets)) == len(tickets)
+        _lib.check(lib.msda_host_wait(prev[0]), "msda_host_wait")
+        check(prev[1][3], oracle_all(prev[1][0]), 2e-5, "fenced step", prev[1][0])
+        _lib.check(lib.msda_host_wait(tickets[0]), "waiting for a completed ticket again is a no-op")
+        _lib.check(lib.msda_host_sync(), "msda_host_sync")
+    finally:
+        _lib.set_option("host_async", 0)
+        lib.msda_host_arena_release()
+
+
 def test_host_saved_grouped_temporal_form():
     """G > 1 through the saved host entries equals the mean of the per-level calls (ms_deform_attn.py:219-235)."""
     import ctypes
