@@ -213,6 +213,33 @@ int msda_host_saved_release(int64_t saved);
 /* Release the device arena used by the *_host entries. */
 int msda_host_arena_release(void);
 
+/* ---- callers either side of the path; fp32, device pointers, row-major contiguous --------------------
+ *
+ * mask_match_cost: the Hungarian matcher's mask costs (mdqe/models/matcher.py:182-200: out_masks = einsum(mask_coeff, proto);
+ * cost_bce = batch_sigmoid_ce_loss(out_masks, tgt) (:36-61); cost_dice = batch_dice_loss(out_masks, tgt) (:11-28)) for ONE clip,
+ * fused with the contraction: coeff [Q,K] (K <= 32), proto [K,Ncols], targets [G,Ncols] -> cost_bce [Q,G], cost_dice [Q,G].
+ * out_masks is never materialised.  workspace: mask_match_cost_workspace_bytes() bytes of device memory. */
+size_t mask_match_cost_workspace_bytes(void);
+int mask_match_cost(void* stream, const void* coeff, const void* proto, const void* targets,
+                    int Q, int K, int G, int64_t Ncols, void* workspace, void* cost_bce, void* cost_dice);
+/* mask_nms_siou: soft-IoU matrix of inference_clip (mdqe/mdqe.py:386-394): mask_pred [Q,T,H,W] -> siou [Q,Q] with
+ * mask_nms = mask_pred[:, ::2] if T >= 5, nearest 0.5x downsampling, soft = sigmoid, hard = soft > 0.5,
+ * siou = soft.hard^T / (sum soft [:,None] + sum hard [None] - soft.hard^T + 1). */
+size_t mask_nms_siou_workspace_bytes(void);
+int mask_nms_siou(void* stream, const void* mask_pred, int Q, int T, int H, int W, void* workspace, void* siou);
+/* aligned_bilinear (mdqe/util/misc.py:485-507) of n_img planes [H,W] by an integer factor, optionally followed by the sigmoid of
+ * mdqe/mdqe.py:357: out [n_img, factor*H, factor*W]. */
+int aligned_bilinear_sigmoid(void* stream, const void* in, int64_t n_img, int H, int W, int factor, int apply_sigmoid, void* out);
+/* Query initialisation sampling (mdqe/models/transformer_dec.py:170-179): for every level l, F.grid_sample(feat_l, 2*coords-1,
+ * bilinear, padding_mode="border", align_corners=False), mean over the L levels.  feat [B,S,C] (C % 4 == 0), shapes [L,2] and
+ * level_start [L] int64 on the device, coords [B,Q,2] normalised (x, y) -> out [B,Q,C].  The backward zero-fills grad_feat
+ * [B,S,C] itself and returns grad_coords [B,Q,2]. */
+int query_init_sample_forward(void* stream, const void* feat, const int64_t* shapes, const int64_t* level_start,
+                              const void* coords, int B, int S, int C, int L, int Q, void* out);
+int query_init_sample_backward(void* stream, const void* feat, const int64_t* shapes, const int64_t* level_start,
+                               const void* coords, const void* grad_out, int B, int S, int C, int L, int Q,
+                               void* grad_feat, void* grad_coords);
+
 /* Per-launch kernel timing (CUDA events on the launching stream, recorded right around the kernel).
  * Enable with msda_set_option("profile", 1); every launch of the given kind since the last read whose
  * work size (pairs N*Lq*M for MSDA, B*Q*Ncols for the mask kernels) is >= min_units is summed into

@@ -53,6 +53,14 @@ PROTOTYPES = {
     "mask_logits_backward_host_saved": (_c_int, [_c_i64, _c_vp, _c_vp, _c_vp]),
     "msda_host_saved_release": (_c_int, [_c_i64]),
     "msda_host_arena_release": (_c_int, []),
+    "mask_match_cost_workspace_bytes": (ctypes.c_size_t, []),
+    "mask_match_cost": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_vp, _c_vp, _c_vp]),
+    "mask_nms_siou_workspace_bytes": (ctypes.c_size_t, []),
+    "mask_nms_siou": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "aligned_bilinear_sigmoid": (_c_int, [_c_vp, _c_vp, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_vp]),
+    "query_init_sample_forward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
+    "query_init_sample_backward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                            _c_vp, _c_vp]),
     "msda_profile_read": (_c_int, [_c_int, _c_i64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_c_i64)]),
     "msda_debug_read": (_c_int, [ctypes.POINTER(ctypes.c_longlong)]),
     "msda_launch_count": (_c_i64, []),

@@ -1,0 +1,104 @@
+"""Golden fixtures for the callers either side of the hot path, made by RUNNING THE REFERENCE'S PYTHON.
+
+Run in the build container only (needs /root/reference):    python tests/golden/make_golden_consumers.py
+
+Executed unmodified from /root/reference (imported with `mdqe`, `mdqe.models`, `mdqe.util` pre-registered as bare namespace
+packages so that mdqe/__init__.py -- detectron2 -- never runs):
+  * mdqe/models/matcher.py:11-28   batch_dice_loss        } on out_masks = einsum('bqm,bmthw->bqthw') as in matcher.py:182-195
+  * mdqe/models/matcher.py:36-61   batch_sigmoid_ce_loss  }
+  * mdqe/util/misc.py:485-507      aligned_bilinear (+ .sigmoid() as in mdqe/mdqe.py:357)
+mdqe/mdqe.py (inference_clip, :386-394) and mdqe/models/transformer_dec.py (:170-179) sit inside classes that need detectron2 /
+a full model; their statements are executed here LITERALLY (same torch calls, same arguments), quoted next to each block.
+"""
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+warnings.filterwarnings("ignore")
+
+
+def import_reference():
+    for name, sub in (("mdqe", "mdqe"), ("mdqe.models", "mdqe/models"), ("mdqe.util", "mdqe/util")):
+        mod = types.ModuleType(name)
+        mod.__path__ = [os.path.join(REF, sub)]
+        sys.modules[name] = mod
+    import mdqe.models.matcher as matcher
+    import mdqe.util.misc as misc
+    return matcher, misc
+
+
+def save(name, **arrays):
+    conv = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in arrays.items()}
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **conv)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def main():
+    matcher, misc = import_reference()
+    g = torch.Generator().manual_seed(11)
+
+    # ---- matcher mask costs, one clip (matcher.py:182, :193-197)
+    for name, (Q, K, G, T, H, W) in {"match_cost_K32": (37, 32, 5, 2, 12, 20), "match_cost_K24": (20, 24, 17, 3, 6, 10)}.items():
+        coeff = torch.tanh(torch.randn(1, Q, K, generator=g))
+        proto = torch.randn(1, K, T, H, W, generator=g)
+        tgt = (torch.rand(G, T, H, W, generator=g) > 0.7).float()
+        out_masks = torch.einsum('bqm, bmthw -> bqthw', coeff, proto)[0]
+        cost_bce = matcher.batch_sigmoid_ce_loss(out_masks, tgt)
+        cost_dice = matcher.batch_dice_loss(out_masks, tgt)
+        save(name, coeff=coeff[0], proto=proto[0], targets=tgt, cost_bce=cost_bce, cost_dice=cost_dice)
+
+    # ---- NMS soft IoU of inference_clip (mdqe/mdqe.py:386-394), statements copied as they are executed there
+    for name, (Q, T, H, W) in {"nms_siou_T4": (23, 4, 12, 20), "nms_siou_T5": (9, 5, 11, 15)}.items():
+        mask_pred = torch.randn(Q, T, H, W, generator=g) * 2 - 0.5
+        mask_nms = mask_pred[:, ::2] if mask_pred.shape[1] >= 5 else mask_pred                 # mdqe.py:386
+        mask_soft = F.interpolate(mask_nms, scale_factor=0.5).flatten(1).sigmoid()             # :387
+        mask_hard = mask_soft.gt(0.5).float()                                                  # :388
+        numerator = torch.mm(mask_soft, mask_hard.t())                                         # :391
+        denominator = mask_soft.sum(-1)[:, None] + mask_hard.sum(-1)[None] - numerator         # :392
+        siou = numerator / (denominator + 1)                                                   # :393
+        save(name, mask_pred=mask_pred, siou=siou)
+
+    # ---- aligned_bilinear(pred_masks, factor=match_stride).sigmoid() (mdqe/mdqe.py:357, misc.py:485-507)
+    for name, (n, C, H, W, f) in {"aligned_bilinear_f4": (2, 3, 6, 10, 4), "aligned_bilinear_f2": (1, 2, 5, 7, 2)}.items():
+        x = torch.randn(n, C, H, W, generator=g) * 3
+        up = misc.aligned_bilinear(x, factor=f)
+        save(name, x=x, up=up, up_sigmoid=up.sigmoid(), factor=f)
+
+    # ---- query initialisation sampling (transformer_dec.py:170-179), statements as executed there (rearrange == view/permute)
+    from einops import rearrange
+    B, C = 3, 16
+    spatial_shapes = [(6, 10), (3, 5), (2, 3)]
+    S = sum(h * w for h, w in spatial_shapes)
+    lvl_start_index = [0]
+    for h, w in spatial_shapes:
+        lvl_start_index.append(lvl_start_index[-1] + h * w)
+    encoded_feat = torch.randn(B, S, C, generator=g, dtype=torch.float64).requires_grad_(True)
+    n_query_bins = 4
+    query_init_coords = (torch.rand(B, n_query_bins * n_query_bins, 2, generator=g, dtype=torch.float64) * 1.1 - 0.05).requires_grad_(True)
+    query_init_coords_grid = rearrange(query_init_coords, 'B (h w) k -> B h w k', h=n_query_bins)      # :167
+    query_init_coords_grid = 2 * query_init_coords_grid - 1                                            # :170
+    query_init = []
+    for l, (H_l, W_l) in enumerate(spatial_shapes):                                                    # :172-178
+        query_init.append(F.grid_sample(rearrange(encoded_feat[:, lvl_start_index[l]:lvl_start_index[l + 1]],
+                                                  'B (H W) C -> B C H W', H=H_l),
+                                        query_init_coords_grid,
+                                        mode='bilinear',
+                                        padding_mode="border",
+                                        align_corners=False))
+    query_init = rearrange(torch.stack(query_init).mean(0), 'B C h w -> B (h w) C')                    # :179
+    grad_out = torch.randn(query_init.shape, generator=g, dtype=torch.float64)
+    query_init.backward(grad_out)
+    save("query_init_f64", feat=encoded_feat, shapes=torch.tensor(spatial_shapes), level_start=torch.tensor(lvl_start_index[:-1]),
+         coords=query_init_coords, out=query_init, grad_out=grad_out, grad_feat=encoded_feat.grad, grad_coords=query_init_coords.grad)
+
+
+if __name__ == "__main__":
+    main()

@@ -13,7 +13,7 @@ HEADER = os.path.join(ROOT, "include", "msda_b200.h")
 def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:msda|mask|tc)_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b((?:msda|mask|tc|aligned_bilinear|query_init)_[a-z0-9_]+)\s*\(", src)))
 
 
 @pytest.fixture(scope="module")
