@@ -50,9 +50,6 @@ struct Options {
   std::atomic<int> tile_q{64};        // queries per CTA of the tiled backward
   std::atomic<int> host_async{0};     // 1 = the *_host entries only enqueue; msda_host_sync() completes them
   std::atomic<int> profile{0};        // 1 = bracket the main kernels with CUDA events (msda_profile_read)
-  std::atomic<int> wc_max_cells{0};   // fp32 backward experiment (measured slower, off by default): levels of at most this many cells
-                                      // write-combine grad_value in thread-private shared-memory slots before the L2 reductions
-  std::atomic<int> wc_chunk{512};     // pairs per CTA of the write-combining backward (longer runs per warp = more hits)
 };
 static Options g_opt;
 
@@ -67,8 +64,6 @@ static std::atomic<int>* find_option(const char* key) {
   if (!strcmp(key, "host_async")) return &g_opt.host_async;
   if (!strcmp(key, "tile_rows")) return &g_opt.tile_rows;
   if (!strcmp(key, "tile_q")) return &g_opt.tile_q;
-  if (!strcmp(key, "wc_max_cells")) return &g_opt.wc_max_cells;
-  if (!strcmp(key, "wc_chunk")) return &g_opt.wc_chunk;
   return nullptr;
 }
 
@@ -184,53 +179,11 @@ static void launch_fwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int ch
 #undef MSDA_FWD2
 }
 
-// fp32 plain operator with P == 4: the write-combining variant (msda_fast2.cuh).  Longer chunks than the default (a warp's cache
-// lives for one chunk), but never fewer than ~2 CTAs per SM.
-template <typename VT, typename LT>
-static bool wc_eligible(const Problem& pb) {
-  if (!std::is_same<VT, float>::value || !std::is_same<LT, float>::value) return false;
-  return g_opt.wc_max_cells.load() > 0 && pb.G == 1 && pb.scale == 1.f && pb.P == 4 && fast2_lp(pb.L * pb.P) && pb.n_pairs >= 148LL * 2 * 64;
-}
-static int wc_chunk_pairs(const Problem& pb) {
-  // whole waves: 4 CTAs of this kernel are resident per SM (64 registers, 56 KB of shared memory); k waves of equal CTAs,
-  // the smallest k that keeps the chunk at or below the wc_chunk option
-  const int unit = kWarpsPerCta * (32 / (pb.L * pb.P));
-  const int64_t slots = 148LL * 4;
-  const int cap = g_opt.wc_chunk.load();
-  for (int k = 1;; ++k) {
-    int64_t chunk = (pb.n_pairs + slots * k - 1) / (slots * k);
-    chunk = ((chunk + unit - 1) / unit) * unit;
-    if (chunk <= cap || chunk <= unit) return static_cast<int>(chunk);
-  }
-}
-
 template <typename VT, typename LT, int D>
 static void launch_bwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int chunk, const VT* v, const int64_t* shapes,
                            const int64_t* lsi, const LT* lc, const LT* a, const VT* go, float* gv, LT* gl, LT* ga) {
   const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
   const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
-  if constexpr (std::is_same<VT, float>::value && std::is_same<LT, float>::value) {
-    if (wc_eligible<VT, LT>(pb)) {
-      const int wchunk = wc_chunk_pairs(pb);
-      const unsigned wgrid = static_cast<unsigned>((pb.n_pairs + wchunk - 1) / wchunk);
-      const int cells = g_opt.wc_max_cells.load();
-      static std::once_flag once;
-      std::call_once(once, [] {
-        cudaFuncSetAttribute(msda_bwd_fast2_kernel<float, float, D, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWcSmemBytes);
-        cudaFuncSetAttribute(msda_bwd_fast2_kernel<float, float, D, 12, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWcSmemBytes);
-        cudaFuncSetAttribute(msda_bwd_fast2_kernel<float, float, D, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWcSmemBytes);
-      });
-#define MSDA_BWD2_WC(LPV) msda_bwd_fast2_kernel<float, float, D, LPV, false, true><<<wgrid, kThreads, kWcSmemBytes, st>>>( \
-      v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, wchunk, dm, dmq, pb.G, pb.scale, pb.fz, cells)
-      switch (pb.L * pb.P) {
-        case 16: MSDA_BWD2_WC(16); break;
-        case 12: MSDA_BWD2_WC(12); break;
-        default: MSDA_BWD2_WC(8); break;
-      }
-#undef MSDA_BWD2_WC
-      return;
-    }
-  }
 #define MSDA_BWD2(LPV, GRP) msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP><<<grid, kThreads, 0, st>>>( \
       v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz)
   const bool grouped = pb.G > 1 || pb.scale != 1.f;

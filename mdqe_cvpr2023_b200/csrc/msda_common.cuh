@@ -74,6 +74,12 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// the same, predicated inside the instruction: no branch around it, so a batch of gathers / reductions stays one basic block
+__device__ __forceinline__ void red_add_f32x4_if(bool on, float* p, float a, float b, float c, float d) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+               ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "r"(static_cast<uint32_t>(on)) : "memory");
+}
+
 // Stage the per-level geometry (int64 on device in the reference API) into shared memory.
 __device__ __forceinline__ void stage_levels(LevelInfo* s_lvl, const int64_t* __restrict__ shapes,
                                              const int64_t* __restrict__ level_start, int L) {

@@ -281,27 +281,17 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 }
 
 // ----------------------------------------------------------------------------------------- backward
-// WC ("write combining", fp32 values, P == 4, plain operator): grad_value rows of the coarse pyramid levels go through a small
-// THREAD-PRIVATE cache in shared memory before they reach L2.  The backward is bound by the fp32 reduction rate of L2
-// (tools/red_microbench.cu: 48.7 G rows/s chip-wide, whatever the instruction shape), and at the coarse levels consecutive
-// queries of a head keep hitting the same few rows.  Every lane owns kWcSlots (tag, float4) entries; the 8 (6) lanes of a
-// corner group always see the same tags, so an eviction is still one full-row vector reduction.  Slot = level class x parity
-// of the corner's (x, y): the four rows of a bilinear footprint never collide.  A warp then walks pairs 8 apart (same head,
-// consecutive queries for M = 8) instead of two adjacent pairs.  No atomics in shared memory (they are CAS loops on sm_100a),
-// no cross-lane dependence, the cache is flushed with reductions when the CTA's chunk ends.
-constexpr int kWcSlots = 8;
-constexpr size_t kWcSmemBytes = static_cast<size_t>(kWarpsPerCta) * kWcSlots * 32 * (sizeof(uint32_t) + sizeof(float4));
+constexpr int kBwdBatch = 4;                 // gathers in flight per lane (see the corner loop)
 
-template <typename VT, typename LT, int D, int LP, bool GROUPED, bool WC = false>
+template <typename VT, typename LT, int D, int LP, bool GROUPED>
 __global__ void __launch_bounds__(kThreads)
 msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                       const int64_t* __restrict__ level_start, const LT* __restrict__ loc,
                       const LT* __restrict__ aw, const VT* __restrict__ grad_out,
                       float* __restrict__ grad_value, LT* __restrict__ grad_loc, LT* __restrict__ grad_aw,
                       int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq,
-                      int G, float scale, FusedArgs fz, int wc_max_cells = 0) {
+                      int G, float scale, FusedArgs fz) {
   using C = Cfg2<VT, D, LP>;
-  static_assert(!WC || (std::is_same<VT, float>::value && !GROUPED && C::NSG == 1), "write combining: fp32 values, plain operator");
   // <grad_out, corner row> per (corner, sample): [4][33] floats per warp.  The partials are folded inside the
   // corner group with shuffles first, so the tile stays tiny and shared memory stays small: the first version
   // kept per-lane partials (34 KB per CTA), which left only ~16 KB of L1 per SM and cost the gathers their hit rate.
@@ -309,8 +299,6 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
   __shared__ LevelInfo s_lvl[kMaxLevels];
   __shared__ __align__(16) Slot s_slot[kWarpsPerCta][C::QPW * C::NSLOT];
   __shared__ float s_dot[kWarpsPerCta][4 * kDotStride];
-  __shared__ __align__(16) uint8_t s_wcpar[WC ? kWarpsPerCta : 1][C::QPW][4][16];      // parity slot of (pair, corner, sample)
-  extern __shared__ float4 s_wc_dyn[];                                                  // WC: [warp][slot][lane] float4, then tags
 
   stage_levels(s_lvl, shapes, level_start, G * L);
   __syncthreads();
@@ -324,16 +312,6 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
   const Slot* my_stream = my_slots + corner * C::LPP + sgrp * C::SPG;
   const VT* vlane = value + c * C::CPL;
   float* gvlane = grad_value + c * C::CPL;
-  // write-combining cache of this lane: wc_acc[slot * 32], wc_tag[slot * 32]
-  float4* wc_acc = s_wc_dyn + warp * (kWcSlots * 32) + lane;
-  uint32_t* wc_tag = reinterpret_cast<uint32_t*>(s_wc_dyn + kWarpsPerCta * kWcSlots * 32) + warp * (kWcSlots * 32) + lane;
-  uint32_t wc_mask = 0;                           // bit l: level l is small enough to be worth caching
-  if constexpr (WC) {
-#pragma unroll
-    for (int e = 0; e < kWcSlots; ++e) wc_tag[e * 32] = kInvalidOff;
-    for (int l = 0; l < L; ++l) wc_mask |= (s_lvl[l].H * s_lvl[l].W <= wc_max_cells ? 1u : 0u) << l;
-  }
-  constexpr uint32_t kPairStride = WC ? kWarpsPerCta : 1;       // WC: the warp's pairs are 8 apart (one head for M = 8)
   // dot of (corner, sample): written by lane 0 of each corner group, read by the sample lanes
   float* dot_w = s_dot[warp] + corner * kDotStride + sgrp * C::SPG;
   const float* dot_r = s_dot[warp] + lane;
@@ -344,18 +322,17 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
   const int ss = lane - ps * LP;
   const int lvl = ss / P;
 
-  for (uint32_t p0 = chunk_begin + warp * (WC ? 1 : C::QPW); p0 < chunk_end; p0 += kWarpsPerCta * C::QPW) {
-    const int npair = static_cast<int>(min(static_cast<uint32_t>(C::QPW), (chunk_end - p0 + kPairStride - 1) / kPairStride));
+  for (uint32_t p0 = chunk_begin + warp * C::QPW; p0 < chunk_end; p0 += kWarpsPerCta * C::QPW) {
+    const int npair = static_cast<int>(min(static_cast<uint32_t>(C::QPW), chunk_end - p0));
     const bool has_sample = lane < npair * LP;
     float x = 0.f, y = 0.f, a = 0.f, a_raw = 0.f, mk_x = 1.f, mk_y = 1.f;
     uint32_t n = 0, m = 0, nq = 0;
-    const int64_t si = static_cast<int64_t>(p0 + ps * kPairStride) * LP + ss;      // this lane's sample (== p0 * LP + lane without WC)
     if (has_sample) {
-      const uint32_t pair = p0 + ps * kPairStride;
+      const uint32_t pair = p0 + ps;
       nq = fd_div(pair, div_m);
       m = pair - nq * div_m.d;
       n = fd_div(pair, div_mq);
-      load_loc_aw<LT>(loc, aw, si, x, y, a);
+      load_loc_aw<LT>(loc, aw, static_cast<int64_t>(p0) * LP + lane, x, y, a);
     }
     bool fused = false;
     if constexpr (std::is_same<LT, float>::value && (LP & (LP - 1)) == 0) {
@@ -371,7 +348,7 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
     if constexpr (GROUPED) {
 #pragma unroll
       for (int pl = 0; pl < C::QPW; ++pl)
-        if (pl < npair) Vec16<VT>::load(grad_out + static_cast<int64_t>(p0 + pl * kPairStride) * D + c * C::CPL, go_g[pl]);
+        if (pl < npair) Vec16<VT>::load(grad_out + static_cast<int64_t>(p0 + pl) * D + c * C::CPL, go_g[pl]);
     }
     float g_aw = 0.f, g_x = 0.f, g_y = 0.f;
 
@@ -385,11 +362,6 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
         const LevelInfo li = s_lvl[g * L + lvl];
         lvl_h = li.H; lvl_w = li.W;
         geo = make_slots2<C::D16, C::LPP>(my_slots + ps * C::NSLOT, ss, x, y, a, li, n, m, S, M);
-        if constexpr (WC) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            s_wcpar[warp][ps][k][ss] = static_cast<uint8_t>(((geo.x0 + (k & 1)) & 1) | (((geo.y0 + (k >> 1)) & 1) << 1));
-        }
       }
       __syncwarp();
 
@@ -401,19 +373,14 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 #pragma unroll
             for (int j = 0; j < C::CPL; ++j) go[j] = go_g[GROUPED ? pl : 0][j];
           } else {
-            Vec16<VT>::load(grad_out + static_cast<int64_t>(p0 + pl * kPairStride) * D + c * C::CPL, go);
-          }
-          uint32_t par[4] = {0u, 0u, 0u, 0u};
-          if constexpr (WC) {
-            const uint4 t4 = *reinterpret_cast<const uint4*>(&s_wcpar[warp][pl][corner][0]);
-            par[0] = t4.x; par[1] = t4.y; par[2] = t4.z; par[3] = t4.w;
+            Vec16<VT>::load(grad_out + static_cast<int64_t>(p0 + pl) * D + c * C::CPL, go);
           }
           // 2-byte values: a lane owns 8 channels for the dot products, but two 16-byte reductions per lane at a 32-byte lane
           // stride would half-fill every L2 sector.  The scatter only needs grad_out, so for it the lane takes channels
           // [4c, 4c+4) and [4G+4c, 4G+4c+4): each warp-wide RED then covers contiguous 16-byte pieces (bf16 backward 439 -> fp32 speed).
           float go_red[C::CPL == 8 ? 8 : 1];
           if constexpr (C::CPL == 8) {
-            const VT* gp = grad_out + static_cast<int64_t>(p0 + pl * kPairStride) * D;
+            const VT* gp = grad_out + static_cast<int64_t>(p0 + pl) * D;
             const uint2 lo4 = __ldg(reinterpret_cast<const uint2*>(gp + 4 * c));
             const uint2 hi4 = __ldg(reinterpret_cast<const uint2*>(gp + 4 * C::G + 4 * c));
             const uint32_t u4[4] = {lo4.x, lo4.y, hi4.x, hi4.y};
@@ -424,70 +391,105 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
             }
           }
           const uint4* stream = reinterpret_cast<const uint4*>(my_stream + pl * C::NSLOT);
+          // Batches of kBwdBatch corner rows: all gathers of a batch are issued first (predicated, no branches), then the dot
+          // products and the reductions (predicated).  The per-lane dot partials of kFold samples are then folded across the
+          // G lanes of the corner group by a transposing butterfly (G - 1 shuffles for G samples instead of G log2 G), which
+          // leaves the dot of sample i in lane i: one store per lane.  The backward is bound by the SM's load/store + shuffle
+          // pipe (gathers, vector reductions, shuffles and shared-memory traffic all queue there), so every shuffle counts.
+          constexpr int kFoldT = C::G > kBwdBatch ? C::G : kBwdBatch;
+          constexpr bool kTransFold = ((C::G & (C::G - 1)) == 0) && (C::SPG % kFoldT == 0) && (kFoldT % C::G == 0);
+          constexpr int kFold = kTransFold ? kFoldT : ((C::SPG % kBwdBatch == 0) ? kBwdBatch : 2);   // samples per fold
+          constexpr int kB = (kFold % kBwdBatch == 0) ? kBwdBatch : 2;                               // gathers in flight
+          static_assert(C::SPG % kFold == 0 && kFold % kB == 0 && kB % 2 == 0, "batches must tile the slot stream");
 #pragma unroll
-          for (int it = 0; it < C::SPG / 2; ++it) {
-            const uint4 two = stream[it];
-            const uint32_t off[2] = {two.x, two.z};
-            const float w[2] = {__uint_as_float(two.y), __uint_as_float(two.w)};
+          for (int f0 = 0; f0 < C::SPG; f0 += kFold) {
+            float dot[kFold];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              float dot = 0.f;
-              if (active && off[u] != kInvalidOff && !MSDA_DBG_SKIP(8, sgrp * C::SPG + 2 * it + u)) {
-                float v[C::CPL];
-                Vec16<VT>::load(row_ptr(vlane, off[u]), v);
+            for (int b0 = f0; b0 < f0 + kFold; b0 += kB) {
+              uint32_t off[kB];
+              float w[kB];
 #pragma unroll
-                for (int j = 0; j < C::CPL; ++j) dot = fmaf(go[j], v[j], dot);
-                if (MSDA_DBG_SKIP(4, sgrp * C::SPG + 2 * it + u)) {
-                } else if constexpr (C::CPL == 8) {
-                  float* gv = grad_value + static_cast<uint64_t>(off[u]) * 8u + 4 * c;      // off counts 16-byte units of 2-byte elements
-                  red_add_f32x4(gv, w[u] * go_red[0], w[u] * go_red[1], w[u] * go_red[2], w[u] * go_red[3]);
-                  red_add_f32x4(gv + 4 * C::G, w[u] * go_red[4], w[u] * go_red[5], w[u] * go_red[6], w[u] * go_red[7]);
+              for (int i = 0; i < kB / 2; ++i) {
+                const uint4 two = stream[(b0 >> 1) + i];
+                off[2 * i] = two.x; w[2 * i] = __uint_as_float(two.y);
+                off[2 * i + 1] = two.z; w[2 * i + 1] = __uint_as_float(two.w);
+              }
+              bool valid[kB];
+              float v[kB][C::CPL];
+#pragma unroll
+              for (int u = 0; u < kB; ++u) {
+                valid[u] = active && off[u] != kInvalidOff && !MSDA_DBG_SKIP(8, sgrp * C::SPG + b0 + u);
+                if (valid[u]) {
+                  Vec16<VT>::load(row_ptr(vlane, off[u]), v[u]);
                 } else {
-                  const int smp = 2 * it + u;                     // it and u are unrolled: the sample index folds to a constant
-                  const int lvl = smp >> 2;                       // WC requires P == 4
-                  bool cached = false;
-                  if constexpr (WC) {
-                    if ((wc_mask >> lvl) & 1u) {
-                      cached = true;
-                      const int slot = ((lvl & 1) << 2) | ((par[smp >> 2] >> (8 * (smp & 3))) & 3u);
-                      const uint32_t tag = wc_tag[slot * 32];
-                      float4 acc = make_float4(w[u] * go[0], w[u] * go[1], w[u] * go[2], w[u] * go[3]);
-                      if (tag == off[u]) {
-                        const float4 old = wc_acc[slot * 32];
-                        acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
-                      } else {
-                        if (tag != kInvalidOff) {
-                          const float4 old = wc_acc[slot * 32];
-                          red_add_f32x4(gvlane + static_cast<uint64_t>(tag) * 4u, old.x, old.y, old.z, old.w);
-                        }
-                        wc_tag[slot * 32] = off[u];
-                      }
-                      wc_acc[slot * 32] = acc;
-                    }
-                  }
-                  if (!cached) {
-                    float* gv = const_cast<float*>(reinterpret_cast<const float*>(
-                        reinterpret_cast<const char*>(gvlane) + static_cast<uint64_t>(off[u]) * (16u * sizeof(float) / sizeof(VT))));
 #pragma unroll
-                    for (int j = 0; j < C::CPL; j += 4)
-                      red_add_f32x4(gv + j, w[u] * go[j], w[u] * go[j + 1], w[u] * go[j + 2], w[u] * go[j + 3]);
-                  }
+                  for (int j = 0; j < C::CPL; ++j) v[u][j] = 0.f;
                 }
               }
-              // fold the G per-lane partials of this corner row (groups are G consecutive lanes)
+#pragma unroll
+              for (int u = 0; u < kB; ++u) {
+                float d = 0.f;
+#pragma unroll
+                for (int j = 0; j < C::CPL; ++j) d = fmaf(go[j], v[u][j], d);
+                dot[b0 - f0 + u] = d;
+              }
+#pragma unroll
+              for (int u = 0; u < kB; ++u) {
+                const bool do_red = valid[u] && !MSDA_DBG_SKIP(4, sgrp * C::SPG + b0 + u);
+                if constexpr (C::CPL == 8) {
+                  float* gv = grad_value + static_cast<uint64_t>(off[u]) * 8u + 4 * c;      // off counts 16-byte units of 2-byte elements
+                  red_add_f32x4_if(do_red, gv, w[u] * go_red[0], w[u] * go_red[1], w[u] * go_red[2], w[u] * go_red[3]);
+                  red_add_f32x4_if(do_red, gv + 4 * C::G, w[u] * go_red[4], w[u] * go_red[5], w[u] * go_red[6], w[u] * go_red[7]);
+                } else {
+                  float* gv = const_cast<float*>(reinterpret_cast<const float*>(
+                      reinterpret_cast<const char*>(gvlane) + static_cast<uint64_t>(off[u]) * (16u * sizeof(float) / sizeof(VT))));
+#pragma unroll
+                  for (int j = 0; j < C::CPL; j += 4)
+                    red_add_f32x4_if(do_red, gv + j, w[u] * go[j], w[u] * go[j + 1], w[u] * go[j + 2], w[u] * go[j + 3]);
+                }
+              }
+            }
+            if constexpr (kTransFold) {
+              // kFold = r * G samples: fold each run of G samples; lane c of the group ends up with sample c of the run
+#pragma unroll
+              for (int r0 = 0; r0 < kFold; r0 += C::G) {
+                float t[C::G];
+#pragma unroll
+                for (int i = 0; i < C::G; ++i) t[i] = dot[r0 + i];
+#pragma unroll
+                for (int h = C::G / 2; h >= 1; h >>= 1) {                  // keep the half selected by bit h of the lane
+                  const bool up = (c & h) != 0;
+#pragma unroll
+                  for (int i = 0; i < h; ++i) {
+                    const float send = up ? t[i] : t[i + h];
+                    const float keep = up ? t[i + h] : t[i];
+                    t[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+                  }
+                }
+                if (active) dot_w[pl * LP + f0 + r0 + c] = t[0];
+              }
+            } else {
               if constexpr ((C::G & (C::G - 1)) == 0) {
 #pragma unroll
-                for (int o = C::G / 2; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-              } else {                                          // G = 6 or 3: walk down inside the group
-                float t = dot;
+                for (int o = C::G / 2; o >= 1; o >>= 1)
 #pragma unroll
-                for (int o = 1; o < C::G; ++o) {
-                  const float nb = __shfl_down_sync(0xffffffffu, dot, o);
-                  if (c + o < C::G) t += nb;
+                  for (int u = 0; u < kFold; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
+              } else {                                            // G = 6 or 3: walk down inside the group
+#pragma unroll
+                for (int u = 0; u < kFold; ++u) {
+                  float t = dot[u];
+#pragma unroll
+                  for (int o = 1; o < C::G; ++o) {
+                    const float nb = __shfl_down_sync(0xffffffffu, dot[u], o);
+                    if (c + o < C::G) t += nb;
+                  }
+                  dot[u] = t;
                 }
-                dot = t;
               }
-              if (active && c == 0) dot_w[pl * LP + 2 * it + u] = dot;
+              if (active && c == 0) {
+#pragma unroll
+                for (int u = 0; u < kFold; ++u) dot_w[pl * LP + f0 + u] = dot[u];
+              }
             }
           }
         }
@@ -512,6 +514,7 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
         const float t = a_raw * (scale * g_aw);
         const float tsum = segment_sum<LP>(t);
         if (has_sample) {
+          const int64_t si = static_cast<int64_t>(p0) * LP + lane;
           const float inv = 1.f / fz.scale;
           store_pair(grad_loc + 2 * si, a * g_x * inv * mk_x, a * g_y * inv * mk_y);       // d / d raw offsets
           st_from_float(grad_aw + si, t - a_raw * tsum);                                   // d / d logits
@@ -520,6 +523,7 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
       }
     }
     if (has_sample) {
+      const int64_t si = static_cast<int64_t>(p0) * LP + lane;
       if constexpr (std::is_same<LT, float>::value) {
         if (g_split) {                                       // zero-filled by the host
           atomicAdd(grad_loc + 2 * si, a * g_x);
@@ -532,18 +536,6 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
       } else {
         store_pair(grad_loc + 2 * si, a * g_x, a * g_y);
         st_from_float(grad_aw + si, scale * g_aw);
-      }
-    }
-  }
-  if constexpr (WC) {                                     // flush: every lane reduces what is left in its slots
-    if (active) {
-#pragma unroll
-      for (int e = 0; e < kWcSlots; ++e) {
-        const uint32_t tag = wc_tag[e * 32];
-        if (tag != kInvalidOff) {
-          const float4 old = wc_acc[e * 32];
-          red_add_f32x4(gvlane + static_cast<uint64_t>(tag) * 4u, old.x, old.y, old.z, old.w);
-        }
       }
     }
   }

@@ -554,20 +554,6 @@ def test_spatial_module_fused_prologue_equals_unfused(pred_offsets):
         assert 0.01 < frac < 0.99, frac
 
 
-@pytest.mark.parametrize("dist,D", [("local", 32), ("wide", 24)])
-def test_write_combining_backward_experiment_is_parity_green(dist, D):
-    """wc_max_cells > 0: grad_value rows of the coarse levels are pre-reduced in thread-private shared-memory slots (measured
-    slower than the plain kernel, profiles/r01v_wc_sweep.json; kept selectable, so it has to stay correct)."""
-    from mdqe_cvpr2023_b200 import _lib
-    inp = make_inputs(4, R50_360, 8, D, 4, dist=dist, seed=21)          # 163 200 pairs: above the variant's size threshold
-    _lib.set_option("wc_max_cells", 256)
-    try:
-        got = run_op(to_cuda(inp))
-    finally:
-        _lib.set_option("wc_max_cells", 0)
-    check(got, oracle_all(inp), 1e-4, "write-combining backward", inp)
-
-
 def test_tiled_fixed_point_backward_experiment_is_parity_green():
     """bwd_variant = 5: grad_value of the coarse levels accumulated in shared memory in per-CTA fixed point
     (csrc/msda_bwd_tile.cuh; not the default because it measured slower) -- must still match the oracle."""
