@@ -571,6 +571,16 @@ def main():
                 "traffic": traffic, "traffic_source": traffic_db.get("source") if traffic else None, "avg_launch_us": us, "launches_timed": n, "algorithmic_bytes": nbytes, "peak_source": peak_src}
 
     roofline = roof(bwd_bytes, bwd_ms, bwd_n, "msda_bwd_fast2_kernel<%s,32,16> (encoder shape N=4,S=Lq=5100)" % ("bf16" if args.dtype == "bf16" else "float"))
+    # What actually binds the backward: grad_value is accumulated with fp32 vector reductions into L2, and L2's reduction rate
+    # (measured by tools/red_microbench.cu, see profiles/ncu_traffic.json) is far below HBM-roofline speed for this op.
+    # Reduction bytes per launch = ncu's lts__t_sectors_srcunit_tex_op_red.sum of the same kernel and shape x 32 B.
+    l2_reduction = None
+    if roofline and args.dtype == "fp32" and args.dist == "local" and traffic_db.get("msda_bwd_fast2_kernel_l2_red_sectors"):
+        red_bytes = 32.0 * traffic_db["msda_bwd_fast2_kernel_l2_red_sectors"]
+        ach = red_bytes / (roofline["avg_launch_us"] * 1e-6) / 1e9
+        l2_reduction = {"kernel": roofline["kernel"], "bound": "l2_fp32_reductions", "achieved": ach, "peak": traffic_db["l2_red_peak_gbs"],
+                        "unit": "GB/s", "frac": ach / traffic_db["l2_red_peak_gbs"], "reduction_bytes_per_launch": red_bytes,
+                        "peak_source": traffic_db["l2_red_peak_source"]}
     roofline_fwd = roof(fwd_bytes, fwd_ms, fwd_n, "msda_fwd_fast2_kernel<%s,32,16> (encoder shape N=4,S=Lq=5100)" % ("bf16" if args.dtype == "bf16" else "float"))
     mB = QUERIES * MASK_K + MASK_K * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
     mO = QUERIES * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
@@ -658,7 +668,7 @@ def main():
                                              "allreduce": "NCCL, 2 buckets per step: decoder 14.94M fp32 overlapped with the encoder backward, encoder 4.54M after it" if world > 1 else None}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "launches_per_step": launches_per_step,
                 "lib_launch_count_per_eager_step": counted_per_step,
-                "roofline": roofline, "roofline_fwd": roofline_fwd, "roofline_mask": roofline_mask,
+                "roofline": roofline, "roofline_binding_resource": l2_reduction, "roofline_fwd": roofline_fwd, "roofline_mask": roofline_mask,
                 "roofline_mask_bwd": roofline_mask_bwd, "eager_ms_per_step": eager_ms, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

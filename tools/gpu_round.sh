@@ -23,4 +23,9 @@ timeout 100 python tools/mask_bwd_timeline.py > gpurun_out/mask_timeline_${TAG}.
 timeout 100 python tools/mask_keepraw_check.py > gpurun_out/mask_keepraw_${TAG}.txt 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:mask_ -s 3 -c 3 -f -o gpurun_out/prof_mask_${TAG} \
     python tools/mask_profile_target.py > gpurun_out/ncu_mask_${TAG}.log 2>&1; echo "ncu mask rc=$?"
+echo "== callers either side of the path (csrc/consumers.cu): timing vs the reference's torch ops, ncu of the matcher-cost kernel"
+timeout 300 python tools/consumers_bench.py > gpurun_out/consumers_bench_${TAG}.log 2>&1; tail -8 gpurun_out/consumers_bench_${TAG}.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:match_cost_kernel -s 2 -c 1 -f -o gpurun_out/prof_match_cost_${TAG} \
+    python tools/consumers_bench.py > gpurun_out/ncu_match_cost_${TAG}.log 2>&1; echo "ncu match_cost rc=$?"
+echo "== encoder-shape fwd / bwd quick table"; timeout 300 python tools/bwd_quick.py > gpurun_out/bwd_quick_${TAG}.log 2>&1; tail -12 gpurun_out/bwd_quick_${TAG}.log
 ls -la gpurun_out | tail -20
