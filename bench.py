@@ -203,6 +203,9 @@ class DeviceStep:
             order = order[:len(order) - n_enc]
         elif part == "tail":
             order = order[len(order) - n_enc:]
+        elif part.startswith("tail"):                          # "tail<i>": the i-th encoder backward of the step (last layer first)
+            i = len(order) - n_enc + int(part[4:])
+            order = order[i:i + 1]
         for grouped, a in order:
             rc |= (lib.msda_backward_grouped if grouped else lib.msda_backward)(st, *a)
         if rc:
@@ -457,10 +460,12 @@ def main():
     calls, mask = build_calls(torch, args.dist, rank, args.layers)
     step = DeviceStep(torch, lib, libmod, calls, mask, device, args.dtype)
     # gradient all-reduce of the enc+dec parameters (decoder 14.94 M, encoder 4.54 M fp32) -- the only
-    # cross-GPU step of clip-sharded DDP training.  Two buckets like DDP's: the decoder bucket is reduced on NCCL's
-    # stream while the encoder backward still runs, the encoder bucket after the backward ends.
+    # cross-GPU step of clip-sharded DDP training.  Buckets like DDP's, in the order the gradients become ready: the decoder
+    # bucket is reduced on NCCL's stream while the encoder backward runs, then one bucket per encoder layer as soon as that
+    # layer's backward has been enqueued; only the last layer's 3 MB are reduced after the backward has ended.
+    n_enc_layers = sum(1 for c in calls if c["kind"] == "enc")
     dec_buf = torch.zeros(14_940_000, device=device) if world > 1 else None
-    enc_buf = torch.zeros(4_540_000, device=device) if world > 1 else None
+    enc_bufs = [torch.zeros(4_540_000 // max(n_enc_layers, 1), device=device) for _ in range(n_enc_layers)] if world > 1 else None
 
     def sync_all():
         torch.cuda.synchronize()
@@ -473,7 +478,8 @@ def main():
         step.run()
         if world > 1:
             dist.all_reduce(dec_buf)
-            dist.all_reduce(enc_buf)
+            for b in enc_bufs:
+                dist.all_reduce(b)
     torch.cuda.synchronize()
     graphs = None
     if not args.no_graph:
@@ -483,7 +489,7 @@ def main():
             step.run()
         torch.cuda.current_stream().wait_stream(side)
         graphs = []
-        for part in (("all",) if world == 1 else ("head", "tail")):
+        for part in (("all",) if world == 1 else ("head",) + tuple(f"tail{i}" for i in range(n_enc_layers))):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 step.run(part)
@@ -505,13 +511,15 @@ def main():
             graphs[0].replay()
         else:
             step.run("head")
-        work = dist.all_reduce(dec_buf, async_op=True)          # overlaps with the encoder backward below
-        if graphs is not None:
-            graphs[1].replay()
-        else:
-            step.run("tail")
-        dist.all_reduce(enc_buf)
-        work.wait()
+        works = [dist.all_reduce(dec_buf, async_op=True)]       # overlaps with the encoder backward below
+        for i in range(n_enc_layers):
+            if graphs is not None:
+                graphs[1 + i].replay()
+            else:
+                step.run(f"tail{i}")
+            works.append(dist.all_reduce(enc_bufs[i], async_op=True))
+        for w in works:
+            w.wait()
 
     # ---- timed region: exactly K steps, CUDA events, max over ranks
     libmod.launch_count_reset()
@@ -665,7 +673,7 @@ def main():
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
                 "config": config_dict(args, {"launch": "cuda_graph" if graph is not None else "eager",
-                                             "allreduce": "NCCL, 2 buckets per step: decoder 14.94M fp32 overlapped with the encoder backward, encoder 4.54M after it" if world > 1 else None}),
+                                             "allreduce": "NCCL, %d buckets per step in gradient-ready order: decoder 14.94M fp32 and one 0.76M bucket per encoder layer, each overlapped with the encoder backward still to run" % (1 + n_enc_layers) if world > 1 else None}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "launches_per_step": launches_per_step,
                 "lib_launch_count_per_eager_step": counted_per_step,
                 "roofline": roofline, "roofline_binding_resource": l2_reduction, "roofline_fwd": roofline_fwd, "roofline_mask": roofline_mask,

@@ -26,24 +26,26 @@ constexpr int kThreads = 256;
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 // ------------------------------------------------------------------------------------------ matcher mask costs
-// One launch handles up to 207 queries and 15 targets (97 KB of shared memory: two CTAs per SM); row Q of the sigmoid tile
-// is all ones (gives sum_c tgt[g,c]) and target G is all ones (gives sum_c sigmoid[q,c]) so that both row sums fall out of
-// the same product.
-constexpr int kMcMaxQ = 208, kMcMaxG = 16;
-constexpr int kMcWsFloats = 2 * kMcMaxQ * kMcMaxG + kMcMaxQ;
-constexpr size_t kMcSmem = static_cast<size_t>(kMcMaxQ + 32 + kMcMaxG + 2 * kMcMaxQ) * kPad * sizeof(float);
+// One launch handles up to 207 queries and 15 targets (68 KB of shared memory: three CTAs per SM).  Per 32 plane columns:
+//   stage 1  x = coeff . proto for 4 x 4 (query, column) tiles, sigmoid(x) to shared memory, softplus(x) summed per query;
+//   stage 2  sigmoid (rows) x targets (columns), 4 x 4 tile per thread.  Row Q of the sigmoid tile is all ones (gives
+//            sum_c tgt[g,c]) and target G is all ones (gives sum_c sigmoid[q,c]): both row sums fall out of the same product;
+//   stage 3  PT[k,g] += sum_c proto[k,c] tgt[g,c].  The BCE term needs sum_c x[q,c] tgt[g,c] = sum_k coeff[q,k] PT[k,g]: by
+//            associativity the big product over the plane is 32 x G instead of Q x G, and x never goes to shared memory.
+constexpr int kMcMaxQ = 208, kMcMaxG = 16, kMcK = 32;
+constexpr int kMcWsFloats = kMcMaxQ * kMcMaxG + kMcK * kMcMaxG + kMcMaxQ;      // sigmoid x targets, PT, softplus row sums
+constexpr size_t kMcSmem = static_cast<size_t>(kMcMaxQ + kMcK + kMcMaxG + kMcMaxQ) * kPad * sizeof(float);
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 match_cost_kernel(const float* __restrict__ coeff, const float* __restrict__ proto, const float* __restrict__ tgt, int Q, int K, int G,
                   int64_t N, int64_t cols_per_cta, float* __restrict__ ws) {
   extern __shared__ float4 smem4[];
   float* s_coeff = reinterpret_cast<float*>(smem4);          // [kMcMaxQ][kPad]  coeff[q][k], zero padded
   float* s_proto = s_coeff + kMcMaxQ * kPad;                 // [32][kPad]       proto[k][c]
-  float* s_tgt = s_proto + 32 * kPad;                        // [kMcMaxG][kPad]  tgt[g][c], row G = 1
+  float* s_tgt = s_proto + kMcK * kPad;                      // [kMcMaxG][kPad]  tgt[g][c], row G = 1
   float* s_sig = s_tgt + kMcMaxG * kPad;                     // [kMcMaxQ][kPad]  sigmoid(x[q][c]), row Q = 1
-  float* s_x = s_sig + kMcMaxQ * kPad;                       // [kMcMaxQ][kPad]  x[q][c]
   const int t = threadIdx.x;
-  for (int i = t; i < (kMcMaxQ + 32 + kMcMaxG + 2 * kMcMaxQ) * kPad; i += kThreads) s_coeff[i] = 0.f;
+  for (int i = t; i < (kMcMaxQ + kMcK + kMcMaxG + kMcMaxQ) * kPad; i += kThreads) s_coeff[i] = 0.f;
   __syncthreads();
   for (int i = t; i < Q * K; i += kThreads) s_coeff[(i / K) * kPad + (i % K)] = coeff[i];
 
@@ -52,15 +54,17 @@ match_cost_kernel(const float* __restrict__ coeff, const float* __restrict__ pro
   const int rows = Q + 1;                                     // incl. the all-ones row
   const int k_end = (K + 3) & ~3;
   float neg_sum[2][4] = {};
-  float acc_s[4][4] = {}, acc_x[4][4] = {};
+  float acc_s[4][4] = {};
+  float acc_pt[2] = {0.f, 0.f};
   const int q4_2 = t >> 2, g4_2 = t & 3;                     // stage-2 tile of this thread
+  const int k_3 = t >> 3, g2_3 = t & 7;                      // stage-3 outputs of this thread: PT[k_3][2 g2_3], PT[k_3][2 g2_3 + 1]
 
   for (int64_t c0 = c_begin; c0 < c_end; c0 += kTC) {
-    __syncthreads();                                          // previous iteration's stage 2 is done with the tiles
+    __syncthreads();                                          // previous iteration's stages 2 / 3 are done with the tiles
     {
       const int c = t & 31;
       const bool ok = c0 + c < c_end;
-      for (int k = t >> 5; k < 32; k += 8) s_proto[k * kPad + c] = (ok && k < K) ? __ldg(proto + k * N + c0 + c) : 0.f;
+      for (int k = t >> 5; k < kMcK; k += 8) s_proto[k * kPad + c] = (ok && k < K) ? __ldg(proto + k * N + c0 + c) : 0.f;
       for (int g = t >> 5; g < kMcMaxG; g += 8)
         s_tgt[g * kPad + c] = !ok ? 0.f : (g < G ? __ldg(tgt + g * N + c0 + c) : (g == G ? 1.f : 0.f));
     }
@@ -93,7 +97,7 @@ match_cost_kernel(const float* __restrict__ coeff, const float* __restrict__ pro
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const int q = q4 * 4 + r;
-          float sg[4], xv[4];
+          float sg[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const bool ok = c0 + c4 * 4 + j < c_end;
@@ -106,38 +110,40 @@ match_cost_kernel(const float* __restrict__ coeff, const float* __restrict__ pro
               const float r1 = __frcp_rn(1.f + e);
               neg_sum[pass][r] += fmaxf(v, 0.f) + __logf(1.f + e);
               sg[j] = v >= 0.f ? r1 : e * r1;
-              xv[j] = v;
             } else {
               sg[j] = (q == Q && ok) ? 1.f : 0.f;
-              xv[j] = 0.f;
             }
           }
-          if (q < kMcMaxQ) {
-            *reinterpret_cast<float4*>(s_sig + q * kPad + c4 * 4) = make_float4(sg[0], sg[1], sg[2], sg[3]);
-            *reinterpret_cast<float4*>(s_x + q * kPad + c4 * 4) = make_float4(xv[0], xv[1], xv[2], xv[3]);
-          }
+          if (q < kMcMaxQ) *reinterpret_cast<float4*>(s_sig + q * kPad + c4 * 4) = make_float4(sg[0], sg[1], sg[2], sg[3]);
         }
       }
     }
+    // stage 3 (reads only s_proto / s_tgt, so it can run before the barrier): PT[k][g] += proto[k][:] . tgt[g][:]
+    if (g2_3 * 2 < G) {
+#pragma unroll
+      for (int c4 = 0; c4 < kTC / 4; ++c4) {
+        const float4 p = lds4(s_proto + k_3 * kPad + c4 * 4);
+        const float4 t0 = lds4(s_tgt + (g2_3 * 2) * kPad + c4 * 4), t1 = lds4(s_tgt + (g2_3 * 2 + 1) * kPad + c4 * 4);
+        acc_pt[0] += p.x * t0.x + p.y * t0.y + p.z * t0.z + p.w * t0.w;
+        acc_pt[1] += p.x * t1.x + p.y * t1.y + p.z * t1.z + p.w * t1.w;
+      }
+    }
     __syncthreads();
-    // stage 2: [sigmoid; x] (rows) x targets (columns), 4 x 4 tile per thread
+    // stage 2: sigmoid (rows) x targets (columns), 4 x 4 tile per thread
     if (q4_2 * 4 < rows && g4_2 * 4 <= G) {
 #pragma unroll
       for (int c4 = 0; c4 < kTC / 4; ++c4) {
-        float4 sg[4], xv[4], tg[4];
+        float4 sg[4], tg[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           sg[r] = lds4(s_sig + (q4_2 * 4 + r) * kPad + c4 * 4);
-          xv[r] = lds4(s_x + (q4_2 * 4 + r) * kPad + c4 * 4);
           tg[r] = lds4(s_tgt + (g4_2 * 4 + r) * kPad + c4 * 4);
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 4; ++g)
             acc_s[r][g] += sg[r].x * tg[g].x + sg[r].y * tg[g].y + sg[r].z * tg[g].z + sg[r].w * tg[g].w;
-            acc_x[r][g] += xv[r].x * tg[g].x + xv[r].y * tg[g].y + xv[r].z * tg[g].z + xv[r].w * tg[g].w;
-          }
       }
     }
   }
@@ -148,11 +154,12 @@ match_cost_kernel(const float* __restrict__ coeff, const float* __restrict__ pro
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int q = q4_2 * 4 + r, gg = g4_2 * 4 + g;
-        if (q < rows && gg <= G) {
-          atomicAdd(ws + q * kMcMaxG + gg, acc_s[r][g]);
-          atomicAdd(ws + kMcMaxQ * kMcMaxG + q * kMcMaxG + gg, acc_x[r][g]);
-        }
+        if (q < rows && gg <= G) atomicAdd(ws + q * kMcMaxG + gg, acc_s[r][g]);
       }
+  }
+  if (g2_3 * 2 < G && k_3 < K) {
+    atomicAdd(ws + kMcMaxQ * kMcMaxG + k_3 * kMcMaxG + g2_3 * 2, acc_pt[0]);
+    if (g2_3 * 2 + 1 < G) atomicAdd(ws + kMcMaxQ * kMcMaxG + k_3 * kMcMaxG + g2_3 * 2 + 1, acc_pt[1]);
   }
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
@@ -165,18 +172,21 @@ match_cost_kernel(const float* __restrict__ coeff, const float* __restrict__ pro
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 4);
       const int q = q4 * 4 + r;
-      if ((t & 7) == 0 && q < Q) atomicAdd(ws + 2 * kMcMaxQ * kMcMaxG + q, v);
+      if ((t & 7) == 0 && q < Q) atomicAdd(ws + kMcMaxQ * kMcMaxG + kMcK * kMcMaxG + q, v);
     }
   }
 }
 
-__global__ void match_cost_finalize_kernel(const float* __restrict__ ws, int Q, int G, int64_t N, int ld, float* __restrict__ cost_bce,
-                                           float* __restrict__ cost_dice) {
+__global__ void match_cost_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ coeff, int Q, int K, int G, int64_t N, int ld,
+                                           float* __restrict__ cost_bce, float* __restrict__ cost_dice) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Q * G) return;
   const int q = i / G, g = i % G;
-  const float st = ws[q * kMcMaxG + g], xt = ws[kMcMaxQ * kMcMaxG + q * kMcMaxG + g];
-  const float sig_sum = ws[q * kMcMaxG + G], tgt_sum = ws[Q * kMcMaxG + g], neg = ws[2 * kMcMaxQ * kMcMaxG + q];
+  const float* pt = ws + kMcMaxQ * kMcMaxG;
+  float xt = 0.f;                                               // sum_c x[q,c] tgt[g,c] = sum_k coeff[q,k] PT[k,g]
+  for (int k = 0; k < K; ++k) xt = fmaf(coeff[q * K + k], pt[k * kMcMaxG + g], xt);
+  const float st = ws[q * kMcMaxG + g];
+  const float sig_sum = ws[q * kMcMaxG + G], tgt_sum = ws[Q * kMcMaxG + g], neg = ws[kMcMaxQ * kMcMaxG + kMcK * kMcMaxG + q];
   // pos * t + neg * (1 - t) = neg - x * t  (pos - neg = -x), matcher.py:58-61
   cost_bce[q * ld + g] = (neg - xt) / static_cast<float>(N);
   cost_dice[q * ld + g] = 1.f - (2.f * st + 1.f) / (sig_sum + tgt_sum + 1.f);           // matcher.py:25-27
@@ -272,13 +282,16 @@ __global__ void nms_siou_finalize_kernel(const float* __restrict__ ws, int i0, i
 // ------------------------------------------------------------------------------------------ aligned_bilinear (+ sigmoid)
 // out[y, x] = bilinear(in, max(y - f/2, 0) / f, max(x - f/2, 0) / f) with the source index clamped at the last row / column:
 // replicate-pad by one, align_corners=True resize to (f*h + 1, f*w + 1), replicate-pad f/2 at the top / left, crop (misc.py:494-507).
-// block = 64 quads of 4 output pixels (x) by 16 output rows (4 per thread: the column geometry is computed once per thread)
+// block = 64 quads of 4 output pixels (x) by 16 output rows of ONE image (4 consecutive rows per thread: the column geometry
+// is computed once per thread, consecutive rows mostly share their two source rows); 32-bit index arithmetic
 constexpr int kAbRows = 16;
 __global__ void __launch_bounds__(kThreads)
-aligned_bilinear_kernel(const float* __restrict__ in, int64_t n_rows_total, int H, int W, int f, int do_sigmoid, float* __restrict__ out) {
+aligned_bilinear_kernel(const float* __restrict__ in, int blocks_per_img, int H, int W, int f, int do_sigmoid, float* __restrict__ out) {
   const int OW = W * f, OH = H * f;
   const int xq = blockIdx.y * 64 + threadIdx.x;
   if (xq * 4 >= OW) return;
+  const unsigned img = blockIdx.x / static_cast<unsigned>(blocks_per_img);
+  const int y_base = (blockIdx.x - img * blocks_per_img) * kAbRows + threadIdx.y * 4;
   const float inv_f = 1.f / static_cast<float>(f);
   int xa[4], xb[4];
   float lx[4];
@@ -291,17 +304,17 @@ aligned_bilinear_kernel(const float* __restrict__ in, int64_t n_rows_total, int 
     xa[j] = min(x0, W - 1);
     xb[j] = min(x0 + 1, W - 1);
   }
+  const float* src = in + static_cast<size_t>(img) * H * W;
+  float* dst_img = out + static_cast<size_t>(img) * OH * OW;
 #pragma unroll
-  for (int k = 0; k < kAbRows / 4; ++k) {
-    const int64_t row = static_cast<int64_t>(blockIdx.x) * kAbRows + k * 4 + threadIdx.y;        // img * OH + y
-    if (row >= n_rows_total) return;
-    const int64_t img = row / OH;
-    const int y = static_cast<int>(row - img * OH);
+  for (int k = 0; k < 4; ++k) {
+    const int y = y_base + k;
+    if (y >= OH) return;
     const float sy = static_cast<float>(max(y - f / 2, 0)) * inv_f;
     const int y0 = static_cast<int>(sy);
     const float ly = sy - static_cast<float>(y0);
-    const float* r0 = in + (img * H + min(y0, H - 1)) * W;
-    const float* r1 = in + (img * H + min(y0 + 1, H - 1)) * W;
+    const float* r0 = src + min(y0, H - 1) * W;
+    const float* r1 = src + min(y0 + 1, H - 1) * W;
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -312,7 +325,7 @@ aligned_bilinear_kernel(const float* __restrict__ in, int64_t n_rows_total, int 
       if (do_sigmoid) o = __frcp_rn(1.f + expf(-o));          // correctly rounded reciprocal == 1.f / x
       v[j] = o;
     }
-    float* dst = out + row * OW + xq * 4;
+    float* dst = dst_img + static_cast<size_t>(y) * OW + xq * 4;
     if ((OW & 3) == 0) __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));    // streaming: written once, 16x the input
     else
       for (int j = 0; j < 4 && xq * 4 + j < OW; ++j) dst[j] = v[j];
@@ -436,7 +449,7 @@ int mask_match_cost(void* stream, const void* coeff, const void* proto, const vo
     attr = true;
   }
   const int64_t chunks = (Ncols + kTC - 1) / kTC;
-  const int slots = 2 * sm_count();                           // two resident CTAs per SM
+  const int slots = 3 * sm_count();                           // three resident CTAs per SM
   const int ctas = static_cast<int>(chunks < slots ? chunks : slots);
   const int64_t cols_per_cta = ((chunks + ctas - 1) / ctas) * kTC;
   for (int q0 = 0; q0 < Q; q0 += kMcMaxQ - 1) {
@@ -451,7 +464,8 @@ int mask_match_cost(void* stream, const void* coeff, const void* proto, const vo
                                                            cols_per_cta, static_cast<float*>(workspace));
       }
       if (int rc = after_launch("match_cost_kernel")) return rc;
-      match_cost_finalize_kernel<<<(qn * gn + 255) / 256, 256, 0, st>>>(static_cast<const float*>(workspace), qn, gn, Ncols, G,
+      match_cost_finalize_kernel<<<(qn * gn + 255) / 256, 256, 0, st>>>(static_cast<const float*>(workspace),
+                                                                         static_cast<const float*>(coeff) + static_cast<int64_t>(q0) * K, qn, K, gn, Ncols, G,
                                                                          static_cast<float*>(cost_bce) + static_cast<int64_t>(q0) * G + g0,
                                                                          static_cast<float*>(cost_dice) + static_cast<int64_t>(q0) * G + g0);
       if (int rc = after_launch("match_cost_finalize_kernel")) return rc;
@@ -501,13 +515,13 @@ int aligned_bilinear_sigmoid(void* stream, const void* in, int64_t n_img, int H,
   if (n_img == 0) return 0;
   if (!in || !out) return fail(MSDA_ERR_INVALID_ARG, "aligned_bilinear_sigmoid: NULL pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t rows = n_img * H * factor;
+  const int blocks_per_img = (H * factor + kAbRows - 1) / kAbRows;
   const int quads = (W * factor + 3) / 4;
-  if ((rows + kAbRows - 1) / kAbRows > 0x7fffffff) return fail(MSDA_ERR_INVALID_ARG, "aligned_bilinear_sigmoid: too many rows");
+  if (n_img * blocks_per_img > 0x7fffffff) return fail(MSDA_ERR_INVALID_ARG, "aligned_bilinear_sigmoid: too many rows");
   {
-    ProfScope prof(st, 6, rows * quads);
-    aligned_bilinear_kernel<<<dim3(static_cast<unsigned>((rows + kAbRows - 1) / kAbRows), (quads + 63) / 64), dim3(64, 4), 0, st>>>(
-        static_cast<const float*>(in), rows, H, W, factor, apply_sigmoid, static_cast<float*>(out));
+    ProfScope prof(st, 6, n_img * H * factor * quads);
+    aligned_bilinear_kernel<<<dim3(static_cast<unsigned>(n_img * blocks_per_img), (quads + 63) / 64), dim3(64, 4), 0, st>>>(
+        static_cast<const float*>(in), blocks_per_img, H, W, factor, apply_sigmoid, static_cast<float*>(out));
   }
   return after_launch("aligned_bilinear_kernel");
 }
