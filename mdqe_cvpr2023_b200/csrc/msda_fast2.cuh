@@ -281,10 +281,16 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 }
 
 // ----------------------------------------------------------------------------------------- backward
-constexpr int kBwdBatch = 4;                 // gathers in flight per lane (see the corner loop)
+#ifndef MSDA_BWD_BATCH
+#define MSDA_BWD_BATCH 4                     // tools/bwd_variants.sh builds A/B libraries with other values
+#endif
+#ifndef MSDA_BWD_MINB
+#define MSDA_BWD_MINB 1
+#endif
+constexpr int kBwdBatch = MSDA_BWD_BATCH;    // gathers in flight per lane (see the corner loop)
 
 template <typename VT, typename LT, int D, int LP, bool GROUPED>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, MSDA_BWD_MINB)
 msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                       const int64_t* __restrict__ level_start, const LT* __restrict__ loc,
                       const LT* __restrict__ aw, const VT* __restrict__ grad_out,
