@@ -222,11 +222,28 @@ int msda_host_arena_release(void);
 size_t mask_match_cost_workspace_bytes(void);
 int mask_match_cost(void* stream, const void* coeff, const void* proto, const void* targets,
                     int Q, int K, int G, int64_t Ncols, void* workspace, void* cost_bce, void* cost_dice);
+/* mask_losses_*: the criterion's mask losses of the G matched queries of a batch (mdqe/models/criterion.py:440-473): with
+ * src_masks = coeff[G,K] . proto[K,Ncols] (never materialised), loss_mask / loss_dice are sigmoid_ce_loss / dice_loss (:87-108, :20-43)
+ * when targets_interinst is NULL and interinst_sigmoid_ce_loss / interinst_dice_loss (:116-145, :51-81) otherwise
+ * (targets, targets_interinst [G,Ncols]; all rows must share one proto, i.e. one call per clip).  G <= 32 per call, K <= 32.
+ * forward:  losses[2] = (loss_mask, loss_dice), row_stats [G,8] = per-row plane sums kept for the backward.
+ * backward: grad_losses[2] on the device (upstream gradients of the two losses) -> grad_coeff [G,K], grad_proto [K,Ncols]. */
+size_t mask_losses_workspace_bytes(void);
+int mask_losses_forward(void* stream, const void* coeff, const void* proto, const void* targets, const void* targets_interinst,
+                        int G, int K, int64_t Ncols, float num_masks, void* workspace, void* row_stats, void* losses);
+int mask_losses_backward(void* stream, const void* coeff, const void* proto, const void* targets, const void* targets_interinst,
+                         const void* row_stats, const void* grad_losses, int G, int K, int64_t Ncols, float num_masks,
+                         void* grad_coeff, void* grad_proto);
 /* mask_nms_siou: soft-IoU matrix of inference_clip (mdqe/mdqe.py:386-394): mask_pred [Q,T,H,W] -> siou [Q,Q] with
  * mask_nms = mask_pred[:, ::2] if T >= 5, nearest 0.5x downsampling, soft = sigmoid, hard = soft > 0.5,
  * siou = soft.hard^T / (sum soft [:,None] + sum hard [None] - soft.hard^T + 1). */
 size_t mask_nms_siou_workspace_bytes(void);
 int mask_nms_siou(void* stream, const void* mask_pred, int Q, int T, int H, int W, void* workspace, void* siou);
+/* mask_track_siou: the tracker's mask IoU (mdqe/tracking/OverTracker.py:92-113, OverTracker._get_siou): saved_masks [Ns,T,H,W] and
+ * input_masks [Ni,T,H,W] are probabilities, thresholded at 0.5; siou [Ns,Ni] = |s & i| / (|s| + |i| - |s & i| + 1e-6), 0 for pairs
+ * with an empty mask.  workspace: mask_nms_siou_workspace_bytes(). */
+int mask_track_siou(void* stream, const void* saved_masks, const void* input_masks, int Ns, int Ni, int T, int H, int W,
+                    void* workspace, void* siou);
 /* aligned_bilinear (mdqe/util/misc.py:485-507) of n_img planes [H,W] by an integer factor, optionally followed by the sigmoid of
  * mdqe/mdqe.py:357: out [n_img, factor*H, factor*W]. */
 int aligned_bilinear_sigmoid(void* stream, const void* in, int64_t n_img, int H, int W, int factor, int apply_sigmoid, void* out);

@@ -55,8 +55,13 @@ PROTOTYPES = {
     "msda_host_arena_release": (_c_int, []),
     "mask_match_cost_workspace_bytes": (ctypes.c_size_t, []),
     "mask_match_cost": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_vp, _c_vp, _c_vp]),
+    "mask_losses_workspace_bytes": (ctypes.c_size_t, []),
+    "mask_losses_forward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_i64, ctypes.c_float, _c_vp, _c_vp, _c_vp]),
+    "mask_losses_backward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_i64, ctypes.c_float,
+                                      _c_vp, _c_vp]),
     "mask_nms_siou_workspace_bytes": (ctypes.c_size_t, []),
     "mask_nms_siou": (_c_int, [_c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    "mask_track_siou": (_c_int, [_c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
     "aligned_bilinear_sigmoid": (_c_int, [_c_vp, _c_vp, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "query_init_sample_forward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "query_init_sample_backward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int,

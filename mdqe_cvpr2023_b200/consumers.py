@@ -3,7 +3,9 @@ inference head and query initialisation would call instead of their chains of to
 operator itself there is no CPU or PyTorch fallback (CPU tensors raise RuntimeError).
 
   mask_match_cost(mask_coeff, proto, tgt_masks)          mdqe/models/matcher.py:182-197 (one clip)
+  mask_losses(mask_coeff, proto, tgt, tgt_interinst, n)  mdqe/models/criterion.py:440-473 (one clip, autograd-capable)
   mask_nms_siou(mask_pred)                               mdqe/mdqe.py:386-393
+  mask_track_siou(saved_masks, input_masks)              mdqe/tracking/OverTracker.py:92-113
   aligned_bilinear(tensor, factor, sigmoid=False)        mdqe/util/misc.py:485-507 (+ mdqe/mdqe.py:357)
   query_init_sample(encoded_feat, spatial_shapes, level_start_index, coords)
                                                          mdqe/models/transformer_dec.py:170-179 (autograd-capable)
@@ -47,6 +49,67 @@ def mask_match_cost(mask_coeff, proto, tgt_masks):
     return bce, dice
 
 
+class _MaskLossesFunction(Function):
+    """(loss_mask, loss_dice) of up to 32 matched rows of one clip; see mask_losses()."""
+
+    @staticmethod
+    def forward(ctx, coeff, proto, tgt, tgt_inter, num_masks):
+        who = "mask_losses"
+        tensors = [("mask_coeff", coeff), ("proto", proto), ("tgt_masks", tgt)] + ([("tgt_interinst_masks", tgt_inter)] if tgt_inter is not None else [])
+        _f32(who, tensors)
+        G, K = coeff.shape
+        ncols = proto.numel() // max(K, 1)
+        if proto.shape[0] != K or tgt.numel() != G * ncols or (tgt_inter is not None and tgt_inter.numel() != G * ncols):
+            raise RuntimeError(f"{who}: expected mask_coeff[G,K], proto[K,...], targets[G,...], got {tuple(coeff.shape)} {tuple(proto.shape)} {tuple(tgt.shape)}")
+        lib = _lib.load()
+        with torch.cuda.device(proto.device):
+            ws = torch.empty(lib.mask_losses_workspace_bytes(), dtype=torch.uint8, device=proto.device)
+            stats = torch.empty(max(G, 1), 8, dtype=torch.float32, device=proto.device)
+            losses = torch.empty(2, dtype=torch.float32, device=proto.device)
+            rc = lib.mask_losses_forward(_stream_ptr(proto.device), coeff.data_ptr(), proto.data_ptr(), tgt.data_ptr(),
+                                         tgt_inter.data_ptr() if tgt_inter is not None else None, G, K, ncols, float(num_masks),
+                                         ws.data_ptr(), stats.data_ptr(), losses.data_ptr())
+        _lib.check(rc, who)
+        ctx.save_for_backward(coeff, proto, tgt, tgt_inter, stats)
+        ctx.num_masks = float(num_masks)
+        return losses
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_losses):
+        coeff, proto, tgt, tgt_inter, stats = ctx.saved_tensors
+        G, K = coeff.shape
+        ncols = proto.numel() // max(K, 1)
+        grad_losses = grad_losses.contiguous().float()
+        lib = _lib.load()
+        with torch.cuda.device(proto.device):
+            gc = torch.empty_like(coeff)
+            gp = torch.empty_like(proto)
+            rc = lib.mask_losses_backward(_stream_ptr(proto.device), coeff.data_ptr(), proto.data_ptr(), tgt.data_ptr(),
+                                          tgt_inter.data_ptr() if tgt_inter is not None else None, stats.data_ptr(), grad_losses.data_ptr(),
+                                          G, K, ncols, ctx.num_masks, gc.data_ptr(), gp.data_ptr())
+        _lib.check(rc, "mask_losses (backward)")
+        return gc, gp, None, None, None
+
+
+def mask_losses(mask_coeff, proto, tgt_masks, tgt_interinst_masks, num_masks):
+    """loss_mask, loss_dice of SetCriterion.loss_masks (mdqe/models/criterion.py:440-473) for the matched queries of ONE clip:
+    mask_coeff [G,K] = outputs["mask_coeff"][b][src_idx], proto [K,T,H,W] = outputs["proto"][b], tgt_masks [G,T,H,W];
+    tgt_interinst_masks [G,T,H,W] selects the inter-instance forms (:467-470), None the plain ones (:472-475).
+    Autograd-capable (gradients for mask_coeff and proto); the [Q,T,H,W] src_masks of the reference are never materialised.
+    Clips of a batch are summed by the caller: every loss is a sum over rows divided by the same num_masks."""
+    tgt_masks = tgt_masks.to(proto.dtype).contiguous()
+    ti = tgt_interinst_masks.to(proto.dtype).contiguous() if tgt_interinst_masks is not None else None
+    mask_coeff, proto = mask_coeff.contiguous(), proto.contiguous()
+    G = mask_coeff.shape[0]
+    total = None
+    for g0 in range(0, max(G, 1), 32):                     # the kernels take up to 32 rows per launch
+        part = _MaskLossesFunction.apply(mask_coeff[g0:g0 + 32].contiguous(), proto, tgt_masks[g0:g0 + 32].contiguous(),
+                                         ti[g0:g0 + 32].contiguous() if ti is not None else None, num_masks)
+        total = part if total is None else total + part
+    return total[0], total[1]
+
+
 def mask_nms_siou(mask_pred):
     """siou [Q,Q] of mdqe/mdqe.py:386-393 from mask_pred [Q,T,H,W] in one pass."""
     who = "mask_nms_siou"
@@ -59,6 +122,25 @@ def mask_nms_siou(mask_pred):
         ws = torch.empty(lib.mask_nms_siou_workspace_bytes(), dtype=torch.uint8, device=mask_pred.device)
         siou = torch.empty(Q, Q, dtype=torch.float32, device=mask_pred.device)
         rc = lib.mask_nms_siou(_stream_ptr(mask_pred.device), mask_pred.data_ptr(), Q, T, H, W, ws.data_ptr(), siou.data_ptr())
+    _lib.check(rc, who)
+    return siou
+
+
+def mask_track_siou(saved_masks, input_masks):
+    """Drop-in for OverTracker._get_siou(saved_masks, input_masks) (mdqe/tracking/OverTracker.py:92-113): [Ns,T,H,W] and
+    [Ni,T,H,W] mask probabilities -> hard-mask IoU [Ns,Ni]."""
+    who = "mask_track_siou"
+    _f32(who, [("saved_masks", saved_masks), ("input_masks", input_masks)])
+    if saved_masks.dim() != 4 or input_masks.dim() != 4 or tuple(saved_masks.shape[1:]) != tuple(input_masks.shape[1:]):
+        raise RuntimeError(f"{who}: expected [Ns,T,H,W] and [Ni,T,H,W], got {tuple(saved_masks.shape)} {tuple(input_masks.shape)}")
+    Ns, T, H, W = saved_masks.shape
+    Ni = input_masks.shape[0]
+    lib = _lib.load()
+    with torch.cuda.device(saved_masks.device):
+        ws = torch.empty(lib.mask_nms_siou_workspace_bytes(), dtype=torch.uint8, device=saved_masks.device)
+        siou = torch.empty(Ns, Ni, dtype=torch.float32, device=saved_masks.device)
+        rc = lib.mask_track_siou(_stream_ptr(saved_masks.device), saved_masks.data_ptr(), input_masks.data_ptr(), Ns, Ni, T, H, W,
+                                 ws.data_ptr(), siou.data_ptr())
     _lib.check(rc, who)
     return siou
 

@@ -3,8 +3,11 @@
 //   mask_match_cost          mdqe/models/matcher.py:182-200 with batch_sigmoid_ce_loss (:36-61) and batch_dice_loss (:11-28):
 //                            the Hungarian matcher's mask costs, fused with the mask contraction -- out_masks [Q, T*H*W]
 //                            (48 MB per clip at R50_ovis_360) is never written, proto and the targets are read once;
+//   mask_losses_*            mdqe/models/criterion.py:440-473: BCE + dice (plain or inter-instance) of the matched rows, forward and
+//                            backward, fused with the contraction of those rows;
 //   mask_nms_siou            mdqe/mdqe.py:386-399: soft-IoU matrix of inference_clip (frame stride 2 for clips of 5+ frames,
 //                            nearest 0.5x downsampling, sigmoid, threshold, Q x Q product) in one pass over mask_pred;
+//   mask_track_siou          mdqe/tracking/OverTracker.py:92-113: hard-mask IoU between the tracker's memory and a new clip;
 //   aligned_bilinear_sigmoid mdqe/util/misc.py:485-507 + mdqe/mdqe.py:357: the 4x mask upsampling of the inference output;
 //   query_init_sample_*      mdqe/models/transformer_dec.py:170-179: per-level F.grid_sample (bilinear, border padding,
 //                            align_corners=False) of the encoder memory at the selected query points, mean over levels.
@@ -192,13 +195,192 @@ __global__ void match_cost_finalize_kernel(const float* __restrict__ ws, const f
   cost_dice[q * ld + g] = 1.f - (2.f * st + 1.f) / (sig_sum + tgt_sum + 1.f);           // matcher.py:25-27
 }
 
+// ------------------------------------------------------------------------------------------ matched-mask losses
+// criterion.py:440-473 with sigmoid_ce_loss / dice_loss (:20-43, :87-108) or the inter-instance forms (:51-81, :116-145), fused with the
+// contraction of the G matched coefficient rows: x[g,c] = coeff[g,:] . proto[:,c] is recomputed per 32 plane columns in both passes
+// and never written.  Per row g the forward needs 7 sums over the plane (kept in row_stats for the backward):
+//   0: sum l*w   (l = softplus(x) - x*t, w = ti + 1)      1: sum w      2: sum s*t      3: sum (1 - s)*tib      4: sum s      5: sum t
+//   6: sum tib   (tib = ti > 0.5 and 1 - t > 0.5)
+constexpr int kMlMaxG = 32, kMlStats = 8;
+
+__device__ __forceinline__ void ml_point(float x, float t, float ti, float& s, float& l, float& w, float& tib) {
+  const float e = expf(-fabsf(x));
+  const float r = 1.f / (1.f + e);
+  s = x >= 0.f ? r : e * r;
+  l = fmaxf(x, 0.f) + log1pf(e) - x * t;                       // binary_cross_entropy_with_logits(x, t)
+  w = ti + 1.f;                                                // criterion.py:140
+  tib = (ti > 0.5f && (1.f - t) > 0.5f) ? 1.f : 0.f;           // :69
+}
+
+// thread (c = t % 32, rows g = t / 32 + 8 j): the proto column lives in registers and is reused by the thread's 4 rows
+__global__ void __launch_bounds__(kThreads)
+mask_losses_fwd_kernel(const float* __restrict__ coeff, const float* __restrict__ proto, const float* __restrict__ tgt,
+                       const float* __restrict__ tgt_inter, int G, int K, int64_t N, int64_t cols_per_cta, float* __restrict__ ws) {
+  __shared__ float s_coeff[kMlMaxG][33];
+  const int t = threadIdx.x, c = t & 31, g0 = t >> 5;
+  for (int i = t; i < kMlMaxG * 32; i += kThreads) s_coeff[i >> 5][i & 31] = ((i >> 5) < G && (i & 31) < K) ? coeff[(i >> 5) * K + (i & 31)] : 0.f;
+  __syncthreads();
+  const int64_t c_begin = blockIdx.x * cols_per_cta, c_end = min(N, c_begin + cols_per_cta);
+  float acc[4][7] = {};
+  for (int64_t c0 = c_begin; c0 < c_end; c0 += kTC) {
+    const int64_t cc = c0 + c;
+    if (cc >= c_end) continue;
+    float p[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) p[k] = k < K ? __ldg(proto + k * N + cc) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = g0 + 8 * j;
+      if (g < G) {
+        float x = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) x = fmaf(s_coeff[g][k], p[k], x);
+        const float tv = __ldg(tgt + g * N + cc), ti = tgt_inter ? __ldg(tgt_inter + g * N + cc) : 0.f;
+        float sg, l, w, tib;
+        ml_point(x, tv, ti, sg, l, w, tib);
+        acc[j][0] += l * w; acc[j][1] += w; acc[j][2] += sg * tv; acc[j][3] += (1.f - sg) * tib; acc[j][4] += sg; acc[j][5] += tv; acc[j][6] += tib;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      float v = acc[j][i];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (c == 0 && g0 + 8 * j < G) atomicAdd(ws + (g0 + 8 * j) * kMlStats + i, v);
+    }
+}
+
+__global__ void mask_losses_finalize_kernel(const float* __restrict__ ws, int G, int64_t N, int has_inter, float num_masks, float* __restrict__ row_stats,
+                                            float* __restrict__ losses) {
+  __shared__ float s_b[kMlMaxG], s_d[kMlMaxG];
+  const int g = threadIdx.x;
+  if (g < G) {
+    const float* r = ws + g * kMlStats;
+    // plain forms: loss.mean(1) (:108) and no tib terms -- the same expressions with w == 1 (sum w = N) and tib == 0
+    const float wsum = has_inter ? fmaxf(r[1], 1.f) : static_cast<float>(N);
+    s_b[g] = r[0] / wsum;                                                         // :142 / :108
+    const float num = 2.f * r[2] + r[3], den = r[4] + r[5] + r[6];                // :77-78 / :39-40
+    s_d[g] = 1.f - (num + 1.f) / (den + 1.f);                                     // :79 / :41
+    for (int i = 0; i < kMlStats; ++i) row_stats[g * kMlStats + i] = i < 7 ? r[i] : 0.f;
+  }
+  __syncthreads();
+  if (g == 0) {
+    float b = 0.f, d = 0.f;
+    for (int i = 0; i < G; ++i) { b += s_b[i]; d += s_d[i]; }
+    const float inv = 1.f / fmaxf(num_masks, 1.f);                                // :144 / :81
+    losses[0] = b * inv;
+    losses[1] = d * inv;
+  }
+}
+
+// backward: gx[g,c] = d(g_mask * loss_mask + g_dice * loss_dice) / d x[g,c], then grad_proto = coeff^T . gx (written per column tile)
+// and grad_coeff = gx . proto^T (accumulated per CTA, atomics at the end)
+__global__ void __launch_bounds__(kThreads)
+mask_losses_bwd_kernel(const float* __restrict__ coeff, const float* __restrict__ proto, const float* __restrict__ tgt,
+                       const float* __restrict__ tgt_inter, const float* __restrict__ row_stats, const float* __restrict__ grad_losses,
+                       int G, int K, int64_t N, int64_t cols_per_cta, float num_masks, float* __restrict__ grad_coeff_ws, float* __restrict__ grad_proto) {
+  __shared__ float s_coeff[kMlMaxG][33];
+  __shared__ __align__(16) float s_gx[kMlMaxG][kPad];
+  __shared__ __align__(16) float s_proto[32][kPad];
+  __shared__ float s_cb[kMlMaxG], s_cd1[kMlMaxG], s_cd2[kMlMaxG];      // per-row constants of the two gradients
+  const int t = threadIdx.x, c = t & 31, g0 = t >> 5;
+  for (int i = t; i < kMlMaxG * 32; i += kThreads) s_coeff[i >> 5][i & 31] = ((i >> 5) < G && (i & 31) < K) ? coeff[(i >> 5) * K + (i & 31)] : 0.f;
+  for (int i = t; i < kMlMaxG * kPad; i += kThreads) (&s_gx[0][0])[i] = 0.f;
+  if (t < kMlMaxG) {
+    float cb = 0.f, cd1 = 0.f, cd2 = 0.f;
+    if (t < G) {
+      const float* r = row_stats + t * kMlStats;
+      const float inv = 1.f / fmaxf(num_masks, 1.f);
+      const float wsum = tgt_inter ? fmaxf(r[1], 1.f) : static_cast<float>(N);
+      const float num = 2.f * r[2] + r[3], den = r[4] + r[5] + r[6];
+      cb = grad_losses[0] * inv / wsum;                                 // d loss_mask / d x = cb * (s - t) * w
+      // d loss_dice / d x = -s(1-s) [ (2t - tib)(den + 1) - (num + 1) ] / (den + 1)^2 = s(1-s) [ cd2 - cd1 (2t - tib) ]
+      cd1 = grad_losses[1] * inv / (den + 1.f);
+      cd2 = grad_losses[1] * inv * (num + 1.f) / ((den + 1.f) * (den + 1.f));
+    }
+    s_cb[t] = cb; s_cd1[t] = cd1; s_cd2[t] = cd2;
+  }
+  __syncthreads();
+  const int64_t c_begin = blockIdx.x * cols_per_cta, c_end = min(N, c_begin + cols_per_cta);
+  const int gB = t >> 3, k4B = t & 7;                                   // grad_coeff tile of this thread: row gB, k = 4 k4B .. +3
+  float acc_gc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t c0 = c_begin; c0 < c_end; c0 += kTC) {
+    const int64_t cc = c0 + c;
+    const bool ok = cc < c_end;
+    __syncthreads();                                                    // previous iteration is done with s_gx / s_proto
+    float p[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      p[k] = (ok && k < K) ? __ldg(proto + k * N + cc) : 0.f;
+      if (g0 == (k & 7)) s_proto[k][c] = p[k];                          // each of the 8 warps stores 4 of the 32 rows
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = g0 + 8 * j;
+      float gx = 0.f;
+      if (g < G && ok) {
+        float x = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) x = fmaf(s_coeff[g][k], p[k], x);
+        const float tv = __ldg(tgt + g * N + cc), ti = tgt_inter ? __ldg(tgt_inter + g * N + cc) : 0.f;
+        float sg, l, w, tib;
+        ml_point(x, tv, ti, sg, l, w, tib);
+        gx = s_cb[g] * (sg - tv) * w + sg * (1.f - sg) * (s_cd2[g] - s_cd1[g] * (2.f * tv - tib));
+      }
+      s_gx[g][c] = gx;
+    }
+    __syncthreads();
+    {                                                                   // grad_proto[k][c0 + 4 c4 ..] = sum_g coeff[g][k] gx[g][..]
+      const int k = t >> 3, c4 = t & 7;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int g = 0; g < G; ++g) {
+        const float a = s_coeff[g][k];
+        const float4 v = lds4(&s_gx[g][c4 * 4]);
+        o.x = fmaf(a, v.x, o.x); o.y = fmaf(a, v.y, o.y); o.z = fmaf(a, v.z, o.z); o.w = fmaf(a, v.w, o.w);
+      }
+      if (k < K) {
+        const int64_t col = c0 + c4 * 4;
+        float* dst = grad_proto + k * N + col;
+        if (col + 3 < c_end && (N & 3) == 0) *reinterpret_cast<float4*>(dst) = o;
+        else {
+          const float ov[4] = {o.x, o.y, o.z, o.w};
+          for (int i = 0; i < 4 && col + i < c_end; ++i) dst[i] = ov[i];
+        }
+      }
+    }
+    if (gB < G) {                                                       // grad_coeff[g][k] += sum_c gx[g][c] proto[k][c]
+#pragma unroll
+      for (int c4 = 0; c4 < kTC / 4; ++c4) {
+        const float4 v = lds4(&s_gx[gB][c4 * 4]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 q = lds4(&s_proto[k4B * 4 + i][c4 * 4]);
+          acc_gc[i] += v.x * q.x + v.y * q.y + v.z * q.z + v.w * q.w;
+        }
+      }
+    }
+  }
+  if (gB < G) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (k4B * 4 + i < K) atomicAdd(grad_coeff_ws + gB * K + k4B * 4 + i, acc_gc[i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ NMS soft IoU
 constexpr int kSiMaxQ = 128;                                   // rows per chunk incl. the all-ones row
 constexpr size_t kSiSmem = static_cast<size_t>(2 * kSiMaxQ) * kPad * sizeof(float);
 
+// TRACK = false: NMS form (one logit tensor, rows i = sigmoid, rows j = sigmoid > 0.5, frame stride + nearest 0.5x downsampling).
+// TRACK = true:  tracker form (mdqe/tracking/OverTracker.py:92-113): rows i = saved_masks > 0.5, rows j = input_masks > 0.5 on
+//                probabilities, every pixel; `mask` / `mask_b` are the two tensors, N2 = T*H*W (T2 = T, H2 = H, W2 = W, t_step = 1).
+template <bool TRACK>
 __global__ void __launch_bounds__(kThreads)
-nms_siou_kernel(const float* __restrict__ mask, int i0, int Qi, int j0, int Qj, int T, int H, int W, int t_step, int T2, int H2, int W2,
-                int64_t cols_per_cta, float* __restrict__ ws) {
+nms_siou_kernel(const float* __restrict__ mask, const float* __restrict__ mask_b, int i0, int Qi, int j0, int Qj, int T, int H, int W, int t_step,
+                int T2, int H2, int W2, int64_t cols_per_cta, float* __restrict__ ws) {
   extern __shared__ float4 smem4[];
   float* s_soft = reinterpret_cast<float*>(smem4);            // [kSiMaxQ][kPad] sigmoid of rows i0.., row Qi = 1
   float* s_hard = s_soft + kSiMaxQ * kPad;                    // [kSiMaxQ][kPad] (logit > 0) of rows j0.., row Qj = 1
@@ -214,15 +396,20 @@ nms_siou_kernel(const float* __restrict__ mask, int i0, int Qi, int j0, int Qj, 
       const int c = t & 31;
       const int64_t cc = c0 + c;
       const bool ok = cc < c_end;
-      int64_t src = 0;
-      if (ok) {                                               // nearest, scale 0.5: source pixel (2y, 2x); frames t_step apart
+      int64_t src = cc;
+      if (ok && !TRACK) {                                     // nearest, scale 0.5: source pixel (2y, 2x); frames t_step apart
         const int x2 = static_cast<int>(cc % W2), y2 = static_cast<int>((cc / W2) % H2), t2 = static_cast<int>(cc / (static_cast<int64_t>(W2) * H2));
         src = static_cast<int64_t>(t2) * t_step * plane + static_cast<int64_t>(2 * y2) * W + 2 * x2;
       }
       const int r_end = max(Qi, Qj) + 1;                      // rows beyond stay zero from the initial fill
       for (int r = t >> 5; r < r_end; r += 8) {
         float so = 0.f, ha = 0.f;
-        if (ok) {
+        if (ok && TRACK) {
+          if (r < Qi) so = __ldg(mask + static_cast<int64_t>(i0 + r) * T * plane + src) > 0.5f ? 1.f : 0.f;       // OverTracker.py:99
+          else if (r == Qi) so = 1.f;
+          if (r < Qj) ha = __ldg(mask_b + static_cast<int64_t>(j0 + r) * T * plane + src) > 0.5f ? 1.f : 0.f;     // :98
+          else if (r == Qj) ha = 1.f;
+        } else if (ok) {
           if (r < Qi) so = 1.f / (1.f + expf(-__ldg(mask + static_cast<int64_t>(i0 + r) * T * plane + src)));
           else if (r == Qi) so = 1.f;
           // mask_soft.gt(0.5) on the fp32 sigmoid (mdqe.py:388-389), not logit > 0: they differ for tiny positive logits
@@ -270,13 +457,14 @@ nms_siou_kernel(const float* __restrict__ mask, int i0, int Qi, int j0, int Qj, 
   }
 }
 
-__global__ void nms_siou_finalize_kernel(const float* __restrict__ ws, int i0, int Qi, int j0, int Qj, int Q, float* __restrict__ siou) {
+__global__ void nms_siou_finalize_kernel(const float* __restrict__ ws, int i0, int Qi, int j0, int Qj, int ld, float eps, float* __restrict__ siou) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Qi * Qj) return;
   const int i = idx / Qj, j = idx % Qj;
   const float num = ws[i * kSiMaxQ + j];
-  const float den = ws[i * kSiMaxQ + Qj] + ws[Qi * kSiMaxQ + j] - num;      // mdqe.py:393
-  siou[static_cast<int64_t>(i0 + i) * Q + j0 + j] = num / (den + 1.f);
+  const float den = ws[i * kSiMaxQ + Qj] + ws[Qi * kSiMaxQ + j] - num;      // mdqe.py:392 / OverTracker.py:106-110
+  // eps = 1 (mdqe.py:393) or 1e-6 (OverTracker.py:111; its `saved_valid` factor only zeroes pairs whose numerator is 0 anyway)
+  siou[static_cast<int64_t>(i0 + i) * ld + j0 + j] = num / (den + eps);
 }
 
 // ------------------------------------------------------------------------------------------ aligned_bilinear (+ sigmoid)
@@ -476,38 +664,108 @@ int mask_match_cost(void* stream, const void* coeff, const void* proto, const vo
 
 size_t mask_nms_siou_workspace_bytes(void) { return static_cast<size_t>(kSiMaxQ) * kSiMaxQ * sizeof(float); }
 
-int mask_nms_siou(void* stream, const void* mask_pred, int Q, int T, int H, int W, void* workspace, void* siou) {
-  if (Q < 0 || T <= 0 || H < 2 || W < 2) return fail(MSDA_ERR_INVALID_ARG, "mask_nms_siou: Q=%d T=%d H=%d W=%d", Q, T, H, W);
-  if (Q == 0) return 0;
-  if (!mask_pred || !workspace || !siou) return fail(MSDA_ERR_INVALID_ARG, "mask_nms_siou: NULL pointer");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int siou_launch(const char* who, cudaStream_t st, bool track, const float* a, const float* b, int Qa, int Qb, int T, int H, int W,
+                       void* workspace, float* siou) {
   static bool attr = false;
   if (!attr) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(nms_siou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSiSmem)), "cudaFuncSetAttribute")) return rc;
+    if (int rc = check_cuda(cudaFuncSetAttribute(nms_siou_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSiSmem)), "cudaFuncSetAttribute")) return rc;
+    if (int rc = check_cuda(cudaFuncSetAttribute(nms_siou_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSiSmem)), "cudaFuncSetAttribute")) return rc;
     attr = true;
   }
-  const int t_step = T >= 5 ? 2 : 1;                            // mask_pred[:, ::2] if T >= 5 (mdqe.py:386)
-  const int T2 = (T + t_step - 1) / t_step, H2 = H / 2, W2 = W / 2;
+  const int t_step = (!track && T >= 5) ? 2 : 1;                // mask_pred[:, ::2] if T >= 5 (mdqe.py:386)
+  const int T2 = (T + t_step - 1) / t_step, H2 = track ? H : H / 2, W2 = track ? W : W / 2;
   const int64_t N2 = static_cast<int64_t>(T2) * H2 * W2;
   const int64_t chunks = (N2 + kTC - 1) / kTC;
   const int ctas = static_cast<int>(chunks < sm_count() ? chunks : sm_count());
   const int64_t cols_per_cta = ((chunks + ctas - 1) / ctas) * kTC;
-  for (int i0 = 0; i0 < Q; i0 += kSiMaxQ - 1) {
-    const int qi = Q - i0 < kSiMaxQ - 1 ? Q - i0 : kSiMaxQ - 1;
-    for (int j0 = 0; j0 < Q; j0 += kSiMaxQ - 1) {
-      const int qj = Q - j0 < kSiMaxQ - 1 ? Q - j0 : kSiMaxQ - 1;
+  for (int i0 = 0; i0 < Qa; i0 += kSiMaxQ - 1) {
+    const int qi = Qa - i0 < kSiMaxQ - 1 ? Qa - i0 : kSiMaxQ - 1;
+    for (int j0 = 0; j0 < Qb; j0 += kSiMaxQ - 1) {
+      const int qj = Qb - j0 < kSiMaxQ - 1 ? Qb - j0 : kSiMaxQ - 1;
       if (int rc = check_cuda(cudaMemsetAsync(workspace, 0, mask_nms_siou_workspace_bytes(), st), "cudaMemsetAsync(workspace)")) return rc;
       {
         ProfScope prof(st, 5, static_cast<int64_t>(qi) * N2);
-        nms_siou_kernel<<<ctas, kThreads, kSiSmem, st>>>(static_cast<const float*>(mask_pred), i0, qi, j0, qj, T, H, W, t_step, T2, H2, W2, cols_per_cta,
-                                                         static_cast<float*>(workspace));
+        if (track)
+          nms_siou_kernel<true><<<ctas, kThreads, kSiSmem, st>>>(a, b, i0, qi, j0, qj, T, H, W, t_step, T2, H2, W2, cols_per_cta, static_cast<float*>(workspace));
+        else
+          nms_siou_kernel<false><<<ctas, kThreads, kSiSmem, st>>>(a, b, i0, qi, j0, qj, T, H, W, t_step, T2, H2, W2, cols_per_cta, static_cast<float*>(workspace));
       }
-      if (int rc = after_launch("nms_siou_kernel")) return rc;
-      nms_siou_finalize_kernel<<<(qi * qj + 255) / 256, 256, 0, st>>>(static_cast<const float*>(workspace), i0, qi, j0, qj, Q, static_cast<float*>(siou));
+      if (int rc = after_launch(who)) return rc;
+      nms_siou_finalize_kernel<<<(qi * qj + 255) / 256, 256, 0, st>>>(static_cast<const float*>(workspace), i0, qi, j0, qj, Qb, track ? 1e-6f : 1.f, siou);
       if (int rc = after_launch("nms_siou_finalize_kernel")) return rc;
     }
   }
   return 0;
+}
+
+int mask_nms_siou(void* stream, const void* mask_pred, int Q, int T, int H, int W, void* workspace, void* siou) {
+  if (Q < 0 || T <= 0 || H < 2 || W < 2) return fail(MSDA_ERR_INVALID_ARG, "mask_nms_siou: Q=%d T=%d H=%d W=%d", Q, T, H, W);
+  if (Q == 0) return 0;
+  if (!mask_pred || !workspace || !siou) return fail(MSDA_ERR_INVALID_ARG, "mask_nms_siou: NULL pointer");
+  return siou_launch("nms_siou_kernel", static_cast<cudaStream_t>(stream), false, static_cast<const float*>(mask_pred),
+                     static_cast<const float*>(mask_pred), Q, Q, T, H, W, workspace, static_cast<float*>(siou));
+}
+
+int mask_track_siou(void* stream, const void* saved_masks, const void* input_masks, int Ns, int Ni, int T, int H, int W, void* workspace,
+                    void* siou) {
+  if (Ns < 0 || Ni < 0 || T <= 0 || H <= 0 || W <= 0) return fail(MSDA_ERR_INVALID_ARG, "mask_track_siou: Ns=%d Ni=%d T=%d H=%d W=%d", Ns, Ni, T, H, W);
+  if (Ns == 0 || Ni == 0) return 0;
+  if (!saved_masks || !input_masks || !workspace || !siou) return fail(MSDA_ERR_INVALID_ARG, "mask_track_siou: NULL pointer");
+  return siou_launch("track_siou_kernel", static_cast<cudaStream_t>(stream), true, static_cast<const float*>(saved_masks),
+                     static_cast<const float*>(input_masks), Ns, Ni, T, H, W, workspace, static_cast<float*>(siou));
+}
+
+size_t mask_losses_workspace_bytes(void) { return static_cast<size_t>(kMlMaxG) * kMlStats * sizeof(float); }
+
+static int mask_losses_check(const char* who, const void* coeff, const void* proto, const void* tgt, int G, int K, int64_t Ncols) {
+  if (G < 0 || G > kMlMaxG || K <= 0 || K > 32 || Ncols <= 0) return fail(MSDA_ERR_INVALID_ARG, "%s: G=%d (<= %d per call) K=%d (<= 32) Ncols=%lld", who, G, kMlMaxG, K, (long long)Ncols);
+  if (G > 0 && (!coeff || !proto || !tgt)) return fail(MSDA_ERR_INVALID_ARG, "%s: NULL pointer", who);
+  return 0;
+}
+static void mask_losses_grid(int64_t Ncols, int* ctas, int64_t* cols_per_cta) {
+  const int64_t chunks = (Ncols + kTC - 1) / kTC;
+  const int slots = 4 * sm_count();
+  *ctas = static_cast<int>(chunks < slots ? chunks : slots);
+  *cols_per_cta = ((chunks + *ctas - 1) / *ctas) * kTC;
+}
+
+int mask_losses_forward(void* stream, const void* coeff, const void* proto, const void* targets, const void* targets_interinst, int G, int K,
+                        int64_t Ncols, float num_masks, void* workspace, void* row_stats, void* losses) {
+  if (int rc = mask_losses_check("mask_losses_forward", coeff, proto, targets, G, K, Ncols)) return rc;
+  if (!workspace || !row_stats || !losses) return fail(MSDA_ERR_INVALID_ARG, "mask_losses_forward: NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = check_cuda(cudaMemsetAsync(workspace, 0, mask_losses_workspace_bytes(), st), "cudaMemsetAsync(workspace)")) return rc;
+  if (G > 0) {
+    int ctas; int64_t cpc;
+    mask_losses_grid(Ncols, &ctas, &cpc);
+    ProfScope prof(st, 7, static_cast<int64_t>(G) * Ncols);
+    mask_losses_fwd_kernel<<<ctas, kThreads, 0, st>>>(static_cast<const float*>(coeff), static_cast<const float*>(proto), static_cast<const float*>(targets),
+                                                      static_cast<const float*>(targets_interinst), G, K, Ncols, cpc, static_cast<float*>(workspace));
+    if (int rc = after_launch("mask_losses_fwd_kernel")) return rc;
+  }
+  mask_losses_finalize_kernel<<<1, kMlMaxG, 0, st>>>(static_cast<const float*>(workspace), G, Ncols, targets_interinst != nullptr, num_masks,
+                                                     static_cast<float*>(row_stats), static_cast<float*>(losses));
+  return after_launch("mask_losses_finalize_kernel");
+}
+
+int mask_losses_backward(void* stream, const void* coeff, const void* proto, const void* targets, const void* targets_interinst,
+                         const void* row_stats, const void* grad_losses, int G, int K, int64_t Ncols, float num_masks, void* grad_coeff,
+                         void* grad_proto) {
+  if (int rc = mask_losses_check("mask_losses_backward", coeff, proto, targets, G, K, Ncols)) return rc;
+  if (!grad_proto || (G > 0 && (!row_stats || !grad_losses || !grad_coeff))) return fail(MSDA_ERR_INVALID_ARG, "mask_losses_backward: NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (G == 0) return check_cuda(cudaMemsetAsync(grad_proto, 0, static_cast<size_t>(K) * Ncols * sizeof(float), st), "cudaMemsetAsync(grad_proto)");
+  if (int rc = check_cuda(cudaMemsetAsync(grad_coeff, 0, static_cast<size_t>(G) * K * sizeof(float), st), "cudaMemsetAsync(grad_coeff)")) return rc;
+  int ctas; int64_t cpc;
+  mask_losses_grid(Ncols, &ctas, &cpc);
+  {
+    ProfScope prof(st, 8, static_cast<int64_t>(G) * Ncols);
+    mask_losses_bwd_kernel<<<ctas, kThreads, 0, st>>>(static_cast<const float*>(coeff), static_cast<const float*>(proto), static_cast<const float*>(targets),
+                                                      static_cast<const float*>(targets_interinst), static_cast<const float*>(row_stats),
+                                                      static_cast<const float*>(grad_losses), G, K, Ncols, cpc, num_masks, static_cast<float*>(grad_coeff),
+                                                      static_cast<float*>(grad_proto));
+  }
+  return after_launch("mask_losses_bwd_kernel");
 }
 
 int aligned_bilinear_sigmoid(void* stream, const void* in, int64_t n_img, int H, int W, int factor, int apply_sigmoid, void* out) {

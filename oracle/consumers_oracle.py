@@ -30,6 +30,39 @@ def match_cost(coeff, proto, targets):
     return cost_bce, cost_dice
 
 
+def mask_losses(coeff, proto, targets, targets_interinst, num_masks, grad_weights=None):
+    """mdqe/models/criterion.py:440-473 for the matched rows: coeff [G,K], proto [K,...], targets / targets_interinst [G,...]
+    (targets_interinst None: sigmoid_ce_loss :87-108 + dice_loss :20-43, else the inter-instance forms :116-145, :51-81).
+    Returns (loss_mask, loss_dice) and, with grad_weights = (d/d loss_mask, d/d loss_dice), also (grad_coeff, grad_proto)."""
+    G, K = coeff.shape
+    c = np.asarray(coeff, dtype=np.float64)
+    p = np.asarray(proto, dtype=np.float64).reshape(K, -1)
+    t = np.asarray(targets, dtype=np.float64).reshape(G, -1)
+    x = c @ p                                                                                     # :440
+    s = _sigmoid(x)
+    l = _softplus(x) - x * t                                                                      # binary_cross_entropy_with_logits
+    inv = 1.0 / max(num_masks, 1)
+    if targets_interinst is None:
+        w = np.ones_like(x)
+        wsum = np.full(G, float(x.shape[1]))                                                      # loss.mean(1) (:108)
+        tib = np.zeros_like(x)
+    else:
+        ti = np.asarray(targets_interinst, dtype=np.float64).reshape(G, -1)
+        w = ti + 1                                                                                # :140
+        wsum = np.maximum(w.sum(1), 1)                                                            # :142
+        tib = ((ti > 0.5) & ((1 - t) > 0.5)).astype(np.float64)                                   # :69
+    loss_mask = ((l * w).sum(1) / wsum).sum() * inv                                               # :142-144
+    num = 2 * (s * t).sum(1) + ((1 - s) * tib).sum(1)                                             # :77 (:39 without tib)
+    den = s.sum(1) + t.sum(1) + tib.sum(1)                                                        # :78
+    loss_dice = (1 - (num + 1) / (den + 1)).sum() * inv                                           # :79-81
+    if grad_weights is None:
+        return loss_mask, loss_dice
+    gm, gd = float(grad_weights[0]) * inv, float(grad_weights[1]) * inv
+    ds = s * (1 - s)
+    gx = gm * (s - t) * w / wsum[:, None] + gd * ds * ((num + 1)[:, None] / (den + 1)[:, None] ** 2 - (2 * t - tib) / (den + 1)[:, None])
+    return loss_mask, loss_dice, gx @ p.T, (c.T @ gx).reshape(np.asarray(proto).shape)
+
+
 def nms_siou(mask_pred):
     """mdqe/mdqe.py:386-393.  mask_pred [Q,T,H,W] -> siou [Q,Q]."""
     m = np.asarray(mask_pred)
@@ -42,6 +75,16 @@ def nms_siou(mask_pred):
     num = soft @ hard.T                                             # :391
     den = soft.sum(-1)[:, None] + hard.sum(-1)[None, :] - num       # :392
     return num / (den + 1)                                          # :393
+
+
+def track_siou(saved_masks, input_masks):
+    """mdqe/tracking/OverTracker.py:92-113 (OverTracker._get_siou).  [Ns,T,H,W], [Ni,T,H,W] -> siou [Ns,Ni]."""
+    i = (np.asarray(input_masks).reshape(input_masks.shape[0], -1) > 0.5).astype(np.float64)      # :98
+    s = (np.asarray(saved_masks).reshape(saved_masks.shape[0], -1) > 0.5).astype(np.float64)      # :99
+    valid = (s.any(-1)[:, None] & i.any(-1)[None, :]).astype(np.float64)                          # :103
+    num = s @ i.T                                                                                 # :106
+    den = s.sum(-1)[:, None] + i.sum(-1)[None, :] - num                                           # :107
+    return (num * valid) / (den * valid + 1e-6)                                                   # :109-111
 
 
 def aligned_bilinear(x, factor):

@@ -7,6 +7,12 @@ packages so that mdqe/__init__.py -- detectron2 -- never runs):
   * mdqe/models/matcher.py:11-28   batch_dice_loss        } on out_masks = einsum('bqm,bmthw->bqthw') as in matcher.py:182-195
   * mdqe/models/matcher.py:36-61   batch_sigmoid_ce_loss  }
   * mdqe/util/misc.py:485-507      aligned_bilinear (+ .sigmoid() as in mdqe/mdqe.py:357)
+  * mdqe/models/criterion.py:20-43, 51-81, 87-108, 116-145  dice_loss, interinst_dice_loss, sigmoid_ce_loss, interinst_sigmoid_ce_loss
+                                   applied to src_masks = einsum(...)[idx] as in loss_masks (:440, :467-473), with autograd for the
+                                   gradients (the module's detectron2.projects.point_rend import is satisfied by a stand-in function
+                                   that the loss functions never call)
+  * mdqe/tracking/OverTracker.py:92-113  OverTracker._get_siou (the module's `from detectron2.structures import Instances` is
+                                   satisfied by an empty stand-in class; _get_siou never touches it)
 mdqe/mdqe.py (inference_clip, :386-394) and mdqe/models/transformer_dec.py (:170-179) sit inside classes that need detectron2 /
 a full model; their statements are executed here LITERALLY (same torch calls, same arguments), quoted next to each block.
 """
@@ -31,7 +37,18 @@ def import_reference():
         sys.modules[name] = mod
     import mdqe.models.matcher as matcher
     import mdqe.util.misc as misc
-    return matcher, misc
+    for name in ("detectron2", "detectron2.structures"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["detectron2.structures"].Instances = type("Instances", (), {})
+    trk = types.ModuleType("mdqe.tracking")
+    trk.__path__ = [os.path.join(REF, "mdqe/tracking")]
+    sys.modules["mdqe.tracking"] = trk
+    import mdqe.tracking.OverTracker as tracker
+    for name in ("detectron2.projects", "detectron2.projects.point_rend", "detectron2.projects.point_rend.point_features"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["detectron2.projects.point_rend.point_features"].get_uncertain_point_coords_on_grid = lambda *a, **k: None
+    import mdqe.models.criterion as criterion
+    return matcher, misc, tracker, criterion
 
 
 def save(name, **arrays):
@@ -42,7 +59,7 @@ def save(name, **arrays):
 
 
 def main():
-    matcher, misc = import_reference()
+    matcher, misc, tracker, criterion = import_reference()
     g = torch.Generator().manual_seed(11)
 
     # ---- matcher mask costs, one clip (matcher.py:182, :193-197)
@@ -65,6 +82,36 @@ def main():
         denominator = mask_soft.sum(-1)[:, None] + mask_hard.sum(-1)[None] - numerator         # :392
         siou = numerator / (denominator + 1)                                                   # :393
         save(name, mask_pred=mask_pred, siou=siou)
+
+    # ---- criterion mask losses of the matched queries (criterion.py:440, :467-473), inter-instance and plain forms
+    for name, (Q, K, G, T, H, W, inter) in {"mask_losses_interinst": (30, 32, 6, 2, 12, 20, True), "mask_losses_plain": (12, 24, 3, 3, 6, 10, False)}.items():
+        coeff = torch.tanh(torch.randn(1, Q, K, generator=g)).requires_grad_(True)
+        proto = torch.randn(1, K, T, H, W, generator=g).requires_grad_(True)
+        src_idx = torch.randperm(Q, generator=g)[:G]
+        idx = (torch.zeros(G, dtype=torch.long), src_idx)
+        tgt = (torch.rand(G, T, H, W, generator=g) > 0.7).float()
+        tgt_inter = (torch.rand(G, T, H, W, generator=g) > 0.6).float()
+        num_masks = 4.0
+        src_masks = torch.einsum('bqm, bmthw -> bqthw', coeff, proto)[idx]                        # criterion.py:440
+        if inter:
+            loss_mask = criterion.interinst_sigmoid_ce_loss(src_masks, tgt, tgt_inter, num_masks)    # :468
+            loss_dice = criterion.interinst_dice_loss(src_masks, tgt, tgt_inter, num_masks)          # :469
+        else:
+            loss_mask = criterion.sigmoid_ce_loss(src_masks, tgt, num_masks)                         # :474
+            loss_dice = criterion.dice_loss(src_masks, tgt, num_masks)                               # :475
+        gw = torch.tensor([0.7, 1.9])
+        (gw[0] * loss_mask + gw[1] * loss_dice).backward()
+        save(name, coeff=coeff[0], proto=proto[0], src_idx=src_idx, targets=tgt, targets_interinst=tgt_inter, interinst=int(inter),
+             num_masks=num_masks, grad_weights=gw, loss_mask=loss_mask, loss_dice=loss_dice, grad_coeff=coeff.grad[0], grad_proto=proto.grad[0])
+
+    # ---- tracker mask IoU (OverTracker._get_siou, OverTracker.py:92-113); an empty saved mask and an empty input mask included
+    for name, (Ns, Ni, T, H, W) in {"track_siou_a": (7, 5, 3, 10, 14), "track_siou_b": (3, 11, 1, 9, 9)}.items():
+        saved = torch.rand(Ns, T, H, W, generator=g)
+        inp = torch.rand(Ni, T, H, W, generator=g)
+        saved[1] = 0.2
+        inp[0] = 0.0
+        siou = tracker.OverTracker._get_siou(None, saved, inp)
+        save(name, saved_masks=saved, input_masks=inp, siou=siou)
 
     # ---- aligned_bilinear(pred_masks, factor=match_stride).sigmoid() (mdqe/mdqe.py:357, misc.py:485-507)
     for name, (n, C, H, W, f) in {"aligned_bilinear_f4": (2, 3, 6, 10, 4), "aligned_bilinear_f2": (1, 2, 5, 7, 2)}.items():

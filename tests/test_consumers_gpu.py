@@ -71,6 +71,42 @@ def test_match_cost_rejects_cpu_tensors(pkg):
         pkg.mask_match_cost(torch.zeros(2, 32), torch.zeros(32, 8), torch.zeros(1, 8))
 
 
+@pytest.mark.parametrize("name", ["mask_losses_interinst", "mask_losses_plain"])
+def test_mask_losses_golden_with_autograd(pkg, name):
+    """criterion.py:440-473 on the reference's own numbers: losses and, through autograd, the gradients of mask_coeff (scattered back
+    to the Q rows by the indexing, as in the reference) and proto."""
+    d = load(name)
+    coeff = d["coeff"].cuda().requires_grad_(True)
+    proto = d["proto"].cuda().requires_grad_(True)
+    idx = d["src_idx"].cuda()
+    ti = d["targets_interinst"].cuda() if int(d["interinst"]) else None
+    lm, ld = pkg.mask_losses(coeff[idx], proto, d["targets"].cuda(), ti, float(d["num_masks"]))
+    assert abs(float(lm) - float(d["loss_mask"])) < 1e-5 * abs(float(d["loss_mask"]))
+    assert abs(float(ld) - float(d["loss_dice"])) < 1e-5 * abs(float(d["loss_dice"]))
+    gw = d["grad_weights"].cuda()
+    (gw[0] * lm + gw[1] * ld).backward()
+    assert nerr(coeff.grad, d["grad_coeff"]) < TOL and nerr(proto.grad, d["grad_proto"]) < TOL
+
+
+@pytest.mark.parametrize("G,K,N,inter", [(1, 32, 33, True), (9, 32, 4 * 96 * 160, True), (32, 24, 1000, False), (45, 32, 777, True), (0, 32, 64, True)])
+def test_mask_losses_vs_oracle(pkg, G, K, N, inter):
+    from oracle import consumers_oracle as co
+    g = torch.Generator().manual_seed(G * 5 + K)
+    coeff = torch.tanh(torch.randn(G, K, generator=g))
+    proto = torch.randn(K, N, generator=g)
+    tgt = (torch.rand(G, N, generator=g) > 0.7).float()
+    ti = (torch.rand(G, N, generator=g) > 0.5).float() if inter else None
+    c, p = coeff.cuda().requires_grad_(True), proto.cuda().requires_grad_(True)
+    lm, ld = pkg.mask_losses(c, p, tgt.cuda(), ti.cuda() if inter else None, 3.0)
+    (0.5 * lm + 2.0 * ld).backward()
+    if G == 0:
+        assert float(lm) == 0.0 and float(ld) == 0.0 and float(p.grad.abs().max()) == 0.0
+        return
+    want = co.mask_losses(coeff.numpy(), proto.numpy(), tgt.numpy(), ti.numpy() if inter else None, 3.0, (0.5, 2.0))
+    assert abs(float(lm) - want[0]) < 1e-5 * abs(want[0]) and abs(float(ld) - want[1]) < 1e-5 * abs(want[1])
+    assert nerr(c.grad, want[2]) < TOL and nerr(p.grad, want[3]) < TOL
+
+
 @pytest.mark.parametrize("name", ["nms_siou_T4", "nms_siou_T5"])
 def test_nms_siou_golden(pkg, name):
     d = load(name)
@@ -89,6 +125,25 @@ def test_nms_siou_vs_reference_ops_on_gpu(pkg, Q, T, H, W):
     num = soft @ hard.t()
     want = num / (soft.sum(-1)[:, None] + hard.sum(-1)[None] - num + 1)
     assert nerr(got, want) < TOL
+
+
+@pytest.mark.parametrize("name", ["track_siou_a", "track_siou_b"])
+def test_track_siou_golden(pkg, name):
+    d = load(name)
+    assert nerr(pkg.mask_track_siou(d["saved_masks"].cuda(), d["input_masks"].cuda()), d["siou"]) < TOL
+
+
+@pytest.mark.parametrize("Ns,Ni,T,H,W", [(1, 1, 1, 1, 1), (20, 35, 4, 96, 160), (130, 5, 2, 12, 20), (4, 260, 1, 7, 9)])
+def test_track_siou_vs_oracle(pkg, Ns, Ni, T, H, W):
+    from oracle import consumers_oracle as co
+    g = torch.Generator().manual_seed(Ns * 3 + Ni)
+    saved = torch.rand(Ns, T, H, W, generator=g)
+    inp = torch.rand(Ni, T, H, W, generator=g)
+    inp[0] = 0.1                                            # an empty mask: the whole column is 0
+    got = pkg.mask_track_siou(saved.cuda(), inp.cuda())
+    want = co.track_siou(saved.numpy(), inp.numpy())
+    assert nerr(got, want) < TOL
+    assert float(got[:, 0].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("name", ["aligned_bilinear_f4", "aligned_bilinear_f2"])

@@ -31,6 +31,24 @@ def test_nms_siou_oracle(name):
     assert nerr(co.nms_siou(d["mask_pred"]), d["siou"]) < 5e-6
 
 
+@pytest.mark.parametrize("name", ["mask_losses_interinst", "mask_losses_plain"])
+def test_mask_losses_oracle(name):
+    d = load(name)
+    ti = d["targets_interinst"] if int(d["interinst"]) else None
+    lm, ld, gc, gp = co.mask_losses(d["coeff"][d["src_idx"]], d["proto"], d["targets"], ti, float(d["num_masks"]), d["grad_weights"])
+    assert abs(lm - float(d["loss_mask"])) < 5e-6 * abs(float(d["loss_mask"])) and abs(ld - float(d["loss_dice"])) < 5e-6 * abs(float(d["loss_dice"]))
+    want_gc = d["grad_coeff"][d["src_idx"]]
+    assert nerr(gc, want_gc) < 1e-5 and nerr(gp, d["grad_proto"]) < 1e-5
+    unmatched = np.setdiff1d(np.arange(d["coeff"].shape[0]), d["src_idx"])
+    assert np.abs(d["grad_coeff"][unmatched]).max() == 0.0          # the reference's gradient lives on the matched rows only
+
+
+@pytest.mark.parametrize("name", ["track_siou_a", "track_siou_b"])
+def test_track_siou_oracle(name):
+    d = load(name)
+    assert nerr(co.track_siou(d["saved_masks"], d["input_masks"]), d["siou"]) < 5e-6
+
+
 @pytest.mark.parametrize("name", ["aligned_bilinear_f4", "aligned_bilinear_f2"])
 def test_aligned_bilinear_oracle(name):
     d = load(name)

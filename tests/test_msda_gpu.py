@@ -14,7 +14,7 @@ from tests.helpers import GOLDEN, load_golden, nerr
 pytestmark = pytest.mark.gpu
 
 CORE = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-              if not os.path.basename(p).startswith(("module_", "mask_", "match_cost_", "nms_siou_", "aligned_bilinear_", "query_init_")))
+              if not os.path.basename(p).startswith(("module_", "mask_", "mask_losses_", "match_cost_", "nms_siou_", "track_siou_", "aligned_bilinear_", "query_init_")))
 
 
 @pytest.fixture(autouse=True)

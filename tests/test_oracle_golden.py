@@ -15,7 +15,7 @@ from oracle import msda_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CORE = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-              if not os.path.basename(p).startswith(("module_", "mask_", "match_cost_", "nms_siou_", "aligned_bilinear_", "query_init_")))
+              if not os.path.basename(p).startswith(("module_", "mask_", "mask_losses_", "match_cost_", "nms_siou_", "track_siou_", "aligned_bilinear_", "query_init_")))
 
 
 def nerr(a, b):

@@ -67,6 +67,40 @@ def ref_query_init(feat, shapes_list, starts, coords):       # transformer_dec.p
     return torch.stack(qi).mean(0).flatten(2).transpose(1, 2)
 
 
+def ref_mask_losses(coeff_all, proto, idx, tgt, ti, num_masks):      # criterion.py:440, :116-145, :51-81 (inter-instance forms), fwd + bwd
+    coeff_all = coeff_all.detach().requires_grad_(True)
+    proto = proto.detach().requires_grad_(True)
+    src = torch.einsum('bqm, bmthw -> bqthw', coeff_all[None], proto[None])[(torch.zeros_like(idx), idx)]
+    inputs, targets, tinter = src.flatten(1), tgt.flatten(1), ti.flatten(1)
+    weights = tinter + 1
+    loss = F.binary_cross_entropy_with_logits(inputs, targets, reduction="none")
+    loss_mask = ((loss * weights).sum(1) / weights.sum(1).clamp(min=1)).sum() / max(num_masks, 1)
+    tib = (tinter.gt(0.5) & (1 - targets).gt(0.5)).float()
+    fg, bg = inputs.sigmoid(), (-inputs).sigmoid()
+    numerator = 2 * (fg * targets).sum(1) + (bg * tib).sum(1)
+    denominator = fg.sum(1) + targets.sum(1) + tib.sum(1)
+    loss_dice = (1 - (numerator + 1) / (denominator + 1)).sum() / max(num_masks, 1)
+    (loss_mask + loss_dice).backward()
+    return coeff_all.grad, proto.grad
+
+
+def our_mask_losses(coeff_all, proto, idx, tgt, ti, num_masks):
+    coeff_all = coeff_all.detach().requires_grad_(True)
+    proto = proto.detach().requires_grad_(True)
+    lm, ld = pkg.mask_losses(coeff_all[idx], proto, tgt, ti, num_masks)
+    (lm + ld).backward()
+    return coeff_all.grad, proto.grad
+
+
+def ref_track_siou(saved_masks, input_masks):                         # OverTracker.py:92-113
+    input_masks = input_masks.flatten(1).gt(0.5).float().unsqueeze(0)
+    saved_masks = saved_masks.flatten(1).gt(0.5).float().unsqueeze(1)
+    saved_valid = (saved_masks.any(dim=-1) & input_masks.any(dim=-1)).unsqueeze(-1)
+    numerator = saved_masks * input_masks
+    denominator = saved_masks + input_masks - numerator
+    return (numerator * saved_valid).sum(-1) / ((denominator * saved_valid).sum(-1) + 1e-6)
+
+
 res = {}
 g = torch.Generator().manual_seed(0)
 for tag, (T, H, W) in {"360p": (4, 96, 160), "720p": (4, 160, 288)}.items():
@@ -78,6 +112,13 @@ for tag, (T, H, W) in {"360p": (4, 96, 160), "720p": (4, 160, 288)}.items():
     ours, ref = timed(lambda: pkg.mask_match_cost(coeff, proto, tgt)), timed(lambda: ref_match_cost(coeff, proto, tgt))
     res[f"match_cost_{tag}"] = {"ours_us": ours, "torch_ops_us": ref, "algorithmic_MB": 4e-6 * (Q * K + K * N + G * N + 2 * Q * G),
                                 "GBps": 4e-3 * (Q * K + K * N + G * N + 2 * Q * G) / ours, "Q": Q, "G": G, "N": N}
+    idx = torch.randperm(Q, generator=g)[:G].cuda()
+    ti = (torch.rand(G, T, H, W, generator=g) > 0.6).float().cuda()
+    ours, ref = timed(lambda: our_mask_losses(coeff, proto, idx, tgt, ti, 8.0)), timed(lambda: ref_mask_losses(coeff, proto, idx, tgt, ti, 8.0))
+    res[f"mask_losses_fwd_bwd_{tag}"] = {"ours_us": ours, "torch_ops_us": ref, "G": G, "note": "incl. autograd bookkeeping on both sides"}
+    saved_m, input_m = torch.rand(20, T, H, W, generator=g).cuda(), torch.rand(12, T, H, W, generator=g).cuda()
+    ours, ref = timed(lambda: pkg.mask_track_siou(saved_m, input_m)), timed(lambda: ref_track_siou(saved_m, input_m))
+    res[f"track_siou_{tag}"] = {"ours_us": ours, "torch_ops_us": ref, "Ns": 20, "Ni": 12}
     Qd = 50
     mask_pred = (torch.randn(Qd, T, H, W, generator=g) * 2 - 0.5).cuda()
     ours, ref = timed(lambda: pkg.mask_nms_siou(mask_pred)), timed(lambda: ref_siou(mask_pred))
