@@ -637,7 +637,7 @@ int mask_match_cost(void* stream, const void* coeff, const void* proto, const vo
     attr = true;
   }
   const int64_t chunks = (Ncols + kTC - 1) / kTC;
-  const int slots = 3 * sm_count();                           // three resident CTAs per SM
+  const int slots = option("consumer_ctas") > 0 ? option("consumer_ctas") : 3 * sm_count();      // three resident CTAs per SM
   const int ctas = static_cast<int>(chunks < slots ? chunks : slots);
   const int64_t cols_per_cta = ((chunks + ctas - 1) / ctas) * kTC;
   for (int q0 = 0; q0 < Q; q0 += kMcMaxQ - 1) {
@@ -676,7 +676,9 @@ static int siou_launch(const char* who, cudaStream_t st, bool track, const float
   const int T2 = (T + t_step - 1) / t_step, H2 = track ? H : H / 2, W2 = track ? W : W / 2;
   const int64_t N2 = static_cast<int64_t>(T2) * H2 * W2;
   const int64_t chunks = (N2 + kTC - 1) / kTC;
-  const int ctas = static_cast<int>(chunks < sm_count() ? chunks : sm_count());
+  // measured (tools/consumer_cta_sweep.py): the sigmoid-heavy NMS form likes two CTAs per SM, the tracker form one
+  const int64_t slots = option("consumer_ctas") > 0 ? option("consumer_ctas") : (track ? 1 : 2) * sm_count();
+  const int ctas = static_cast<int>(chunks < slots ? chunks : slots);
   const int64_t cols_per_cta = ((chunks + ctas - 1) / ctas) * kTC;
   for (int i0 = 0; i0 < Qa; i0 += kSiMaxQ - 1) {
     const int qi = Qa - i0 < kSiMaxQ - 1 ? Qa - i0 : kSiMaxQ - 1;

@@ -50,6 +50,7 @@ struct Options {
   std::atomic<int> tile_q{64};        // queries per CTA of the tiled backward
   std::atomic<int> host_async{0};     // 1 = the *_host entries only enqueue; msda_host_sync() completes them
   std::atomic<int> profile{0};        // 1 = bracket the main kernels with CUDA events (msda_profile_read)
+  std::atomic<int> consumer_ctas{0};  // > 0: CTAs of the matcher-cost / IoU kernels (tuning; 0 = auto)
 };
 static Options g_opt;
 
@@ -64,6 +65,7 @@ static std::atomic<int>* find_option(const char* key) {
   if (!strcmp(key, "host_async")) return &g_opt.host_async;
   if (!strcmp(key, "tile_rows")) return &g_opt.tile_rows;
   if (!strcmp(key, "tile_q")) return &g_opt.tile_q;
+  if (!strcmp(key, "consumer_ctas")) return &g_opt.consumer_ctas;
   return nullptr;
 }
 
