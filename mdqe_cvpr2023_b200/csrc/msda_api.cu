@@ -51,6 +51,7 @@ struct Options {
   std::atomic<int> host_async{0};     // 1 = the *_host entries only enqueue; msda_host_sync() completes them
   std::atomic<int> profile{0};        // 1 = bracket the main kernels with CUDA events (msda_profile_read)
   std::atomic<int> consumer_ctas{0};  // > 0: CTAs of the matcher-cost / IoU kernels (tuning; 0 = auto)
+  std::atomic<int> bwd_merge{1};      // 1 = merge grad_value reductions of a (pair, level) that hit the same row (P = 2 or 4); 0 = off (A/B)
 };
 static Options g_opt;
 
@@ -66,6 +67,7 @@ static std::atomic<int>* find_option(const char* key) {
   if (!strcmp(key, "tile_rows")) return &g_opt.tile_rows;
   if (!strcmp(key, "tile_q")) return &g_opt.tile_q;
   if (!strcmp(key, "consumer_ctas")) return &g_opt.consumer_ctas;
+  if (!strcmp(key, "bwd_merge")) return &g_opt.bwd_merge;
   return nullptr;
 }
 
@@ -187,8 +189,9 @@ static void launch_bwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int ch
   const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
   const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
 #define MSDA_BWD2(LPV, GRP) msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP><<<grid, kThreads, 0, st>>>( \
-      v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz)
+      v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz, merge)
   const bool grouped = pb.G > 1 || pb.scale != 1.f;
+  const int merge = (g_opt.bwd_merge.load() != 0 && (pb.P == 4 || pb.P == 2)) ? pb.P : 0;
   switch (pb.L * pb.P) {
     case 16: if (grouped) MSDA_BWD2(16, true); else MSDA_BWD2(16, false); break;
     case 12: if (grouped) MSDA_BWD2(12, true); else MSDA_BWD2(12, false); break;

@@ -132,6 +132,58 @@ __device__ __forceinline__ SampleGeom make_slots2(Slot* dst, int s, float locx, 
   return g;
 }
 
+// The same records kept in registers (backward: they are merged across the points of a level before they are stored).
+template <int D16>
+__device__ __forceinline__ SampleGeom make_slot_regs(Slot (&sl)[4], float locx, float locy, float a, const LevelInfo li,
+                                                     uint32_t n, uint32_t m, int S, int M) {
+  const SampleGeom g = sample_geom(locx, locy, li.H, li.W);
+  const uint32_t row = static_cast<uint32_t>(M) * D16;
+  const uint32_t base = (n * static_cast<uint32_t>(S) + li.start) * row + m * D16;
+  const uint32_t o00 = base + static_cast<uint32_t>(g.y0 * li.W + g.x0) * row;
+  const uint32_t o10 = o00 + static_cast<uint32_t>(li.W) * row;
+  const float hx = 1.f - g.lx, hy = 1.f - g.ly;
+  const bool v00 = g.oky0 && g.okx0, v01 = g.oky0 && g.okx1, v10 = g.oky1 && g.okx0, v11 = g.oky1 && g.okx1;
+  sl[0].off = v00 ? o00 : kInvalidOff;        sl[0].w = v00 ? hx * hy * a : 0.f;
+  sl[1].off = v01 ? o00 + row : kInvalidOff;  sl[1].w = v01 ? g.lx * hy * a : 0.f;
+  sl[2].off = v10 ? o10 : kInvalidOff;        sl[2].w = v10 ? hx * g.ly * a : 0.f;
+  sl[3].off = v11 ? o10 + row : kInvalidOff;  sl[3].w = v11 ? g.lx * g.ly * a : 0.f;
+  return g;
+}
+
+// Backward only: every grad_value reduction of a pair carries the same vector (the pair's grad_out row) times a scalar, so
+// corners of the P points of one (pair, level) that land on the same value row can share ONE reduction with the summed
+// scalar.  The P lanes of the level exchange their four (row, weight) records with xor shuffles; the lowest lane holding a
+// row keeps it with the sum of all weights, the others zero theirs (a zero weight skips the reduction; the gather and the
+// dot product are untouched -- skipping them as well, with the owner's dot forwarded through the dot tile, measured no
+// faster).  The coarse pyramid levels, where the points of a query crowd into a few cells, lose most of their reductions
+// this way -- and L2's reduction rate is what bounds the backward.  The same merge in the forward (one gather
+// per distinct row) costs more in shuffles than the gathers it saves (82 -> 98 us).  All 32 lanes must call.
+template <int PTS>
+__device__ __forceinline__ void merge_level_slots(Slot (&sl)[4], int lane) {
+  const int me = lane & (PTS - 1);
+  float wsum[4];
+  unsigned kill = 0;
+#pragma unroll
+  for (int cn = 0; cn < 4; ++cn) wsum[cn] = sl[cn].w;
+#pragma unroll 1                                     // one partner at a time: 8 shuffled values live, not 24
+  for (int j = 1; j < PTS; ++j) {
+    const bool owner = me < (me ^ j);
+#pragma unroll
+    for (int cp = 0; cp < 4; ++cp) {
+      const uint32_t po = __shfl_xor_sync(0xffffffffu, sl[cp].off, j);
+      const float pw = __shfl_xor_sync(0xffffffffu, sl[cp].w, j);
+#pragma unroll
+      for (int cn = 0; cn < 4; ++cn) {
+        const bool same = sl[cn].off == po;          // two invalid records "match" too: harmless, both are weightless
+        wsum[cn] += same ? pw : 0.f;
+        kill |= (same && !owner) ? (1u << cn) : 0u;
+      }
+    }
+  }
+#pragma unroll
+  for (int cn = 0; cn < 4; ++cn) sl[cn].w = ((kill >> cn) & 1u) ? 0.f : wsum[cn];
+}
+
 // ------------------------------------------------------------------------------------------ forward
 // MINB = minimum resident CTAs per SM promised to ptxas: 3 leaves it 80+ registers, enough to keep a whole
 // batch of gathers in flight; 6 reproduces the register-lean, load-by-load schedule.
@@ -296,7 +348,7 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
                       const LT* __restrict__ aw, const VT* __restrict__ grad_out,
                       float* __restrict__ grad_value, LT* __restrict__ grad_loc, LT* __restrict__ grad_aw,
                       int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq,
-                      int G, float scale, FusedArgs fz) {
+                      int G, float scale, FusedArgs fz, int merge) {
   using C = Cfg2<VT, D, LP>;
   // <grad_out, corner row> per (corner, sample): [4][33] floats per warp.  The partials are folded inside the
   // corner group with shuffles first, so the tile stays tiny and shared memory stays small: the first version
@@ -364,10 +416,20 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
     for (int g = g_begin; g < g_end; ++g) {
       SampleGeom geo;
       int lvl_h = 0, lvl_w = 0;
+      Slot sl[4];
+#pragma unroll
+      for (int cn = 0; cn < 4; ++cn) { sl[cn].off = kInvalidOff; sl[cn].w = 0.f; }
       if (has_sample) {
         const LevelInfo li = s_lvl[g * L + lvl];
         lvl_h = li.H; lvl_w = li.W;
-        geo = make_slots2<C::D16, C::LPP>(my_slots + ps * C::NSLOT, ss, x, y, a, li, n, m, S, M);
+        geo = make_slot_regs<C::D16>(sl, x, y, a, li, n, m, S, M);
+      }
+      if (merge == 4) merge_level_slots<4>(sl, lane);          // warp-uniform: P == 4 (or 2) and the option is on
+      else if (merge == 2) merge_level_slots<2>(sl, lane);
+      if (has_sample) {
+        Slot* dst = my_slots + ps * C::NSLOT + ss;
+#pragma unroll
+        for (int cn = 0; cn < 4; ++cn) dst[cn * C::LPP] = sl[cn];
       }
       __syncwarp();
 
@@ -441,7 +503,7 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
               }
 #pragma unroll
               for (int u = 0; u < kB; ++u) {
-                const bool do_red = valid[u] && !MSDA_DBG_SKIP(4, sgrp * C::SPG + b0 + u);
+                const bool do_red = valid[u] && w[u] != 0.f && !MSDA_DBG_SKIP(4, sgrp * C::SPG + b0 + u);
                 if constexpr (C::CPL == 8) {
                   float* gv = grad_value + static_cast<uint64_t>(off[u]) * 8u + 4 * c;      // off counts 16-byte units of 2-byte elements
                   red_add_f32x4_if(do_red, gv, w[u] * go_red[0], w[u] * go_red[1], w[u] * go_red[2], w[u] * go_red[3]);
