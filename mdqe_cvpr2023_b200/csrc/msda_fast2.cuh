@@ -337,12 +337,16 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 #define MSDA_BWD_BATCH 4                     // tools/bwd_variants.sh builds A/B libraries with other values
 #endif
 #ifndef MSDA_BWD_MINB
-#define MSDA_BWD_MINB 1
+#define MSDA_BWD_MINB 4                      // resident CTAs per SM promised to ptxas for the plain operator: 64 registers, no spills.
+#endif                                       // With the merged reductions the kernel is latency bound, not reduction bound, and
+                                             // 32 resident warps beat 16 (216 -> 185 us; 1/3/5/6: 216/194/192/224, profiles/r01y)
+#ifndef MSDA_BWD_MINB_GROUPED
+#define MSDA_BWD_MINB_GROUPED 1              // the grouped form keeps grad_out rows of all pairs in registers (108) and its calls are small
 #endif
 constexpr int kBwdBatch = MSDA_BWD_BATCH;    // gathers in flight per lane (see the corner loop)
 
 template <typename VT, typename LT, int D, int LP, bool GROUPED>
-__global__ void __launch_bounds__(kThreads, MSDA_BWD_MINB)
+__global__ void __launch_bounds__(kThreads, GROUPED ? MSDA_BWD_MINB_GROUPED : MSDA_BWD_MINB)
 msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                       const int64_t* __restrict__ level_start, const LT* __restrict__ loc,
                       const LT* __restrict__ aw, const VT* __restrict__ grad_out,

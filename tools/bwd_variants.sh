@@ -3,7 +3,7 @@
 # MSDA_B200_LIB pointing at each.  Build here (no GPU needed):  bash tools/bwd_variants.sh build ; on the GPU box: bash tools/bwd_variants.sh run
 cd "$(dirname "$0")/.."
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -shared"
-VARIANTS="2:1 2:5 4:5 8:1 8:3"
+VARIANTS="${VARIANTS:-4:3 2:3 4:4 2:4 8:2 8:3}"
 if [ "$1" = "build" ]; then
   for v in $VARIANTS; do
     b=${v%%:*}; m=${v##*:}
