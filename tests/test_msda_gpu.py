@@ -23,6 +23,7 @@ def _reset_options():
     yield
     for k in ("fwd_variant", "bwd_variant", "chunk_pairs", "mask_variant"):
         _lib.set_option(k, 0)
+    _lib.set_option("bwd_merge", 1)
 
 
 def run_op(inp):
@@ -117,6 +118,39 @@ def test_chunk_sizes(chunk):
     _lib.set_option("chunk_pairs", chunk)
     inp = make_inputs(2, [(12, 20), (6, 10), (3, 5), (2, 3)], 8, 32, 4, dist="local", seed=6)
     check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"chunk {chunk}", inp)
+
+
+@pytest.mark.parametrize("P,case", [(4, "crowded"), (4, "identical"), (4, "border"), (2, "crowded"), (4, "one_cell")])
+def test_backward_merged_reductions(P, case):
+    """The backward merges the grad_value reductions of the P points of a (pair, level) that hit the same value row
+    (csrc/msda_fast2.cuh merge_level_slots).  Cases where nearly every record merges: points crowded into one or two cells,
+    bit-identical points, points straddling the image border (out-of-range corners alias other rows' offsets and must
+    never match), a 1x1 level.  Checked against the oracle and against the unmerged kernel (option bwd_merge = 0)."""
+    from mdqe_cvpr2023_b200 import _lib
+    shapes = [(6, 10), (3, 5), (2, 2), (1, 1)] if case == "one_cell" else [(12, 20), (6, 10), (3, 5), (2, 3)]
+    inp = make_inputs(2, shapes, 8, 32, P, Lq=77, dist="local", seed=11)
+    g = torch.Generator().manual_seed(12)
+    loc = inp["loc"]                                   # [N, Lq, M, L, P, 2]
+    centre = loc[:, :, :, :, :1, :]
+    if case in ("crowded", "one_cell"):
+        loc = centre + 0.02 * torch.randn(loc.shape, generator=g)
+    elif case == "identical":
+        loc = centre.expand_as(loc).clone()
+    else:                                              # points within ~1 cell of the left / top / right / bottom border
+        edge = torch.randint(0, 4, loc.shape[:4] + (1,), generator=g)
+        base = torch.rand(loc.shape[:4] + (1, 2), generator=g)
+        base[..., 0] = torch.where(edge == 0, torch.zeros(()), torch.where(edge == 2, torch.ones(()), base[..., 0]))
+        base[..., 1] = torch.where(edge == 1, torch.zeros(()), torch.where(edge == 3, torch.ones(()), base[..., 1]))
+        loc = base + 0.03 * torch.randn(loc.shape, generator=g)
+    inp["loc"] = loc.contiguous()
+    want = oracle_all(inp)
+    dev = to_cuda(inp)
+    got = run_op(dev)
+    check(got, want, 2e-5, f"merged P{P} {case}", inp, max_kink=1.0 if case == "identical" else 5e-2)
+    _lib.set_option("bwd_merge", 0)
+    plain = run_op(dev)
+    for a, b, n in zip(got, plain, ("out", "grad_value", "grad_loc", "grad_aw")):
+        assert nerr(a, b.cpu().numpy()) <= 1e-5, f"merge on/off differ in {n} ({case})"
 
 
 @pytest.mark.parametrize("loc_dtype", [torch.bfloat16, torch.float32])

@@ -7,7 +7,7 @@ from tools.kernel_bench import timed
 flush = torch.empty(128 * 1024 * 1024, device="cuda")
 inp = to_cuda(make_inputs(4, R50_360, 8, 32, 4, dist="local", seed=0))
 a = (inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["aw"])
-for chunk in (16, 32, 48, 64, 96, 128):
+for chunk in (16, 32, 48, 64, 80, 96, 112, 128, 160, 192, 256):
     _lib.set_option("chunk_pairs", chunk)
     f = timed(lambda: ops.ms_deform_attn_forward(*a, 64), 15, flush)
     b = timed(lambda: ops.ms_deform_attn_backward(*a, inp["grad_out"], 64), 15, flush)
