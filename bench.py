@@ -579,9 +579,21 @@ def main():
                 "traffic": traffic, "traffic_source": traffic_db.get("source") if traffic else None, "avg_launch_us": us, "launches_timed": n, "algorithmic_bytes": nbytes, "peak_source": peak_src}
 
     roofline = roof(bwd_bytes, bwd_ms, bwd_n, "msda_bwd_fast2_kernel<%s,32,16> (encoder shape N=4,S=Lq=5100)" % ("bf16" if args.dtype == "bf16" else "float"))
-    # What actually binds the backward: grad_value is accumulated with fp32 vector reductions into L2, and L2's reduction rate
-    # (measured by tools/red_microbench.cu, see profiles/ncu_traffic.json) is far below HBM-roofline speed for this op.
-    # Reduction bytes per launch = ncu's lts__t_sectors_srcunit_tex_op_red.sum of the same kernel and shape x 32 B.
+    # What actually binds the two sampling kernels: the SM's L1 data pipe, which retires one 128-byte wavefront
+    # per clock -- every gathered corner row, every vector reduction, every shared-memory access and every shuffle is one.
+    # Wavefronts per launch come from the committed ncu capture of the same kernel and shape (profiles/ncu_traffic.json); the
+    # time is the live per-launch figure above and the clock the one sampled during the timed region.  The backward's second
+    # ceiling, L2's fp32 reduction rate (tools/red_microbench.cu), is reported beside it.
+    def l1_pipe(roof_entry, key):
+        if not (roof_entry and args.dtype == "fp32" and args.dist == "local" and traffic_db.get(key)):
+            return None
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        peak = 148 * mhz * 1e6 / 1e9                                  # G wavefronts / s
+        ach = traffic_db[key] / (roof_entry["avg_launch_us"] * 1e-6) / 1e9
+        return {"kernel": roof_entry["kernel"], "bound": "l1_data_pipe_wavefronts", "achieved": ach, "peak": peak, "unit": "Gwavefront/s",
+                "frac": ach / peak, "wavefronts_per_launch": traffic_db[key], "source": traffic_db.get("l1_wavefronts_source")}
+
+    binding = l1_pipe(roofline, "msda_bwd_fast2_kernel_l1_wavefronts")
     l2_reduction = None
     if roofline and args.dtype == "fp32" and args.dist == "local" and traffic_db.get("msda_bwd_fast2_kernel_l2_red_sectors"):
         red_bytes = 32.0 * traffic_db["msda_bwd_fast2_kernel_l2_red_sectors"]
@@ -592,6 +604,7 @@ def main():
     roofline_fwd = roof(fwd_bytes, fwd_ms, fwd_n, "msda_fwd_fast2_kernel<%s,32,16> (encoder shape N=4,S=Lq=5100)" % ("bf16" if args.dtype == "bf16" else "float"))
     mB = QUERIES * MASK_K + MASK_K * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
     mO = QUERIES * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
+    binding_fwd = l1_pipe(roofline_fwd, "msda_fwd_fast2_kernel_l1_wavefronts")
     roofline_mask = roof(mB * esize + mO * esize, mfw_ms, mfw_n, "mask_fwd_tc2_kernel<bf16> (tcgen05)" if args.dtype == "bf16" else "mask_fwd_tc4_kernel<float,false> (tcgen05, 3xTF32)")
     if roofline_mask:
         flops = 2.0 * QUERIES * MASK_K * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
@@ -676,7 +689,8 @@ def main():
                                              "allreduce": "NCCL, %d buckets per step in gradient-ready order: decoder 14.94M fp32 and one 0.76M bucket per encoder layer, each overlapped with the encoder backward still to run" % (1 + n_enc_layers) if world > 1 else None}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "launches_per_step": launches_per_step,
                 "lib_launch_count_per_eager_step": counted_per_step,
-                "roofline": roofline, "roofline_binding_resource": l2_reduction, "roofline_fwd": roofline_fwd, "roofline_mask": roofline_mask,
+                "roofline": roofline, "roofline_binding_resource": binding, "roofline_l2_reductions": l2_reduction,
+                "roofline_fwd": roofline_fwd, "roofline_fwd_binding_resource": binding_fwd, "roofline_mask": roofline_mask,
                 "roofline_mask_bwd": roofline_mask_bwd, "eager_ms_per_step": eager_ms, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

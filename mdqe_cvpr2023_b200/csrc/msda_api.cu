@@ -167,6 +167,10 @@ static bool split_groups(const Problem& pb) {
   return pb.n_pairs < 148LL * 4 * 16;
 }
 
+#ifndef MSDA_FWD_MINB
+#define MSDA_FWD_MINB 6                      // resident CTAs per SM promised to ptxas for the register-lean forward (A/B: tools/fwd_variants.sh)
+#endif
+
 template <typename VT, typename LT, int D, int MINB>
 static void launch_fwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int chunk, const VT* v, const int64_t* shapes,
                            const int64_t* lsi, const LT* lc, const LT* a, VT* o) {
@@ -220,10 +224,10 @@ static int launch_fwd(cudaStream_t st, const Problem& pb, bool fast, const void*
         }
         const bool lean = g_opt.fwd_variant.load() != 3;      // default: register-lean schedule (82 vs 90 us on the encoder shape, profiles/r01d); 3 = batched gathers
         if (pb.D == 32) {
-          if (lean) launch_fwd2_lp<VT, LT, 32, 6>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);
+          if (lean) launch_fwd2_lp<VT, LT, 32, MSDA_FWD_MINB>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);
           else launch_fwd2_lp<VT, LT, 32, 3>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);
         } else {
-          if (lean) launch_fwd2_lp<VT, LT, 24, 6>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);
+          if (lean) launch_fwd2_lp<VT, LT, 24, MSDA_FWD_MINB>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);
           else launch_fwd2_lp<VT, LT, 24, 3>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);
         }
         return after_launch("msda_fwd_fast2_kernel");

@@ -184,43 +184,6 @@ __device__ __forceinline__ void merge_level_slots(Slot (&sl)[4], int lane) {
   for (int cn = 0; cn < 4; ++cn) sl[cn].w = ((kill >> cn) & 1u) ? 0.f : wsum[cn];
 }
 
-// Variant of the merge that also drops the gather and the dot product of a merged record (-DMSDA_BWD_MERGE_GATHERS, A/B):
-// the owner's dot is found through `src` (one byte per corner = corner * kDotStride + owner lane) in the warp's dot tile.
-template <int PTS, int kDotStride>
-__device__ __forceinline__ uint32_t merge_level_slots_src(Slot (&sl)[4], int lane) {
-  const int me = lane & (PTS - 1);
-  float wsum[4];
-  int own[4], ownc[4];                               // lowest lane (within the level) holding this row, and its corner
-#pragma unroll
-  for (int cn = 0; cn < 4; ++cn) { wsum[cn] = sl[cn].w; own[cn] = me; ownc[cn] = cn; }
-#pragma unroll 1
-  for (int j = 1; j < PTS; ++j) {
-    const int pidx = me ^ j;
-#pragma unroll
-    for (int cp = 0; cp < 4; ++cp) {
-      const uint32_t po = __shfl_xor_sync(0xffffffffu, sl[cp].off, j);
-      const float pw = __shfl_xor_sync(0xffffffffu, sl[cp].w, j);
-#pragma unroll
-      for (int cn = 0; cn < 4; ++cn) {
-        const bool same = sl[cn].off == po && po != kInvalidOff;
-        wsum[cn] += same ? pw : 0.f;
-        const bool lower = same && pidx < own[cn];
-        own[cn] = lower ? pidx : own[cn];
-        ownc[cn] = lower ? cp : ownc[cn];
-      }
-    }
-  }
-  uint32_t src = 0;
-#pragma unroll
-  for (int cn = 0; cn < 4; ++cn) {
-    const bool mine = own[cn] == me;
-    sl[cn].w = mine ? wsum[cn] : 0.f;
-    sl[cn].off = mine ? sl[cn].off : kInvalidOff;
-    src |= static_cast<uint32_t>(ownc[cn] * kDotStride + (lane - me + own[cn])) << (8 * cn);
-  }
-  return src;
-}
-
 // ------------------------------------------------------------------------------------------ forward
 // MINB = minimum resident CTAs per SM promised to ptxas: 3 leaves it 80+ registers, enough to keep a whole
 // batch of gathers in flight; 6 reproduces the register-lean, load-by-load schedule.
@@ -465,14 +428,8 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
         lvl_h = li.H; lvl_w = li.W;
         geo = make_slot_regs<C::D16>(sl, x, y, a, li, n, m, S, M);
       }
-#ifdef MSDA_BWD_MERGE_GATHERS
-      uint32_t dot_src = static_cast<uint32_t>(lane) * 0x01010101u + ((3u * kDotStride) << 24 | (2u * kDotStride) << 16 | (1u * kDotStride) << 8);
-      if (merge == 4) dot_src = merge_level_slots_src<4, kDotStride>(sl, lane);
-      else if (merge == 2) dot_src = merge_level_slots_src<2, kDotStride>(sl, lane);
-#else
       if (merge == 4) merge_level_slots<4>(sl, lane);          // warp-uniform: P == 4 (or 2) and the option is on
       else if (merge == 2) merge_level_slots<2>(sl, lane);
-#endif
       if (has_sample) {
         Slot* dst = my_slots + ps * C::NSLOT + ss;
 #pragma unroll
@@ -614,11 +571,7 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
       if (has_sample) {
         float dc[4];                              // per-corner <grad_out, value row>
 #pragma unroll
-#ifdef MSDA_BWD_MERGE_GATHERS
-        for (int e = 0; e < 4; ++e) dc[e] = s_dot[warp][(dot_src >> (8 * e)) & 0xffu];
-#else
         for (int e = 0; e < 4; ++e) dc[e] = dot_r[e * kDotStride];
-#endif
         const float hx = 1.f - geo.lx, hy = 1.f - geo.ly;
         g_aw += hy * (hx * dc[0] + geo.lx * dc[1]) + geo.ly * (hx * dc[2] + geo.lx * dc[3]);
         g_x += static_cast<float>(lvl_w) * (hy * (dc[1] - dc[0]) + geo.ly * (dc[3] - dc[2]));

@@ -19,6 +19,9 @@ KEYS = {
     "lts__t_sector_hit_rate.pct": "l2_hit_pct",
     "l1tex__t_sector_hit_rate.pct": "l1_hit_pct",
     "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "l1_wavefront_pct",
+    "l1tex__data_pipe_lsu_wavefronts.sum": "l1_wavefronts",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum": "l1_wavefronts_shared",
+    "sm__cycles_elapsed.avg": "sm_cycles",
     "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
     "smsp__inst_executed.sum": "warp_instructions",
