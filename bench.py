@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--e2e-sync-every-step", action="store_true", help="drain the host pipeline after every step instead of keeping two steps in flight (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-allreduce", action="store_true", help="debug: multi-GPU step without the gradient all-reduce (not a valid bench value)")
     return ap.parse_args()
 
 
@@ -511,13 +512,14 @@ def main():
             graphs[0].replay()
         else:
             step.run("head")
-        works = [dist.all_reduce(dec_buf, async_op=True)]       # overlaps with the encoder backward below
+        works = [] if args.no_allreduce else [dist.all_reduce(dec_buf, async_op=True)]       # overlaps with the encoder backward below
         for i in range(n_enc_layers):
             if graphs is not None:
                 graphs[1 + i].replay()
             else:
                 step.run(f"tail{i}")
-            works.append(dist.all_reduce(enc_bufs[i], async_op=True))
+            if not args.no_allreduce:
+                works.append(dist.all_reduce(enc_bufs[i], async_op=True))
         for w in works:
             w.wait()
 
