@@ -63,7 +63,8 @@ const char* msda_last_error(void);
 
 /* Tuning knobs (kernel variant selection used by bench.py / tests); unknown keys fail.
  * Keys: "fwd_variant", "bwd_variant", "chunk_pairs", "mask_variant", "profile", "mask_debug", "host_async",
- * "tile_rows", "tile_q".  mask_variant: 0 auto (tensor cores when eligible), 1 SIMT, 2 require tensor cores,
+ * "tile_rows", "tile_q", "consumer_ctas", "bwd_merge" (1 = the backward merges the grad_value reductions of one query's
+ * points that hit the same value row -- default; 0 = one reduction per corner, for A/B).  mask_variant: 0 auto (tensor cores when eligible), 1 SIMT, 2 require tensor cores,
  * 3 / 5 earlier tensor-core kernels and 4 the first SIMT backward (kept for A/B timing). */
 int msda_set_option(const char* key, int value);
 int msda_get_option(const char* key, int* value);
