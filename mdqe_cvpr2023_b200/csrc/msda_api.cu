@@ -3,6 +3,7 @@
 // contract and the reference interfaces each entry replaces.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <deque>
@@ -167,6 +168,24 @@ static bool split_groups(const Problem& pb) {
   return pb.n_pairs < 148LL * 4 * 16;
 }
 
+// The driver's default shared-memory carve-out for the sampling kernels is 132 KB (ncu launch__shared_mem_config_size,
+// profiles/r01z) although their resident CTAs need < 64 KB, which leaves L1 only ~120 KB of the SM's 256 KB.  Asking for exactly
+// what `ctas_per_sm` resident CTAs use (static + 1 KB reserved each) is worth 1-2 % on every backward shape (183 -> 181 us at 360p,
+// 564 -> 560 us at 720p) and nothing on the forward (82 -> 84 us: left at the driver's choice) -- the reuse distance of the
+// gathered rows is beyond either L1 size.  Once per instantiation; MSDA_DEFAULT_CARVEOUT=1 keeps the driver's choice (A/B).
+template <typename K>
+static bool prefer_small_carveout(K kernel, int ctas_per_sm) {
+  const char* env = getenv("MSDA_DEFAULT_CARVEOUT");
+  if (env && env[0] == '1') return false;
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) { cudaGetLastError(); return false; }
+  const size_t need = static_cast<size_t>(ctas_per_sm) * (fa.sharedSizeBytes + 1024);
+  int pct = static_cast<int>((need * 100 + 233471) / 233472);
+  if (pct > 100) pct = 100;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess) { cudaGetLastError(); return false; }
+  return true;
+}
+
 #ifndef MSDA_FWD_MINB
 #define MSDA_FWD_MINB 6                      // resident CTAs per SM promised to ptxas for the register-lean forward (A/B: tools/fwd_variants.sh)
 #endif
@@ -192,8 +211,10 @@ static void launch_bwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int ch
                            const int64_t* lsi, const LT* lc, const LT* a, const VT* go, float* gv, LT* gl, LT* ga) {
   const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
   const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
-#define MSDA_BWD2(LPV, GRP) msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP><<<grid, kThreads, 0, st>>>( \
-      v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz, merge)
+#define MSDA_BWD2(LPV, GRP) do { \
+      static const bool carve = prefer_small_carveout(msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP>, (GRP) ? 2 : MSDA_BWD_MINB); (void)carve; \
+      msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP><<<grid, kThreads, 0, st>>>( \
+      v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz, merge); } while (0)
   const bool grouped = pb.G > 1 || pb.scale != 1.f;
   const int merge = (g_opt.bwd_merge.load() != 0 && (pb.P == 4 || pb.P == 2)) ? pb.P : 0;
   switch (pb.L * pb.P) {
@@ -222,7 +243,10 @@ static int launch_fwd(cudaStream_t st, const Problem& pb, bool fast, const void*
           grid2.y = pb.G;
           if (check_cuda(cudaMemsetAsync(o, 0, (size_t)pb.n_pairs * pb.D * sizeof(VT), st), "cudaMemsetAsync(out)")) return MSDA_ERR_CUDA;
         }
-        const bool lean = g_opt.fwd_variant.load() != 3;      // default: register-lean schedule (82 vs 90 us on the encoder shape, profiles/r01d); 3 = batched gathers
+        // default: register-lean schedule (82 vs 90 us on the encoder shape, profiles/r01d); 3 = batched gathers.  Calls too small
+        // to fill the SMs (the decoder's 196 queries: 392 CTAs) are latency bound and take the batched build (8.2 -> 7.4 us, cold)
+        const bool small_grid = g_opt.fwd_variant.load() == 0 && static_cast<uint64_t>(grid) * grid2.y < 148u * 4u;
+        const bool lean = g_opt.fwd_variant.load() != 3 && !small_grid;
         if (pb.D == 32) {
           if (lean) launch_fwd2_lp<VT, LT, 32, MSDA_FWD_MINB>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);
           else launch_fwd2_lp<VT, LT, 32, 3>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);

@@ -36,16 +36,29 @@ def graph_time(fn):
     return sorted(ts)[len(ts) // 2]
 
 
-inp = to_cuda(make_inputs(4, R50_360, 8, 32, 4, Lq=196, dist="local", seed=0))
-a = (inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["aw"])
-for key, vals in (("fwd_variant", (0, 3)),):
-    for v in vals:
-        _lib.set_option(key, v)
-        print(f"dec spatial fwd  {key}={v}: {graph_time(lambda: ops.ms_deform_attn_forward(*a, 64)):6.2f} us", flush=True)
-    _lib.set_option(key, 0)
+# 8 distinct input sets (8 x 21 MB of value > the 126 MB L2 together with loc/aw/out): every launch finds its rows in HBM
+sets = []
+for k in range(8):
+    inp = to_cuda(make_inputs(4, R50_360, 8, 32, 4, Lq=196, dist="local", seed=k))
+    sets.append(inp)
+
+
+def fwd_all():
+    for inp in sets:
+        ops.ms_deform_attn_forward(inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["aw"], 64)
+
+
+def bwd_all():
+    for inp in sets:
+        ops.ms_deform_attn_backward(inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["aw"], inp["grad_out"], 64)
+
+
+REP = 1
+for v in (0, 3):
+    _lib.set_option("fwd_variant", v)
+    print(f"dec spatial fwd (cold)  fwd_variant={v}: {graph_time(fwd_all) / len(sets):6.2f} us", flush=True)
+_lib.set_option("fwd_variant", 0)
 for chunk in (0, 16, 32):
     _lib.set_option("chunk_pairs", chunk)
-    f = graph_time(lambda: ops.ms_deform_attn_forward(*a, 64))
-    b = graph_time(lambda: ops.ms_deform_attn_backward(*a, inp["grad_out"], 64))
-    print(f"dec spatial chunk={chunk}: fwd {f:6.2f} us  bwd (+memset) {b:6.2f} us", flush=True)
+    print(f"dec spatial (cold) chunk={chunk}: fwd {graph_time(fwd_all) / len(sets):6.2f} us  bwd (+memset) {graph_time(bwd_all) / len(sets):6.2f} us", flush=True)
 _lib.set_option("chunk_pairs", 0)
