@@ -194,10 +194,15 @@ class DeviceStep:
         st = self.torch.cuda.current_stream(self.device).cuda_stream
         rc = 0
         n_enc = sum(1 for k in self.kinds if k == "enc")
-        if part in ("all", "head"):
+        if part in ("all", "head", "fwd"):
             for grouped, a in self.fwd:
                 rc |= (lib.msda_forward_grouped if grouped else lib.msda_forward)(st, *a)
             rc |= lib.mask_logits_forward(st, *self.mask_fwd)
+            if part == "fwd":                                  # inference: forward calls + mask logits only
+                if rc:
+                    from mdqe_cvpr2023_b200 import _lib
+                    raise RuntimeError("C-ABI call failed: " + _lib.last_error())
+                return
             rc |= lib.mask_logits_backward(st, *self.mask_bwd)
         order = list(reversed(self.bwd))                       # decoder calls first, the n_enc encoder calls last
         if part == "head":
@@ -616,6 +621,24 @@ def main():
         roofline_mask["tflops"] = flops / (roofline_mask["avg_launch_us"] * 1e-6) / 1e12
     roofline_mask_bwd = roof((mB + mO + mB) * 4, mbw_ms, mbw_n, "mask_backward_tc: mask_grad_coeff_tc_kernel + mask_fwd_tc4_kernel<float,true> (tcgen05, 3xTF32)")
 
+    # ---- forward only (BASELINE configs[1]: the inference pass of the same clip -- 36 MSDeformAttn forward calls + mask logits)
+    fwd_only = None
+    if world == 1 and not args.no_graph:
+        gf = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gf):
+            step.run("fwd")
+        for _ in range(3):
+            gf.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            gf.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        f_ms = e0.elapsed_time(e1) / args.steps
+        fwd_only = {"ms_per_step": f_ms, "clips_per_s": 1e3 / f_ms, "launches_per_step": len(step.fwd) + 1,
+                    "what": "forward calls of the same clip + mask logits (inference pass), CUDA-graph replay, inputs resident"}
+
     # ---- eager (no graph) step time, for reference
     sync_all()
     libmod.launch_count_reset()
@@ -696,7 +719,7 @@ def main():
                 "lib_launch_count_per_eager_step": counted_per_step,
                 "roofline": roofline, "roofline_binding_resource": binding, "roofline_l2_reductions": l2_reduction,
                 "roofline_fwd": roofline_fwd, "roofline_fwd_binding_resource": binding_fwd, "roofline_mask": roofline_mask,
-                "roofline_mask_bwd": roofline_mask_bwd, "eager_ms_per_step": eager_ms, "cpu_baseline": cpu}
+                "roofline_mask_bwd": roofline_mask_bwd, "eager_ms_per_step": eager_ms, "forward_only": fwd_only, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
