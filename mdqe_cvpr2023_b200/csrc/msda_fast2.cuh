@@ -354,10 +354,13 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
                       int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq,
                       int G, float scale, FusedArgs fz, int merge) {
   using C = Cfg2<VT, D, LP>;
-  // <grad_out, corner row> per (corner, sample): [4][33] floats per warp.  The partials are folded inside the
+  // <grad_out, corner row> per (corner, sample): [4][40] floats per warp.  The partials are folded inside the
   // corner group with shuffles first, so the tile stays tiny and shared memory stays small: the first version
   // kept per-lane partials (34 KB per CTA), which left only ~16 KB of L1 per SM and cost the gathers their hit rate.
-  constexpr int kDotStride = 33;
+  // stride 40 = 8 (mod 32): the four corner groups' stores (lane c of group g writes entry g * stride + c) land in disjoint bank
+  // octets, and the sample lanes' reads (entry e * stride + lane) are conflict-free for any stride; 33 made the stores 4-way
+  // conflicted (ncu: 6 of 8 store wavefronts per pair excessive)
+  constexpr int kDotStride = 40;
   __shared__ LevelInfo s_lvl[kMaxLevels];
   __shared__ __align__(16) Slot s_slot[kWarpsPerCta][C::QPW * C::NSLOT];
   __shared__ float s_dot[kWarpsPerCta][4 * kDotStride];
