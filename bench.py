@@ -715,7 +715,10 @@ def main():
                 "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
                 "config": config_dict(args, {"launch": "cuda_graph" if graph is not None else "eager",
                                              "allreduce": "NCCL, %d buckets per step in gradient-ready order: decoder 14.94M fp32 and one 0.76M bucket per encoder layer, each overlapped with the encoder backward still to run" % (1 + n_enc_layers) if world > 1 else None}),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "launches_per_step": launches_per_step,
+                # kernels of this library launched inside the timed region: the library's own launch counter over an eager pass of
+                # the same step (the graph replays re-launch exactly those kernels) x steps; `launches_per_step` is the C-ABI call count
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(round(counted_per_step * args.steps)) if counted_per_step else gpu_launches,
+                "launches_per_step": launches_per_step,
                 "lib_launch_count_per_eager_step": counted_per_step,
                 "roofline": roofline, "roofline_binding_resource": binding, "roofline_l2_reductions": l2_reduction,
                 "roofline_fwd": roofline_fwd, "roofline_fwd_binding_resource": binding_fwd, "roofline_mask": roofline_mask,
