@@ -53,12 +53,35 @@ def bwd_all():
         ops.ms_deform_attn_backward(inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["aw"], inp["grad_out"], 64)
 
 
+# the clip-level (grouped temporal) call of the bench: G = 4 level tables, T = 4 frames as "levels", 196 queries, N = 1
+T, S = 4, sum(h * w for h, w in R50_360)
+shapes_l = torch.tensor(R50_360, dtype=torch.long)
+lsi_l = torch.cat([shapes_l.new_zeros(1), (shapes_l[:, 0] * shapes_l[:, 1]).cumsum(0)[:-1]])
+gsets = []
+for k in range(8):
+    g = torch.Generator().manual_seed(100 + k)
+    gsets.append(dict(
+        value=torch.randn(1, T * S, 8, 32, generator=g).cuda(),
+        shapes=shapes_l.view(4, 1, 2).expand(4, T, 2).contiguous().cuda(),
+        lsi=(lsi_l.view(4, 1) + (torch.arange(T) * S).view(1, T)).contiguous().cuda(),
+        loc=torch.rand(1, 196, 8, T, 4, 2, generator=g).cuda(),
+        aw=torch.softmax(torch.randn(1, 196, 8, T * 4, generator=g), -1).view(1, 196, 8, T, 4).cuda(),
+        go=torch.randn(1, 196, 256, generator=g).cuda()))
+
+
+def gfwd_all():
+    for d in gsets:
+        ops.ms_deform_attn_grouped_forward(d["value"], d["shapes"], d["lsi"], d["loc"], d["aw"], 0.25)
+
+
+def gbwd_all():
+    for d in gsets:
+        ops.ms_deform_attn_grouped_backward(d["value"], d["shapes"], d["lsi"], d["loc"], d["aw"], d["go"], 0.25)
+
+
 REP = 1
-for v in (0, 3):
-    _lib.set_option("fwd_variant", v)
-    print(f"dec spatial fwd (cold)  fwd_variant={v}: {graph_time(fwd_all) / len(sets):6.2f} us", flush=True)
-_lib.set_option("fwd_variant", 0)
-for chunk in (0, 16, 32):
-    _lib.set_option("chunk_pairs", chunk)
-    print(f"dec spatial (cold) chunk={chunk}: fwd {graph_time(fwd_all) / len(sets):6.2f} us  bwd (+memset) {graph_time(bwd_all) / len(sets):6.2f} us", flush=True)
-_lib.set_option("chunk_pairs", 0)
+print(f"cold: dec spatial fwd {graph_time(fwd_all) / 8:6.2f} us  bwd+memset {graph_time(bwd_all) / 8:6.2f} us | "
+      f"grouped fwd {graph_time(gfwd_all) / 8:6.2f} us  bwd+memset {graph_time(gbwd_all) / 8:6.2f} us", flush=True)
+# Measured and dropped (fourth session): one pair per warp round for calls too small to fill the SMs (twice the CTAs, half the
+# per-warp chain): dec spatial fwd 7.24 -> 8.92 us, bwd 17.6 -> 20.1 us, grouped fwd 9.0 -> 10.7 us -- CTA scheduling, not the
+# warp's latency chain, is what these calls wait for.
