@@ -185,6 +185,9 @@ __device__ __forceinline__ void merge_level_slots(Slot (&sl)[4], int lane) {
 }
 
 // ------------------------------------------------------------------------------------------ forward
+#ifndef MSDA_FWD_PAIR_FOLD
+#define MSDA_FWD_PAIR_FOLD 1
+#endif
 // MINB = minimum resident CTAs per SM promised to ptxas: 3 leaves it 80+ registers, enough to keep a whole
 // batch of gathers in flight; 6 reproduces the register-lean, load-by-load schedule.
 template <typename VT, typename LT, int D, int LP, int MINB, bool GROUPED>
@@ -240,8 +243,13 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
     a *= scale;
     // GROUPED keeps one accumulator set per pair alive across the G level tables; the plain operator (G == 1)
     // reduces and stores each pair as soon as its corner loop ends (fewer live registers: 81 vs 94 us measured)
-    float acc_g[GROUPED ? C::QPW : 1][C::CPL];
-    if constexpr (GROUPED) {
+    // kPairFold (plain operator, two pairs per round, four corner groups of 8 lanes, 4 channels per lane): both pairs' partial
+    // sums are folded across the corner groups by ONE transposing butterfly -- 4 + 2 shuffles per round instead of 2 x 8 -- which
+    // leaves lane (pair, half, c) with channels 4c + 2*half + {0,1} of its pair: one 8-byte store per lane.  Every shuffle is a
+    // wavefront on the L1 data pipe that binds this kernel.
+    constexpr bool kPairFold = MSDA_FWD_PAIR_FOLD && !GROUPED && C::QPW == 2 && C::NG == 4 && C::G == 8 && C::CPL == 4 && C::kAllLanes;
+    float acc_g[(GROUPED || kPairFold) ? C::QPW : 1][C::CPL];
+    if constexpr (GROUPED || kPairFold) {
 #pragma unroll
       for (int pl = 0; pl < C::QPW; ++pl)
 #pragma unroll
@@ -292,9 +300,9 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 #pragma unroll
               for (int j = 0; j < C::CPL; ++j) acc[j] = fmaf(w[u], v[u][j], acc[j]);
           }
-          if constexpr (GROUPED) {
+          if constexpr (GROUPED || kPairFold) {
 #pragma unroll
-            for (int j = 0; j < C::CPL; ++j) acc_g[GROUPED ? pl : 0][j] = acc[j];
+            for (int j = 0; j < C::CPL; ++j) acc_g[(GROUPED || kPairFold) ? pl : 0][j] = acc[j];
           } else {
 #pragma unroll
             for (int k = C::NG / 2; k >= 1; k >>= 1) {
@@ -308,6 +316,28 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
       __syncwarp();
     }
 
+    if constexpr (kPairFold) {
+      const bool hi_pair = (lane & 16) != 0, hi_half = (lane & 8) != 0;
+      float keep[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float mine = hi_pair ? acc_g[kPairFold ? 1 : 0][j] : acc_g[0][j];
+        const float send = hi_pair ? acc_g[0][j] : acc_g[kPairFold ? 1 : 0][j];
+        keep[j] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+      float two[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float mine = hi_half ? keep[2 + i] : keep[i];
+        const float send = hi_half ? keep[i] : keep[2 + i];
+        two[i] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      const int pl = lane >> 4;
+      if (pl < npair) {
+        if constexpr (std::is_same<VT, float>::value)
+          *reinterpret_cast<float2*>(out + static_cast<int64_t>(p0 + pl) * D + (lane & 7) * 4 + (hi_half ? 2 : 0)) = make_float2(two[0], two[1]);
+      }
+    }
     if constexpr (GROUPED) {
 #pragma unroll
       for (int pl = 0; pl < C::QPW; ++pl) {
