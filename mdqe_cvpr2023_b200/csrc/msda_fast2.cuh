@@ -158,26 +158,40 @@ __device__ __forceinline__ SampleGeom make_slot_regs(Slot (&sl)[4], float locx, 
 // faster).  The coarse pyramid levels, where the points of a query crowd into a few cells, lose most of their reductions
 // this way -- and L2's reduction rate is what bounds the backward.  The same merge in the forward (one gather
 // per distinct row) costs more in shuffles than the gathers it saves (82 -> 98 us).  All 32 lanes must call.
+// Rows are matched through their cells, not their offsets: lanes exchange ONE packed cell coordinate (x0 + 8 | (y0 + 8) << 16) and
+// their four weights (5 shuffles per partner instead of 8); with (ex, ey) = partner cell - own cell, own corner (dx, dy) coincides
+// with partner corner (dx - ex, dy - ey) when that lies in {0,1}^2, i.e. the partner's 2x2 weights shifted by (ex, ey) are what is
+// added -- two select stages instead of sixteen compares.  Cells coincide exactly when row offsets do (same pair, same level); an
+// out-of-range cell is out of range for both lanes (weight 0, invalid offset), so merging it is a no-op.  `key` must be a value
+// no other lane of the level can match (kNoMergeKey) for lanes without a sample and for levels wider than the 15-bit fields.
+constexpr uint32_t kNoMergeKey = 0xFFFF8000u;
 template <int PTS>
-__device__ __forceinline__ void merge_level_slots(Slot (&sl)[4], int lane) {
+__device__ __forceinline__ void merge_level_slots(Slot (&sl)[4], uint32_t key, int lane) {
   const int me = lane & (PTS - 1);
+  const int cx = static_cast<int>(key & 0xffffu), cy = static_cast<int>(key >> 16);
   float wsum[4];
   unsigned kill = 0;
 #pragma unroll
   for (int cn = 0; cn < 4; ++cn) wsum[cn] = sl[cn].w;
-#pragma unroll 1                                     // one partner at a time: 8 shuffled values live, not 24
+#pragma unroll 1                                     // one partner at a time: 5 shuffled values live, not 15
   for (int j = 1; j < PTS; ++j) {
-    const bool owner = me < (me ^ j);
+    const bool lower_partner = (me ^ j) < me;
+    const uint32_t pk = __shfl_xor_sync(0xffffffffu, key, j);
+    float pw[4];
 #pragma unroll
-    for (int cp = 0; cp < 4; ++cp) {
-      const uint32_t po = __shfl_xor_sync(0xffffffffu, sl[cp].off, j);
-      const float pw = __shfl_xor_sync(0xffffffffu, sl[cp].w, j);
-#pragma unroll
-      for (int cn = 0; cn < 4; ++cn) {
-        const bool same = sl[cn].off == po;          // two invalid records "match" too: harmless, both are weightless
-        wsum[cn] += same ? pw : 0.f;
-        kill |= (same && !owner) ? (1u << cn) : 0u;
-      }
+    for (int cp = 0; cp < 4; ++cp) pw[cp] = __shfl_xor_sync(0xffffffffu, sl[cp].w, j);
+    const int ex = static_cast<int>(pk & 0xffffu) - cx, ey = static_cast<int>(pk >> 16) - cy;
+    const bool x0 = ex == 0, xm = ex == -1, xp = ex == 1, y0 = ey == 0, ym = ey == -1, yp = ey == 1;
+    // partner row r (0: y0, 1: y0 + 1) seen from own column dx
+    const float a00 = x0 ? pw[0] : (xm ? pw[1] : 0.f), a01 = x0 ? pw[1] : (xp ? pw[0] : 0.f);
+    const float a10 = x0 ? pw[2] : (xm ? pw[3] : 0.f), a11 = x0 ? pw[3] : (xp ? pw[2] : 0.f);
+    wsum[0] += y0 ? a00 : (ym ? a10 : 0.f);
+    wsum[1] += y0 ? a01 : (ym ? a11 : 0.f);
+    wsum[2] += y0 ? a10 : (yp ? a00 : 0.f);
+    wsum[3] += y0 ? a11 : (yp ? a01 : 0.f);
+    if (lower_partner) {                             // a lower lane holds the cell: it keeps the record
+      const bool mx0 = x0 || xm, mx1 = x0 || xp, my0 = y0 || ym, my1 = y0 || yp;
+      kill |= (mx0 && my0 ? 1u : 0u) | (mx1 && my0 ? 2u : 0u) | (mx0 && my1 ? 4u : 0u) | (mx1 && my1 ? 8u : 0u);
     }
   }
 #pragma unroll
@@ -456,13 +470,16 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
       Slot sl[4];
 #pragma unroll
       for (int cn = 0; cn < 4; ++cn) { sl[cn].off = kInvalidOff; sl[cn].w = 0.f; }
+      uint32_t cell_key = kNoMergeKey + 4u * static_cast<uint32_t>(lane & 3);
       if (has_sample) {
         const LevelInfo li = s_lvl[g * L + lvl];
         lvl_h = li.H; lvl_w = li.W;
         geo = make_slot_regs<C::D16>(sl, x, y, a, li, n, m, S, M);
+        if (li.H < 32752 && li.W < 32752)
+          cell_key = static_cast<uint32_t>(geo.x0 + 8) | (static_cast<uint32_t>(geo.y0 + 8) << 16);
       }
-      if (merge == 4) merge_level_slots<4>(sl, lane);          // warp-uniform: P == 4 (or 2) and the option is on
-      else if (merge == 2) merge_level_slots<2>(sl, lane);
+      if (merge == 4) merge_level_slots<4>(sl, cell_key, lane);          // warp-uniform: P == 4 (or 2) and the option is on
+      else if (merge == 2) merge_level_slots<2>(sl, cell_key, lane);
       if (has_sample) {
         Slot* dst = my_slots + ps * C::NSLOT + ss;
 #pragma unroll
