@@ -29,3 +29,6 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:matc
     python tools/consumers_bench.py > gpurun_out/ncu_match_cost_${TAG}.log 2>&1; echo "ncu match_cost rc=$?"
 echo "== encoder-shape fwd / bwd quick table"; timeout 300 python tools/bwd_quick.py > gpurun_out/bwd_quick_${TAG}.log 2>&1; tail -12 gpurun_out/bwd_quick_${TAG}.log
 ls -la gpurun_out | tail -20
+echo "== backward merge on/off, decoder-sized calls (cold)"; timeout 200 python tools/merge_ab.py > gpurun_out/merge_ab_${TAG}.log 2>&1; grep float32 gpurun_out/merge_ab_${TAG}.log
+timeout 200 python tools/small_calls_ab.py > gpurun_out/small_calls_${TAG}.log 2>&1; tail -2 gpurun_out/small_calls_${TAG}.log
+timeout 200 python tools/module_bench.py > gpurun_out/module_bench_${TAG}.log 2>&1; tail -3 gpurun_out/module_bench_${TAG}.log
