@@ -254,7 +254,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
 }
 
 // fp32 accumulation image -> bf16 grad_value
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 cvt_f32_to_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t n4) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {

@@ -18,6 +18,7 @@
 
 namespace msda {
 
+
 #ifdef MSDA_DBG_MASK
 // timing experiments only (tools/whatif_bench.py builds a separate library with -DMSDA_DBG_MASK): per-level bits that
 // drop work from the kernels -- bits 0-3 forward gathers, 4-7 backward reductions, 8-11 backward gathers + reductions
@@ -199,6 +200,12 @@ __device__ __forceinline__ void merge_level_slots(Slot (&sl)[4], uint32_t key, i
 }
 
 // ------------------------------------------------------------------------------------------ forward
+#ifndef MSDA_PACKED_FMA
+#define MSDA_PACKED_FMA 1       // fma.rn.f32x2 (sm_100): two channels per FMA instruction
+#endif
+#ifndef MSDA_FWD_LEAN_BATCH
+#define MSDA_FWD_LEAN_BATCH 4
+#endif
 #ifndef MSDA_FWD_PAIR_FOLD
 #define MSDA_FWD_PAIR_FOLD 1
 #endif
@@ -287,7 +294,8 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
           const uint4* stream = reinterpret_cast<const uint4*>(my_stream + pl * C::NSLOT);
           // Batches of kBatch corner rows: slot records, then the gathers, then the FMAs (with MINB = 3 ptxas keeps
           // the whole batch in flight; the default register-lean build interleaves them, which measured faster).
-          constexpr int kBatch = (C::SPG % 8 == 0) ? 8 : ((C::SPG % 6 == 0) ? 6 : ((C::SPG % 4 == 0) ? 4 : 2));   // must divide SPG
+          constexpr int kWant = MINB >= 5 ? MSDA_FWD_LEAN_BATCH : 8;      // gathers in flight per lane: what the register budget allows
+          constexpr int kBatch = (C::SPG % kWant == 0) ? kWant : ((C::SPG % 6 == 0 && kWant > 6) ? 6 : ((C::SPG % 4 == 0 && kWant > 4) ? 4 : 2));   // must divide SPG
           static_assert(C::SPG % kBatch == 0 && kBatch % 2 == 0, "batch must tile the slot stream");
 #pragma unroll
           for (int b0 = 0; b0 < C::SPG; b0 += kBatch) {
@@ -299,20 +307,26 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
               off[2 * i] = two.x; w[2 * i] = __uint_as_float(two.y);
               off[2 * i + 1] = two.z; w[2 * i + 1] = __uint_as_float(two.w);
             }
-            float v[kBatch][C::CPL];
+            // a corner that is out of range has weight 0: gather and FMAs sit under ONE condition, so ptxas predicates both
+            // and the destination registers need no zero-fill
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
               if (active && w[u] != 0.f && !MSDA_DBG_SKIP(0, sgrp * C::SPG + b0 + u)) {
-                Vec16<VT>::load(row_ptr(vlane, off[u]), v[u]);
-              } else {
+                float v[C::CPL];
+                Vec16<VT>::load(row_ptr(vlane, off[u]), v);
+#if MSDA_PACKED_FMA
+                const float2 ww = make_float2(w[u], w[u]);
 #pragma unroll
-                for (int j = 0; j < C::CPL; ++j) v[u][j] = 0.f;
+                for (int j = 0; j < C::CPL; j += 2) {
+                  const float2 r = __ffma2_rn(ww, make_float2(v[j], v[j + 1]), make_float2(acc[j], acc[j + 1]));
+                  acc[j] = r.x; acc[j + 1] = r.y;
+                }
+#else
+#pragma unroll
+                for (int j = 0; j < C::CPL; ++j) acc[j] = fmaf(w[u], v[j], acc[j]);
+#endif
               }
             }
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u)
-#pragma unroll
-              for (int j = 0; j < C::CPL; ++j) acc[j] = fmaf(w[u], v[u][j], acc[j]);
           }
           if constexpr (GROUPED || kPairFold) {
 #pragma unroll

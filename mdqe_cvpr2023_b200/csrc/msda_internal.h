@@ -1,6 +1,8 @@
 // Internal glue shared by the translation units of libmsda_b200.so (not part of the public ABI).
 #pragma once
 
+#include <atomic>
+
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -17,6 +19,20 @@ int check_cuda(cudaError_t err, const char* what);
 int after_launch(const char* kernel_name);
 
 int option(const char* key);          // current value of a tuning knob
+
+struct Options {
+  std::atomic<int> fwd_variant{0};    // 0 = auto (fast2 / fast when eligible), 1 = force generic, 2 = first-generation fast, 3 = fast2 with batched gathers (80 registers)
+  std::atomic<int> bwd_variant{0};    // 0 = auto (fast2 / fast), 1 = generic, 2 = first-generation fast
+  std::atomic<int> chunk_pairs{0};    // 0 = auto
+  std::atomic<int> mask_variant{0};   // 0 = auto (tcgen05 when eligible), 1 = SIMT fp32, 2 = force tcgen05, 3/5 = earlier tensor-core kernels (A/B), 4 = first fused SIMT backward
+  std::atomic<int> mask_debug{0};     // 1 = the tcgen05 mask kernel records per-item clock stamps of CTA 0
+  std::atomic<int> host_async{0};     // 1 = the *_host entries only enqueue; msda_host_sync() completes them
+  std::atomic<int> profile{0};        // 1 = bracket the main kernels with CUDA events (msda_profile_read)
+  std::atomic<int> consumer_ctas{0};  // > 0: CTAs of the matcher-cost / IoU kernels (tuning; 0 = auto)
+  std::atomic<int> bwd_merge{1};      // 1 = merge grad_value reductions of a (pair, level) that hit the same row (P = 2 or 4); 0 = off (A/B)
+};
+const Options& options();
+
 
 // RAII event bracket around one kernel launch; active only when the "profile" option is 1 and the
 // stream is not being captured into a CUDA graph.

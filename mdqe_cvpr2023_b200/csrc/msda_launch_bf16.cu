@@ -1,0 +1,6 @@
+// Sampling kernels for one dtype combination (value, location / weight, grad_value accumulator): see msda_launch.cuh.
+#include "msda_launch.cuh"
+
+namespace msda {
+MSDA_LAUNCH_EXTERN(, __nv_bfloat16, __nv_bfloat16, float)
+}  // namespace msda
