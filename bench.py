@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- MDQE hot-path throughput on B200: MSDeformAttn fwd+bwd clips/s (+ roofline, CPU baseline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dist local|uniform]
-                    [--dtype fp32|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shape r50_360|r50_720|swinl_360]
+                    [--dist local|uniform] [--dtype fp32|bf16] [--arm abi|module]
 
-One *step* = the hot path of ONE training clip per GPU at the R50_ovis_360 shape (BASELINE.json
-configs[1]; T=4 frames 384x640 padded, 4-level pyramid 48x80..6x10 => S=5100, 8 heads x D=32, 4 points):
+One *step* = the hot path of ONE training clip per GPU.  The headline configuration is the R50_ovis_360 shape
+(BASELINE.json configs[1]; T=4 frames 384x640 padded, 4-level pyramid 48x80..6x10 => S=5100, 8 heads x D=32, 4 points):
 
   36 MSDeformAttn forward + 36 backward calls through the C ABI of libmsda_b200.so
      6 encoder layers        N=4 frames, Lq=S=5100, L=4          (transformer_enc.py:100-110)
@@ -21,7 +21,10 @@ output buffers (~1.5 GB per step, so no call finds its inputs in the 126 MB L2).
 Output: ONE JSON line (rank 0).  `value` is clips/s with inputs resident in HBM (CUDA-graph replay of the
 step, CUDA events, max over ranks); `e2e` is the same step through the *_host C-ABI entries with pinned
 host buffers (H2D of every input and D2H of every output inside the timed region); `roofline` is the
-dominant kernel (encoder-shape backward) timed per launch with CUDA events on its stream;
+dominant kernel (encoder-shape backward) timed per launch with CUDA events on its stream; `other_configs`
+carries the other BASELINE.json configurations (R50_ovis_720 training step, swinl_ytvis21 inference and training,
+bf16 storage) measured the same way in the same run; `module_arm` is the step through the
+`mdqe_cvpr2023_b200.MSDeformAttn` modules (Linear layers + fused sampler, torch autograd, CUDA graph);
 `cpu_baseline` / `--impl reference` time oracle/torch_port.py (the reference's CPU path restated:
 F.grid_sample + autograd) on the host cores.
 """
@@ -39,10 +42,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-PYRAMID = [(48, 80), (24, 40), (12, 20), (6, 10)]   # R50_ovis_360: 384x640 padded frame, strides 8..64
-T_FRAMES, HEADS, HEAD_DIM, POINTS, QUERIES, MASK_K = 4, 8, 32, 4, 196, 32
-MASK_PLANE = (96, 160)
-N_LAYERS = 6
+HEADS, POINTS, QUERIES, N_LAYERS = 8, 4, 196, 6
+# configs/R50_ovis_360.yaml:36,44 / R50_ovis_720.yaml:37,45 / swinl_ytvis21.yaml:33,41 (SURVEY 8 shape table)
+SHAPES = {
+    "r50_360": dict(name="R50_ovis_360", pyramid=[(48, 80), (24, 40), (12, 20), (6, 10)], frames=4, head_dim=32, mask_k=32,
+                    mask_plane=(96, 160)),
+    "r50_720": dict(name="R50_ovis_720", pyramid=[(80, 144), (40, 72), (20, 36), (10, 18)], frames=4, head_dim=32, mask_k=32,
+                    mask_plane=(160, 288)),
+    "swinl_360": dict(name="swinl_ytvis21", pyramid=[(48, 80), (24, 40), (12, 20), (6, 10)], frames=3, head_dim=24, mask_k=24,
+                      mask_plane=(96, 160)),
+}
 METRIC = "msda_fwd_bwd_clips_per_s"
 UNIT = "clips/s"
 
@@ -53,6 +62,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="r50_360", choices=sorted(SHAPES), help="headline workload (default: BASELINE.json configs[1])")
+    ap.add_argument("--arm", default="abi", choices=["abi", "module"], help="abi: the raw C-ABI step (headline); module: only the MSDeformAttn-module step")
     ap.add_argument("--dist", default="local", choices=["local", "uniform"])
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--layers", type=int, default=N_LAYERS, help="debug: fewer layers (the result is then not a valid bench value)")
@@ -61,62 +72,66 @@ def parse_args():
     ap.add_argument("--e2e-sync-every-step", action="store_true", help="drain the host pipeline after every step instead of keeping two steps in flight (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the other BASELINE configurations and the module arm")
+    ap.add_argument("--no-prezero", action="store_true", help="A/B: zero-fill grad_value inside every backward call (on the critical path) instead of on a side branch")
     ap.add_argument("--no-allreduce", action="store_true", help="debug: multi-GPU step without the gradient all-reduce (not a valid bench value)")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------------------- workload
-def ref_points(torch, shapes):
+def ref_points(torch, shapes, device="cpu"):
     pts = []
     for H, W in shapes:
-        ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32) + 0.5, torch.arange(W, dtype=torch.float32) + 0.5,
-                                indexing="ij")
+        ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=device) + 0.5,
+                                torch.arange(W, dtype=torch.float32, device=device) + 0.5, indexing="ij")
         pts.append(torch.stack([xs.reshape(-1) / W, ys.reshape(-1) / H], -1))
     return torch.cat(pts)
 
 
-def make_loc(torch, g, ref, N, Lq, L, dist):
-    if dist == "uniform":
-        return torch.rand(N, Lq, HEADS, L, POINTS, 2, generator=g)
-    loc = ref.view(1, Lq, 1, 1, 1, 2) + 0.05 * torch.randn(N, Lq, HEADS, L, POINTS, 2, generator=g)
-    return loc.clamp_(-0.1, 1.1)
-
-
-def build_calls(torch, dist, seed, layers):
-    """CPU tensors of every MSDA call of one clip, in forward order, plus the mask operands."""
-    g = torch.Generator().manual_seed(seed)
-    shapes = torch.tensor(PYRAMID, dtype=torch.long)
+def build_calls(torch, shape, dist, seed, layers, device="cpu"):
+    """Tensors of every MSDA call of one clip, in forward order, plus the mask operands.  device="cpu": seeded CPU tensors
+    (the headline configuration: the host-buffer arm and the CPU baseline need them); a CUDA device: generated there."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    pyr, T, D = shape["pyramid"], shape["frames"], shape["head_dim"]
+    kw = dict(generator=g, device=device)
+    shapes = torch.tensor(pyr, dtype=torch.long, device=device)
     sizes = shapes[:, 0] * shapes[:, 1]
     S = int(sizes.sum())
     lsi = torch.cat([sizes.new_zeros(1), sizes.cumsum(0)[:-1]])
-    pix = ref_points(torch, PYRAMID)
+    pix = ref_points(torch, pyr, device)
+
+    def make_loc(ref, N, Lq, L):
+        if dist == "uniform":
+            return torch.rand(N, Lq, HEADS, L, POINTS, 2, **kw)
+        loc = ref.view(1, Lq, 1, 1, 1, 2) + 0.05 * torch.randn(N, Lq, HEADS, L, POINTS, 2, **kw)
+        return loc.clamp_(-0.1, 1.1)
 
     def aw_(N, Lq, L):
-        return torch.softmax(torch.randn(N, Lq, HEADS, L * POINTS, generator=g), -1).view(N, Lq, HEADS, L, POINTS)
+        return torch.softmax(torch.randn(N, Lq, HEADS, L * POINTS, **kw), -1).view(N, Lq, HEADS, L, POINTS)
 
     calls = []
     for _ in range(layers):                                   # encoder self-attention, queries = pixels
-        calls.append(dict(kind="enc", value=torch.randn(T_FRAMES, S, HEADS, HEAD_DIM, generator=g), shapes=shapes,
-                          lsi=lsi, loc=make_loc(torch, g, pix, T_FRAMES, S, 4, dist), aw=aw_(T_FRAMES, S, 4),
-                          go=torch.randn(T_FRAMES, S, HEADS * HEAD_DIM, generator=g)))
+        calls.append(dict(kind="enc", value=torch.randn(T, S, HEADS, D, **kw), shapes=shapes,
+                          lsi=lsi, loc=make_loc(pix, T, S, 4), aw=aw_(T, S, 4), go=torch.randn(T, S, HEADS * D, **kw)))
     for _ in range(layers):                                   # decoder: frame-level then clip-level cross-attention
-        qref = torch.rand(QUERIES, 2, generator=g)
-        calls.append(dict(kind="dec_spatial", value=torch.randn(T_FRAMES, S, HEADS, HEAD_DIM, generator=g), shapes=shapes,
-                          lsi=lsi, loc=make_loc(torch, g, qref, T_FRAMES, QUERIES, 4, dist), aw=aw_(T_FRAMES, QUERIES, 4),
-                          go=torch.randn(T_FRAMES, QUERIES, HEADS * HEAD_DIM, generator=g)))
-        value_t = torch.randn(1, T_FRAMES * S, HEADS, HEAD_DIM, generator=g)
-        loc_t = make_loc(torch, g, qref, 1, QUERIES, T_FRAMES, dist)
-        aw_t = aw_(1, QUERIES, T_FRAMES)
-        go_t = torch.randn(1, QUERIES, HEADS * HEAD_DIM, generator=g)
+        qref = torch.rand(QUERIES, 2, **kw)
+        calls.append(dict(kind="dec_spatial", value=torch.randn(T, S, HEADS, D, **kw), shapes=shapes,
+                          lsi=lsi, loc=make_loc(qref, T, QUERIES, 4), aw=aw_(T, QUERIES, 4),
+                          go=torch.randn(T, QUERIES, HEADS * D, **kw)))
+        value_t = torch.randn(1, T * S, HEADS, D, **kw)
+        loc_t = make_loc(qref, 1, QUERIES, T)
+        aw_t = aw_(1, QUERIES, T)
+        go_t = torch.randn(1, QUERIES, HEADS * D, **kw)
+        frame_base = torch.arange(T, device=device) * S
         for lvl in range(4):                                  # reference form: one call per pyramid level; "levels" = the T frames
-            calls.append(dict(kind="dec_temporal", value=value_t, shapes=shapes[lvl].view(1, 2).expand(T_FRAMES, 2).contiguous(),
-                              lsi=torch.arange(T_FRAMES) * S + lsi[lvl], loc=loc_t, aw=aw_t, go=go_t))
+            calls.append(dict(kind="dec_temporal", value=value_t, shapes=shapes[lvl].view(1, 2).expand(T, 2).contiguous(),
+                              lsi=frame_base + lsi[lvl], loc=loc_t, aw=aw_t, go=go_t))
         # the same four calls as ONE grouped launch (msda_forward_grouped: G = 4 level tables, mean folded in)
-        calls.append(dict(kind="dec_temporal_grouped", value=value_t, shapes=shapes.view(4, 1, 2).expand(4, T_FRAMES, 2).contiguous(),
-                          lsi=(lsi.view(4, 1) + (torch.arange(T_FRAMES) * S).view(1, T_FRAMES)).contiguous(), loc=loc_t, aw=aw_t, go=go_t))
-    mask = dict(coeff=torch.tanh(torch.randn(1, QUERIES, MASK_K, generator=g)),
-                proto=torch.randn(1, MASK_K, T_FRAMES, *MASK_PLANE, generator=g),
-                go=torch.randn(1, QUERIES, T_FRAMES, *MASK_PLANE, generator=g))
+        calls.append(dict(kind="dec_temporal_grouped", value=value_t, shapes=shapes.view(4, 1, 2).expand(4, T, 2).contiguous(),
+                          lsi=(lsi.view(4, 1) + frame_base.view(1, T)).contiguous(), loc=loc_t, aw=aw_t, go=go_t))
+    K, plane = shape["mask_k"], shape["mask_plane"]
+    mask = dict(coeff=torch.tanh(torch.randn(1, QUERIES, K, **kw)), proto=torch.randn(1, K, T, *plane, **kw),
+                go=torch.randn(1, QUERIES, T, *plane, **kw))
     return calls, mask
 
 
@@ -139,15 +154,22 @@ def algorithmic_bytes(c, esize, lsize):
 
 # -------------------------------------------------------------------------------------------- our arm
 class DeviceStep:
-    """All buffers of one clip resident on the GPU + pre-bound C-ABI argument lists."""
+    """All buffers of one clip resident on the GPU + pre-bound C-ABI argument lists.
 
-    def __init__(self, torch, lib, libmod, calls, mask, device, dtype):
-        self.torch, self.lib, self.device = torch, lib, device
+    prezero=True (default): the backward's grad_value accumulators are zero-filled (msda_zero_fill) on a side stream that is
+    forked at the start of the step and joined before the first backward call, so the 18 fills of 20.9 MB overlap the forward
+    pass instead of sitting in front of every backward kernel; the backward calls then carry MSDA_BWD_ACC_ZEROED.  This is what
+    MSDeformAttnFunction does under autograd (functions.py).  All of it is inside the timed region / the captured graph."""
+
+    def __init__(self, torch, lib, libmod, calls, mask, device, dtype, prezero=True):
+        self.torch, self.lib, self.libmod, self.device = torch, lib, libmod, device
         vt = torch.bfloat16 if dtype == "bf16" else torch.float32
         self.code = libmod.MSDA_BF16 if dtype == "bf16" else libmod.MSDA_F32
         self.mcode = self.code
+        self.prezero = prezero
+        self.side = torch.cuda.Stream(device) if prezero else None
         self.keep = []
-        self.fwd, self.bwd, self.kinds = [], [], []
+        self.fwd, self.bwd, self.kinds, self.fills = [], [], [], []
         cache = {}
 
         def dev(t, cast=True):
@@ -156,6 +178,7 @@ class DeviceStep:
                 cache[key] = (t.to(vt) if (cast and t.is_floating_point()) else t).to(device).contiguous()
             return cache[key]
 
+        flags = libmod.BWD_ACC_ZEROED if prezero else 0
         for c in calls:
             if c["kind"] == "dec_temporal":
                 continue                                      # the device step runs the grouped form instead
@@ -169,54 +192,61 @@ class DeviceStep:
             self.keep += [v, loc, aw, go, sh, ls, out, gv, gl, ga, ws]
             grouped = c["kind"] == "dec_temporal_grouped"
             self.kinds.append(c["kind"])
-            dims = (N, S, M, D, 4, L, Lq, P, 0.25) if grouped else (N, S, M, D, L, Lq, P)
-            self.fwd.append((grouped, (self.code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr()) + dims
-                             + (out.data_ptr(),)))
-            self.bwd.append((grouped, (self.code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr(), go.data_ptr())
-                             + dims + (gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), ws.data_ptr() if ws_bytes else None, ws_bytes)))
+            self.fwd.append((grouped, (self.code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr())
+                             + ((N, S, M, D, 4, L, Lq, P, 0.25) if grouped else (N, S, M, D, L, Lq, P)) + (out.data_ptr(),)))
+            G, Lb, scale = (4, L, 0.25) if grouped else (1, L, 1.0)
+            self.bwd.append((self.code, v.data_ptr(), sh.data_ptr(), ls.data_ptr(), loc.data_ptr(), aw.data_ptr(), go.data_ptr(),
+                             N, S, M, D, G, Lb, Lq, P, scale, gv.data_ptr(), gl.data_ptr(), ga.data_ptr(),
+                             ws.data_ptr() if ws_bytes else None, ws_bytes, flags))
+            self.fills.append((ws.data_ptr(), ws_bytes) if ws_bytes else (gv.data_ptr(), gv.numel() * gv.element_size()))
         # mask contraction: forward in the I/O dtype, backward is fp32-only (training precision of the reference)
         mc, mp = dev(mask["coeff"]), dev(mask["proto"])
         B, Q, K = mc.shape
         ncols = mp.numel() // (B * K)
         mo = torch.empty(B, Q, ncols, dtype=vt, device=device)
         self.mask_fwd = (self.mcode, self.mcode, mc.data_ptr(), mp.data_ptr(), B, Q, K, ncols, mo.data_ptr())
-        c32, p32, g32 = mask["coeff"].to(device), mask["proto"].to(device), mask["go"].to(device)
+        c32, p32, g32 = mask["coeff"].float().to(device), mask["proto"].float().to(device), mask["go"].float().to(device)
         gc, gp = torch.empty_like(c32), torch.empty_like(p32)
         self.mask_bwd = (libmod.MSDA_F32, c32.data_ptr(), p32.data_ptr(), g32.data_ptr(), B, Q, K, ncols, gc.data_ptr(), gp.data_ptr())
         self.keep += [mc, mp, mo, c32, p32, g32, gc, gp]
         self.outputs = dict(mask=mo)
+        self.n_enc = sum(1 for k in self.kinds if k == "enc")
+
+    def _check(self, rc):
+        if rc:
+            from mdqe_cvpr2023_b200 import _lib
+            raise RuntimeError("C-ABI call failed: " + _lib.last_error())
 
     def run(self, part="all"):
         """enqueue one step on the current stream (no host sync).  part "head" = forward + mask + decoder backward,
-        part "tail" = encoder backward (the split lets the multi-GPU run overlap the decoder-gradient all-reduce with
-        the encoder backward, as DDP's buckets do)."""
-        lib = self.lib
-        st = self.torch.cuda.current_stream(self.device).cuda_stream
+        part "tail<i>" = the i-th encoder backward (the split lets the multi-GPU run overlap the decoder-gradient all-reduce
+        with the encoder backward, as DDP's buckets do); "fwd" = the inference pass (forward calls + mask logits)."""
+        lib, torch = self.lib, self.torch
+        cur = torch.cuda.current_stream(self.device)
+        st = cur.cuda_stream
         rc = 0
-        n_enc = sum(1 for k in self.kinds if k == "enc")
         if part in ("all", "head", "fwd"):
+            if self.prezero and part != "fwd":                 # fork: zero-fill every accumulator of this step on the side stream
+                self.side.wait_stream(cur)
+                for ptr, nbytes in self.fills:
+                    rc |= lib.msda_zero_fill(self.side.cuda_stream, ptr, nbytes)
             for grouped, a in self.fwd:
                 rc |= (lib.msda_forward_grouped if grouped else lib.msda_forward)(st, *a)
             rc |= lib.mask_logits_forward(st, *self.mask_fwd)
             if part == "fwd":                                  # inference: forward calls + mask logits only
-                if rc:
-                    from mdqe_cvpr2023_b200 import _lib
-                    raise RuntimeError("C-ABI call failed: " + _lib.last_error())
-                return
+                return self._check(rc)
             rc |= lib.mask_logits_backward(st, *self.mask_bwd)
+            if self.prezero:
+                cur.wait_stream(self.side)                     # join before the first backward
         order = list(reversed(self.bwd))                       # decoder calls first, the n_enc encoder calls last
         if part == "head":
-            order = order[:len(order) - n_enc]
-        elif part == "tail":
-            order = order[len(order) - n_enc:]
+            order = order[:len(order) - self.n_enc]
         elif part.startswith("tail"):                          # "tail<i>": the i-th encoder backward of the step (last layer first)
-            i = len(order) - n_enc + int(part[4:])
+            i = len(order) - self.n_enc + int(part[4:])
             order = order[i:i + 1]
-        for grouped, a in order:
-            rc |= (lib.msda_backward_grouped if grouped else lib.msda_backward)(st, *a)
-        if rc:
-            from mdqe_cvpr2023_b200 import _lib
-            raise RuntimeError("C-ABI call failed: " + _lib.last_error())
+        for a in order:
+            rc |= lib.msda_backward_grouped_flags(st, *a)
+        self._check(rc)
 
 
 class HostStep:
@@ -227,7 +257,6 @@ class HostStep:
     (every call re-uploads its inputs, temporal calls per level, no mask backward) kept for A/B timing."""
 
     def __init__(self, torch, lib, libmod, calls, mask, device_index, dtype, legacy=False):
-        import ctypes
         self.lib, self.dev, self.legacy, self.ctypes = lib, device_index, legacy, ctypes
         vt = torch.bfloat16 if dtype == "bf16" else torch.float32
         code = libmod.MSDA_BF16 if dtype == "bf16" else libmod.MSDA_F32
@@ -387,26 +416,37 @@ def cpu_sample(torch, calls, mask, reps, warm):
     return sum(t_layer) / len(t_layer), sum(t_mask) / len(t_mask)
 
 
-def config_dict(args, extra=None):
-    cfg = {"workload": "R50_ovis_360 clip hot path: 36 MSDeformAttn fwd+bwd (6 enc N=4 S=Lq=5100, 6 dec-spatial Lq=196, "
-                       "24 dec-temporal L=T=4 run as 6 grouped launches) + mask contraction Q=196 K=32 N=61440 fwd+bwd",
-           "clips_per_gpu_per_step": 1, "frames": T_FRAMES, "pyramid": PYRAMID, "heads": HEADS, "head_dim": HEAD_DIM,
-           "points": POINTS, "queries": QUERIES, "layers": args.layers, "loc_dist": args.dist,
-           "l2_policy": "inputs larger than L2 (every call has its own buffers, ~1.5 GB touched per step)",
-           "parallelism": f"clip-sharded x{args.gpus}"}
-    cfg.update(extra or {})
-    return cfg
+def workload_text(shape):
+    T, pyr, D, K = shape["frames"], shape["pyramid"], shape["head_dim"], shape["mask_k"]
+    S = sum(h * w for h, w in pyr)
+    ncols = T * shape["mask_plane"][0] * shape["mask_plane"][1]
+    return (f"{shape['name']} clip hot path: 36 MSDeformAttn fwd+bwd (6 enc N={T} S=Lq={S}, 6 dec-spatial Lq={QUERIES}, "
+            f"24 dec-temporal L=T={T} run as 6 grouped launches) + mask contraction Q={QUERIES} K={K} N={ncols} fwd+bwd")
+
+
+def config_dict(args, shape):
+    """identical for both arms (the driver compares the two `config` objects)"""
+    return {"workload": workload_text(shape), "clips_per_gpu_per_step": 1, "frames": shape["frames"], "pyramid": shape["pyramid"],
+            "heads": HEADS, "head_dim": shape["head_dim"], "points": POINTS, "queries": QUERIES, "layers": args.layers,
+            "loc_dist": args.dist,
+            "l2_policy": "inputs larger than L2 (every call has its own buffers, ~1.5 GB touched per step)",
+            "parallelism": f"clip-sharded x{args.gpus}"}
 
 
 # --------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
+    """The reference's CPU implementation of the path (oracle/torch_port.py: F.grid_sample + autograd, the restatement of
+    ms_deform_attn_core_pytorch, ms_deform_attn_func.py:45-65) on all host cores.  One timed step = a bounded sample of the
+    clip: ONE of the six identical layers (1 encoder + 1 decoder-spatial + 4 decoder-temporal MSDA fwd+bwd) + the mask
+    contraction fwd+bwd; `ms_per_step` is that measured sample, `value` the clips/s it implies (clip = 6 layers + mask)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
+    shape = SHAPES[args.shape]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    calls, mask = build_calls(torch, args.dist, 0, 1)
+    calls, mask = build_calls(torch, shape, args.dist, 0, 1)
     t_layer, t_mask = [], []
     for it in range(args.warmup + args.steps):
         a, b = cpu_sample(torch, calls, mask, 1, 0)
@@ -414,17 +454,149 @@ def run_reference(args):
             t_layer.append(a)
             t_mask.append(b)
     tl, tm = sum(t_layer) / len(t_layer), sum(t_mask) / len(t_mask)
-    clip_s = N_LAYERS * tl + tm
+    clip_s = args.layers * tl + tm
     value = 1.0 / clip_s
-    sample = "each step = 1 of the 6 layers (1 enc + 1 dec-spatial + 4 dec-temporal MSDA fwd+bwd) + mask fwd+bwd; clip time = 6*layer + mask"
+    sample = (f"each timed step = 1 of the {args.layers} identical layers (1 enc + 1 dec-spatial + 4 dec-temporal MSDA fwd+bwd) + mask fwd+bwd "
+              f"= ms_per_step; clip time = {args.layers} * layer + mask (clip_ms), value = 1 / clip time")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": clip_s * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args, {"device": "cpu", "threads": torch.get_num_threads()}),
+            "warmup": args.warmup, "ms_per_step": (tl + tm) * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, shape),
+            "step_is": "bounded sample: 1 layer + mask (see cpu_baseline.sample)", "clip_ms": clip_s * 1e3,
+            "layer_ms": tl * 1e3, "mask_ms": tm * 1e3, "device": "cpu", "threads": torch.get_num_threads(),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- helpers
+def capture(torch, fn):
+    """warm `fn` on a side stream, then capture it into a CUDA graph"""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return g
+
+
+def time_replays(torch, graph, steps, warm=3):
+    for _ in range(warm):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def enc_kernel_times(torch, libmod, step, enc_pairs, reps=5):
+    """per-launch CUDA-event times of the encoder-shape sampling kernels (eager pass, events right around the kernels)"""
+    libmod.set_option("profile", 1)
+    for _ in range(reps):
+        step.run()
+    torch.cuda.synchronize()
+    bwd_ms, bwd_n = libmod.profile_read(libmod.PROF_MSDA_BWD, enc_pairs)
+    fwd_ms, fwd_n = libmod.profile_read(libmod.PROF_MSDA_FWD, enc_pairs)
+    libmod.set_option("profile", 0)
+    return (fwd_ms / fwd_n * 1e3 if fwd_n else None), (bwd_ms / bwd_n * 1e3 if bwd_n else None)
+
+
+def measure_other_config(torch, lib, libmod, key, dtype, dist, device, steps, hbm_peak):
+    """One of the other BASELINE.json configurations, measured like the headline: CUDA-graph replay of the clip's training step
+    and of its inference pass, inputs resident (generated on the device), plus the encoder-shape kernels per launch."""
+    shape = SHAPES[key]
+    calls, mask = build_calls(torch, shape, dist, 1, N_LAYERS, device=device)
+    step = DeviceStep(torch, lib, libmod, calls, mask, device, dtype)
+    for _ in range(2):
+        step.run()
+    torch.cuda.synchronize()
+    train_ms = time_replays(torch, capture(torch, step.run), steps)
+    fwd_ms = time_replays(torch, capture(torch, lambda: step.run("fwd")), steps)
+    enc = next(c for c in calls if c["kind"] == "enc")
+    esize = 2 if dtype == "bf16" else 4
+    fwd_b, bwd_b = algorithmic_bytes(enc, esize, esize)
+    enc_pairs = shape["frames"] * sum(h * w for h, w in shape["pyramid"]) * HEADS
+    f_us, b_us = enc_kernel_times(torch, libmod, step, enc_pairs)
+    res = {"workload": workload_text(shape), "dtype": "bf16" if dtype == "bf16" else "f32", "loc_dist": dist,
+           "train_step_ms": train_ms, "train_clips_per_s": 1e3 / train_ms,
+           "inference_ms": fwd_ms, "inference_clips_per_s": 1e3 / fwd_ms,
+           "enc_fwd_us": f_us, "enc_bwd_us": b_us, "enc_fwd_bytes": fwd_b, "enc_bwd_bytes": bwd_b,
+           "enc_fwd_bwd_frac_of_hbm_peak": ((fwd_b + bwd_b) / ((f_us + b_us) * 1e-6) / 1e9 / hbm_peak) if (f_us and b_us) else None,
+           "timing": f"CUDA-graph replay x{steps}, CUDA events; enc_* = per-launch CUDA events around the encoder-shape kernels"}
+    del step, calls, mask
+    torch.cuda.empty_cache()
+    return res
+
+
+def module_arm(torch, shape, device, steps, dist="local"):
+    """The same clip through `mdqe_cvpr2023_b200.MSDeformAttn` (what train_net.py would run): 6 encoder self-attention modules on
+    the [T, S, 256] pyramid, then 6 x (frame-level + clip-level) decoder cross-attention modules, residual connections between
+    them, forward + backward with every parameter gradient; Linear layers as 3xTF32 tensor-core GEMMs, softmax / location
+    arithmetic inside the sampler, grad_value accumulators zero-filled on a side stream.  Timed as one replayed CUDA graph."""
+    from mdqe_cvpr2023_b200 import MSDeformAttn
+    T, pyr, D = shape["frames"], shape["pyramid"], shape["head_dim"]
+    C = HEADS * D
+    S = sum(h * w for h, w in pyr)
+    torch.manual_seed(0)
+    enc = [MSDeformAttn(C, 4, HEADS, POINTS, pred_offsets=True, mode="spatial").to(device) for _ in range(N_LAYERS)]
+    dec_f = [MSDeformAttn(C, 4, HEADS, POINTS, pred_offsets=False, mode="spatial").to(device) for _ in range(N_LAYERS)]
+    dec_c = [MSDeformAttn(C, 4, HEADS, POINTS, n_frames=T, pred_offsets=False, mode="temporal").to(device) for _ in range(N_LAYERS)]
+    params = [p for m in enc + dec_f + dec_c for p in m.parameters()]
+    g = torch.Generator(device=device).manual_seed(0)
+    for m in enc:                                              # trained-like offsets: ~0.05 of the image around the reference point
+        m.sampling_offsets.weight.data.normal_(0, 0.4 / C ** 0.5, generator=g)
+    shapes = torch.tensor(pyr, device=device)
+    src = torch.randn(T, S, C, device=device, generator=g).requires_grad_(True)
+    pix = ref_points(torch, pyr, device)
+    enc_ref = torch.cat([pix, torch.full_like(pix, 0.1)], -1).unsqueeze(0).expand(T, S, 4).contiguous()
+    q_f = torch.randn(T, QUERIES, C, device=device, generator=g).requires_grad_(True)
+    q_c = torch.randn(1, QUERIES, C, device=device, generator=g).requires_grad_(True)
+    box = torch.cat([torch.rand(QUERIES, 2, device=device, generator=g), torch.full((QUERIES, 2), 0.1, device=device)], -1)
+    ref_f, ref_c = box.unsqueeze(0).expand(T, QUERIES, 4).contiguous(), box.unsqueeze(0).contiguous()
+
+    def forward():
+        x = src
+        for m in enc:
+            x = x + m(x, enc_ref, x, shapes, None)
+        qf, qc = q_f, q_c
+        mem_c = x.view(1, T, S, C)
+        for mf, mc in zip(dec_f, dec_c):
+            qf = qf + mf(qf, ref_f, x, shapes, None)
+            qc = qc + mc(qc, ref_c, mem_c, shapes, None)
+        return x, qf, qc
+
+    def train_step():
+        x, qf, qc = forward()
+        return torch.autograd.grad(x.sum() + qf.sum() + qc.sum(), [src, q_f, q_c] + params)
+
+    def infer_step():
+        with torch.no_grad():
+            return forward()
+
+    train_ms = time_replays(torch, capture(torch, train_step), steps)
+    infer_ms = time_replays(torch, capture(torch, infer_step), steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        train_step()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        train_step()
+    e1.record()
+    torch.cuda.synchronize()
+    return {"what": "18 MSDeformAttn modules of one clip (6 encoder, 6 frame-level + 6 clip-level decoder) forward+backward incl. all "
+                    "parameter gradients, through mdqe_cvpr2023_b200.MSDeformAttn (tc_linear + fused prologue + grouped temporal launch)",
+            "shape": shape["name"], "train_step_ms": train_ms, "train_clips_per_s": 1e3 / train_ms, "inference_ms": infer_ms,
+            "inference_clips_per_s": 1e3 / infer_ms, "eager_train_step_ms": e0.elapsed_time(e1) / 5,
+            "parameters": sum(p.numel() for p in params), "timing": f"CUDA-graph replay x{steps}, CUDA events"}
 
 
 # ----------------------------------------------------------------------------------------------- main
@@ -441,6 +613,8 @@ def main():
     import torch.distributed as dist
     from mdqe_cvpr2023_b200 import _lib as libmod
     lib = libmod.load()
+    shape = SHAPES[args.shape]
+    T, PYRAMID, HEAD_DIM, MASK_K, MASK_PLANE = shape["frames"], shape["pyramid"], shape["head_dim"], shape["mask_k"], shape["mask_plane"]
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -466,13 +640,30 @@ def main():
             os.close(saved_fd)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    calls, mask = build_calls(torch, args.dist, rank, args.layers)
-    step = DeviceStep(torch, lib, libmod, calls, mask, device, args.dtype)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    else:
+        hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    if args.arm == "module":                                   # only the module-level step
+        res = module_arm(torch, shape, device, args.steps, args.dist)
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": world * res["train_clips_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "warmup": 3, "ms_per_step": res["train_step_ms"], "higher_is_better": True, "scaling": "weak",
+                              "vs_baseline": None, "dtype": "f32", "data": "synthetic", "arm": "module", "config": config_dict(args, shape),
+                              "module_arm": res}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    calls, mask = build_calls(torch, shape, args.dist, rank, args.layers)
+    step = DeviceStep(torch, lib, libmod, calls, mask, device, args.dtype, prezero=not args.no_prezero)
     # gradient all-reduce of the enc+dec parameters (decoder 14.94 M, encoder 4.54 M fp32) -- the only
     # cross-GPU step of clip-sharded DDP training.  Buckets like DDP's, in the order the gradients become ready: the decoder
     # bucket is reduced on NCCL's stream while the encoder backward runs, then one bucket per encoder layer as soon as that
     # layer's backward has been enqueued; only the last layer's 3 MB are reduced after the backward has ended.
-    n_enc_layers = sum(1 for c in calls if c["kind"] == "enc")
+    n_enc_layers = step.n_enc
     dec_buf = torch.zeros(14_940_000, device=device) if world > 1 else None
     enc_bufs = [torch.zeros(4_540_000 // max(n_enc_layers, 1), device=device) for _ in range(n_enc_layers)] if world > 1 else None
 
@@ -492,22 +683,12 @@ def main():
     torch.cuda.synchronize()
     graphs = None
     if not args.no_graph:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            step.run()
-        torch.cuda.current_stream().wait_stream(side)
-        graphs = []
-        for part in (("all",) if world == 1 else ("head",) + tuple(f"tail{i}" for i in range(n_enc_layers))):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                step.run(part)
-            graphs.append(g)
+        graphs = [capture(torch, (lambda p=part: step.run(p)))
+                  for part in (("all",) if world == 1 else ("head",) + tuple(f"tail{i}" for i in range(n_enc_layers)))]
         for _ in range(2):
             for g in graphs:
                 g.replay()
         torch.cuda.synchronize()
-    graph = graphs
 
     def one_step():
         if world == 1:
@@ -549,14 +730,13 @@ def main():
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     launches_per_step = len(step.fwd) + len(step.bwd) + 2 + (len(step.bwd) if args.dtype == "bf16" else 0)
-    n_msda_calls = sum(4 if g else 1 for g, _ in step.fwd)     # reference-equivalent Function applications (36 per direction)
     gpu_launches = launches_per_step * args.steps      # graph replays re-launch the captured kernels
     value = world * 1.0 / (ms_step / 1e3)
 
     # ---- per-launch kernel timing (eager pass over the same buffers, events right around the kernels)
     esize = 2 if args.dtype == "bf16" else 4
     enc = next(c for c in calls if c["kind"] == "enc")
-    enc_pairs = T_FRAMES * sum(h * w for h, w in PYRAMID) * HEADS
+    enc_pairs = T * sum(h * w for h, w in PYRAMID) * HEADS
     libmod.set_option("profile", 1)
     for _ in range(min(args.steps, 10)):
         step.run()
@@ -568,15 +748,9 @@ def main():
     libmod.set_option("profile", 0)
     fwd_bytes, bwd_bytes = algorithmic_bytes(enc, esize, esize)
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peaks = json.load(open(peaks_path))
-        hbm_peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json"
-    else:
-        hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-
     traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     traffic_db = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+    main_shape = args.shape == "r50_360"                       # the committed ncu captures are of this shape
 
     def roof(nbytes, ms, n, name):
         if not n:
@@ -584,18 +758,20 @@ def main():
         us = ms / n * 1e3
         ach = nbytes / (us * 1e-6) / 1e9
         # DRAM bytes of one launch from the committed `ncu --set full` capture of the same kernel and shape (fp32)
-        traffic = traffic_db.get(name.split("<")[0].split(":")[0]) if args.dtype == "fp32" else None
+        traffic = traffic_db.get(name.split("<")[0].split(":")[0]) if (args.dtype == "fp32" and main_shape) else None
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                 "traffic": traffic, "traffic_source": traffic_db.get("source") if traffic else None, "avg_launch_us": us, "launches_timed": n, "algorithmic_bytes": nbytes, "peak_source": peak_src}
 
-    roofline = roof(bwd_bytes, bwd_ms, bwd_n, "msda_bwd_fast2_kernel<%s,32,16> (encoder shape N=4,S=Lq=5100)" % ("bf16" if args.dtype == "bf16" else "float"))
-    # What actually binds the two sampling kernels: the SM's L1 data pipe, which retires one 128-byte wavefront
-    # per clock -- every gathered corner row, every vector reduction, every shared-memory access and every shuffle is one.
+    vt_name = "bf16" if args.dtype == "bf16" else "float"
+    enc_desc = f"(encoder shape N={T},S=Lq={sum(h * w for h, w in PYRAMID)})"
+    roofline = roof(bwd_bytes, bwd_ms, bwd_n, f"msda_bwd_fast2_kernel<{vt_name},{HEAD_DIM},16> {enc_desc}")
+    # What actually binds the two sampling kernels: the SM's memory pipeline -- every gathered corner row, every
+    # vector reduction, every shared-memory access and every shuffle is a wavefront on the L1 data pipe (one per clock).
     # Wavefronts per launch come from the committed ncu capture of the same kernel and shape (profiles/ncu_traffic.json); the
     # time is the live per-launch figure above and the clock the one sampled during the timed region.  The backward's second
     # ceiling, L2's fp32 reduction rate (tools/red_microbench.cu), is reported beside it.
     def l1_pipe(roof_entry, key):
-        if not (roof_entry and args.dtype == "fp32" and args.dist == "local" and traffic_db.get(key)):
+        if not (roof_entry and args.dtype == "fp32" and args.dist == "local" and main_shape and traffic_db.get(key)):
             return None
         mhz = (clocks or {}).get("sm_mhz") or 1965.0
         peak = 148 * mhz * 1e6 / 1e9                                  # G wavefronts / s
@@ -605,37 +781,26 @@ def main():
 
     binding = l1_pipe(roofline, "msda_bwd_fast2_kernel_l1_wavefronts")
     l2_reduction = None
-    if roofline and args.dtype == "fp32" and args.dist == "local" and traffic_db.get("msda_bwd_fast2_kernel_l2_red_sectors"):
+    if roofline and args.dtype == "fp32" and args.dist == "local" and main_shape and traffic_db.get("msda_bwd_fast2_kernel_l2_red_sectors"):
         red_bytes = 32.0 * traffic_db["msda_bwd_fast2_kernel_l2_red_sectors"]
         ach = red_bytes / (roofline["avg_launch_us"] * 1e-6) / 1e9
         l2_reduction = {"kernel": roofline["kernel"], "bound": "l2_fp32_reductions", "achieved": ach, "peak": traffic_db["l2_red_peak_gbs"],
                         "unit": "GB/s", "frac": ach / traffic_db["l2_red_peak_gbs"], "reduction_bytes_per_launch": red_bytes,
                         "peak_source": traffic_db["l2_red_peak_source"]}
-    roofline_fwd = roof(fwd_bytes, fwd_ms, fwd_n, "msda_fwd_fast2_kernel<%s,32,16> (encoder shape N=4,S=Lq=5100)" % ("bf16" if args.dtype == "bf16" else "float"))
-    mB = QUERIES * MASK_K + MASK_K * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
-    mO = QUERIES * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
+    roofline_fwd = roof(fwd_bytes, fwd_ms, fwd_n, f"msda_fwd_fast2_kernel<{vt_name},{HEAD_DIM},16> {enc_desc}")
+    mB = QUERIES * MASK_K + MASK_K * T * MASK_PLANE[0] * MASK_PLANE[1]
+    mO = QUERIES * T * MASK_PLANE[0] * MASK_PLANE[1]
     binding_fwd = l1_pipe(roofline_fwd, "msda_fwd_fast2_kernel_l1_wavefronts")
     roofline_mask = roof(mB * esize + mO * esize, mfw_ms, mfw_n, "mask_fwd_tc2_kernel<bf16> (tcgen05)" if args.dtype == "bf16" else "mask_fwd_tc4_kernel<float,false> (tcgen05, 3xTF32)")
     if roofline_mask:
-        flops = 2.0 * QUERIES * MASK_K * T_FRAMES * MASK_PLANE[0] * MASK_PLANE[1]
+        flops = 2.0 * QUERIES * MASK_K * T * MASK_PLANE[0] * MASK_PLANE[1]
         roofline_mask["tflops"] = flops / (roofline_mask["avg_launch_us"] * 1e-6) / 1e12
     roofline_mask_bwd = roof((mB + mO + mB) * 4, mbw_ms, mbw_n, "mask_backward_tc: mask_grad_coeff_tc_kernel + mask_fwd_tc4_kernel<float,true> (tcgen05, 3xTF32)")
 
     # ---- forward only (BASELINE configs[1]: the inference pass of the same clip -- 36 MSDeformAttn forward calls + mask logits)
     fwd_only = None
     if world == 1 and not args.no_graph:
-        gf = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gf):
-            step.run("fwd")
-        for _ in range(3):
-            gf.replay()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(args.steps):
-            gf.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        f_ms = e0.elapsed_time(e1) / args.steps
+        f_ms = time_replays(torch, capture(torch, lambda: step.run("fwd")), args.steps)
         fwd_only = {"ms_per_step": f_ms, "clips_per_s": 1e3 / f_ms, "launches_per_step": len(step.fwd) + 1,
                     "what": "forward calls of the same clip + mask logits (inference pass), CUDA-graph replay, inputs resident"}
 
@@ -650,12 +815,21 @@ def main():
     eager_ms = e0.elapsed_time(e1) / min(args.steps, 10)
     counted_per_step = libmod.launch_count() / min(args.steps, 10)
 
+    # ---- the step with the zero-fills on the critical path (what round 1 measured), for comparison
+    inline_fill = None
+    if world == 1 and not args.no_graph and not args.no_prezero and not args.no_other_configs:
+        step.prezero = False
+        saved_bwd = step.bwd
+        step.bwd = [a[:-1] + (0,) for a in saved_bwd]
+        inline_fill = {"ms_per_step": time_replays(torch, capture(torch, step.run), args.steps),
+                       "what": "same step with grad_value zero-filled inside every backward call (cudaMemsetAsync in front of the kernel)"}
+        step.bwd, step.prezero = saved_bwd, True
+
     # ---- end to end through the host-buffer C ABI (H2D + kernels + D2H every call), wall clock
     e2e = None
     if not args.no_e2e:
         host = HostStep(torch, lib, libmod, calls, mask, local_rank, args.dtype, legacy=args.e2e_legacy)
         libmod.set_option("host_async", 1)           # calls enqueue on the library's H2D / compute / D2H streams ...
-        import ctypes
 
         def fence():
             t = ctypes.c_int64(0)
@@ -690,13 +864,37 @@ def main():
             t = torch.tensor([dt], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        gbs = world * (host.h2d + host.d2h) * n_e2e / dt / 1e9
         e2e = {"value": world * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": host.h2d, "d2h_bytes_per_step": host.d2h,
-               "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3, "timing": ("wall clock; *_host C-ABI calls in host_async mode (3-stream pipeline), msda_host_sync() at the end of every step" if args.e2e_sync_every_step else
+               "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3, "host_link_gbs_all_ranks": gbs,
+               "limit": "host<->device link: the step moves h2d+d2h bytes per rank through PCIe; see profiles/ for the per-rank copy bandwidth at this rank count",
+               "timing": ("wall clock; *_host C-ABI calls in host_async mode (3-stream pipeline), msda_host_sync() at the end of every step" if args.e2e_sync_every_step else
                           "wall clock over all steps; *_host C-ABI calls in host_async mode (3-stream pipeline); every step ends with msda_host_fence() and is "
                           "waited for (msda_host_wait: all its results in host memory) while the next step is enqueued -- at most two steps in flight"),
                "note": ("first-generation host path: every call re-uploads its inputs, per-level temporal calls, no mask backward" if args.e2e_legacy else
                         "same launches as the device step; forward inputs stay on the device for the backward (*_host_saved entries)")}
         lib.msda_host_arena_release()
+        del host
+
+    # ---- the other BASELINE.json configurations and the module-level arm (single-GPU runs; rank 0 of a multi-GPU run skips them)
+    other, modarm = None, None
+    if world == 1 and not args.no_other_configs and not args.no_graph:
+        del step
+        torch.cuda.empty_cache()
+        n_other = max(3, min(args.steps, 10))
+        other = {}
+        for name, key, dt_ in (("R50_ovis_720_train_fp32", "r50_720", "fp32"), ("swinl_ytvis21_fp32", "swinl_360", "fp32"),
+                               ("R50_ovis_360_bf16", "r50_360", "bf16"), ("R50_ovis_720_bf16", "r50_720", "bf16")):
+            if key == args.shape and dt_ == args.dtype:
+                continue
+            try:
+                other[name] = measure_other_config(torch, lib, libmod, key, dt_, args.dist, device, n_other, hbm_peak)
+            except Exception as e:  # noqa: BLE001 -- a failing side measurement must not lose the headline line
+                other[name] = {"error": repr(e)[:300]}
+        try:
+            modarm = module_arm(torch, shape, device, n_other, args.dist)
+        except Exception as e:  # noqa: BLE001
+            modarm = {"error": repr(e)[:300]}
 
     # ---- CPU baseline (rank 0, single-GPU runs only): the reference's CPU path restated in torch
     cpu = None
@@ -712,9 +910,11 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
-                "config": config_dict(args, {"launch": "cuda_graph" if graph is not None else "eager",
-                                             "allreduce": "NCCL, %d buckets per step in gradient-ready order: decoder 14.94M fp32 and one 0.76M bucket per encoder layer, each overlapped with the encoder backward still to run" % (1 + n_enc_layers) if world > 1 else None}),
+                "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic", "config": config_dict(args, shape),
+                "launch": "cuda_graph" if graphs is not None else "eager",
+                "zero_fill": ("grad_value accumulators zero-filled on a side branch of the step (msda_zero_fill, MSDA_BWD_ACC_ZEROED)" if not args.no_prezero
+                              else "inside every backward call"),
+                "allreduce": ("NCCL, %d buckets per step in gradient-ready order: decoder 14.94M fp32 and one 0.76M bucket per encoder layer, each overlapped with the encoder backward still to run" % (1 + n_enc_layers)) if world > 1 else None,
                 # kernels of this library launched inside the timed region: the library's own launch counter over an eager pass of
                 # the same step (the graph replays re-launch exactly those kernels) x steps; `launches_per_step` is the C-ABI call count
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(round(counted_per_step * args.steps)) if counted_per_step else gpu_launches,
@@ -722,7 +922,8 @@ def main():
                 "lib_launch_count_per_eager_step": counted_per_step,
                 "roofline": roofline, "roofline_binding_resource": binding, "roofline_l2_reductions": l2_reduction,
                 "roofline_fwd": roofline_fwd, "roofline_fwd_binding_resource": binding_fwd, "roofline_mask": roofline_mask,
-                "roofline_mask_bwd": roofline_mask_bwd, "eager_ms_per_step": eager_ms, "forward_only": fwd_only, "cpu_baseline": cpu}
+                "roofline_mask_bwd": roofline_mask_bwd, "eager_ms_per_step": eager_ms, "step_with_inline_zero_fill": inline_fill,
+                "forward_only": fwd_only, "other_configs": other, "module_arm": modarm, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

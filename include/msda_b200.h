@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 2
+#define MSDA_B200_ABI_VERSION 3
 
 typedef enum {
   MSDA_OK = 0,
@@ -63,9 +63,9 @@ const char* msda_last_error(void);
 
 /* Tuning knobs (kernel variant selection used by bench.py / tests); unknown keys fail.
  * Keys: "fwd_variant", "bwd_variant", "chunk_pairs", "mask_variant", "profile", "mask_debug", "host_async",
- * "tile_rows", "tile_q", "consumer_ctas", "bwd_merge" (1 = the backward merges the grad_value reductions of one query's
+ * "consumer_ctas", "bwd_merge" (1 = the backward merges the grad_value reductions of one query's
  * points that hit the same value row -- default; 0 = one reduction per corner, for A/B).  mask_variant: 0 auto (tensor cores when eligible), 1 SIMT, 2 require tensor cores,
- * 3 / 5 earlier tensor-core kernels and 4 the first SIMT backward (kept for A/B timing). */
+ * (earlier A/B kernels were removed in round 2). */
 int msda_set_option(const char* key, int value);
 int msda_get_option(const char* key, int* value);
 
@@ -109,6 +109,21 @@ int msda_backward_grouped(void* stream, int dtype,
                           void* grad_value, void* grad_loc, void* grad_aw,
                           void* workspace, size_t workspace_bytes);
 
+/* The backward accumulates grad_value with vector reductions, so its accumulator -- grad_value itself (fp32 / fp64) or the
+ * fp32 workspace (bf16 modes) -- must start at zero.  The reference zero-fills right before its kernel (`at::zeros_like`,
+ * ms_deform_attn_cuda.cu:121), which puts a 20.9 MB memset per call on the critical path (6.7 % of the R50_ovis_360 training
+ * step).  A caller that can fill the buffer earlier and elsewhere -- on a side stream while the forward pass runs, as
+ * MSDeformAttnFunction and bench.py do -- passes MSDA_BWD_ACC_ZEROED and the call launches the sampling kernel only.
+ * msda_zero_fill is that fill as a stream-ordered call (no allocation, graph-capturable).  G = 1, scale = 1: the plain operator. */
+#define MSDA_BWD_ACC_ZEROED 1
+int msda_zero_fill(void* stream, void* ptr, size_t bytes);
+int msda_backward_grouped_flags(void* stream, int dtype,
+                                const void* value, const int64_t* shapes, const int64_t* level_start,
+                                const void* loc, const void* aw, const void* grad_out,
+                                int N, int S, int M, int D, int G, int L, int Lq, int P, float scale,
+                                void* grad_value, void* grad_loc, void* grad_aw,
+                                void* workspace, size_t workspace_bytes, int flags);
+
 /* Fused sampler prologue (replaces the elementwise tail of MSDeformAttn.forward, ms_deform_attn.py:142-161):
  * the kernel takes what the module's Linear layers produce and computes softmax and sampling locations itself.
  *   offsets [N,Lq,M,L,P,2] raw output of sampling_offsets / sampling_grid_offsets,  logits [N,Lq,M,L*P] raw attention logits,
@@ -130,6 +145,12 @@ int msda_fused_backward(void* stream, int dtype,
                         int mode, float offset_scale, const void* grad_out,
                         int N, int S, int M, int D, int G, int L, int Lq, int P, float scale,
                         void* grad_value, void* grad_offsets, void* grad_logits);
+int msda_fused_backward_flags(void* stream, int dtype,
+                              const void* value, const int64_t* shapes, const int64_t* level_start,
+                              const void* ref_points, int R, const void* offsets, const void* logits, const void* grid,
+                              int mode, float offset_scale, const void* grad_out,
+                              int N, int S, int M, int D, int G, int L, int Lq, int P, float scale,
+                              void* grad_value, void* grad_offsets, void* grad_logits, int flags);
 
 /* Mask contraction: out[b,q,n] = sum_k coeff[b,q,k] * proto[b,k,n], n over the flattened (t,h,w)
  * plane (Ncols = T*H*W).  coeff [B,Q,K], proto [B,K,Ncols], out [B,Q,Ncols].

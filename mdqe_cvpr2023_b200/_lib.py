@@ -12,7 +12,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(PKG_DIR, "libmsda_b200.so")
 
 MSDA_F32, MSDA_BF16, MSDA_F64, MSDA_BF16_LOC32 = 0, 1, 2, 3
-ABI_VERSION = 2
+ABI_VERSION = 3
+BWD_ACC_ZEROED = 1
 
 _c_int, _c_vp, _c_i64, _c_sz = ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t
 _SEVEN = [_c_int] * 7
@@ -30,6 +31,11 @@ PROTOTYPES = {
     "msda_forward_grouped": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + [_c_int] * 8 + [ctypes.c_float, _c_vp]),
     "msda_backward_grouped": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + [_c_int] * 8
                               + [ctypes.c_float, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz]),
+    "msda_zero_fill": (_c_int, [_c_vp, _c_vp, _c_sz]),
+    "msda_backward_grouped_flags": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + [_c_int] * 8
+                                    + [ctypes.c_float, _c_vp, _c_vp, _c_vp, _c_vp, _c_sz, _c_int]),
+    "msda_fused_backward_flags": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, ctypes.c_float,
+                                           _c_vp] + [_c_int] * 8 + [ctypes.c_float, _c_vp, _c_vp, _c_vp, _c_int]),
     "msda_fused_forward": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, ctypes.c_float]
                            + [_c_int] * 8 + [ctypes.c_float, _c_vp]),
     "msda_fused_backward": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, ctypes.c_float,

@@ -605,16 +605,6 @@ query_init_kernel(const float* __restrict__ feat, const int64_t* __restrict__ sh
   }
 }
 
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
 
 }  // namespace
 }  // namespace msda
@@ -631,11 +621,7 @@ int mask_match_cost(void* stream, const void* coeff, const void* proto, const vo
   if (Q == 0 || G == 0) return 0;
   if (!coeff || !proto || !targets || !workspace || !cost_bce || !cost_dice) return fail(MSDA_ERR_INVALID_ARG, "mask_match_cost: NULL pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr = false;
-  if (!attr) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(match_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMcSmem)), "cudaFuncSetAttribute")) return rc;
-    attr = true;
-  }
+  if (int rc = ensure_func_attr(match_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMcSmem))) return rc;
   const int64_t chunks = (Ncols + kTC - 1) / kTC;
   const int slots = option("consumer_ctas") > 0 ? option("consumer_ctas") : 3 * sm_count();      // three resident CTAs per SM
   const int ctas = static_cast<int>(chunks < slots ? chunks : slots);
@@ -666,12 +652,8 @@ size_t mask_nms_siou_workspace_bytes(void) { return static_cast<size_t>(kSiMaxQ)
 
 static int siou_launch(const char* who, cudaStream_t st, bool track, const float* a, const float* b, int Qa, int Qb, int T, int H, int W,
                        void* workspace, float* siou) {
-  static bool attr = false;
-  if (!attr) {
-    if (int rc = check_cuda(cudaFuncSetAttribute(nms_siou_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSiSmem)), "cudaFuncSetAttribute")) return rc;
-    if (int rc = check_cuda(cudaFuncSetAttribute(nms_siou_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSiSmem)), "cudaFuncSetAttribute")) return rc;
-    attr = true;
-  }
+  if (int rc = ensure_func_attr(nms_siou_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSiSmem))) return rc;
+  if (int rc = ensure_func_attr(nms_siou_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSiSmem))) return rc;
   const int t_step = (!track && T >= 5) ? 2 : 1;                // mask_pred[:, ::2] if T >= 5 (mdqe.py:386)
   const int T2 = (T + t_step - 1) / t_step, H2 = track ? H : H / 2, W2 = track ? W : W / 2;
   const int64_t N2 = static_cast<int64_t>(T2) * H2 * W2;

@@ -107,11 +107,8 @@ static int launch_mask_tc2(cudaStream_t st, const void* coeff, const void* proto
   if (int rc = make_map_in(&map_coeff, coeff, false, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QN)) return rc;
   if (int rc = make_map_out(&map_out, out, sizeof(OT) == 2, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B)) return rc;
   const size_t smem = mask_tc2_smem_bytes(KP, QN, sizeof(OT));
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(mask_fwd_tc2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(mask_fwd_tc2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  });
+  if (int rc = ensure_func_attr(mask_fwd_tc2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) return rc;
+  if (int rc = ensure_func_attr(mask_fwd_tc2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) return rc;
   const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);
   long long* dbg = nullptr;
   if (option("mask_debug")) {
@@ -127,75 +124,13 @@ static int launch_mask_tc2(cudaStream_t st, const void* coeff, const void* proto
   return after_launch("mask_fwd_tc2_kernel");
 }
 
-// fp32 tensor [d2, d1, d0], no swizzle, box {128, box1, 1}: the proto tile of the 3xTF32 kernel (transposed on chip)
-static int make_map_plain_f32(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1,
-                              uint32_t box0 = kTcTileN) {
-  PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
-  if (!enc) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t dims[3] = {d0, d1, d2};
-  const cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
-  const cuuint32_t box[3] = {box0, box1, 1};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled(proto fp32) failed (CUresult %d)", static_cast<int>(r));
-  return 0;
-}
-
-// fp32 inputs: 3xTF32 on the tensor cores (mask_fwd_tc3_kernel)
+// fp32 inputs: 3xTF32 on the tensor cores (mask_fwd_tc4_kernel)
 static bool mask_tc3_eligible(int in_dtype, const void* coeff, const void* proto, int Q, int K, int64_t Ncols) {
   if (in_dtype != MSDA_F32) return false;
   if (K < 4 || K % 4 != 0) return false;                               // 16-byte global row strides (reduction walked 32 at a time)
   if (Q < 1) return false;
   if (Ncols % 4 != 0 || Ncols >= (int64_t(1) << 31)) return false;     // 16-byte global strides
   return ((reinterpret_cast<uintptr_t>(coeff) | reinterpret_cast<uintptr_t>(proto)) & 15u) == 0;
-}
-
-// out[b, r, n] = sum_k A[b, r, k] * P[b, k, n]  (kTransA: A is given as [b, k, r]).  Q = rows r, K = reduction length.
-template <typename OT, bool kTransA>
-static int launch_mask_tc3(cudaStream_t st, const void* coeff, const void* proto, void* out, int B, int Q, int K,
-                           int64_t Ncols, int prof_kind = MSDA_PROF_MASK_FWD) {
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int n_kchunks = (K + 31) / 32;
-  const int n_tiles_n = static_cast<int>((Ncols + kTcTileN - 1) / kTcTileN);
-  const int64_t tiles = (int64_t)B * n_tiles_n;
-  int n_qchunks = (Q + 127) / 128;                                      // at most 128 query rows per item (shared-memory budget)
-  while (n_qchunks < 4 && tiles * n_qchunks < 6LL * sms && (Q / (n_qchunks + 1)) / 32 * 32 >= 32) ++n_qchunks;
-  int QS = 0, QN = 0;
-  for (;; ++n_qchunks) {                                                 // chunk starts are multiples of 32, the last takes the rest
-    QS = (n_qchunks == 1) ? ((Q + 31) / 32 * 32) : (Q / n_qchunks) / 32 * 32;
-    if (QS < 32) break;
-    const int last_rows = Q - (n_qchunks - 1) * QS;
-    QN = ((QS > last_rows ? QS : last_rows) + 15) / 16 * 16;
-    if (QN <= 128) break;
-  }
-  if (QN > 128 || QS < 32) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: cannot chunk Q=%d for the tensor-core kernel", Q);
-  const int64_t n_items = tiles * n_qchunks;
-  if (n_items >= (int64_t(1) << 31)) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: too many tiles");
-  CUtensorMap map_proto, map_coeff, map_out;
-  if (int rc = make_map_plain_f32(&map_proto, proto, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, 32u)) return rc;
-  if (kTransA) {
-    if (int rc = make_map_plain_f32(&map_coeff, coeff, (uint64_t)Q, (uint64_t)K, (uint64_t)B, 32u, (uint32_t)QN)) return rc;
-  } else {
-    if (int rc = make_map_in(&map_coeff, coeff, true, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QN)) return rc;
-  }
-  if (int rc = make_map_out(&map_out, out, sizeof(OT) == 2, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B)) return rc;
-  const size_t smem = mask_tc3_smem_bytes(QN, sizeof(OT), kTransA);
-  if (smem > 225 * 1024) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: tile does not fit shared memory");
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(mask_fwd_tc3_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-    cudaFuncSetAttribute(mask_fwd_tc3_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-    cudaFuncSetAttribute(mask_fwd_tc3_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-    cudaFuncSetAttribute(mask_fwd_tc3_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-  });
-  const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);
-  ProfScope prof(st, prof_kind, (int64_t)B * Q * Ncols);
-  mask_fwd_tc3_kernel<OT, kTransA><<<grid, kTc3Threads, smem, st>>>(map_proto, map_coeff, map_out, Q, n_kchunks, QS, QN, n_qchunks, n_tiles_n,
-                                                          static_cast<int>(n_items));
-  return after_launch("mask_fwd_tc3_kernel");
 }
 
 // fp32 tensor [d2, d1, d0], box {32, 32, 1}, "128B swizzle with 32B atoms": the MN-major tf32 operand layout (UMMA layout type 1)
@@ -250,40 +185,16 @@ static int launch_mask_tc4(cudaStream_t st, const void* coeff, const void* proto
   if (n_stages > kTc4MaxStages) n_stages = kTc4MaxStages;
   if (n_stages > n_kchunks + 2) n_stages = n_kchunks + 2;
   if (n_stages < 2) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits: tile does not fit shared memory");
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(mask_fwd_tc4_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    cudaFuncSetAttribute(mask_fwd_tc4_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    cudaFuncSetAttribute(mask_fwd_tc4_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    cudaFuncSetAttribute(mask_fwd_tc4_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-  });
+  if (int rc = ensure_func_attr(mask_fwd_tc4_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) return rc;
+  if (int rc = ensure_func_attr(mask_fwd_tc4_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) return rc;
+  if (int rc = ensure_func_attr(mask_fwd_tc4_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) return rc;
+  if (int rc = ensure_func_attr(mask_fwd_tc4_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) return rc;
   const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);
   ProfScope prof(st, prof_kind, (int64_t)B * Q * Ncols);
   mask_fwd_tc4_kernel<OT, kTransB><<<grid, kTc4Threads, 1024 + n_stages * stage + out_bytes, st>>>(
       map_plane, map_rows, map_out, Q, n_kchunks, QS, QN, n_qchunks, n_tiles_n, static_cast<int>(n_items), n_stages,
       option("mask_debug") != 2);
   return after_launch("mask_fwd_tc4_kernel");
-}
-
-template <typename OT>
-static int launch_mask_tc(cudaStream_t st, const void* coeff, const void* proto, void* out, int B, int Q, int K,
-                          int64_t Ncols) {
-  const int KP = (K + 15) / 16 * 16, QP = (Q + 15) / 16 * 16;
-  int tmem_cols = 32;
-  while (tmem_cols < QP) tmem_cols *= 2;
-  CUtensorMap map_proto, map_coeff;
-  if (int rc = make_map_in(&map_proto, proto, false, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, (uint32_t)KP)) return rc;
-  if (int rc = make_map_in(&map_coeff, coeff, false, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QP)) return rc;
-  const size_t smem = mask_tc_smem_bytes(KP, QP);
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(mask_fwd_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(mask_fwd_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  });
-  const dim3 grid(static_cast<unsigned>((Ncols + kTcTileN - 1) / kTcTileN), B);
-  ProfScope prof(st, MSDA_PROF_MASK_FWD, (int64_t)B * Q * Ncols);
-  mask_fwd_tc_kernel<OT><<<grid, kTcThreads, smem, st>>>(map_proto, map_coeff, static_cast<OT*>(out), Q, Ncols, KP, QP, tmem_cols);
-  return after_launch("mask_fwd_tc_kernel");
 }
 
 template <typename IT, typename OT>
@@ -304,19 +215,11 @@ int mask_forward_dispatch(cudaStream_t st, int in_dtype, int out_dtype, const vo
   const bool tc_ok = mask_tc_eligible(in_dtype, coeff, proto, Q, K, Ncols);
   if (variant == 2 && !tc_ok && !mask_tc3_eligible(in_dtype, coeff, proto, Q, K, Ncols))
     return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: tcgen05 path needs K %% 8 == 0 with K <= 64 (bf16) / 32 (fp32) and 16-byte aligned rows");
-  if (variant == 3 && tc_ok && Q <= 256) {           // 3 = first (one tile per CTA) tensor-core kernel, kept for A/B timing
-    if (out_dtype == MSDA_F32) return launch_mask_tc<float>(st, coeff, proto, out, B, Q, K, Ncols);
-    return launch_mask_tc<__nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
-  }
   if (variant != 1 && tc_ok) {
     if (out_dtype == MSDA_F32) return launch_mask_tc2<float>(st, coeff, proto, out, B, Q, K, Ncols);
     return launch_mask_tc2<__nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
   }
   if (variant != 1 && mask_tc3_eligible(in_dtype, coeff, proto, Q, K, Ncols)) {
-    if (variant == 5) {                                // 5 = third-generation kernel (on-chip transposition), kept for A/B timing
-      if (out_dtype == MSDA_F32) return launch_mask_tc3<float, false>(st, coeff, proto, out, B, Q, K, Ncols);
-      return launch_mask_tc3<__nv_bfloat16, false>(st, coeff, proto, out, B, Q, K, Ncols);
-    }
     if (out_dtype == MSDA_F32) return launch_mask_tc4<float, false>(st, coeff, proto, out, B, Q, K, Ncols);
     return launch_mask_tc4<__nv_bfloat16, false>(st, coeff, proto, out, B, Q, K, Ncols);
   }
@@ -348,10 +251,7 @@ static int launch_mask_grad_coeff_tc(cudaStream_t st, const void* proto, const v
   CUtensorMap map_go, map_proto;
   if (int rc = make_map_in(&map_go, grad_out, true, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B, 128u)) return rc;
   if (int rc = make_map_in(&map_proto, proto, true, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, (uint32_t)KP)) return rc;
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(mask_grad_coeff_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-  });
+  if (int rc = ensure_func_attr(mask_grad_coeff_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) return rc;
   const dim3 grid(static_cast<unsigned>(slices), static_cast<unsigned>(n_qblocks), static_cast<unsigned>(B));
   long long* dbg = nullptr;
   if (option("mask_debug") == 1) {
@@ -378,13 +278,6 @@ int mask_backward_dispatch(cudaStream_t st, int dtype, const void* coeff, const 
   }
   if (!grad_coeff && !grad_proto) return 0;
   ProfScope prof(st, MSDA_PROF_MASK_BWD, (int64_t)B * Q * Ncols);
-  if (option("mask_variant") == 4) {                    // 4 = first-generation fused backward (A/B timing)
-    const dim3 grid(static_cast<unsigned>((Ncols + kMaskTN - 1) / kMaskTN), (K + kMaskKC - 1) / kMaskKC, B);
-    mask_bwd_simt_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(coeff), static_cast<const float*>(proto),
-                                               static_cast<const float*>(grad_out), static_cast<float*>(grad_coeff),
-                                               static_cast<float*>(grad_proto), Q, K, Ncols);
-    return after_launch("mask_bwd_simt_kernel");
-  }
   const unsigned kblocks = (K + 31) / 32;
   const bool tc_ok = option("mask_variant") != 1 && K % 4 == 0 && K <= 128 && Ncols % 4 == 0 && Ncols < (int64_t(1) << 31) && Q < 65536 * 128 &&
                      ((reinterpret_cast<uintptr_t>(coeff) | reinterpret_cast<uintptr_t>(proto) | reinterpret_cast<uintptr_t>(grad_out) |
@@ -406,11 +299,8 @@ int mask_backward_dispatch(cudaStream_t st, int dtype, const void* coeff, const 
   }
   // grad_proto[b, k, n] = sum_q coeff[b, q, k] * grad_out[b, q, n] on the tensor cores (3xTF32): the forward kernel with
   // rows = k, reduction = q (7 chunks of 32 for Q = 196) and the row operand transposed on chip
-  if (grad_proto && tc_ok && option("mask_variant") != 5) {
-    return launch_mask_tc4<float, true>(st, coeff, grad_out, grad_proto, B, K, Q, Ncols, -1);
-  }
   if (grad_proto && tc_ok) {
-    return launch_mask_tc3<float, true>(st, coeff, grad_out, grad_proto, B, K, Q, Ncols, -1);
+    return launch_mask_tc4<float, true>(st, coeff, grad_out, grad_proto, B, K, Q, Ncols, -1);
   }
   if (grad_proto) {
     const dim3 grid(static_cast<unsigned>((Ncols + kGpTN - 1) / kGpTN), kblocks, B);
@@ -457,12 +347,9 @@ static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const 
   if (kBMn) { if (int rc = make_map_mn_f32(&map_b, Bm, (uint64_t)N, (uint64_t)K, 1)) return rc; }
   else { if (int rc = make_map_in(&map_b, Bm, true, (uint64_t)K, (uint64_t)N, 1, kG3Tile)) return rc; }
   if (int rc = make_map_c(&map_c, C, (uint64_t)N, (uint64_t)M)) return rc;
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(gemm3x_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes);
-    cudaFuncSetAttribute(gemm3x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes);
-    cudaFuncSetAttribute(gemm3x_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes);
-  });
+  if (int rc = ensure_func_attr(gemm3x_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes)) return rc;
+  if (int rc = ensure_func_attr(gemm3x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes)) return rc;
+  if (int rc = ensure_func_attr(gemm3x_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes)) return rc;
   const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);
   gemm3x_kernel<kAMn, kBMn><<<grid, kG3Threads, kG3SmemBytes, st>>>(map_a, map_b, map_c, bias, row_mask, (int)M, (int)N, n_kchunks, cps,
                                                                    tiles_m, tiles_n, (int)n_items, splits > 1 ? 1 : 0);

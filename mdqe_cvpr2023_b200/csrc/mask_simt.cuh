@@ -97,100 +97,6 @@ mask_fwd_simt_kernel(const IT* __restrict__ coeff, const IT* __restrict__ proto,
   }
 }
 
-// Backward (fp32 only; the reference trains in fp32, configs/R50_coco.yaml:41-42 AMP disabled).
-// grid: (ceil(Ncols/TN), ceil(K/32), B).  One pass over grad_out produces both gradients:
-//   grad_proto[b,k,n] = sum_q coeff[b,q,k] go[b,q,n]      (complete per CTA)
-//   grad_coeff[b,q,k] = sum_n go[b,q,n] proto[b,k,n]      (per-CTA partial over its n tile -> atomicAdd;
-//                                                          the caller zero-fills grad_coeff)
-__global__ void __launch_bounds__(256)
-mask_bwd_simt_kernel(const float* __restrict__ coeff, const float* __restrict__ proto, const float* __restrict__ go,
-                     float* __restrict__ gcoeff, float* __restrict__ gproto, int Q, int K, int64_t Ncols) {
-  constexpr int QC = 32;
-  __shared__ __align__(16) float sP[kMaskKC][kMaskTN];     // proto tile
-  __shared__ __align__(16) float sG[QC][kMaskTN];          // grad_out chunk
-  __shared__ __align__(16) float sC[QC][kMaskKC];          // coeff chunk
-  const int b = blockIdx.z;
-  const int k0 = blockIdx.y * kMaskKC;
-  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * kMaskTN;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // grad_proto: 4 k x 4 n per thread
-  const int cq = threadIdx.x >> 3, ck = (threadIdx.x & 7) * 4;     // grad_coeff: 1 q x 4 k per thread
-  const float* A = coeff + static_cast<int64_t>(b) * Q * K;
-  const float* Pm = proto + static_cast<int64_t>(b) * K * Ncols;
-  const float* G = go + static_cast<int64_t>(b) * Q * Ncols;
-
-  for (int idx = threadIdx.x; idx < kMaskKC * kMaskTN; idx += 256) {
-    const int kk = idx / kMaskTN, nn = idx % kMaskTN;
-    const bool ok = (k0 + kk < K) && (n0 + nn < Ncols);
-    sP[kk][nn] = ok ? __ldg(Pm + static_cast<int64_t>(k0 + kk) * Ncols + n0 + nn) : 0.f;
-  }
-  float gp[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) gp[i][j] = 0.f;
-
-  for (int q0 = 0; q0 < Q; q0 += QC) {
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < QC * kMaskTN; idx += 256) {
-      const int qi = idx / kMaskTN, nn = idx % kMaskTN;
-      const bool ok = (q0 + qi < Q) && (n0 + nn < Ncols);
-      sG[qi][nn] = ok ? __ldg(G + static_cast<int64_t>(q0 + qi) * Ncols + n0 + nn) : 0.f;
-    }
-    for (int idx = threadIdx.x; idx < QC * kMaskKC; idx += 256) {
-      const int qi = idx / kMaskKC, kk = idx % kMaskKC;
-      const bool ok = (q0 + qi < Q) && (k0 + kk < K);
-      sC[qi][kk] = ok ? __ldg(A + static_cast<int64_t>(q0 + qi) * K + k0 + kk) : 0.f;
-    }
-    __syncthreads();
-    if (gproto) {
-#pragma unroll 8
-      for (int qi = 0; qi < QC; ++qi) {
-        const float4 a = *reinterpret_cast<const float4*>(&sC[qi][ty * 4]);
-        const float4 g = *reinterpret_cast<const float4*>(&sG[qi][tx * 4]);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          gp[i][0] = fmaf(av[i], g.x, gp[i][0]);
-          gp[i][1] = fmaf(av[i], g.y, gp[i][1]);
-          gp[i][2] = fmaf(av[i], g.z, gp[i][2]);
-          gp[i][3] = fmaf(av[i], g.w, gp[i][3]);
-        }
-      }
-    }
-    if (gcoeff) {
-      float gc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-      for (int nn = 0; nn < kMaskTN; nn += 4) {
-        const float4 g = *reinterpret_cast<const float4*>(&sG[cq][nn]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 p = *reinterpret_cast<const float4*>(&sP[ck + i][nn]);
-          gc[i] = fmaf(g.x, p.x, fmaf(g.y, p.y, fmaf(g.z, p.z, fmaf(g.w, p.w, gc[i]))));
-        }
-      }
-      if (q0 + cq < Q) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (k0 + ck + i < K) atomicAdd(gcoeff + (static_cast<int64_t>(b) * Q + q0 + cq) * K + k0 + ck + i, gc[i]);
-      }
-    }
-  }
-  if (gproto) {
-    float* GP = gproto + static_cast<int64_t>(b) * K * Ncols;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = k0 + ty * 4 + i;
-      if (k >= K) continue;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t n = n0 + tx * 4 + j;
-        if (n < Ncols) GP[static_cast<int64_t>(k) * Ncols + n] = gp[i][j];
-      }
-    }
-  }
-}
-
-
 // ------------------------------------------------------------------------------------------------------------
 // Second-generation fp32 backward: two register-tiled kernels instead of the fused one above (542 us at R50_360;
 // its grad_coeff half issued 5 shared loads per 16 FMAs).  grad_out (48 MB) is read by both, back to back, so the

@@ -31,7 +31,6 @@
 namespace msda {
 
 constexpr int kTcTileN = 128;        // plane columns per CTA (= MMA M)
-constexpr int kTcThreads = 128;      // 4 warps: warp w drains TMEM lanes 32w..32w+31
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -95,93 +94,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-template <typename OT>
-__device__ __forceinline__ void mask_store(OT* p, float v);
-template <> __device__ __forceinline__ void mask_store<float>(float* p, float v) { __stcs(p, v); }
-template <> __device__ __forceinline__ void mask_store<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
-
-// grid (ceil(Ncols/128), B); block 128 threads; dynamic smem: see mask_tc_smem_bytes().
-//   KP     K rounded up to 16 (<= 64)          QP  Q rounded up to 16 (<= 256)
-//   tmem_cols  power of two >= max(32, QP)
-template <typename OT>
-__global__ void __launch_bounds__(kTcThreads)
-mask_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_constant__ CUtensorMap map_coeff,
-                   OT* __restrict__ out, int Q, int64_t Ncols, int KP, int QP, int tmem_cols) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte aligned operand tiles (required by the 128B swizzle pattern)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t a_bytes_half = static_cast<uint32_t>(KP) * 128u;          // one 64-column half of the proto tile
-  uint8_t* sA = smem;                                                      // 2 halves
-  uint8_t* sB = smem + 2 * a_bytes_half;                                   // QP rows x 128 B (2*KP*128 is a multiple of 1024)
-  __shared__ __align__(8) uint64_t bars[2];                                // [0] operands landed, [1] accumulator ready
-  __shared__ uint32_t s_tmem_base;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y;
-  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * kTcTileN;
-  const uint32_t bar_full = smem_u32(&bars[0]), bar_acc = smem_u32(&bars[1]);
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar_full, 1);
-    mbar_init(bar_acc, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_proto) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_coeff) : "memory");
-  }
-  if (warp == 0) {                                                         // one warp owns TMEM allocation
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = s_tmem_base;
-
-  if (threadIdx.x == 0) {
-    // ---- TMA: both halves of the proto tile + the coefficient block, one transaction barrier
-    const uint32_t tx = 2 * a_bytes_half + static_cast<uint32_t>(QP) * 128u;
-    mbar_expect_tx(bar_full, tx);
-    tma_load_3d(smem_u32(sA), &map_proto, bar_full, static_cast<int>(n0), 0, b);
-    tma_load_3d(smem_u32(sA + a_bytes_half), &map_proto, bar_full, static_cast<int>(n0) + 64, 0, b);
-    tma_load_3d(smem_u32(sB), &map_coeff, bar_full, 0, 0, b);
-    // ---- MMA: KP/16 instructions of 128 x QP x 16, issued by this one thread
-    mbar_wait(bar_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(QP));
-    const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
-    for (int ks = 0; ks < KP / 16; ++ks) {
-      const uint64_t a_desc = umma_desc_sw128(a_addr + ks * 2048u, /*lbo=*/a_bytes_half, /*sbo=*/1024u);
-      const uint64_t b_desc = umma_desc_sw128(b_addr + ks * 32u, /*lbo=*/16u, /*sbo=*/1024u);
-      umma_bf16(tmem_base, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
-    }
-    // arrives on bar_acc when the MMAs above have completed (implies fence::before_thread_sync)
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_acc) : "memory");
-  }
-  __syncwarp();
-
-  // ---- epilogue: every warp drains its 32 lanes; lane i <-> plane column n0 + 32*warp + i
-  mbar_wait(bar_acc, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const int64_t col = n0 + warp * 32 + lane;
-  const bool col_ok = col < Ncols;
-  OT* orow = out + static_cast<int64_t>(b) * Q * Ncols + col;
-  const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  for (int q0 = 0; q0 < Q; q0 += 32) {
-    float v[32];
-    tmem_ld32(lane_base + static_cast<uint32_t>(q0), v);
-    if (col_ok) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (q0 + j < Q) mask_store<OT>(orow + static_cast<int64_t>(q0 + j) * Ncols, v[j]);
-    }
-  }
-
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -376,20 +288,9 @@ mask_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_
 // -------------------------------------------------------------------------------------------------
 // fp32 inputs on the tensor cores with fp32 accuracy ("3xTF32"): the reference trains in fp32 (AMP disabled,
 // configs/R50_coco.yaml:41-42) and a single TF32 or bf16 pass would miss the 1e-4 parity bar, so every operand is split
-// on chip into  a = hi + lo,  hi = a with the low 13 mantissa bits cleared (exactly a TF32 number), lo = a - hi (exact in
-// fp32, 13 significant bits), and the product is accumulated as  hi*hi + hi*lo + lo*hi  in the fp32 TMEM accumulator
-// (the dropped lo*lo term is 2^-22 relative).  Same persistent pipeline as mask_fwd_tc2_kernel plus one stage:
-//   warp 0 TMA producer -> warps 10..13 "split" warps (hi in place, lo to a twin tile; generic-proxy writes are made
-//   visible to the tensor core with fence.proxy.async) -> warp 1 MMA issuer (kind::tf32, K = 8 per instruction, 3 terms)
-//   -> warps 2..9 epilogue (TMEM -> shared -> bulk tensor store).
-// Both operands are staged K-major for kind::tf32: coeff rows (32 k x 4 B = one 128-byte swizzle row) arrive that way
-// from TMA and are split in place; the proto tile arrives as plain [k][128 columns] rows (no swizzle) and the split warps
-// transpose it into the canonical K-major 128B-swizzle layout while splitting (element (n, k) -> n*128 + ((k/4) ^ (n%8))*16
-// + (k%4)*4: 4 conflict-free LDS.32 and one conflict-free STS.128 per 4 elements).  K <= 32, <= 128 query rows per item.
-constexpr int kTc3Stages = 2;
-constexpr int kTc3Threads = 448;
-constexpr int kTc3SplitWarps = 4;
-
+// into  a = hi + lo  (hi = a truncated to TF32, which is what the MMA does to a raw fp32 operand; lo = a - hi, exact in fp32)
+// and the product is accumulated as  hi*hi + hi*lo + lo*hi  in the fp32 TMEM accumulator (the dropped lo*lo term is 2^-22
+// relative).  The kernels are in mask_tc4.cuh (forward / grad_proto), mask_tc_bwd.cuh (grad_coeff) and gemm3x.cuh (Linear).
 // kind::tf32, D = fp32, A and B both K-major (32-bit operands are staged K-major: the split warps transpose proto)
 __host__ __device__ constexpr uint32_t umma_idesc_tf32_m128(uint32_t n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
@@ -402,226 +303,9 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint
       ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// kTransA: the row operand is given as [reduction][rows] (rows contiguous) instead of [rows][reduction] -- the layout of
-// `coeff` when the kernel computes grad_proto[k, n] = sum_q coeff[q, k] * grad_out[q, n].  Its chunk then arrives as a
-// plain [32 q][QN k] box and the split warps transpose it like the column operand.
-template <typename OT, bool kTransA>
-__global__ void __launch_bounds__(kTc3Threads, 1)
-mask_fwd_tc3_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_constant__ CUtensorMap map_coeff,
-                    const __grid_constant__ CUtensorMap map_out, int Q, int n_kchunks, int QS, int QN, int n_qchunks,
-                    int n_tiles_n, int n_items) {
-  // The reduction dimension is walked in chunks of 32 (one 128-byte fp32 swizzle row): n_kchunks stages per work item.
-  // TMA zero-fills rows / columns beyond the tensor, so partial chunks need no special casing.
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr uint32_t raw_bytes = 32u * kTcTileN * 4u;                   // proto chunk as loaded: [32 k][128 n], plain rows
-  const uint32_t a_bytes = kTcTileN * 128u;                              // K-major operand tile: 128 rows (n) x 128 B
-  const uint32_t b_bytes = (static_cast<uint32_t>(QN) * 128u + 1023u) & ~1023u;
-  const uint32_t rawb_bytes = kTransA ? ((32u * static_cast<uint32_t>(QN) * 4u + 1023u) & ~1023u) : 0u;   // [32 q][QN k] plain
-  const uint32_t stage_bytes = raw_bytes + 2 * a_bytes + 2 * b_bytes + rawb_bytes;   // [raw][A hi][A lo][B hi][B lo][raw B]
-  constexpr uint32_t kOutBuf = 32u * kTcTileN * sizeof(OT);
-  uint8_t* out_stage = smem + kTc3Stages * stage_bytes;
-  __shared__ __align__(8) uint64_t bars[3 * kTc3Stages + 4];
-  __shared__ uint32_t s_tmem_base;
-  const uint32_t bar0 = smem_u32(&bars[0]);
-  auto bar_full = [&](int s) { return bar0 + 8u * s; };                                  // TMA landed
-  auto bar_ready = [&](int s) { return bar0 + 8u * (kTc3Stages + s); };                  // split done
-  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * kTc3Stages + s); };              // MMAs consumed the stage
-  auto bar_tfull = [&](int a) { return bar0 + 8u * (3 * kTc3Stages + a); };
-  auto bar_tempty = [&](int a) { return bar0 + 8u * (3 * kTc3Stages + 2 + a); };
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kTc3Stages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_ready(s), kTc3SplitWarps); mbar_init(bar_empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), kTc2EpiWarps); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_proto) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_coeff) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = s_tmem_base;
-
-  auto decode = [&](int item, int& b, int& tile, int& qc) {
-    const int per_chunk = n_items / n_qchunks;
-    qc = item / per_chunk;
-    const int t = item - qc * per_chunk;
-    tile = t % n_tiles_n;
-    b = t / n_tiles_n;
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int i = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x)
-        for (int kc = 0; kc < n_kchunks; ++kc, ++i) {
-          const int s = i % kTc3Stages;
-          const uint32_t ph = (i / kTc3Stages) & 1;
-          int b, tile, qc;
-          decode(item, b, tile, qc);
-          mbar_wait(bar_empty(s), ph ^ 1);
-          const uint32_t dst = smem_u32(smem) + s * stage_bytes;
-          mbar_expect_tx(bar_full(s), raw_bytes + static_cast<uint32_t>(QN) * 128u);
-          tma_load_3d(dst, &map_proto, bar_full(s), tile * kTcTileN, kc * 32, b);
-          if constexpr (kTransA) tma_load_3d(dst + raw_bytes + 2 * a_bytes + 2 * b_bytes, &map_coeff, bar_full(s), qc * QS, kc * 32, b);
-          else tma_load_3d(dst + raw_bytes + 2 * a_bytes, &map_coeff, bar_full(s), kc * 32, qc * QS, b);
-        }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32_m128(static_cast<uint32_t>(QN));
-      int i = 0, it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int a = it & 1;
-        const uint32_t aph = (it >> 1) & 1;
-        mbar_wait(bar_tempty(a), aph ^ 1);
-        uint32_t acc = 0;
-        for (int kc = 0; kc < n_kchunks; ++kc, ++i) {
-          const int s = i % kTc3Stages;
-          const uint32_t ph = (i / kTc3Stages) & 1;
-          mbar_wait(bar_ready(s), ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_hi = smem_u32(smem) + s * stage_bytes + raw_bytes, a_lo = a_hi + a_bytes;
-          const uint32_t b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
-          const uint32_t a_sel[3] = {a_hi, a_hi, a_lo}, b_sel[3] = {b_hi, b_lo, b_hi};     // hi*hi + hi*lo + lo*hi
-          for (int term = 0; term < 3; ++term)
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t a_desc = umma_desc_sw128(a_sel[term] + ks * 32u, 16u, 1024u);
-              const uint64_t b_desc = umma_desc_sw128(b_sel[term] + ks * 32u, 16u, 1024u);
-              umma_tf32(tmem_base + a * 256u, a_desc, b_desc, idesc, acc);
-              acc = 1;
-            }
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_empty(s)) : "memory");
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_tfull(a)) : "memory");
-      }
-    }
-  } else if (warp >= 2 + kTc2EpiWarps) {
-    // ---- split warps: hi in place, lo into the twin tile (same swizzled position: the op is element-wise)
-    const int t = threadIdx.x - (2 + kTc2EpiWarps) * 32;                 // 0 .. 127
-    int i = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x)
-     for (int kc = 0; kc < n_kchunks; ++kc, ++i) {
-      const int s = i % kTc3Stages;
-      const uint32_t ph = (i / kTc3Stages) & 1;
-      mbar_wait(bar_full(s), ph);
-      uint8_t* st = smem + s * stage_bytes;
-      const float* raw = reinterpret_cast<const float*>(st);
-      uint8_t* a_hi = st + raw_bytes;
-      uint8_t* a_lo = a_hi + a_bytes;
-      uint4* b_hi = reinterpret_cast<uint4*>(st + raw_bytes + 2 * a_bytes);
-      uint4* b_lo = reinterpret_cast<uint4*>(st + raw_bytes + 2 * a_bytes + b_bytes);
-      auto split = [](uint4& v, uint4& lo) {
-        uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
-        uint32_t* pl = reinterpret_cast<uint32_t*>(&lo);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t hi = pv[e] & 0xffffe000u;
-          pl[e] = __float_as_uint(__uint_as_float(pv[e]) - __uint_as_float(hi));
-          pv[e] = hi;
-        }
-      };
-      // proto: transpose [k][n] -> K-major rows of n, split; thread <-> column n (conflict-free both ways)
-      {
-        const int n = t;                                                // 128 split threads <-> 128 columns
-        const uint32_t rowoff = static_cast<uint32_t>(n) * 128u;
-#pragma unroll
-        for (int kq = 0; kq < 8; ++kq) {
-          uint4 v, lo;                                        // rows beyond the tensor were zero-filled by TMA
-          v.x = __float_as_uint(raw[(kq * 4 + 0) * kTcTileN + n]);
-          v.y = __float_as_uint(raw[(kq * 4 + 1) * kTcTileN + n]);
-          v.z = __float_as_uint(raw[(kq * 4 + 2) * kTcTileN + n]);
-          v.w = __float_as_uint(raw[(kq * 4 + 3) * kTcTileN + n]);
-          split(v, lo);
-          const uint32_t off = rowoff + static_cast<uint32_t>((kq ^ (n & 7)) * 16);
-          *reinterpret_cast<uint4*>(a_hi + off) = v;
-          *reinterpret_cast<uint4*>(a_lo + off) = lo;
-        }
-      }
-      if constexpr (kTransA) {
-        // row operand: [32 q][QN k] plain -> K-major rows k of 32 q, swizzled, split
-        const float* rawb = reinterpret_cast<const float*>(st + raw_bytes + 2 * a_bytes + 2 * b_bytes);
-        uint8_t* bh = reinterpret_cast<uint8_t*>(b_hi);
-        uint8_t* bl = reinterpret_cast<uint8_t*>(b_lo);
-        for (int task = t; task < QN * 8; task += kTc3SplitWarps * 32) {
-          const int row = task % QN, qq = task / QN;                     // lanes walk the rows (k): conflict-free reads
-          uint4 v, lo;
-          v.x = __float_as_uint(rawb[(qq * 4 + 0) * QN + row]);
-          v.y = __float_as_uint(rawb[(qq * 4 + 1) * QN + row]);
-          v.z = __float_as_uint(rawb[(qq * 4 + 2) * QN + row]);
-          v.w = __float_as_uint(rawb[(qq * 4 + 3) * QN + row]);
-          split(v, lo);
-          const uint32_t off = static_cast<uint32_t>(row) * 128u + static_cast<uint32_t>((qq ^ (row & 7)) * 16);
-          *reinterpret_cast<uint4*>(bh + off) = v;
-          *reinterpret_cast<uint4*>(bl + off) = lo;
-        }
-      } else {
-        for (uint32_t k = t; k < static_cast<uint32_t>(QN) * 8u; k += kTc3SplitWarps * 32) { uint4 v = b_hi[k], lo; split(v, lo); b_hi[k] = v; b_lo[k] = lo; }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_ready(s));
-    }
-  } else {
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
-    const bool is_issuer = ((warp - 2) & 3) == 0 && lane == 0;
-    OT* my_stage = reinterpret_cast<OT*>(out_stage + (half * 2) * kOutBuf);
-    uint32_t use = 0;
-    int i = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
-      const int a = i & 1;
-      const uint32_t aph = (i >> 1) & 1;
-      int b, tile, qc;
-      decode(item, b, tile, qc);
-      const int q_begin = qc * QS;
-      const int rows = (qc == n_qchunks - 1) ? (Q - q_begin) : QS;
-      mbar_wait(bar_tfull(a), aph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t lane_base = tmem_base + a * 256u + (static_cast<uint32_t>(quarter * 32) << 16);
-      for (int q0 = half * 32; q0 < rows; q0 += 64, ++use) {
-        OT* buf = my_stage + (use & 1) * (32 * kTcTileN);
-        if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        named_bar_sync(1 + half, 128);
-        float v[32];
-        tmem_ld32(lane_base + static_cast<uint32_t>(q0), v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) st_stage(buf + j * kTcTileN + quarter * 32 + lane, v[j]);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        named_bar_sync(1 + half, 128);
-        if (is_issuer) tma_store_3d(&map_out, smem_u32(buf), tile * kTcTileN, q_begin + q0, b);
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty(a));
-    }
-    if (is_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  }
-
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 1)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-}
-
-inline size_t mask_tc3_smem_bytes(int QN, size_t out_elem, bool trans_a) {
-  const size_t raw_bytes = static_cast<size_t>(32) * kTcTileN * 4;
-  const size_t a_bytes = static_cast<size_t>(kTcTileN) * 128;
-  const size_t b_bytes = (static_cast<size_t>(QN) * 128 + 1023) & ~size_t(1023);
-  const size_t rawb = trans_a ? ((static_cast<size_t>(32) * QN * 4 + 1023) & ~size_t(1023)) : 0;
-  return 1024 + kTc3Stages * (raw_bytes + 2 * a_bytes + 2 * b_bytes + rawb) + 4 * 32 * kTcTileN * out_elem;
-}
-
 inline size_t mask_tc2_smem_bytes(int KP, int QN, size_t out_elem) {
   const size_t stage = (2 * static_cast<size_t>(KP) * 128 + static_cast<size_t>(QN) * 128 + 1023) & ~size_t(1023);
   return 1024 + kTc2Stages * stage + 4 * 32 * kTcTileN * out_elem;
 }
-
-inline size_t mask_tc_smem_bytes(int KP, int QP) { return 1024 + 2 * static_cast<size_t>(KP) * 128 + static_cast<size_t>(QP) * 128; }
 
 }  // namespace msda

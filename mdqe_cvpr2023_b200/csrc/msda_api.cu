@@ -54,6 +54,34 @@ static std::atomic<int>* find_option(const char* key) {
   return nullptr;
 }
 
+namespace {
+struct AttrKey { const void* func; int attr, device, value; };
+std::mutex g_attr_mu;
+std::vector<AttrKey> g_attr_done;
+}  // namespace
+
+int ensure_func_attr_impl(const void* func, cudaFuncAttribute attr, int value) {
+  int dev = 0;
+  if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  std::lock_guard<std::mutex> lock(g_attr_mu);
+  for (const AttrKey& k : g_attr_done)
+    if (k.func == func && k.attr == static_cast<int>(attr) && k.device == dev && k.value == value) return 0;
+  if (int rc = check_cuda(cudaFuncSetAttribute(func, attr, value), "cudaFuncSetAttribute")) return rc;
+  g_attr_done.push_back(AttrKey{func, static_cast<int>(attr), dev, value});
+  return 0;
+}
+
+int sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 148; }
+  if (dev >= 0 && dev < 64 && cache[dev].load(std::memory_order_relaxed) > 0) return cache[dev].load(std::memory_order_relaxed);
+  int sms = 148;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); sms = 148; }
+  if (dev >= 0 && dev < 64) cache[dev].store(sms, std::memory_order_relaxed);
+  return sms;
+}
+
 int option(const char* key) {
   std::atomic<int>* o = find_option(key);
   return o ? o->load() : 0;
@@ -154,7 +182,7 @@ int64_t msda_launch_count(void) { return g_launches.load(); }
 void msda_launch_count_reset(void) { g_launches.store(0); }
 
 static int grouped_supported(const char* who, int dtype, const Problem& pb, bool fast) {
-  if (pb.G == 1) return 0;
+  if (pb.G == 1 && pb.scale == 1.f) return 0;            // the plain operator: every kernel family implements it
   if (pb.G < 1 || pb.G * pb.L > kMaxLevels) return fail(MSDA_ERR_UNSUPPORTED, "%s: G*L = %d exceeds %d level tables", who, pb.G * pb.L, kMaxLevels);
   if (!fast || !fast2_lp(pb.L * pb.P) || dtype == MSDA_F64)
     return fail(MSDA_ERR_UNSUPPORTED, "%s: the grouped form needs D in {32,24}, L*P in {8,12,16}, fp32/bf16 and 16-byte aligned tensors", who);
@@ -210,7 +238,7 @@ size_t msda_backward_workspace_bytes(int dtype, int N, int S, int M, int D) {
 static int backward_impl(const char* who, void* stream, int dtype, const void* value, const int64_t* shapes,
                          const int64_t* level_start, const void* loc, const void* aw, const void* grad_out, int N, int S, int M,
                          int D, int G, int L, int Lq, int P, float scale, void* grad_value, void* grad_loc, void* grad_aw,
-                         void* workspace, size_t workspace_bytes, FusedArgs fz = FusedArgs{nullptr, nullptr, 0, 0, 1.f}) {
+                         void* workspace, size_t workspace_bytes, FusedArgs fz = FusedArgs{nullptr, nullptr, 0, 0, 1.f}, int flags = 0) {
   if (int rc = validate(who, dtype, value, shapes, level_start, loc, aw, N, S, M, D, L, Lq, P)) return rc;
   Problem pb{N, S, M, D, L, Lq, P, (int64_t)N * Lq * M, G, scale, fz};
   const size_t n_value = (size_t)N * S * M * D;
@@ -222,7 +250,8 @@ static int backward_impl(const char* who, void* stream, int dtype, const void* v
     return fail(MSDA_ERR_WORKSPACE, "%s: bf16 needs a %zu-byte fp32 workspace (got %zu)", who, need, workspace_bytes);
   void* acc = is_bf16 ? workspace : grad_value;
   const size_t acc_bytes = is_bf16 ? need : n_value * dtype_size(dtype);
-  if (acc_bytes > 0)
+  if (flags & ~MSDA_BWD_ACC_ZEROED) return fail(MSDA_ERR_INVALID_ARG, "%s: unknown flags 0x%x", who, flags);
+  if (acc_bytes > 0 && !(flags & MSDA_BWD_ACC_ZEROED))    // MSDA_BWD_ACC_ZEROED: the caller zero-filled it off the critical path
     if (int rc = check_cuda(cudaMemsetAsync(acc, 0, acc_bytes, st), "cudaMemsetAsync(grad_value)")) return rc;
   if (pb.n_pairs == 0) {
     if (is_bf16 && n_value > 0)
@@ -289,6 +318,20 @@ int msda_backward_grouped(void* stream, int dtype, const void* value, const int6
                        Lq, P, scale, grad_value, grad_loc, grad_aw, workspace, workspace_bytes);
 }
 
+int msda_backward_grouped_flags(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                                const void* loc, const void* aw, const void* grad_out, int N, int S, int M, int D, int G, int L,
+                                int Lq, int P, float scale, void* grad_value, void* grad_loc, void* grad_aw, void* workspace,
+                                size_t workspace_bytes, int flags) {
+  return backward_impl("msda_backward_grouped_flags", stream, dtype, value, shapes, level_start, loc, aw, grad_out, N, S, M, D, G, L,
+                       Lq, P, scale, grad_value, grad_loc, grad_aw, workspace, workspace_bytes, FusedArgs{nullptr, nullptr, 0, 0, 1.f}, flags);
+}
+
+int msda_zero_fill(void* stream, void* ptr, size_t bytes) {
+  if (bytes == 0) return 0;
+  if (!ptr) return fail(MSDA_ERR_INVALID_ARG, "msda_zero_fill: NULL pointer");
+  return check_cuda(cudaMemsetAsync(ptr, 0, bytes, static_cast<cudaStream_t>(stream)), "cudaMemsetAsync(msda_zero_fill)");
+}
+
 int msda_fused_forward(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
                        const void* ref_points, int R, const void* offsets, const void* logits, const void* grid, int mode,
                        float offset_scale, int N, int S, int M, int D, int G, int L, int Lq, int P, float scale, void* out) {
@@ -306,6 +349,16 @@ int msda_fused_backward(void* stream, int dtype, const void* value, const int64_
   const FusedArgs fz{static_cast<const float*>(ref_points), static_cast<const float*>(grid), R, mode, offset_scale};
   return backward_impl("msda_fused_backward", stream, dtype, value, shapes, level_start, offsets, logits, grad_out, N, S, M, D, G,
                        L, Lq, P, scale, grad_value, grad_offsets, grad_logits, nullptr, 0, fz);
+}
+
+int msda_fused_backward_flags(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                        const void* ref_points, int R, const void* offsets, const void* logits, const void* grid, int mode,
+                        float offset_scale, const void* grad_out, int N, int S, int M, int D, int G, int L, int Lq, int P,
+                        float scale, void* grad_value, void* grad_offsets, void* grad_logits, int flags) {
+  if (!ref_points) return fail(MSDA_ERR_INVALID_ARG, "msda_fused_backward_flags: reference points are NULL");
+  const FusedArgs fz{static_cast<const float*>(ref_points), static_cast<const float*>(grid), R, mode, offset_scale};
+  return backward_impl("msda_fused_backward_flags", stream, dtype, value, shapes, level_start, offsets, logits, grad_out, N, S, M, D, G,
+                       L, Lq, P, scale, grad_value, grad_offsets, grad_logits, nullptr, 0, fz, flags);
 }
 
 int mask_logits_forward(void* stream, int in_dtype, int out_dtype, const void* coeff, const void* proto, int B, int Q,

@@ -80,14 +80,25 @@ __device__ __forceinline__ void red_add_f32x4_if(bool on, float* p, float a, flo
                ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "r"(static_cast<uint32_t>(on)) : "memory");
 }
 
+// A level table entry is usable only if its window [start, start + H*W) lies inside the S rows of a batch element.  The
+// reference asserts sum(H_l*W_l) == S on the host (ms_deform_attn.py:134, one device sync per call); here a table that does not
+// fit disables that level (H = W = 0: every sample of it is out of range, contributes 0 and gets zero gradients) instead of
+// letting the gathers and, worse, the grad_value reductions run past the tensor.
+__device__ __forceinline__ bool level_fits(int64_t H, int64_t W, int64_t start, int S) {
+  return H >= 0 && W >= 0 && start >= 0 && H <= 0x7fffffff && W <= 0x7fffffff && H * W <= static_cast<int64_t>(S) &&
+         start <= static_cast<int64_t>(S) - H * W;
+}
+
 // Stage the per-level geometry (int64 on device in the reference API) into shared memory.
 __device__ __forceinline__ void stage_levels(LevelInfo* s_lvl, const int64_t* __restrict__ shapes,
-                                             const int64_t* __restrict__ level_start, int L) {
+                                             const int64_t* __restrict__ level_start, int L, int S) {
   if (threadIdx.x < L) {
+    const int64_t H = shapes[2 * threadIdx.x], W = shapes[2 * threadIdx.x + 1], start = level_start[threadIdx.x];
+    const bool ok = level_fits(H, W, start, S);
     LevelInfo li;
-    li.H = static_cast<int>(shapes[2 * threadIdx.x]);
-    li.W = static_cast<int>(shapes[2 * threadIdx.x + 1]);
-    li.start = static_cast<int>(level_start[threadIdx.x]);
+    li.H = ok ? static_cast<int>(H) : 0;
+    li.W = ok ? static_cast<int>(W) : 0;
+    li.start = ok ? static_cast<int>(start) : 0;
     li.pad = 0;
     s_lvl[threadIdx.x] = li;
   }

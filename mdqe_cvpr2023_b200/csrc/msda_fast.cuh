@@ -92,7 +92,7 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   __shared__ LevelInfo s_lvl[kMaxLevels];
   __shared__ __align__(16) Slot s_slot[kWarpsPerCta][128];
 
-  stage_levels(s_lvl, shapes, level_start, L);
+  stage_levels(s_lvl, shapes, level_start, L, S);
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -164,7 +164,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   __shared__ __align__(16) Slot s_slot[kWarpsPerCta][128];
   __shared__ __align__(16) float s_dot[kWarpsPerCta][32 * C::ROW];
 
-  stage_levels(s_lvl, shapes, level_start, L);
+  stage_levels(s_lvl, shapes, level_start, L, S);
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

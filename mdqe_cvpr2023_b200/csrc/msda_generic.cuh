@@ -67,8 +67,9 @@ msda_fwd_generic_kernel(const VT* __restrict__ value, const int64_t* __restrict_
       const bool cok = c < D;
       AT acc = 0;
       for (int l = 0; l < L; ++l) {
-        const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
-        const VT* vl = value + (n * S + level_start[l]) * row + static_cast<int64_t>(m) * D;
+        const bool fits = level_fits(shapes[2 * l], shapes[2 * l + 1], level_start[l], S);      // see msda_common.cuh
+        const int H = fits ? static_cast<int>(shapes[2 * l]) : 0, W = fits ? static_cast<int>(shapes[2 * l + 1]) : 0;
+        const VT* vl = value + (n * S + (fits ? level_start[l] : 0)) * row + static_cast<int64_t>(m) * D;
         for (int p = 0; p < P; ++p) {
           const int64_t si = (pair * L + l) * P + p;
           const AT a = static_cast<AT>(ld_as_float(aw + si));
@@ -110,8 +111,9 @@ msda_bwd_generic_kernel(const VT* __restrict__ value, const int64_t* __restrict_
     const int64_t n = pair / (static_cast<int64_t>(M) * Lq);
     const VT* go = grad_out + pair * D;
     for (int l = 0; l < L; ++l) {
-      const int H = static_cast<int>(shapes[2 * l]), W = static_cast<int>(shapes[2 * l + 1]);
-      const int64_t lbase = (n * S + level_start[l]) * row + static_cast<int64_t>(m) * D;
+      const bool fits = level_fits(shapes[2 * l], shapes[2 * l + 1], level_start[l], S);
+      const int H = fits ? static_cast<int>(shapes[2 * l]) : 0, W = fits ? static_cast<int>(shapes[2 * l + 1]) : 0;
+      const int64_t lbase = (n * S + (fits ? level_start[l] : 0)) * row + static_cast<int64_t>(m) * D;
       for (int p = 0; p < P; ++p) {
         const int64_t si = (pair * L + l) * P + p;
         const AT a = static_cast<AT>(ld_as_float(aw + si));

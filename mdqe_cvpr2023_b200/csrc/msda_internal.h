@@ -20,6 +20,16 @@ int after_launch(const char* kernel_name);
 
 int option(const char* key);          // current value of a tuning knob
 
+// cudaFuncSetAttribute is per device (context), so "set once per process" leaves every device but the first without its
+// opt-in to > 48 KB of dynamic shared memory (launches then fail with `invalid argument` under nn.DataParallel, per-device
+// threads, or the *_host entries' `device` argument).  This remembers (function, attribute, current device) triples instead.
+int ensure_func_attr_impl(const void* func, cudaFuncAttribute attr, int value);
+template <typename K>
+inline int ensure_func_attr(K kernel, cudaFuncAttribute attr, int value) {
+  return ensure_func_attr_impl(reinterpret_cast<const void*>(kernel), attr, value);
+}
+int sm_count();                       // multiprocessors of the CURRENT device (cached per device)
+
 struct Options {
   std::atomic<int> fwd_variant{0};    // 0 = auto (fast2 / fast when eligible), 1 = force generic, 2 = first-generation fast, 3 = fast2 with batched gathers (80 registers)
   std::atomic<int> bwd_variant{0};    // 0 = auto (fast2 / fast), 1 = generic, 2 = first-generation fast

@@ -37,9 +37,7 @@ inline int pick_chunk(const Problem& pb) {
   const int unit = kWarpsPerCta * qpw;                   // pairs one CTA round covers
   int chunk = options().chunk_pairs.load();
   if (chunk <= 0) {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t want = pb.n_pairs / (int64_t(sms) * 8);  // aim at >= 8 CTAs per SM
+    const int64_t want = pb.n_pairs / (int64_t(sm_count()) * 8);  // aim at >= 8 CTAs per SM
     chunk = static_cast<int>(want < 48 ? want : 48);        // 48: 3400 CTAs on the encoder shape = 5.7 waves of 4 CTAs/SM (64: 4.3 waves, 2 % slower)
   }
   chunk = ((chunk + unit - 1) / unit) * unit;
@@ -83,8 +81,7 @@ inline bool prefer_small_carveout(K kernel, int ctas_per_sm) {
   const size_t need = static_cast<size_t>(ctas_per_sm) * (fa.sharedSizeBytes + 1024);
   int pct = static_cast<int>((need * 100 + 233471) / 233472);
   if (pct > 100) pct = 100;
-  if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess) { cudaGetLastError(); return false; }
-  return true;
+  return ensure_func_attr(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct) == 0;      // remembered per device
 }
 
 #ifndef MSDA_FWD_MINB
@@ -113,7 +110,7 @@ inline void launch_bwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int ch
   const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
   const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
 #define MSDA_BWD2(LPV, GRP) do { \
-      static const bool carve = prefer_small_carveout(msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP>, (GRP) ? 2 : MSDA_BWD_MINB); (void)carve; \
+      prefer_small_carveout(msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP>, (GRP) ? 2 : MSDA_BWD_MINB); \
       msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP><<<grid, kThreads, 0, st>>>( \
       v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz, merge); } while (0)
   const bool grouped = pb.G > 1 || pb.scale != 1.f;

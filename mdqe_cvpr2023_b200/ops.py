@@ -84,9 +84,35 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     return out
 
 
+def new_backward_accumulator(value):
+    """Zero-filled tensor the backward accumulates grad_value into: grad_value itself (fp32 / fp64) or the fp32 workspace of
+    the bf16 modes.  Allocate it early (MSDeformAttnFunction does so on a side stream during the forward pass) and hand it to
+    the backward entries as ``accumulator=`` -- the 20.9 MB zero-fill then leaves the critical path (MSDA_BWD_ACC_ZEROED)."""
+    dtype = torch.float32 if value.dtype == torch.bfloat16 else value.dtype
+    return torch.zeros(value.shape, dtype=dtype, device=value.device)
+
+
+def _backward_buffers(value, code, accumulator, who):
+    """-> (grad_value, workspace tensor or None, workspace bytes, flags)"""
+    lib = _lib.load()
+    N, S, M, D = value.shape
+    ws_bytes = lib.msda_backward_workspace_bytes(code, N, S, M, D)
+    if accumulator is None:
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
+        return torch.empty_like(value), ws, ws_bytes, 0
+    want = torch.float32 if ws_bytes else value.dtype
+    if accumulator.dtype != want or accumulator.numel() != value.numel() or accumulator.device != value.device or \
+            not accumulator.is_contiguous():
+        raise RuntimeError(f"{who}: accumulator must be a contiguous zero-filled {want} tensor shaped like value")
+    if ws_bytes:
+        return torch.empty_like(value), accumulator, ws_bytes, _lib.BWD_ACC_ZEROED
+    return accumulator.view(value.shape), None, 0, _lib.BWD_ACC_ZEROED
+
+
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-                            im2col_step):
-    """-> [grad_value, grad_sampling_loc, grad_attn_weight]; drop-in for the extension's backward."""
+                            im2col_step, accumulator=None):
+    """-> [grad_value, grad_sampling_loc, grad_attn_weight]; drop-in for the extension's backward.
+    ``accumulator``: optional result of new_backward_accumulator(value) (zero-filled ahead of time)."""
     who = "ms_deform_attn_backward"
     _check_inputs(who, [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                         ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("grad_output", grad_output)])
@@ -96,16 +122,14 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     code = _dtype_code(value, sampling_loc, attn_weight, who)
     lib = _lib.load()
     with torch.cuda.device(value.device):
-        grad_value = torch.empty_like(value)
+        grad_value, ws, ws_bytes, flags = _backward_buffers(value, code, accumulator, who)
         grad_loc = torch.empty_like(sampling_loc)
         grad_aw = torch.empty_like(attn_weight)
-        ws_bytes = lib.msda_backward_workspace_bytes(code, N, S, M, D)
-        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
-        rc = lib.msda_backward(_stream_ptr(value.device), code, value.data_ptr(), spatial_shapes.data_ptr(),
-                               level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
-                               grad_output.data_ptr(), N, S, M, D, L, Lq, P,
-                               grad_value.data_ptr(), grad_loc.data_ptr(), grad_aw.data_ptr(),
-                               ws.data_ptr() if ws is not None else None, ws_bytes)
+        rc = lib.msda_backward_grouped_flags(_stream_ptr(value.device), code, value.data_ptr(), spatial_shapes.data_ptr(),
+                                             level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                                             grad_output.data_ptr(), N, S, M, D, 1, L, Lq, P, 1.0,
+                                             grad_value.data_ptr(), grad_loc.data_ptr(), grad_aw.data_ptr(),
+                                             ws.data_ptr() if ws is not None else None, ws_bytes, flags)
     _lib.check(rc, who)
     return [grad_value, grad_loc, grad_aw]
 
@@ -148,7 +172,8 @@ def ms_deform_attn_grouped_forward(value, spatial_shapes, level_start_index, sam
     return out
 
 
-def ms_deform_attn_grouped_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, scale):
+def ms_deform_attn_grouped_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, scale,
+                                    accumulator=None):
     who = "ms_deform_attn_grouped_backward"
     _check_inputs(who, [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                         ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("grad_output", grad_output)])
@@ -158,14 +183,13 @@ def ms_deform_attn_grouped_backward(value, spatial_shapes, level_start_index, sa
     code = _dtype_code(value, sampling_loc, attn_weight, who)
     lib = _lib.load()
     with torch.cuda.device(value.device):
-        grad_value, grad_loc, grad_aw = torch.empty_like(value), torch.empty_like(sampling_loc), torch.empty_like(attn_weight)
-        ws_bytes = lib.msda_backward_workspace_bytes(code, N, S, M, D)
-        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
-        rc = lib.msda_backward_grouped(_stream_ptr(value.device), code, value.data_ptr(), spatial_shapes.data_ptr(),
-                                       level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
-                                       grad_output.data_ptr(), N, S, M, D, G, L, Lq, P, float(scale),
-                                       grad_value.data_ptr(), grad_loc.data_ptr(), grad_aw.data_ptr(),
-                                       ws.data_ptr() if ws is not None else None, ws_bytes)
+        grad_value, ws, ws_bytes, flags = _backward_buffers(value, code, accumulator, who)
+        grad_loc, grad_aw = torch.empty_like(sampling_loc), torch.empty_like(attn_weight)
+        rc = lib.msda_backward_grouped_flags(_stream_ptr(value.device), code, value.data_ptr(), spatial_shapes.data_ptr(),
+                                             level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                                             grad_output.data_ptr(), N, S, M, D, G, L, Lq, P, float(scale),
+                                             grad_value.data_ptr(), grad_loc.data_ptr(), grad_aw.data_ptr(),
+                                             ws.data_ptr() if ws is not None else None, ws_bytes, flags)
     _lib.check(rc, who)
     return [grad_value, grad_loc, grad_aw]
 
@@ -219,7 +243,7 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, refer
 
 
 def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, reference_points, offsets, logits, grid, mode,
-                                  offset_scale, grad_output, scale=1.0):
+                                  offset_scale, grad_output, scale=1.0, accumulator=None):
     who = "ms_deform_attn_fused_backward"
     tensors = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                ("reference_points", reference_points), ("offsets", offsets), ("logits", logits), ("grad_output", grad_output)]
@@ -230,12 +254,13 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, refe
                                                                offsets, logits, grid, mode, who)
     lib = _lib.load()
     with torch.cuda.device(value.device):
-        grad_value, grad_offsets, grad_logits = torch.empty_like(value), torch.empty_like(offsets), torch.empty_like(logits)
-        rc = lib.msda_fused_backward(_stream_ptr(value.device), _lib.MSDA_F32, value.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
-                                     reference_points.data_ptr(), R, offsets.data_ptr(), logits.data_ptr(),
-                                     grid.data_ptr() if grid is not None else None, int(mode), float(offset_scale),
-                                     grad_output.data_ptr(), N, S, M, D, G, L, Lq, P, float(scale),
-                                     grad_value.data_ptr(), grad_offsets.data_ptr(), grad_logits.data_ptr())
+        grad_value, _, _, flags = _backward_buffers(value, _lib.MSDA_F32, accumulator, who)
+        grad_offsets, grad_logits = torch.empty_like(offsets), torch.empty_like(logits)
+        rc = lib.msda_fused_backward_flags(_stream_ptr(value.device), _lib.MSDA_F32, value.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
+                                           reference_points.data_ptr(), R, offsets.data_ptr(), logits.data_ptr(),
+                                           grid.data_ptr() if grid is not None else None, int(mode), float(offset_scale),
+                                           grad_output.data_ptr(), N, S, M, D, G, L, Lq, P, float(scale),
+                                           grad_value.data_ptr(), grad_offsets.data_ptr(), grad_logits.data_ptr(), flags)
     _lib.check(rc, who)
     return grad_value, grad_offsets, grad_logits
 

@@ -23,7 +23,10 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "msda_fwd_bwd_clips_per_s" and d["unit"] == "clips/s"
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
-    assert d["value"] > 0 and abs(d["value"] - 1e3 / d["ms_per_step"]) < 1e-6 * d["value"]
+    # a timed step is a bounded sample of the clip (1 of 6 layers + mask); the clip time it implies is reported beside it
+    assert d["value"] > 0 and abs(d["value"] - 1e3 / d["clip_ms"]) < 1e-6 * d["value"]
+    assert abs(d["ms_per_step"] - (d["layer_ms"] + d["mask_ms"])) < 1e-6 * d["ms_per_step"] and d["ms_per_step"] < d["clip_ms"]
+    assert abs(d["clip_ms"] - (6 * d["layer_ms"] + d["mask_ms"])) < 1e-6 * d["clip_ms"]
     assert d["config"]["workload"].startswith("R50_ovis_360") and "model" not in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -586,13 +586,3 @@ def test_spatial_module_fused_prologue_equals_unfused(pred_offsets):
         bound = ref[..., 2:].view(B, Q, 1, 1, 1, 2) * 8
         frac = ((res <= -bound) | (res >= bound)).float().mean().item()
         assert 0.01 < frac < 0.99, frac
-
-
-def test_tiled_fixed_point_backward_experiment_is_parity_green():
-    """bwd_variant = 5: grad_value of the coarse levels accumulated in shared memory in per-CTA fixed point
-    (csrc/msda_bwd_tile.cuh; not the default because it measured slower) -- must still match the oracle."""
-    from mdqe_cvpr2023_b200 import _lib
-    _lib.set_option("bwd_variant", 5)
-    for dist in ("local", "wide"):
-        inp = make_inputs(1, R50_360, 8, 32, 4, dist=dist, seed=40)
-        check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"tiled bwd {dist}", inp)

@@ -76,12 +76,6 @@ def main():
                 rec(f"ours_fwd_chunk{chunk}", timed(lambda: ops.ms_deform_attn_forward(*a, 64), args.iters, flush), fwd_b)
                 rec(f"ours_bwd_chunk{chunk}", timed(lambda: ops.ms_deform_attn_backward(*a, inp["grad_out"], 64), args.iters, flush), bwd_b)
             _lib.set_option("chunk_pairs", 0)
-            _lib.set_option("bwd_variant", 5)
-            for rows, qpc in ((64, 64), (320, 64), (320, 32), (320, 128)):
-                _lib.set_option("tile_rows", rows); _lib.set_option("tile_q", qpc)
-                rec(f"ours_bwd_tile_r{rows}_q{qpc}", timed(lambda: ops.ms_deform_attn_backward(*a, inp["grad_out"], 64), args.iters, flush), bwd_b)
-            _lib.set_option("tile_rows", 320); _lib.set_option("tile_q", 64)
-            _lib.set_option("bwd_variant", 0)
             _lib.set_option("fwd_variant", 3)
             rec("ours_fwd_lean", timed(lambda: ops.ms_deform_attn_forward(*a, 64), args.iters, flush), fwd_b)
             _lib.set_option("fwd_variant", 2)
