@@ -55,8 +55,11 @@ typedef enum {
  *   MSDA_BF16       : value/out/grad_out/grad_value AND loc/aw/grad_loc/grad_aw are bf16
  *   MSDA_F64        : everything fp64 (gradcheck path of ops/test.py:63-78)
  *   MSDA_BF16_LOC32 : value/out/grad_out/grad_value bf16; loc/aw/grad_loc/grad_aw fp32
+ *   MSDA_F16        : IEEE half -- mask_logits_forward only: the reference evaluates under autocast (train_net.py:207-208), so
+ *                     the einsum at mdqe/mdqe.py:384 and transformer_dec.py:255 runs in fp16 there; the sampling operator
+ *                     itself is cast to fp32 by its custom_fwd (ms_deform_attn_func.py:24) and has no fp16 mode
  */
-typedef enum { MSDA_F32 = 0, MSDA_BF16 = 1, MSDA_F64 = 2, MSDA_BF16_LOC32 = 3 } msda_dtype;
+typedef enum { MSDA_F32 = 0, MSDA_BF16 = 1, MSDA_F64 = 2, MSDA_BF16_LOC32 = 3, MSDA_F16 = 4 } msda_dtype;
 
 int msda_abi_version(void);
 const char* msda_last_error(void);
@@ -155,8 +158,9 @@ int msda_fused_backward_flags(void* stream, int dtype,
 /* Mask contraction: out[b,q,n] = sum_k coeff[b,q,k] * proto[b,k,n], n over the flattened (t,h,w)
  * plane (Ncols = T*H*W).  coeff [B,Q,K], proto [B,K,Ncols], out [B,Q,Ncols].
  *   in_dtype  MSDA_F32 (3xTF32: operands split on chip into hi + lo TF32 parts, hi*hi + hi*lo + lo*hi
- *             accumulated in fp32, parity with the fp32 einsum to ~1e-6) or MSDA_BF16 (one pass)
- *   out_dtype MSDA_F32 or MSDA_BF16
+ *             accumulated in fp32, parity with the fp32 einsum to ~1e-6), MSDA_BF16 or MSDA_F16 (one kind::f16 pass,
+ *             fp32 accumulation)
+ *   out_dtype MSDA_F32, or the 16-bit type of the inputs (fp32 inputs: MSDA_F32 or MSDA_BF16)
  * Runs on the 5th-gen tensor cores (tcgen05, accumulators in TMEM). */
 int mask_logits_forward(void* stream, int in_dtype, int out_dtype,
                         const void* coeff, const void* proto,

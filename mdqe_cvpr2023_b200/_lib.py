@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 # MSDA_B200_LIB: experiment builds only (tools/whatif_bench.py); the product library is always the in-tree one
 LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(PKG_DIR, "libmsda_b200.so")
 
-MSDA_F32, MSDA_BF16, MSDA_F64, MSDA_BF16_LOC32 = 0, 1, 2, 3
+MSDA_F32, MSDA_BF16, MSDA_F64, MSDA_BF16_LOC32, MSDA_F16 = 0, 1, 2, 3, 4
 ABI_VERSION = 3
 BWD_ACC_ZEROED = 1
 

@@ -30,7 +30,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
 }
 
 // bf16 / fp32 tensor [d2, d1, d0] (d0 contiguous) -> 3-D tiled map with a {128 bytes, box1, 1} box and 128B swizzle.
-static int make_map_in(CUtensorMap* map, const void* base, bool fp32, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1) {
+static int make_map_in(CUtensorMap* map, const void* base, int dtype, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1) {
+  const bool fp32 = dtype == MSDA_F32;
   PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
   if (!enc) return fail(MSDA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const uint64_t es = fp32 ? 4 : 2;
@@ -38,7 +39,8 @@ static int make_map_in(CUtensorMap* map, const void* base, bool fp32, uint64_t d
   const cuuint64_t strides[2] = {d0 * es, d0 * d1 * es};
   const cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / es), box1, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = enc(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  const CUtensorMapDataType dt = fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (dtype == MSDA_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  const CUresult r = enc(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          option("mask_debug") == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -47,7 +49,7 @@ static int make_map_in(CUtensorMap* map, const void* base, bool fp32, uint64_t d
 }
 
 static bool mask_tc_eligible(int in_dtype, const void* coeff, const void* proto, int Q, int K, int64_t Ncols) {
-  if (in_dtype != MSDA_BF16) return false;
+  if (in_dtype != MSDA_BF16 && in_dtype != MSDA_F16) return false;
   if (K < 8 || K > 64 || K % 8 != 0) return false;                     // 16-byte global strides, <= 4 K steps
   if (Q < 1) return false;
   if (Ncols % 8 != 0 || Ncols >= (int64_t(1) << 31)) return false;
@@ -81,7 +83,7 @@ static int make_map_out(CUtensorMap* map, void* base, bool bf16, uint64_t d0, ui
 }
 
 template <typename OT>
-static int launch_mask_tc2(cudaStream_t st, const void* coeff, const void* proto, void* out, int B, int Q, int K,
+static int launch_mask_tc2(cudaStream_t st, int in_dtype, const void* coeff, const void* proto, void* out, int B, int Q, int K,
                            int64_t Ncols) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -103,12 +105,11 @@ static int launch_mask_tc2(cudaStream_t st, const void* coeff, const void* proto
   const int64_t n_items = tiles * n_qchunks;
   if (n_items >= (int64_t(1) << 31)) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: too many tiles");
   CUtensorMap map_proto, map_coeff, map_out;
-  if (int rc = make_map_in(&map_proto, proto, false, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, (uint32_t)KP)) return rc;
-  if (int rc = make_map_in(&map_coeff, coeff, false, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QN)) return rc;
+  if (int rc = make_map_in(&map_proto, proto, in_dtype, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, (uint32_t)KP)) return rc;
+  if (int rc = make_map_in(&map_coeff, coeff, in_dtype, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QN)) return rc;
   if (int rc = make_map_out(&map_out, out, sizeof(OT) == 2, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B)) return rc;
   const size_t smem = mask_tc2_smem_bytes(KP, QN, sizeof(OT));
-  if (int rc = ensure_func_attr(mask_fwd_tc2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) return rc;
-  if (int rc = ensure_func_attr(mask_fwd_tc2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) return rc;
+  if (int rc = ensure_func_attr(mask_fwd_tc2_kernel<OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) return rc;
   const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);
   long long* dbg = nullptr;
   if (option("mask_debug")) {
@@ -120,7 +121,7 @@ static int launch_mask_tc2(cudaStream_t st, const void* coeff, const void* proto
   }
   ProfScope prof(st, MSDA_PROF_MASK_FWD, (int64_t)B * Q * Ncols);
   mask_fwd_tc2_kernel<OT><<<grid, kTc2Threads, smem, st>>>(map_proto, map_coeff, map_out, Q, KP, QS, QN, n_qchunks, n_tiles_n,
-                                                          static_cast<int>(n_items), dbg);
+                                                          static_cast<int>(n_items), in_dtype == MSDA_F16 ? 1 : 0, dbg);
   return after_launch("mask_fwd_tc2_kernel");
 }
 
@@ -176,7 +177,7 @@ static int launch_mask_tc4(cudaStream_t st, const void* coeff, const void* proto
   if (kTransB) {
     if (int rc = make_map_mn_f32(&map_rows, coeff, (uint64_t)Q, (uint64_t)K, (uint64_t)B)) return rc;
   } else {
-    if (int rc = make_map_in(&map_rows, coeff, true, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QN)) return rc;
+    if (int rc = make_map_in(&map_rows, coeff, MSDA_F32, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QN)) return rc;
   }
   if (int rc = make_map_out(&map_out, out, sizeof(OT) == 2, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B)) return rc;
   const size_t stage = mask_tc4_stage_bytes(QN, kTransB);
@@ -216,8 +217,9 @@ int mask_forward_dispatch(cudaStream_t st, int in_dtype, int out_dtype, const vo
   if (variant == 2 && !tc_ok && !mask_tc3_eligible(in_dtype, coeff, proto, Q, K, Ncols))
     return fail(MSDA_ERR_UNSUPPORTED, "mask_logits_forward: tcgen05 path needs K %% 8 == 0 with K <= 64 (bf16) / 32 (fp32) and 16-byte aligned rows");
   if (variant != 1 && tc_ok) {
-    if (out_dtype == MSDA_F32) return launch_mask_tc2<float>(st, coeff, proto, out, B, Q, K, Ncols);
-    return launch_mask_tc2<__nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
+    if (out_dtype == MSDA_F32) return launch_mask_tc2<float>(st, in_dtype, coeff, proto, out, B, Q, K, Ncols);
+    if (out_dtype == MSDA_F16) return launch_mask_tc2<__half>(st, in_dtype, coeff, proto, out, B, Q, K, Ncols);
+    return launch_mask_tc2<__nv_bfloat16>(st, in_dtype, coeff, proto, out, B, Q, K, Ncols);
   }
   if (variant != 1 && mask_tc3_eligible(in_dtype, coeff, proto, Q, K, Ncols)) {
     if (out_dtype == MSDA_F32) return launch_mask_tc4<float, false>(st, coeff, proto, out, B, Q, K, Ncols);
@@ -226,6 +228,8 @@ int mask_forward_dispatch(cudaStream_t st, int in_dtype, int out_dtype, const vo
   if (in_dtype == MSDA_F32 && out_dtype == MSDA_F32) return launch_mask_simt<float, float>(st, coeff, proto, out, B, Q, K, Ncols);
   if (in_dtype == MSDA_F32 && out_dtype == MSDA_BF16) return launch_mask_simt<float, __nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
   if (in_dtype == MSDA_BF16 && out_dtype == MSDA_F32) return launch_mask_simt<__nv_bfloat16, float>(st, coeff, proto, out, B, Q, K, Ncols);
+  if (in_dtype == MSDA_F16 && out_dtype == MSDA_F32) return launch_mask_simt<__half, float>(st, coeff, proto, out, B, Q, K, Ncols);
+  if (in_dtype == MSDA_F16) return launch_mask_simt<__half, __half>(st, coeff, proto, out, B, Q, K, Ncols);
   return launch_mask_simt<__nv_bfloat16, __nv_bfloat16>(st, coeff, proto, out, B, Q, K, Ncols);
 }
 
@@ -249,8 +253,8 @@ static int launch_mask_grad_coeff_tc(cudaStream_t st, const void* proto, const v
   const int cps = static_cast<int>((n_chunks + slices - 1) / slices);
   slices = (n_chunks + cps - 1) / cps;
   CUtensorMap map_go, map_proto;
-  if (int rc = make_map_in(&map_go, grad_out, true, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B, 128u)) return rc;
-  if (int rc = make_map_in(&map_proto, proto, true, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, (uint32_t)KP)) return rc;
+  if (int rc = make_map_in(&map_go, grad_out, MSDA_F32, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B, 128u)) return rc;
+  if (int rc = make_map_in(&map_proto, proto, MSDA_F32, (uint64_t)Ncols, (uint64_t)K, (uint64_t)B, (uint32_t)KP)) return rc;
   if (int rc = ensure_func_attr(mask_grad_coeff_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) return rc;
   const dim3 grid(static_cast<unsigned>(slices), static_cast<unsigned>(n_qblocks), static_cast<unsigned>(B));
   long long* dbg = nullptr;
@@ -343,9 +347,9 @@ static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const 
   if (n_items >= (int64_t(1) << 31)) return fail(MSDA_ERR_UNSUPPORTED, "%s: too many tiles", who);
   CUtensorMap map_a, map_b, map_c;
   if (kAMn) { if (int rc = make_map_mn_f32(&map_a, A, (uint64_t)M, (uint64_t)K, 1)) return rc; }
-  else { if (int rc = make_map_in(&map_a, A, true, (uint64_t)K, (uint64_t)M, 1, kG3Tile)) return rc; }
+  else { if (int rc = make_map_in(&map_a, A, MSDA_F32, (uint64_t)K, (uint64_t)M, 1, kG3Tile)) return rc; }
   if (kBMn) { if (int rc = make_map_mn_f32(&map_b, Bm, (uint64_t)N, (uint64_t)K, 1)) return rc; }
-  else { if (int rc = make_map_in(&map_b, Bm, true, (uint64_t)K, (uint64_t)N, 1, kG3Tile)) return rc; }
+  else { if (int rc = make_map_in(&map_b, Bm, MSDA_F32, (uint64_t)K, (uint64_t)N, 1, kG3Tile)) return rc; }
   if (int rc = make_map_c(&map_c, C, (uint64_t)N, (uint64_t)M)) return rc;
   if (int rc = ensure_func_attr(gemm3x_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes)) return rc;
   if (int rc = ensure_func_attr(gemm3x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes)) return rc;

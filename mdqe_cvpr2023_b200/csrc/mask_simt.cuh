@@ -18,12 +18,18 @@ constexpr int kMaskKC = 32;     // k slice held in shared memory
 template <typename T> __device__ __forceinline__ float mk_ld(const T* p);
 template <> __device__ __forceinline__ float mk_ld<float>(const float* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float mk_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ float mk_ld<__half>(const __half* p) { return __half2float(*p); }
 
 __device__ __forceinline__ void mk_st4(float* p, const float (&v)[4]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
 __device__ __forceinline__ void mk_st4(__nv_bfloat16* p, const float (&v)[4]) {
   const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+
+__device__ __forceinline__ void mk_st4(__half* p, const float (&v)[4]) {
+  const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
   *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
 }
 

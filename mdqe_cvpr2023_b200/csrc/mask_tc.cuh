@@ -67,9 +67,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
-// kind::f16 instruction descriptor: D = fp32, A = B = bf16, A MN-major, B K-major, M = 128, N = n.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_m128(uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (0u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 instruction descriptor: D = fp32, A and B both bf16 (format 1) or both fp16 (format 0), A MN-major, B K-major,
+// M = 128, N = n.
+__host__ __device__ constexpr uint32_t umma_idesc_16bit_m128(uint32_t n, bool fp16) {
+  return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10) | (1u << 15) | (0u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -145,6 +146,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void st_stage(float* p, float v) { *p = v; }
 __device__ __forceinline__ void st_stage(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void st_stage(__half* p, float v) { *p = __float2half_rn(v); }
 
 // Work item = (b, 128-column tile, query chunk qc): rows [qc*QS, qc*QS + rows) with QS a multiple of 32 so that the
 // 32-row output boxes of one item never reach into the next item's rows; the last chunk takes the remainder and
@@ -158,7 +160,7 @@ template <typename OT>
 __global__ void __launch_bounds__(kTc2Threads, 1)
 mask_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_constant__ CUtensorMap map_coeff,
                     const __grid_constant__ CUtensorMap map_out, int Q, int KP, int QS, int QN, int n_qchunks,
-                    int n_tiles_n, int n_items, long long* __restrict__ dbg) {
+                    int n_tiles_n, int n_items, int in_fp16, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_half = static_cast<uint32_t>(KP) * 128u;
@@ -220,7 +222,7 @@ mask_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16_m128(static_cast<uint32_t>(QN));
+      const uint32_t idesc = umma_idesc_16bit_m128(static_cast<uint32_t>(QN), in_fp16 != 0);
       int i = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
         const int s = i % kTc2Stages, a = i & 1;

@@ -51,6 +51,7 @@ static std::atomic<int>* find_option(const char* key) {
   if (!strcmp(key, "host_async")) return &g_opt.host_async;
   if (!strcmp(key, "consumer_ctas")) return &g_opt.consumer_ctas;
   if (!strcmp(key, "bwd_merge")) return &g_opt.bwd_merge;
+  if (!strcmp(key, "pdl")) return &g_opt.pdl;
   return nullptr;
 }
 
@@ -364,8 +365,11 @@ int msda_fused_backward_flags(void* stream, int dtype, const void* value, const 
 int mask_logits_forward(void* stream, int in_dtype, int out_dtype, const void* coeff, const void* proto, int B, int Q,
                         int K, int64_t Ncols, void* out) {
   if (B < 0 || Q < 0 || K <= 0 || Ncols < 0) return fail(MSDA_ERR_INVALID_ARG, "mask_logits_forward: bad sizes B=%d Q=%d K=%d Ncols=%lld", B, Q, K, (long long)Ncols);
-  if ((in_dtype != MSDA_F32 && in_dtype != MSDA_BF16) || (out_dtype != MSDA_F32 && out_dtype != MSDA_BF16))
-    return fail(MSDA_ERR_INVALID_ARG, "mask_logits_forward: dtypes must be MSDA_F32 or MSDA_BF16");
+  const bool in_ok = in_dtype == MSDA_F32 || in_dtype == MSDA_BF16 || in_dtype == MSDA_F16;
+  const bool out_ok = out_dtype == MSDA_F32 || (in_dtype == MSDA_F32 ? out_dtype == MSDA_BF16 : out_dtype == in_dtype);
+  if (!in_ok || !out_ok)
+    return fail(MSDA_ERR_INVALID_ARG, "mask_logits_forward: in_dtype must be MSDA_F32 / MSDA_BF16 / MSDA_F16 and out_dtype MSDA_F32 or "
+                "the inputs' 16-bit type (fp32 inputs: MSDA_F32 or MSDA_BF16); got %d -> %d", in_dtype, out_dtype);
   if ((int64_t)B * Q * Ncols == 0) return 0;
   if (!coeff || !proto || !out) return fail(MSDA_ERR_INVALID_ARG, "mask_logits_forward: NULL tensor");
   return mask_forward_dispatch(static_cast<cudaStream_t>(stream), in_dtype, out_dtype, coeff, proto, B, Q, K, Ncols, out);

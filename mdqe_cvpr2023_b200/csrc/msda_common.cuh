@@ -7,6 +7,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -33,6 +34,7 @@ __device__ __forceinline__ double ld_as_float(const double* p) { return __ldg(p)
 
 __device__ __forceinline__ void st_from_float(float* p, float v) { *p = v; }
 __device__ __forceinline__ void st_from_float(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void st_from_float(__half* p, float v) { *p = __float2half_rn(v); }
 __device__ __forceinline__ void st_from_float(double* p, double v) { *p = v; }
 
 // 16-byte channel vector of the value tensor -> fp32 registers.
@@ -88,6 +90,12 @@ __device__ __forceinline__ bool level_fits(int64_t H, int64_t W, int64_t start, 
   return H >= 0 && W >= 0 && start >= 0 && H <= 0x7fffffff && W <= 0x7fffffff && H * W <= static_cast<int64_t>(S) &&
          start <= static_cast<int64_t>(S) - H * W;
 }
+
+// Programmatic dependent launch (see launch_kernel in msda_launch.cuh).  pdl_wait(): blocks until the kernel this one was
+// serialised behind has completed and its writes are visible (a no-op for a normal launch) -- must precede every global
+// memory access.  pdl_trigger(): lets the NEXT kernel's CTAs be scheduled once every CTA of this grid has passed this point.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Stage the per-level geometry (int64 on device in the reference API) into shared memory.
 __device__ __forceinline__ void stage_levels(LevelInfo* s_lvl, const int64_t* __restrict__ shapes,

@@ -223,6 +223,8 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
   __shared__ LevelInfo s_lvl[kMaxLevels];
   __shared__ __align__(16) Slot s_slot[kWarpsPerCta][C::QPW * C::NSLOT];
 
+  pdl_wait();
+  pdl_trigger();
   stage_levels(s_lvl, shapes, level_start, G * L, S);
   __syncthreads();
   MSDA_DBG_LOAD
@@ -423,6 +425,8 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
   __shared__ __align__(16) Slot s_slot[kWarpsPerCta][C::QPW * C::NSLOT];
   __shared__ float s_dot[kWarpsPerCta][4 * kDotStride];
 
+  pdl_wait();
+  pdl_trigger();
   stage_levels(s_lvl, shapes, level_start, G * L, S);
   __syncthreads();
   MSDA_DBG_LOAD

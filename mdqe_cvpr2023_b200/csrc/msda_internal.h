@@ -39,6 +39,7 @@ struct Options {
   std::atomic<int> host_async{0};     // 1 = the *_host entries only enqueue; msda_host_sync() completes them
   std::atomic<int> profile{0};        // 1 = bracket the main kernels with CUDA events (msda_profile_read)
   std::atomic<int> consumer_ctas{0};  // > 0: CTAs of the matcher-cost / IoU kernels (tuning; 0 = auto)
+  std::atomic<int> pdl{1};            // 1 = launch the sampling kernels with programmatic stream serialization (see msda_launch.cuh)
   std::atomic<int> bwd_merge{1};      // 1 = merge grad_value reductions of a (pair, level) that hit the same row (P = 2 or 4); 0 = off (A/B)
 };
 const Options& options();
@@ -78,6 +79,7 @@ inline size_t dtype_size(int dtype) {
     case MSDA_BF16: return 2;
     case MSDA_F64: return 8;
     case MSDA_BF16_LOC32: return 2;
+    case MSDA_F16: return 2;              // mask contraction only
     default: return 0;
   }
 }

@@ -148,7 +148,17 @@ class _MaskLogitsFunction(Function):
 
 def mask_logits(coeff, proto):
     """Drop-in for ``torch.einsum('bqm,bmthw->bqthw', coeff, proto)`` (also accepts the unbatched
-    'qm,mthw->qthw' form of mdqe/mdqe.py:384)."""
+    'qm,mthw->qthw' form of mdqe/mdqe.py:384).
+
+    Dtypes follow the einsum it replaces.  Under ``torch.autocast`` -- how the reference evaluates (train_net.py:207-208; neither
+    Transformer_Dec.forward nor inference_clip disables it, so mdqe/mdqe.py:384 and transformer_dec.py:255 run in fp16) -- both
+    operands are cast to the autocast dtype and the result has that dtype; outside autocast float32, bfloat16 and float16
+    operands of one common dtype give a result of that dtype (mixed dtypes raise, like einsum)."""
+    if torch.is_autocast_enabled("cuda") and coeff.is_cuda:
+        dt = torch.get_autocast_dtype("cuda")
+        coeff, proto = coeff.to(dt), proto.to(dt)
+        with torch.autocast("cuda", enabled=False):
+            return mask_logits(coeff, proto)
     if coeff.dim() == 2:
         return _MaskLogitsFunction.apply(coeff.unsqueeze(0).contiguous(), proto.unsqueeze(0).contiguous()).squeeze(0)
     return _MaskLogitsFunction.apply(coeff.contiguous(), proto.contiguous())

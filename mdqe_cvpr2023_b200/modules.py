@@ -61,6 +61,7 @@ class MSDeformAttn(nn.Module):
         # {32,24}, L*P in {8,16}, reference points without gradient); set False to run the reference's op sequence
         self.fused_prologue = True
         self.tc_linear = True
+        self.check_shapes = False          # True: assert sum(H_l * W_l) == S like the reference (one host sync per call)
 
         # what the operator sees as "levels": pyramid levels of a frame, or the frames of a clip
         if mode == 'spatial':
@@ -153,9 +154,11 @@ class MSDeformAttn(nn.Module):
     @staticmethod
     def _geometry(spatial_shapes, n_frames=0, rows_per_frame=0):
         """level_start_index and (temporal mode) the [G,T,2] / [G,T] level tables, computed on the device without a host
-        sync (the reference's shape assert, ms_deform_attn.py:134, costs one sync per call; a mismatch here surfaces as
-        out-of-range level starts instead).  Not cached: callers rebuild `spatial_shapes` every forward
-        (transformer_enc.py:46) and multi-scale training changes its contents."""
+        sync.  The reference asserts sum(H_l*W_l) == S on the host (ms_deform_attn.py:134: one sync per call); here the kernels
+        check every level window against the S rows they may touch and disable a level that does not fit
+        (csrc/msda_common.cuh level_fits) -- a mismatch gives zeros for that level, never an out-of-bounds access.  Set
+        MSDeformAttn.check_shapes = True to get the reference's assertion (and its sync) back.  Not cached: callers rebuild
+        `spatial_shapes` every forward (transformer_enc.py:46) and multi-scale training changes its contents."""
         sizes = spatial_shapes.prod(-1)
         starts = torch.cat([sizes.new_zeros(1), sizes.cumsum(0)[:-1]]).long()
         shapes_c = spatial_shapes.contiguous()
@@ -178,9 +181,11 @@ class MSDeformAttn(nn.Module):
     @torch.amp.autocast("cuda", enabled=False)
     def spatial_forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_padding_mask=None):
         """query BxQxC, reference_points BxQx4 (cx, cy, w, h), input_flatten BxSxC with S = sum_l H_l*W_l."""
+        if self.check_shapes:
+            assert int(input_spatial_shapes.prod(-1).sum()) == input_flatten.shape[1], "spatial_shapes do not add up to the rows of input_flatten"
         level_start, shapes_c, _, _ = self._geometry(input_spatial_shapes)
         value = self._project_value(input_flatten, input_padding_mask).contiguous()  # B S H D
-        if self.fused_prologue and ops.fused_supported(value, reference_points, 1, self.lvl, self.n_points):
+        if self.fused_prologue and ops.fused_supported(value, reference_points, 1, self.lvl, self.n_points, query.shape[1]):
             offsets, logits, grid, mode = self._fused_inputs(query)
             sampled = MSDeformAttnFusedFunction.apply(value, shapes_c, level_start,
                                                       reference_points.contiguous(), offsets, logits, grid, mode, self.scale, 1.0)
@@ -196,11 +201,13 @@ class MSDeformAttn(nn.Module):
         """query BxQxC, reference_points BxQx4, input_flatten BxTxSxC; the T frames play the role of levels."""
         B, T, S, _ = input_flatten.shape
         assert T == self.n_frames, f"temporal MSDeformAttn built for {self.n_frames} frames, got {T}"
+        if self.check_shapes:
+            assert int(input_spatial_shapes.prod(-1).sum()) == S, "spatial_shapes do not add up to the rows of input_flatten"
         level_start, _, shapes_g, starts_g = self._geometry(input_spatial_shapes, T, S)
         value = self._project_value(input_flatten, input_padding_mask)               # B T S H D
         value = value.contiguous().view(B, T * S, self.n_heads, -1)                  # frames back to back, no copies
         n_lvl = input_spatial_shapes.shape[0]
-        if self.fused_prologue and ops.fused_supported(value, reference_points, n_lvl, T, self.n_points):
+        if self.fused_prologue and ops.fused_supported(value, reference_points, n_lvl, T, self.n_points, query.shape[1]):
             # one launch: all pyramid levels (grouped form) + softmax / location arithmetic inside the kernel
             offsets, logits, grid, mode = self._fused_inputs(query)
             sampled = MSDeformAttnFusedFunction.apply(value, shapes_g, starts_g, reference_points.contiguous(), offsets, logits,
@@ -208,7 +215,7 @@ class MSDeformAttn(nn.Module):
             return self._linear(self.output_proj, sampled)
         locations, weights = self._sampling(query, reference_points)
         locations, weights = locations.contiguous(), weights.contiguous()
-        if ops.grouped_supported(value, n_lvl, T, self.n_points):
+        if ops.grouped_supported(value, n_lvl, T, self.n_points, query.shape[1], locations, weights):
             # all pyramid levels in ONE launch: level table g = the T frames of pyramid level g, mean folded in
             sampled = MSDeformAttnGroupedFunction.apply(value, shapes_g, starts_g, locations, weights, 1.0 / n_lvl)
             return self._linear(self.output_proj, sampled)

@@ -134,10 +134,21 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     return [grad_value, grad_loc, grad_aw]
 
 
-def grouped_supported(value, n_groups, n_levels, n_points):
-    """True when msda_forward_grouped / msda_backward_grouped implement this configuration (fast kernels only)."""
+def _fast_kernel_limits(value, n_queries, *others):
+    """the conditions csrc/msda_launch.cuh (fast_eligible) puts on the fast kernels besides the shape family: 32-bit row
+    offsets and pair indices, 16-byte aligned tensors"""
+    if value.numel() >= 2 ** 31 or value.data_ptr() % 16:
+        return False
+    if n_queries is not None and value.shape[0] * n_queries * value.shape[2] >= 2 ** 31 // 64:
+        return False
+    return all(t is None or t.data_ptr() % 16 == 0 for t in others)
+
+
+def grouped_supported(value, n_groups, n_levels, n_points, n_queries=None, *others):
+    """True when msda_forward_grouped / msda_backward_grouped implement this configuration (fast kernels only);
+    mirrors grouped_supported() / fast_eligible() of the library so that callers can fall back instead of failing."""
     return (value.is_cuda and value.dim() == 4 and value.shape[3] in (32, 24) and value.dtype in (torch.float32, torch.bfloat16)
-            and n_levels * n_points in (8, 12, 16) and n_groups * n_levels <= 32 and value.numel() < 2 ** 31)
+            and n_levels * n_points in (8, 12, 16) and n_groups * n_levels <= 32 and _fast_kernel_limits(value, n_queries, *others))
 
 
 def _grouped_dims(value, shapes, level_start, loc, aw, who):
@@ -194,12 +205,12 @@ def ms_deform_attn_grouped_backward(value, spatial_shapes, level_start_index, sa
     return [grad_value, grad_loc, grad_aw]
 
 
-def fused_supported(value, reference_points, n_groups, n_levels, n_points):
+def fused_supported(value, reference_points, n_groups, n_levels, n_points, n_queries=None, *others):
     """True when msda_fused_forward / msda_fused_backward implement this configuration."""
     return (value.is_cuda and value.dim() == 4 and value.dtype == torch.float32 and value.shape[3] in (32, 24)
-            and n_levels * n_points in (8, 16) and n_groups * n_levels <= 32 and value.numel() < 2 ** 31
+            and n_levels * n_points in (8, 16) and n_groups * n_levels <= 32
             and reference_points.dtype == torch.float32 and reference_points.shape[-1] in (2, 4)
-            and not reference_points.requires_grad)
+            and not reference_points.requires_grad and _fast_kernel_limits(value, n_queries, reference_points, *others))
 
 
 def _fused_dims(value, shapes, level_start, ref, offsets, logits, grid, mode, who):
@@ -265,7 +276,7 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, refe
     return grad_value, grad_offsets, grad_logits
 
 
-_MASK_CODES = {torch.float32: _lib.MSDA_F32, torch.bfloat16: _lib.MSDA_BF16}
+_MASK_CODES = {torch.float32: _lib.MSDA_F32, torch.bfloat16: _lib.MSDA_BF16, torch.float16: _lib.MSDA_F16}
 
 
 def mask_logits_forward(coeff, proto, out_dtype=None):
@@ -275,8 +286,10 @@ def mask_logits_forward(coeff, proto, out_dtype=None):
     if coeff.dim() != 3 or proto.dim() < 3 or proto.shape[0] != coeff.shape[0] or proto.shape[1] != coeff.shape[2]:
         raise RuntimeError(f"{who}: expected coeff[B,Q,K] and proto[B,K,...], got {tuple(coeff.shape)} {tuple(proto.shape)}")
     if coeff.dtype != proto.dtype or coeff.dtype not in _MASK_CODES:
-        raise RuntimeError(f"{who}: coeff/proto must both be float32 or bfloat16")
+        raise RuntimeError(f"{who}: coeff/proto must both be float32, bfloat16 or float16")
     out_dtype = out_dtype or coeff.dtype
+    if out_dtype not in _MASK_CODES:
+        raise RuntimeError(f"{who}: unsupported out_dtype {out_dtype}")
     B, Q, K = coeff.shape
     plane = tuple(proto.shape[2:])
     ncols = 1
@@ -292,8 +305,14 @@ def mask_logits_forward(coeff, proto, out_dtype=None):
 
 
 def mask_logits_backward(coeff, proto, grad_out, need_coeff=True, need_proto=True):
+    """(grad_coeff, grad_proto) of mask_logits_forward.  The kernels are fp32 (the reference trains the mask head in fp32, AMP
+    disabled: configs/R50_coco.yaml:41-42); 16-bit operands -- only met when a caller trains under autocast -- are widened,
+    differentiated in fp32 and the gradients rounded back to the operand dtype."""
     who = "mask_logits_backward"
     _check_inputs(who, [("coeff", coeff), ("proto", proto), ("grad_out", grad_out)])
+    if coeff.dtype != torch.float32:
+        gc, gp = mask_logits_backward(coeff.float(), proto.float(), grad_out.float().contiguous(), need_coeff, need_proto)
+        return (gc.to(coeff.dtype) if gc is not None else None), (gp.to(proto.dtype) if gp is not None else None)
     B, Q, K = coeff.shape
     ncols = proto.numel() // max(1, B * K)
     lib = _lib.load()
@@ -309,9 +328,11 @@ def mask_logits_backward(coeff, proto, grad_out, need_coeff=True, need_proto=Tru
 
 
 def linear_supported(x, weight):
-    """The tensor-core Linear needs fp32 CUDA tensors with in/out features that are multiples of 4."""
+    """The tensor-core Linear needs fp32 CUDA tensors with in/out features that are multiples of 4, 16-byte aligned, and
+    fewer than 2^31 - 128 rows (linear_forward_dispatch in csrc/mask_gemm.cu)."""
     return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and weight.dim() == 2
-            and weight.shape[0] % 4 == 0 and weight.shape[1] % 4 == 0 and x.shape[-1] == weight.shape[1])
+            and weight.shape[0] % 4 == 0 and weight.shape[1] % 4 == 0 and x.shape[-1] == weight.shape[1]
+            and x.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0 and x.numel() // max(weight.shape[1], 1) < 2 ** 31 - 128)
 
 
 def tc_linear_forward(x, weight, bias=None, row_mask=None):

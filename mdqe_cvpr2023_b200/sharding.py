@@ -53,24 +53,34 @@ def gather_clip_outputs(local, n_items, group=None):
 def allreduce_mean_gradients(parameters, group=None, bucket_bytes=64 << 20):
     """Average .grad over the ranks in flat buckets (what DDP does; for loops that do not wrap the model in
     DistributedDataParallel).  Buckets are sized for launch latency, not for link count: NVSwitch gives
-    every GPU full bandwidth to every peer."""
+    every GPU full bandwidth to every peer.
+
+    Every rank must issue the same collectives on the same sizes, so the buckets are built from ALL parameters that require
+    a gradient, in the order given, whether or not this rank produced one: a parameter unused on this rank (e.g.
+    `sampling_grid_offsets` when a clip has no matched instance) contributes zeros and receives the mean of the other ranks'
+    gradients as its `.grad`.  Buckets never mix dtypes (torch.cat would promote and the copy back would truncate)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 0
     world = dist.get_world_size(group)
-    grads = [p.grad for p in parameters if p.grad is not None]
+    params = [p for p in parameters if p.requires_grad]
     n_buckets, i = 0, 0
-    while i < len(grads):
-        bucket, size = [], 0
-        while i < len(grads) and (not bucket or size + grads[i].numel() * grads[i].element_size() <= bucket_bytes):
-            bucket.append(grads[i])
-            size += grads[i].numel() * grads[i].element_size()
+    while i < len(params):
+        bucket, size, dtype = [], 0, params[i].dtype
+        while i < len(params) and params[i].dtype == dtype and \
+                (not bucket or size + params[i].numel() * params[i].element_size() <= bucket_bytes):
+            bucket.append(params[i])
+            size += params[i].numel() * params[i].element_size()
             i += 1
-        flat = torch.cat([g.reshape(-1) for g in bucket])
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
         dist.all_reduce(flat, group=group)
         flat.div_(world)
         off = 0
-        for g in bucket:
-            g.copy_(flat[off: off + g.numel()].view_as(g))
-            off += g.numel()
+        for p in bucket:
+            piece = flat[off: off + p.numel()].view_as(p)
+            if p.grad is None:
+                p.grad = piece.clone()
+            else:
+                p.grad.copy_(piece)
+            off += p.numel()
         n_buckets += 1
     return n_buckets

@@ -52,6 +52,54 @@ def test_mask_sweep_vs_einsum(Q, T, plane, K, variant):
     assert nerr(out_mixed.float(), want) < 2e-2
 
 
+CONFIG5 = [(Q, T, plane, K) for Q in (100, 196, 300) for T in (2, 4, 8) for plane in ((96, 160), (160, 288)) for K in (32, 24)
+           if not (T == 8 and plane == (160, 288) and Q == 300)] + [(300, 8, (160, 288), 32)]
+
+
+@pytest.mark.parametrize("Q,T,plane,K", CONFIG5[::3] + [(7, 1, (5, 9), 32), (130, 2, (33, 17), 40), (64, 2, (12, 20), 20)])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_mask_fp16_vs_fp16_einsum(Q, T, plane, K, variant):
+    """The reference's evaluation dtype (autocast: train_net.py:207-208 -> mdqe/mdqe.py:384 runs in fp16): fp16 operands,
+    fp16 result, against torch.einsum on the same fp16 tensors (<= 2e-2) and against the exact product of the rounded
+    operands; BASELINE config 5 sweep (every third point) plus odd sizes that take the SIMT kernel."""
+    from mdqe_cvpr2023_b200 import _lib, ops
+    _lib.set_option("mask_variant", variant)
+    g = torch.Generator(device="cuda").manual_seed(Q * 7 + T)
+    coeff = torch.tanh(torch.randn(1, Q, K, device="cuda", generator=g)).half()
+    proto = torch.randn(1, K, T, *plane, device="cuda", generator=g).half()
+    out = ops.mask_logits_forward(coeff, proto)
+    assert out.dtype == torch.float16 and tuple(out.shape) == (1, Q, T) + plane
+    ref16 = torch.einsum("bqm,bmthw->bqthw", coeff, proto)
+    exact = torch.einsum("bqm,bmthw->bqthw", coeff.double(), proto.double())
+    assert nerr(out.float(), ref16.float()) < 2e-2
+    assert nerr(out.float(), exact) < 2e-3                                     # fp32 accumulation, one rounding to fp16
+    out32 = ops.mask_logits_forward(coeff, proto, out_dtype=torch.float32)
+    assert out32.dtype == torch.float32 and nerr(out32, exact) < 1e-5
+    with pytest.raises(RuntimeError):
+        ops.mask_logits_forward(coeff, proto, out_dtype=torch.bfloat16)
+
+
+def test_mask_logits_under_autocast_matches_einsum_semantics():
+    """`mask_logits` is a drop-in for the einsum at the reference's call sites under the reference's own eval setting."""
+    from mdqe_cvpr2023_b200 import mask_logits
+    g = torch.Generator(device="cuda").manual_seed(5)
+    coeff = torch.tanh(torch.randn(2, 196, 32, device="cuda", generator=g)).requires_grad_(True)
+    proto = torch.randn(2, 32, 4, 24, 40, device="cuda", generator=g).requires_grad_(True)
+    for dt in (torch.float16, torch.bfloat16):
+        with torch.autocast("cuda", dtype=dt):
+            want = torch.einsum("bqm,bmthw->bqthw", coeff, proto)
+            got = mask_logits(coeff, proto)
+            got1 = mask_logits(coeff[0], proto[0])                              # the unbatched form of mdqe/mdqe.py:384
+        assert got.dtype == want.dtype == dt and got1.dtype == dt
+        assert nerr(got.float(), want.float()) < 2e-2 and nerr(got1.float(), want[0].float()) < 2e-2
+        gw = torch.autograd.grad(want.float().sum(), (coeff, proto), retain_graph=True)
+        gg = torch.autograd.grad(got.float().sum(), (coeff, proto))
+        for a, b in zip(gg, gw):
+            assert a.dtype == b.dtype == torch.float32 and nerr(a, b) < 2e-2
+    out = mask_logits(coeff, proto)                                             # outside autocast: fp32 as before
+    assert out.dtype == torch.float32 and nerr(out, torch.einsum("bqm,bmthw->bqthw", coeff.double(), proto.double())) < 2e-5
+
+
 def test_mask_unbatched_form_and_empty():
     from mdqe_cvpr2023_b200 import mask_logits, ops
     coeff = torch.randn(5, 32, device="cuda")

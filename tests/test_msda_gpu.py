@@ -211,9 +211,9 @@ def test_error_behaviour_matches_reference():
         ops.ms_deform_attn_forward(inp["value"].half(), inp["shapes"], inp["level_start"], inp["loc"], inp["aw"], 64)
 
 
-@pytest.mark.parametrize("D", [30, 32, 64, 71, 1025])
+@pytest.mark.parametrize("D", [30, 32, 64, 71, 1025, 2048, 3096])
 def test_gradcheck_double_reference_sweep(D):
-    """ops/test.py:63-86 check_gradient_numerical on the reference fixture (D list minus the two largest)."""
+    """ops/test.py:63-86 check_gradient_numerical on the reference fixture, the reference's full channel list (:85-86)."""
     from mdqe_cvpr2023_b200 import MSDeformAttnFunction
     N, M, Lq, L, P = 1, 2, 2, 2, 2
     shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long).cuda()
@@ -239,6 +239,123 @@ def test_autograd_function_and_autocast():
     out2 = MSDeformAttnFunction.apply(v, d["shapes"], d["level_start"], l, a, 64)
     out2.backward(d["grad_out"])
     check((out2, v.grad, l.grad, a.grad), want, 2e-5, "autograd", inp)
+
+
+@pytest.mark.parametrize("name,N,pyr,D", [("R50_ovis_360", 4, R50_360, 32), ("R50_ovis_720", 4, R50_720, 32), ("swinl_ytvis21", 3, R50_360, 24)])
+@pytest.mark.parametrize("dist", ["local", "uniform"])
+def test_full_size_fp32_vs_oracle(name, N, pyr, D, dist):
+    """The encoder call of every BASELINE.json configuration at its full size (the batch, grid and FastDiv path bench.py runs),
+    all four results against the C oracle (OpenMP: well under a second per case)."""
+    inp = make_inputs(N, pyr, 8, D, 4, dist=dist, seed=41)
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"{name} N{N} {dist}", inp)
+
+
+@pytest.mark.parametrize("name,N,pyr,D", [("R50_ovis_360", 4, R50_360, 32), ("R50_ovis_720", 4, R50_720, 32), ("swinl_ytvis21", 3, R50_360, 24)])
+@pytest.mark.parametrize("loc_dtype", [torch.bfloat16, torch.float32])
+def test_full_size_bf16_vs_oracle(name, N, pyr, D, loc_dtype):
+    """bf16 storage at the BASELINE shapes: inputs rounded to bf16, oracle in fp32 on the rounded values, <= 2e-2 (north_star)."""
+    inp = make_inputs(N, pyr, 8, D, 4, dist="local", seed=42)
+    for k in ("value", "grad_out"):
+        inp[k] = inp[k].to(torch.bfloat16)
+    for k in ("loc", "aw"):
+        inp[k] = inp[k].to(loc_dtype)
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-2, f"bf16 {name} loc={loc_dtype}", inp,
+          max_kink=0.05 if loc_dtype == torch.bfloat16 else 2e-3)
+
+
+def test_level_table_that_does_not_fit_is_disabled_not_dereferenced():
+    """spatial_shapes / level_start_index that reach past the S rows of `value` (the mismatch the reference asserts on the host,
+    ms_deform_attn.py:134): that level contributes nothing and nothing is written out of bounds -- value and grad_value sit in
+    the middle of a guarded allocation whose guard words must survive."""
+    from mdqe_cvpr2023_b200 import ops
+    inp = make_inputs(2, [(12, 20), (6, 10)], 8, 32, 4, Lq=64, dist="wide", seed=43)
+    good = oracle_all(dict(inp, aw=torch.cat([inp["aw"][:, :, :, :1], torch.zeros_like(inp["aw"][:, :, :, 1:])], 3)))
+    d = to_cuda(inp)
+    bad_shapes = d["shapes"].clone()
+    bad_shapes[1] = torch.tensor([60, 100], device="cuda")                # 6000 rows from row 240 of a 300-row tensor
+    for variant in (0, 1):                                                  # fast and generic kernels
+        from mdqe_cvpr2023_b200 import _lib
+        _lib.set_option("fwd_variant", variant)
+        _lib.set_option("bwd_variant", variant)
+        out = ops.ms_deform_attn_forward(d["value"], bad_shapes, d["level_start"], d["loc"], d["aw"], 64)
+        gv, gl, ga = ops.ms_deform_attn_backward(d["value"], bad_shapes, d["level_start"], d["loc"], d["aw"], d["grad_out"], 64)
+        torch.cuda.synchronize()
+        assert nerr(out, good[0]) < 2e-5 and nerr(gv, good[1]) < 2e-5
+        assert float(gl[:, :, :, 1:].abs().max()) == 0 and float(ga[:, :, :, 1:].abs().max()) == 0
+        assert nerr(gl[:, :, :, :1], np.asarray(good[2])[:, :, :, :1]) < 2e-5
+        # a start that lies outside, and a negative one
+        for start in (10 ** 6, -5):
+            ls = d["level_start"].clone()
+            ls[1] = start
+            out2 = ops.ms_deform_attn_forward(d["value"], d["shapes"], ls, d["loc"], d["aw"], 64)
+            assert nerr(out2, good[0]) < 2e-5
+    _lib.set_option("fwd_variant", 0)
+    _lib.set_option("bwd_variant", 0)
+
+
+def test_prezeroed_accumulator_paths():
+    """MSDA_BWD_ACC_ZEROED: the Function zero-fills grad_value's accumulator on a side stream during the forward; results equal
+    the in-call zero-fill, the accumulator is consumed once (second backward falls back), bf16 uses the fp32 workspace."""
+    from mdqe_cvpr2023_b200 import MSDeformAttnFunction, functions, ops
+    inp = make_inputs(2, R50_360, 8, 32, 4, Lq=300, dist="local", seed=44)
+    want = oracle_all(inp)
+    d = to_cuda(inp)
+    res = {}
+    for pre in (True, False):
+        functions.PREZERO_GRAD_VALUE = pre
+        v, l, a = (d[k].clone().requires_grad_(True) for k in ("value", "loc", "aw"))
+        out = MSDeformAttnFunction.apply(v, d["shapes"], d["level_start"], l, a, 64)
+        out.backward(d["grad_out"], retain_graph=True)
+        check((out, v.grad, l.grad, a.grad), want, 2e-5, f"prezero={pre}", inp)
+        first = v.grad.clone()
+        v.grad = None
+        out.backward(d["grad_out"])                                          # the accumulator was consumed: regular path
+        assert nerr(v.grad, first) < 1e-5
+        res[pre] = first
+    functions.PREZERO_GRAD_VALUE = True
+    assert nerr(res[True], res[False]) < 1e-5
+    # explicit accumulator through the tensor-level entry, bf16 (accumulator = fp32 workspace)
+    b = {k: (t.bfloat16() if t.is_floating_point() else t) for k, t in d.items()}
+    acc = ops.new_backward_accumulator(b["value"])
+    assert acc.dtype == torch.float32
+    got = ops.ms_deform_attn_backward(b["value"], b["shapes"], b["level_start"], b["loc"], b["aw"], b["grad_out"], 64, accumulator=acc)
+    ref = ops.ms_deform_attn_backward(b["value"], b["shapes"], b["level_start"], b["loc"], b["aw"], b["grad_out"], 64)
+    assert nerr(got[0].float(), ref[0].float()) < 1e-2 and torch.equal(got[1], ref[1])
+    with pytest.raises(RuntimeError, match="accumulator"):
+        ops.ms_deform_attn_backward(d["value"], d["shapes"], d["level_start"], d["loc"], d["aw"], d["grad_out"], 64,
+                                    accumulator=torch.zeros(3, device="cuda"))
+
+
+def test_function_under_cuda_graph_capture_with_side_stream_fill():
+    """whole forward+backward of the Function captured into one CUDA graph (the side-stream zero-fill forks and joins inside
+    the capture) and replayed on new input values"""
+    from mdqe_cvpr2023_b200 import MSDeformAttnFunction
+    inp = make_inputs(2, R50_360, 8, 32, 4, Lq=196, dist="local", seed=45)
+    d = to_cuda(inp)
+    v, l, a = (d[k].clone().requires_grad_(True) for k in ("value", "loc", "aw"))
+
+    def step():
+        out = MSDeformAttnFunction.apply(v, d["shapes"], d["level_start"], l, a, 64)
+        return (out,) + torch.autograd.grad(out, (v, l, a), d["grad_out"])
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        res = step()
+    inp2 = make_inputs(2, R50_360, 8, 32, 4, Lq=196, dist="local", seed=46)
+    with torch.no_grad():
+        v.copy_(inp2["value"]); l.copy_(inp2["loc"]); a.copy_(inp2["aw"])
+    d["grad_out"].copy_(inp2["grad_out"])
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    check(res, oracle_all(inp2), 2e-5, "graph replay", inp2)
 
 
 def test_full_size_properties_r50_720():

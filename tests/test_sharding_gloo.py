@@ -71,6 +71,23 @@ def _worker(rank, world, port, q):
         ((mod(x[b:e], ref[b:e], x[b:e], shapes) - tgt[b:e]) ** 2).sum().backward()
         nb = allreduce_mean_gradients(list(mod.parameters()), bucket_bytes=4096)
         helper = {k: p.grad.clone() for k, p in mod.named_parameters()}
+        # (b') a parameter that only rank 0 used (and of another dtype): same collectives on every rank, no hang, and the
+        # ranks that had no gradient receive the mean
+        extra = torch.nn.Linear(4, 3).double()
+        with torch.no_grad():
+            for j, p in enumerate(extra.parameters()):
+                p.copy_(torch.arange(p.numel(), dtype=torch.float64).view_as(p) * 0.1 + j)
+        xin = torch.arange(8.0, dtype=torch.float64).view(2, 4)
+        g0 = torch.autograd.grad((extra(xin) ** 2).sum(), list(extra.parameters()))
+        if rank == 0:
+            (extra(xin) ** 2).sum().backward()
+        mod.zero_grad()
+        ((mod(x[b:e], ref[b:e], x[b:e], shapes) - tgt[b:e]) ** 2).sum().backward()
+        allreduce_mean_gradients(list(extra.parameters()) + list(mod.parameters()), bucket_bytes=4096)
+        for p_, g_ in zip(extra.parameters(), g0):
+            assert p_.grad is not None and p_.grad.dtype == torch.float64 and torch.allclose(p_.grad, g_ / world), "unused-parameter bucket"
+        for k, p_ in mod.named_parameters():
+            assert torch.allclose(p_.grad, helper[k], atol=1e-6), k
         # (c) training under DistributedDataParallel (equal shard sizes needed: use the first 4 clips)
         b4, e4 = shard_bounds(4, rank, world)
         ddp = torch.nn.parallel.DistributedDataParallel(mod)
