@@ -51,6 +51,7 @@ static std::atomic<int>* find_option(const char* key) {
   if (!strcmp(key, "host_async")) return &g_opt.host_async;
   if (!strcmp(key, "consumer_ctas")) return &g_opt.consumer_ctas;
   if (!strcmp(key, "bwd_merge")) return &g_opt.bwd_merge;
+  if (!strcmp(key, "pair_map")) return &g_opt.pair_map;
   if (!strcmp(key, "pdl")) return &g_opt.pdl;
   return nullptr;
 }

@@ -37,6 +37,31 @@ __device__ __forceinline__ uint32_t fd_div(uint32_t x, const FastDiv f) {
   return f.d == 1 ? x : (__umulhi(x, f.mul) >> f.shr);
 }
 
+// Which pairs a CTA walks, and in which order.  Linear (hrun = 0): CTA b owns pairs [b * chunk, (b + 1) * chunk) of the
+// flattened (n, q, m) index, i.e. chunk / M consecutive queries with all their heads.  Head-run (hrun = 1): CTA b owns ONE head
+// m = b % M of `chunk` consecutive queries; its warps then sweep neighbouring queries of the same head together, so the corner
+// rows they gather (same head => same 128-byte lines when the samples land in the same cells) are reused out of L1 while they
+// are still there.  `begin`/`end` delimit the CTA's virtual pair indices, pair(v) maps one to the flattened pair index.
+struct PairMap {
+  uint32_t begin, end, base, stride, head;
+  __device__ __forceinline__ PairMap(int hrun, uint32_t block, int chunk_pairs, uint32_t n_pairs, const FastDiv div_m) {
+    if (hrun) {
+      const uint32_t run = fd_div(block, div_m);
+      head = block - run * div_m.d;
+      base = run * static_cast<uint32_t>(chunk_pairs);
+      stride = div_m.d;
+      begin = 0;
+      const uint32_t nq_total = fd_div(n_pairs, div_m);
+      end = min(static_cast<uint32_t>(chunk_pairs), nq_total - base);
+    } else {
+      begin = block * static_cast<uint32_t>(chunk_pairs);
+      end = min(n_pairs, begin + static_cast<uint32_t>(chunk_pairs));
+      base = 0; stride = 1; head = 0;
+    }
+  }
+  __device__ __forceinline__ uint32_t pair(uint32_t v) const { return (base + v) * stride + head; }
+};
+
 // Fused sampler prologue (ms_deform_attn.py:142-161 folded into the kernel): instead of ready-made
 // sampling locations and softmax-normalised weights the kernel gets what the module's Linear layers produce --
 // raw offsets (in the `loc` slot) and raw attention logits (in the `aw` slot) -- plus the reference points, and does
@@ -217,7 +242,7 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
                       const int64_t* __restrict__ level_start, const LT* __restrict__ loc,
                       const LT* __restrict__ aw, VT* __restrict__ out,
                       int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq,
-                      int G, float scale, FusedArgs fz) {
+                      int G, float scale, FusedArgs fz, int hrun) {
   // G > 1: "grouped" (temporal) form -- G level tables share loc/aw, out = scale * sum_g (see msda_forward_grouped)
   using C = Cfg2<VT, D, LP>;
   __shared__ LevelInfo s_lvl[kMaxLevels];
@@ -238,8 +263,8 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
   const Slot* my_stream = my_slots + corner * C::LPP + sgrp * C::SPG;
   const VT* vlane = value + c * C::CPL;
 
-  const uint32_t chunk_begin = blockIdx.x * static_cast<uint32_t>(chunk_pairs);
-  const uint32_t chunk_end = min(n_pairs, chunk_begin + static_cast<uint32_t>(chunk_pairs));
+  const PairMap pm(hrun, blockIdx.x, chunk_pairs, n_pairs, div_m);
+  const uint32_t chunk_begin = pm.begin, chunk_end = pm.end;
   const int ps = (lane < C::QPW * LP) ? lane / LP : 0;        // phase-1 role: pair slot and sample of this lane
   const int ss = lane - ps * LP;
   const int lvl = ss / P;
@@ -250,11 +275,11 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
     float x = 0.f, y = 0.f, a = 0.f;
     uint32_t n = 0, m = 0, nq = 0;
     if (has_sample) {
-      const uint32_t pair = p0 + ps;
+      const uint32_t pair = pm.pair(p0 + ps);
       nq = fd_div(pair, div_m);
       m = pair - nq * div_m.d;
       n = fd_div(pair, div_mq);
-      load_loc_aw<LT>(loc, aw, static_cast<int64_t>(p0) * LP + lane, x, y, a);
+      load_loc_aw<LT>(loc, aw, static_cast<int64_t>(pair) * LP + ss, x, y, a);
     }
     if constexpr (std::is_same<LT, float>::value && (LP & (LP - 1)) == 0) {
       if (fz.ref != nullptr) {                      // fused prologue: (x, y) are raw offsets, a is a raw logit
@@ -339,7 +364,7 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 #pragma unroll
               for (int j = 0; j < C::CPL; ++j) acc[j] += __shfl_down_sync(0xffffffffu, acc[j], k * C::G);
             }
-            if (lane < C::G) Vec16<VT>::store(out + static_cast<int64_t>(p0 + pl) * D + lane * C::CPL, acc);
+            if (lane < C::G) Vec16<VT>::store(out + static_cast<int64_t>(pm.pair(p0 + pl)) * D + lane * C::CPL, acc);
           }
         }
       }
@@ -365,7 +390,7 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
       const int pl = lane >> 4;
       if (pl < npair) {
         if constexpr (std::is_same<VT, float>::value)
-          *reinterpret_cast<float2*>(out + static_cast<int64_t>(p0 + pl) * D + (lane & 7) * 4 + (hi_half ? 2 : 0)) = make_float2(two[0], two[1]);
+          *reinterpret_cast<float2*>(out + static_cast<int64_t>(pm.pair(p0 + pl)) * D + (lane & 7) * 4 + (hi_half ? 2 : 0)) = make_float2(two[0], two[1]);
       }
     }
     if constexpr (GROUPED) {
@@ -378,7 +403,7 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
             for (int j = 0; j < C::CPL; ++j) acc_g[pl][j] += __shfl_down_sync(0xffffffffu, acc_g[pl][j], k * C::G);
           }
           if (lane < C::G) {
-            VT* dst = out + static_cast<int64_t>(p0 + pl) * D + lane * C::CPL;
+            VT* dst = out + static_cast<int64_t>(pm.pair(p0 + pl)) * D + lane * C::CPL;
             if constexpr (std::is_same<VT, float>::value) {
               if (g_split) red_add_f32x4(dst, acc_g[pl][0], acc_g[pl][1], acc_g[pl][2], acc_g[pl][3]);
               else Vec16<VT>::store(dst, acc_g[pl]);
@@ -412,7 +437,7 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
                       const LT* __restrict__ aw, const VT* __restrict__ grad_out,
                       float* __restrict__ grad_value, LT* __restrict__ grad_loc, LT* __restrict__ grad_aw,
                       int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq,
-                      int G, float scale, FusedArgs fz, int merge) {
+                      int G, float scale, FusedArgs fz, int merge, int hrun) {
   using C = Cfg2<VT, D, LP>;
   // <grad_out, corner row> per (corner, sample): [4][40] floats per warp.  The partials are folded inside the
   // corner group with shuffles first, so the tile stays tiny and shared memory stays small: the first version
@@ -443,8 +468,8 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
   float* dot_w = s_dot[warp] + corner * kDotStride + sgrp * C::SPG;
   const float* dot_r = s_dot[warp] + lane;
 
-  const uint32_t chunk_begin = blockIdx.x * static_cast<uint32_t>(chunk_pairs);
-  const uint32_t chunk_end = min(n_pairs, chunk_begin + static_cast<uint32_t>(chunk_pairs));
+  const PairMap pm(hrun, blockIdx.x, chunk_pairs, n_pairs, div_m);
+  const uint32_t chunk_begin = pm.begin, chunk_end = pm.end;
   const int ps = (lane < C::QPW * LP) ? lane / LP : 0;
   const int ss = lane - ps * LP;
   const int lvl = ss / P;
@@ -454,12 +479,14 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
     const bool has_sample = lane < npair * LP;
     float x = 0.f, y = 0.f, a = 0.f, a_raw = 0.f, mk_x = 1.f, mk_y = 1.f;
     uint32_t n = 0, m = 0, nq = 0;
+    int64_t si = 0;                                  // this lane's sample: index into loc / aw and their gradients
     if (has_sample) {
-      const uint32_t pair = p0 + ps;
+      const uint32_t pair = pm.pair(p0 + ps);
       nq = fd_div(pair, div_m);
       m = pair - nq * div_m.d;
       n = fd_div(pair, div_mq);
-      load_loc_aw<LT>(loc, aw, static_cast<int64_t>(p0) * LP + lane, x, y, a);
+      si = static_cast<int64_t>(pair) * LP + ss;
+      load_loc_aw<LT>(loc, aw, si, x, y, a);
     }
     bool fused = false;
     if constexpr (std::is_same<LT, float>::value && (LP & (LP - 1)) == 0) {
@@ -475,7 +502,7 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
     if constexpr (GROUPED) {
 #pragma unroll
       for (int pl = 0; pl < C::QPW; ++pl)
-        if (pl < npair) Vec16<VT>::load(grad_out + static_cast<int64_t>(p0 + pl) * D + c * C::CPL, go_g[pl]);
+        if (pl < npair) Vec16<VT>::load(grad_out + static_cast<int64_t>(pm.pair(p0 + pl)) * D + c * C::CPL, go_g[pl]);
     }
     float g_aw = 0.f, g_x = 0.f, g_y = 0.f;
 
@@ -513,14 +540,14 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 #pragma unroll
             for (int j = 0; j < C::CPL; ++j) go[j] = go_g[GROUPED ? pl : 0][j];
           } else {
-            Vec16<VT>::load(grad_out + static_cast<int64_t>(p0 + pl) * D + c * C::CPL, go);
+            Vec16<VT>::load(grad_out + static_cast<int64_t>(pm.pair(p0 + pl)) * D + c * C::CPL, go);
           }
           // 2-byte values: a lane owns 8 channels for the dot products, but two 16-byte reductions per lane at a 32-byte lane
           // stride would half-fill every L2 sector.  The scatter only needs grad_out, so for it the lane takes channels
           // [4c, 4c+4) and [4G+4c, 4G+4c+4): each warp-wide RED then covers contiguous 16-byte pieces (bf16 backward 439 -> fp32 speed).
           float go_red[C::CPL == 8 ? 8 : 1];
           if constexpr (C::CPL == 8) {
-            const VT* gp = grad_out + static_cast<int64_t>(p0 + pl) * D;
+            const VT* gp = grad_out + static_cast<int64_t>(pm.pair(p0 + pl)) * D;
             const uint2 lo4 = __ldg(reinterpret_cast<const uint2*>(gp + 4 * c));
             const uint2 hi4 = __ldg(reinterpret_cast<const uint2*>(gp + 4 * C::G + 4 * c));
             const uint32_t u4[4] = {lo4.x, lo4.y, hi4.x, hi4.y};
@@ -654,7 +681,6 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
         const float t = a_raw * (scale * g_aw);
         const float tsum = segment_sum<LP>(t);
         if (has_sample) {
-          const int64_t si = static_cast<int64_t>(p0) * LP + lane;
           const float inv = 1.f / fz.scale;
           store_pair(grad_loc + 2 * si, a * g_x * inv * mk_x, a * g_y * inv * mk_y);       // d / d raw offsets
           st_from_float(grad_aw + si, t - a_raw * tsum);                                   // d / d logits
@@ -663,7 +689,6 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
       }
     }
     if (has_sample) {
-      const int64_t si = static_cast<int64_t>(p0) * LP + lane;
       if constexpr (std::is_same<LT, float>::value) {
         if (g_split) {                                       // zero-filled by the host
           atomicAdd(grad_loc + 2 * si, a * g_x);

@@ -11,6 +11,10 @@
 #include "msda_generic.cuh"
 #include "msda_internal.h"
 
+#ifndef MSDA_HEAD_RUN_DEFAULT
+#define MSDA_HEAD_RUN_DEFAULT 1
+#endif
+
 namespace msda {
 
 struct Problem {
@@ -42,6 +46,22 @@ inline int pick_chunk(const Problem& pb) {
   }
   chunk = ((chunk + unit - 1) / unit) * unit;
   return chunk < unit ? unit : chunk;
+}
+
+// Head-run pair order (PairMap in msda_fast2.cuh): on for calls large enough that co-resident CTAs would otherwise sit in
+// unrelated parts of the image.  The grid becomes ceil(N*Lq / chunk) runs x M heads.
+// Measured (profiles/r02_pair_map.md): the backward gains 3-6 % on every encoder shape (L1 hit rate 28 -> 41 %, L2 read sectors
+// 20.1 M -> 12.1 M per call); the forward's hit rate rises too (43 -> 61 %) but its time does not move (it is bound by the number
+// of wavefronts, not by where the rows come from), so `auto` keeps the forward on the linear order.
+inline bool head_run(const Problem& pb, bool split, bool backward) {
+  const int mode = options().pair_map.load();
+  if (split || mode == 1) return false;
+  if (mode == 2) return true;
+  return MSDA_HEAD_RUN_DEFAULT != 0 && backward && pb.n_pairs >= 148LL * 4 * 64;
+}
+inline unsigned head_run_grid(const Problem& pb, int chunk) {
+  const int64_t nq = pb.n_pairs / pb.M;
+  return static_cast<unsigned>(((nq + chunk - 1) / chunk) * pb.M);
 }
 
 inline FastDiv make_fastdiv(uint32_t d) {
@@ -109,12 +129,12 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 #endif
 
 template <typename VT, typename LT, int D, int MINB>
-inline void launch_fwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int chunk, const VT* v, const int64_t* shapes,
+inline void launch_fwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int chunk, int hrun, const VT* v, const int64_t* shapes,
                            const int64_t* lsi, const LT* lc, const LT* a, VT* o) {
   const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
   const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
 #define MSDA_FWD2(LPV, GRP) launch_kernel(msda_fwd_fast2_kernel<VT, LT, D, LPV, MINB, GRP>, grid, dim3(kThreads), 0, st, \
-      v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz)
+      v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz, hrun)
   const bool grouped = pb.G > 1 || pb.scale != 1.f;
   switch (pb.L * pb.P) {
     case 16: if (grouped) MSDA_FWD2(16, true); else MSDA_FWD2(16, false); break;
@@ -125,14 +145,14 @@ inline void launch_fwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int ch
 }
 
 template <typename VT, typename LT, int D>
-inline void launch_bwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int chunk, const VT* v, const int64_t* shapes,
+inline void launch_bwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int chunk, int hrun, const VT* v, const int64_t* shapes,
                            const int64_t* lsi, const LT* lc, const LT* a, const VT* go, float* gv, LT* gl, LT* ga) {
   const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
   const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
 #define MSDA_BWD2(LPV, GRP) do { \
       prefer_small_carveout(msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP>, (GRP) ? 2 : MSDA_BWD_MINB); \
       launch_kernel(msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP>, grid, dim3(kThreads), 0, st, \
-      v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz, merge); } while (0)
+      v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz, merge, hrun); } while (0)
   const bool grouped = pb.G > 1 || pb.scale != 1.f;
   const int merge = (options().bwd_merge.load() != 0 && (pb.P == 4 || pb.P == 2)) ? pb.P : 0;
   switch (pb.L * pb.P) {
@@ -163,14 +183,16 @@ int launch_fwd(cudaStream_t st, const Problem& pb, bool fast, const void* value,
         }
         // default: register-lean schedule (82 vs 90 us on the encoder shape, profiles/r01d); 3 = batched gathers.  Calls too small
         // to fill the SMs (the decoder's 196 queries: 392 CTAs) are latency bound and take the batched build (8.2 -> 7.4 us, cold)
+        const int hrun = head_run(pb, grid2.y > 1, false) ? 1 : 0;
+        if (hrun) grid2.x = head_run_grid(pb, chunk);
         const bool small_grid = options().fwd_variant.load() == 0 && static_cast<uint64_t>(grid) * grid2.y < 148u * 4u;
         const bool lean = options().fwd_variant.load() != 3 && !small_grid;
         if (pb.D == 32) {
-          if (lean) launch_fwd2_lp<VT, LT, 32, MSDA_FWD_MINB>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);
-          else launch_fwd2_lp<VT, LT, 32, 3>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);
+          if (lean) launch_fwd2_lp<VT, LT, 32, MSDA_FWD_MINB>(st, pb, grid2, chunk, hrun, v, shapes, lsi, lc, a, o);
+          else launch_fwd2_lp<VT, LT, 32, 3>(st, pb, grid2, chunk, hrun, v, shapes, lsi, lc, a, o);
         } else {
-          if (lean) launch_fwd2_lp<VT, LT, 24, MSDA_FWD_MINB>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);
-          else launch_fwd2_lp<VT, LT, 24, 3>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, o);
+          if (lean) launch_fwd2_lp<VT, LT, 24, MSDA_FWD_MINB>(st, pb, grid2, chunk, hrun, v, shapes, lsi, lc, a, o);
+          else launch_fwd2_lp<VT, LT, 24, 3>(st, pb, grid2, chunk, hrun, v, shapes, lsi, lc, a, o);
         }
         return after_launch("msda_fwd_fast2_kernel");
       }
@@ -210,8 +232,10 @@ int launch_bwd(cudaStream_t st, const Problem& pb, bool fast, const void* value,
           if (check_cuda(cudaMemsetAsync(gl, 0, n_smp * 2 * sizeof(LT), st), "cudaMemsetAsync(grad_loc)")) return MSDA_ERR_CUDA;
           if (check_cuda(cudaMemsetAsync(ga, 0, n_smp * sizeof(LT), st), "cudaMemsetAsync(grad_aw)")) return MSDA_ERR_CUDA;
         }
-        if (pb.D == 32) launch_bwd2_lp<VT, LT, 32>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, go, gv_acc, gl, ga);
-        else launch_bwd2_lp<VT, LT, 24>(st, pb, grid2, chunk, v, shapes, lsi, lc, a, go, gv_acc, gl, ga);
+        const int hrun = head_run(pb, grid2.y > 1, true) ? 1 : 0;
+        if (hrun) grid2.x = head_run_grid(pb, chunk);
+        if (pb.D == 32) launch_bwd2_lp<VT, LT, 32>(st, pb, grid2, chunk, hrun, v, shapes, lsi, lc, a, go, gv_acc, gl, ga);
+        else launch_bwd2_lp<VT, LT, 24>(st, pb, grid2, chunk, hrun, v, shapes, lsi, lc, a, go, gv_acc, gl, ga);
         return after_launch("msda_bwd_fast2_kernel");
       }
       if (pb.D == 32)

@@ -20,7 +20,13 @@ ap.add_argument("what")
 ap.add_argument("--dist", default="local")
 ap.add_argument("--dtype", default="fp32")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--opt", default="", help="library options, e.g. pair_map=2,chunk_pairs=64")
 args = ap.parse_args()
+if args.opt:
+    from mdqe_cvpr2023_b200 import _lib
+    for kv in args.opt.split(","):
+        k, v = kv.split("=")
+        _lib.set_option(k, int(v))
 
 if args.what.startswith("mask"):
     coeff = torch.tanh(torch.randn(1, 196, 32, device="cuda"))
