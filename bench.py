@@ -75,6 +75,14 @@ def parse_args():
     ap.add_argument("--no-other-configs", action="store_true", help="skip the other BASELINE configurations and the module arm")
     ap.add_argument("--no-prezero", action="store_true", help="A/B: zero-fill grad_value inside every backward call (on the critical path) instead of on a side branch")
     ap.add_argument("--no-allreduce", action="store_true", help="debug: multi-GPU step without the gradient all-reduce (not a valid bench value)")
+    ap.add_argument("--allreduce-impl", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU gradient all-reduce: 'peer' = msda_allreduce_f32 (this library's kernel over NVLink peer memory: multimem "
+                         "through the switch when available, else two-shot P2P; few CTAs so that it runs beside the encoder backward), "
+                         "'nccl' = torch.distributed.all_reduce")
+    ap.add_argument("--allreduce-ctas", type=int, default=4, help="CTAs of the peer all-reduce while it overlaps the backward")
+    ap.add_argument("--allreduce-mode", default="graph", choices=["graph", "split"],
+                    help="multi-GPU: 'graph' = ONE CUDA graph per step with the NCCL all-reduces captured on a forked branch; "
+                         "'split' = round 1's 1 + n_enc graphs with the all-reduces enqueued between them")
     return ap.parse_args()
 
 
@@ -536,7 +544,7 @@ def measure_other_config(torch, lib, libmod, key, dtype, dist, device, steps, hb
     return res
 
 
-def module_arm(torch, shape, device, steps, dist="local"):
+def module_arm(torch, shape, device, steps, dist="local", world=1):
     """The same clip through `mdqe_cvpr2023_b200.MSDeformAttn` (what train_net.py would run): 6 encoder self-attention modules on
     the [T, S, 256] pyramid, then 6 x (frame-level + clip-level) decoder cross-attention modules, residual connections between
     them, forward + backward with every parameter gradient; Linear layers as 3xTF32 tensor-core GEMMs, softmax / location
@@ -577,10 +585,36 @@ def module_arm(torch, shape, device, steps, dist="local"):
         x, qf, qc = forward()
         return torch.autograd.grad(x.sum() + qf.sum() + qc.sum(), [src, q_f, q_c] + params)
 
+    def ddp_step():
+        # clip-sharded data parallel training (train_net.py:256-271): every rank runs its own clip, then the parameter gradients
+        # THIS step produced are averaged over the ranks (bucketed NCCL all-reduce, mdqe_cvpr2023_b200/sharding.py) -- all captured
+        from mdqe_cvpr2023_b200.sharding import allreduce_mean_gradients
+        for p in params:
+            p.grad = None
+        x, qf, qc = forward()
+        (x.sum() + qf.sum() + qc.sum()).backward()
+        allreduce_mean_gradients(params)
+
     def infer_step():
         with torch.no_grad():
             return forward()
 
+    ddp = None
+    if world > 1:
+        import torch.distributed as tdist
+        for p in params:                                       # replicas start from the same weights (rank 0's), inputs differ per rank
+            tdist.broadcast(p.data, 0)
+        g_ddp = capture(torch, ddp_step)
+        ddp_ms = time_replays(torch, g_ddp, steps)
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        sums = [torch.zeros(2, device=device, dtype=torch.float64) for _ in range(world)]
+        tdist.all_gather(sums, torch.stack([flat.double().sum(), flat.double().abs().sum()]))
+        same = all(bool((t == sums[0]).all()) for t in sums)
+        ddp = {"train_step_ms": ddp_ms, "aggregate_clips_per_s": world * 1e3 / ddp_ms, "grad_elements_reduced": int(flat.numel()),
+               "grad_abs_sum": float(sums[0][1]), "grads_identical_on_all_ranks": same,
+               "what": "the same module step on every rank (own clip), then the parameter gradients it produced averaged over the ranks "
+                       "with the bucketed NCCL all-reduce of mdqe_cvpr2023_b200/sharding.py, all inside one captured CUDA graph"}
+        del g_ddp
     train_ms = time_replays(torch, capture(torch, train_step), steps)
     infer_ms = time_replays(torch, capture(torch, infer_step), steps)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -596,7 +630,7 @@ def module_arm(torch, shape, device, steps, dist="local"):
                     "parameter gradients, through mdqe_cvpr2023_b200.MSDeformAttn (tc_linear + fused prologue + grouped temporal launch)",
             "shape": shape["name"], "train_step_ms": train_ms, "train_clips_per_s": 1e3 / train_ms, "inference_ms": infer_ms,
             "inference_clips_per_s": 1e3 / infer_ms, "eager_train_step_ms": e0.elapsed_time(e1) / 5,
-            "parameters": sum(p.numel() for p in params), "timing": f"CUDA-graph replay x{steps}, CUDA events"}
+            "parameters": sum(p.numel() for p in params), "timing": f"CUDA-graph replay x{steps}, CUDA events", "ddp": ddp}
 
 
 # ----------------------------------------------------------------------------------------------- main
@@ -647,7 +681,7 @@ def main():
         hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
 
     if args.arm == "module":                                   # only the module-level step
-        res = module_arm(torch, shape, device, args.steps, args.dist)
+        res = module_arm(torch, shape, device, args.steps, args.dist, world)
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": world * res["train_clips_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
                               "warmup": 3, "ms_per_step": res["train_step_ms"], "higher_is_better": True, "scaling": "weak",
@@ -664,8 +698,28 @@ def main():
     # bucket is reduced on NCCL's stream while the encoder backward runs, then one bucket per encoder layer as soon as that
     # layer's backward has been enqueued; only the last layer's 3 MB are reduced after the backward has ended.
     n_enc_layers = step.n_enc
-    dec_buf = torch.zeros(14_940_000, device=device) if world > 1 else None
-    enc_bufs = [torch.zeros(4_540_000 // max(n_enc_layers, 1), device=device) for _ in range(n_enc_layers)] if world > 1 else None
+    DEC_ELEMS = 14_940_000
+    enc_elems = (4_540_000 // max(n_enc_layers, 1) + 3) // 4 * 4
+    peer_ar, peer_note = None, None
+    dec_buf = enc_bufs = None
+    if world > 1 and args.allreduce_impl == "peer":
+        try:
+            from mdqe_cvpr2023_b200.collectives import PeerAllReduce
+            peer_ar = PeerAllReduce(DEC_ELEMS + n_enc_layers * enc_elems, device, n_ctas=args.allreduce_ctas)
+        except Exception as e:  # noqa: BLE001 -- no symmetric memory on this box / torch build: NCCL does the reduction
+            peer_note = "peer all-reduce unavailable (%s); NCCL used" % repr(e)[:200]
+    if world > 1 and peer_ar is None:
+        dec_buf = torch.zeros(DEC_ELEMS, device=device)
+        enc_bufs = [torch.zeros(enc_elems, device=device) for _ in range(n_enc_layers)]
+
+    def reduce_bucket(i, last=False):
+        """bucket -1 = decoder parameters, i >= 0 = encoder layer i (gradient-ready order); enqueues on the current stream"""
+        if peer_ar is not None:
+            off, n = (0, DEC_ELEMS) if i < 0 else (DEC_ELEMS + i * enc_elems, enc_elems)
+            # the last bucket has nothing left to hide behind: give it enough CTAs to finish quickly
+            peer_ar.all_reduce_(off, n, mean=True, n_ctas=16 if last else args.allreduce_ctas)
+        else:
+            dist.all_reduce(dec_buf if i < 0 else enc_bufs[i])
 
     def sync_all():
         torch.cuda.synchronize()
@@ -677,21 +731,51 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step.run()
         if world > 1:
-            dist.all_reduce(dec_buf)
-            for b in enc_bufs:
-                dist.all_reduce(b)
+            for i in range(-1, n_enc_layers):
+                reduce_bucket(i, last=(i == n_enc_layers - 1))
     torch.cuda.synchronize()
     graphs = None
-    if not args.no_graph:
+    # high priority: the few CTAs of a bucket's all-reduce are dispatched as soon as an SM has room, not behind the 3400 CTAs of the backward
+    nccl_side = torch.cuda.Stream(device, priority=-1) if world > 1 else None
+
+    def whole_step(with_allreduce=True):
+        """One multi-GPU step for capture: the decoder-gradient bucket is all-reduced on a forked branch as soon as the decoder
+        backward has been enqueued, one encoder bucket after each encoder layer's backward; the branch joins at the end."""
+        cur = torch.cuda.current_stream(device)
+        step.run("head")
+        if with_allreduce:
+            nccl_side.wait_stream(cur)
+            with torch.cuda.stream(nccl_side):
+                reduce_bucket(-1)
+        for i in range(n_enc_layers):
+            step.run(f"tail{i}")
+            if with_allreduce:
+                nccl_side.wait_stream(cur)
+                with torch.cuda.stream(nccl_side):
+                    reduce_bucket(i, last=(i == n_enc_layers - 1))
+        if with_allreduce:
+            cur.wait_stream(nccl_side)
+
+    one_graph = world > 1 and args.allreduce_mode == "graph" and not args.no_graph
+    graph_note = None
+    if one_graph:
+        try:
+            graphs = [capture(torch, lambda: whole_step(not args.no_allreduce))]
+        except Exception as e:  # noqa: BLE001 -- NCCL builds that cannot be captured fall back to the split form
+            graph_note = "whole-step capture failed (%s); fell back to split graphs" % repr(e)[:200]
+            one_graph, graphs = False, None
+            torch.cuda.synchronize()
+    if graphs is None and not args.no_graph:
         graphs = [capture(torch, (lambda p=part: step.run(p)))
                   for part in (("all",) if world == 1 else ("head",) + tuple(f"tail{i}" for i in range(n_enc_layers)))]
+    if graphs is not None:
         for _ in range(2):
             for g in graphs:
                 g.replay()
         torch.cuda.synchronize()
 
     def one_step():
-        if world == 1:
+        if world == 1 or one_graph:
             if graphs is not None:
                 graphs[0].replay()
             else:
@@ -701,16 +785,21 @@ def main():
             graphs[0].replay()
         else:
             step.run("head")
-        works = [] if args.no_allreduce else [dist.all_reduce(dec_buf, async_op=True)]       # overlaps with the encoder backward below
+        cur = torch.cuda.current_stream(device)
+        if not args.no_allreduce:                               # overlaps with the encoder backward below
+            nccl_side.wait_stream(cur)
+            with torch.cuda.stream(nccl_side):
+                reduce_bucket(-1)
         for i in range(n_enc_layers):
             if graphs is not None:
                 graphs[1 + i].replay()
             else:
                 step.run(f"tail{i}")
             if not args.no_allreduce:
-                works.append(dist.all_reduce(enc_bufs[i], async_op=True))
-        for w in works:
-            w.wait()
+                nccl_side.wait_stream(cur)
+                with torch.cuda.stream(nccl_side):
+                    reduce_bucket(i, last=(i == n_enc_layers - 1))
+        cur.wait_stream(nccl_side)
 
     # ---- timed region: exactly K steps, CUDA events, max over ranks
     libmod.launch_count_reset()
@@ -722,6 +811,8 @@ def main():
         one_step()
     e1.record()
     sync_all()
+    if peer_ar is not None:
+        peer_ar.check()                                # a peer that never reached a barrier would have been reported here
     clocks = sampler.stop() if sampler else None
     ms_total = e0.elapsed_time(e1)
     if world > 1:
@@ -876,8 +967,25 @@ def main():
         lib.msda_host_arena_release()
         del host
 
+    # ---- multi-GPU: the same captured step without the collectives (what the all-reduce costs), and the module-level step with
+    # the parameter gradients it produces averaged over the ranks
+    no_coll_ms, modarm_ddp = None, None
+    if world > 1 and one_graph and not args.no_allreduce:
+        g_nc = capture(torch, lambda: whole_step(False))
+        sync_all()
+        no_coll_ms = time_replays(torch, g_nc, args.steps)
+        t = torch.tensor([no_coll_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        no_coll_ms = float(t.item())
+        del g_nc
+    if world > 1 and not args.no_other_configs and not args.no_graph:
+        try:
+            modarm_ddp = module_arm(torch, shape, device, max(3, min(args.steps, 10)), args.dist, world)
+        except Exception as e:  # noqa: BLE001
+            modarm_ddp = {"error": repr(e)[:300]}
+
     # ---- the other BASELINE.json configurations and the module-level arm (single-GPU runs; rank 0 of a multi-GPU run skips them)
-    other, modarm = None, None
+    other, modarm = None, modarm_ddp
     if world == 1 and not args.no_other_configs and not args.no_graph:
         del step
         torch.cuda.empty_cache()
@@ -911,10 +1019,14 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic", "config": config_dict(args, shape),
-                "launch": "cuda_graph" if graphs is not None else "eager",
+                "launch": ("cuda_graph (one graph per step, NCCL all-reduces captured on a forked branch)" if one_graph else
+                           ("cuda_graph" if graphs is not None else "eager")), "launch_note": graph_note,
+                "ms_per_step_without_allreduce": no_coll_ms,
                 "zero_fill": ("grad_value accumulators zero-filled on a side branch of the step (msda_zero_fill, MSDA_BWD_ACC_ZEROED)" if not args.no_prezero
                               else "inside every backward call"),
-                "allreduce": ("NCCL, %d buckets per step in gradient-ready order: decoder 14.94M fp32 and one 0.76M bucket per encoder layer, each overlapped with the encoder backward still to run" % (1 + n_enc_layers)) if world > 1 else None,
+                "allreduce": ((("msda_allreduce_f32 (%s over NVLink peer memory, %d CTAs; 16 for the last bucket)" % (peer_ar.algo, args.allreduce_ctas)) if peer_ar is not None else "NCCL")
+                              + ", %d buckets per step in gradient-ready order: decoder 14.94M fp32 and one 0.76M bucket per encoder layer, each overlapped with the encoder backward still to run" % (1 + n_enc_layers)) if world > 1 else None,
+                "allreduce_note": peer_note,
                 # kernels of this library launched inside the timed region: the library's own launch counter over an eager pass of
                 # the same step (the graph replays re-launch exactly those kernels) x steps; `launches_per_step` is the C-ABI call count
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(round(counted_per_step * args.steps)) if counted_per_step else gpu_launches,
@@ -925,8 +1037,23 @@ def main():
                 "roofline_mask_bwd": roofline_mask_bwd, "eager_ms_per_step": eager_ms, "step_with_inline_zero_fill": inline_fill,
                 "forward_only": fwd_only, "other_configs": other, "module_arm": modarm, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
+    if world > 1 and peer_ar is not None:
+        torch.cuda.synchronize()
+        peer_ar.check()
     if world > 1:
-        dist.destroy_process_group()
+        # captured NCCL kernels keep references into the communicator: drop the graphs and drain the device before tearing the
+        # process group down, and do not let a slow teardown hold the line (already printed) hostage
+        graphs = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        import threading
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(20.0)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

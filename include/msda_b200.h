@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 3
+#define MSDA_B200_ABI_VERSION 4
 
 typedef enum {
   MSDA_OK = 0,
@@ -126,6 +126,24 @@ int msda_backward_grouped_flags(void* stream, int dtype,
                                 int N, int S, int M, int D, int G, int L, int Lq, int P, float scale,
                                 void* grad_value, void* grad_loc, void* grad_aw,
                                 void* workspace, size_t workspace_bytes, int flags);
+
+/* Gradient all-reduce of clip-sharded data-parallel training over NVLink peer memory (the reference leaves it to
+ * PyTorch DDP over NCCL, train_net.py:256-271 -- detectron2's launch wraps the model in DistributedDataParallel).  One small
+ * kernel (n_ctas CTAs) instead of NCCL's 24-32 channel CTAs, so that the bucket can be reduced UNDER the encoder backward
+ * without taking its SMs:   bucket[i] = scale * sum_r bucket_r[i]   in place, in every rank's replica.
+ *   peer_ptrs[world]  : the bucket's base address as mapped in THIS process for every rank (peer_ptrs[rank] = the local one);
+ *                       a symmetric allocation -- same size and layout on every rank (cudaIpc / VMM handles / torch symmetric memory)
+ *   multicast_ptr     : NVSwitch multicast mapping of the same allocation (algo 1) or 0
+ *   flag_ptrs[world]  : msda_allreduce_flag_bytes(n_ctas) bytes per rank, mapped like the bucket, zero before the first call
+ *   error_word        : int on the local device, set to 1 if a peer never arrived (bounded spin instead of a hang)
+ *   algo 0            : two-shot P2P -- rank r loads slice r from every peer, adds in rank order, stores the sum to every peer
+ *   algo 1            : multimem -- multimem.ld_reduce / multimem.st: the switch adds and broadcasts (needs multicast_ptr)
+ * offset_elems / n_elems address a sub-range of the bucket (multiples of 4 floats).  Every rank must issue the same calls in
+ * the same order; calls only enqueue (graph-capturable).  world <= msda_allreduce_max_ranks(). */
+int msda_allreduce_max_ranks(void);
+size_t msda_allreduce_flag_bytes(int n_ctas);
+int msda_allreduce_f32(void* stream, int algo, int rank, int world, const uint64_t* peer_ptrs, uint64_t multicast_ptr,
+                       const uint64_t* flag_ptrs, void* error_word, int64_t offset_elems, int64_t n_elems, float scale, int n_ctas);
 
 /* Fused sampler prologue (replaces the elementwise tail of MSDeformAttn.forward, ms_deform_attn.py:142-161):
  * the kernel takes what the module's Linear layers produce and computes softmax and sampling locations itself.

@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(PKG_DIR, "libmsda_b200.so")
 
 MSDA_F32, MSDA_BF16, MSDA_F64, MSDA_BF16_LOC32, MSDA_F16 = 0, 1, 2, 3, 4
-ABI_VERSION = 3
+ABI_VERSION = 4
 BWD_ACC_ZEROED = 1
 
 _c_int, _c_vp, _c_i64, _c_sz = ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t
@@ -72,6 +72,10 @@ PROTOTYPES = {
     "query_init_sample_forward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "query_init_sample_backward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int,
                                             _c_vp, _c_vp]),
+    "msda_allreduce_max_ranks": (_c_int, []),
+    "msda_allreduce_flag_bytes": (_c_sz, [_c_int]),
+    "msda_allreduce_f32": (_c_int, [_c_vp, _c_int, _c_int, _c_int, ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint64,
+                                    ctypes.POINTER(ctypes.c_uint64), _c_vp, _c_i64, _c_i64, ctypes.c_float, _c_int]),
     "msda_profile_read": (_c_int, [_c_int, _c_i64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_c_i64)]),
     "msda_debug_read": (_c_int, [ctypes.POINTER(ctypes.c_longlong)]),
     "msda_launch_count": (_c_i64, []),

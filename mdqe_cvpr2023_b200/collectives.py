@@ -1,0 +1,99 @@
+"""Gradient all-reduce over NVLink peer memory: the host side of csrc/allreduce.cu.
+
+The reference trains with PyTorch DDP over NCCL (train_net.py:256-271).  Here the bucket lives in a *symmetric* allocation --
+every rank maps every other rank's copy, plus the NVSwitch multicast alias when the box has one -- and ONE small kernel of this
+library reduces it in place (`msda_allreduce_f32`): multimem.ld_reduce / multimem.st through the switch, or two-shot P2P loads
+and stores.  torch.distributed is used for the plumbing only: allocation and handle exchange
+(`torch.distributed._symmetric_memory`), never for the reduction itself.
+
+    ar = PeerAllReduce(n_floats, device)            # collective: every rank of the group calls it
+    ar.buffer[...] = flat gradients                 # (or build the gradient buckets as views of ar.buffer)
+    ar.all_reduce_(mean=True)                       # enqueue on the current stream; graph-capturable
+    ar.check()                                      # after a synchronize: raises if a peer never arrived
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class PeerAllReduce:
+    ALGOS = {"p2p": 0, "multimem": 1}
+
+    def __init__(self, numel, device, group=None, algo="auto", n_ctas=8):
+        import torch.distributed._symmetric_memory as symm
+        if not dist.is_initialized():
+            raise RuntimeError("PeerAllReduce needs an initialised process group (plumbing: handle exchange)")
+        lib = _lib.load()
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > lib.msda_allreduce_max_ranks():
+            raise RuntimeError(f"PeerAllReduce supports up to {lib.msda_allreduce_max_ranks()} ranks (one NVSwitch box)")
+        self.numel = (int(numel) + 3) // 4 * 4
+        self.n_ctas = int(n_ctas)
+        self.device = torch.device(device)
+        try:                                         # older torch builds want the group registered first; newer ones deprecate it
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:  # noqa: BLE001
+            pass
+        self.buffer = symm.empty(self.numel, dtype=torch.float32, device=self.device)
+        self._flags = symm.empty(lib.msda_allreduce_flag_bytes(148) // 4, dtype=torch.int32, device=self.device)
+        self.buffer.zero_()
+        self._flags.zero_()
+        self._hb = symm.rendezvous(self.buffer, group.group_name)
+        self._hf = symm.rendezvous(self._flags, group.group_name)
+        self._peers = (ctypes.c_uint64 * self.world)(*[int(p) for p in self._hb.buffer_ptrs])
+        self._flag_ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in self._hf.buffer_ptrs])
+        self._mc = int(getattr(self._hb, "multicast_ptr", 0) or 0)          # 0: no NVSwitch multicast on this box
+        if algo == "auto":
+            algo = "multimem" if self._mc else "p2p"
+        if algo == "multimem" and not self._mc:
+            raise RuntimeError("multimem all-reduce needs NVSwitch multicast support on this box")
+        self.algo = algo
+        self._error = torch.zeros(1, dtype=torch.int32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)                          # every rank's flags are zero before anybody's first kernel
+
+    def all_reduce_(self, offset=0, numel=None, mean=True, stream=None, n_ctas=None):
+        """bucket[offset:offset+numel] = (mean or sum) over the ranks, in place in every replica.  Enqueues one kernel."""
+        numel = self.numel - offset if numel is None else int(numel)
+        st = (stream or torch.cuda.current_stream(self.device)).cuda_stream
+        _lib.check(_lib.load().msda_allreduce_f32(st, self.ALGOS[self.algo], self.rank, self.world, self._peers, self._mc, self._flag_ptrs,
+                                                  self._error.data_ptr(), int(offset), numel, (1.0 / self.world) if mean else 1.0,
+                                                  n_ctas or self.n_ctas), "msda_allreduce_f32")
+        return self.buffer[offset:offset + numel]
+
+    def check(self):
+        """after a device synchronize: did every peer arrive at every barrier?"""
+        if int(self._error.item()) != 0:
+            raise RuntimeError("msda_allreduce_f32: a peer never reached the barrier (bounded spin expired)")
+
+
+def allreduce_mean_gradients_peer(parameters, ar):
+    """DDP's gradient averaging with the peer-memory kernel: flatten every parameter's .grad (zeros where this rank produced
+    none) into ar.buffer, reduce, copy back.  Same collective on every rank, like sharding.allreduce_mean_gradients."""
+    params = [p for p in parameters if p.requires_grad]
+    total = sum(p.numel() for p in params)
+    if total > ar.numel:
+        raise RuntimeError(f"bucket of {ar.numel} floats is too small for {total} gradient elements")
+    off = 0
+    for p in params:
+        n = p.numel()
+        if p.grad is None:
+            ar.buffer[off:off + n].zero_()
+        else:
+            ar.buffer[off:off + n].copy_(p.grad.reshape(-1))
+        off += n
+    ar.all_reduce_(0, (total + 3) // 4 * 4, mean=True)
+    off = 0
+    for p in params:
+        n = p.numel()
+        piece = ar.buffer[off:off + n].view_as(p)
+        if p.grad is None:
+            p.grad = piece.clone()
+        else:
+            p.grad.copy_(piece)
+        off += n
+    return 1
