@@ -79,7 +79,9 @@ def parse_args():
                     help="multi-GPU gradient all-reduce: 'peer' = msda_allreduce_f32 (this library's kernel over NVLink peer memory: multimem "
                          "through the switch when available, else two-shot P2P; few CTAs so that it runs beside the encoder backward), "
                          "'nccl' = torch.distributed.all_reduce")
-    ap.add_argument("--allreduce-ctas", type=int, default=4, help="CTAs of the peer all-reduce while it overlaps the backward")
+    ap.add_argument("--allreduce-ctas", type=int, default=0,
+                    help="CTAs of the peer all-reduce while it overlaps the backward (0 = auto: 6 on two GPUs, 4 on more -- through the "
+                         "switch one CTA moves 70 GB/s at world 2 and 190 GB/s at world 8, profiles/r02_allreduce.md)")
     ap.add_argument("--allreduce-mode", default="graph", choices=["graph", "split"],
                     help="multi-GPU: 'graph' = ONE CUDA graph per step with the NCCL all-reduces captured on a forked branch; "
                          "'split' = round 1's 1 + n_enc graphs with the all-reduces enqueued between them")
@@ -702,6 +704,8 @@ def main():
     enc_elems = (4_540_000 // max(n_enc_layers, 1) + 3) // 4 * 4
     peer_ar, peer_note = None, None
     dec_buf = enc_bufs = None
+    if args.allreduce_ctas <= 0:
+        args.allreduce_ctas = 6 if world == 2 else 4
     if world > 1 and args.allreduce_impl == "peer":
         try:
             from mdqe_cvpr2023_b200.collectives import PeerAllReduce
@@ -958,7 +962,9 @@ def main():
         gbs = world * (host.h2d + host.d2h) * n_e2e / dt / 1e9
         e2e = {"value": world * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": host.h2d, "d2h_bytes_per_step": host.d2h,
                "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3, "host_link_gbs_all_ranks": gbs,
-               "limit": "host<->device link: the step moves h2d+d2h bytes per rank through PCIe; see profiles/ for the per-rank copy bandwidth at this rank count",
+               "limit": "host<->device link: the step moves h2d+d2h bytes per rank through PCIe.  Measured on this pool's 8-GPU box with all ranks copying "
+                        "at once (tools/hostlink_probe.py, profiles/r02_hostlink.md): 78 GB/s full duplex for one rank alone, but only 154 GB/s in total for 8 "
+                        "ranks (16-23 GB/s per rank), i.e. >= 79 ms per step at 8 GPUs whatever the kernels do -- the host side of the box, not NVLink or the GPU",
                "timing": ("wall clock; *_host C-ABI calls in host_async mode (3-stream pipeline), msda_host_sync() at the end of every step" if args.e2e_sync_every_step else
                           "wall clock over all steps; *_host C-ABI calls in host_async mode (3-stream pipeline); every step ends with msda_host_fence() and is "
                           "waited for (msda_host_wait: all its results in host memory) while the next step is enqueued -- at most two steps in flight"),

@@ -12,4 +12,4 @@ for l in sys.stdin:
         d = json.loads(l); print('%-44s step %.4f ms  without all-reduce %.4f ms  value %.1f  %s' % ('$*', d['ms_per_step'], d.get('ms_per_step_without_allreduce') or 0, d['value'], (d.get('allreduce') or '')[:60]))" | tee -a $OUT
 }
 run --allreduce-impl nccl
-for c in 2 4 6 8; do run --allreduce-impl peer --allreduce-ctas $c; done
+for c in ${CTAS:-4 8}; do run --allreduce-impl peer --allreduce-ctas $c; done
