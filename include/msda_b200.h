@@ -206,6 +206,9 @@ int tc_linear_forward(void* stream, const void* x, const void* weight, const voi
                       int64_t rows, int in_features, int out_features, void* y);
 int tc_linear_backward(void* stream, const void* grad_y, const void* x, const void* weight,
                        int64_t rows, int in_features, int out_features, void* grad_x, void* grad_weight);
+/* grad_bias[o] = sum_r grad_y[r, o] (nn.Linear's bias gradient; torch's strided sum(0) costs 28 us per encoder-sized call, this
+ * streams grad_y once at memory speed).  grad_bias is zero-filled inside; out_features a multiple of 4. */
+int tc_linear_bias_grad(void* stream, const void* grad_y, int64_t rows, int out_features, void* grad_bias);
 
 /* Host-buffer entries: same semantics, every pointer is HOST memory (pinned memory makes the
  * copies asynchronous).  The library owns a grow-only device arena per process; `device` selects

@@ -44,6 +44,7 @@ PROTOTYPES = {
     "mask_logits_backward": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_vp, _c_vp]),
     "tc_linear_forward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_int, _c_vp]),
     "tc_linear_backward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_int, _c_vp, _c_vp]),
+    "tc_linear_bias_grad": (_c_int, [_c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
     "msda_forward_host": (_c_int, [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + _SEVEN + [_c_vp]),
     "msda_backward_host": (_c_int, [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + _SEVEN
                            + [_c_vp, _c_vp, _c_vp]),

@@ -613,7 +613,10 @@ using namespace msda;
 
 extern "C" {
 
-size_t mask_match_cost_workspace_bytes(void) { return kMcWsFloats * sizeof(float); }
+size_t mask_match_cost_workspace_bytes(void) {
+  const size_t tc = match_cost_tc_workspace_floats();
+  return (tc > static_cast<size_t>(kMcWsFloats) ? tc : static_cast<size_t>(kMcWsFloats)) * sizeof(float);
+}
 
 int mask_match_cost(void* stream, const void* coeff, const void* proto, const void* targets, int Q, int K, int G, int64_t Ncols,
                     void* workspace, void* cost_bce, void* cost_dice) {
@@ -621,6 +624,23 @@ int mask_match_cost(void* stream, const void* coeff, const void* proto, const vo
   if (Q == 0 || G == 0) return 0;
   if (!coeff || !proto || !targets || !workspace || !cost_bce || !cost_dice) return fail(MSDA_ERR_INVALID_ARG, "mask_match_cost: NULL pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // tensor-core path (csrc/match_cost_tc.cuh): contraction as 3xTF32 tcgen05 MMAs, costs formed in the epilogue out of TMEM
+  const int tc_mode = option("consumer_tc");
+  const bool tc_ok = match_cost_tc_eligible(coeff, proto, targets, K, Ncols);
+  if (tc_mode == 2 && !tc_ok) return fail(MSDA_ERR_UNSUPPORTED, "mask_match_cost: the tensor-core kernel needs K %% 4 == 0, Ncols %% 4 == 0 and 16-byte aligned tensors");
+  if (tc_mode != 1 && tc_ok) {
+    for (int q0 = 0; q0 < Q; q0 += 256) {
+      const int qn = Q - q0 < 256 ? Q - q0 : 256;
+      for (int g0 = 0; g0 < G; g0 += 16) {
+        const int gn = G - g0 < 16 ? G - g0 : 16;
+        if (int rc = match_cost_tc_dispatch(st, static_cast<const float*>(coeff) + static_cast<int64_t>(q0) * K, static_cast<const float*>(proto),
+                                            static_cast<const float*>(targets) + static_cast<int64_t>(g0) * Ncols, qn, K, gn, Ncols,
+                                            static_cast<float*>(workspace), static_cast<float*>(cost_bce) + static_cast<int64_t>(q0) * G + g0,
+                                            static_cast<float*>(cost_dice) + static_cast<int64_t>(q0) * G + g0, G)) return rc;
+      }
+    }
+    return 0;
+  }
   if (int rc = ensure_func_attr(match_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMcSmem))) return rc;
   const int64_t chunks = (Ncols + kTC - 1) / kTC;
   const int slots = option("consumer_ctas") > 0 ? option("consumer_ctas") : 3 * sm_count();      // three resident CTAs per SM

@@ -41,7 +41,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
               const unsigned char* __restrict__ row_mask, int M, int N, int n_kchunks, int chunks_per_split, int tiles_m,
               int tiles_n, int n_items, int reduce) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* out_stage = smem + kG3Stages * kG3StageBytes;                // 2 x 16 KB (one per column half)
   __shared__ __align__(8) uint64_t bars[3 * kG3Stages + 4];
   __shared__ uint32_t s_tmem_base;

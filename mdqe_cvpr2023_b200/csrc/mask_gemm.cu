@@ -9,6 +9,7 @@
 #include "mask_tc4.cuh"
 #include "mask_tc_bwd.cuh"
 #include "gemm3x.cuh"
+#include "match_cost_tc.cuh"
 #include "msda_internal.h"
 
 namespace msda {
@@ -207,6 +208,41 @@ static int launch_mask_simt(cudaStream_t st, const void* coeff, const void* prot
   mask_fwd_simt_kernel<IT, OT><<<grid, 256, 0, st>>>(static_cast<const IT*>(coeff), static_cast<const IT*>(proto),
                                                       static_cast<OT*>(out), Q, K, Ncols, vec_ok);
   return after_launch("mask_fwd_simt_kernel");
+}
+
+// Matcher mask costs on the tensor cores (match_cost_tc.cuh).  One launch: Q <= 256 queries, G <= 16 targets.
+size_t match_cost_tc_workspace_floats() { return static_cast<size_t>(kMtMaxCtas + 1) * kMtWsPerCta; }    // per-CTA blocks + their sum
+bool match_cost_tc_eligible(const void* coeff, const void* proto, const void* tgt, int K, int64_t Ncols) {
+  if (K < 4 || K > 32 || K % 4 != 0) return false;                       // 16-byte global strides, one 32-deep reduction chunk
+  if (Ncols % 4 != 0 || Ncols >= (int64_t(1) << 31) - kMtTile) return false;
+  return ((reinterpret_cast<uintptr_t>(coeff) | reinterpret_cast<uintptr_t>(proto) | reinterpret_cast<uintptr_t>(tgt)) & 15u) == 0;
+}
+int match_cost_tc_dispatch(cudaStream_t st, const float* coeff, const float* proto, const float* tgt, int Q, int K, int G, int64_t Ncols,
+                           float* ws, float* cost_bce, float* cost_dice, int ld) {
+  if (Q < 1 || Q > kMtMaxQ || G < 1 || G > kMtGP) return fail(MSDA_ERR_INVALID_ARG, "match_cost_tc: Q=%d G=%d per launch", Q, G);
+  CUtensorMap map_plane, map_coeff;
+  if (int rc = make_map_mn_f32(&map_plane, proto, (uint64_t)Ncols, (uint64_t)K, 1)) return rc;
+  if (int rc = make_map_in(&map_coeff, coeff, MSDA_F32, (uint64_t)K, (uint64_t)Q, 1, (uint32_t)kMtMaxQ)) return rc;
+  const int64_t n_items = (Ncols + kMtTile - 1) / kMtTile;
+  int ctas = option("consumer_ctas") > 0 ? option("consumer_ctas") : sm_count();
+  if (ctas > kMtMaxCtas) ctas = kMtMaxCtas;
+  if (ctas > n_items) ctas = static_cast<int>(n_items);
+  {
+    ProfScope prof(st, 4, static_cast<int64_t>(Q) * Ncols);
+#define MSDA_MT_LAUNCH(GPV)                                                                                                             \
+    do {                                                                                                                                \
+      if (int rc = ensure_func_attr(match_cost_tc_kernel<GPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMtSmemBytes))) return rc; \
+      match_cost_tc_kernel<GPV><<<ctas, kMtThreads, kMtSmemBytes, st>>>(map_plane, map_coeff, tgt, Q, G, Ncols, static_cast<int>(n_items), ws);       \
+    } while (0)
+    if (G <= 4) MSDA_MT_LAUNCH(4); else if (G <= 8) MSDA_MT_LAUNCH(8); else if (G <= 12) MSDA_MT_LAUNCH(12); else MSDA_MT_LAUNCH(16);
+#undef MSDA_MT_LAUNCH
+  }
+  if (int rc = after_launch("match_cost_tc_kernel")) return rc;
+  float* total = ws + static_cast<size_t>(kMtMaxCtas) * kMtWsPerCta;
+  match_cost_tc_reduce_kernel<<<(kMtWsPerCta + 127) / 128, 128, 0, st>>>(ws, ctas, total);
+  if (int rc = after_launch("match_cost_tc_reduce_kernel")) return rc;
+  match_cost_tc_finalize_kernel<<<(Q * G + 127) / 128, 128, 0, st>>>(total, coeff, Q, K, G, Ncols, ld, cost_bce, cost_dice);
+  return after_launch("match_cost_tc_finalize_kernel");
 }
 
 int mask_forward_dispatch(cudaStream_t st, int in_dtype, int out_dtype, const void* coeff, const void* proto, int B,

@@ -162,7 +162,7 @@ mask_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_
                     const __grid_constant__ CUtensorMap map_out, int Q, int KP, int QS, int QN, int n_qchunks,
                     int n_tiles_n, int n_items, int in_fp16, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   const uint32_t a_half = static_cast<uint32_t>(KP) * 128u;
   const uint32_t b_bytes = static_cast<uint32_t>(QN) * 128u;
   const uint32_t stage_bytes = (2 * a_half + b_bytes + 1023u) & ~1023u;

@@ -44,7 +44,7 @@ mask_fwd_tc4_kernel(const __grid_constant__ CUtensorMap map_plane, const __grid_
                     const __grid_constant__ CUtensorMap map_out, int Q, int n_kchunks, int QS, int QN, int n_qchunks,
                     int n_tiles_n, int n_items, int n_stages, int keep_raw) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   constexpr uint32_t a_bytes = kTcTileN * 128u;                          // plane tile: 4 boxes {32 n, 32 k}
   const uint32_t b_rows = kTransB ? static_cast<uint32_t>((QN + 31) / 32 * 32) : static_cast<uint32_t>(QN);
   const uint32_t b_bytes = (b_rows * 128u + 1023u) & ~1023u;

@@ -36,7 +36,7 @@ mask_grad_coeff_tc_kernel(const __grid_constant__ CUtensorMap map_go, const __gr
   const int q_base = blockIdx.y * 128 * MH;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   const uint32_t a_bytes = static_cast<uint32_t>(MH) * kGcTcHalfBytes;
   const uint32_t b_bytes = (static_cast<uint32_t>(KP) * 128u + 1023u) & ~1023u;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;       // [A hi][A lo][B hi][B lo]

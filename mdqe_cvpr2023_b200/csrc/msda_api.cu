@@ -50,6 +50,7 @@ static std::atomic<int>* find_option(const char* key) {
   if (!strcmp(key, "mask_debug")) return &g_opt.mask_debug;
   if (!strcmp(key, "host_async")) return &g_opt.host_async;
   if (!strcmp(key, "consumer_ctas")) return &g_opt.consumer_ctas;
+  if (!strcmp(key, "consumer_tc")) return &g_opt.consumer_tc;
   if (!strcmp(key, "bwd_merge")) return &g_opt.bwd_merge;
   if (!strcmp(key, "pair_map")) return &g_opt.pair_map;
   if (!strcmp(key, "pdl")) return &g_opt.pdl;
@@ -136,6 +137,45 @@ MSDA_LAUNCH_EXTERN(extern, double, double, double)
 using namespace msda;
 
 // ===================================================================================== public ABI
+// column sums of grad_y: thread = (4 columns, one of 4 row phases); rows are split across CTAs, partial sums meet in grad_bias
+__global__ void __launch_bounds__(256) linear_bias_grad_kernel(const float* __restrict__ gy, int64_t rows, int out_f, int64_t rows_per_cta,
+                                                                float* __restrict__ gb) {
+  __shared__ float4 s_part[4][64];
+  const int c4 = blockIdx.y * 64 + (threadIdx.x & 63), phase = threadIdx.x >> 6;
+  const bool col_ok = c4 * 4 < out_f;
+  const int64_t r_begin = blockIdx.x * rows_per_cta, r_end = min(rows, r_begin + rows_per_cta);
+  float4 acc[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col_ok) {
+    const float4* base = reinterpret_cast<const float4*>(gy) + c4;
+    const int64_t stride4 = out_f / 4;
+    for (int64_t r = r_begin + phase; r < r_end; r += 16) {             // four independent loads in flight per thread
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t rr = r + 4 * u;
+        if (rr < r_end) {
+          const float4 v = __ldg(base + rr * stride4);
+          acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+        }
+      }
+    }
+  }
+  float4 a = make_float4((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y),
+                         (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z), (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w));
+  s_part[phase][threadIdx.x & 63] = a;
+  __syncthreads();
+  if (phase == 0 && col_ok) {
+    const int c = threadIdx.x & 63;
+    const float4 b1 = s_part[1][c], b2 = s_part[2][c], b3 = s_part[3][c];
+    float* dst = gb + 4 * c4;
+    atomicAdd(dst + 0, (a.x + b1.x) + (b2.x + b3.x));
+    atomicAdd(dst + 1, (a.y + b1.y) + (b2.y + b3.y));
+    atomicAdd(dst + 2, (a.z + b1.z) + (b2.z + b3.z));
+    atomicAdd(dst + 3, (a.w + b1.w) + (b2.w + b3.w));
+  }
+}
+
 extern "C" {
 
 int msda_abi_version(void) { return MSDA_B200_ABI_VERSION; }
@@ -389,6 +429,23 @@ int tc_linear_forward(void* stream, const void* x, const void* weight, const voi
   if (rows < 0 || in_features <= 0 || out_features <= 0) return fail(MSDA_ERR_INVALID_ARG, "tc_linear_forward: bad sizes");
   if (rows > 0 && (!x || !weight || !y)) return fail(MSDA_ERR_INVALID_ARG, "tc_linear_forward: NULL tensor");
   return linear_forward_dispatch(static_cast<cudaStream_t>(stream), x, weight, bias, row_mask, rows, in_features, out_features, y);
+}
+
+int tc_linear_bias_grad(void* stream, const void* grad_y, int64_t rows, int out_features, void* grad_bias) {
+  if (rows < 0 || out_features <= 0 || !grad_bias || (rows > 0 && !grad_y)) return fail(MSDA_ERR_INVALID_ARG, "tc_linear_bias_grad: bad arguments");
+  if (out_features % 4 != 0 || (reinterpret_cast<uintptr_t>(grad_y) & 15u))
+    return fail(MSDA_ERR_UNSUPPORTED, "tc_linear_bias_grad: out_features must be a multiple of 4 and grad_y 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = check_cuda(cudaMemsetAsync(grad_bias, 0, static_cast<size_t>(out_features) * sizeof(float), st), "cudaMemsetAsync(grad_bias)")) return rc;
+  if (rows == 0) return 0;
+  const int col_blocks = (out_features / 4 + 63) / 64;
+  int64_t ctas = (2LL * sm_count() + col_blocks - 1) / col_blocks;        // ~2 CTAs per SM in total
+  if (ctas > (rows + 15) / 16) ctas = (rows + 15) / 16;
+  if (ctas < 1) ctas = 1;
+  const int64_t rows_per_cta = (rows + ctas - 1) / ctas;
+  linear_bias_grad_kernel<<<dim3(static_cast<unsigned>(ctas), col_blocks), 256, 0, st>>>(static_cast<const float*>(grad_y), rows, out_features,
+                                                                                         rows_per_cta, static_cast<float*>(grad_bias));
+  return after_launch("linear_bias_grad_kernel");
 }
 
 int tc_linear_backward(void* stream, const void* grad_y, const void* x, const void* weight, int64_t rows, int in_features,

@@ -38,6 +38,7 @@ struct Options {
   std::atomic<int> mask_debug{0};     // 1 = the tcgen05 mask kernel records per-item clock stamps of CTA 0
   std::atomic<int> host_async{0};     // 1 = the *_host entries only enqueue; msda_host_sync() completes them
   std::atomic<int> profile{0};        // 1 = bracket the main kernels with CUDA events (msda_profile_read)
+  std::atomic<int> consumer_tc{0};    // matcher mask costs: 0 = auto (tensor-core kernel when eligible), 1 = SIMT kernel, 2 = require the tensor-core kernel
   std::atomic<int> consumer_ctas{0};  // > 0: CTAs of the matcher-cost / IoU kernels (tuning; 0 = auto)
   std::atomic<int> pdl{1};            // 1 = launch the sampling kernels with programmatic stream serialization (see msda_launch.cuh)
   std::atomic<int> pair_map{0};       // order in which a CTA of the fast2 sampling kernels walks its pairs: 0 = auto, 1 = linear (chunk / M queries x all heads), 2 = head-run (one head x chunk queries; PairMap in msda_fast2.cuh)
@@ -68,6 +69,11 @@ int mask_forward_dispatch(cudaStream_t stream, int in_dtype, int out_dtype, cons
                           int B, int Q, int K, int64_t Ncols, void* out);
 int mask_backward_dispatch(cudaStream_t stream, int dtype, const void* coeff, const void* proto, const void* grad_out,
                            int B, int Q, int K, int64_t Ncols, void* grad_coeff, void* grad_proto);
+
+size_t match_cost_tc_workspace_floats();
+bool match_cost_tc_eligible(const void* coeff, const void* proto, const void* tgt, int K, int64_t Ncols);
+int match_cost_tc_dispatch(cudaStream_t stream, const float* coeff, const float* proto, const float* tgt, int Q, int K, int G, int64_t Ncols,
+                           float* ws, float* cost_bce, float* cost_dice, int ld);
 
 int linear_forward_dispatch(cudaStream_t stream, const void* x, const void* w, const void* bias, const unsigned char* row_mask,
                             int64_t rows, int in_f, int out_f, void* y);

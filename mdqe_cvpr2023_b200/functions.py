@@ -179,7 +179,7 @@ class _TcLinearFunction(Function):
         if row_mask is not None:
             grad_y = grad_y.masked_fill(row_mask.unsqueeze(-1), 0.0)
         gx, gw = ops.tc_linear_backward(grad_y, x, weight, need_x=ctx.needs_input_grad[0], need_weight=ctx.needs_input_grad[1])
-        gb = grad_y.reshape(-1, grad_y.shape[-1]).sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        gb = ops.tc_linear_bias_grad(grad_y) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return gx, gw, gb, None
 
 

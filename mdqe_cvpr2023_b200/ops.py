@@ -366,6 +366,21 @@ def tc_linear_forward(x, weight, bias=None, row_mask=None):
     return y
 
 
+def tc_linear_bias_grad(grad_y):
+    """grad_bias = grad_y.reshape(-1, out_features).sum(0) in one pass at memory speed (csrc/msda_api.cu linear_bias_grad_kernel)."""
+    who = "tc_linear_bias_grad"
+    _check_inputs(who, [("grad_y", grad_y)])
+    out_f = grad_y.shape[-1]
+    rows = grad_y.numel() // max(out_f, 1)
+    if out_f % 4 != 0 or grad_y.data_ptr() % 16 != 0 or grad_y.dtype != torch.float32:
+        return grad_y.reshape(-1, out_f).sum(0)
+    with torch.cuda.device(grad_y.device):
+        gb = torch.empty(out_f, dtype=torch.float32, device=grad_y.device)
+        rc = _lib.load().tc_linear_bias_grad(_stream_ptr(grad_y.device), grad_y.data_ptr(), rows, out_f, gb.data_ptr())
+    _lib.check(rc, who)
+    return gb
+
+
 def tc_linear_backward(grad_y, x, weight, need_x=True, need_weight=True):
     """(grad_x, grad_weight) of y = x @ weight.T; grad_y must already carry the row mask (masked rows zero)."""
     who = "tc_linear_backward"

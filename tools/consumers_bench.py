@@ -109,8 +109,12 @@ for tag, (T, H, W) in {"360p": (4, 96, 160), "720p": (4, 160, 288)}.items():
     proto = torch.randn(K, T, H, W, generator=g).cuda()
     tgt = (torch.rand(G, T, H, W, generator=g) > 0.8).float().cuda()
     N = T * H * W
+    from mdqe_cvpr2023_b200 import _lib
+    _lib.set_option("consumer_tc", 1)
+    simt = timed(lambda: pkg.mask_match_cost(coeff, proto, tgt))
+    _lib.set_option("consumer_tc", 0)
     ours, ref = timed(lambda: pkg.mask_match_cost(coeff, proto, tgt)), timed(lambda: ref_match_cost(coeff, proto, tgt))
-    res[f"match_cost_{tag}"] = {"ours_us": ours, "torch_ops_us": ref, "algorithmic_MB": 4e-6 * (Q * K + K * N + G * N + 2 * Q * G),
+    res[f"match_cost_{tag}"] = {"ours_us": ours, "simt_kernel_us": simt, "torch_ops_us": ref, "algorithmic_MB": 4e-6 * (Q * K + K * N + G * N + 2 * Q * G),
                                 "GBps": 4e-3 * (Q * K + K * N + G * N + 2 * Q * G) / ours, "Q": Q, "G": G, "N": N}
     idx = torch.randperm(Q, generator=g)[:G].cuda()
     ti = (torch.rand(G, T, H, W, generator=g) > 0.6).float().cuda()
