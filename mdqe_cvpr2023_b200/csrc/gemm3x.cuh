@@ -71,11 +71,20 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   const uint32_t tmem_base = s_tmem_base;
 
   // item -> (split, row tile, column tile); column tiles of one row tile are neighbours so that A is re-read from L2
+  const float inv_tiles_n = 1.f / static_cast<float>(tiles_n), inv_tiles_m = 1.f / static_cast<float>(tiles_m);
+  const bool small_items = n_items < (1 << 23);
   auto decode = [&](int item, int& split, int& tm, int& tn) {
-    tn = item % tiles_n;
-    const int r = item / tiles_n;
-    tm = r % tiles_m;
-    split = r / tiles_m;
+    if (small_items) {
+      const int r = fast_div_small(item, tiles_n, inv_tiles_n);
+      tn = item - r * tiles_n;
+      split = fast_div_small(r, tiles_m, inv_tiles_m);
+      tm = r - split * tiles_m;
+    } else {
+      tn = item % tiles_n;
+      const int r = item / tiles_n;
+      tm = r % tiles_m;
+      split = r / tiles_m;
+    }
   };
   auto chunk_range = [&](int split, int& c0, int& c1) {
     c0 = split * chunks_per_split;

@@ -34,6 +34,17 @@ constexpr int kTcTileN = 128;        // plane columns per CTA (= MMA M)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// t / n for 0 <= t < 2^23, n > 0, inv_n = 1.f / n: a multiply and two corrections instead of the ~40-instruction integer
+// division sequence.  The persistent kernels decode one work item per ~1500 cycles in every role, and the three dependent
+// divisions of `decode` sat on the epilogue warps' critical path (clock stamps: ~450 idle cycles between two items,
+// profiles/r02_mask_kernels.md).
+__device__ __forceinline__ int fast_div_small(int t, int n, float inv_n) {
+  int q = __float2int_rz(static_cast<float>(t) * inv_n);
+  q -= (q * n > t) ? 1 : 0;
+  q += ((q + 1) * n <= t) ? 1 : 0;
+  return q;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -95,6 +106,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// the same load without the wait: several can be in flight before one tcgen05.wait::ld
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_nocommit(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -195,12 +223,21 @@ mask_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_
   const uint32_t tmem_base = s_tmem_base;
 
   // items are ordered chunk-major (all tiles of chunk 0, then chunk 1, ...): neighbouring CTAs share `coeff` rows
+  const int per_chunk = n_items / n_qchunks;
+  const float inv_per_chunk = 1.f / static_cast<float>(per_chunk), inv_tiles_n = 1.f / static_cast<float>(n_tiles_n);
+  const bool small_items = n_items < (1 << 23);
   auto decode = [&](int item, int& b, int& tile, int& qc) {
-    const int per_chunk = n_items / n_qchunks;
-    qc = item / per_chunk;
-    const int t = item - qc * per_chunk;
-    tile = t % n_tiles_n;
-    b = t / n_tiles_n;
+    if (small_items) {
+      qc = fast_div_small(item, per_chunk, inv_per_chunk);
+      const int t = item - qc * per_chunk;
+      b = fast_div_small(t, n_tiles_n, inv_tiles_n);
+      tile = t - b * n_tiles_n;
+    } else {
+      qc = item / per_chunk;
+      const int t = item - qc * per_chunk;
+      tile = t % n_tiles_n;
+      b = t / n_tiles_n;
+    }
   };
 
   if (warp == 0) {
@@ -246,8 +283,8 @@ mask_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_
     // epilogue: two independent groups ("halves") of four warps; a group owns alternate 32-row chunks of an item
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     const bool is_issuer = ((warp - 2) & 3) == 0 && lane == 0;    // first warp of each group
-    OT* my_stage = reinterpret_cast<OT*>(out_stage + (half * 2) * kOutBuf);
-    uint32_t use = 0;                                               // chunks this group has staged so far
+    OT* my_stage = reinterpret_cast<OT*>(out_stage + (half * (sizeof(OT) == 2 ? 4 : 2)) * kOutBuf);
+    uint32_t use = 0;                                               // passes this group has staged so far
     int i = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
       const int a = i & 1;
@@ -260,6 +297,35 @@ mask_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_
       if (dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 16) dbg[3 * 16 + i] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t lane_base = tmem_base + a * 256u + (static_cast<uint32_t>(quarter * 32) << 16);
+      if constexpr (sizeof(OT) == 2) {
+        // 16-bit outputs: a group stages TWO 32-row chunks per pass (buffers of 8 KB: four per group, two passes in flight), so an
+        // item of <= 128 rows costs each group one pair of barriers, one TMEM wait and one proxy fence instead of two of each
+        // (clock stamps before / after: profiles/r02_mask_kernels.md)
+        for (int q0 = half * 32; q0 < rows; q0 += 128, ++use) {
+          OT* buf0 = my_stage + (use & 1) * (2 * 32 * kTcTileN);
+          OT* buf1 = buf0 + 32 * kTcTileN;
+          const bool two = q0 + 64 < rows;
+          if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // the pass before the previous one has been read
+          named_bar_sync(1 + half, 128);
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(lane_base + static_cast<uint32_t>(q0), r0);
+          if (two) tmem_ld32_nowait(lane_base + static_cast<uint32_t>(q0 + 64), r1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) st_stage(buf0 + j * kTcTileN + quarter * 32 + lane, __uint_as_float(r0[j]));
+          if (two) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) st_stage(buf1 + j * kTcTileN + quarter * 32 + lane, __uint_as_float(r1[j]));
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          named_bar_sync(1 + half, 128);
+          if (is_issuer) {
+            tma_store_3d_nocommit(&map_out, smem_u32(buf0), tile * kTcTileN, q_begin + q0, b);
+            if (two) tma_store_3d_nocommit(&map_out, smem_u32(buf1), tile * kTcTileN, q_begin + q0 + 64, b);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else {
       for (int q0 = half * 32; q0 < rows; q0 += 64, ++use) {
         OT* buf = my_stage + (use & 1) * (32 * kTcTileN);
         // the bulk store that last read this buffer (two chunks ago) must have drained it
@@ -272,6 +338,7 @@ mask_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_proto, const __grid_
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         named_bar_sync(1 + half, 128);
         if (is_issuer) tma_store_3d(&map_out, smem_u32(buf), tile * kTcTileN, q_begin + q0, b);
+      }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -307,7 +374,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint
 
 inline size_t mask_tc2_smem_bytes(int KP, int QN, size_t out_elem) {
   const size_t stage = (2 * static_cast<size_t>(KP) * 128 + static_cast<size_t>(QN) * 128 + 1023) & ~size_t(1023);
-  return 1024 + kTc2Stages * stage + 4 * 32 * kTcTileN * out_elem;
+  return 1024 + kTc2Stages * stage + (out_elem == 2 ? 8 : 4) * 32 * kTcTileN * out_elem;      // 16-bit outputs: two chunks per pass
 }
 
 }  // namespace msda

@@ -78,12 +78,21 @@ mask_fwd_tc4_kernel(const __grid_constant__ CUtensorMap map_plane, const __grid_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = s_tmem_base;
 
+  const int per_chunk = n_items / n_qchunks;
+  const float inv_per_chunk = 1.f / static_cast<float>(per_chunk), inv_tiles_n = 1.f / static_cast<float>(n_tiles_n);
+  const bool small_items = n_items < (1 << 23);
   auto decode = [&](int item, int& b, int& tile, int& qc) {
-    const int per_chunk = n_items / n_qchunks;
-    qc = item / per_chunk;
-    const int t = item - qc * per_chunk;
-    tile = t % n_tiles_n;
-    b = t / n_tiles_n;
+    if (small_items) {
+      qc = fast_div_small(item, per_chunk, inv_per_chunk);
+      const int t = item - qc * per_chunk;
+      b = fast_div_small(t, n_tiles_n, inv_tiles_n);
+      tile = t - b * n_tiles_n;
+    } else {
+      qc = item / per_chunk;
+      const int t = item - qc * per_chunk;
+      tile = t % n_tiles_n;
+      b = t / n_tiles_n;
+    }
   };
 
   if (warp == 0) {
