@@ -34,10 +34,6 @@ class PeerAllReduce:
         self.numel = (int(numel) + 3) // 4 * 4
         self.n_ctas = int(n_ctas)
         self.device = torch.device(device)
-        try:                                         # older torch builds want the group registered first; newer ones deprecate it
-            symm.enable_symm_mem_for_group(group.group_name)
-        except Exception:  # noqa: BLE001
-            pass
         self.buffer = symm.empty(self.numel, dtype=torch.float32, device=self.device)
         self._flags = symm.empty(lib.msda_allreduce_flag_bytes(148) // 4, dtype=torch.int32, device=self.device)
         self.buffer.zero_()
@@ -97,3 +93,31 @@ def allreduce_mean_gradients_peer(parameters, ar):
             p.grad.copy_(piece)
         off += n
     return 1
+
+
+def make_ddp_comm_hook(ar):
+    """A `torch.nn.parallel.DistributedDataParallel` communication hook that averages every gradient bucket with the peer-memory
+    kernel instead of NCCL's all-reduce -- how the reference's training loop (detectron2 wraps the model in DDP, train_net.py:256-271)
+    picks the kernel up without any other change:
+
+        ar = PeerAllReduce(largest_bucket_elements, device)
+        ddp_model.register_comm_hook(None, make_ddp_comm_hook(ar))
+
+    The bucket is copied into the symmetric buffer, reduced in place and copied back, all on the current stream; the returned future
+    is already complete (its tensor carries the stream-ordered result, like DDP's own no-op hook pattern)."""
+    def hook(state, bucket):
+        t = bucket.buffer()
+        n = t.numel()
+        if t.dtype != torch.float32 or n > ar.numel:
+            raise RuntimeError(f"peer all-reduce hook: bucket of {n} {t.dtype} elements does not fit the fp32 buffer of {ar.numel}")
+        n4 = (n + 3) // 4 * 4
+        flat = t.reshape(-1)
+        ar.buffer[:n].copy_(flat)
+        if n4 > n:
+            ar.buffer[n:n4].zero_()
+        ar.all_reduce_(0, n4, mean=True)
+        flat.copy_(ar.buffer[:n])
+        fut = torch.futures.Future()
+        fut.set_result(t)
+        return fut
+    return hook

@@ -69,7 +69,7 @@ def _loss(stack, inp, w, dev):
     return sum((o * wi.to(dev)).sum() for o, wi in zip(outs, w))
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, mode="helper"):
     import torch.distributed as dist
     from mdqe_cvpr2023_b200.sharding import allreduce_mean_gradients, shard_bounds
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -82,8 +82,23 @@ def _worker(rank, world, port, ret):
         b0, b1 = shard_bounds(B, rank, world)
         assert b1 - b0 == 1
         ci, cw = _clip(inp, w, b0)
-        _loss(stack, ci, cw, dev).backward()
-        n_buckets = allreduce_mean_gradients(list(stack.parameters()))
+        if mode == "ddp_hook":
+            # torch DDP with this library's peer-memory all-reduce as its communication hook (collectives.make_ddp_comm_hook)
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            from mdqe_cvpr2023_b200.collectives import PeerAllReduce, make_ddp_comm_hook
+            n_param = sum(p.numel() for p in stack.parameters())
+            ar = PeerAllReduce(n_param, dev, n_ctas=4)
+            ddp = DDP(stack, device_ids=[rank], bucket_cap_mb=2)
+            ddp.register_comm_hook(None, make_ddp_comm_hook(ar))
+            moved = {k: (v.to(dev) if v is not None else None) for k, v in ci.items()}
+            outs = ddp(**moved)
+            sum((o * wi.to(dev)).sum() for o, wi in zip(outs, cw)).backward()
+            torch.cuda.synchronize()
+            ar.check()
+            n_buckets = 1
+        else:
+            _loss(stack, ci, cw, dev).backward()
+            n_buckets = allreduce_mean_gradients(list(stack.parameters()))
         torch.cuda.synchronize()
         if rank == 0:
             ret["ddp"] = {k: p.grad.detach().cpu() for k, p in stack.named_parameters()}
@@ -93,7 +108,8 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_two_rank_nccl_step_equals_one_rank_step_on_both_clips():
+@pytest.mark.parametrize("mode", ["helper", "ddp_hook"])
+def test_two_rank_nccl_step_equals_one_rank_step_on_both_clips(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
@@ -101,7 +117,7 @@ def test_two_rank_nccl_step_equals_one_rank_step_on_both_clips():
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret, mode)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
@@ -126,4 +142,4 @@ def test_two_rank_nccl_step_equals_one_rank_step_on_both_clips():
         # pixel-centre line may fall on the other side of it: DESIGN.md section 2); typical value 1e-6
         tol = 5e-3 if "offsets" in k else 5e-4
         assert rel <= tol, f"{k}: 2-rank NCCL gradient differs from the 1-rank gradient, rel L2 {rel:.2e}"
-    print(f"2-rank NCCL vs 1-rank CUDA: worst relative L2 over {len(ddp)} parameters = {worst:.2e}")
+    print(f"2-rank ({mode}) vs 1-rank CUDA: worst relative L2 over {len(ddp)} parameters = {worst:.2e}")
