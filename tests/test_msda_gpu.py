@@ -21,7 +21,7 @@ CORE = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "
 def _reset_options():
     from mdqe_cvpr2023_b200 import _lib
     yield
-    for k in ("fwd_variant", "bwd_variant", "chunk_pairs", "mask_variant"):
+    for k in ("fwd_variant", "bwd_variant", "chunk_pairs", "mask_variant", "pair_map"):
         _lib.set_option(k, 0)
     _lib.set_option("bwd_merge", 1)
 
@@ -118,6 +118,21 @@ def test_chunk_sizes(chunk):
     _lib.set_option("chunk_pairs", chunk)
     inp = make_inputs(2, [(12, 20), (6, 10), (3, 5), (2, 3)], 8, 32, 4, dist="local", seed=6)
     check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"chunk {chunk}", inp)
+
+
+@pytest.mark.parametrize("M,D,P,Lq,chunk", [(8, 32, 4, 203, 0), (8, 32, 4, 17, 48), (4, 32, 4, 131, 32), (6, 24, 4, 77, 16), (8, 32, 2, 333, 64),
+                                             (1, 32, 4, 50, 0), (8, 24, 3, 90, 0)])
+@pytest.mark.parametrize("pair_map", [1, 2])
+def test_pair_orders(M, D, P, Lq, chunk, pair_map):
+    """Both orders in which a CTA of the fast2 kernels walks its pairs (csrc/msda_fast2.cuh PairMap): linear (chunk / M queries x all
+    heads) and head-run (one head x chunk queries; the default of encoder-sized backward calls, forced here on small shapes).
+    Ragged ends everywhere: N * Lq not a multiple of the chunk, runs that straddle a batch element, head counts that do not divide
+    the chunk, L*P = 8 / 12 / 16, D = 24."""
+    from mdqe_cvpr2023_b200 import _lib
+    _lib.set_option("pair_map", pair_map)
+    _lib.set_option("chunk_pairs", chunk)
+    inp = make_inputs(3, [(12, 20), (6, 10), (3, 5), (2, 3)], M, D, P, Lq=Lq, dist="wide", seed=M * 100 + Lq)
+    check(run_op(to_cuda(inp)), oracle_all(inp), 2e-5, f"pair_map {pair_map} M={M} Lq={Lq}", inp, max_kink=1e-2)
 
 
 @pytest.mark.parametrize("P,case", [(4, "crowded"), (4, "identical"), (4, "border"), (2, "crowded"), (4, "one_cell")])
