@@ -94,6 +94,33 @@ def _worker(rank, world, port, q):
         ddp.zero_grad()
         ((ddp(x[b4:e4], ref[b4:e4], x[b4:e4], shapes) - tgt[b4:e4]) ** 2).sum().backward()
         ddp_grads = {k: p.grad.clone() for k, p in mod.named_parameters()}
+        # (d) the same under DDP with collectives.make_ddp_comm_hook: the hook's bucket plumbing (copy in, reduce a multiple of 4
+        # floats, copy back, completed future) on a stand-in for PeerAllReduce whose "kernel" is gloo's all_reduce -- the real
+        # kernel needs NVLink peers (tests/test_ddp_nccl_gpu.py[ddp_hook], tests/test_allreduce_gpu.py)
+        from mdqe_cvpr2023_b200.collectives import make_ddp_comm_hook
+
+        class GlooStandIn:
+            def __init__(self, numel):
+                self.numel = numel
+                self.buffer = torch.zeros(numel)
+                self.calls = 0
+
+            def all_reduce_(self, offset, numel, mean=True):
+                assert offset % 4 == 0 and numel % 4 == 0, "msda_allreduce_f32 takes multiples of 4 floats"
+                seg = self.buffer[offset:offset + numel]
+                dist.all_reduce(seg)
+                if mean:
+                    seg.div_(world)
+                self.calls += 1
+
+        stand_in = GlooStandIn(sum(p.numel() for p in mod.parameters()) + 8)
+        ddp2 = torch.nn.parallel.DistributedDataParallel(mod)
+        ddp2.register_comm_hook(None, make_ddp_comm_hook(stand_in))
+        ddp2.zero_grad()
+        ((ddp2(x[b4:e4], ref[b4:e4], x[b4:e4], shapes) - tgt[b4:e4]) ** 2).sum().backward()
+        assert stand_in.calls >= 1, "the hook did not run"
+        for k, p_ in mod.named_parameters():
+            assert torch.allclose(p_.grad, ddp_grads[k], atol=1e-6), f"comm hook: {k}"
         if rank == 0:
             # plain numpy through the queue (tensor fd-sharing does not survive the worker's exit)
             q.put(dict(full=full.numpy(), helper={k: v.numpy() for k, v in helper.items()},
