@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 4
+#define MSDA_B200_ABI_VERSION 5
 
 typedef enum {
   MSDA_OK = 0,
@@ -144,6 +144,22 @@ int msda_allreduce_max_ranks(void);
 size_t msda_allreduce_flag_bytes(int n_ctas);
 int msda_allreduce_f32(void* stream, int algo, int rank, int world, const uint64_t* peer_ptrs, uint64_t multicast_ptr,
                        const uint64_t* flag_ptrs, void* error_word, int64_t offset_elems, int64_t n_elems, float scale, int n_ctas);
+
+/* bf16 forward on a paired-corner value layout (north_star: bf16x2 loads of a value tensor re-laid per level).  The
+ * forward is bound by the number of 128-byte lines it gathers -- four per sample in the reference layout
+ * (ms_deform_im2col_cuda.cuh:33-84 reads the four corners of a sample from four rows), whatever the element size.  msda_pack_value
+ * re-lays value [N,S,M,32] (fp32 or bf16: what value_proj produces, ms_deform_attn.py:136) so that the two x-neighbours of a sample
+ * share one aligned 128-byte line of bf16; msda_forward_packed then gathers two lines per sample.  Same result as msda_forward
+ * with MSDA_BF16 / MSDA_BF16_LOC32 storage (value rounded to bf16, fp32 arithmetic, bf16 out).
+ *   packed : msda_packed_value_bytes(N,S,M,D) bytes, 16-byte aligned; 0 = shape not supported (D must be 32)
+ *   dtype of msda_pack_value     : storage type of `value` (MSDA_F32 or MSDA_BF16)
+ *   dtype of msda_forward_packed : MSDA_BF16 (loc / aw bf16) or MSDA_BF16_LOC32 (loc / aw fp32); out is bf16 [N,Lq,M*32]; L*P = 16
+ * shapes / level_start must be the ones the pack pass saw. */
+size_t msda_packed_value_bytes(int N, int S, int M, int D);
+int msda_pack_value(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                    int N, int S, int M, int D, int L, void* packed);
+int msda_forward_packed(void* stream, int dtype, const void* packed, const int64_t* shapes, const int64_t* level_start,
+                        const void* loc, const void* aw, int N, int S, int M, int D, int L, int Lq, int P, void* out);
 
 /* Fused sampler prologue (replaces the elementwise tail of MSDeformAttn.forward, ms_deform_attn.py:142-161):
  * the kernel takes what the module's Linear layers produce and computes softmax and sampling locations itself.

@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(PKG_DIR, "libmsda_b200.so")
 
 MSDA_F32, MSDA_BF16, MSDA_F64, MSDA_BF16_LOC32, MSDA_F16 = 0, 1, 2, 3, 4
-ABI_VERSION = 4
+ABI_VERSION = 5
 BWD_ACC_ZEROED = 1
 
 _c_int, _c_vp, _c_i64, _c_sz = ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t
@@ -73,6 +73,9 @@ PROTOTYPES = {
     "query_init_sample_forward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_vp]),
     "query_init_sample_backward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_int,
                                             _c_vp, _c_vp]),
+    "msda_packed_value_bytes": (_c_sz, [_c_int] * 4),
+    "msda_pack_value": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp] + [_c_int] * 5 + [_c_vp]),
+    "msda_forward_packed": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + _SEVEN + [_c_vp]),
     "msda_allreduce_max_ranks": (_c_int, []),
     "msda_allreduce_flag_bytes": (_c_sz, [_c_int]),
     "msda_allreduce_f32": (_c_int, [_c_vp, _c_int, _c_int, _c_int, ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint64,

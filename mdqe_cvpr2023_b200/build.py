@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(PKG_DIR, "_obj")
 LIB_PATH = os.path.join(PKG_DIR, "libmsda_b200.so")
 SOURCES = ["msda_api.cu", "msda_launch_f32.cu", "msda_launch_bf16.cu", "msda_launch_bf16_loc32.cu", "msda_launch_f64.cu",
-           "mask_gemm.cu", "consumers.cu", "allreduce.cu"]
+           "mask_gemm.cu", "consumers.cu", "allreduce.cu", "msda_packed.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMPILE_FLAGS = ARCH_FLAGS + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 NVCC_FLAGS = COMPILE_FLAGS + ["-shared"]          # one-shot form (tools/ build experiment libraries with it)

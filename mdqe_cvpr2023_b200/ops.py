@@ -84,6 +84,58 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     return out
 
 
+def packed_supported(value, n_levels, n_points, n_queries):
+    """True when the paired-corner bf16 forward (msda_pack_value + msda_forward_packed) implements this configuration."""
+    N, S, M, D = value.shape
+    return (value.is_cuda and D == 32 and n_levels * n_points == 16 and n_levels <= 32 and value.data_ptr() % 16 == 0
+            and N * 2 * S * M < 2 ** 32 and N * n_queries * M < 2 ** 31 // 64)
+
+
+def pack_value(value, spatial_shapes, level_start_index):
+    """value [N,S,M,32] (float32 or bfloat16) -> the paired-corner bf16 layout of csrc/msda_packed.cu (opaque uint8 tensor): the two
+    x-neighbours of a bilinear sample share one 128-byte line, so the sampler gathers two lines per sample instead of four."""
+    who = "pack_value"
+    _check_inputs(who, [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index)])
+    if value.dim() != 4 or value.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"{who}: value must be a float32 or bfloat16 [N,S,M,D] tensor")
+    N, S, M, D = value.shape
+    lib = _lib.load()
+    nbytes = lib.msda_packed_value_bytes(N, S, M, D)
+    if nbytes == 0:
+        raise RuntimeError(f"{who}: the paired-corner layout needs D = 32 (got {D})")
+    with torch.cuda.device(value.device):
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=value.device)
+        rc = lib.msda_pack_value(_stream_ptr(value.device), _lib.MSDA_F32 if value.dtype == torch.float32 else _lib.MSDA_BF16,
+                                 value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), N, S, M, D,
+                                 spatial_shapes.shape[0], packed.data_ptr())
+    _lib.check(rc, who)
+    return packed
+
+
+def ms_deform_attn_forward_packed(packed, value_shape, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+    """-> bfloat16 Tensor[N, Lq, M*32]: the forward on a tensor produced by ``pack_value`` (same shapes / level starts);
+    sampling_loc / attn_weight bfloat16 or float32."""
+    who = "ms_deform_attn_forward_packed"
+    _check_inputs(who, [("packed", packed), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                        ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)])
+    N, S, M, D = value_shape
+    if sampling_loc.dim() != 6 or attn_weight.dim() != 5 or sampling_loc.dtype != attn_weight.dtype or \
+            sampling_loc.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"{who}: sampling_loc [N,Lq,M,L,P,2] and attn_weight [N,Lq,M,L,P] must both be float32 or bfloat16")
+    _, Lq, _, L, P, _ = sampling_loc.shape
+    lib = _lib.load()
+    if packed.numel() * packed.element_size() < lib.msda_packed_value_bytes(N, S, M, D):
+        raise RuntimeError(f"{who}: packed tensor too small for value shape {tuple(value_shape)}")
+    code = _lib.MSDA_BF16 if sampling_loc.dtype == torch.bfloat16 else _lib.MSDA_BF16_LOC32
+    with torch.cuda.device(packed.device):
+        out = torch.empty((N, Lq, M * D), dtype=torch.bfloat16, device=packed.device)
+        rc = lib.msda_forward_packed(_stream_ptr(packed.device), code, packed.data_ptr(), spatial_shapes.data_ptr(),
+                                     level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                                     N, S, M, D, L, Lq, P, out.data_ptr())
+    _lib.check(rc, who)
+    return out
+
+
 def new_backward_accumulator(value):
     """Zero-filled tensor the backward accumulates grad_value into: grad_value itself (fp32 / fp64) or the fp32 workspace of
     the bf16 modes.  Allocate it early (MSDeformAttnFunction does so on a side stream during the forward pass) and hand it to

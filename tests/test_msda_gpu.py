@@ -718,3 +718,29 @@ def test_spatial_module_fused_prologue_equals_unfused(pred_offsets):
         bound = ref[..., 2:].view(B, Q, 1, 1, 1, 2) * 8
         frac = ((res <= -bound) | (res >= bound)).float().mean().item()
         assert 0.01 < frac < 0.99, frac
+
+
+@pytest.mark.parametrize("loc_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("N,pyr,M,Lq,dist,vdt", [(2, [(12, 20), (6, 10), (3, 5), (2, 3)], 8, None, "wide", torch.bfloat16),
+                                                  (3, [(7, 9), (5, 4), (1, 1), (2, 6)], 4, 77, "wide", torch.float32),
+                                                  (1, [(24, 40), (12, 20), (6, 10), (3, 5)], 8, 196, "local", torch.bfloat16),
+                                                  (4, R50_360, 8, None, "local", torch.float32)])
+def test_packed_bf16_forward(N, pyr, M, Lq, dist, vdt, loc_dtype):
+    """The bf16 forward on the paired-corner layout (csrc/msda_packed.cu: msda_pack_value + msda_forward_packed) against the oracle
+    on the bf16-rounded value (north_star: <= 2e-2 in bf16) and against the library's own bf16 kernel on the reference layout
+    (same inputs, fp32 arithmetic in both: they may differ by the summation order only, i.e. by one bf16 rounding of the output).
+    Samples outside the image on every side ("wide"), a 1x1 level, fp32 value packed directly (what value_proj produces)."""
+    from mdqe_cvpr2023_b200 import ops
+    inp = make_inputs(N, pyr, M, 32, 4, Lq=Lq, dist=dist, seed=N * 10 + M)
+    v_bf = inp["value"].bfloat16()
+    loc, aw = inp["loc"].to(loc_dtype), inp["aw"].to(loc_dtype)
+    dev = to_cuda(dict(value=inp["value"].to(vdt), shapes=inp["shapes"], level_start=inp["level_start"], loc=loc, aw=aw))
+    assert ops.packed_supported(dev["value"], len(pyr), 4, loc.shape[1])
+    packed = ops.pack_value(dev["value"], dev["shapes"], dev["level_start"])
+    out = ops.ms_deform_attn_forward_packed(packed, dev["value"].shape, dev["shapes"], dev["level_start"], dev["loc"], dev["aw"])
+    torch.cuda.synchronize()
+    ref_inp = dict(inp, value=v_bf.float(), loc=loc.float(), aw=aw.float())
+    want = oracle_all(ref_inp)[0]
+    assert nerr(out.float(), np.asarray(want).reshape(tuple(out.shape))) <= 2e-2
+    same = ops.ms_deform_attn_forward(v_bf.cuda(), dev["shapes"], dev["level_start"], dev["loc"], dev["aw"], 64)
+    assert nerr(out.float(), same.float()) <= 1.0 / 128, "more than one bf16 rounding away from the reference-layout bf16 kernel"
