@@ -587,15 +587,28 @@ def module_arm(torch, shape, device, steps, dist="local", world=1):
         x, qf, qc = forward()
         return torch.autograd.grad(x.sum() + qf.sum() + qc.sum(), [src, q_f, q_c] + params)
 
+    peer = None
+    if world > 1:
+        try:                                                   # this library's all-reduce over NVLink peer memory; NCCL if unavailable
+            from mdqe_cvpr2023_b200.collectives import PeerAllReduce
+            peer = PeerAllReduce(sum(p.numel() for p in params), device, n_ctas=16)
+        except Exception:  # noqa: BLE001
+            peer = None
+
     def ddp_step():
         # clip-sharded data parallel training (train_net.py:256-271): every rank runs its own clip, then the parameter gradients
-        # THIS step produced are averaged over the ranks (bucketed NCCL all-reduce, mdqe_cvpr2023_b200/sharding.py) -- all captured
+        # THIS step produced are averaged over the ranks -- by msda_allreduce_f32 (collectives.allreduce_mean_gradients_peer) or,
+        # where symmetric memory is unavailable, by the bucketed NCCL all-reduce of sharding.py -- all captured in one graph
+        from mdqe_cvpr2023_b200.collectives import allreduce_mean_gradients_peer
         from mdqe_cvpr2023_b200.sharding import allreduce_mean_gradients
         for p in params:
             p.grad = None
         x, qf, qc = forward()
         (x.sum() + qf.sum() + qc.sum()).backward()
-        allreduce_mean_gradients(params)
+        if peer is not None:
+            allreduce_mean_gradients_peer(params, peer)
+        else:
+            allreduce_mean_gradients(params)
 
     def infer_step():
         with torch.no_grad():
@@ -614,8 +627,12 @@ def module_arm(torch, shape, device, steps, dist="local", world=1):
         same = all(bool((t == sums[0]).all()) for t in sums)
         ddp = {"train_step_ms": ddp_ms, "aggregate_clips_per_s": world * 1e3 / ddp_ms, "grad_elements_reduced": int(flat.numel()),
                "grad_abs_sum": float(sums[0][1]), "grads_identical_on_all_ranks": same,
+               "allreduce": ("msda_allreduce_f32 (%s over NVLink peer memory)" % peer.algo) if peer is not None else "NCCL (sharding.allreduce_mean_gradients)",
                "what": "the same module step on every rank (own clip), then the parameter gradients it produced averaged over the ranks "
-                       "with the bucketed NCCL all-reduce of mdqe_cvpr2023_b200/sharding.py, all inside one captured CUDA graph"}
+                       "(one concatenation, one all-reduce kernel, one multi-tensor copy back), all inside one captured CUDA graph"}
+        if peer is not None:
+            torch.cuda.synchronize()
+            peer.check()
         del g_ddp
     train_ms = time_replays(torch, capture(torch, train_step), steps)
     infer_ms = time_replays(torch, capture(torch, infer_step), steps)

@@ -68,30 +68,27 @@ class PeerAllReduce:
 
 
 def allreduce_mean_gradients_peer(parameters, ar):
-    """DDP's gradient averaging with the peer-memory kernel: flatten every parameter's .grad (zeros where this rank produced
-    none) into ar.buffer, reduce, copy back.  Same collective on every rank, like sharding.allreduce_mean_gradients."""
+    """DDP's gradient averaging with the peer-memory kernel: every parameter's .grad (zeros where this rank produced none) is
+    gathered into ar.buffer with ONE concatenation kernel, reduced in place by msda_allreduce_f32, and scattered back with one
+    multi-tensor copy.  Same collective on every rank, like sharding.allreduce_mean_gradients; graph-capturable."""
     params = [p for p in parameters if p.requires_grad]
+    for p in params:
+        if p.dtype != torch.float32:
+            raise RuntimeError("allreduce_mean_gradients_peer: fp32 parameters only (the bucket is an fp32 symmetric buffer)")
     total = sum(p.numel() for p in params)
     if total > ar.numel:
         raise RuntimeError(f"bucket of {ar.numel} floats is too small for {total} gradient elements")
-    off = 0
     for p in params:
-        n = p.numel()
         if p.grad is None:
-            ar.buffer[off:off + n].zero_()
-        else:
-            ar.buffer[off:off + n].copy_(p.grad.reshape(-1))
-        off += n
-    ar.all_reduce_(0, (total + 3) // 4 * 4, mean=True)
-    off = 0
-    for p in params:
-        n = p.numel()
-        piece = ar.buffer[off:off + n].view_as(p)
-        if p.grad is None:
-            p.grad = piece.clone()
-        else:
-            p.grad.copy_(piece)
-        off += n
+            p.grad = torch.zeros_like(p)
+    n4 = (total + 3) // 4 * 4
+    flat = ar.buffer[:total]
+    torch.cat([p.grad.reshape(-1) for p in params], out=flat)
+    if n4 > total:
+        ar.buffer[total:n4].zero_()
+    ar.all_reduce_(0, n4, mean=True)
+    pieces = flat.split([p.numel() for p in params])
+    torch._foreach_copy_([p.grad.view(-1) for p in params], list(pieces))
     return 1
 
 

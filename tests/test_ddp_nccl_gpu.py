@@ -96,6 +96,14 @@ def _worker(rank, world, port, ret, mode="helper"):
             torch.cuda.synchronize()
             ar.check()
             n_buckets = 1
+        elif mode == "peer_helper":
+            # the bucketed helper's twin on the peer-memory kernel: one concatenation, msda_allreduce_f32, one multi-tensor copy back
+            from mdqe_cvpr2023_b200.collectives import PeerAllReduce, allreduce_mean_gradients_peer
+            ar = PeerAllReduce(sum(p.numel() for p in stack.parameters()), dev, n_ctas=8)
+            _loss(stack, ci, cw, dev).backward()
+            n_buckets = allreduce_mean_gradients_peer(list(stack.parameters()), ar)
+            torch.cuda.synchronize()
+            ar.check()
         else:
             _loss(stack, ci, cw, dev).backward()
             n_buckets = allreduce_mean_gradients(list(stack.parameters()))
@@ -108,7 +116,7 @@ def _worker(rank, world, port, ret, mode="helper"):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["helper", "ddp_hook"])
+@pytest.mark.parametrize("mode", ["helper", "peer_helper", "ddp_hook"])
 def test_two_rank_nccl_step_equals_one_rank_step_on_both_clips(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
