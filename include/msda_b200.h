@@ -297,7 +297,7 @@ int mask_losses_forward(void* stream, const void* coeff, const void* proto, cons
 int mask_losses_backward(void* stream, const void* coeff, const void* proto, const void* targets, const void* targets_interinst,
                          const void* row_stats, const void* grad_losses, int G, int K, int64_t Ncols, float num_masks,
                          void* grad_coeff, void* grad_proto);
-/* mask_nms_siou: soft-IoU matrix of inference_clip (mdqe/mdqe.py:386-394): mask_pred [Q,T,H,W] -> siou [Q,Q] with
+/* mask_nms_siou: soft-IoU matrix of inference_clip (mdqe/mdqe.py:394-401): mask_pred [Q,T,H,W] -> siou [Q,Q] with
  * mask_nms = mask_pred[:, ::2] if T >= 5, nearest 0.5x downsampling, soft = sigmoid, hard = soft > 0.5,
  * siou = soft.hard^T / (sum soft [:,None] + sum hard [None] - soft.hard^T + 1). */
 size_t mask_nms_siou_workspace_bytes(void);

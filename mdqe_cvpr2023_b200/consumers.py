@@ -4,7 +4,7 @@ operator itself there is no CPU or PyTorch fallback (CPU tensors raise RuntimeEr
 
   mask_match_cost(mask_coeff, proto, tgt_masks)          mdqe/models/matcher.py:182-197 (one clip)
   mask_losses(mask_coeff, proto, tgt, tgt_interinst, n)  mdqe/models/criterion.py:440-473 (one clip, autograd-capable)
-  mask_nms_siou(mask_pred)                               mdqe/mdqe.py:386-393
+  mask_nms_siou(mask_pred)                               mdqe/mdqe.py:394-401
   mask_track_siou(saved_masks, input_masks)              mdqe/tracking/OverTracker.py:92-113
   aligned_bilinear(tensor, factor, sigmoid=False)        mdqe/util/misc.py:485-507 (+ mdqe/mdqe.py:357)
   query_init_sample(encoded_feat, spatial_shapes, level_start_index, coords)
@@ -111,7 +111,7 @@ def mask_losses(mask_coeff, proto, tgt_masks, tgt_interinst_masks, num_masks):
 
 
 def mask_nms_siou(mask_pred):
-    """siou [Q,Q] of mdqe/mdqe.py:386-393 from mask_pred [Q,T,H,W] in one pass."""
+    """siou [Q,Q] of mdqe/mdqe.py:394-401 from mask_pred [Q,T,H,W] in one pass."""
     who = "mask_nms_siou"
     _f32(who, [("mask_pred", mask_pred)])
     if mask_pred.dim() != 4:

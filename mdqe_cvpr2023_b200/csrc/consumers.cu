@@ -5,7 +5,7 @@
 //                            (48 MB per clip at R50_ovis_360) is never written, proto and the targets are read once;
 //   mask_losses_*            mdqe/models/criterion.py:440-473: BCE + dice (plain or inter-instance) of the matched rows, forward and
 //                            backward, fused with the contraction of those rows;
-//   mask_nms_siou            mdqe/mdqe.py:386-399: soft-IoU matrix of inference_clip (frame stride 2 for clips of 5+ frames,
+//   mask_nms_siou            mdqe/mdqe.py:394-407: soft-IoU matrix of inference_clip (frame stride 2 for clips of 5+ frames,
 //                            nearest 0.5x downsampling, sigmoid, threshold, Q x Q product) in one pass over mask_pred;
 //   mask_track_siou          mdqe/tracking/OverTracker.py:92-113: hard-mask IoU between the tracker's memory and a new clip;
 //   aligned_bilinear_sigmoid mdqe/util/misc.py:485-507 + mdqe/mdqe.py:357: the 4x mask upsampling of the inference output;
@@ -412,7 +412,7 @@ nms_siou_kernel(const float* __restrict__ mask, const float* __restrict__ mask_b
         } else if (ok) {
           if (r < Qi) so = 1.f / (1.f + expf(-__ldg(mask + static_cast<int64_t>(i0 + r) * T * plane + src)));
           else if (r == Qi) so = 1.f;
-          // mask_soft.gt(0.5) on the fp32 sigmoid (mdqe.py:388-389), not logit > 0: they differ for tiny positive logits
+          // mask_soft.gt(0.5) on the fp32 sigmoid (mdqe.py:396), not logit > 0: they differ for tiny positive logits
           if (r < Qj) ha = (1.f / (1.f + expf(-__ldg(mask + static_cast<int64_t>(j0 + r) * T * plane + src)))) > 0.5f ? 1.f : 0.f;
           else if (r == Qj) ha = 1.f;
         }
@@ -462,8 +462,8 @@ __global__ void nms_siou_finalize_kernel(const float* __restrict__ ws, int i0, i
   if (idx >= Qi * Qj) return;
   const int i = idx / Qj, j = idx % Qj;
   const float num = ws[i * kSiMaxQ + j];
-  const float den = ws[i * kSiMaxQ + Qj] + ws[Qi * kSiMaxQ + j] - num;      // mdqe.py:392 / OverTracker.py:106-110
-  // eps = 1 (mdqe.py:393) or 1e-6 (OverTracker.py:111; its `saved_valid` factor only zeroes pairs whose numerator is 0 anyway)
+  const float den = ws[i * kSiMaxQ + Qj] + ws[Qi * kSiMaxQ + j] - num;      // mdqe.py:400 / OverTracker.py:106-110
+  // eps = 1 (mdqe.py:401) or 1e-6 (OverTracker.py:111; its `saved_valid` factor only zeroes pairs whose numerator is 0 anyway)
   siou[static_cast<int64_t>(i0 + i) * ld + j0 + j] = num / (den + eps);
 }
 
@@ -674,7 +674,7 @@ static int siou_launch(const char* who, cudaStream_t st, bool track, const float
                        void* workspace, float* siou) {
   if (int rc = ensure_func_attr(nms_siou_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSiSmem))) return rc;
   if (int rc = ensure_func_attr(nms_siou_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSiSmem))) return rc;
-  const int t_step = (!track && T >= 5) ? 2 : 1;                // mask_pred[:, ::2] if T >= 5 (mdqe.py:386)
+  const int t_step = (!track && T >= 5) ? 2 : 1;                // mask_pred[:, ::2] if T >= 5 (mdqe.py:394)
   const int T2 = (T + t_step - 1) / t_step, H2 = track ? H : H / 2, W2 = track ? W : W / 2;
   const int64_t N2 = static_cast<int64_t>(T2) * H2 * W2;
   const int64_t chunks = (N2 + kTC - 1) / kTC;

@@ -64,7 +64,7 @@ def mask_losses(coeff, proto, targets, targets_interinst, num_masks, grad_weight
 
 
 def nms_siou(mask_pred):
-    """mdqe/mdqe.py:386-393.  mask_pred [Q,T,H,W] -> siou [Q,Q]."""
+    """mdqe/mdqe.py:394-401.  mask_pred [Q,T,H,W] -> siou [Q,Q]."""
     m = np.asarray(mask_pred)
     nms = m[:, ::2] if m.shape[1] >= 5 else m                       # :386
     H2, W2 = nms.shape[2] // 2, nms.shape[3] // 2

@@ -13,8 +13,9 @@ packages so that mdqe/__init__.py -- detectron2 -- never runs):
                                    that the loss functions never call)
   * mdqe/tracking/OverTracker.py:92-113  OverTracker._get_siou (the module's `from detectron2.structures import Instances` is
                                    satisfied by an empty stand-in class; _get_siou never touches it)
-mdqe/mdqe.py (inference_clip, :386-394) and mdqe/models/transformer_dec.py (:170-179) sit inside classes that need detectron2 /
-a full model; their statements are executed here LITERALLY (same torch calls, same arguments), quoted next to each block.
+mdqe/mdqe.py (inference_clip, :386-393) and mdqe/models/transformer_dec.py (:167-179) sit inside methods of classes that need
+detectron2 / a full model to be constructed; the LINES THEMSELVES are read from the reference files at generation time and executed
+(`reference_source`), with the handful of local names they use bound here -- no statement of the reference is re-typed.
 """
 import os
 import sys
@@ -51,6 +52,17 @@ def import_reference():
     return matcher, misc, tracker, criterion
 
 
+def reference_source(relpath, first_marker, last_marker):
+    """the reference's own source text from the line containing `first_marker` to the line containing `last_marker`, dedented --
+    executed, never copied into the repo.  -> (source, first line number, last line number)"""
+    import textwrap
+    with open(os.path.join(REF, relpath)) as f:
+        lines = f.readlines()
+    first = next(i for i, l in enumerate(lines) if first_marker in l)
+    last = next(i for i, l in enumerate(lines) if last_marker in l and i >= first)
+    return textwrap.dedent("".join(lines[first:last + 1])), first + 1, last + 1
+
+
 def save(name, **arrays):
     conv = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in arrays.items()}
     path = os.path.join(HERE, name + ".npz")
@@ -72,15 +84,21 @@ def main():
         cost_dice = matcher.batch_dice_loss(out_masks, tgt)
         save(name, coeff=coeff[0], proto=proto[0], targets=tgt, cost_bce=cost_bce, cost_dice=cost_dice)
 
-    # ---- NMS soft IoU of inference_clip (mdqe/mdqe.py:386-394), statements copied as they are executed there
+    # ---- NMS soft IoU of inference_clip (mdqe/mdqe.py:394-401), statements copied as they are executed there
     for name, (Q, T, H, W) in {"nms_siou_T4": (23, 4, 12, 20), "nms_siou_T5": (9, 5, 11, 15)}.items():
         mask_pred = torch.randn(Q, T, H, W, generator=g) * 2 - 0.5
-        mask_nms = mask_pred[:, ::2] if mask_pred.shape[1] >= 5 else mask_pred                 # mdqe.py:386
-        mask_soft = F.interpolate(mask_nms, scale_factor=0.5).flatten(1).sigmoid()             # :387
-        mask_hard = mask_soft.gt(0.5).float()                                                  # :388
-        numerator = torch.mm(mask_soft, mask_hard.t())                                         # :391
-        denominator = mask_soft.sum(-1)[:, None] + mask_hard.sum(-1)[None] - numerator         # :392
-        siou = numerator / (denominator + 1)                                                   # :393
+        # mdqe/mdqe.py:394-401 run from the reference file itself (the lines between "# Just avoid running out of memory" and the
+        # siou matrix of MDQE.inference_clip); checked below against the statements typed out, which is what the first version of this
+        # script executed
+        src, l0, l1 = reference_source("mdqe/mdqe.py", "mask_nms = mask_pred[:, ::2]", "siou = numerator / (denominator + 1)")
+        assert (l0, l1) == (394, 401), f"reference lines moved: {l0}-{l1}"
+        env = {"torch": torch, "F": F, "mask_pred": mask_pred}
+        exec(compile(src, f"/root/reference/mdqe/mdqe.py:{l0}-{l1}", "exec"), env)
+        siou = env["siou"]
+        mask_soft = F.interpolate(mask_pred[:, ::2] if T >= 5 else mask_pred, scale_factor=0.5).flatten(1).sigmoid()
+        mask_hard = mask_soft.gt(0.5).float()
+        numerator = torch.mm(mask_soft, mask_hard.t())
+        assert torch.equal(siou, numerator / (mask_soft.sum(-1)[:, None] + mask_hard.sum(-1)[None] - numerator + 1))
         save(name, mask_pred=mask_pred, siou=siou)
 
     # ---- criterion mask losses of the matched queries (criterion.py:440, :467-473), inter-instance and plain forms
@@ -130,17 +148,16 @@ def main():
     encoded_feat = torch.randn(B, S, C, generator=g, dtype=torch.float64).requires_grad_(True)
     n_query_bins = 4
     query_init_coords = (torch.rand(B, n_query_bins * n_query_bins, 2, generator=g, dtype=torch.float64) * 1.1 - 0.05).requires_grad_(True)
-    query_init_coords_grid = rearrange(query_init_coords, 'B (h w) k -> B h w k', h=n_query_bins)      # :167
-    query_init_coords_grid = 2 * query_init_coords_grid - 1                                            # :170
-    query_init = []
-    for l, (H_l, W_l) in enumerate(spatial_shapes):                                                    # :172-178
-        query_init.append(F.grid_sample(rearrange(encoded_feat[:, lvl_start_index[l]:lvl_start_index[l + 1]],
-                                                  'B (H W) C -> B C H W', H=H_l),
-                                        query_init_coords_grid,
-                                        mode='bilinear',
-                                        padding_mode="border",
-                                        align_corners=False))
-    query_init = rearrange(torch.stack(query_init).mean(0), 'B C h w -> B (h w) C')                    # :179
+    # transformer_dec.py:167-179 run from the reference file itself: coordinates -> grid in [-1, 1], F.grid_sample per pyramid level
+    # (bilinear, border padding, align_corners=False), mean over the levels.  `self.n_query_bins` is the only attribute the lines touch.
+    src, l0, l1 = reference_source("mdqe/models/transformer_dec.py", "query_init_coords_grid = rearrange(query_init_coords",
+                                   "query_init = rearrange(torch.stack(query_init).mean(0)")
+    assert (l0, l1) == (167, 179) and "F.grid_sample" in src, f"reference lines moved: {l0}-{l1}"
+    env = {"torch": torch, "F": F, "rearrange": rearrange, "self": types.SimpleNamespace(n_query_bins=n_query_bins),
+           "query_init_coords": query_init_coords, "spatial_shapes": spatial_shapes, "encoded_feat": encoded_feat,
+           "lvl_start_index": lvl_start_index}
+    exec(compile(src, f"/root/reference/mdqe/models/transformer_dec.py:{l0}-{l1}", "exec"), env)
+    query_init = env["query_init"]
     grad_out = torch.randn(query_init.shape, generator=g, dtype=torch.float64)
     query_init.backward(grad_out)
     save("query_init_f64", feat=encoded_feat, shapes=torch.tensor(spatial_shapes), level_start=torch.tensor(lvl_start_index[:-1]),

@@ -130,7 +130,7 @@ def test_nms_siou_vs_reference_ops_on_gpu(pkg, Q, T, H, W):
     g = torch.Generator().manual_seed(Q + T)
     m = (torch.randn(Q, T, H, W, generator=g) * 2 - 0.3).cuda()
     got = pkg.mask_nms_siou(m)
-    nms = m[:, ::2] if T >= 5 else m                                                        # mdqe.py:386
+    nms = m[:, ::2] if T >= 5 else m                                                        # mdqe.py:394
     soft = torch.nn.functional.interpolate(nms, scale_factor=0.5).flatten(1).sigmoid()      # :387
     hard = soft.gt(0.5).double()
     soft = soft.double()

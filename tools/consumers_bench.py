@@ -41,7 +41,7 @@ def ref_match_cost(coeff, proto, tgt):                       # matcher.py:182, :
     return bce, dice
 
 
-def ref_siou(mask_pred):                                     # mdqe.py:386-393
+def ref_siou(mask_pred):                                     # mdqe.py:394-401
     mask_nms = mask_pred[:, ::2] if mask_pred.shape[1] >= 5 else mask_pred
     mask_soft = F.interpolate(mask_nms, scale_factor=0.5).flatten(1).sigmoid()
     mask_hard = mask_soft.gt(0.5).float()
