@@ -11,6 +11,7 @@
 #include "gemm3x.cuh"
 #include "match_cost_tc.cuh"
 #include "msda_internal.h"
+#include "msda_launch.cuh"
 
 namespace msda {
 
@@ -232,16 +233,16 @@ int match_cost_tc_dispatch(cudaStream_t st, const float* coeff, const float* pro
 #define MSDA_MT_LAUNCH(GPV)                                                                                                             \
     do {                                                                                                                                \
       if (int rc = ensure_func_attr(match_cost_tc_kernel<GPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMtSmemBytes))) return rc; \
-      match_cost_tc_kernel<GPV><<<ctas, kMtThreads, kMtSmemBytes, st>>>(map_plane, map_coeff, tgt, Q, G, Ncols, static_cast<int>(n_items), ws);       \
+      if (int rc = check_cuda(launch_kernel(match_cost_tc_kernel<GPV>, dim3(ctas), dim3(kMtThreads), kMtSmemBytes, st, map_plane, map_coeff, tgt, Q, G, Ncols, static_cast<int>(n_items), ws), "launch")) return rc; \
     } while (0)
     if (G <= 4) MSDA_MT_LAUNCH(4); else if (G <= 8) MSDA_MT_LAUNCH(8); else if (G <= 12) MSDA_MT_LAUNCH(12); else MSDA_MT_LAUNCH(16);
 #undef MSDA_MT_LAUNCH
   }
   if (int rc = after_launch("match_cost_tc_kernel")) return rc;
   float* total = ws + static_cast<size_t>(kMtMaxCtas) * kMtWsPerCta;
-  match_cost_tc_reduce_kernel<<<(kMtWsPerCta + 127) / 128, 128, 0, st>>>(ws, ctas, total);
+  if (int rc = check_cuda(launch_kernel(match_cost_tc_reduce_kernel, dim3((kMtWsPerCta + 127) / 128), dim3(128), 0, st, static_cast<const float*>(ws), ctas, total), "launch")) return rc;
   if (int rc = after_launch("match_cost_tc_reduce_kernel")) return rc;
-  match_cost_tc_finalize_kernel<<<(Q * G + 127) / 128, 128, 0, st>>>(total, coeff, Q, K, G, Ncols, ld, cost_bce, cost_dice);
+  if (int rc = check_cuda(launch_kernel(match_cost_tc_finalize_kernel, dim3((Q * G + 127) / 128), dim3(128), 0, st, static_cast<const float*>(total), coeff, Q, K, G, Ncols, ld, cost_bce, cost_dice), "launch")) return rc;
   return after_launch("match_cost_tc_finalize_kernel");
 }
 
@@ -396,7 +397,7 @@ static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const 
   return after_launch("gemm3x_kernel");
 }
 
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// aligned16(): msda_launch.cuh
 
 int linear_forward_dispatch(cudaStream_t st, const void* x, const void* w, const void* bias, const unsigned char* row_mask,
                             int64_t rows, int in_f, int out_f, void* y) {

@@ -19,6 +19,7 @@
 #pragma once
 
 #include "mask_tc4.cuh"
+#include "msda_common.cuh"
 
 namespace msda {
 
@@ -76,6 +77,8 @@ match_cost_tc_kernel(const __grid_constant__ CUtensorMap map_plane, const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int MT = Q > 128 ? 2 : 1;
+  pdl_wait();                                                 // programmatic dependent launch: see launch_kernel (msda_launch.cuh)
+  pdl_trigger();                                              // the two small kernels behind this one may be scheduled early; they wait
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMtStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_ready(s), kMtSplitWarps); mbar_init(bar_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), kMtEpiWarps); mbar_init(bar_tgt(a), kMtSplitWarps); }
@@ -300,6 +303,8 @@ match_cost_tc_kernel(const __grid_constant__ CUtensorMap map_plane, const __grid
 
 // add the per-CTA partial blocks into one (thread = one element of the block: coalesced, n_ctas independent loads)
 __global__ void match_cost_tc_reduce_kernel(const float* __restrict__ ws, int n_ctas, float* __restrict__ total) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kMtWsPerCta) return;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -317,6 +322,8 @@ __global__ void match_cost_tc_reduce_kernel(const float* __restrict__ ws, int n_
 // one thread per (query, target): form the two costs from the summed block
 __global__ void match_cost_tc_finalize_kernel(const float* __restrict__ total, const float* __restrict__ coeff, int Q, int K, int G,
                                               int64_t N, int ld, float* __restrict__ cost_bce, float* __restrict__ cost_dice) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Q * G) return;
   const int q = i / G, g = i % G;
