@@ -224,45 +224,6 @@ __device__ __forceinline__ void merge_level_slots(Slot (&sl)[4], uint32_t key, i
   for (int cn = 0; cn < 4; ++cn) sl[cn].w = ((kill >> cn) & 1u) ? 0.f : wsum[cn];
 }
 
-// Cross-pair merge (round 2 experiment, option bwd_merge = 2; head-run order only): with the head-run pair order the two pairs of a
-// warp round are the SAME head of two neighbouring queries, so a value row that both touch can take ONE reduction carrying
-// wA * go_A + wB * go_B.  After the in-pair merge every distinct row of a (pair, level) has exactly one owner record (weight != 0).
-// Lanes 0-15 (pair A) and 16-31 (pair B) of a level meet in four exchange steps (partner = lane ^ 16 ^ j): both sides receive the
-// other's cell and weights and shift them onto their own 2x2 footprint exactly as merge_level_slots does; an A owner adds B's weight
-// for the row to wB[corner], and B zeroes that weight -- both decide from the same exchanged data (A's weight for the row != 0), so a
-// row is absorbed exactly once.  20 shuffles per round.  Pairs from different batch elements never match (the caller gives B's
-// lanes a no-merge key then).
-__device__ __forceinline__ void cross_pair_merge(Slot (&sl)[4], float (&wB)[4], uint32_t key, int lane) {
-  const bool isA = lane < 16;
-  const int cx = static_cast<int>(key & 0xffffu), cy = static_cast<int>(key >> 16);
-#pragma unroll 1
-  for (int j = 0; j < 4; ++j) {
-    const int mask = 16 ^ j;
-    const uint32_t pk = __shfl_xor_sync(0xffffffffu, key, mask);
-    float pw[4];
-#pragma unroll
-    for (int cp = 0; cp < 4; ++cp) pw[cp] = __shfl_xor_sync(0xffffffffu, sl[cp].w, mask);
-    const int ex = static_cast<int>(pk & 0xffffu) - cx, ey = static_cast<int>(pk >> 16) - cy;
-    const bool x0 = ex == 0, xm = ex == -1, xp = ex == 1, y0 = ey == 0, ym = ey == -1, yp = ey == 1;
-    // partner's weight for the row of own corner (dx, dy); 0 where the footprints do not overlap
-    const float a00 = x0 ? pw[0] : (xm ? pw[1] : 0.f), a01 = x0 ? pw[1] : (xp ? pw[0] : 0.f);
-    const float a10 = x0 ? pw[2] : (xm ? pw[3] : 0.f), a11 = x0 ? pw[3] : (xp ? pw[2] : 0.f);
-    float m[4];
-    m[0] = y0 ? a00 : (ym ? a10 : 0.f);
-    m[1] = y0 ? a01 : (ym ? a11 : 0.f);
-    m[2] = y0 ? a10 : (yp ? a00 : 0.f);
-    m[3] = y0 ? a11 : (yp ? a01 : 0.f);
-#pragma unroll
-    for (int cn = 0; cn < 4; ++cn) {
-      if (isA) {
-        if (sl[cn].w != 0.f) wB[cn] += m[cn];          // this lane owns the row in pair A: it carries B's share as well
-      } else {
-        if (m[cn] != 0.f) sl[cn].w = 0.f;              // pair A owns the row (its owner's weight is what arrived): B drops its record
-      }
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------ forward
 #ifndef MSDA_PACKED_FMA
 #define MSDA_PACKED_FMA 1       // fma.rn.f32x2 (sm_100): two channels per FMA instruction
@@ -469,7 +430,7 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 #endif
 constexpr int kBwdBatch = MSDA_BWD_BATCH;    // gathers in flight per lane (see the corner loop)
 
-template <typename VT, typename LT, int D, int LP, bool GROUPED, bool XM = false>
+template <typename VT, typename LT, int D, int LP, bool GROUPED>
 __global__ void __launch_bounds__(kThreads, GROUPED ? MSDA_BWD_MINB_GROUPED : MSDA_BWD_MINB)
 msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                       const int64_t* __restrict__ level_start, const LT* __restrict__ loc,
@@ -488,7 +449,6 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
   __shared__ LevelInfo s_lvl[kMaxLevels];
   __shared__ __align__(16) Slot s_slot[kWarpsPerCta][C::QPW * C::NSLOT];
   __shared__ float s_dot[kWarpsPerCta][4 * kDotStride];
-  __shared__ float s_wb[XM ? kWarpsPerCta : 1][XM ? C::NSLOT : 1];       // XM: pair B's share of pair A's reductions, laid out like the slots
 
   pdl_wait();
   pdl_trigger();
@@ -565,18 +525,6 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
       }
       if (merge == 4) merge_level_slots<4>(sl, cell_key, lane);          // warp-uniform: P == 4 (or 2) and the option is on
       else if (merge == 2) merge_level_slots<2>(sl, cell_key, lane);
-      if constexpr (XM) {                                                // LP == 16, P == 4, two pairs of one head per round
-        float wB[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint32_t n_other = __shfl_xor_sync(0xffffffffu, n, 16);
-        uint32_t xkey = cell_key;
-        if (npair < 2 || n_other != n || (cell_key & 0xffff8000u) == kNoMergeKey) xkey = kNoMergeKey + 4u * static_cast<uint32_t>(lane & 3) + 64u * static_cast<uint32_t>(lane >> 4);
-        cross_pair_merge(sl, wB, xkey, lane);
-        if (lane < LP) {
-          float* wdst = s_wb[warp] + ss;
-#pragma unroll
-          for (int cn = 0; cn < 4; ++cn) wdst[cn * C::LPP] = wB[cn];
-        }
-      }
       if (has_sample) {
         Slot* dst = my_slots + ps * C::NSLOT + ss;
 #pragma unroll
@@ -610,17 +558,6 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
             }
           }
           const uint4* stream = reinterpret_cast<const uint4*>(my_stream + pl * C::NSLOT);
-          // XM: pair A's reductions also carry pair B's share of the rows both touch: wb * go_B
-          float goB[XM ? C::CPL : 1];
-          const float2* wb_stream = nullptr;
-          if constexpr (XM) {
-#pragma unroll
-            for (int j = 0; j < C::CPL; ++j) goB[j] = 0.f;
-            if (pl == 0) {
-              if (npair > 1) Vec16<VT>::load(grad_out + static_cast<int64_t>(pm.pair(p0 + 1)) * D + c * C::CPL, goB);
-              wb_stream = reinterpret_cast<const float2*>(s_wb[warp] + corner * C::LPP + sgrp * C::SPG);
-            }
-          }
           // Batches of kBwdBatch corner rows: all gathers of a batch are issued first (predicated, no branches), then the dot
           // products and the reductions (predicated).  The per-lane dot partials of kFold samples are then folded across the
           // G lanes of the corner group by a transposing butterfly (G - 1 shuffles for G samples instead of G log2 G), which
@@ -638,17 +575,11 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
             for (int b0 = f0; b0 < f0 + kFold; b0 += kB) {
               uint32_t off[kB];
               float w[kB];
-              float wb[XM ? kB : 1];
 #pragma unroll
               for (int i = 0; i < kB / 2; ++i) {
                 const uint4 two = stream[(b0 >> 1) + i];
                 off[2 * i] = two.x; w[2 * i] = __uint_as_float(two.y);
                 off[2 * i + 1] = two.z; w[2 * i + 1] = __uint_as_float(two.w);
-                if constexpr (XM) {
-                  float2 t2 = make_float2(0.f, 0.f);
-                  if (pl == 0) t2 = wb_stream[(b0 >> 1) + i];
-                  wb[2 * i] = t2.x; wb[2 * i + 1] = t2.y;
-                }
               }
               bool valid[kB];
               float v[kB][C::CPL];
@@ -680,13 +611,8 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
                   float* gv = const_cast<float*>(reinterpret_cast<const float*>(
                       reinterpret_cast<const char*>(gvlane) + static_cast<uint64_t>(off[u]) * (16u * sizeof(float) / sizeof(VT))));
 #pragma unroll
-                  for (int j = 0; j < C::CPL; j += 4) {
-                    if constexpr (XM)
-                      red_add_f32x4_if(do_red, gv + j, fmaf(wb[u], goB[j], w[u] * go[j]), fmaf(wb[u], goB[j + 1], w[u] * go[j + 1]),
-                                       fmaf(wb[u], goB[j + 2], w[u] * go[j + 2]), fmaf(wb[u], goB[j + 3], w[u] * go[j + 3]));
-                    else
-                      red_add_f32x4_if(do_red, gv + j, w[u] * go[j], w[u] * go[j + 1], w[u] * go[j + 2], w[u] * go[j + 3]);
-                  }
+                  for (int j = 0; j < C::CPL; j += 4)
+                    red_add_f32x4_if(do_red, gv + j, w[u] * go[j], w[u] * go[j + 1], w[u] * go[j + 2], w[u] * go[j + 3]);
                 }
               }
             }

@@ -155,16 +155,6 @@ inline void launch_bwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int ch
       v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz, merge, hrun); } while (0)
   const bool grouped = pb.G > 1 || pb.scale != 1.f;
   const int merge = (options().bwd_merge.load() != 0 && (pb.P == 4 || pb.P == 2)) ? pb.P : 0;
-  // bwd_merge = 2: additionally merge the reductions of the two pairs of a warp round (cross_pair_merge; A/B experiment) -- plain
-  // fp32 operator, D = 32, L*P = 16 with P = 4, head-run order, no fused prologue
-  if constexpr (std::is_same<VT, float>::value && std::is_same<LT, float>::value && D == 32) {
-    if (options().bwd_merge.load() == 2 && hrun && !grouped && pb.P == 4 && pb.L * pb.P == 16 && pb.fz.ref == nullptr) {
-      prefer_small_carveout(msda_bwd_fast2_kernel<VT, LT, D, 16, false, true>, MSDA_BWD_MINB);
-      launch_kernel(msda_bwd_fast2_kernel<VT, LT, D, 16, false, true>, grid, dim3(kThreads), 0, st,
-                    v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz, merge, hrun);
-      return;
-    }
-  }
   switch (pb.L * pb.P) {
     case 16: if (grouped) MSDA_BWD2(16, true); else MSDA_BWD2(16, false); break;
     case 12: if (grouped) MSDA_BWD2(12, true); else MSDA_BWD2(12, false); break;

@@ -744,25 +744,3 @@ def test_packed_bf16_forward(N, pyr, M, Lq, dist, vdt, loc_dtype):
     assert nerr(out.float(), np.asarray(want).reshape(tuple(out.shape))) <= 2e-2
     same = ops.ms_deform_attn_forward(v_bf.cuda(), dev["shapes"], dev["level_start"], dev["loc"], dev["aw"], 64)
     assert nerr(out.float(), same.float()) <= 1.0 / 128, "more than one bf16 rounding away from the reference-layout bf16 kernel"
-
-
-@pytest.mark.parametrize("N,pyr,Lq,dist,chunk", [(2, [(12, 20), (6, 10), (3, 5), (2, 3)], None, "local", 0), (3, [(12, 20), (6, 10), (3, 5), (2, 3)], 77, "wide", 48),
-                                                 (2, [(6, 10), (3, 5), (1, 1), (2, 3)], 33, "local", 16), (1, [(24, 40), (12, 20), (6, 10), (3, 5)], None, "local", 0)])
-def test_backward_cross_pair_merge(N, pyr, Lq, dist, chunk):
-    """Option bwd_merge = 2 (csrc/msda_fast2.cuh cross_pair_merge): in the head-run order the two pairs of a warp round are one head
-    of two neighbouring queries, and value rows both touch take ONE reduction carrying wA*go_A + wB*go_B.  Against the oracle and
-    against the in-pair merge: odd query counts (a round whose second pair is missing), runs that straddle batch elements (pairs
-    of different n must never merge), a 1x1 level where everything merges, samples outside the image."""
-    from mdqe_cvpr2023_b200 import _lib
-    inp = make_inputs(N, pyr, 8, 32, 4, Lq=Lq, dist=dist, seed=N * 7 + (Lq or 0))
-    want = oracle_all(inp)
-    dev = to_cuda(inp)
-    _lib.set_option("pair_map", 2)
-    _lib.set_option("chunk_pairs", chunk)
-    _lib.set_option("bwd_merge", 1)
-    base = run_op(dev)
-    _lib.set_option("bwd_merge", 2)
-    got = run_op(dev)
-    check(got, want, 2e-5, "cross-pair merge", inp, max_kink=1e-2)
-    for a, b, name in zip(got, base, ("out", "grad_value", "grad_loc", "grad_aw")):
-        assert nerr(a, b) <= 2e-6, f"{name}: differs from the in-pair merge"
