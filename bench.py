@@ -1027,6 +1027,30 @@ def main():
         except Exception as e:  # noqa: BLE001
             modarm = {"error": repr(e)[:300]}
 
+    # ---- inference window of the reference: the encoder sees a window of up to 30 frames at once
+    if other is not None and args.shape == "r50_360":
+        try:
+            Nw, Sw = 30, sum(h * w for h, w in PYRAMID)
+            gw = torch.Generator(device=device).manual_seed(7)
+            vw = torch.randn(Nw, Sw, HEADS, HEAD_DIM, device=device, generator=gw)
+            refw = ref_points(torch, PYRAMID, device)
+            locw = (refw.view(1, Sw, 1, 1, 1, 2) + 0.05 * torch.randn(Nw, Sw, HEADS, len(PYRAMID), POINTS, 2, device=device, generator=gw)).clamp_(-0.1, 1.1)
+            aww = torch.softmax(torch.randn(Nw, Sw, HEADS, len(PYRAMID) * POINTS, device=device, generator=gw), -1)
+            shw = torch.tensor(PYRAMID, device=device)
+            lsw = torch.cat([shw.new_zeros(1), (shw[:, 0] * shw[:, 1]).cumsum(0)[:-1]])
+            outw = torch.empty(Nw, Sw, HEADS * HEAD_DIM, device=device)
+            stw = torch.cuda.current_stream(device).cuda_stream
+            run_w = lambda: libmod.check(lib.msda_forward(stw, libmod.MSDA_F32, vw.data_ptr(), shw.data_ptr(), lsw.data_ptr(), locw.data_ptr(),
+                                                          aww.data_ptr(), Nw, Sw, HEADS, HEAD_DIM, len(PYRAMID), Sw, POINTS, outw.data_ptr()), "msda_forward")
+            w_ms = time_replays(torch, capture(torch, run_w), n_other)
+            bytes_w = 4 * (vw.numel() + locw.numel() + aww.numel() + outw.numel())
+            other["R50_ovis_360_encoder_window30_fwd"] = {"what": "one encoder MSDeformAttn forward over the reference's 30-frame inference window (N=30, S=Lq=5100)",
+                                                         "us": w_ms * 1e3, "frames_per_s": Nw / (w_ms * 1e-3), "algorithmic_bytes": bytes_w,
+                                                         "frac_of_hbm_peak": bytes_w / (w_ms * 1e-3) / 1e9 / hbm_peak}
+            del vw, locw, aww, outw
+        except Exception as e:  # noqa: BLE001
+            other["R50_ovis_360_encoder_window30_fwd"] = {"error": repr(e)[:300]}
+
     # ---- CPU baseline (rank 0, single-GPU runs only): the reference's CPU path restated in torch
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

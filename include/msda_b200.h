@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 5
+#define MSDA_B200_ABI_VERSION 6
 
 typedef enum {
   MSDA_OK = 0,
@@ -225,6 +225,12 @@ int tc_linear_backward(void* stream, const void* grad_y, const void* x, const vo
 /* grad_bias[o] = sum_r grad_y[r, o] (nn.Linear's bias gradient; torch's strided sum(0) costs 28 us per encoder-sized call, this
  * streams grad_y once at memory speed).  grad_bias is zero-filled inside; out_features a multiple of 4. */
 int tc_linear_bias_grad(void* stream, const void* grad_y, int64_t rows, int out_features, void* grad_bias);
+/* tc_linear_backward with the bias gradient in the same call (grad_bias [out_features] or NULL, zero-filled inside).  When
+ * grad_weight is requested the column sums of grad_y are taken inside the weight-gradient GEMM by the warps that stage grad_y
+ * for the tensor cores (no extra pass over grad_y, no extra launch; accumulated with atomics across the CTAs of the split
+ * reduction); otherwise this is tc_linear_backward followed by tc_linear_bias_grad. */
+int tc_linear_backward_bias(void* stream, const void* grad_y, const void* x, const void* weight,
+                            int64_t rows, int in_features, int out_features, void* grad_x, void* grad_weight, void* grad_bias);
 
 /* Host-buffer entries: same semantics, every pointer is HOST memory (pinned memory makes the
  * copies asynchronous).  The library owns a grow-only device arena per process; `device` selects

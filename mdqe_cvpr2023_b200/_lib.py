@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(PKG_DIR, "libmsda_b200.so")
 
 MSDA_F32, MSDA_BF16, MSDA_F64, MSDA_BF16_LOC32, MSDA_F16 = 0, 1, 2, 3, 4
-ABI_VERSION = 5
+ABI_VERSION = 6
 BWD_ACC_ZEROED = 1
 
 _c_int, _c_vp, _c_i64, _c_sz = ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t
@@ -45,6 +45,7 @@ PROTOTYPES = {
     "tc_linear_forward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_int, _c_vp]),
     "tc_linear_backward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_int, _c_vp, _c_vp]),
     "tc_linear_bias_grad": (_c_int, [_c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
+    "tc_linear_backward_bias": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_int, _c_vp, _c_vp, _c_vp]),
     "msda_forward_host": (_c_int, [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + _SEVEN + [_c_vp]),
     "msda_backward_host": (_c_int, [_c_int, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp] + _SEVEN
                            + [_c_vp, _c_vp, _c_vp]),

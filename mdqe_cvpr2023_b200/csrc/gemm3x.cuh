@@ -14,6 +14,13 @@
 // One persistent CTA per SM: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM owner), warps 2-9 epilogue (TMEM -> registers ->
 // bias / row mask -> swizzled staging tile -> TMA store), warps 10-17 produce the lo tiles.  Tile 128 x 128, reduction in
 // chunks of 32, 3-stage ring, two accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// kATm (A operand through tensor memory): an MMA of shape M128 x N128 x K8 fetches 4 KB of A and 4 KB of B from shared memory at
+// 128 B/clk -- 64 clocks, as long as its math -- and the lo tiles cost another read + write of every operand byte, so the all-shared
+// form is bound by shared-memory bandwidth (192 KB per 32-wide chunk = 1536 clocks against 813 clocks of tensor-core time).  With
+// kATm the split warps read the raw A tile once and write `hi` and `lo` straight into TMEM (tcgen05.st, lane = row, column = k);
+// the MMAs take A from there ([a_tmem] operand form) and only B from shared memory: 128 KB per chunk, and the stage shrinks from
+// 64 to 48 KB (4 stages instead of 3).  TMEM: columns 0-255 accumulators, 256 + 64 s + {0, 32} the hi / lo chunk of stage s.
 #pragma once
 
 #include "mask_tc4.cuh"
@@ -21,11 +28,14 @@
 namespace msda {
 
 constexpr int kG3Tile = 128;
-constexpr int kG3Stages = 3;
+constexpr int kG3Stages = 3;                                           // A and B in shared memory
+constexpr int kG3StagesTm = 4;                                         // A through tensor memory
 constexpr int kG3SplitWarps = 8;
 constexpr int kG3Threads = (2 + 8 + kG3SplitWarps) * 32;               // 576
 constexpr uint32_t kG3OpBytes = kG3Tile * 128u;                        // one operand tile: 128 rows/columns x 32 fp32
 constexpr uint32_t kG3StageBytes = 4 * kG3OpBytes;                     // [A hi][A lo][B hi][B lo]
+constexpr uint32_t kG3StageBytesTm = 3 * kG3OpBytes;                   // [A raw][B hi][B lo]
+constexpr uint32_t kG3TmemACol = 256;                                  // first TMEM column of the A chunks (kATm)
 constexpr uint32_t kG3OutBytes = kG3Tile * 128u;                       // staging: 128 rows x 32 columns
 
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
@@ -34,27 +44,48 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-template <bool kAMn, bool kBMn>
+__device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// 16 consecutive TMEM columns of the calling warp's 32 lanes (shape 32x32b: thread i owns lane i of the warp's quarter)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                 "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+
+__device__ __forceinline__ uint32_t tf32_lo(uint32_t v) { return __float_as_uint(__uint_as_float(v) - __uint_as_float(v & 0xffffe000u)); }
+
+template <bool kAMn, bool kBMn, bool kATm>
 __global__ void __launch_bounds__(kG3Threads, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
               const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias,
-              const unsigned char* __restrict__ row_mask, int M, int N, int n_kchunks, int chunks_per_split, int tiles_m,
-              int tiles_n, int n_items, int reduce) {
+              const unsigned char* __restrict__ row_mask, float* __restrict__ col_sum_a, int M, int N, int n_kchunks, int chunks_per_split,
+              int tiles_m, int tiles_n, int n_items, int reduce) {
+  constexpr int kStages = kATm ? kG3StagesTm : kG3Stages;
+  constexpr uint32_t kStageBytes = kATm ? kG3StageBytesTm : kG3StageBytes;
+  constexpr uint32_t kBOff = kATm ? kG3OpBytes : 2 * kG3OpBytes;        // B hi inside a stage; B lo follows it
+  constexpr uint32_t kTmemCols = kATm ? 512u : 256u;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
-  uint8_t* out_stage = smem + kG3Stages * kG3StageBytes;                // 2 x 16 KB (one per column half)
-  __shared__ __align__(8) uint64_t bars[3 * kG3Stages + 4];
+  uint8_t* out_stage = smem + kStages * kStageBytes;                    // 2 x 16 KB (one per column half)
+  __shared__ __align__(8) uint64_t bars[3 * kStages + 4];
   __shared__ uint32_t s_tmem_base;
   const uint32_t bar0 = smem_u32(&bars[0]);
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_ready = [&](int s) { return bar0 + 8u * (kG3Stages + s); };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * kG3Stages + s); };
-  auto bar_tfull = [&](int a) { return bar0 + 8u * (3 * kG3Stages + a); };
-  auto bar_tempty = [&](int a) { return bar0 + 8u * (3 * kG3Stages + 2 + a); };
+  auto bar_ready = [&](int s) { return bar0 + 8u * (kStages + s); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
+  auto bar_tfull = [&](int a) { return bar0 + 8u * (3 * kStages + a); };
+  auto bar_tempty = [&](int a) { return bar0 + 8u * (3 * kStages + 2 + a); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kG3Stages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_ready(s), kG3SplitWarps); mbar_init(bar_empty(s), 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_ready(s), kG3SplitWarps); mbar_init(bar_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -62,7 +93,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(256) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -99,10 +130,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         decode(item, split, tm, tn);
         chunk_range(split, c0, c1);
         for (int kc = c0; kc < c1; ++kc, ++i) {
-          const int s = i % kG3Stages;
-          const uint32_t ph = (i / kG3Stages) & 1;
+          const int s = i % kStages;
+          const uint32_t ph = (i / kStages) & 1;
           mbar_wait(bar_empty(s), ph ^ 1);
-          const uint32_t dst = smem_u32(smem) + s * kG3StageBytes;
+          const uint32_t dst = smem_u32(smem) + s * kStageBytes;
           mbar_expect_tx(bar_full(s), 2 * kG3OpBytes);
           if constexpr (kAMn) {
             for (int j = 0; j < 4; ++j) tma_load_3d(dst + j * 4096u, &map_a, bar_full(s), tm * kG3Tile + j * 32, kc * 32, 0);
@@ -110,16 +141,16 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             tma_load_3d(dst, &map_a, bar_full(s), kc * 32, tm * kG3Tile, 0);
           }
           if constexpr (kBMn) {
-            for (int j = 0; j < 4; ++j) tma_load_3d(dst + 2 * kG3OpBytes + j * 4096u, &map_b, bar_full(s), tn * kG3Tile + j * 32, kc * 32, 0);
+            for (int j = 0; j < 4; ++j) tma_load_3d(dst + kBOff + j * 4096u, &map_b, bar_full(s), tn * kG3Tile + j * 32, kc * 32, 0);
           } else {
-            tma_load_3d(dst + 2 * kG3OpBytes, &map_b, bar_full(s), kc * 32, tn * kG3Tile, 0);
+            tma_load_3d(dst + kBOff, &map_b, bar_full(s), kc * 32, tn * kG3Tile, 0);
           }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(kG3Tile, kAMn ? 1u : 0u, kBMn ? 1u : 0u);
+      const uint32_t idesc = umma_idesc_tf32(kG3Tile, (kAMn && !kATm) ? 1u : 0u, kBMn ? 1u : 0u);
       int i = 0, it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         int split, tm, tn, c0, c1;
@@ -130,18 +161,23 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         mbar_wait(bar_tempty(a), aph ^ 1);
         uint32_t acc = 0;
         for (int kc = c0; kc < c1; ++kc, ++i) {
-          const int s = i % kG3Stages;
-          const uint32_t ph = (i / kG3Stages) & 1;
+          const int s = i % kStages;
+          const uint32_t ph = (i / kStages) & 1;
           mbar_wait(bar_ready(s), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_hi = smem_u32(smem) + s * kG3StageBytes, a_lo = a_hi + kG3OpBytes;
-          const uint32_t b_hi = a_hi + 2 * kG3OpBytes, b_lo = b_hi + kG3OpBytes;
+          const uint32_t a_hi = smem_u32(smem) + s * kStageBytes, a_lo = a_hi + kG3OpBytes;
+          const uint32_t b_hi = a_hi + kBOff, b_lo = b_hi + kG3OpBytes;
           const uint32_t a_sel[3] = {a_hi, a_hi, a_lo}, b_sel[3] = {b_hi, b_lo, b_hi};     // hi*hi + hi*lo + lo*hi
+          const uint32_t a_tm = tmem_base + kG3TmemACol + static_cast<uint32_t>(s) * 64u;   // kATm: hi at +0, lo at +32
           for (int term = 0; term < 3; ++term)
             for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t a_desc = kAMn ? umma_desc(a_sel[term] + ks * 1024u, 4096u, 512u, 1u) : umma_desc(a_sel[term] + ks * 32u, 16u, 1024u, 2u);
               const uint64_t b_desc = kBMn ? umma_desc(b_sel[term] + ks * 1024u, 4096u, 512u, 1u) : umma_desc(b_sel[term] + ks * 32u, 16u, 1024u, 2u);
-              umma_tf32(tmem_base + a * 128u, a_desc, b_desc, idesc, acc);
+              if constexpr (kATm) {
+                umma_tf32_ta(tmem_base + a * 128u, a_tm + (term == 2 ? 32u : 0u) + ks * 8u, b_desc, idesc, acc);
+              } else {
+                const uint64_t a_desc = kAMn ? umma_desc(a_sel[term] + ks * 1024u, 4096u, 512u, 1u) : umma_desc(a_sel[term] + ks * 32u, 16u, 1024u, 2u);
+                umma_tf32(tmem_base + a * 128u, a_desc, b_desc, idesc, acc);
+              }
               acc = 1;
             }
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_empty(s)) : "memory");
@@ -150,36 +186,72 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       }
     }
   } else if (warp >= 10) {
-    // ---- lo tiles: element-wise, layout-agnostic
+    // ---- lo tiles (element-wise, layout-agnostic); kATm: the A chunk goes to TMEM as hi / lo columns, lane = row of the tile
     const uint32_t t = threadIdx.x - 10 * 32;                              // 0 .. 255
+    const int quarter = warp & 3, khalf = (warp - 10) >> 2;                 // TMEM lane quarter of this warp; which 16 of the chunk's 32 k
+    const int row = quarter * 32 + lane;
+    float col_sum = 0.f;                                                    // kATm && kAMn: sum over the reduction index of A[., row]
     int i = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int split, tm, tn, c0, c1;
       decode(item, split, tm, tn);
       chunk_range(split, c0, c1);
       for (int kc = c0; kc < c1; ++kc, ++i) {
-        const int s = i % kG3Stages;
-        const uint32_t ph = (i / kG3Stages) & 1;
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
         mbar_wait(bar_full(s), ph);
-        uint8_t* st = smem + s * kG3StageBytes;
+        uint8_t* st = smem + s * kStageBytes;
+        if constexpr (kATm) {
+          uint32_t hi[16], lo[16];
+          if constexpr (kAMn) {
+            // boxes {32 m, 32 k}: row k = 128 bytes holding 32 m, 32-byte chunk index XOR (k & 3)  [128B swizzle, 32B atoms]
+            const uint8_t* box = st + quarter * 4096;
 #pragma unroll
-        for (int op = 0; op < 2; ++op) {
-          const uint4* hi = reinterpret_cast<const uint4*>(st + op * 2 * kG3OpBytes);
-          uint4* lo = reinterpret_cast<uint4*>(st + op * 2 * kG3OpBytes + kG3OpBytes);
+            for (int j = 0; j < 16; ++j) {
+              const int k = khalf * 16 + j;
+              hi[j] = *reinterpret_cast<const uint32_t*>(box + k * 128 + ((((lane >> 3) ^ (k & 3)) << 5) | ((lane & 7) << 2)));
+              lo[j] = tf32_lo(hi[j]);
+              col_sum += __uint_as_float(hi[j]);
+            }
+          } else {
+            // K-major rows of 32 k (128 bytes), 16-byte chunk index XOR (row & 7)  [128B swizzle]
+            const uint8_t* a_row = st + row * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 v = *reinterpret_cast<const uint4*>(a_row + ((((khalf * 4 + j) ^ (row & 7))) << 4));
+              hi[4 * j] = v.x; hi[4 * j + 1] = v.y; hi[4 * j + 2] = v.z; hi[4 * j + 3] = v.w;
+              lo[4 * j] = tf32_lo(v.x); lo[4 * j + 1] = tf32_lo(v.y); lo[4 * j + 2] = tf32_lo(v.z); lo[4 * j + 3] = tf32_lo(v.w);
+            }
+          }
+          const uint32_t a_tm = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + kG3TmemACol + static_cast<uint32_t>(s) * 64u + khalf * 16u;
+          tmem_st16(a_tm, hi);
+          tmem_st16(a_tm + 32u, lo);
+        }
+#pragma unroll
+        for (int op = kATm ? 1 : 0; op < 2; ++op) {
+          const uint4* hi = reinterpret_cast<const uint4*>(st + (op == 0 ? 0u : kBOff));
+          uint4* lo = reinterpret_cast<uint4*>(st + (op == 0 ? 0u : kBOff) + kG3OpBytes);
 #pragma unroll
           for (uint32_t k = t; k < kG3OpBytes / 16; k += kG3SplitWarps * 32) {
             const uint4 v = hi[k];
             uint4 l;
-            l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xffffe000u));
-            l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xffffe000u));
-            l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xffffe000u));
-            l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xffffe000u));
+            l.x = tf32_lo(v.x);
+            l.y = tf32_lo(v.y);
+            l.z = tf32_lo(v.z);
+            l.w = tf32_lo(v.w);
             lo[k] = l;
           }
         }
+        if constexpr (kATm) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if constexpr (kATm) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_ready(s));
+      }
+      if constexpr (kATm && kAMn) {
+        // column sums of A over this item's reduction range: the bias gradient of a Linear layer when A = grad_y (tn == 0 items only)
+        if (col_sum_a != nullptr && tn == 0 && tm * kG3Tile + row < M) atomicAdd(col_sum_a + tm * kG3Tile + row, col_sum);
+        col_sum = 0.f;
       }
     }
   } else {
@@ -237,9 +309,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
 }
 
 constexpr size_t kG3SmemBytes = 1024 + kG3Stages * kG3StageBytes + 2 * kG3OutBytes;
+constexpr size_t kG3SmemBytesTm = 1024 + kG3StagesTm * kG3StageBytesTm + 2 * kG3OutBytes;
 
 }  // namespace msda

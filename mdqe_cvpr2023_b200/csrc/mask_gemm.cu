@@ -369,11 +369,10 @@ static int make_map_c(CUtensorMap* map, void* base, uint64_t d0, uint64_t d1) {
 
 // C[M x N] (+)= A * B.  a_mn: A is stored [K][M] (else [M][K]); b_mn: B is stored [K][N] (else [N][K]).  splits > 1: the reduction
 // is cut into `splits` ranges whose partial tiles are added into C (which must be zero) with TMA reduce-add stores.
-template <bool kAMn, bool kBMn>
+template <bool kAMn, bool kBMn, bool kATm>
 static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const void* Bm, void* C, int64_t M, int64_t N, int64_t K,
-                         const float* bias, const unsigned char* row_mask, int splits) {
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                         const float* bias, const unsigned char* row_mask, int splits, float* col_sum_a = nullptr) {
+  const int sms = sm_count();
   const int n_kchunks = static_cast<int>((K + 31) / 32);
   const int tiles_m = static_cast<int>((M + kG3Tile - 1) / kG3Tile), tiles_n = static_cast<int>((N + kG3Tile - 1) / kG3Tile);
   if (splits < 1) splits = 1;
@@ -388,12 +387,11 @@ static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const 
   if (kBMn) { if (int rc = make_map_mn_f32(&map_b, Bm, (uint64_t)N, (uint64_t)K, 1)) return rc; }
   else { if (int rc = make_map_in(&map_b, Bm, MSDA_F32, (uint64_t)K, (uint64_t)N, 1, kG3Tile)) return rc; }
   if (int rc = make_map_c(&map_c, C, (uint64_t)N, (uint64_t)M)) return rc;
-  if (int rc = ensure_func_attr(gemm3x_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes)) return rc;
-  if (int rc = ensure_func_attr(gemm3x_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes)) return rc;
-  if (int rc = ensure_func_attr(gemm3x_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes)) return rc;
+  constexpr size_t smem_bytes = kATm ? kG3SmemBytesTm : kG3SmemBytes;
+  if (int rc = ensure_func_attr(gemm3x_kernel<kAMn, kBMn, kATm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) return rc;
   const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);
-  gemm3x_kernel<kAMn, kBMn><<<grid, kG3Threads, kG3SmemBytes, st>>>(map_a, map_b, map_c, bias, row_mask, (int)M, (int)N, n_kchunks, cps,
-                                                                   tiles_m, tiles_n, (int)n_items, splits > 1 ? 1 : 0);
+  gemm3x_kernel<kAMn, kBMn, kATm><<<grid, kG3Threads, smem_bytes, st>>>(map_a, map_b, map_c, bias, row_mask, col_sum_a, (int)M, (int)N,
+                                                                         n_kchunks, cps, tiles_m, tiles_n, (int)n_items, splits > 1 ? 1 : 0);
   return after_launch("gemm3x_kernel");
 }
 
@@ -405,25 +403,36 @@ int linear_forward_dispatch(cudaStream_t st, const void* x, const void* w, const
   if (in_f % 4 != 0 || out_f % 4 != 0 || !aligned16(x) || !aligned16(w) || !aligned16(y))
     return fail(MSDA_ERR_UNSUPPORTED, "tc_linear_forward: in_features / out_features must be multiples of 4 and the tensors 16-byte aligned");
   if (rows == 0) return 0;
-  return launch_gemm3x<false, false>(st, "tc_linear_forward", x, w, y, rows, out_f, in_f, static_cast<const float*>(bias), row_mask, 1);
+  if (option("gemm_smem_a"))
+    return launch_gemm3x<false, false, false>(st, "tc_linear_forward", x, w, y, rows, out_f, in_f, static_cast<const float*>(bias), row_mask, 1);
+  return launch_gemm3x<false, false, true>(st, "tc_linear_forward", x, w, y, rows, out_f, in_f, static_cast<const float*>(bias), row_mask, 1);
 }
 
 int linear_backward_dispatch(cudaStream_t st, const void* gy, const void* x, const void* w, int64_t rows, int in_f, int out_f,
-                             void* gx, void* gw) {
+                             void* gx, void* gw, void* gb, bool* gb_done) {
+  if (gb_done) *gb_done = false;
   if (rows >= (int64_t(1) << 31) - kG3Tile) return fail(MSDA_ERR_UNSUPPORTED, "tc_linear_backward: rows=%lld too large", (long long)rows);
   if (in_f % 4 != 0 || out_f % 4 != 0 || !aligned16(gy) || (gx && (!aligned16(gx) || !aligned16(w))) || (gw && (!aligned16(gw) || !aligned16(x))))
     return fail(MSDA_ERR_UNSUPPORTED, "tc_linear_backward: in_features / out_features must be multiples of 4 and the tensors 16-byte aligned");
+  const bool smem_a = option("gemm_smem_a") != 0;
+  const bool fuse_bias = gb != nullptr && gw != nullptr && !smem_a;         // the weight-gradient GEMM stages grad_y: its column sums come for free
   if (gw)
     if (int rc = check_cuda(cudaMemsetAsync(gw, 0, (size_t)out_f * in_f * sizeof(float), st), "cudaMemsetAsync(grad_weight)")) return rc;
+  if (fuse_bias) {
+    if (int rc = check_cuda(cudaMemsetAsync(gb, 0, (size_t)out_f * sizeof(float), st), "cudaMemsetAsync(grad_bias)")) return rc;
+    if (gb_done) *gb_done = true;
+  }
   if (rows == 0) return 0;
-  if (gx)                                                   // dx[r, i] = sum_o dy[r, o] W[o, i]
-    if (int rc = launch_gemm3x<false, true>(st, "tc_linear_backward", gy, w, gx, rows, in_f, out_f, nullptr, nullptr, 1)) return rc;
+  if (gx) {                                                 // dx[r, i] = sum_o dy[r, o] W[o, i]
+    if (int rc = smem_a ? launch_gemm3x<false, true, false>(st, "tc_linear_backward", gy, w, gx, rows, in_f, out_f, nullptr, nullptr, 1)
+                        : launch_gemm3x<false, true, true>(st, "tc_linear_backward", gy, w, gx, rows, in_f, out_f, nullptr, nullptr, 1)) return rc;
+  }
   if (gw) {                                                 // dW[o, i] = sum_r dy[r, o] x[r, i]: reduction over the rows, split across the SMs
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int tiles = ((out_f + kG3Tile - 1) / kG3Tile) * ((in_f + kG3Tile - 1) / kG3Tile);
-    int splits = (sms + tiles - 1) / tiles;
-    if (int rc = launch_gemm3x<true, true>(st, "tc_linear_backward", gy, x, gw, out_f, in_f, rows, nullptr, nullptr, splits)) return rc;
+    const int splits = (sm_count() + tiles - 1) / tiles;
+    if (int rc = smem_a ? launch_gemm3x<true, true, false>(st, "tc_linear_backward", gy, x, gw, out_f, in_f, rows, nullptr, nullptr, splits)
+                        : launch_gemm3x<true, true, true>(st, "tc_linear_backward", gy, x, gw, out_f, in_f, rows, nullptr, nullptr, splits,
+                                                          fuse_bias ? static_cast<float*>(gb) : nullptr)) return rc;
   }
   return 0;
 }

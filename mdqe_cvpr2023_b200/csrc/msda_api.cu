@@ -54,6 +54,7 @@ static std::atomic<int>* find_option(const char* key) {
   if (!strcmp(key, "bwd_merge")) return &g_opt.bwd_merge;
   if (!strcmp(key, "pair_map")) return &g_opt.pair_map;
   if (!strcmp(key, "pdl")) return &g_opt.pdl;
+  if (!strcmp(key, "gemm_smem_a")) return &g_opt.gemm_smem_a;
   return nullptr;
 }
 
@@ -453,6 +454,17 @@ int tc_linear_backward(void* stream, const void* grad_y, const void* x, const vo
   if (rows < 0 || in_features <= 0 || out_features <= 0) return fail(MSDA_ERR_INVALID_ARG, "tc_linear_backward: bad sizes");
   if (rows > 0 && (!grad_y || (grad_x && !weight) || (grad_weight && !x))) return fail(MSDA_ERR_INVALID_ARG, "tc_linear_backward: NULL tensor");
   return linear_backward_dispatch(static_cast<cudaStream_t>(stream), grad_y, x, weight, rows, in_features, out_features, grad_x, grad_weight);
+}
+
+int tc_linear_backward_bias(void* stream, const void* grad_y, const void* x, const void* weight, int64_t rows, int in_features,
+                            int out_features, void* grad_x, void* grad_weight, void* grad_bias) {
+  if (rows < 0 || in_features <= 0 || out_features <= 0) return fail(MSDA_ERR_INVALID_ARG, "tc_linear_backward_bias: bad sizes");
+  if (rows > 0 && (!grad_y || (grad_x && !weight) || (grad_weight && !x))) return fail(MSDA_ERR_INVALID_ARG, "tc_linear_backward_bias: NULL tensor");
+  bool bias_done = false;
+  if (int rc = linear_backward_dispatch(static_cast<cudaStream_t>(stream), grad_y, x, weight, rows, in_features, out_features, grad_x, grad_weight,
+                                        grad_bias, &bias_done)) return rc;
+  if (grad_bias && !bias_done) return tc_linear_bias_grad(stream, grad_y, rows, out_features, grad_bias);
+  return 0;
 }
 
 // ------------------------------------------------------------------------------- host-buffer entries

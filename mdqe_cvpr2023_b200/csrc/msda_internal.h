@@ -42,6 +42,7 @@ struct Options {
   std::atomic<int> consumer_ctas{0};  // > 0: CTAs of the matcher-cost / IoU kernels (tuning; 0 = auto)
   std::atomic<int> pdl{1};            // 1 = launch the sampling kernels with programmatic stream serialization (see msda_launch.cuh)
   std::atomic<int> pair_map{0};       // order in which a CTA of the fast2 sampling kernels walks its pairs: 0 = auto, 1 = linear (chunk / M queries x all heads), 2 = head-run (one head x chunk queries; PairMap in msda_fast2.cuh)
+  std::atomic<int> gemm_smem_a{0};    // Linear-layer GEMMs: 1 = both operands from shared memory (first form, A/B); 0 = A through tensor memory (gemm3x.cuh)
   std::atomic<int> bwd_merge{1};      // 1 = merge grad_value reductions of a (pair, level) that hit the same row (P = 2 or 4); 0 = off (A/B)
 };
 const Options& options();
@@ -78,7 +79,7 @@ int match_cost_tc_dispatch(cudaStream_t stream, const float* coeff, const float*
 int linear_forward_dispatch(cudaStream_t stream, const void* x, const void* w, const void* bias, const unsigned char* row_mask,
                             int64_t rows, int in_f, int out_f, void* y);
 int linear_backward_dispatch(cudaStream_t stream, const void* gy, const void* x, const void* w, int64_t rows, int in_f, int out_f,
-                             void* gx, void* gw);
+                             void* gx, void* gw, void* gb = nullptr, bool* gb_done = nullptr);
 
 inline size_t dtype_size(int dtype) {
   switch (dtype) {

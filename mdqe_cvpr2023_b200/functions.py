@@ -178,8 +178,10 @@ class _TcLinearFunction(Function):
         grad_y = grad_y.contiguous()
         if row_mask is not None:
             grad_y = grad_y.masked_fill(row_mask.unsqueeze(-1), 0.0)
-        gx, gw = ops.tc_linear_backward(grad_y, x, weight, need_x=ctx.needs_input_grad[0], need_weight=ctx.needs_input_grad[1])
-        gb = ops.tc_linear_bias_grad(grad_y) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gx, gw, gb = ops.tc_linear_backward(grad_y, x, weight, need_x=ctx.needs_input_grad[0], need_weight=ctx.needs_input_grad[1], need_bias=True)
+        else:
+            (gx, gw), gb = ops.tc_linear_backward(grad_y, x, weight, need_x=ctx.needs_input_grad[0], need_weight=ctx.needs_input_grad[1]), None
         return gx, gw, gb, None
 
 

@@ -433,8 +433,9 @@ def tc_linear_bias_grad(grad_y):
     return gb
 
 
-def tc_linear_backward(grad_y, x, weight, need_x=True, need_weight=True):
-    """(grad_x, grad_weight) of y = x @ weight.T; grad_y must already carry the row mask (masked rows zero)."""
+def tc_linear_backward(grad_y, x, weight, need_x=True, need_weight=True, need_bias=False):
+    """(grad_x, grad_weight) of y = x @ weight.T; grad_y must already carry the row mask (masked rows zero).  With ``need_bias`` the
+    result is (grad_x, grad_weight, grad_bias): the column sums of grad_y come out of the weight-gradient GEMM (tc_linear_backward_bias)."""
     who = "tc_linear_backward"
     _check_inputs(who, [("grad_y", grad_y), ("x", x), ("weight", weight)])
     out_f, in_f = weight.shape
@@ -445,6 +446,12 @@ def tc_linear_backward(grad_y, x, weight, need_x=True, need_weight=True):
     with torch.cuda.device(x.device):
         gx = torch.empty_like(x) if need_x else None
         gw = torch.empty_like(weight) if need_weight else None
+        if need_bias:
+            gb = torch.empty(out_f, dtype=torch.float32, device=x.device)
+            rc = lib.tc_linear_backward_bias(_stream_ptr(x.device), grad_y.data_ptr(), x.data_ptr(), weight.data_ptr(), rows, in_f, out_f,
+                                             gx.data_ptr() if gx is not None else None, gw.data_ptr() if gw is not None else None, gb.data_ptr())
+            _lib.check(rc, who)
+            return gx, gw, gb
         rc = lib.tc_linear_backward(_stream_ptr(x.device), grad_y.data_ptr(), x.data_ptr(), weight.data_ptr(), rows, in_f, out_f,
                                     gx.data_ptr() if gx is not None else None, gw.data_ptr() if gw is not None else None)
     _lib.check(rc, who)

@@ -40,7 +40,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 def test_abi_version_and_options(lib):
     from mdqe_cvpr2023_b200 import _lib
-    assert lib.msda_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.msda_abi_version() == _lib.ABI_VERSION == 6
     _lib.set_option("chunk_pairs", 48)
     assert _lib.get_option("chunk_pairs") == 48
     _lib.set_option("chunk_pairs", 0)

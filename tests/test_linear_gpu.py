@@ -9,6 +9,15 @@ from tests.helpers import nerr
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["a_tmem", "a_smem"], autouse=True)
+def operand_path(request):
+    """Both forms of the GEMM: A operand through tensor memory (default) and both operands from shared memory (option gemm_smem_a)."""
+    from mdqe_cvpr2023_b200 import _lib
+    _lib.set_option("gemm_smem_a", 1 if request.param == "a_smem" else 0)
+    yield request.param
+    _lib.set_option("gemm_smem_a", 0)
+
+
 @pytest.mark.parametrize("rows,in_f,out_f", [(4 * 5100, 256, 256), (4 * 5100, 256, 128), (784, 256, 256), (3 * 5100, 192, 192),
                                              (3 * 5100, 192, 96), (1, 256, 256), (130, 36, 20), (257, 8, 300), (1000, 260, 4)])
 def test_tc_linear_vs_fp64(rows, in_f, out_f):
@@ -33,6 +42,32 @@ def test_tc_linear_vs_fp64(rows, in_f, out_f):
     y2 = tc_linear(x3, w.detach())
     assert y2.shape == x3.shape[:-1] + (out_f,)
     assert nerr(y2.reshape(rows, out_f), F.linear(x.detach().double(), w.detach().double())) < 2e-5
+
+
+@pytest.mark.parametrize("rows,in_f,out_f", [(4 * 5100, 256, 256), (784, 256, 128), (130, 36, 20), (1, 8, 4), (0, 8, 4)])
+def test_backward_with_bias_in_one_call(rows, in_f, out_f):
+    """tc_linear_backward_bias: the bias gradient out of the weight-gradient GEMM (column sums taken by the staging warps), and the
+    fallback to the bias kernel when no weight gradient is asked for."""
+    from mdqe_cvpr2023_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(rows + out_f)
+    x = torch.randn(rows, in_f, device="cuda", generator=g)
+    w = torch.randn(out_f, in_f, device="cuda", generator=g) / in_f ** 0.5
+    gy = torch.randn(rows, out_f, device="cuda", generator=g) + 0.25
+    want_b = gy.double().sum(0)
+    want_w = gy.double().t() @ x.double()
+    want_x = gy.double() @ w.double()
+    for need_x, need_w in ((True, True), (False, True), (True, False), (False, False)):
+        gx, gw, gb = ops.tc_linear_backward(gy, x, w, need_x=need_x, need_weight=need_w, need_bias=True)
+        assert (gx is None) == (not need_x) and (gw is None) == (not need_w)
+        scale = max(float(want_b.abs().max()), 1e-30)
+        assert float((gb.double() - want_b).abs().max()) / scale < 2e-5 or rows == 0
+        if rows == 0:
+            assert float(gb.abs().max()) == 0.0
+            continue
+        if need_x:
+            assert nerr(gx, want_x) < 2e-5
+        if need_w:
+            assert nerr(gw, want_w) < 2e-5
 
 
 def test_tc_linear_rejects_unsupported():

@@ -256,6 +256,19 @@ def test_autograd_function_and_autocast():
     check((out2, v.grad, l.grad, a.grad), want, 2e-5, "autograd", inp)
 
 
+def test_inference_window_of_30_frames_forward_vs_oracle():
+    """The reference's inference feeds the encoder a window of up to 30 frames at once (configs/R50_ovis_360.yaml:12
+    WINDOW_FRAME_NUM_TEST): N=30, S=Lq=5100 -- 1.22 M pairs, the largest grid the shipped configs produce."""
+    from mdqe_cvpr2023_b200 import ops
+    from oracle import msda_oracle as O
+    inp = make_inputs(30, R50_360, 8, 32, 4, dist="local", seed=43)
+    dev = to_cuda({k: inp[k] for k in ("value", "shapes", "level_start", "loc", "aw")})
+    out = ops.ms_deform_attn_forward(dev["value"], dev["shapes"], dev["level_start"], dev["loc"], dev["aw"], 64)
+    torch.cuda.synchronize()
+    want = O.msda_forward(inp["value"].numpy(), inp["shapes"].numpy(), inp["loc"].numpy(), inp["aw"].numpy(), inp["level_start"].numpy())
+    assert nerr(out, np.asarray(want).reshape(tuple(out.shape))) <= 2e-5
+
+
 @pytest.mark.parametrize("name,N,pyr,D", [("R50_ovis_360", 4, R50_360, 32), ("R50_ovis_720", 4, R50_720, 32), ("swinl_ytvis21", 3, R50_360, 24)])
 @pytest.mark.parametrize("dist", ["local", "uniform"])
 def test_full_size_fp32_vs_oracle(name, N, pyr, D, dist):

@@ -8,7 +8,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F
 
-from mdqe_cvpr2023_b200 import ops
+from mdqe_cvpr2023_b200 import _lib, ops
+
+if "--smem-a" in sys.argv:                       # A/B: both GEMM operands from shared memory (the first form of gemm3x_kernel)
+    _lib.set_option("gemm_smem_a", 1)
 
 torch.backends.cuda.matmul.allow_tf32 = False
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -58,14 +61,16 @@ for name, rows, in_f, out_f in [("enc value/output/offsets proj (R50_360, T=4)",
     r = {"shape": name, "rows": rows, "in": in_f, "out": out_f,
          "tc_fwd_us": timed(lambda: ops.tc_linear_forward(x, w, b)), "torch_fwd_us": timed(lambda: F.linear(x, w, b)),
          "tc_dgrad_us": timed(lambda: ops.tc_linear_backward(gy, x, w, True, False)), "torch_dgrad_us": timed(lambda: gy @ w),
-         "tc_wgrad_us": timed(lambda: ops.tc_linear_backward(gy, x, w, False, True)), "torch_wgrad_us": timed(lambda: gy.t() @ x)}
+         "tc_wgrad_us": timed(lambda: ops.tc_linear_backward(gy, x, w, False, True)), "torch_wgrad_us": timed(lambda: gy.t() @ x),
+         "tc_wgrad_bias_us": timed(lambda: ops.tc_linear_backward(gy, x, w, False, True, True))}
     r.update({"tc_fwd_graph_us": timed_graph(lambda: ops.tc_linear_forward(x, w, b)), "torch_fwd_graph_us": timed_graph(lambda: F.linear(x, w, b)),
               "tc_dgrad_graph_us": timed_graph(lambda: ops.tc_linear_backward(gy, x, w, True, False)), "torch_dgrad_graph_us": timed_graph(lambda: gy @ w),
-              "tc_wgrad_graph_us": timed_graph(lambda: ops.tc_linear_backward(gy, x, w, False, True)), "torch_wgrad_graph_us": timed_graph(lambda: gy.t() @ x)})
+              "tc_wgrad_graph_us": timed_graph(lambda: ops.tc_linear_backward(gy, x, w, False, True)), "torch_wgrad_graph_us": timed_graph(lambda: gy.t() @ x),
+              "tc_wgrad_bias_graph_us": timed_graph(lambda: ops.tc_linear_backward(gy, x, w, False, True, True))})
     flops = 2.0 * rows * in_f * out_f
     r["tc_fwd_tflops"] = flops / r["tc_fwd_us"] / 1e6
     r["fwd_bytes_GBps"] = (rows * (in_f + out_f) * 4) / r["tc_fwd_us"] / 1e3
     res.append(r)
     print(json.dumps({k: (round(v, 1) if isinstance(v, float) else v) for k, v in r.items()}))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(res, open("gpurun_out/linear_bench.json", "w"), indent=1)
+json.dump(res, open("gpurun_out/linear_bench%s.json" % ("_smem_a" if "--smem-a" in sys.argv else ""), "w"), indent=1)

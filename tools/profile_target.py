@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Tiny launch target for `ncu`: runs ONE kind of call a few times so that -k/-s/-c select it easily.
 
-    python tools/profile_target.py enc_fwd|enc_bwd|dec_fwd|dec_bwd|mask_fwd|mask_bwd [--dist local] [--dtype fp32] [--reps 3]
+    python tools/profile_target.py enc_fwd|enc_bwd|dec_fwd|dec_bwd|mask_fwd|mask_bwd|lin_fwd|lin_dgrad|lin_wgrad [--dist local] [--dtype fp32] [--reps 3]
 """
 import argparse
 import os
@@ -28,7 +28,19 @@ if args.opt:
         k, v = kv.split("=")
         _lib.set_option(k, int(v))
 
-if args.what.startswith("mask"):
+if args.what.startswith("lin"):
+    x = torch.randn(4 * 5100, 256, device="cuda")
+    w = torch.randn(256, 256, device="cuda") / 16
+    b = torch.randn(256, device="cuda")
+    gy = torch.randn(4 * 5100, 256, device="cuda")
+    for _ in range(args.reps):
+        if args.what == "lin_fwd":
+            ops.tc_linear_forward(x, w, b)
+        elif args.what == "lin_dgrad":
+            ops.tc_linear_backward(gy, x, w, True, False)
+        else:
+            ops.tc_linear_backward(gy, x, w, False, True, True)
+elif args.what.startswith("mask"):
     coeff = torch.tanh(torch.randn(1, 196, 32, device="cuda"))
     proto = torch.randn(1, 32, 4, 96, 160, device="cuda")
     go = torch.randn(1, 196, 4, 96, 160, device="cuda")
