@@ -188,6 +188,24 @@ int msda_fused_backward_flags(void* stream, int dtype,
                               int mode, float offset_scale, const void* grad_out,
                               int N, int S, int M, int D, int G, int L, int Lq, int P, float scale,
                               void* grad_value, void* grad_offsets, void* grad_logits, int flags);
+/* Joint query projection: `qproj` [N*Lq, row_stride] fp32 is the output of ONE Linear layer over the concatenated weights of
+ * sampling_offsets (or sampling_grid_offsets) and attention_weights (ms_deform_attn.py:143-146, :157): columns [0, 2*M*L*P) are
+ * the raw offsets in [M,L,P,2] order, columns [2*M*L*P, 3*M*L*P) the raw logits in [M,L*P] order; further columns are ignored.
+ * The backward writes the gradient in the same layout into grad_qproj [N*Lq, row_stride] (columns beyond 3*M*L*P are not
+ * written), so the query side of a module is one GEMM forward, one for grad_query and one for the weight gradients instead of
+ * two each plus an addition.  row_stride a multiple of 4; `flags` as for msda_backward_flags.  Otherwise as msda_fused_*. */
+int msda_fused_forward_joint(void* stream, int dtype,
+                             const void* value, const int64_t* shapes, const int64_t* level_start,
+                             const void* ref_points, int R, const void* qproj, int row_stride, const void* grid,
+                             int mode, float offset_scale,
+                             int N, int S, int M, int D, int G, int L, int Lq, int P, float scale,
+                             void* out);
+int msda_fused_backward_joint(void* stream, int dtype,
+                              const void* value, const int64_t* shapes, const int64_t* level_start,
+                              const void* ref_points, int R, const void* qproj, int row_stride, const void* grid,
+                              int mode, float offset_scale, const void* grad_out,
+                              int N, int S, int M, int D, int G, int L, int Lq, int P, float scale,
+                              void* grad_value, void* grad_qproj, int flags);
 
 /* Mask contraction: out[b,q,n] = sum_k coeff[b,q,k] * proto[b,k,n], n over the flattened (t,h,w)
  * plane (Ncols = T*H*W).  coeff [B,Q,K], proto [B,K,Ncols], out [B,Q,Ncols].

@@ -5,15 +5,15 @@ import os
 import sys
 
 from . import _lib  # noqa: F401
-from .functions import (MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnGroupedFunction,  # noqa: F401
-                        mask_logits, tc_linear)
+from .functions import (MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnFusedJointFunction,  # noqa: F401
+                        MSDeformAttnGroupedFunction, mask_logits, tc_linear)
 from .consumers import (aligned_bilinear, mask_losses, mask_match_cost, mask_nms_siou, mask_track_siou,  # noqa: F401
                         query_init_sample)
 from .modules import MSDeformAttn  # noqa: F401
 from .ops import (mask_logits_backward, mask_logits_forward, ms_deform_attn_backward,  # noqa: F401
                   ms_deform_attn_forward)
 
-__all__ = ["MSDeformAttn", "MSDeformAttnFunction", "MSDeformAttnGroupedFunction", "MSDeformAttnFusedFunction", "mask_logits", "tc_linear", "ms_deform_attn_forward",
+__all__ = ["MSDeformAttn", "MSDeformAttnFunction", "MSDeformAttnGroupedFunction", "MSDeformAttnFusedFunction", "MSDeformAttnFusedJointFunction", "mask_logits", "tc_linear", "ms_deform_attn_forward",
            "ms_deform_attn_backward", "mask_logits_forward", "mask_logits_backward", "install_dropin",
            "mask_match_cost", "mask_losses", "mask_nms_siou", "mask_track_siou", "aligned_bilinear", "query_init_sample"]
 

@@ -40,6 +40,10 @@ PROTOTYPES = {
                            + [_c_int] * 8 + [ctypes.c_float, _c_vp]),
     "msda_fused_backward": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, ctypes.c_float,
                                      _c_vp] + [_c_int] * 8 + [ctypes.c_float, _c_vp, _c_vp, _c_vp]),
+    "msda_fused_forward_joint": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_vp, _c_int, ctypes.c_float]
+                                 + [_c_int] * 8 + [ctypes.c_float, _c_vp]),
+    "msda_fused_backward_joint": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_vp, _c_int, ctypes.c_float,
+                                           _c_vp] + [_c_int] * 8 + [ctypes.c_float, _c_vp, _c_vp, _c_int]),
     "mask_logits_forward": (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_vp]),
     "mask_logits_backward": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_vp, _c_vp]),
     "tc_linear_forward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_int, _c_vp]),

@@ -367,9 +367,42 @@ static int make_map_c(CUtensorMap* map, void* base, uint64_t d0, uint64_t d1) {
   return 0;
 }
 
+// Per-tile flags of the stream-K form: one zero-initialised ring per device, a fresh stretch of it per launch (launches that overlap
+// on different streams or graph branches never share flags; the kernel leaves its flags zero again).  Allocated on first use outside
+// of stream capture; until then (first call inside a capture) the GEMMs run in the round-robin tile form.
+namespace {
+constexpr int kFlagRing = 1 << 20;                     // 4 MB: thousands of launches between two uses of the same flags
+struct FlagRing { int* base = nullptr; int cursor = 0; };
+std::mutex g_flag_mu;
+FlagRing g_flag_ring[64];
+}  // namespace
+
+static int* gemm_tile_flags(cudaStream_t st, int tiles) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || tiles > kFlagRing / 4) { cudaGetLastError(); return nullptr; }
+  std::lock_guard<std::mutex> lock(g_flag_mu);
+  FlagRing& ring = g_flag_ring[dev];
+  if (!ring.base) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }
+    int* p = nullptr;
+    if (cudaMalloc(&p, kFlagRing * sizeof(int)) != cudaSuccess || cudaMemset(p, 0, kFlagRing * sizeof(int)) != cudaSuccess) {
+      cudaGetLastError();
+      if (p) cudaFree(p);
+      return nullptr;
+    }
+    ring.base = p;
+  }
+  if (ring.cursor + tiles > kFlagRing) ring.cursor = 0;
+  int* out = ring.base + ring.cursor;
+  ring.cursor += tiles;
+  return out;
+}
+
 // C[M x N] (+)= A * B.  a_mn: A is stored [K][M] (else [M][K]); b_mn: B is stored [K][N] (else [N][K]).  splits > 1: the reduction
-// is cut into `splits` ranges whose partial tiles are added into C (which must be zero) with TMA reduce-add stores.
-template <bool kAMn, bool kBMn, bool kATm>
+// is cut into `splits` ranges whose partial tiles are added into C (which must be zero) with TMA reduce-add stores; splits == 1:
+// the (tile, chunk) units are dealt out as one contiguous range per CTA (stream-K, see gemm3x.cuh).
+template <bool kAMn, bool kBMn>
 static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const void* Bm, void* C, int64_t M, int64_t N, int64_t K,
                          const float* bias, const unsigned char* row_mask, int splits, float* col_sum_a = nullptr) {
   const int sms = sm_count();
@@ -379,7 +412,15 @@ static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const 
   if (splits > n_kchunks) splits = n_kchunks;
   const int cps = (n_kchunks + splits - 1) / splits;
   splits = (n_kchunks + cps - 1) / cps;
-  const int64_t n_items = (int64_t)tiles_m * tiles_n * splits;
+  const int64_t tiles = (int64_t)tiles_m * tiles_n;
+  int64_t n_items = tiles * splits;
+  int mode = splits > 1 ? kG3ModeReduce : kG3ModeStore;
+  int* flags = nullptr;
+  if (splits == 1 && tiles * n_kchunks < (int64_t(1) << 31) && option("gemm_stream_k") != 0 && (tiles % sms != 0) &&
+      (flags = gemm_tile_flags(st, static_cast<int>(tiles))) != nullptr) {
+    mode = kG3ModeStreamK;
+    n_items = tiles * n_kchunks;
+  }
   if (n_items >= (int64_t(1) << 31)) return fail(MSDA_ERR_UNSUPPORTED, "%s: too many tiles", who);
   CUtensorMap map_a, map_b, map_c;
   if (kAMn) { if (int rc = make_map_mn_f32(&map_a, A, (uint64_t)M, (uint64_t)K, 1)) return rc; }
@@ -387,11 +428,10 @@ static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const 
   if (kBMn) { if (int rc = make_map_mn_f32(&map_b, Bm, (uint64_t)N, (uint64_t)K, 1)) return rc; }
   else { if (int rc = make_map_in(&map_b, Bm, MSDA_F32, (uint64_t)K, (uint64_t)N, 1, kG3Tile)) return rc; }
   if (int rc = make_map_c(&map_c, C, (uint64_t)N, (uint64_t)M)) return rc;
-  constexpr size_t smem_bytes = kATm ? kG3SmemBytesTm : kG3SmemBytes;
-  if (int rc = ensure_func_attr(gemm3x_kernel<kAMn, kBMn, kATm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) return rc;
+  if (int rc = ensure_func_attr(gemm3x_kernel<kAMn, kBMn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes)) return rc;
   const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);
-  gemm3x_kernel<kAMn, kBMn, kATm><<<grid, kG3Threads, smem_bytes, st>>>(map_a, map_b, map_c, bias, row_mask, col_sum_a, (int)M, (int)N,
-                                                                         n_kchunks, cps, tiles_m, tiles_n, (int)n_items, splits > 1 ? 1 : 0);
+  gemm3x_kernel<kAMn, kBMn><<<grid, kG3Threads, kG3SmemBytes, st>>>(map_a, map_b, map_c, bias, row_mask, col_sum_a, flags, (int)M, (int)N,
+                                                                    n_kchunks, cps, tiles_m, tiles_n, (int)n_items, mode);
   return after_launch("gemm3x_kernel");
 }
 
@@ -403,9 +443,7 @@ int linear_forward_dispatch(cudaStream_t st, const void* x, const void* w, const
   if (in_f % 4 != 0 || out_f % 4 != 0 || !aligned16(x) || !aligned16(w) || !aligned16(y))
     return fail(MSDA_ERR_UNSUPPORTED, "tc_linear_forward: in_features / out_features must be multiples of 4 and the tensors 16-byte aligned");
   if (rows == 0) return 0;
-  if (option("gemm_smem_a"))
-    return launch_gemm3x<false, false, false>(st, "tc_linear_forward", x, w, y, rows, out_f, in_f, static_cast<const float*>(bias), row_mask, 1);
-  return launch_gemm3x<false, false, true>(st, "tc_linear_forward", x, w, y, rows, out_f, in_f, static_cast<const float*>(bias), row_mask, 1);
+  return launch_gemm3x<false, false>(st, "tc_linear_forward", x, w, y, rows, out_f, in_f, static_cast<const float*>(bias), row_mask, 1);
 }
 
 int linear_backward_dispatch(cudaStream_t st, const void* gy, const void* x, const void* w, int64_t rows, int in_f, int out_f,
@@ -414,8 +452,7 @@ int linear_backward_dispatch(cudaStream_t st, const void* gy, const void* x, con
   if (rows >= (int64_t(1) << 31) - kG3Tile) return fail(MSDA_ERR_UNSUPPORTED, "tc_linear_backward: rows=%lld too large", (long long)rows);
   if (in_f % 4 != 0 || out_f % 4 != 0 || !aligned16(gy) || (gx && (!aligned16(gx) || !aligned16(w))) || (gw && (!aligned16(gw) || !aligned16(x))))
     return fail(MSDA_ERR_UNSUPPORTED, "tc_linear_backward: in_features / out_features must be multiples of 4 and the tensors 16-byte aligned");
-  const bool smem_a = option("gemm_smem_a") != 0;
-  const bool fuse_bias = gb != nullptr && gw != nullptr && !smem_a;         // the weight-gradient GEMM stages grad_y: its column sums come for free
+  const bool fuse_bias = gb != nullptr && gw != nullptr;                    // the weight-gradient GEMM stages grad_y: its column sums come for free
   if (gw)
     if (int rc = check_cuda(cudaMemsetAsync(gw, 0, (size_t)out_f * in_f * sizeof(float), st), "cudaMemsetAsync(grad_weight)")) return rc;
   if (fuse_bias) {
@@ -424,15 +461,13 @@ int linear_backward_dispatch(cudaStream_t st, const void* gy, const void* x, con
   }
   if (rows == 0) return 0;
   if (gx) {                                                 // dx[r, i] = sum_o dy[r, o] W[o, i]
-    if (int rc = smem_a ? launch_gemm3x<false, true, false>(st, "tc_linear_backward", gy, w, gx, rows, in_f, out_f, nullptr, nullptr, 1)
-                        : launch_gemm3x<false, true, true>(st, "tc_linear_backward", gy, w, gx, rows, in_f, out_f, nullptr, nullptr, 1)) return rc;
+    if (int rc = launch_gemm3x<false, true>(st, "tc_linear_backward", gy, w, gx, rows, in_f, out_f, nullptr, nullptr, 1)) return rc;
   }
   if (gw) {                                                 // dW[o, i] = sum_r dy[r, o] x[r, i]: reduction over the rows, split across the SMs
     const int tiles = ((out_f + kG3Tile - 1) / kG3Tile) * ((in_f + kG3Tile - 1) / kG3Tile);
     const int splits = (sm_count() + tiles - 1) / tiles;
-    if (int rc = smem_a ? launch_gemm3x<true, true, false>(st, "tc_linear_backward", gy, x, gw, out_f, in_f, rows, nullptr, nullptr, splits)
-                        : launch_gemm3x<true, true, true>(st, "tc_linear_backward", gy, x, gw, out_f, in_f, rows, nullptr, nullptr, splits,
-                                                          fuse_bias ? static_cast<float*>(gb) : nullptr)) return rc;
+    if (int rc = launch_gemm3x<true, true>(st, "tc_linear_backward", gy, x, gw, out_f, in_f, rows, nullptr, nullptr, splits,
+                                           fuse_bias ? static_cast<float*>(gb) : nullptr)) return rc;
   }
   return 0;
 }

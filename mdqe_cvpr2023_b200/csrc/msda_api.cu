@@ -54,7 +54,7 @@ static std::atomic<int>* find_option(const char* key) {
   if (!strcmp(key, "bwd_merge")) return &g_opt.bwd_merge;
   if (!strcmp(key, "pair_map")) return &g_opt.pair_map;
   if (!strcmp(key, "pdl")) return &g_opt.pdl;
-  if (!strcmp(key, "gemm_smem_a")) return &g_opt.gemm_smem_a;
+  if (!strcmp(key, "gemm_stream_k")) return &g_opt.gemm_stream_k;
   return nullptr;
 }
 
@@ -402,6 +402,42 @@ int msda_fused_backward_flags(void* stream, int dtype, const void* value, const 
   const FusedArgs fz{static_cast<const float*>(ref_points), static_cast<const float*>(grid), R, mode, offset_scale};
   return backward_impl("msda_fused_backward_flags", stream, dtype, value, shapes, level_start, offsets, logits, grad_out, N, S, M, D, G,
                        L, Lq, P, scale, grad_value, grad_offsets, grad_logits, nullptr, 0, fz, flags);
+}
+
+static int joint_args(const char* who, const void* qproj, int row_stride, int M, int L, int P) {
+  const int64_t lp = (int64_t)M * L * P;
+  if (!qproj) return fail(MSDA_ERR_INVALID_ARG, "%s: qproj is NULL", who);
+  if (row_stride < 3 * lp || (row_stride & 3) || (lp & 1) || (reinterpret_cast<uintptr_t>(qproj) & 15u))
+    return fail(MSDA_ERR_INVALID_ARG, "%s: row_stride=%d must be a multiple of 4 and >= 3*M*L*P=%lld, qproj 16-byte aligned", who, row_stride,
+                (long long)(3 * lp));
+  return 0;
+}
+
+int msda_fused_forward_joint(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                             const void* ref_points, int R, const void* qproj, int row_stride, const void* grid, int mode,
+                             float offset_scale, int N, int S, int M, int D, int G, int L, int Lq, int P, float scale, void* out) {
+  if (!ref_points) return fail(MSDA_ERR_INVALID_ARG, "msda_fused_forward_joint: reference points are NULL");
+  if (int rc = joint_args("msda_fused_forward_joint", qproj, row_stride, M, L, P)) return rc;
+  const FusedArgs fz{static_cast<const float*>(ref_points), static_cast<const float*>(grid), R, mode, offset_scale, row_stride};
+  const float* q = static_cast<const float*>(qproj);
+  return forward_impl("msda_fused_forward_joint", stream, dtype, value, shapes, level_start, q, q + (int64_t)2 * M * L * P, N, S, M, D, G, L,
+                      Lq, P, scale, out, fz);
+}
+
+int msda_fused_backward_joint(void* stream, int dtype, const void* value, const int64_t* shapes, const int64_t* level_start,
+                              const void* ref_points, int R, const void* qproj, int row_stride, const void* grid, int mode,
+                              float offset_scale, const void* grad_out, int N, int S, int M, int D, int G, int L, int Lq, int P,
+                              float scale, void* grad_value, void* grad_qproj, int flags) {
+  if (!ref_points) return fail(MSDA_ERR_INVALID_ARG, "msda_fused_backward_joint: reference points are NULL");
+  if (int rc = joint_args("msda_fused_backward_joint", qproj, row_stride, M, L, P)) return rc;
+  if (!grad_qproj || (reinterpret_cast<uintptr_t>(grad_qproj) & 15u))
+    return fail(MSDA_ERR_INVALID_ARG, "msda_fused_backward_joint: grad_qproj must be a 16-byte aligned [N*Lq, row_stride] buffer");
+  const FusedArgs fz{static_cast<const float*>(ref_points), static_cast<const float*>(grid), R, mode, offset_scale, row_stride};
+  const float* q = static_cast<const float*>(qproj);
+  float* gq = static_cast<float*>(grad_qproj);
+  const int64_t lp2 = (int64_t)2 * M * L * P;
+  return backward_impl("msda_fused_backward_joint", stream, dtype, value, shapes, level_start, q, q + lp2, grad_out, N, S, M, D, G, L, Lq, P,
+                       scale, grad_value, gq, gq + lp2, nullptr, 0, fz, flags);
 }
 
 int mask_logits_forward(void* stream, int in_dtype, int out_dtype, const void* coeff, const void* proto, int B, int Q,

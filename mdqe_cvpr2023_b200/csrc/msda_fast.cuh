@@ -52,6 +52,20 @@ __device__ __forceinline__ void load_loc_aw<__nv_bfloat16>(const __nv_bfloat16* 
   a = __bfloat162float(aw[si]);
 }
 
+// two-index form: loc is addressed in (x, y) pairs by `li`, aw by `ai`.  They differ only for the joint query projection of the
+// fused prologue (fp32; FusedArgs::row_stride), where offsets and logits are column ranges of one [N*Lq, row_stride] matrix.
+template <typename LT>
+__device__ __forceinline__ void load_loc_aw2(const LT* __restrict__ loc, const LT* __restrict__ aw, int64_t li, int64_t ai,
+                                             float& x, float& y, float& a) {
+  load_loc_aw<LT>(loc, aw, li, x, y, a);
+}
+template <>
+__device__ __forceinline__ void load_loc_aw2<float>(const float* __restrict__ loc, const float* __restrict__ aw, int64_t li,
+                                                    int64_t ai, float& x, float& y, float& a) {
+  const float2 t = __ldg(reinterpret_cast<const float2*>(loc) + li);
+  x = t.x; y = t.y; a = __ldg(aw + ai);
+}
+
 __device__ __forceinline__ void store_pair(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 __device__ __forceinline__ void store_pair(__nv_bfloat16* p, float a, float b) {
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);

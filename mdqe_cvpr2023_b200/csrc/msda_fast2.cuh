@@ -75,6 +75,9 @@ struct FusedArgs {
   int R;                // 2 (cx, cy) or 4 (cx, cy, w, h)
   int mode;
   float scale;          // the module's self.scale (8)
+  int row_stride;       // 0: offsets [N*Lq, M*L*P*2] and logits [N*Lq, M*L*P] are dense tensors of their own; > 0 (even): both are
+                        // column ranges of one [N*Lq, row_stride] matrix -- the output of ONE Linear layer over the concatenated
+                        // sampling_offsets / attention_weights weights -- and so are their gradients
 };
 
 // softmax over the LP-lane segment that holds one (query, head) pair; every lane of the warp must call this
@@ -279,7 +282,15 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
       nq = fd_div(pair, div_m);
       m = pair - nq * div_m.d;
       n = fd_div(pair, div_mq);
-      load_loc_aw<LT>(loc, aw, static_cast<int64_t>(pair) * LP + ss, x, y, a);
+      int64_t li = static_cast<int64_t>(pair) * LP + ss, ai = li;
+      if constexpr (std::is_same<LT, float>::value && (LP & (LP - 1)) == 0) {
+        if (fz.ref != nullptr && fz.row_stride > 0) {
+          const int64_t row = static_cast<int64_t>(nq) * fz.row_stride;
+          li = (row >> 1) + m * LP + ss;
+          ai = row + m * LP + ss;
+        }
+      }
+      load_loc_aw2<LT>(loc, aw, li, ai, x, y, a);
     }
     if constexpr (std::is_same<LT, float>::value && (LP & (LP - 1)) == 0) {
       if (fz.ref != nullptr) {                      // fused prologue: (x, y) are raw offsets, a is a raw logit
@@ -479,14 +490,21 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
     const bool has_sample = lane < npair * LP;
     float x = 0.f, y = 0.f, a = 0.f, a_raw = 0.f, mk_x = 1.f, mk_y = 1.f;
     uint32_t n = 0, m = 0, nq = 0;
-    int64_t si = 0;                                  // this lane's sample: index into loc / aw and their gradients
+    int64_t si = 0, li = 0;                          // this lane's sample: index into aw / loc (in pairs) and their gradients
     if (has_sample) {
       const uint32_t pair = pm.pair(p0 + ps);
       nq = fd_div(pair, div_m);
       m = pair - nq * div_m.d;
       n = fd_div(pair, div_mq);
-      si = static_cast<int64_t>(pair) * LP + ss;
-      load_loc_aw<LT>(loc, aw, si, x, y, a);
+      si = li = static_cast<int64_t>(pair) * LP + ss;
+      if constexpr (std::is_same<LT, float>::value && (LP & (LP - 1)) == 0) {
+        if (fz.ref != nullptr && fz.row_stride > 0) {
+          const int64_t row = static_cast<int64_t>(nq) * fz.row_stride;
+          li = (row >> 1) + m * LP + ss;
+          si = row + m * LP + ss;
+        }
+      }
+      load_loc_aw2<LT>(loc, aw, li, si, x, y, a);
     }
     bool fused = false;
     if constexpr (std::is_same<LT, float>::value && (LP & (LP - 1)) == 0) {
@@ -682,7 +700,7 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
         const float tsum = segment_sum<LP>(t);
         if (has_sample) {
           const float inv = 1.f / fz.scale;
-          store_pair(grad_loc + 2 * si, a * g_x * inv * mk_x, a * g_y * inv * mk_y);       // d / d raw offsets
+          store_pair(grad_loc + 2 * li, a * g_x * inv * mk_x, a * g_y * inv * mk_y);       // d / d raw offsets
           st_from_float(grad_aw + si, t - a_raw * tsum);                                   // d / d logits
         }
         continue;

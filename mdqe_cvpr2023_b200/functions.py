@@ -131,6 +131,38 @@ class MSDeformAttnFusedFunction(Function):
         return gv, None, None, None, goff, glog, None, None, None, None
 
 
+class MSDeformAttnFusedJointFunction(Function):
+    """apply(value, spatial_shapes, level_start_index, reference_points, qproj, n_points, grid, mode, offset_scale, scale):
+    MSDeformAttnFusedFunction with the raw offsets and logits given as column ranges of one tensor ``qproj`` [N,Lq,3*M*L*P]
+    (offsets first) -- the output of ONE Linear layer over the concatenated sampling_offsets / attention_weights parameters.
+    The gradient comes back in the same layout, so the query side of a module costs one GEMM forward, one for grad_query and
+    one for the weight gradients (instead of two each and an addition)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, value, spatial_shapes, level_start_index, reference_points, qproj, n_points, grid, mode, offset_scale, scale):
+        ctx.cfg = (int(n_points), int(mode), float(offset_scale), float(scale))
+        n_points, mode, offset_scale, scale = ctx.cfg
+        out = ops.ms_deform_attn_fused_forward_joint(value, spatial_shapes, level_start_index, reference_points, qproj, n_points,
+                                                     grid, mode, offset_scale, scale)
+        ctx.has_grid = grid is not None
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, reference_points, qproj, *([grid] if grid is not None else []))
+        _prezero(ctx, value)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        saved = ctx.saved_tensors
+        value, shapes, starts, ref, qproj = saved[:5]
+        grid = saved[5] if ctx.has_grid else None
+        n_points, mode, offset_scale, scale = ctx.cfg
+        gv, gq = ops.ms_deform_attn_fused_backward_joint(value, shapes, starts, ref, qproj, n_points, grid, mode, offset_scale,
+                                                         grad_output.contiguous(), scale, _take_accumulator(ctx, value.device))
+        return gv, None, None, None, gq, None, None, None, None, None
+
+
 class _MaskLogitsFunction(Function):
     @staticmethod
     def forward(ctx, coeff, proto):

@@ -29,7 +29,8 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnGroupedFunction, tc_linear
+from .functions import (MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnFusedJointFunction, MSDeformAttnGroupedFunction,
+                        tc_linear)
 
 
 def _is_power_of_2(n):
@@ -63,6 +64,7 @@ class MSDeformAttn(nn.Module):
         # {32,24}, L*P in {8,16}, reference points without gradient); set False to run the reference's op sequence
         self.fused_prologue = True
         self.tc_linear = True
+        self.joint_query_proj = True       # fused prologue + tc_linear: offsets and logits from ONE GEMM over the concatenated weights
         self.check_shapes = False          # True: assert sum(H_l * W_l) == S like the reference (one host sync per call)
 
         # what the operator sees as "levels": pyramid levels of a frame, or the frames of a clip
@@ -149,6 +151,28 @@ class MSDeformAttn(nn.Module):
         grid = None if self.pred_offsets else self.sampling_offsets.reshape(H, L, K, 2).contiguous()
         return offsets, logits, grid, (0 if self.pred_offsets else 1)
 
+    def _joint_query_projection(self, query):
+        """sampling_offsets (or sampling_grid_offsets) and attention_weights as ONE Linear layer over the concatenated parameters
+        -> [B,Q,3*H*L*K] with the raw offsets in the first 2*H*L*K columns; None where the tensor-core Linear does not apply.
+        The two `cat`s are the only extra work; autograd hands their gradient back to the two layers as views."""
+        lin = self.sampling_offsets if self.pred_offsets else self.sampling_grid_offsets
+        aw = self.attention_weights
+        if not (self.joint_query_proj and self.tc_linear and ops.linear_supported(query, lin.weight)) or torch.is_autocast_enabled():
+            return None
+        weight = torch.cat([lin.weight, aw.weight], 0)
+        bias = torch.cat([lin.bias, aw.bias], 0)
+        return tc_linear(query, weight, bias)
+
+    def _fused_sampler(self, value, shapes, starts, reference_points, query, scale):
+        reference_points = reference_points.contiguous()
+        qproj = self._joint_query_projection(query)
+        if qproj is not None:
+            grid = None if self.pred_offsets else self.sampling_offsets.reshape(self.n_heads, self.lvl, self.n_points, 2).contiguous()
+            return MSDeformAttnFusedJointFunction.apply(value, shapes, starts, reference_points, qproj, self.n_points, grid,
+                                                        0 if self.pred_offsets else 1, self.scale, scale)
+        offsets, logits, grid, mode = self._fused_inputs(query)
+        return MSDeformAttnFusedFunction.apply(value, shapes, starts, reference_points, offsets, logits, grid, mode, self.scale, scale)
+
     _geometry_cache = []
 
     def _project_value(self, input_flatten, input_padding_mask):
@@ -200,9 +224,7 @@ class MSDeformAttn(nn.Module):
         level_start, shapes_c, _, _ = self._geometry(input_spatial_shapes)
         value = self._project_value(input_flatten, input_padding_mask).contiguous()  # B S H D
         if self.fused_prologue and ops.fused_supported(value, reference_points, 1, self.lvl, self.n_points, query.shape[1]):
-            offsets, logits, grid, mode = self._fused_inputs(query)
-            sampled = MSDeformAttnFusedFunction.apply(value, shapes_c, level_start,
-                                                      reference_points.contiguous(), offsets, logits, grid, mode, self.scale, 1.0)
+            sampled = self._fused_sampler(value, shapes_c, level_start, reference_points, query, 1.0)
             return self._linear(self.output_proj, sampled)
         locations, weights = self._sampling(query, reference_points)
         sampled = MSDeformAttnFunction.apply(value.contiguous(), shapes_c, level_start,
@@ -223,9 +245,7 @@ class MSDeformAttn(nn.Module):
         n_lvl = input_spatial_shapes.shape[0]
         if self.fused_prologue and ops.fused_supported(value, reference_points, n_lvl, T, self.n_points, query.shape[1]):
             # one launch: all pyramid levels (grouped form) + softmax / location arithmetic inside the kernel
-            offsets, logits, grid, mode = self._fused_inputs(query)
-            sampled = MSDeformAttnFusedFunction.apply(value, shapes_g, starts_g, reference_points.contiguous(), offsets, logits,
-                                                      grid, mode, self.scale, 1.0 / n_lvl)
+            sampled = self._fused_sampler(value, shapes_g, starts_g, reference_points, query, 1.0 / n_lvl)
             return self._linear(self.output_proj, sampled)
         locations, weights = self._sampling(query, reference_points)
         locations, weights = locations.contiguous(), weights.contiguous()

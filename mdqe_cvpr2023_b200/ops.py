@@ -257,6 +257,72 @@ def ms_deform_attn_grouped_backward(value, spatial_shapes, level_start_index, sa
     return [grad_value, grad_loc, grad_aw]
 
 
+def _joint_dims(value, shapes, level_start, ref, qproj, grid, mode, n_points, who):
+    if shapes.dim() == 2:
+        shapes, level_start = shapes.unsqueeze(0), level_start.unsqueeze(0)
+    if shapes.dim() != 3 or shapes.shape[2] != 2 or tuple(level_start.shape) != tuple(shapes.shape[:2]):
+        raise RuntimeError(f"{who}: expected spatial_shapes[G,L,2] (or [L,2]) and matching level_start_index")
+    G, L = shapes.shape[0], shapes.shape[1]
+    N, S, M, D = value.shape
+    P = int(n_points)
+    if qproj.dim() != 3 or qproj.shape[0] != N or qproj.shape[2] < 3 * M * L * P or qproj.shape[2] % 4 or qproj.dtype != torch.float32:
+        raise RuntimeError(f"{who}: qproj must be fp32 [N,Lq,row_stride] with row_stride % 4 == 0 and >= 3*M*L*P, got {tuple(qproj.shape)}")
+    Lq = qproj.shape[1]
+    if ref.dim() != 3 or tuple(ref.shape[:2]) != (N, Lq):
+        raise RuntimeError(f"{who}: reference_points must be [N,Lq,R]")
+    if mode == 1 and (grid is None or grid.numel() != M * L * P * 2 or ref.shape[2] != 4):
+        raise RuntimeError(f"{who}: mode 1 needs grid[M,L,P,2] and 4-component reference points")
+    return shapes, level_start, (N, S, M, D, G, L, Lq, P), int(ref.shape[2])
+
+
+def ms_deform_attn_fused_forward_joint(value, spatial_shapes, level_start_index, reference_points, qproj, n_points, grid, mode,
+                                       offset_scale, scale=1.0):
+    """ms_deform_attn_fused_forward with offsets and logits given as column ranges of ONE matrix ``qproj`` [N,Lq,row_stride] -- the
+    output of a single Linear layer over the concatenated sampling_offsets / attention_weights weights (msda_fused_forward_joint)."""
+    who = "ms_deform_attn_fused_forward_joint"
+    tensors = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+               ("reference_points", reference_points), ("qproj", qproj)]
+    if grid is not None:
+        tensors.append(("grid", grid))
+    _check_inputs(who, tensors)
+    shapes, starts, (N, S, M, D, G, L, Lq, P), R = _joint_dims(value, spatial_shapes, level_start_index, reference_points, qproj, grid,
+                                                               mode, n_points, who)
+    lib = _lib.load()
+    with torch.cuda.device(value.device):
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        rc = lib.msda_fused_forward_joint(_stream_ptr(value.device), _lib.MSDA_F32, value.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
+                                          reference_points.data_ptr(), R, qproj.data_ptr(), int(qproj.shape[2]),
+                                          grid.data_ptr() if grid is not None else None, int(mode), float(offset_scale),
+                                          N, S, M, D, G, L, Lq, P, float(scale), out.data_ptr())
+    _lib.check(rc, who)
+    return out
+
+
+def ms_deform_attn_fused_backward_joint(value, spatial_shapes, level_start_index, reference_points, qproj, n_points, grid, mode,
+                                        offset_scale, grad_output, scale=1.0, accumulator=None):
+    """-> (grad_value, grad_qproj); grad_qproj has the layout of qproj (columns beyond 3*M*L*P are zero)."""
+    who = "ms_deform_attn_fused_backward_joint"
+    tensors = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+               ("reference_points", reference_points), ("qproj", qproj), ("grad_output", grad_output)]
+    if grid is not None:
+        tensors.append(("grid", grid))
+    _check_inputs(who, tensors)
+    shapes, starts, (N, S, M, D, G, L, Lq, P), R = _joint_dims(value, spatial_shapes, level_start_index, reference_points, qproj, grid,
+                                                               mode, n_points, who)
+    lib = _lib.load()
+    with torch.cuda.device(value.device):
+        grad_value, _, _, flags = _backward_buffers(value, _lib.MSDA_F32, accumulator, who)
+        exact = qproj.shape[2] == 3 * M * L * P
+        grad_qproj = torch.empty_like(qproj) if exact else torch.zeros_like(qproj)
+        rc = lib.msda_fused_backward_joint(_stream_ptr(value.device), _lib.MSDA_F32, value.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
+                                           reference_points.data_ptr(), R, qproj.data_ptr(), int(qproj.shape[2]),
+                                           grid.data_ptr() if grid is not None else None, int(mode), float(offset_scale),
+                                           grad_output.data_ptr(), N, S, M, D, G, L, Lq, P, float(scale),
+                                           grad_value.data_ptr(), grad_qproj.data_ptr(), flags)
+    _lib.check(rc, who)
+    return grad_value, grad_qproj
+
+
 def fused_supported(value, reference_points, n_groups, n_levels, n_points, n_queries=None, *others):
     """True when msda_fused_forward / msda_fused_backward implement this configuration."""
     return (value.is_cuda and value.dim() == 4 and value.dtype == torch.float32 and value.shape[3] in (32, 24)

@@ -24,17 +24,22 @@ def test_l0_extension_module_name_and_signatures():
         assert nerr(g, z[k]) < 2e-5
 
 
-@pytest.mark.parametrize("tc_linear", [False, True])
+@pytest.mark.parametrize("linear", ["torch", "tc_separate", "tc_joint"])
 @pytest.mark.parametrize("name", ["module_spatial_pred", "module_spatial_grid", "module_temporal_grid"])
-def test_l2_module_matches_reference_module(name, tc_linear):
+def test_l2_module_matches_reference_module(name, linear):
     """Output, input gradients and every parameter gradient against fixtures recorded from the unmodified reference module.
     tc_linear=False keeps the Linear layers on torch (bit-comparable sampling locations); tc_linear=True (the default) runs them
     as 3xTF32 GEMMs, whose ~1e-6 differences can move a sample across a pixel-centre line, where grad_sampling_loc is
-    discontinuous: when that happens the offset-branch gradients are held to 5e-3 instead of 1e-4."""
+    discontinuous: when that happens the offset-branch gradients are held to 5e-3 instead of 1e-4.
+    tc_joint (the default) additionally computes sampling offsets and attention logits with ONE GEMM over the concatenated
+    weights and hands the sampler that matrix (MSDeformAttnFusedJointFunction); tc_separate keeps one GEMM per layer."""
     from mdqe_cvpr2023_b200 import MSDeformAttn
     z = load_golden(name)
     mod = module_from_golden(z, MSDeformAttn).cuda()
+    tc_linear = linear != "torch"
+    assert mod.tc_linear and mod.joint_query_proj, "the shipped default is tc_joint"
     mod.tc_linear = tc_linear
+    mod.joint_query_proj = linear == "tc_joint"
     query, ref, inp, shapes, mask = module_inputs(z, "cuda")
     out = mod(query, ref, inp, shapes, mask)
     assert nerr(out, z["out"]) <= 1e-4

@@ -9,13 +9,14 @@ from tests.helpers import nerr
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["a_tmem", "a_smem"], autouse=True)
-def operand_path(request):
-    """Both forms of the GEMM: A operand through tensor memory (default) and both operands from shared memory (option gemm_smem_a)."""
+@pytest.fixture(params=["stream_k", "tiles"], autouse=True)
+def work_distribution(request):
+    """Both work distributions of the GEMM: contiguous (tile, chunk) ranges per CTA with tiles combined in the output (default) and
+    whole tiles dealt round-robin (option gemm_stream_k = 0)."""
     from mdqe_cvpr2023_b200 import _lib
-    _lib.set_option("gemm_smem_a", 1 if request.param == "a_smem" else 0)
+    _lib.set_option("gemm_stream_k", 1 if request.param == "stream_k" else 0)
     yield request.param
-    _lib.set_option("gemm_smem_a", 0)
+    _lib.set_option("gemm_stream_k", 1)
 
 
 @pytest.mark.parametrize("rows,in_f,out_f", [(4 * 5100, 256, 256), (4 * 5100, 256, 128), (784, 256, 256), (3 * 5100, 192, 192),
@@ -68,6 +69,48 @@ def test_backward_with_bias_in_one_call(rows, in_f, out_f):
             assert nerr(gx, want_x) < 2e-5
         if need_w:
             assert nerr(gw, want_w) < 2e-5
+
+
+def test_repeated_launches_leave_the_tile_flags_clean():
+    """The stream-K form combines split tiles through per-tile flags that every launch must leave zero: many launches in a row, on two
+    streams, inside a CUDA graph, all against the same fp64 answer."""
+    from mdqe_cvpr2023_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    cases = []
+    for rows, in_f, out_f in ((4 * 5100, 256, 256), (784, 256, 128), (300, 512, 96)):
+        x = torch.randn(rows, in_f, device="cuda", generator=g)
+        w = torch.randn(out_f, in_f, device="cuda", generator=g) / in_f ** 0.5
+        b = torch.randn(out_f, device="cuda", generator=g)
+        cases.append((x, w, b, F.linear(x.double(), w.double(), b.double())))
+    for _ in range(40):
+        for x, w, b, want in cases:
+            assert nerr(ops.tc_linear_forward(x, w, b), want) < 2e-5
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for i in range(20):
+        for st in (s1, s2):
+            with torch.cuda.stream(st):
+                x, w, b, want = cases[i % 3]
+                outs.append((ops.tc_linear_forward(x, w, b), want))
+    torch.cuda.synchronize()
+    for y, want in outs:
+        assert nerr(y, want) < 2e-5
+    x, w, b, want = cases[0]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.tc_linear_forward(x, w, b)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        y = ops.tc_linear_forward(x, w, b)
+        gx, _ = ops.tc_linear_backward(y, x, w, True, False)
+    for _ in range(5):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert nerr(y, want) < 2e-5
+    assert nerr(gx, want @ w.double()) < 2e-5
 
 
 def test_tc_linear_rejects_unsupported():

@@ -10,8 +10,8 @@ import torch.nn.functional as F
 
 from mdqe_cvpr2023_b200 import _lib, ops
 
-if "--smem-a" in sys.argv:                       # A/B: both GEMM operands from shared memory (the first form of gemm3x_kernel)
-    _lib.set_option("gemm_smem_a", 1)
+if "--tiles" in sys.argv:                        # A/B: whole tiles dealt round-robin instead of contiguous (tile, chunk) ranges
+    _lib.set_option("gemm_stream_k", 0)
 
 torch.backends.cuda.matmul.allow_tf32 = False
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -73,4 +73,4 @@ for name, rows, in_f, out_f in [("enc value/output/offsets proj (R50_360, T=4)",
     res.append(r)
     print(json.dumps({k: (round(v, 1) if isinstance(v, float) else v) for k, v in r.items()}))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(res, open("gpurun_out/linear_bench%s.json" % ("_smem_a" if "--smem-a" in sys.argv else ""), "w"), indent=1)
+json.dump(res, open("gpurun_out/linear_bench%s.json" % ("_tiles" if "--tiles" in sys.argv else ""), "w"), indent=1)
