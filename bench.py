@@ -1039,8 +1039,7 @@ def main():
             shw = torch.tensor(PYRAMID, device=device)
             lsw = torch.cat([shw.new_zeros(1), (shw[:, 0] * shw[:, 1]).cumsum(0)[:-1]])
             outw = torch.empty(Nw, Sw, HEADS * HEAD_DIM, device=device)
-            stw = torch.cuda.current_stream(device).cuda_stream
-            run_w = lambda: libmod.check(lib.msda_forward(stw, libmod.MSDA_F32, vw.data_ptr(), shw.data_ptr(), lsw.data_ptr(), locw.data_ptr(),
+            run_w = lambda: libmod.check(lib.msda_forward(torch.cuda.current_stream(device).cuda_stream, libmod.MSDA_F32, vw.data_ptr(), shw.data_ptr(), lsw.data_ptr(), locw.data_ptr(),
                                                           aww.data_ptr(), Nw, Sw, HEADS, HEAD_DIM, len(PYRAMID), Sw, POINTS, outw.data_ptr()), "msda_forward")
             w_ms = time_replays(torch, capture(torch, run_w), n_other)
             bytes_w = 4 * (vw.numel() + locw.numel() + aww.numel() + outw.numel())

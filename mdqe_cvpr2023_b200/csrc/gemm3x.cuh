@@ -46,7 +46,7 @@ constexpr uint32_t kG3TmemACol = 256;                                  // first 
 constexpr uint32_t kG3OutBytes = kG3Tile * 128u;                       // staging: 128 rows x 32 columns
 constexpr int kG3FlagSpins = 1 << 22;                                  // x 64 ns: a lost flag costs a quarter second, not a hang
 
-enum : int { kG3ModeStore = 0, kG3ModeReduce = 1, kG3ModeStreamK = 2 };
+enum : int { kG3ModeStore = 0, kG3ModeReduce = 1, kG3ModeStreamK = 2, kG3ModeStreamKReduce = 3 };
 
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -76,12 +76,13 @@ __device__ __forceinline__ uint32_t tf32_lo(uint32_t v) { return __float_as_uint
 struct G3Seg { int tm, tn, c0, c1, out, tile; bool with_bias; };
 
 // The same walk is made by all four roles of a CTA.  mode 0 / 1: items (split, tm, tn) dealt round-robin, the reduction cut into
-// `chunks_per_split` ranges; mode 2: one contiguous range of tile-major (tile, chunk) units per CTA.
+// `chunks_per_split` ranges; mode 2: one contiguous range of tile-major (tile, chunk) units per CTA; mode 3: the same ranges with
+// every stretch reduce-added into a zeroed C (the weight gradient: few tiles, a long reduction -- no flags, no bias).
 struct G3Walk {
   int mode, n_kchunks, cps, tiles_m, tiles_n, cur, end, stride;
   __device__ G3Walk(int mode_, int n_kchunks_, int cps_, int tiles_m_, int tiles_n_, int n_items)
       : mode(mode_), n_kchunks(n_kchunks_), cps(cps_), tiles_m(tiles_m_), tiles_n(tiles_n_) {
-    if (mode == kG3ModeStreamK) {
+    if (mode >= kG3ModeStreamK) {
       const int q = n_items / static_cast<int>(gridDim.x), r = n_items % static_cast<int>(gridDim.x), c = static_cast<int>(blockIdx.x);
       cur = c * q + min(c, r);
       end = cur + q + (c < r ? 1 : 0);
@@ -94,15 +95,15 @@ struct G3Walk {
   }
   __device__ bool next(G3Seg& s) {
     if (cur >= end) return false;
-    if (mode == kG3ModeStreamK) {
+    if (mode >= kG3ModeStreamK) {
       s.tile = cur / n_kchunks;
       s.c0 = cur - s.tile * n_kchunks;
       s.c1 = min(n_kchunks, s.c0 + (end - cur));
       cur += s.c1 - s.c0;
       s.tm = s.tile / tiles_n;
       s.tn = s.tile - s.tm * tiles_n;
-      s.out = s.c1 == n_kchunks ? (s.c0 == 0 ? 0 : 2) : 3;
-      s.with_bias = s.out != 3;
+      s.out = mode == kG3ModeStreamKReduce ? 1 : (s.c1 == n_kchunks ? (s.c0 == 0 ? 0 : 2) : 3);
+      s.with_bias = (s.out & 1) == 0;
     } else {
       const int r = cur / tiles_n, split = r / tiles_m;
       s.tn = cur - r * tiles_n;
@@ -160,6 +161,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = s_tmem_base;
+  pdl_wait();            // launched with programmatic stream serialization: everything above overlaps the previous kernel's drain
 
   G3Walk walk(mode, n_kchunks, chunks_per_split, tiles_m, tiles_n, n_items);
   G3Seg sg;

@@ -2,6 +2,7 @@
 // See include/msda_b200.h (mask_logits_*) for the contract.
 #include <cudaTypedefs.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "mask_simt.cuh"
@@ -416,8 +417,11 @@ static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const 
   int64_t n_items = tiles * splits;
   int mode = splits > 1 ? kG3ModeReduce : kG3ModeStore;
   int* flags = nullptr;
-  if (splits == 1 && tiles * n_kchunks < (int64_t(1) << 31) && option("gemm_stream_k") != 0 && (tiles % sms != 0) &&
-      (flags = gemm_tile_flags(st, static_cast<int>(tiles))) != nullptr) {
+  const bool stream_k = option("gemm_stream_k") != 0 && tiles * n_kchunks < (int64_t(1) << 31);
+  if (splits > 1 && stream_k) {
+    mode = kG3ModeStreamKReduce;                            // contiguous unit ranges, every stretch added into the zeroed C
+    n_items = tiles * n_kchunks;
+  } else if (splits == 1 && stream_k && (tiles % sms != 0) && (flags = gemm_tile_flags(st, static_cast<int>(tiles))) != nullptr) {
     mode = kG3ModeStreamK;
     n_items = tiles * n_kchunks;
   }
@@ -430,8 +434,9 @@ static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const 
   if (int rc = make_map_c(&map_c, C, (uint64_t)N, (uint64_t)M)) return rc;
   if (int rc = ensure_func_attr(gemm3x_kernel<kAMn, kBMn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes)) return rc;
   const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);
-  gemm3x_kernel<kAMn, kBMn><<<grid, kG3Threads, kG3SmemBytes, st>>>(map_a, map_b, map_c, bias, row_mask, col_sum_a, flags, (int)M, (int)N,
-                                                                    n_kchunks, cps, tiles_m, tiles_n, (int)n_items, mode);
+  if (int rc = check_cuda(launch_kernel(gemm3x_kernel<kAMn, kBMn>, dim3(grid), dim3(kG3Threads), kG3SmemBytes, st, map_a, map_b, map_c, bias,
+                                        row_mask, col_sum_a, flags, (int)M, (int)N, n_kchunks, cps, tiles_m, tiles_n, (int)n_items, mode),
+                          "gemm3x_kernel launch")) return rc;
   return after_launch("gemm3x_kernel");
 }
 
@@ -465,7 +470,7 @@ int linear_backward_dispatch(cudaStream_t st, const void* gy, const void* x, con
   }
   if (gw) {                                                 // dW[o, i] = sum_r dy[r, o] x[r, i]: reduction over the rows, split across the SMs
     const int tiles = ((out_f + kG3Tile - 1) / kG3Tile) * ((in_f + kG3Tile - 1) / kG3Tile);
-    const int splits = (sm_count() + tiles - 1) / tiles;
+    const int splits = std::max(2, sm_count() / tiles);     // round-robin form: at most one item per SM
     if (int rc = launch_gemm3x<true, true>(st, "tc_linear_backward", gy, x, gw, out_f, in_f, rows, nullptr, nullptr, splits,
                                            fuse_bias ? static_cast<float*>(gb) : nullptr)) return rc;
   }
