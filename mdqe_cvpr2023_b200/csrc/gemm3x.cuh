@@ -46,7 +46,7 @@ constexpr uint32_t kG3TmemACol = 256;                                  // first 
 constexpr uint32_t kG3OutBytes = kG3Tile * 128u;                       // staging: 128 rows x 32 columns
 constexpr int kG3FlagSpins = 1 << 22;                                  // x 64 ns: a lost flag costs a quarter second, not a hang
 
-enum : int { kG3ModeStore = 0, kG3ModeReduce = 1, kG3ModeStreamK = 2, kG3ModeStreamKReduce = 3 };
+enum : int { kG3ModeStore = 0, kG3ModeReduce = 1, kG3ModeStreamK = 2 };
 
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -76,13 +76,12 @@ __device__ __forceinline__ uint32_t tf32_lo(uint32_t v) { return __float_as_uint
 struct G3Seg { int tm, tn, c0, c1, out, tile; bool with_bias; };
 
 // The same walk is made by all four roles of a CTA.  mode 0 / 1: items (split, tm, tn) dealt round-robin, the reduction cut into
-// `chunks_per_split` ranges; mode 2: one contiguous range of tile-major (tile, chunk) units per CTA; mode 3: the same ranges with
-// every stretch reduce-added into a zeroed C (the weight gradient: few tiles, a long reduction -- no flags, no bias).
+// `chunks_per_split` ranges; mode 2: one contiguous range of tile-major (tile, chunk) units per CTA.
 struct G3Walk {
   int mode, n_kchunks, cps, tiles_m, tiles_n, cur, end, stride;
   __device__ G3Walk(int mode_, int n_kchunks_, int cps_, int tiles_m_, int tiles_n_, int n_items)
       : mode(mode_), n_kchunks(n_kchunks_), cps(cps_), tiles_m(tiles_m_), tiles_n(tiles_n_) {
-    if (mode >= kG3ModeStreamK) {
+    if (mode == kG3ModeStreamK) {
       const int q = n_items / static_cast<int>(gridDim.x), r = n_items % static_cast<int>(gridDim.x), c = static_cast<int>(blockIdx.x);
       cur = c * q + min(c, r);
       end = cur + q + (c < r ? 1 : 0);
@@ -95,15 +94,15 @@ struct G3Walk {
   }
   __device__ bool next(G3Seg& s) {
     if (cur >= end) return false;
-    if (mode >= kG3ModeStreamK) {
+    if (mode == kG3ModeStreamK) {
       s.tile = cur / n_kchunks;
       s.c0 = cur - s.tile * n_kchunks;
       s.c1 = min(n_kchunks, s.c0 + (end - cur));
       cur += s.c1 - s.c0;
       s.tm = s.tile / tiles_n;
       s.tn = s.tile - s.tm * tiles_n;
-      s.out = mode == kG3ModeStreamKReduce ? 1 : (s.c1 == n_kchunks ? (s.c0 == 0 ? 0 : 2) : 3);
-      s.with_bias = (s.out & 1) == 0;
+      s.out = s.c1 == n_kchunks ? (s.c0 == 0 ? 0 : 2) : 3;
+      s.with_bias = s.out != 3;
     } else {
       const int r = cur / tiles_n, split = r / tiles_m;
       s.tn = cur - r * tiles_n;
@@ -325,6 +324,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           }
         }
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      // the accumulator is free again: before the flag traffic, which
+      __syncwarp();                                                         // waits for the bulk stores to land
+      if (lane == 0) mbar_arrive(bar_tempty(a));
       if (is_issuer && sg.out >= 2) {
         if (sg.out == 2) {                                                  // publish: both column halves stored -> flag = 2
           asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -334,9 +336,6 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           atomicExch(flags + sg.tile, 0);                                   // every part has passed the wait: leave the flag clean for the next launch
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty(a));
     }
     if (is_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging tiles have been read; the writes complete with the grid
   }

@@ -417,11 +417,12 @@ static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const 
   int64_t n_items = tiles * splits;
   int mode = splits > 1 ? kG3ModeReduce : kG3ModeStore;
   int* flags = nullptr;
-  const bool stream_k = option("gemm_stream_k") != 0 && tiles * n_kchunks < (int64_t(1) << 31);
-  if (splits > 1 && stream_k) {
-    mode = kG3ModeStreamKReduce;                            // contiguous unit ranges, every stretch added into the zeroed C
-    n_items = tiles * n_kchunks;
-  } else if (splits == 1 && stream_k && (tiles % sms != 0) && (flags = gemm_tile_flags(st, static_cast<int>(tiles))) != nullptr) {
+  // contiguous ranges pay when whole tiles dealt round-robin would leave the SMs idle for >= 4 chunk times on average (or there are
+  // fewer tiles than SMs): the flag hand-over of the split tiles costs about one (A/B per shape: profiles/r02ao_linear_bench_*.json)
+  const int64_t idle_units = ((tiles + sms - 1) / sms * sms - tiles) * n_kchunks;
+  const bool worth = tiles < sms || idle_units >= 4 * (int64_t)sms || option("gemm_stream_k") == 2;
+  if (splits == 1 && tiles * n_kchunks < (int64_t(1) << 31) && option("gemm_stream_k") != 0 && worth &&
+      (flags = gemm_tile_flags(st, static_cast<int>(tiles))) != nullptr) {
     mode = kG3ModeStreamK;
     n_items = tiles * n_kchunks;
   }
@@ -470,7 +471,7 @@ int linear_backward_dispatch(cudaStream_t st, const void* gy, const void* x, con
   }
   if (gw) {                                                 // dW[o, i] = sum_r dy[r, o] x[r, i]: reduction over the rows, split across the SMs
     const int tiles = ((out_f + kG3Tile - 1) / kG3Tile) * ((in_f + kG3Tile - 1) / kG3Tile);
-    const int splits = std::max(2, sm_count() / tiles);     // round-robin form: at most one item per SM
+    const int splits = std::max(2, sm_count() / tiles);     // at most one (tile, reduction range) item per SM: 6 tiles x 24, not 25
     if (int rc = launch_gemm3x<true, true>(st, "tc_linear_backward", gy, x, gw, out_f, in_f, rows, nullptr, nullptr, splits,
                                            fuse_bias ? static_cast<float*>(gb) : nullptr)) return rc;
   }

@@ -14,7 +14,7 @@ def work_distribution(request):
     """Both work distributions of the GEMM: contiguous (tile, chunk) ranges per CTA with tiles combined in the output (default) and
     whole tiles dealt round-robin (option gemm_stream_k = 0)."""
     from mdqe_cvpr2023_b200 import _lib
-    _lib.set_option("gemm_stream_k", 1 if request.param == "stream_k" else 0)
+    _lib.set_option("gemm_stream_k", 2 if request.param == "stream_k" else 0)              # 2 = on every shape, 1 (default) = where it pays
     yield request.param
     _lib.set_option("gemm_stream_k", 1)
 
