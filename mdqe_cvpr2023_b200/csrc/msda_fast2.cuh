@@ -239,7 +239,7 @@ __device__ __forceinline__ void merge_level_slots(Slot (&sl)[4], uint32_t key, i
 #endif
 // MINB = minimum resident CTAs per SM promised to ptxas: 3 leaves it 80+ registers, enough to keep a whole
 // batch of gathers in flight; 6 reproduces the register-lean, load-by-load schedule.
-template <typename VT, typename LT, int D, int LP, int MINB, bool GROUPED>
+template <typename VT, typename LT, int D, int LP, int MINB, bool GROUPED, bool FUSED = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                       const int64_t* __restrict__ level_start, const LT* __restrict__ loc,
@@ -247,6 +247,9 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
                       int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq,
                       int G, float scale, FusedArgs fz, int hrun) {
   // G > 1: "grouped" (temporal) form -- G level tables share loc/aw, out = scale * sum_g (see msda_forward_grouped)
+  // FUSED: the module's softmax / location arithmetic in phase 1 (fz) -- its own instantiation, so that the plain operator carries
+  // none of it (as a run-time branch the joint-layout addressing alone cost the encoder-sized kernels 1-2 %: profiles/r02ap)
+  constexpr bool kFused = FUSED && std::is_same<LT, float>::value && (LP & (LP - 1)) == 0;
   using C = Cfg2<VT, D, LP>;
   __shared__ LevelInfo s_lvl[kMaxLevels];
   __shared__ __align__(16) Slot s_slot[kWarpsPerCta][C::QPW * C::NSLOT];
@@ -283,8 +286,8 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
       m = pair - nq * div_m.d;
       n = fd_div(pair, div_mq);
       int64_t li = static_cast<int64_t>(pair) * LP + ss, ai = li;
-      if constexpr (std::is_same<LT, float>::value && (LP & (LP - 1)) == 0) {
-        if (fz.ref != nullptr && fz.row_stride > 0) {
+      if constexpr (kFused) {
+        if (fz.row_stride > 0) {
           const int64_t row = static_cast<int64_t>(nq) * fz.row_stride;
           li = (row >> 1) + m * LP + ss;
           ai = row + m * LP + ss;
@@ -292,12 +295,10 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
       }
       load_loc_aw2<LT>(loc, aw, li, ai, x, y, a);
     }
-    if constexpr (std::is_same<LT, float>::value && (LP & (LP - 1)) == 0) {
-      if (fz.ref != nullptr) {                      // fused prologue: (x, y) are raw offsets, a is a raw logit
-        a = segment_softmax<LP>(a, has_sample);
-        float mk_x, mk_y;
-        if (has_sample) fused_location(fz, nq, m, ss, LP, x, y, mk_x, mk_y);
-      }
+    if constexpr (kFused) {                         // fused prologue: (x, y) are raw offsets, a is a raw logit
+      a = segment_softmax<LP>(a, has_sample);
+      float mk_x, mk_y;
+      if (has_sample) fused_location(fz, nq, m, ss, LP, x, y, mk_x, mk_y);
     }
     a *= scale;
     // GROUPED keeps one accumulator set per pair alive across the G level tables; the plain operator (G == 1)
@@ -441,7 +442,7 @@ msda_fwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
 #endif
 constexpr int kBwdBatch = MSDA_BWD_BATCH;    // gathers in flight per lane (see the corner loop)
 
-template <typename VT, typename LT, int D, int LP, bool GROUPED>
+template <typename VT, typename LT, int D, int LP, bool GROUPED, bool FUSED = false>
 __global__ void __launch_bounds__(kThreads, GROUPED ? MSDA_BWD_MINB_GROUPED : MSDA_BWD_MINB)
 msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                       const int64_t* __restrict__ level_start, const LT* __restrict__ loc,
@@ -449,6 +450,7 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
                       float* __restrict__ grad_value, LT* __restrict__ grad_loc, LT* __restrict__ grad_aw,
                       int S, int M, int L, int P, uint32_t n_pairs, int chunk_pairs, FastDiv div_m, FastDiv div_mq,
                       int G, float scale, FusedArgs fz, int merge, int hrun) {
+  constexpr bool kFused = FUSED && std::is_same<LT, float>::value && (LP & (LP - 1)) == 0;    // see the forward kernel
   using C = Cfg2<VT, D, LP>;
   // <grad_out, corner row> per (corner, sample): [4][40] floats per warp.  The partials are folded inside the
   // corner group with shuffles first, so the tile stays tiny and shared memory stays small: the first version
@@ -497,8 +499,8 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
       m = pair - nq * div_m.d;
       n = fd_div(pair, div_mq);
       si = li = static_cast<int64_t>(pair) * LP + ss;
-      if constexpr (std::is_same<LT, float>::value && (LP & (LP - 1)) == 0) {
-        if (fz.ref != nullptr && fz.row_stride > 0) {
+      if constexpr (kFused) {
+        if (fz.row_stride > 0) {
           const int64_t row = static_cast<int64_t>(nq) * fz.row_stride;
           li = (row >> 1) + m * LP + ss;
           si = row + m * LP + ss;
@@ -506,13 +508,9 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
       }
       load_loc_aw2<LT>(loc, aw, li, si, x, y, a);
     }
-    bool fused = false;
-    if constexpr (std::is_same<LT, float>::value && (LP & (LP - 1)) == 0) {
-      fused = fz.ref != nullptr;
-      if (fused) {                                  // fused prologue: (x, y) are raw offsets, a is a raw logit
-        a = segment_softmax<LP>(a, has_sample);
-        if (has_sample) fused_location(fz, nq, m, ss, LP, x, y, mk_x, mk_y);
-      }
+    if constexpr (kFused) {                         // fused prologue: (x, y) are raw offsets, a is a raw logit
+      a = segment_softmax<LP>(a, has_sample);
+      if (has_sample) fused_location(fz, nq, m, ss, LP, x, y, mk_x, mk_y);
     }
     a_raw = a;
     a *= scale;                                     // d out / d value carries the group scale; aw/loc grads are rescaled below
@@ -693,8 +691,8 @@ msda_bwd_fast2_kernel(const VT* __restrict__ value, const int64_t* __restrict__ 
       __syncwarp();
     }
 
-    if constexpr (std::is_same<LT, float>::value && (LP & (LP - 1)) == 0) {
-      if (fused) {
+    if constexpr (kFused) {
+      {
         // softmax backward inside the pair's lane segment, chain rule through loc = ref + offsets / scale (+ clamp)
         const float t = a_raw * (scale * g_aw);
         const float tsum = segment_sum<LP>(t);

@@ -133,14 +133,21 @@ inline void launch_fwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int ch
                            const int64_t* lsi, const LT* lc, const LT* a, VT* o) {
   const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
   const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
-#define MSDA_FWD2(LPV, GRP) launch_kernel(msda_fwd_fast2_kernel<VT, LT, D, LPV, MINB, GRP>, grid, dim3(kThreads), 0, st, \
+#define MSDA_FWD2_(LPV, GRP, FUS) launch_kernel(msda_fwd_fast2_kernel<VT, LT, D, LPV, MINB, GRP, FUS>, grid, dim3(kThreads), 0, st, \
       v, shapes, lsi, lc, a, o, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz, hrun)
+  // the fused prologue (fp32, L*P a power of two: fused_supported) is its own instantiation of the kernels
+#define MSDA_FWD2(LPV, GRP) do { \
+      if constexpr (std::is_same<VT, float>::value && std::is_same<LT, float>::value && ((LPV) & ((LPV) - 1)) == 0) { \
+        if (pb.fz.ref != nullptr) { MSDA_FWD2_(LPV, GRP, true); break; } \
+      } \
+      MSDA_FWD2_(LPV, GRP, false); } while (0)
   const bool grouped = pb.G > 1 || pb.scale != 1.f;
   switch (pb.L * pb.P) {
     case 16: if (grouped) MSDA_FWD2(16, true); else MSDA_FWD2(16, false); break;
     case 12: if (grouped) MSDA_FWD2(12, true); else MSDA_FWD2(12, false); break;
     default: if (grouped) MSDA_FWD2(8, true); else MSDA_FWD2(8, false); break;
   }
+#undef MSDA_FWD2_
 #undef MSDA_FWD2
 }
 
@@ -149,10 +156,15 @@ inline void launch_bwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int ch
                            const int64_t* lsi, const LT* lc, const LT* a, const VT* go, float* gv, LT* gl, LT* ga) {
   const FastDiv dm = make_fastdiv(pb.M), dmq = make_fastdiv((uint32_t)pb.M * (uint32_t)pb.Lq);
   const uint32_t np = static_cast<uint32_t>(pb.n_pairs);
-#define MSDA_BWD2(LPV, GRP) do { \
-      prefer_small_carveout(msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP>, (GRP) ? 2 : MSDA_BWD_MINB); \
-      launch_kernel(msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP>, grid, dim3(kThreads), 0, st, \
+#define MSDA_BWD2_(LPV, GRP, FUS) do { \
+      prefer_small_carveout(msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP, FUS>, (GRP) ? 2 : MSDA_BWD_MINB); \
+      launch_kernel(msda_bwd_fast2_kernel<VT, LT, D, LPV, GRP, FUS>, grid, dim3(kThreads), 0, st, \
       v, shapes, lsi, lc, a, go, gv, gl, ga, pb.S, pb.M, pb.L, pb.P, np, chunk, dm, dmq, pb.G, pb.scale, pb.fz, merge, hrun); } while (0)
+#define MSDA_BWD2(LPV, GRP) do { \
+      if constexpr (std::is_same<VT, float>::value && std::is_same<LT, float>::value && ((LPV) & ((LPV) - 1)) == 0) { \
+        if (pb.fz.ref != nullptr) { MSDA_BWD2_(LPV, GRP, true); break; } \
+      } \
+      MSDA_BWD2_(LPV, GRP, false); } while (0)
   const bool grouped = pb.G > 1 || pb.scale != 1.f;
   const int merge = (options().bwd_merge.load() != 0 && (pb.P == 4 || pb.P == 2)) ? pb.P : 0;
   switch (pb.L * pb.P) {
@@ -161,6 +173,7 @@ inline void launch_bwd2_lp(cudaStream_t st, const Problem& pb, dim3 grid, int ch
     default: if (grouped) MSDA_BWD2(8, true); else MSDA_BWD2(8, false); break;
   }
 #undef MSDA_BWD2
+#undef MSDA_BWD2_
 }
 
 template <typename VT, typename LT>
