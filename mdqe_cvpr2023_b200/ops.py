@@ -63,8 +63,33 @@ def _dims(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, i
     return N, S, M, D, L, Lq, P
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream_ptr(device):
+    """cudaStream_t of torch's current stream on `device` (the raw getter when this torch has it: the Stream object costs microseconds,
+    and an eager module step is host-bound -- tools/host_overhead_profile.py)."""
+    if _raw_stream is not None and device.index is not None:
+        return _raw_stream(device.index)
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class _on_device:
+    """`with _on_device(dev)` that does nothing when `dev` already is the current device (the usual case; the context
+    manager costs two device switches and several Python frames per call)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if (device.index is None or device.index == torch.cuda.current_device()) else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False
 
 
 def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
@@ -75,7 +100,7 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     N, S, M, D, L, Lq, P = _dims(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step, who)
     code = _dtype_code(value, sampling_loc, attn_weight, who)
     lib = _lib.load()
-    with torch.cuda.device(value.device):
+    with _on_device(value.device):
         out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
         rc = lib.msda_forward(_stream_ptr(value.device), code, value.data_ptr(), spatial_shapes.data_ptr(),
                               level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
@@ -103,7 +128,7 @@ def pack_value(value, spatial_shapes, level_start_index):
     nbytes = lib.msda_packed_value_bytes(N, S, M, D)
     if nbytes == 0:
         raise RuntimeError(f"{who}: the paired-corner layout needs D = 32 (got {D})")
-    with torch.cuda.device(value.device):
+    with _on_device(value.device):
         packed = torch.empty(nbytes, dtype=torch.uint8, device=value.device)
         rc = lib.msda_pack_value(_stream_ptr(value.device), _lib.MSDA_F32 if value.dtype == torch.float32 else _lib.MSDA_BF16,
                                  value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), N, S, M, D,
@@ -127,7 +152,7 @@ def ms_deform_attn_forward_packed(packed, value_shape, spatial_shapes, level_sta
     if packed.numel() * packed.element_size() < lib.msda_packed_value_bytes(N, S, M, D):
         raise RuntimeError(f"{who}: packed tensor too small for value shape {tuple(value_shape)}")
     code = _lib.MSDA_BF16 if sampling_loc.dtype == torch.bfloat16 else _lib.MSDA_BF16_LOC32
-    with torch.cuda.device(packed.device):
+    with _on_device(packed.device):
         out = torch.empty((N, Lq, M * D), dtype=torch.bfloat16, device=packed.device)
         rc = lib.msda_forward_packed(_stream_ptr(packed.device), code, packed.data_ptr(), spatial_shapes.data_ptr(),
                                      level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
@@ -173,7 +198,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
         raise RuntimeError(f"{who}: grad_output must be {value.dtype} with {N * Lq * M * D} elements")
     code = _dtype_code(value, sampling_loc, attn_weight, who)
     lib = _lib.load()
-    with torch.cuda.device(value.device):
+    with _on_device(value.device):
         grad_value, ws, ws_bytes, flags = _backward_buffers(value, code, accumulator, who)
         grad_loc = torch.empty_like(sampling_loc)
         grad_aw = torch.empty_like(attn_weight)
@@ -226,7 +251,7 @@ def ms_deform_attn_grouped_forward(value, spatial_shapes, level_start_index, sam
     N, S, M, D, G, L, Lq, P = _grouped_dims(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, who)
     code = _dtype_code(value, sampling_loc, attn_weight, who)
     lib = _lib.load()
-    with torch.cuda.device(value.device):
+    with _on_device(value.device):
         out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
         rc = lib.msda_forward_grouped(_stream_ptr(value.device), code, value.data_ptr(), spatial_shapes.data_ptr(),
                                       level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
@@ -245,7 +270,7 @@ def ms_deform_attn_grouped_backward(value, spatial_shapes, level_start_index, sa
         raise RuntimeError(f"{who}: grad_output must be {value.dtype} with {N * Lq * M * D} elements")
     code = _dtype_code(value, sampling_loc, attn_weight, who)
     lib = _lib.load()
-    with torch.cuda.device(value.device):
+    with _on_device(value.device):
         grad_value, ws, ws_bytes, flags = _backward_buffers(value, code, accumulator, who)
         grad_loc, grad_aw = torch.empty_like(sampling_loc), torch.empty_like(attn_weight)
         rc = lib.msda_backward_grouped_flags(_stream_ptr(value.device), code, value.data_ptr(), spatial_shapes.data_ptr(),
@@ -288,7 +313,7 @@ def ms_deform_attn_fused_forward_joint(value, spatial_shapes, level_start_index,
     shapes, starts, (N, S, M, D, G, L, Lq, P), R = _joint_dims(value, spatial_shapes, level_start_index, reference_points, qproj, grid,
                                                                mode, n_points, who)
     lib = _lib.load()
-    with torch.cuda.device(value.device):
+    with _on_device(value.device):
         out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
         rc = lib.msda_fused_forward_joint(_stream_ptr(value.device), _lib.MSDA_F32, value.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
                                           reference_points.data_ptr(), R, qproj.data_ptr(), int(qproj.shape[2]),
@@ -310,7 +335,7 @@ def ms_deform_attn_fused_backward_joint(value, spatial_shapes, level_start_index
     shapes, starts, (N, S, M, D, G, L, Lq, P), R = _joint_dims(value, spatial_shapes, level_start_index, reference_points, qproj, grid,
                                                                mode, n_points, who)
     lib = _lib.load()
-    with torch.cuda.device(value.device):
+    with _on_device(value.device):
         grad_value, _, _, flags = _backward_buffers(value, _lib.MSDA_F32, accumulator, who)
         exact = qproj.shape[2] == 3 * M * L * P
         grad_qproj = torch.empty_like(qproj) if exact else torch.zeros_like(qproj)
@@ -361,7 +386,7 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, refer
     shapes, starts, (N, S, M, D, G, L, Lq, P), R = _fused_dims(value, spatial_shapes, level_start_index, reference_points,
                                                                offsets, logits, grid, mode, who)
     lib = _lib.load()
-    with torch.cuda.device(value.device):
+    with _on_device(value.device):
         out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
         rc = lib.msda_fused_forward(_stream_ptr(value.device), _lib.MSDA_F32, value.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
                                     reference_points.data_ptr(), R, offsets.data_ptr(), logits.data_ptr(),
@@ -382,7 +407,7 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, refe
     shapes, starts, (N, S, M, D, G, L, Lq, P), R = _fused_dims(value, spatial_shapes, level_start_index, reference_points,
                                                                offsets, logits, grid, mode, who)
     lib = _lib.load()
-    with torch.cuda.device(value.device):
+    with _on_device(value.device):
         grad_value, _, _, flags = _backward_buffers(value, _lib.MSDA_F32, accumulator, who)
         grad_offsets, grad_logits = torch.empty_like(offsets), torch.empty_like(logits)
         rc = lib.msda_fused_backward_flags(_stream_ptr(value.device), _lib.MSDA_F32, value.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
@@ -414,7 +439,7 @@ def mask_logits_forward(coeff, proto, out_dtype=None):
     for s in plane:
         ncols *= s
     lib = _lib.load()
-    with torch.cuda.device(coeff.device):
+    with _on_device(coeff.device):
         out = torch.empty((B, Q) + plane, dtype=out_dtype, device=coeff.device)
         rc = lib.mask_logits_forward(_stream_ptr(coeff.device), _MASK_CODES[coeff.dtype], _MASK_CODES[out_dtype],
                                      coeff.data_ptr(), proto.data_ptr(), B, Q, K, ncols, out.data_ptr())
@@ -434,7 +459,7 @@ def mask_logits_backward(coeff, proto, grad_out, need_coeff=True, need_proto=Tru
     B, Q, K = coeff.shape
     ncols = proto.numel() // max(1, B * K)
     lib = _lib.load()
-    with torch.cuda.device(coeff.device):
+    with _on_device(coeff.device):
         gc = torch.empty_like(coeff) if need_coeff else None
         gp = torch.empty_like(proto) if need_proto else None
         rc = lib.mask_logits_backward(_stream_ptr(coeff.device), _MASK_CODES[coeff.dtype], coeff.data_ptr(),
@@ -475,7 +500,7 @@ def tc_linear_forward(x, weight, bias=None, row_mask=None):
             raise RuntimeError(f"{who}: row_mask must have one entry per row of x")
         mask8 = row_mask.view(torch.uint8) if row_mask.dtype == torch.bool else row_mask.to(torch.uint8)
     lib = _lib.load()
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         y = torch.empty(x.shape[:-1] + (out_f,), dtype=torch.float32, device=x.device)
         rc = lib.tc_linear_forward(_stream_ptr(x.device), x.data_ptr(), weight.data_ptr(),
                                    bias.data_ptr() if bias is not None else None,
@@ -492,7 +517,7 @@ def tc_linear_bias_grad(grad_y):
     rows = grad_y.numel() // max(out_f, 1)
     if out_f % 4 != 0 or grad_y.data_ptr() % 16 != 0 or grad_y.dtype != torch.float32:
         return grad_y.reshape(-1, out_f).sum(0)
-    with torch.cuda.device(grad_y.device):
+    with _on_device(grad_y.device):
         gb = torch.empty(out_f, dtype=torch.float32, device=grad_y.device)
         rc = _lib.load().tc_linear_bias_grad(_stream_ptr(grad_y.device), grad_y.data_ptr(), rows, out_f, gb.data_ptr())
     _lib.check(rc, who)
@@ -509,7 +534,7 @@ def tc_linear_backward(grad_y, x, weight, need_x=True, need_weight=True, need_bi
     if grad_y.numel() != rows * out_f:
         raise RuntimeError(f"{who}: grad_y{tuple(grad_y.shape)} does not match x{tuple(x.shape)} / weight{tuple(weight.shape)}")
     lib = _lib.load()
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         gx = torch.empty_like(x) if need_x else None
         gw = torch.empty_like(weight) if need_weight else None
         if need_bias:

@@ -757,3 +757,49 @@ def test_packed_bf16_forward(N, pyr, M, Lq, dist, vdt, loc_dtype):
     assert nerr(out.float(), np.asarray(want).reshape(tuple(out.shape))) <= 2e-2
     same = ops.ms_deform_attn_forward(v_bf.cuda(), dev["shapes"], dev["level_start"], dev["loc"], dev["aw"], 64)
     assert nerr(out.float(), same.float()) <= 1.0 / 128, "more than one bf16 rounding away from the reference-layout bf16 kernel"
+
+
+@pytest.mark.parametrize("mode,G,pad", [(0, 1, 0), (1, 1, 16), (1, 3, 0), (0, 2, 4)])
+def test_joint_query_projection_layout(mode, G, pad):
+    """msda_fused_*_joint: offsets and logits as column ranges of ONE [N, Lq, row_stride] matrix (what a single Linear layer over the
+    concatenated sampling_offsets / attention_weights weights produces) against the two-tensor entries on the same numbers: forward,
+    grad_value and the gradient written back in the joint layout; extra columns (row_stride > 3*M*L*P) are ignored and get zero
+    gradient; plain (G = 1) and grouped (temporal) forms; bad strides are refused."""
+    from mdqe_cvpr2023_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(100 + 10 * mode + G + pad)
+    N, M, D, L, P, Lq = 2, 8, 32, 4, 4, 37
+    pyr = torch.tensor([(9, 13), (5, 7), (3, 4), (2, 2)], device="cuda")
+    sizes = pyr.prod(-1)
+    S1 = int(sizes.sum())
+    starts = torch.cat([sizes.new_zeros(1), sizes.cumsum(0)[:-1]])
+    if G > 1:                                   # G tables of L levels over G*S1 rows, as the temporal module builds them
+        shapes = pyr.view(1, L, 2).expand(G, L, 2).contiguous()
+        starts = (starts.view(1, L) + (torch.arange(G, device="cuda") * S1).view(G, 1)).contiguous()
+        S = G * S1
+    else:
+        shapes, S = pyr, S1
+    value = torch.randn(N, S, M, D, device="cuda", generator=g)
+    ref = torch.cat([torch.rand(N, Lq, 2, device="cuda", generator=g), torch.rand(N, Lq, 2, device="cuda", generator=g) * 0.3 + 0.05], -1)
+    lp = M * L * P
+    row = 3 * lp + pad
+    qproj = torch.randn(N, Lq, row, device="cuda", generator=g) * 2.0
+    offsets = qproj[..., :2 * lp].reshape(N, Lq, M, L, P, 2).contiguous()
+    logits = qproj[..., 2 * lp:3 * lp].reshape(N, Lq, M, L * P).contiguous()
+    grid = torch.randn(M, L, P, 2, device="cuda", generator=g) if mode == 1 else None
+    go = torch.randn(N, Lq, M * D, device="cuda", generator=g)
+    scale = 1.0 / G
+    want = ops.ms_deform_attn_fused_forward(value, shapes, starts, ref, offsets, logits, grid, mode, 8.0, scale)
+    got = ops.ms_deform_attn_fused_forward_joint(value, shapes, starts, ref, qproj, P, grid, mode, 8.0, scale)
+    assert torch.equal(got, want), "same kernel arithmetic, only the addresses differ"
+    gv_w, goff_w, glog_w = ops.ms_deform_attn_fused_backward(value, shapes, starts, ref, offsets, logits, grid, mode, 8.0, go, scale)
+    gv, gq = ops.ms_deform_attn_fused_backward_joint(value, shapes, starts, ref, qproj, P, grid, mode, 8.0, go, scale)
+    assert tuple(gq.shape) == tuple(qproj.shape)
+    assert nerr(gv, gv_w) < 1e-6                 # atomics: the order of the reductions may differ
+    assert torch.equal(gq[..., :2 * lp].reshape(goff_w.shape), goff_w)
+    assert torch.equal(gq[..., 2 * lp:3 * lp].reshape(glog_w.shape), glog_w)
+    if pad:
+        assert float(gq[..., 3 * lp:].abs().max()) == 0.0
+    with pytest.raises(RuntimeError, match="row_stride"):
+        ops.ms_deform_attn_fused_forward_joint(value, shapes, starts, ref, qproj[..., :3 * lp - 4].contiguous(), P, grid, mode, 8.0, scale)
+    with pytest.raises(RuntimeError, match="row_stride"):
+        ops.ms_deform_attn_fused_forward_joint(value, shapes, starts, ref, torch.zeros(N, Lq, 3 * lp + 2, device="cuda"), P, grid, mode, 8.0, scale)
