@@ -54,23 +54,6 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-__device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-// 16 consecutive TMEM columns of the calling warp's 32 lanes (shape 32x32b: thread i owns lane i of the warp's quarter)
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-                 "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
-}
-
-__device__ __forceinline__ uint32_t tf32_lo(uint32_t v) { return __float_as_uint(__uint_as_float(v) - __uint_as_float(v & 0xffffe000u)); }
-
 // One stretch of work of a CTA: chunks [c0, c1) of the reduction for output tile (tm, tn).
 //   out: 0 = store (+ bias), 1 = reduce-add, 2 = store (+ bias) and publish flags[tile], 3 = wait for flags[tile], then reduce-add
 struct G3Seg { int tm, tn, c0, c1, out, tile; bool with_bias; };

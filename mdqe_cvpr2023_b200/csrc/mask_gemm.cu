@@ -183,7 +183,10 @@ static int launch_mask_tc4(cudaStream_t st, const void* coeff, const void* proto
     if (int rc = make_map_in(&map_rows, coeff, MSDA_F32, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QN)) return rc;
   }
   if (int rc = make_map_out(&map_out, out, sizeof(OT) == 2, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B)) return rc;
-  const size_t stage = mask_tc4_stage_bytes(QN, kTransB);
+  // plane operand through tensor memory (mask_tc4.cuh): option mask_a_tmem 1 = never, 2 = always, 0 = where it was measured to pay
+  const int mv = option("mask_a_tmem");
+  const bool a_tm = mv == 2 || (mv == 0 && kTransB);
+  const size_t stage = mask_tc4_stage_bytes(QN, kTransB, a_tm);
   const size_t out_bytes = 4 * 32 * kTcTileN * sizeof(OT);
   int n_stages = static_cast<int>((224 * 1024 - out_bytes) / stage);
   if (n_stages > kTc4MaxStages) n_stages = kTc4MaxStages;
@@ -197,7 +200,7 @@ static int launch_mask_tc4(cudaStream_t st, const void* coeff, const void* proto
   ProfScope prof(st, prof_kind, (int64_t)B * Q * Ncols);
   mask_fwd_tc4_kernel<OT, kTransB><<<grid, kTc4Threads, 1024 + n_stages * stage + out_bytes, st>>>(
       map_plane, map_rows, map_out, Q, n_kchunks, QS, QN, n_qchunks, n_tiles_n, static_cast<int>(n_items), n_stages,
-      option("mask_debug") != 2);
+      option("mask_debug") != 2, a_tm ? 1 : 0);
   return after_launch("mask_fwd_tc4_kernel");
 }
 

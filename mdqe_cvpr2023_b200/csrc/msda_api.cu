@@ -55,6 +55,7 @@ static std::atomic<int>* find_option(const char* key) {
   if (!strcmp(key, "pair_map")) return &g_opt.pair_map;
   if (!strcmp(key, "pdl")) return &g_opt.pdl;
   if (!strcmp(key, "gemm_stream_k")) return &g_opt.gemm_stream_k;
+  if (!strcmp(key, "mask_a_tmem")) return &g_opt.mask_a_tmem;
   return nullptr;
 }
 

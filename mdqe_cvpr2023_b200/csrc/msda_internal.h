@@ -34,7 +34,7 @@ struct Options {
   std::atomic<int> fwd_variant{0};    // 0 = auto (fast2 / fast when eligible), 1 = force generic, 2 = first-generation fast, 3 = fast2 with batched gathers (80 registers)
   std::atomic<int> bwd_variant{0};    // 0 = auto (fast2 / fast), 1 = generic, 2 = first-generation fast
   std::atomic<int> chunk_pairs{0};    // 0 = auto
-  std::atomic<int> mask_variant{0};   // 0 = auto (tcgen05 when eligible), 1 = SIMT fp32, 2 = force tcgen05, 3/5 = earlier tensor-core kernels (A/B), 4 = first fused SIMT backward
+  std::atomic<int> mask_variant{0};   // 0 = auto (tcgen05 when eligible), 1 = SIMT fp32, 2 = force tcgen05
   std::atomic<int> mask_debug{0};     // 1 = the tcgen05 mask kernel records per-item clock stamps of CTA 0
   std::atomic<int> host_async{0};     // 1 = the *_host entries only enqueue; msda_host_sync() completes them
   std::atomic<int> profile{0};        // 1 = bracket the main kernels with CUDA events (msda_profile_read)
@@ -42,6 +42,7 @@ struct Options {
   std::atomic<int> consumer_ctas{0};  // > 0: CTAs of the matcher-cost / IoU kernels (tuning; 0 = auto)
   std::atomic<int> pdl{1};            // 1 = launch the sampling kernels with programmatic stream serialization (see msda_launch.cuh)
   std::atomic<int> pair_map{0};       // order in which a CTA of the fast2 sampling kernels walks its pairs: 0 = auto, 1 = linear (chunk / M queries x all heads), 2 = head-run (one head x chunk queries; PairMap in msda_fast2.cuh)
+  std::atomic<int> mask_a_tmem{0};    // 3xTF32 mask kernels (mask_tc4.cuh): plane operand through tensor memory: 0 = auto (grad_proto), 1 = never, 2 = always (A/B)
   std::atomic<int> gemm_stream_k{1};  // Linear-layer GEMMs: 1 = (tile, chunk) units dealt out as one contiguous range per CTA where that pays (launch_gemm3x), 2 = always, 0 = whole tiles round-robin (A/B; gemm3x.cuh)
   std::atomic<int> bwd_merge{1};      // 1 = merge grad_value reductions of a (pair, level) that hit the same row (P = 2 or 4); 0 = off (A/B)
 };
