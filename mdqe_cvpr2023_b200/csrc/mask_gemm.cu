@@ -185,7 +185,9 @@ static int launch_mask_tc4(cudaStream_t st, const void* coeff, const void* proto
   if (int rc = make_map_out(&map_out, out, sizeof(OT) == 2, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B)) return rc;
   // plane operand through tensor memory (mask_tc4.cuh): option mask_a_tmem 1 = never, 2 = always, 0 = where it was measured to pay
   const int mv = option("mask_a_tmem");
-  const bool a_tm = mv == 2 || (mv == 0 && kTransB);
+  // (tools/mask_atm_ab.py, profiles/r02au_mask_atm_ab.txt: forward 21.5 -> 19.5 us at R50_360, 46.1 -> 42.0 at R50_720, 44.1 -> 37.9 at
+  // Q300; the grad_proto form -- seven chunks of N = 32 MMAs per tile -- does not move: 37.9 vs 37.9, 80.9 vs 82.9)
+  const bool a_tm = mv == 2 || (mv == 0 && !kTransB);
   const size_t stage = mask_tc4_stage_bytes(QN, kTransB, a_tm);
   const size_t out_bytes = 4 * 32 * kTcTileN * sizeof(OT);
   int n_stages = static_cast<int>((224 * 1024 - out_bytes) / stage);
