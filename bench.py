@@ -759,17 +759,19 @@ def main():
     # high priority: the few CTAs of a bucket's all-reduce are dispatched as soon as an SM has room, not behind the 3400 CTAs of the backward
     nccl_side = torch.cuda.Stream(device, priority=-1) if world > 1 else None
 
-    def whole_step(with_allreduce=True):
+    def whole_step(with_allreduce=True, st=None):
         """One multi-GPU step for capture: the decoder-gradient bucket is all-reduced on a forked branch as soon as the decoder
-        backward has been enqueued, one encoder bucket after each encoder layer's backward; the branch joins at the end."""
+        backward has been enqueued, one encoder bucket after each encoder layer's backward; the branch joins at the end.
+        st: the DeviceStep to run (default: the headline shape's)."""
+        st = step if st is None else st
         cur = torch.cuda.current_stream(device)
-        step.run("head")
+        st.run("head")
         if with_allreduce:
             nccl_side.wait_stream(cur)
             with torch.cuda.stream(nccl_side):
                 reduce_bucket(-1)
         for i in range(n_enc_layers):
-            step.run(f"tail{i}")
+            st.run(f"tail{i}")
             if with_allreduce:
                 nccl_side.wait_stream(cur)
                 with torch.cuda.stream(nccl_side):
@@ -1007,8 +1009,55 @@ def main():
         except Exception as e:  # noqa: BLE001
             modarm_ddp = {"error": repr(e)[:300]}
 
+    # ---- multi-GPU runs: BASELINE.json configs 3 and 4 at this GPU count: the R50_ovis_720 DDP training step with the
+    # same gradient all-reduce, and the Swin-L clip-sharded inference pass (no collective); max over ranks, aggregate over all GPUs
+    other_multi = None
+    if world > 1 and one_graph and not args.no_other_configs and not args.no_allreduce and args.dtype == "fp32":
+        other_multi = {}
+        n_other = max(3, min(args.steps, 10))
+
+        def max_over_ranks(ms):
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        for name, key in (("R50_ovis_720_train_fp32", "r50_720"), ("swinl_ytvis21_fp32", "swinl_360")):
+            if key == args.shape:
+                continue
+            try:
+                calls2, mask2 = build_calls(torch, SHAPES[key], args.dist, rank, args.layers, device=device)
+                st2 = DeviceStep(torch, lib, libmod, calls2, mask2, device, "fp32")
+                for _ in range(2):
+                    st2.run()
+                sync_all()
+                if key == "r50_720":
+                    g2 = capture(torch, lambda: whole_step(True, st2))
+                    sync_all()
+                    ms2 = max_over_ranks(time_replays(torch, g2, n_other))
+                    g3 = capture(torch, lambda: whole_step(False, st2))
+                    sync_all()
+                    ms3 = max_over_ranks(time_replays(torch, g3, n_other))
+                    other_multi[name] = {"workload": workload_text(SHAPES[key]), "n_gpus": world, "train_step_ms": ms2,
+                                         "aggregate_train_clips_per_s": world * 1e3 / ms2, "train_step_ms_without_allreduce": ms3,
+                                         "what": "one clip per GPU, 36 MSDeformAttn fwd+bwd + mask, gradient all-reduce of the enc+dec parameters "
+                                                 "(same buckets and kernel as the headline step) inside the one captured graph; max over ranks"}
+                    del g2, g3
+                else:
+                    g2 = capture(torch, lambda: st2.run("fwd"))
+                    sync_all()
+                    ms2 = max_over_ranks(time_replays(torch, g2, n_other))
+                    other_multi[name] = {"workload": workload_text(SHAPES[key]), "n_gpus": world, "inference_ms": ms2,
+                                         "aggregate_inference_clips_per_s": world * 1e3 / ms2,
+                                         "what": "clips sharded over the GPUs, forward calls of a clip + mask logits per GPU, no collective; max over ranks"}
+                    del g2
+                del st2, calls2, mask2
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001 -- a failing side measurement must not lose the headline line
+                other_multi[name] = {"error": repr(e)[:300]}
+                sync_all()
+
     # ---- the other BASELINE.json configurations and the module-level arm (single-GPU runs; rank 0 of a multi-GPU run skips them)
-    other, modarm = None, modarm_ddp
+    other, modarm = other_multi, modarm_ddp
     if world == 1 and not args.no_other_configs and not args.no_graph:
         del step
         torch.cuda.empty_cache()
@@ -1028,7 +1077,7 @@ def main():
             modarm = {"error": repr(e)[:300]}
 
     # ---- inference window of the reference: the encoder sees a window of up to 30 frames at once
-    if other is not None and args.shape == "r50_360":
+    if other is not None and world == 1 and args.shape == "r50_360":
         try:
             Nw, Sw = 30, sum(h * w for h, w in PYRAMID)
             gw = torch.Generator(device=device).manual_seed(7)
