@@ -1021,40 +1021,50 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
 
+        def all_ranks_ok(ok):
+            t = torch.tensor([1.0 if ok else 0.0], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return float(t.item()) > 0.5
+
         for name, key in (("R50_ovis_720_train_fp32", "r50_720"), ("swinl_ytvis21_fp32", "swinl_360")):
             if key == args.shape:
                 continue
+            # build and capture first (what can fail), agree across the ranks, only then enter the timed collectives together
+            st2 = g2 = g3 = None
+            err = None
             try:
                 calls2, mask2 = build_calls(torch, SHAPES[key], args.dist, rank, args.layers, device=device)
                 st2 = DeviceStep(torch, lib, libmod, calls2, mask2, device, "fp32")
                 for _ in range(2):
                     st2.run()
-                sync_all()
+                torch.cuda.synchronize()
                 if key == "r50_720":
                     g2 = capture(torch, lambda: whole_step(True, st2))
-                    sync_all()
-                    ms2 = max_over_ranks(time_replays(torch, g2, n_other))
                     g3 = capture(torch, lambda: whole_step(False, st2))
-                    sync_all()
-                    ms3 = max_over_ranks(time_replays(torch, g3, n_other))
-                    other_multi[name] = {"workload": workload_text(SHAPES[key]), "n_gpus": world, "train_step_ms": ms2,
-                                         "aggregate_train_clips_per_s": world * 1e3 / ms2, "train_step_ms_without_allreduce": ms3,
-                                         "what": "one clip per GPU, 36 MSDeformAttn fwd+bwd + mask, gradient all-reduce of the enc+dec parameters "
-                                                 "(same buckets and kernel as the headline step) inside the one captured graph; max over ranks"}
-                    del g2, g3
                 else:
                     g2 = capture(torch, lambda: st2.run("fwd"))
-                    sync_all()
-                    ms2 = max_over_ranks(time_replays(torch, g2, n_other))
-                    other_multi[name] = {"workload": workload_text(SHAPES[key]), "n_gpus": world, "inference_ms": ms2,
-                                         "aggregate_inference_clips_per_s": world * 1e3 / ms2,
-                                         "what": "clips sharded over the GPUs, forward calls of a clip + mask logits per GPU, no collective; max over ranks"}
-                    del g2
-                del st2, calls2, mask2
-                torch.cuda.empty_cache()
             except Exception as e:  # noqa: BLE001 -- a failing side measurement must not lose the headline line
-                other_multi[name] = {"error": repr(e)[:300]}
+                err = repr(e)[:300]
+            if not all_ranks_ok(err is None):
+                other_multi[name] = {"error": err or "failed on another rank"}
+            elif key == "r50_720":
                 sync_all()
+                ms2 = max_over_ranks(time_replays(torch, g2, n_other))
+                sync_all()
+                ms3 = max_over_ranks(time_replays(torch, g3, n_other))
+                other_multi[name] = {"workload": workload_text(SHAPES[key]), "n_gpus": world, "train_step_ms": ms2,
+                                     "aggregate_train_clips_per_s": world * 1e3 / ms2, "train_step_ms_without_allreduce": ms3,
+                                     "what": "one clip per GPU, 36 MSDeformAttn fwd+bwd + mask, gradient all-reduce of the enc+dec parameters "
+                                             "(same buckets and kernel as the headline step) inside the one captured graph; max over ranks"}
+            else:
+                sync_all()
+                ms2 = max_over_ranks(time_replays(torch, g2, n_other))
+                other_multi[name] = {"workload": workload_text(SHAPES[key]), "n_gpus": world, "inference_ms": ms2,
+                                     "aggregate_inference_clips_per_s": world * 1e3 / ms2,
+                                     "what": "clips sharded over the GPUs, forward calls of a clip + mask logits per GPU, no collective; max over ranks"}
+            g2 = g3 = st2 = calls2 = mask2 = None
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
 
     # ---- the other BASELINE.json configurations and the module-level arm (single-GPU runs; rank 0 of a multi-GPU run skips them)
     other, modarm = other_multi, modarm_ddp
