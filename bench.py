@@ -636,6 +636,25 @@ def module_arm(torch, shape, device, steps, dist="local", world=1):
         del g_ddp
     train_ms = time_replays(torch, capture(torch, train_step), steps)
     infer_ms = time_replays(torch, capture(torch, infer_step), steps)
+    # the same inference pass with value kept only as the sampler's paired-corner bf16 layout where that pays: the 6 encoder modules
+    # (value_proj GEMM epilogue -> packed sampler with the fused prologue; value rounded to bf16, everything else fp32); the
+    # decoder modules' 196-query calls stay fp32 (MSDeformAttn._packed_inference_ok)
+    packed = None
+    if D == 32:
+        try:
+            want = [t.clone() for t in infer_step()]
+            for m in enc + dec_f:
+                m.value_storage = "bf16_packed"
+            got = infer_step()
+            err = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(got, want))
+            packed_ms = time_replays(torch, capture(torch, infer_step), steps)
+            packed = {"inference_ms": packed_ms, "inference_clips_per_s": 1e3 / packed_ms, "max_normalised_error_vs_fp32": err,
+                      "what": "value_storage = 'bf16_packed': the 6 encoder modules run tc_linear_forward_packed + msda_fused_forward_packed_joint (the decoder's 196-query calls stay fp32: the packed epilogue does not pay there)"}
+        except Exception as e:  # noqa: BLE001
+            packed = {"error": repr(e)[:300]}
+        finally:
+            for m in enc + dec_f:
+                m.value_storage = "fp32"
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(2):
         train_step()
@@ -649,6 +668,7 @@ def module_arm(torch, shape, device, steps, dist="local", world=1):
                     "parameter gradients, through mdqe_cvpr2023_b200.MSDeformAttn (tc_linear + fused prologue + grouped temporal launch)",
             "shape": shape["name"], "train_step_ms": train_ms, "train_clips_per_s": 1e3 / train_ms, "inference_ms": infer_ms,
             "inference_clips_per_s": 1e3 / infer_ms, "eager_train_step_ms": e0.elapsed_time(e1) / 5,
+            "inference_bf16_packed": packed,
             "parameters": sum(p.numel() for p in params), "timing": f"CUDA-graph replay x{steps}, CUDA events", "ddp": ddp}
 
 

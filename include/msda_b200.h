@@ -160,6 +160,20 @@ int msda_pack_value(void* stream, int dtype, const void* value, const int64_t* s
                     int N, int S, int M, int D, int L, void* packed);
 int msda_forward_packed(void* stream, int dtype, const void* packed, const int64_t* shapes, const int64_t* level_start,
                         const void* loc, const void* aw, int N, int S, int M, int D, int L, int Lq, int P, void* out);
+/* The two producers / consumers that make the packed layout free for a module ("value_proj GEMM epilogue writing
+ * head-major bf16 + masked_fill"; ms_deform_attn.py:136-138, :142-171):
+ *   tc_linear_forward_packed : value_proj as the 3xTF32 GEMM of tc_linear_forward whose EPILOGUE writes the packed layout directly
+ *     (bias added, rows with row_mask != 0 zeroed, rounded to bf16) -- no fp32 value tensor, no pack pass.  x [N*S, in_features],
+ *     weight [heads*32, in_features], packed as for msda_pack_value.  Bit-identical to msda_pack_value(tc_linear_forward(x)).
+ *   msda_fused_forward_packed_joint : msda_forward_packed with the fused prologue of msda_fused_forward_joint (softmax and sampling
+ *     locations from the raw query projection `qproj` [N*Lq, row_stride]); out_dtype MSDA_BF16 or MSDA_F32 (what output_proj takes).
+ * Inference only (the backward kernels read the reference layout). */
+int tc_linear_forward_packed(void* stream, const void* x, const void* weight, const void* bias, const unsigned char* row_mask,
+                             int N, int S, int in_features, int heads, const int64_t* shapes, const int64_t* level_start, int L,
+                             void* packed);
+int msda_fused_forward_packed_joint(void* stream, const void* packed, const int64_t* shapes, const int64_t* level_start,
+                                    const void* ref_points, int R, const void* qproj, int row_stride, const void* grid, int mode,
+                                    float offset_scale, int N, int S, int M, int D, int L, int Lq, int P, int out_dtype, void* out);
 
 /* Fused sampler prologue (replaces the elementwise tail of MSDeformAttn.forward, ms_deform_attn.py:142-161):
  * the kernel takes what the module's Linear layers produce and computes softmax and sampling locations itself.

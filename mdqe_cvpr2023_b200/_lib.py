@@ -44,6 +44,9 @@ PROTOTYPES = {
                                  + [_c_int] * 8 + [ctypes.c_float, _c_vp]),
     "msda_fused_backward_joint": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_vp, _c_int, ctypes.c_float,
                                            _c_vp] + [_c_int] * 8 + [ctypes.c_float, _c_vp, _c_vp, _c_int]),
+    "tc_linear_forward_packed": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_int, _c_vp, _c_vp, _c_int, _c_vp]),
+    "msda_fused_forward_packed_joint": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_vp, _c_int, _c_vp, _c_int, ctypes.c_float]
+                                        + [_c_int] * 8 + [_c_vp]),
     "mask_logits_forward": (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_vp]),
     "mask_logits_backward": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_int, _c_int, _c_int, _c_i64, _c_vp, _c_vp]),
     "tc_linear_forward": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_int, _c_vp]),

@@ -108,17 +108,28 @@ __device__ __forceinline__ int g3_tile_parts(int tile, int n_kchunks, int n_unit
   return cta_of(tile * n_kchunks + n_kchunks - 1) - cta_of(tile * n_kchunks) + 1;
 }
 
+// Epilogue that writes C as the sampler's paired-corner bf16 value layout (PackedLevel, msda_common.cuh) instead of a row-major fp32
+// matrix: C rows are the (n, s) pixels of value_proj's output, every 32 columns one head.  packed == nullptr: the normal epilogue.
+struct G3Packed {
+  uint4* packed;
+  const int64_t* shapes;
+  const int64_t* level_start;
+  int L, S, heads;
+};
+
 template <bool kAMn, bool kBMn>
 __global__ void __launch_bounds__(kG3Threads, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
               const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias,
               const unsigned char* __restrict__ row_mask, float* __restrict__ col_sum_a, int* __restrict__ flags, int M, int N,
-              int n_kchunks, int chunks_per_split, int tiles_m, int tiles_n, int n_items, int mode) {
+              int n_kchunks, int chunks_per_split, int tiles_m, int tiles_n, int n_items, int mode, G3Packed pk) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   uint8_t* out_stage = smem + kG3Stages * kG3StageBytes;                // 2 x 16 KB (one per column half)
   __shared__ __align__(8) uint64_t bars[3 * kG3Stages + 4];
   __shared__ uint32_t s_tmem_base;
+  __shared__ PackedLevel s_plv[kMaxLevels];                             // pk.packed only
+  __shared__ int s_ptotal;
   const uint32_t bar0 = smem_u32(&bars[0]);
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_ready = [&](int s) { return bar0 + 8u * (kG3Stages + s); };
@@ -144,6 +155,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = s_tmem_base;
   pdl_wait();            // launched with programmatic stream serialization: everything above overlaps the previous kernel's drain
+  if (pk.packed != nullptr) {                                            // (uniform) level table of the packed layout for the epilogue
+    stage_packed_levels(s_plv, &s_ptotal, pk.shapes, pk.level_start, pk.L, pk.S);
+    __syncthreads();
+  }
 
   G3Walk walk(mode, n_kchunks, chunks_per_split, tiles_m, tiles_n, n_items);
   G3Seg sg;
@@ -271,6 +286,77 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       mbar_wait(bar_tfull(a), aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t lane_base = tmem_base + a * 128u + (static_cast<uint32_t>(quarter * 32) << 16);
+      if (pk.packed != nullptr) {
+        // ---- packed value epilogue: this thread's row is pixel (n, s); each 32-column group is one head's 32 channels = 64 bytes of
+        // bf16, which is the RIGHT half of line xp = x and the LEFT half of line xp = x + 1 of its level row (zeros beyond the level)
+        int64_t line = -1;                                                  // line of (y, xp = x), head 0; -1: row outside the table
+        bool first_x = false, last_x = false;
+        if (m < M) {
+          const int n = m / pk.S, s_ = m - n * pk.S;
+          for (int l = 0; l < pk.L; ++l) {
+            const PackedLevel lv = s_plv[l];
+            const int q = s_ - lv.start;
+            if (q >= 0 && q < lv.H * lv.W) {
+              const int y = q / lv.W, x = q - y * lv.W;
+              line = (static_cast<int64_t>(n) * 2 * pk.S + lv.pstart + y * (lv.W + 1) + x) * pk.heads;
+              first_x = x == 0;
+              last_x = x == lv.W - 1;
+              break;
+            }
+          }
+        }
+        // The 64-byte rows go through the staging tile (16-byte pieces XOR-swizzled: conflict-free both ways) so that four
+        // consecutive lanes write one contiguous 64-byte half line -- full sectors -- instead of every lane its own 16 bytes 1 KB apart.
+        uint2* s_line = reinterpret_cast<uint2*>(my_stage + 8192);           // per row of the tile: {line of head 0 (low 32 bits), flags}
+        const int t128 = (warp - 2 - 4 * half) * 32 + lane;                  // 0 .. 127 inside this column half
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          const int col0 = half * 64 + g * 32, n0 = sg.tn * kG3Tile + col0;
+          float v[32];
+          tmem_ld32(lane_base + static_cast<uint32_t>(col0), v);
+          named_bar_sync(1 + half, 128);                                    // the previous group's copies have left the staging tile
+          {
+            uint8_t* row = my_stage + row_in_tile * 64;
+            const int f = (row_in_tile >> 1) & 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t u[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = 8 * j + 2 * e;
+                const bool in_n = n0 + c < N;
+                const float lo_ = (masked || !in_n) ? 0.f : v[c] + (bias != nullptr ? __ldg(bias + n0 + c) : 0.f);
+                const float hi_ = (masked || !in_n) ? 0.f : v[c + 1] + (bias != nullptr ? __ldg(bias + n0 + c + 1) : 0.f);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(lo_, hi_);
+                u[e] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+              *reinterpret_cast<uint4*>(row + ((j ^ f) << 4)) = make_uint4(u[0], u[1], u[2], u[3]);
+            }
+            if (g == 0) s_line[row_in_tile] = make_uint2(static_cast<uint32_t>(line), (line < 0 ? 4u : 0u) | (first_x ? 1u : 0u) | (last_x ? 2u : 0u));
+          }
+          named_bar_sync(1 + half, 128);
+          if (n0 < N) {
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int idx = t128 + 128 * i, r = idx >> 2, pc = idx & 3;
+              const uint2 li = s_line[r];
+              if (li.y & 4u) continue;
+              const uint4 q4 = *reinterpret_cast<const uint4*>(my_stage + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+              uint4* right = pk.packed + (static_cast<int64_t>(li.x) + (n0 >> 5)) * 8 + 4 + pc;      // line xp = x: pieces 4..7
+              uint4* left = right + static_cast<int64_t>(pk.heads) * 8 - 4;                          // line xp = x + 1: pieces 0..3
+              *right = q4;
+              *left = q4;
+              if (li.y & 1u) right[-4] = z;                                 // left half of line xp = 0
+              if (li.y & 2u) left[4] = z;                                   // right half of line xp = W
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty(a));
+        continue;
+      }
 #pragma unroll 1
       for (int g = 0; g < 2; ++g) {
         const int col0 = half * 64 + g * 32;                                // column of the tile

@@ -410,7 +410,8 @@ static int* gemm_tile_flags(cudaStream_t st, int tiles) {
 // the (tile, chunk) units are dealt out as one contiguous range per CTA (stream-K, see gemm3x.cuh).
 template <bool kAMn, bool kBMn>
 static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const void* Bm, void* C, int64_t M, int64_t N, int64_t K,
-                         const float* bias, const unsigned char* row_mask, int splits, float* col_sum_a = nullptr) {
+                         const float* bias, const unsigned char* row_mask, int splits, float* col_sum_a = nullptr,
+                         G3Packed pk = G3Packed{nullptr, nullptr, nullptr, 0, 0, 0}) {
   const int sms = sm_count();
   const int n_kchunks = static_cast<int>((K + 31) / 32);
   const int tiles_m = static_cast<int>((M + kG3Tile - 1) / kG3Tile), tiles_n = static_cast<int>((N + kG3Tile - 1) / kG3Tile);
@@ -426,7 +427,7 @@ static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const 
   // fewer tiles than SMs): the flag hand-over of the split tiles costs about one (A/B per shape: profiles/r02ao_linear_bench_*.json)
   const int64_t idle_units = ((tiles + sms - 1) / sms * sms - tiles) * n_kchunks;
   const bool worth = tiles < sms || idle_units >= 4 * (int64_t)sms || option("gemm_stream_k") == 2;
-  if (splits == 1 && tiles * n_kchunks < (int64_t(1) << 31) && option("gemm_stream_k") != 0 && worth &&
+  if (splits == 1 && pk.packed == nullptr && tiles * n_kchunks < (int64_t(1) << 31) && option("gemm_stream_k") != 0 && worth &&   // packed epilogue: bf16 rounding needs whole tiles
       (flags = gemm_tile_flags(st, static_cast<int>(tiles))) != nullptr) {
     mode = kG3ModeStreamK;
     n_items = tiles * n_kchunks;
@@ -437,11 +438,12 @@ static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const 
   else { if (int rc = make_map_in(&map_a, A, MSDA_F32, (uint64_t)K, (uint64_t)M, 1, kG3Tile)) return rc; }
   if (kBMn) { if (int rc = make_map_mn_f32(&map_b, Bm, (uint64_t)N, (uint64_t)K, 1)) return rc; }
   else { if (int rc = make_map_in(&map_b, Bm, MSDA_F32, (uint64_t)K, (uint64_t)N, 1, kG3Tile)) return rc; }
-  if (int rc = make_map_c(&map_c, C, (uint64_t)N, (uint64_t)M)) return rc;
+  if (pk.packed != nullptr) map_c = map_a;                  // never stored through: the epilogue writes the packed layout itself
+  else if (int rc = make_map_c(&map_c, C, (uint64_t)N, (uint64_t)M)) return rc;
   if (int rc = ensure_func_attr(gemm3x_kernel<kAMn, kBMn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kG3SmemBytes)) return rc;
   const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);
   if (int rc = check_cuda(launch_kernel(gemm3x_kernel<kAMn, kBMn>, dim3(grid), dim3(kG3Threads), kG3SmemBytes, st, map_a, map_b, map_c, bias,
-                                        row_mask, col_sum_a, flags, (int)M, (int)N, n_kchunks, cps, tiles_m, tiles_n, (int)n_items, mode),
+                                        row_mask, col_sum_a, flags, (int)M, (int)N, n_kchunks, cps, tiles_m, tiles_n, (int)n_items, mode, pk),
                           "gemm3x_kernel launch")) return rc;
   return after_launch("gemm3x_kernel");
 }
@@ -455,6 +457,19 @@ int linear_forward_dispatch(cudaStream_t st, const void* x, const void* w, const
     return fail(MSDA_ERR_UNSUPPORTED, "tc_linear_forward: in_features / out_features must be multiples of 4 and the tensors 16-byte aligned");
   if (rows == 0) return 0;
   return launch_gemm3x<false, false>(st, "tc_linear_forward", x, w, y, rows, out_f, in_f, static_cast<const float*>(bias), row_mask, 1);
+}
+
+int linear_forward_packed_dispatch(cudaStream_t st, const void* x, const void* w, const void* bias, const unsigned char* row_mask, int N,
+                                   int S, int in_f, int heads, const int64_t* shapes, const int64_t* level_start, int L, void* packed) {
+  const int64_t rows = (int64_t)N * S;
+  if (rows >= (int64_t(1) << 31) - kG3Tile || (int64_t)N * 2 * S * heads >= (int64_t(1) << 32))
+    return fail(MSDA_ERR_UNSUPPORTED, "tc_linear_forward_packed: N*S=%lld too large", (long long)rows);
+  if (in_f % 4 != 0 || !aligned16(x) || !aligned16(w) || !aligned16(packed) || L > kMaxLevels)
+    return fail(MSDA_ERR_UNSUPPORTED, "tc_linear_forward_packed: in_features must be a multiple of 4, L <= %d and the tensors 16-byte aligned", kMaxLevels);
+  if (rows == 0) return 0;
+  const G3Packed pk{static_cast<uint4*>(packed), shapes, level_start, L, S, heads};
+  return launch_gemm3x<false, false>(st, "tc_linear_forward_packed", x, w, nullptr, rows, (int64_t)heads * 32, in_f, static_cast<const float*>(bias), row_mask, 1,
+                                     nullptr, pk);
 }
 
 int linear_backward_dispatch(cudaStream_t st, const void* gy, const void* x, const void* w, int64_t rows, int in_f, int out_f,

@@ -469,6 +469,15 @@ int tc_linear_forward(void* stream, const void* x, const void* weight, const voi
   return linear_forward_dispatch(static_cast<cudaStream_t>(stream), x, weight, bias, row_mask, rows, in_features, out_features, y);
 }
 
+int tc_linear_forward_packed(void* stream, const void* x, const void* weight, const void* bias, const unsigned char* row_mask,
+                             int N, int S, int in_features, int heads, const int64_t* shapes, const int64_t* level_start, int L,
+                             void* packed) {
+  if (N < 0 || S < 0 || in_features <= 0 || heads <= 0 || L <= 0) return fail(MSDA_ERR_INVALID_ARG, "tc_linear_forward_packed: bad sizes");
+  if (!shapes || !level_start || ((int64_t)N * S > 0 && (!x || !weight || !packed))) return fail(MSDA_ERR_INVALID_ARG, "tc_linear_forward_packed: NULL tensor");
+  return linear_forward_packed_dispatch(static_cast<cudaStream_t>(stream), x, weight, bias, row_mask, N, S, in_features, heads, shapes,
+                                        level_start, L, packed);
+}
+
 int tc_linear_bias_grad(void* stream, const void* grad_y, int64_t rows, int out_features, void* grad_bias) {
   if (rows < 0 || out_features <= 0 || !grad_bias || (rows > 0 && !grad_y)) return fail(MSDA_ERR_INVALID_ARG, "tc_linear_bias_grad: bad arguments");
   if (out_features % 4 != 0 || (reinterpret_cast<uintptr_t>(grad_y) & 15u))

@@ -112,6 +112,32 @@ __device__ __forceinline__ void stage_levels(LevelInfo* s_lvl, const int64_t* __
   }
 }
 
+// Paired-corner bf16 value layout (csrc/msda_packed.cu; also written directly by the value_proj GEMM epilogue, gemm3x.cuh):
+//   packed[n][prow][m] = { value[n, cell(y, xp - 1), m, 0:32], value[n, cell(y, xp), m, 0:32] } as 2 x 64 bytes of bf16,
+//   prow = pstart_l + y * (W_l + 1) + xp, xp in [0, W_l]; batch stride 2 S M lines.
+struct PackedLevel { int H, W, start, pstart; };
+
+// level table + packed prefix (thread 0 adds the <= 32 terms); returns nothing: read s_lvl / s_total after a barrier
+__device__ __forceinline__ void stage_packed_levels(PackedLevel* s_lvl, int* s_total, const int64_t* __restrict__ shapes,
+                                                    const int64_t* __restrict__ level_start, int L, int S) {
+  if (threadIdx.x == 0) {
+    int p = 0;
+    for (int l = 0; l < L; ++l) {
+      const int64_t H = shapes[2 * l], W = shapes[2 * l + 1], st = level_start ? level_start[l] : 0;
+      const bool ok = level_fits(H, W, st, S) && static_cast<int64_t>(p) + H * (W + 1) <= 2 * static_cast<int64_t>(S);
+      PackedLevel pl;
+      pl.H = ok ? static_cast<int>(H) : 0;
+      pl.W = ok ? static_cast<int>(W) : 0;
+      pl.start = ok ? static_cast<int>(st) : 0;
+      pl.pstart = p;
+      s_lvl[l] = pl;
+      p += pl.H * (pl.W + 1);
+    }
+    *s_total = p;
+  }
+}
+
+
 // Geometry of one sample: integer corner, fractional parts and per-corner validity.
 struct SampleGeom {
   int x0, y0;

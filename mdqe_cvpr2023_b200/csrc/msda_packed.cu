@@ -26,8 +26,6 @@
 namespace msda {
 namespace {
 
-struct PackedLevel { int H, W, start, pstart; };
-
 __device__ __forceinline__ FastDiv make_fastdiv_dev(uint32_t d) {      // device twin of make_fastdiv (msda_launch.cuh)
   FastDiv f{d, 0u, 0u};
   if (d <= 1) return f;
@@ -37,26 +35,6 @@ __device__ __forceinline__ FastDiv make_fastdiv_dev(uint32_t d) {      // device
   f.mul = static_cast<uint32_t>(((1ull << p) + d - 1) / d);
   f.shr = p - 32;
   return f;
-}
-
-// level table + packed prefix (thread 0 adds the <= 32 terms); returns nothing: read s_lvl / s_total after a barrier
-__device__ __forceinline__ void stage_packed_levels(PackedLevel* s_lvl, int* s_total, const int64_t* __restrict__ shapes,
-                                                    const int64_t* __restrict__ level_start, int L, int S) {
-  if (threadIdx.x == 0) {
-    int p = 0;
-    for (int l = 0; l < L; ++l) {
-      const int64_t H = shapes[2 * l], W = shapes[2 * l + 1], st = level_start ? level_start[l] : 0;
-      const bool ok = level_fits(H, W, st, S) && static_cast<int64_t>(p) + H * (W + 1) <= 2 * static_cast<int64_t>(S);
-      PackedLevel pl;
-      pl.H = ok ? static_cast<int>(H) : 0;
-      pl.W = ok ? static_cast<int>(W) : 0;
-      pl.start = ok ? static_cast<int>(st) : 0;
-      pl.pstart = p;
-      s_lvl[l] = pl;
-      p += pl.H * (pl.W + 1);
-    }
-    *s_total = p;
-  }
 }
 
 template <typename VT>
@@ -103,12 +81,19 @@ msda_pack_value_kernel(const VT* __restrict__ value, const int64_t* __restrict__
 
 struct __align__(8) PRec { uint32_t line; float w; };
 
-template <typename LT, int LP>
+__device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
+
+// FUSED: loc / aw are the raw sampling offsets and attention logits of the module (the fused prologue of msda_fast2.cuh: softmax over
+// the L*P lanes of a pair, loc = ref + offsets / scale or the decoder's box-scaled grid), optionally as column ranges of ONE query
+// projection matrix (fz.row_stride).  OT: bf16, or fp32 for a caller whose next layer (output_proj) takes fp32.
+template <typename LT, int LP, bool FUSED, typename OT>
 __global__ void __launch_bounds__(kThreads, 6)
 msda_fwd_packed_kernel(const uint4* __restrict__ packed, const int64_t* __restrict__ shapes, const int64_t* __restrict__ level_start,
                        const LT* __restrict__ loc,
-                       const LT* __restrict__ aw, __nv_bfloat16* __restrict__ out, int S, int M, int L, int P, uint32_t n_pairs,
-                       int chunk_pairs, FastDiv div_m, FastDiv div_mq) {
+                       const LT* __restrict__ aw, OT* __restrict__ out, int S, int M, int L, int P, uint32_t n_pairs,
+                       int chunk_pairs, FastDiv div_m, FastDiv div_mq, FusedArgs fz) {
+  static_assert(!FUSED || std::is_same<LT, float>::value, "the fused prologue takes fp32 offsets / logits");
   constexpr int QPW = 32 / LP;                       // pairs per warp round
   __shared__ PackedLevel s_lvl[kMaxLevels];
   __shared__ int s_total;
@@ -135,11 +120,30 @@ msda_fwd_packed_kernel(const uint4* __restrict__ packed, const int64_t* __restri
       PRec r[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) { r[k].line = 0u; r[k].w = 0.f; }
-      if (ps < npair) {
+      const bool has_sample = ps < npair;
+      float x = 0.f, y = 0.f, a = 0.f;
+      uint32_t nq = 0, m = 0, n = 0;
+      if (has_sample) {
         const uint32_t pair = p0 + ps;
-        const uint32_t nq = fd_div(pair, div_m), m = pair - nq * div_m.d, n = fd_div(pair, div_mq);
-        float x, y, a;
-        load_loc_aw<LT>(loc, aw, static_cast<int64_t>(pair) * LP + ss, x, y, a);
+        nq = fd_div(pair, div_m);
+        m = pair - nq * div_m.d;
+        n = fd_div(pair, div_mq);
+        int64_t li = static_cast<int64_t>(pair) * LP + ss, ai = li;
+        if constexpr (FUSED) {
+          if (fz.row_stride > 0) {
+            const int64_t row = static_cast<int64_t>(nq) * fz.row_stride;
+            li = (row >> 1) + m * LP + ss;
+            ai = row + m * LP + ss;
+          }
+        }
+        load_loc_aw2<LT>(loc, aw, li, ai, x, y, a);
+      }
+      if constexpr (FUSED) {                          // every lane of the warp takes part in the softmax shuffles
+        a = segment_softmax<LP>(a, has_sample);
+        float mk_x, mk_y;
+        if (has_sample) fused_location(fz, nq, m, ss, LP, x, y, mk_x, mk_y);
+      }
+      if (has_sample) {
         const PackedLevel lv = s_lvl[lvl];
         const SampleGeom g = sample_geom(x, y, lv.H, lv.W);
         if (g.x0 >= -1) {                              // sane sample (sample_geom marks the others with -8): x0 + 1 in [0, W]
@@ -200,7 +204,7 @@ msda_fwd_packed_kernel(const uint4* __restrict__ packed, const int64_t* __restri
         const float keep = b2 ? t2[1] : t2[0], send = b2 ? t2[0] : t2[1];
         const float v = keep + __shfl_xor_sync(0xffffffffu, send, 4);
         const int ch = (lane & 3) * 8 + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
-        out[static_cast<int64_t>(p0 + pl) * 32 + ch] = __float2bfloat16_rn(v);
+        store_out(out + static_cast<int64_t>(p0 + pl) * 32 + ch, v);
       }
     }
     __syncwarp();
@@ -261,14 +265,48 @@ int msda_forward_packed(void* stream, int dtype, const void* packed, const int64
   const unsigned grid = static_cast<unsigned>((n_pairs + chunk - 1) / chunk);
   const FastDiv dm = make_fastdiv(M), dmq = make_fastdiv(static_cast<uint32_t>(M) * static_cast<uint32_t>(Lq));
   ProfScope prof(st, MSDA_PROF_MSDA_FWD, n_pairs);
+  const FusedArgs none{nullptr, nullptr, 0, 0, 1.f, 0};
   if (dtype == MSDA_BF16)
-    launch_kernel(msda_fwd_packed_kernel<__nv_bfloat16, 16>, dim3(grid), dim3(kThreads), 0, st, static_cast<const uint4*>(packed), shapes, level_start,
+    launch_kernel(msda_fwd_packed_kernel<__nv_bfloat16, 16, false, __nv_bfloat16>, dim3(grid), dim3(kThreads), 0, st, static_cast<const uint4*>(packed), shapes, level_start,
                   static_cast<const __nv_bfloat16*>(loc), static_cast<const __nv_bfloat16*>(aw), static_cast<__nv_bfloat16*>(out), S, M, L, P,
-                  static_cast<uint32_t>(n_pairs), chunk, dm, dmq);
+                  static_cast<uint32_t>(n_pairs), chunk, dm, dmq, none);
   else
-    launch_kernel(msda_fwd_packed_kernel<float, 16>, dim3(grid), dim3(kThreads), 0, st, static_cast<const uint4*>(packed), shapes, level_start,
+    launch_kernel(msda_fwd_packed_kernel<float, 16, false, __nv_bfloat16>, dim3(grid), dim3(kThreads), 0, st, static_cast<const uint4*>(packed), shapes, level_start,
                   static_cast<const float*>(loc), static_cast<const float*>(aw), static_cast<__nv_bfloat16*>(out), S, M, L, P,
-                  static_cast<uint32_t>(n_pairs), chunk, dm, dmq);
+                  static_cast<uint32_t>(n_pairs), chunk, dm, dmq, none);
+  return after_launch("msda_fwd_packed_kernel");
+}
+
+int msda_fused_forward_packed_joint(void* stream, const void* packed, const int64_t* shapes, const int64_t* level_start,
+                                    const void* ref_points, int R, const void* qproj, int row_stride, const void* grid_, int mode,
+                                    float offset_scale, int N, int S, int M, int D, int L, int Lq, int P, int out_dtype, void* out) {
+  const char* who = "msda_fused_forward_packed_joint";
+  if (!packed || !shapes || !level_start || !ref_points || !qproj || !out) return fail(MSDA_ERR_INVALID_ARG, "%s: NULL pointer", who);
+  if (N <= 0 || S <= 0 || M <= 0 || L <= 0 || Lq <= 0 || P <= 0) return fail(MSDA_ERR_INVALID_ARG, "%s: non-positive size", who);
+  if (out_dtype != MSDA_F32 && out_dtype != MSDA_BF16) return fail(MSDA_ERR_INVALID_ARG, "%s: out_dtype must be MSDA_F32 or MSDA_BF16", who);
+  if (D != 32 || L * P != 16 || L > kMaxLevels) return fail(MSDA_ERR_UNSUPPORTED, "%s: needs D = 32 and L*P = 16 (got D = %d, L*P = %d)", who, D, L * P);
+  if ((R != 2 && R != 4) || (mode != 0 && mode != 1) || (mode == 1 && (R != 4 || !grid_)) || !(offset_scale > 0.f))
+    return fail(MSDA_ERR_INVALID_ARG, "%s: bad fused arguments (R=%d mode=%d scale=%g)", who, R, mode, (double)offset_scale);
+  const int64_t lp = static_cast<int64_t>(M) * L * P;
+  if (row_stride < 3 * lp || (row_stride & 3)) return fail(MSDA_ERR_INVALID_ARG, "%s: row_stride=%d must be a multiple of 4 and >= 3*M*L*P", who, row_stride);
+  const int64_t n_pairs = static_cast<int64_t>(N) * Lq * M;
+  if (n_pairs >= (int64_t(1) << 31) / 64 || static_cast<int64_t>(N) * 2 * S * M >= (int64_t(1) << 32)) return fail(MSDA_ERR_UNSUPPORTED, "%s: problem too large for 32-bit indices", who);
+  if ((reinterpret_cast<uintptr_t>(packed) | reinterpret_cast<uintptr_t>(qproj) | reinterpret_cast<uintptr_t>(out)) & 15u)
+    return fail(MSDA_ERR_UNSUPPORTED, "%s: tensors must be 16-byte aligned", who);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Problem pb{N, S, M, D, L, Lq, P, n_pairs};
+  const int chunk = pick_chunk(pb);
+  const unsigned grid = static_cast<unsigned>((n_pairs + chunk - 1) / chunk);
+  const FastDiv dm = make_fastdiv(M), dmq = make_fastdiv(static_cast<uint32_t>(M) * static_cast<uint32_t>(Lq));
+  const FusedArgs fz{static_cast<const float*>(ref_points), static_cast<const float*>(grid_), R, mode, offset_scale, row_stride};
+  const float* q = static_cast<const float*>(qproj);
+  ProfScope prof(st, MSDA_PROF_MSDA_FWD, n_pairs);
+  if (out_dtype == MSDA_F32)
+    launch_kernel(msda_fwd_packed_kernel<float, 16, true, float>, dim3(grid), dim3(kThreads), 0, st, static_cast<const uint4*>(packed), shapes, level_start,
+                  q, q + 2 * lp, static_cast<float*>(out), S, M, L, P, static_cast<uint32_t>(n_pairs), chunk, dm, dmq, fz);
+  else
+    launch_kernel(msda_fwd_packed_kernel<float, 16, true, __nv_bfloat16>, dim3(grid), dim3(kThreads), 0, st, static_cast<const uint4*>(packed), shapes, level_start,
+                  q, q + 2 * lp, static_cast<__nv_bfloat16*>(out), S, M, L, P, static_cast<uint32_t>(n_pairs), chunk, dm, dmq, fz);
   return after_launch("msda_fwd_packed_kernel");
 }
 

@@ -65,6 +65,10 @@ class MSDeformAttn(nn.Module):
         self.fused_prologue = True
         self.tc_linear = True
         self.joint_query_proj = True       # fused prologue + tc_linear: offsets and logits from ONE GEMM over the concatenated weights
+        # "bf16_packed": inference (no autograd graph) in spatial mode keeps `value` only as the sampler's paired-corner bf16 layout,
+        # written by the value_proj GEMM epilogue (north_star's bf16 mode; value rounded to bf16, everything else fp32: <= 2e-2)
+        self.value_storage = "fp32"
+        self.value_storage_always = False  # True: also for calls with few queries (tests / A-B)
         self.check_shapes = False          # True: assert sum(H_l * W_l) == S like the reference (one host sync per call)
 
         # what the operator sees as "levels": pyramid levels of a frame, or the frames of a clip
@@ -173,6 +177,33 @@ class MSDeformAttn(nn.Module):
         offsets, logits, grid, mode = self._fused_inputs(query)
         return MSDeformAttnFusedFunction.apply(value, shapes, starts, reference_points, offsets, logits, grid, mode, self.scale, scale)
 
+    def _packed_inference_ok(self, query, reference_points, input_flatten):
+        B, S, _ = input_flatten.shape
+        return (not (torch.is_grad_enabled() and (query.requires_grad or input_flatten.requires_grad
+                                                  or any(p.requires_grad for p in self.parameters())))
+                and self.fused_prologue and self.joint_query_proj and self.tc_linear and not torch.is_autocast_enabled()
+                and input_flatten.is_cuda and input_flatten.dtype == torch.float32 and query.dtype == torch.float32
+                and self.d_model == self.n_heads * 32 and self.lvl * self.n_points == 16 and self.lvl <= 32
+                and reference_points.dtype == torch.float32 and reference_points.shape[-1] in (2, 4)
+                and ops.linear_supported(input_flatten, self.value_proj.weight) and ops.linear_supported(query, self.attention_weights.weight)
+                and B * 2 * S * self.n_heads < 2 ** 32 and B * query.shape[1] * self.n_heads < 2 ** 31 // 64
+                # pays where the sampler dominates (encoder: one query per pixel: -16 us per call); with 196 decoder queries the
+                # sampler is launch-bound either way and the packed epilogue only costs (profiles/r02av_packed_module.txt)
+                and (query.shape[1] * 2 >= S or self.value_storage_always))
+
+    def _packed_inference(self, query, reference_points, input_flatten, shapes_c, level_start, input_padding_mask):
+        """value_proj -> packed bf16 value (GEMM epilogue), ONE query-projection GEMM, packed sampler with the fused prologue, output_proj"""
+        B, S, _ = input_flatten.shape
+        packed = ops.tc_linear_forward_packed(input_flatten.contiguous(), self.value_proj.weight, self.value_proj.bias,
+                                              input_padding_mask.contiguous() if input_padding_mask is not None else None,
+                                              shapes_c, level_start, self.n_heads)
+        qproj = self._joint_query_projection(query)
+        grid = None if self.pred_offsets else self.sampling_offsets.reshape(self.n_heads, self.lvl, self.n_points, 2).contiguous()
+        sampled = ops.ms_deform_attn_fused_forward_packed_joint(packed, (B, S, self.n_heads, 32), shapes_c, level_start,
+                                                                reference_points.contiguous(), qproj, self.n_points, grid,
+                                                                0 if self.pred_offsets else 1, self.scale, torch.float32)
+        return self._linear(self.output_proj, sampled)
+
     _geometry_cache = []
 
     def _project_value(self, input_flatten, input_padding_mask):
@@ -222,6 +253,8 @@ class MSDeformAttn(nn.Module):
         if self.check_shapes:
             assert int(input_spatial_shapes.prod(-1).sum()) == input_flatten.shape[1], "spatial_shapes do not add up to the rows of input_flatten"
         level_start, shapes_c, _, _ = self._geometry(input_spatial_shapes)
+        if self.value_storage == "bf16_packed" and self._packed_inference_ok(query, reference_points, input_flatten):
+            return self._packed_inference(query, reference_points, input_flatten, shapes_c, level_start, input_padding_mask)
         value = self._project_value(input_flatten, input_padding_mask).contiguous()  # B S H D
         if self.fused_prologue and ops.fused_supported(value, reference_points, 1, self.lvl, self.n_points, query.shape[1]):
             sampled = self._fused_sampler(value, shapes_c, level_start, reference_points, query, 1.0)

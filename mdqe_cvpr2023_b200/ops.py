@@ -211,6 +211,69 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     return [grad_value, grad_loc, grad_aw]
 
 
+def tc_linear_forward_packed(x, weight, bias, row_mask, spatial_shapes, level_start_index, n_heads):
+    """value_proj whose GEMM epilogue writes the sampler's paired-corner bf16 layout directly (tc_linear_forward_packed): x [N,S,in]
+    fp32, weight [n_heads*32, in], bias or None, row_mask [N,S] or None -> opaque packed tensor (as pack_value would build from the
+    fp32 projection).  Inference only."""
+    who = "tc_linear_forward_packed"
+    tensors = [("x", x), ("weight", weight), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index)]
+    if bias is not None:
+        tensors.append(("bias", bias))
+    if row_mask is not None:
+        tensors.append(("row_mask", row_mask))
+    _check_inputs(who, tensors)
+    if x.dim() != 3 or x.dtype != torch.float32 or weight.dtype != torch.float32 or tuple(weight.shape) != (n_heads * 32, x.shape[2]):
+        raise RuntimeError(f"{who}: x must be fp32 [N,S,in] and weight fp32 [n_heads*32, in]; got {tuple(x.shape)}, {tuple(weight.shape)}")
+    N, S, in_f = x.shape
+    mask8 = None
+    if row_mask is not None:
+        if row_mask.numel() != N * S:
+            raise RuntimeError(f"{who}: row_mask must have one entry per row of x")
+        mask8 = row_mask.view(torch.uint8) if row_mask.dtype == torch.bool else row_mask.to(torch.uint8)
+    lib = _lib.load()
+    nbytes = lib.msda_packed_value_bytes(N, S, n_heads, 32)
+    with _on_device(x.device):
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        rc = lib.tc_linear_forward_packed(_stream_ptr(x.device), x.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                          mask8.data_ptr() if mask8 is not None else None, N, S, in_f, n_heads,
+                                          spatial_shapes.data_ptr(), level_start_index.data_ptr(), spatial_shapes.shape[0], packed.data_ptr())
+    _lib.check(rc, who)
+    return packed
+
+
+def ms_deform_attn_fused_forward_packed_joint(packed, value_shape, spatial_shapes, level_start_index, reference_points, qproj, n_points,
+                                              grid, mode, offset_scale, out_dtype=torch.float32):
+    """The forward on a packed value tensor with the module's softmax / location arithmetic inside the kernel and the raw query
+    projection ``qproj`` [N,Lq,row_stride] as input (msda_fused_forward_packed_joint) -> Tensor[N, Lq, M*32] of ``out_dtype``."""
+    who = "ms_deform_attn_fused_forward_packed_joint"
+    tensors = [("packed", packed), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+               ("reference_points", reference_points), ("qproj", qproj)]
+    if grid is not None:
+        tensors.append(("grid", grid))
+    _check_inputs(who, tensors)
+    N, S, M, D = value_shape
+    L, P = spatial_shapes.shape[0], int(n_points)
+    if qproj.dim() != 3 or qproj.shape[0] != N or qproj.dtype != torch.float32 or qproj.shape[2] < 3 * M * L * P or qproj.shape[2] % 4:
+        raise RuntimeError(f"{who}: qproj must be fp32 [N,Lq,row_stride] with row_stride % 4 == 0 and >= 3*M*L*P, got {tuple(qproj.shape)}")
+    Lq = qproj.shape[1]
+    if reference_points.dim() != 3 or tuple(reference_points.shape[:2]) != (N, Lq) or reference_points.dtype != torch.float32:
+        raise RuntimeError(f"{who}: reference_points must be fp32 [N,Lq,R]")
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"{who}: out_dtype must be float32 or bfloat16")
+    lib = _lib.load()
+    if packed.numel() * packed.element_size() < lib.msda_packed_value_bytes(N, S, M, D):
+        raise RuntimeError(f"{who}: packed tensor too small for value shape {tuple(value_shape)}")
+    with _on_device(packed.device):
+        out = torch.empty((N, Lq, M * D), dtype=out_dtype, device=packed.device)
+        rc = lib.msda_fused_forward_packed_joint(_stream_ptr(packed.device), packed.data_ptr(), spatial_shapes.data_ptr(),
+                                                 level_start_index.data_ptr(), reference_points.data_ptr(), int(reference_points.shape[2]),
+                                                 qproj.data_ptr(), int(qproj.shape[2]), grid.data_ptr() if grid is not None else None,
+                                                 int(mode), float(offset_scale), N, S, M, D, L, Lq, P,
+                                                 _lib.MSDA_F32 if out_dtype == torch.float32 else _lib.MSDA_BF16, out.data_ptr())
+    _lib.check(rc, who)
+    return out
+
+
 def _fast_kernel_limits(value, n_queries, *others):
     """the conditions csrc/msda_launch.cuh (fast_eligible) puts on the fast kernels besides the shape family: 32-bit row
     offsets and pair indices, 16-byte aligned tensors"""

@@ -78,3 +78,37 @@ def test_module_r50_shape_runs_under_autocast():
     with torch.autocast("cuda", dtype=torch.float16):
         y = mod(x, ref, x, shapes, None)
     assert y.dtype == torch.float32 and tuple(y.shape) == (2, S, 256) and bool(torch.isfinite(y).all())
+
+
+@pytest.mark.parametrize("pred_offsets", [True, False])
+def test_module_bf16_packed_inference(pred_offsets):
+    """value_storage = "bf16_packed": under no_grad the spatial module keeps value only as the sampler's paired-corner bf16 layout
+    (value_proj GEMM epilogue -> packed sampler with the fused prologue); <= 2e-2 of the fp32 module (north_star's bf16 bar), padded
+    pixels zeroed, and the autograd path is untouched when gradients are needed."""
+    from mdqe_cvpr2023_b200 import MSDeformAttn
+    torch.manual_seed(3)
+    mod = MSDeformAttn(256, 4, 8, 4, pred_offsets=pred_offsets, mode="spatial").cuda()
+    with torch.no_grad():
+        for p in mod.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    shapes = torch.tensor([(24, 40), (12, 20), (6, 10), (3, 5)], device="cuda")
+    S = int(shapes.prod(-1).sum())
+    B, Q = 2, (S if pred_offsets else 50)
+    x = torch.randn(B, S, 256, device="cuda")
+    q = torch.randn(B, Q, 256, device="cuda")
+    ref = torch.cat([torch.rand(B, Q, 2, device="cuda"), torch.rand(B, Q, 2, device="cuda") * 0.2 + 0.05], -1)
+    pad = torch.rand(B, S, device="cuda") < 0.1
+    with torch.no_grad():
+        want = mod(q, ref, x, shapes, pad)
+        mod.value_storage = "bf16_packed"
+        mod.value_storage_always = True             # the decoder form has few queries: the module would keep fp32 there (it does not pay)
+        assert mod._packed_inference_ok(q, ref, x)
+        got = mod(q, ref, x, shapes, pad)
+    assert got.dtype == torch.float32 and tuple(got.shape) == tuple(want.shape)
+    assert 0.0 < nerr(got, want) <= 2e-2
+    x.requires_grad_(True)                          # training: the flag must not change anything
+    assert not mod._packed_inference_ok(q, ref, x)
+    out = mod(q, ref, x, shapes, pad)
+    assert nerr(out, want) <= 1e-5
+    out.sum().backward()
+    assert x.grad is not None and bool(torch.isfinite(x.grad).all())

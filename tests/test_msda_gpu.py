@@ -803,3 +803,69 @@ def test_joint_query_projection_layout(mode, G, pad):
         ops.ms_deform_attn_fused_forward_joint(value, shapes, starts, ref, qproj[..., :3 * lp - 4].contiguous(), P, grid, mode, 8.0, scale)
     with pytest.raises(RuntimeError, match="row_stride"):
         ops.ms_deform_attn_fused_forward_joint(value, shapes, starts, ref, torch.zeros(N, Lq, 3 * lp + 2, device="cuda"), P, grid, mode, 8.0, scale)
+
+
+def _packed_lines(packed, N, S, M, pyr):
+    """the lines of the paired-corner layout that the level table defines: [N, sum_l H_l (W_l + 1), M, 128] bytes"""
+    sp = sum(h * (w + 1) for h, w in pyr)
+    return packed.view(N, 2 * S, M, 128)[:, :sp]
+
+
+@pytest.mark.parametrize("N,pyr,with_mask", [(2, [(12, 20), (6, 10), (3, 5), (2, 3)], True), (3, [(7, 9), (5, 4), (1, 1), (2, 6)], False),
+                                             (4, R50_360, True)])
+def test_value_proj_epilogue_writes_the_packed_layout(N, pyr, with_mask):
+    """tc_linear_forward_packed (value_proj epilogue writing the sampler's bf16 layout + masked_fill): bit-identical to
+    msda_pack_value of the fp32 projection when both GEMMs walk whole tiles, and within one bf16 rounding of it in the default
+    configuration (the fp32 GEMM may combine split tiles in a different order); ragged row counts, a 1x1 level, padded pixels."""
+    from mdqe_cvpr2023_b200 import _lib, ops
+    g = torch.Generator(device="cuda").manual_seed(N * 7 + len(pyr))
+    M, C = 8, 256
+    shapes = torch.tensor(pyr, device="cuda")
+    sizes = shapes.prod(-1)
+    S = int(sizes.sum())
+    starts = torch.cat([sizes.new_zeros(1), sizes.cumsum(0)[:-1]])
+    x = torch.randn(N, S, C, device="cuda", generator=g)
+    w = torch.randn(M * 32, C, device="cuda", generator=g) / 16
+    b = torch.randn(M * 32, device="cuda", generator=g)
+    mask = (torch.rand(N, S, device="cuda", generator=g) < 0.15) if with_mask else None
+    got = _packed_lines(ops.tc_linear_forward_packed(x, w, b, mask, shapes, starts, M), N, S, M, pyr)
+    for stream_k in (0, 1):
+        _lib.set_option("gemm_stream_k", stream_k)
+        try:
+            value = ops.tc_linear_forward(x, w, b, mask).view(N, S, M, 32)
+        finally:
+            _lib.set_option("gemm_stream_k", 1)
+        want = _packed_lines(ops.pack_value(value, shapes, starts), N, S, M, pyr)
+        if stream_k == 0:
+            assert torch.equal(got, want)
+        else:
+            a = got.contiguous().view(torch.bfloat16).float()
+            c = want.contiguous().view(torch.bfloat16).float()
+            assert float((a - c).abs().max()) <= 2.0 ** -7 * float(c.abs().max())
+    if with_mask:                                   # masked pixels are stored as zeros in both halves they appear in
+        value = ops.tc_linear_forward(x, w, b, mask).view(N, S, M, 32)
+        assert float(value[mask].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("mode,out_dtype", [(0, torch.float32), (1, torch.float32), (1, torch.bfloat16)])
+def test_fused_joint_forward_on_the_packed_layout(mode, out_dtype):
+    """msda_fused_forward_packed_joint against msda_fused_forward_joint on the bf16-rounded value: the same fp32 arithmetic on the
+    same numbers, gathered from two lines per sample instead of four rows (summation order differs)."""
+    from mdqe_cvpr2023_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(31 + mode)
+    N, M, D, L, P, Lq = 3, 8, 32, 4, 4, 77
+    pyr = [(12, 20), (6, 10), (3, 5), (2, 3)]
+    shapes = torch.tensor(pyr, device="cuda")
+    sizes = shapes.prod(-1)
+    S = int(sizes.sum())
+    starts = torch.cat([sizes.new_zeros(1), sizes.cumsum(0)[:-1]])
+    value = torch.randn(N, S, M, D, device="cuda", generator=g)
+    ref = torch.cat([torch.rand(N, Lq, 2, device="cuda", generator=g), torch.rand(N, Lq, 2, device="cuda", generator=g) * 0.3 + 0.05], -1)
+    lp = M * L * P
+    qproj = torch.randn(N, Lq, 3 * lp, device="cuda", generator=g) * 2.0
+    grid = torch.randn(M, L, P, 2, device="cuda", generator=g) if mode == 1 else None
+    packed = ops.pack_value(value, shapes, starts)
+    got = ops.ms_deform_attn_fused_forward_packed_joint(packed, (N, S, M, D), shapes, starts, ref, qproj, P, grid, mode, 8.0, out_dtype)
+    want = ops.ms_deform_attn_fused_forward_joint(value.bfloat16().float(), shapes, starts, ref, qproj, P, grid, mode, 8.0, 1.0)
+    assert got.dtype == out_dtype and tuple(got.shape) == tuple(want.shape)
+    assert nerr(got.float(), want) <= (2e-5 if out_dtype == torch.float32 else 1e-2)
