@@ -183,26 +183,28 @@ static int launch_mask_tc4(cudaStream_t st, const void* coeff, const void* proto
     if (int rc = make_map_in(&map_rows, coeff, MSDA_F32, (uint64_t)K, (uint64_t)Q, (uint64_t)B, (uint32_t)QN)) return rc;
   }
   if (int rc = make_map_out(&map_out, out, sizeof(OT) == 2, (uint64_t)Ncols, (uint64_t)Q, (uint64_t)B)) return rc;
-  // plane operand through tensor memory (mask_tc4.cuh): option mask_a_tmem 1 = never, 2 = always, 0 = where it was measured to pay
-  const int mv = option("mask_a_tmem");
-  // (tools/mask_atm_ab.py, profiles/r02au_mask_atm_ab.txt: forward 21.5 -> 19.5 us at R50_360, 46.1 -> 42.0 at R50_720, 44.1 -> 37.9 at
-  // Q300; the grad_proto form -- seven chunks of N = 32 MMAs per tile -- does not move: 37.9 vs 37.9, 80.9 vs 82.9)
-  const bool a_tm = mv == 2 || (mv == 0 && !kTransB);
+  // plane operand through tensor memory (mask_tc4.cuh; a compile-time variant of the kernel): option mask_a_tmem 1 = off (A/B).
+  // tools/mask_atm_ab.py, profiles/r02aw_mask_atm_ab.txt (graph replays, same box): forward 13.6 -> 12.0 us at R50_360, 40.4 -> 35.9 at
+  // R50_720, 37.1 -> 32.5 at Q = 300; grad_proto (seven chunks of N = 32 MMAs per tile) 23.2 -> 22.8, 53.1 -> 52.1
+  const bool a_tm = option("mask_a_tmem") != 1;
   const size_t stage = mask_tc4_stage_bytes(QN, kTransB, a_tm);
   const size_t out_bytes = 4 * 32 * kTcTileN * sizeof(OT);
   int n_stages = static_cast<int>((224 * 1024 - out_bytes) / stage);
   if (n_stages > kTc4MaxStages) n_stages = kTc4MaxStages;
   if (n_stages > n_kchunks + 2) n_stages = n_kchunks + 2;
   if (n_stages < 2) return fail(MSDA_ERR_UNSUPPORTED, "mask_logits: tile does not fit shared memory");
-  if (int rc = ensure_func_attr(mask_fwd_tc4_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) return rc;
-  if (int rc = ensure_func_attr(mask_fwd_tc4_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) return rc;
-  if (int rc = ensure_func_attr(mask_fwd_tc4_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) return rc;
-  if (int rc = ensure_func_attr(mask_fwd_tc4_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) return rc;
   const unsigned grid = static_cast<unsigned>(n_items < sms ? n_items : sms);
   ProfScope prof(st, prof_kind, (int64_t)B * Q * Ncols);
-  mask_fwd_tc4_kernel<OT, kTransB><<<grid, kTc4Threads, 1024 + n_stages * stage + out_bytes, st>>>(
-      map_plane, map_rows, map_out, Q, n_kchunks, QS, QN, n_qchunks, n_tiles_n, static_cast<int>(n_items), n_stages,
-      option("mask_debug") != 2, a_tm ? 1 : 0);
+#define MSDA_TC4_LAUNCH(ATM)                                                                                                            \
+  do {                                                                                                                                  \
+    if (int rc = ensure_func_attr(mask_fwd_tc4_kernel<OT, kTransB, ATM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) return rc; \
+    mask_fwd_tc4_kernel<OT, kTransB, ATM><<<grid, kTc4Threads, 1024 + n_stages * stage + out_bytes, st>>>(                                 \
+        map_plane, map_rows, map_out, Q, n_kchunks, QS, QN, n_qchunks, n_tiles_n, static_cast<int>(n_items), n_stages,                  \
+        option("mask_debug") != 2);                                                                                                     \
+  } while (0)
+  if (a_tm) MSDA_TC4_LAUNCH(true);
+  else MSDA_TC4_LAUNCH(false);
+#undef MSDA_TC4_LAUNCH
   return after_launch("mask_fwd_tc4_kernel");
 }
 

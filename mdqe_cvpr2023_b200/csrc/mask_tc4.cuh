@@ -61,17 +61,18 @@ __device__ __forceinline__ uint32_t tf32_lo(uint32_t v) { return __float_as_uint
 // (QN <= 128), stages 0-1 use [128, 256), stages 2-3 [384, 512); hi at +0, lo at +32
 __device__ __forceinline__ uint32_t mask_tc4_a_col(int s) { return (s < 2 ? 128u : 256u) + 64u * static_cast<uint32_t>(s); }
 
-template <typename OT, bool kTransB>
+template <typename OT, bool kTransB, bool a_tm>
 __global__ void __launch_bounds__(kTc4Threads, 1)
 mask_fwd_tc4_kernel(const __grid_constant__ CUtensorMap map_plane, const __grid_constant__ CUtensorMap map_rows,
                     const __grid_constant__ CUtensorMap map_out, int Q, int n_kchunks, int QS, int QN, int n_qchunks,
-                    int n_tiles_n, int n_items, int n_stages, int keep_raw, int a_tm) {
+                    int n_tiles_n, int n_items, int n_stages, int keep_raw) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space (LDS / STS, not generic LD / ST)
   constexpr uint32_t a_bytes = kTcTileN * 128u;                          // plane tile: 4 boxes {32 n, 32 k}
   const uint32_t b_rows = kTransB ? static_cast<uint32_t>((QN + 31) / 32 * 32) : static_cast<uint32_t>(QN);
   const uint32_t b_bytes = (b_rows * 128u + 1023u) & ~1023u;
-  // a_tm: the plane operand goes through tensor memory (hi / lo written there by the staging warps), its lo twin in shared memory
+  // a_tm (compile time: as a run-time flag the extra branch per MMA slowed the single issuing thread -- grad_proto 26 -> 36 us):
+  // the plane operand goes through tensor memory (hi / lo written there by the staging warps), its lo twin in shared memory
   // disappears and the row operand moves up: [P raw][A hi][A lo] instead of [P hi][P lo][A hi][A lo]
   const uint32_t b_off = a_tm ? a_bytes : 2 * a_bytes;
   const uint32_t stage_bytes = b_off + 2 * b_bytes;
@@ -164,7 +165,7 @@ mask_fwd_tc4_kernel(const __grid_constant__ CUtensorMap map_plane, const __grid_
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t b_desc = kTransB ? umma_desc(b_sel[term] + ks * 1024u, 4096u, 512u, 1u)
                                               : umma_desc(b_sel[term] + ks * 32u, 16u, 1024u, 2u);
-              if (a_tm) {
+              if constexpr (a_tm) {
                 umma_tf32_ta(tmem_base + a * 256u, a_col + (term == 2 ? 32u : 0u) + ks * 8u, b_desc, idesc, acc);
               } else {
                 const uint64_t a_desc = umma_desc(a_sel[term] + ks * 1024u, 4096u, 512u, 1u);
@@ -204,7 +205,7 @@ mask_fwd_tc4_kernel(const __grid_constant__ CUtensorMap map_plane, const __grid_
         };
 #pragma unroll
         // keep_raw: the MMA truncates fp32 to TF32 itself, so the tile as loaded is the "hi" operand (mask_tc_bwd.cuh)
-        if (a_tm) {
+        if constexpr (a_tm) {
           // plane boxes {32 n, 32 k}: row k = 128 bytes holding 32 n, 32-byte chunk index XOR (k & 3); this thread owns column
           // n = 32 * quarter + lane of the tile (= TMEM lane) and 16 of the chunk's 32 k
           const int quarter = warp & 3, khalf = (warp - (2 + kTc2EpiWarps)) >> 2;
@@ -223,9 +224,9 @@ mask_fwd_tc4_kernel(const __grid_constant__ CUtensorMap map_plane, const __grid_
           for (uint32_t k = t; k < a_vecs; k += kTc4SplitWarps * 32) { uint4 v = a_hi[k], lo; split(v, lo); if (!keep_raw) a_hi[k] = v; a_lo[k] = lo; }
         }
         for (uint32_t k = t; k < b_vecs; k += kTc4SplitWarps * 32) { uint4 v = b_hi[k], lo; split(v, lo); if (!keep_raw) b_hi[k] = v; b_lo[k] = lo; }
-        if (a_tm) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if constexpr (a_tm) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (a_tm) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if constexpr (a_tm) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_ready(s));
       }

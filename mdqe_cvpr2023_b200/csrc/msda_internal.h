@@ -42,7 +42,7 @@ struct Options {
   std::atomic<int> consumer_ctas{0};  // > 0: CTAs of the matcher-cost / IoU kernels (tuning; 0 = auto)
   std::atomic<int> pdl{1};            // 1 = launch the sampling kernels with programmatic stream serialization (see msda_launch.cuh)
   std::atomic<int> pair_map{0};       // order in which a CTA of the fast2 sampling kernels walks its pairs: 0 = auto, 1 = linear (chunk / M queries x all heads), 2 = head-run (one head x chunk queries; PairMap in msda_fast2.cuh)
-  std::atomic<int> mask_a_tmem{0};    // 3xTF32 mask kernels (mask_tc4.cuh): plane operand through tensor memory: 0 = auto (forward), 1 = never, 2 = always (A/B)
+  std::atomic<int> mask_a_tmem{0};    // 3xTF32 mask kernels (mask_tc4.cuh): plane operand through tensor memory: 0 = on, 1 = off (A/B)
   std::atomic<int> gemm_stream_k{1};  // Linear-layer GEMMs: 1 = (tile, chunk) units dealt out as one contiguous range per CTA where that pays (launch_gemm3x), 2 = always, 0 = whole tiles round-robin (A/B; gemm3x.cuh)
   std::atomic<int> bwd_merge{1};      // 1 = merge grad_value reductions of a (pair, level) that hit the same row (P = 2 or 4); 0 = off (A/B)
 };

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B of the plane operand through tensor memory in the 3xTF32 mask kernels (option mask_a_tmem: 1 = never, 0 = auto, 2 = always):
-forward, grad_proto alone, full backward at the BASELINE mask shapes.  CUDA events, L2 flushed, median."""
+forward, grad_proto alone, full backward at the BASELINE mask shapes.  CUDA-graph replays (10 calls per graph)."""
 import os
 import sys
 
@@ -10,20 +10,28 @@ import torch  # noqa: E402
 
 from mdqe_cvpr2023_b200 import _lib, ops  # noqa: E402
 
-flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-
-
-def timed(fn, iters=25):
-    fn(); torch.cuda.synchronize()
-    ts = []
-    for _ in range(iters):
-        flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record()
-        torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b) * 1e3)
-    ts.sort()
-    return ts[len(ts) // 2]
+def timed(fn, reps=20):
+    """10 calls per CUDA graph, replayed: GPU time per call without host dispatch (inputs larger than L2 at every shape but the smallest)"""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(10):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e3 / (10 * reps)
 
 
 for Q, T, plane, K in ((196, 4, (96, 160), 32), (196, 4, (160, 288), 32), (300, 8, (96, 160), 32), (196, 3, (96, 160), 24)):
