@@ -378,6 +378,9 @@ int msda_debug_read(long long* host80);
  * gpu_launches claim is read from here). */
 int64_t msda_launch_count(void);
 void msda_launch_count_reset(void);
+/* The Linear-layer GEMMs combine tiles that are split between CTAs through per-tile flags with BOUNDED waits (csrc/gemm3x.cuh): a wait
+ * that expires is counted here instead of hanging the GPU.  Synchronises the current device; 0 on a healthy run, -1 without a device. */
+int64_t msda_gemm_flag_timeouts(void);
 
 #ifdef __cplusplus
 }

@@ -92,6 +92,7 @@ PROTOTYPES = {
     "msda_debug_read": (_c_int, [ctypes.POINTER(ctypes.c_longlong)]),
     "msda_launch_count": (_c_i64, []),
     "msda_launch_count_reset": (None, []),
+    "msda_gemm_flag_timeouts": (_c_i64, []),
 }
 
 _lib = None

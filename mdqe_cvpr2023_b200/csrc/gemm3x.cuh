@@ -48,6 +48,10 @@ constexpr int kG3FlagSpins = 1 << 22;                                  // x 64 n
 
 enum : int { kG3ModeStore = 0, kG3ModeReduce = 1, kG3ModeStreamK = 2 };
 
+// how often a stream-K stretch gave up waiting for its tile's flag (its reduce-add then lands on whatever the output holds: a wrong
+// tile, never a hang).  Must stay 0; msda_gemm_flag_timeouts() reads it, tests/test_linear_gpu.py asserts it after the stress runs.
+__device__ unsigned int g_g3_flag_timeouts = 0;
+
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -383,7 +387,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         if (is_issuer) {
           if (sg.out == 3 && g == 0) {                                      // the tile's last chunks (another CTA's first work) must be in place
             const volatile int* f = flags + sg.tile;
-            for (int spins = 0; *f < 2 && spins < kG3FlagSpins; ++spins) __nanosleep(64);
+            int spins = 0;
+            for (; *f < 2 && spins < kG3FlagSpins; ++spins) __nanosleep(64);
+            if (spins >= kG3FlagSpins) atomicAdd(&g_g3_flag_timeouts, 1u);
             __threadfence();
             asm volatile("fence.proxy.async;" ::: "memory");
           }

@@ -452,6 +452,12 @@ static int launch_gemm3x(cudaStream_t st, const char* who, const void* A, const 
 
 // aligned16(): msda_launch.cuh
 
+int64_t gemm_flag_timeouts() {
+  unsigned int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_g3_flag_timeouts, sizeof(v)) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return static_cast<int64_t>(v);
+}
+
 int linear_forward_dispatch(cudaStream_t st, const void* x, const void* w, const void* bias, const unsigned char* row_mask,
                             int64_t rows, int in_f, int out_f, void* y) {
   if (rows >= (int64_t(1) << 31) - kG3Tile) return fail(MSDA_ERR_UNSUPPORTED, "tc_linear_forward: rows=%lld too large", (long long)rows);

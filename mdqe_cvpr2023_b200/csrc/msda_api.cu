@@ -224,6 +224,7 @@ int msda_debug_read(long long* host80) { return mask_debug_copy(host80); }
 
 int64_t msda_launch_count(void) { return g_launches.load(); }
 void msda_launch_count_reset(void) { g_launches.store(0); }
+int64_t msda_gemm_flag_timeouts(void) { return gemm_flag_timeouts(); }
 
 static int grouped_supported(const char* who, int dtype, const Problem& pb, bool fast) {
   if (pb.G == 1 && pb.scale == 1.f) return 0;            // the plain operator: every kernel family implements it

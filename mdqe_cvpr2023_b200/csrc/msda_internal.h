@@ -79,6 +79,7 @@ int match_cost_tc_dispatch(cudaStream_t stream, const float* coeff, const float*
 
 int linear_forward_dispatch(cudaStream_t stream, const void* x, const void* w, const void* bias, const unsigned char* row_mask,
                             int64_t rows, int in_f, int out_f, void* y);
+int64_t gemm_flag_timeouts();
 int linear_forward_packed_dispatch(cudaStream_t stream, const void* x, const void* w, const void* bias, const unsigned char* row_mask, int N,
                                    int S, int in_f, int heads, const int64_t* shapes, const int64_t* level_start, int L, void* packed);
 int linear_backward_dispatch(cudaStream_t stream, const void* gy, const void* x, const void* w, int64_t rows, int in_f, int out_f,

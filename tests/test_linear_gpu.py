@@ -111,6 +111,8 @@ def test_repeated_launches_leave_the_tile_flags_clean():
     torch.cuda.synchronize()
     assert nerr(y, want) < 2e-5
     assert nerr(gx, want @ w.double()) < 2e-5
+    from mdqe_cvpr2023_b200 import _lib
+    assert _lib.load().msda_gemm_flag_timeouts() == 0, "a stream-K stretch gave up waiting for its tile's flag"
 
 
 def test_tc_linear_rejects_unsupported():
